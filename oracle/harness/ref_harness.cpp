@@ -1,0 +1,245 @@
+// Oracle tooling only (never linked into the product). Drives the UNMODIFIED reference library
+// (oracle/_ref/libariadne_ref.a, built by oracle/Makefile from /root/reference/src) through its public API:
+//   HybridReachabilityAnalyser::upper_reach_evolve   (reference: src/reachability_analyser.cpp:309-377)
+//   HybridReachabilityAnalyser::outer_chain_reach    (reference: src/reachability_analyser.cpp:380-493)
+//   EvolverInterface::reach_evolve                   (reference: include/evolver_base.h:77-78)
+// and writes golden vectors (hex floats, bit-exact) or timings.
+//
+// Usage:  ref_harness <config> <mode> [key=value ...]
+//   config: watertank | bouncingball | vanderpol | springs | boost | spiral
+//   mode:   info      print grid / lock time / evolver tuning constants
+//           cells     per-enclosure reach/final bounding boxes for the first lap's frontier (parity goldens)
+//           reach     full analyser call; dumps reach (and evolve) cell boxes per location
+//           time      full analyser call, wall clock + cells evolved (CPU baseline)
+//   keys:   acc=<int> T=<float> events=<int> ncells=<int> out=<file> verb=<int> laps=<int>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <map>
+#include <chrono>
+#include <sstream>
+#include <fstream>
+
+#include "ariadne.h"
+#include "taylor_calculus.h"
+#include "hybrid_evolver-image.h"
+#include "logging.h"
+#include <boost/thread.hpp>
+#include "watertank-hysteresis.h"
+#include "springs.h"
+#include "boost-converter.h"
+
+using namespace Ariadne;
+
+typedef LocalisedEnclosureType HEncl;
+typedef ListSet<LocalisedEnclosureType> HEnclList;
+
+struct Config {
+    std::string name;
+    HybridIOAutomaton sys;
+    HybridBoxes domain;
+    HybridBoundedConstraintSet initial;
+    int acc;
+    double T;
+    int events;
+    bool chain;
+};
+
+// van der Pol oscillator, mu=1: x'=y, y'=mu(1-x^2)y-x  (system of examples/vanderpol.cc:36-54)
+static HybridIOAutomaton make_vanderpol() {
+    HybridIOAutomaton a("vanderpol");
+    DiscreteLocation loc("loc");
+    RealParameter mu("mu",Interval(1.0,1.0));
+    RealVariable x("x"), y("y");
+    a.add_internal_var(x); a.add_internal_var(y);
+    a.new_mode(loc);
+    RealExpression dx = y;
+    RealExpression dy = mu * (1.0 - Ariadne::sqr(x))*y - x;
+    a.set_dynamics(loc,x,dx);
+    a.set_dynamics(loc,y,dy);
+    return a;
+}
+
+// bouncing ball: x'=vx, vx'=-g; forced x<=0 -> vx:=-a vx  (system of examples/bouncingball.cc:33-64)
+static HybridIOAutomaton make_bouncingball() {
+    RealParameter a("a",0.5), g("g",9.81);
+    HybridIOAutomaton ball("ball");
+    DiscreteLocation freefall("freefall");
+    DiscreteEvent bounce("bounce");
+    RealVariable x("x"), vx("vx");
+    ball.add_internal_var(x); ball.add_internal_var(vx);
+    ball.new_mode(freefall);
+    RealExpression dx = vx;
+    RealExpression dvx = -g;
+    ball.set_dynamics(freefall,x,dx);
+    ball.set_dynamics(freefall,vx,dvx);
+    RealExpression guard = -x;
+    std::map<RealVariable,RealExpression> reset;
+    reset[x] = x;
+    reset[vx] = -a * vx;
+    ball.new_forced_transition(bounce,freefall,freefall,reset,guard);
+    return ball;
+}
+
+static std::map<std::string,std::string> parse_kv(int argc, char** argv, int first) {
+    std::map<std::string,std::string> kv;
+    for(int i=first;i<argc;++i) { std::string s(argv[i]); size_t p=s.find('='); if(p!=std::string::npos) kv[s.substr(0,p)]=s.substr(p+1); }
+    return kv;
+}
+static double getd(std::map<std::string,std::string>& kv, const char* k, double d) { return kv.count(k)?atof(kv[k].c_str()):d; }
+static int geti(std::map<std::string,std::string>& kv, const char* k, int d) { return kv.count(k)?atoi(kv[k].c_str()):d; }
+
+static Box box_from(std::map<std::string,std::string>& kv, const char* key, const Box& dflt) {
+    if(!kv.count(key)) return dflt;
+    std::vector<double> v; std::stringstream ss(kv[key]); std::string tok;
+    while(std::getline(ss,tok,',')) v.push_back(atof(tok.c_str()));
+    Box b(v.size()/2); for(uint i=0;i<v.size()/2;++i) b[i]=Interval(v[2*i],v[2*i+1]); return b;
+}
+
+static Config make_config(const std::string& name, std::map<std::string,std::string>& kv) {
+    Config c; c.name=name; c.events=geti(kv,"events",5); c.chain=false;
+    if(name=="vanderpol") {
+        c.sys=make_vanderpol();
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,-3.0,3.0,-3.0,3.0)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("loc")]=box_from(kv,"init",Box(2,-2.2,2.2,-2.8,2.8));
+        c.acc=geti(kv,"acc",6); c.T=getd(kv,"T",0.0);
+    } else if(name=="bouncingball") {
+        c.sys=make_bouncingball();
+        // state order is alphabetical: (vx,x)
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,-10.1,10.1,-0.1,2.1)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("freefall")]=box_from(kv,"init",Box(2,0.0,0.001,1.999,2.0));
+        c.acc=geti(kv,"acc",6); c.T=getd(kv,"T",0.0); c.chain=true;
+    } else if(name=="watertank") {
+        c.sys=getWatertankHysteresis();
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,0.0,1.0,4.5,9.0)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("flow,idle,rising")]=Box(2,1.0,1.0,6.0,7.5);
+        c.initial[DiscreteLocation("flow,idle,falling")]=Box(2,0.0,0.0,6.0,7.5);
+        c.acc=geti(kv,"acc",6); c.T=getd(kv,"T",0.0);
+    } else if(name=="springs") {
+        c.sys=getSpringsSystem();
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(5,0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("free")]=box_from(kv,"init",Box(5,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,3.0,3.0));
+        c.acc=geti(kv,"acc",3); c.T=getd(kv,"T",0.0);
+    } else if(name=="boost") {
+        c.sys=getBoostConverter();
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(3,0.0,0.001,0.0,3.0,0.0,6.0)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("incr,below_duty")]=box_from(kv,"init",Box(3,0.0,0.0,1.0,1.0,1.0,1.0));
+        c.acc=geti(kv,"acc",4); c.T=getd(kv,"T",0.0); c.chain=true;
+    } else {
+        fprintf(stderr,"unknown config %s\n",name.c_str()); exit(2);
+    }
+    if(kv.count("chain")) c.chain=geti(kv,"chain",0)!=0;
+    return c;
+}
+
+static void dump_box(FILE* f, const Box& b) { for(uint i=0;i<b.size();++i) fprintf(f," %a %a",b[i].lower(),b[i].upper()); }
+
+static void dump_set(FILE* f, const char* tag, const HybridDenotableSet& s) {
+    for(HybridDenotableSet::locations_const_iterator li=s.locations_begin(); li!=s.locations_end(); ++li) {
+        fprintf(f,"%s loc %s count %lu height %u\n",tag,li->first.name().c_str(),(unsigned long)li->second.size(),li->second.root_cell_height());
+        for(DenotableSetType::const_iterator ci=li->second.begin(); ci!=li->second.end(); ++ci) {
+            fprintf(f,"c"); dump_box(f,*ci); fprintf(f,"\n");
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    if(argc<3) { fprintf(stderr,"usage: ref_harness <config> <mode> [key=value...]\n"); return 2; }
+    std::map<std::string,std::string> kv=parse_kv(argc,argv,3);
+    Config c=make_config(argv[1],kv);
+    std::string mode(argv[2]);
+    FILE* out=stdout; if(kv.count("out")) out=fopen(kv["out"].c_str(),"w");
+    int verb=geti(kv,"verb",0);
+
+    HybridReachabilityAnalyser analyser(c.sys,c.domain,c.acc);
+    analyser.verbosity=verb;
+    if(kv.count("lock")) analyser.settings().lock_to_grid_time=getd(kv,"lock",0.0);
+    double lock=analyser.settings().lock_to_grid_time;
+    double T = c.T>0 ? c.T : getd(kv,"laps",1.0)*lock;
+
+    HybridFloatVector hmad=getHybridMidpointAbsoluteDerivatives(c.sys,c.domain);
+    HybridGrid grid=getHybridGrid(hmad,c.domain,false);
+    ImageSetHybridEvolver evolver(c.sys);
+    evolver.tune_settings(c.domain,grid,c.acc);
+
+    fprintf(out,"config %s acc %d T %a lock %a events %d chain %d\n",c.name.c_str(),c.acc,T,lock,c.events,(int)c.chain);
+    for(HybridGrid::locations_const_iterator gi=grid.locations_begin(); gi!=grid.locations_end(); ++gi) {
+        const Grid& g=gi->second;
+        fprintf(out,"grid loc %s n %u origin",gi->first.name().c_str(),g.dimension());
+        for(uint i=0;i<g.dimension();++i) fprintf(out," %a",g.origin()[i]);
+        fprintf(out," lengths"); for(uint i=0;i<g.dimension();++i) fprintf(out," %a",g.lengths()[i]);
+        fprintf(out," hmad"); for(uint i=0;i<g.dimension();++i) fprintf(out," %a",hmad.find(gi->first)->second[i]);
+        fprintf(out," maxstep %a",evolver.settings().maximum_step_size().find(gi->first)->second);
+        fprintf(out," refw"); for(uint i=0;i<g.dimension();++i) fprintf(out," %a",evolver.settings().reference_enclosure_widths().find(gi->first)->second[i]);
+        fprintf(out,"\n");
+    }
+    if(mode=="info") return 0;
+
+    if(mode=="cells") {
+        // First-lap frontier: enumerate the discretised initial set as the analyser does, then evolve each
+        // enclosure for one lock_to_grid_time through reach_evolve and dump the bounding boxes that the
+        // discretiser consumes (include/hybrid_set.h:976-996).
+        ReachabilityRestriction restriction(c.domain,grid,c.acc);
+        HybridDenotableSet initial=restriction.outer_intersection_with(c.initial);
+        int mince=geti(kv,"mince",0);
+        if(mince) { for(HybridDenotableSet::locations_iterator li=initial.locations_begin(); li!=initial.locations_end(); ++li) li->second.mince(c.acc); }
+        std::list<HEncl> encl=to_enclosures(initial);
+        int ncells=geti(kv,"ncells",1<<30); int stride=geti(kv,"stride",1);
+        bool ignore_act=geti(kv,"ignore_activations",c.chain?1:0)!=0;
+        HybridTime ht(T,c.chain?1:c.events);
+        fprintf(out,"frontier %lu ignore_activations %d\n",(unsigned long)encl.size(),(int)ignore_act);
+        int k=0, done=0;
+        // to_enclosures (src/reachability_analyser.cpp:1244-1253) walks the set in this same order; the cell box itself
+        // is printed (the enclosure's bounding box is the range of scalings(box), which is a few ulps wider).
+        HybridDenotableSet::const_iterator cell_it=initial.begin();
+        for(std::list<HEncl>::const_iterator it=encl.begin(); it!=encl.end() && done<ncells; ++it,++k,++cell_it) {
+            if(k%stride) continue;
+            ++done;
+            fprintf(out,"cell %d loc %s box",k,it->first.name().c_str()); dump_box(out,cell_it->second); fprintf(out,"\n");
+            try {
+                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(*it,ht,ignore_act,DIRECTION_FORWARD,UPPER_SEMANTICS);
+                for(HEnclList::const_iterator r=re.first.begin(); r!=re.first.end(); ++r) {
+                    fprintf(out,"r %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
+                for(HEnclList::const_iterator r=re.second.begin(); r!=re.second.end(); ++r) {
+                    fprintf(out,"f %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
+            } catch(std::exception& e) {
+                fprintf(out,"x %s\n",e.what());
+            }
+        }
+        return 0;
+    }
+
+    std::ofstream logf;
+    std::string logpath=kv.count("log")?kv["log"]:std::string("/tmp/ref_harness.log");
+    if(mode=="time") { analyser.verbosity=4; redirect_log(logpath.c_str()); }
+    std::chrono::steady_clock::time_point t0=std::chrono::steady_clock::now();
+    HybridDenotableSet reach, evolve;
+    std::string err;
+    try {
+        if(c.chain) { reach=analyser.outer_chain_reach(c.initial); }
+        else { make_lpair(reach,evolve)=analyser.upper_reach_evolve(c.initial,HybridTime(T,c.events)); }
+    } catch(std::exception& e) { err=e.what(); }
+    std::chrono::steady_clock::time_point t1=std::chrono::steady_clock::now();
+    double secs=std::chrono::duration<double>(t1-t0).count();
+    if(mode=="time") {
+        std::clog.flush();
+        // cells evolved = sum of "Initial size" (src/reachability_analyser.cpp:190) + serial first lap "Starting from" (:347)
+        std::ifstream lf(logpath.c_str()); std::string line; unsigned long evolved=0;
+        while(std::getline(lf,line)) {
+            size_t p=line.find("Initial size = "); if(p!=std::string::npos) evolved+=strtoul(line.c_str()+p+15,0,10);
+            p=line.find("Starting from "); if(p!=std::string::npos) evolved+=strtoul(line.c_str()+p+14,0,10);
+        }
+        fprintf(out,"time seconds %.6f cells_evolved %lu reach_cells %lu threads %u err '%s'\n",secs,evolved,(unsigned long)reach.size(),boost::thread::hardware_concurrency(),err.c_str());
+        return 0;
+    }
+    fprintf(out,"seconds %.3f err '%s'\n",secs,err.c_str());
+    dump_set(out,"reach",reach);
+    dump_set(out,"evolve",evolve);
+    return 0;
+}

@@ -1,0 +1,222 @@
+// ab200_evolve.cuh -- evolution of one frontier cell for one lock-to-grid lap.
+//
+// Restates ImageSetHybridEvolver::_evolution / _evolution_step (reference: src/hybrid_evolver-image.cpp:258-547,
+// 752-766, 1000-1127, 1159-1178, 1253-1284) for UPPER_SEMANTICS with the shipped settings
+// (src/hybrid_evolver-image.cpp:1347-1359: reconditioning on, subdivisions off, premature termination on,
+// error-rate enforcement off, boxing off) and TaylorCalculus defaults (src/taylor_calculus.cpp:136-146).
+// Output per cell: the bounding boxes of every reach set and of every final set, which is all the discretiser
+// consumes (include/hybrid_set.h:976-996).
+#pragma once
+#include "ab200_calc.cuh"
+#include "ab200_series.cuh"
+#include "ab200_events.cuh"
+
+namespace ab200 {
+
+struct EvolveParams {
+    double T;                  // continuous time of the lap (HybridTime::continuous_time)
+    int32_t max_events;        // HybridTime::discrete_time
+    int32_t ignore_activations;
+    int32_t max_boxes;         // capacity of each per-cell output list
+    int32_t temporal_order;    // 6
+    double ratio;              // maximum_enclosure_widths_ratio = 5.0
+    double spacial_sweep;      // 1e-12
+    int32_t spacial_order;     // 6
+    int32_t max_working_sets;  // per-cell queue capacity (device limit, not a reference setting)
+};
+
+struct CellOutput {
+    // boxes are [lo0,hi0,lo1,hi1,...] records of 2*n doubles; loc index stored separately
+    double* reach;  int32_t* reach_loc;  int32_t n_reach;
+    double* final_; int32_t* final_loc;  int32_t n_final;
+    int32_t stride;            // doubles per box record (2*AB_MAXN)
+    int32_t steps;             // number of _evolution_step calls (work counter)
+};
+
+// The reference hands enclosures to the discretiser through HybridSetConstIterator::dereference
+// (include/hybrid_set.h:883-887), which replaces every TaylorSet by TaylorSet(its box()), i.e. scalings(bbox); the
+// discretiser then takes bounding_box() of THAT (include/hybrid_set.h:991-992). The emitted box is therefore
+// range(scaling(range(set))) per coordinate, a few ulps wider than range(set).
+AB_HD void out_box(Ctx& c, double* dst, int32_t* dloc, int32_t& count, int cap, int stride, int loc, const Ivl* b, int n) {
+    if (count >= cap) { fail(c, ST_OUTPUT); return; }
+    double* p = dst + (size_t)count * stride;
+    for (int i = 0; i < n; ++i) {
+        const int m = c.A.top;
+        TM s = tm_scaling(c, n, i, b[i]);
+        Ivl r = tm_range(c, s);
+        c.A.top = m;
+        p[2 * i] = r.l; p[2 * i + 1] = r.u;
+    }
+    dloc[count] = loc;
+    ++count;
+}
+
+// A working set (EvolutionData, include/hybrid_evolver-image.h): location, event count, set model (n models in p
+// variables) and time model, stored packed in the arena starting at `base`.
+struct WorkingSet {
+    int loc;
+    int n_events;
+    int p;
+    TM set[AB_MAXN];
+    TM time;
+};
+
+// _is_enclosure_too_large  src/hybrid_evolver-image.cpp:1253-1284
+AB_HD bool enclosure_too_large(Ctx& c, const LocDesc& L, const Ivl* range, const double* init_w, double ratio) {
+    const int n = L.n;
+    bool use_init = false;
+    for (int i = 0; i < n; ++i) if (init_w[i] >= L.ref_width[i]) { use_init = true; break; }
+    for (int i = 0; i < n; ++i) {
+        double w = ivl_width(range[i]);
+        if (use_init) { if (div_m(c.rnd, w, init_w[i]) >= ratio) return true; }
+        else { if (w >= mul_m(c.rnd, L.ref_width[i], ratio)) return true; }
+    }
+    return false;
+}
+
+// Evolve one enclosure (a box in location loc0) for time P.T. Mirrors _evolution with a FIFO of working sets.
+AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O) {
+    Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
+    const int n0 = S.loc[loc0].n;
+
+    // ---- _evolution_add_initialSet: set_model(box)=scalings(box) with spacial accuracy; time_model(0.0)
+    WorkingSet ws;
+    ws.loc = loc0; ws.n_events = 0; ws.p = n0;
+    for (int i = 0; i < n0; ++i) { ws.set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); ws.set[i].acc = spacial; }
+    ws.time = tm_const(c, n0, 0.0, spacial);
+    double init_w[AB_MAXN];
+    for (int i = 0; i < n0; ++i) init_w[i] = ivl_width(tm_range(c, ws.set[i]));   // _indexed_set_models_widths
+
+    // FIFO of pending working sets beyond the current one lives above; `qbase` is where the current set starts.
+    WsQueue Q; wsq_init(Q);
+    int guard_iter = 0;
+    bool have = true;
+    while (have && c.status == ST_OK) {
+        if (++guard_iter > 100000) { fail(c, ST_OUTPUT); break; }
+        const int base = ws.set[0].off;               // current working set occupies [base, top)
+        const LocDesc& L = S.loc[ws.loc];
+        const int n = L.n, p = ws.p;
+        Ivl range[AB_MAXN];
+        for (int i = 0; i < n; ++i) range[i] = tm_range(c, ws.set[i]);
+        Ivl trange = tm_range(c, ws.time);
+        bool too_large = enclosure_too_large(c, L, range, init_w, P.ratio);
+        bool done = false;
+        if (trange.l >= P.T || ws.n_events >= P.max_events) {
+            out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
+            done = true;
+        } else if (too_large) {
+            // premature termination on enclosure size; UPPER semantics keeps the set as final (:308-313)
+            out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
+            done = true;
+        }
+        if (!done) {
+            // ---- _evolution_step ------------------------------------------------------------------------------
+            O.steps++;
+            const int mstep = c.A.top;
+#ifdef AB_DEBUG_DUMP
+            printf("STEP %d\n", O.steps - 1);
+            for (int i = 0; i < n; ++i) AB_DUMP(c, "set", i, ws.set[i]);
+            AB_DUMP(c, "time", -1, ws.time);
+#endif
+            double remaining = sub_m(c.rnd, P.T, trange.l);
+            double hprop = dmin(remaining, L.max_step);
+            Ivl bb[AB_MAXN], dom[AB_MAXN + 1];
+            double h = flow_bounds(c, S.ops, L.dyn, n, range, hprop, bb);
+            if (c.status != ST_OK) break;
+            TM flow[AB_MAXN], fset[AB_MAXN];
+            flow_model(c, S.ops, L.dyn, n, range, h, bb, P.temporal_order, flow, dom);
+            flow_apply(c, flow, n, dom, ws.set, p, h, fset);
+#ifdef AB_DEBUG_DUMP
+            printf("h %a bb", h); for (int i = 0; i < n; ++i) printf(" %a %a", bb[i].l, bb[i].u); printf("\n");
+            for (int i = 0; i < n; ++i) AB_DUMP(c, "flow", i, flow[i]);
+#endif
+            vec_slide(c, fset, n, mstep);             // drop the flow model, keep the flow set model
+            for (int i = 0; i < n; ++i) AB_DUMP(c, "fset", i, fset[i]);
+            if (c.status != ST_OK) break;
+
+            // blocking info (src/hybrid_evolver-image.cpp:1085-1127)
+            TM tstep = tm_const(c, p, 1.0, spacial);  // time_model(1.0,Box(p))
+            TM zero_t = tm_const(c, p, 0.0, spacial); // time_model(0.0,Box(p)) (no storage: empty expansion)
+            BlockingInfo B;
+            compute_blocking_info(c, S, L, fset, n, p, tstep, spacial, B);
+            if (c.status != ST_OK) break;
+            if (enclosure_to_be_discarded(c, S, L, ws.set, n, p)) {
+                // the working set is dropped (:532-533)
+                c.A.top = mstep;
+                done = true;
+            } else {
+                if (!P.ignore_activations && has_permissive_or_nontransverse(L, B)) { fail(c, ST_UNSUPPORTED); break; }
+                // reachable set (:1159-1178)
+                {
+                    const int m = c.A.top;
+                    TM reach[AB_MAXN];
+                    reachability_step(c, fset, n, p, zero_t, B.time, spacial, reach);
+                    Ivl rb[AB_MAXN];
+                    for (int i = 0; i < n; ++i) AB_DUMP(c, "reach", i, reach[i]);
+                    for (int i = 0; i < n; ++i) rb[i] = tm_range(c, reach[i]);
+                    out_box(c, O.reach, O.reach_loc, O.n_reach, P.max_boxes, O.stride, ws.loc, rb, n);
+                    c.A.top = m;
+                }
+                // _computeEvolutionForEvents (:1000-1082)
+                TM ev[AB_MAXN];
+                integration_step(c, fset, n, p, B.time, spacial, ev);
+                for (int i = 0; i < n; ++i) AB_DUMP(c, "evolved", i, ev[i]);
+                // final_time_model=time_model+blocking_time_model*time_step
+                TM ft;
+                {
+                    const int m = c.A.top;
+                    TM sc = tm_copy(c, B.time); tm_scal(c, sc, h);
+                    ft = tm_add(c, ws.time, sc);
+                    tm_slide(c, ft, m);
+                }
+                int np = p;
+                {   // reconditioning (enable_reconditioning)
+                    double thr[AB_MAXN];
+                    for (int i = 0; i < n; ++i) thr[i] = div_m(c.rnd, L.ref_width[i], 4.0);
+                    np = uniform_error_recondition(c, ev, n, p, thr);
+                    if (np > p) ft.as = np;                                   // embed(final_time_model,diff)
+                    int disc[AB_MAXARGS + 1];
+                    int nd = kuhn_recondition(c, ev, n, np, disc);
+                    if (nd > 0) {
+                        ft = tm_recondition(c, ft, disc, nd, n, n);
+                        np = 2 * n;
+                    }
+                }
+                // successors
+                bool pushed_next = false;
+                WorkingSet next;
+                if (B.finishing) {
+                    next.loc = ws.loc; next.n_events = ws.n_events; next.p = np;
+                    for (int i = 0; i < n; ++i) next.set[i] = ev[i];
+                    next.time = ft;
+                    pushed_next = true;
+                } else if (!P.ignore_activations && blocking_has_transition(L, B)) {
+                    fail(c, ST_UNSUPPORTED); break;      // jumps inside the evolver (upper_reach with transitions)
+                }
+                if (pushed_next) {
+                    // compact: slide the successor down over the consumed working set
+                    TM pack[AB_MAXN + 1];
+                    // models may be in any arena order after reconditioning: copy to the top in canonical order first
+                    const int mt = c.A.top;
+                    for (int i = 0; i < n; ++i) pack[i] = tm_copy(c, next.set[i]);
+                    pack[n] = tm_copy(c, next.time);
+                    (void)mt;
+                    vec_slide(c, pack, n + 1, base);
+                    for (int i = 0; i < n; ++i) next.set[i] = pack[i];
+                    next.time = pack[n];
+                    ws = next;
+                } else {
+                    c.A.top = base;
+                    done = true;
+                }
+            }
+        } else {
+            c.A.top = base;
+        }
+        if (done) {
+            have = wsq_pop(c, Q, ws);
+        }
+    }
+}
+
+} // namespace ab200

@@ -1,0 +1,97 @@
+// ab200_system.cpp -- parser for the text system description (see ab200_system.h).
+#include "ab200_system.h"
+#include <sstream>
+#include <cstdlib>
+#include <cstring>
+
+namespace ab200 {
+
+static int opcode(const std::string& t) {
+    static const char* names[] = {"CNST","VAR","ADD","SUB","MUL","DIV","NEG","POS","REC","SQR","SQRT","EXP","LOG","SIN","COS","TAN","ABS","MAX","MIN"};
+    for (int i = 0; i < 19; ++i) if (t == names[i]) return i;
+    return -1;
+}
+
+static bool parse_tape(std::istringstream& in, SystemDesc& d, Func& f, std::string& err) {
+    f.begin = d.n_ops;
+    std::string t;
+    while (in >> t) {
+        if (t == ";") { f.end = d.n_ops; return true; }
+        if (d.n_ops >= AB_MAXOPS) { err = "too many tape ops"; return false; }
+        TapeOp o; o.op = 0; o.arg = 0; o.lo = 0; o.hi = 0;
+        if (t[0] == 'V' && t.size() > 1 && isdigit(t[1])) { o.op = OP_VAR; o.arg = atoi(t.c_str() + 1); }
+        else if (t[0] == 'C' && t.size() > 1 && t != "COS") {
+            size_t comma = t.find(',');
+            if (comma == std::string::npos) { err = "bad constant " + t; return false; }
+            o.op = OP_CNST; o.lo = strtod(t.substr(1, comma - 1).c_str(), 0); o.hi = strtod(t.substr(comma + 1).c_str(), 0);
+        } else {
+            int oc = opcode(t);
+            if (oc < 2) { err = "bad tape token " + t; return false; }
+            o.op = oc;
+        }
+        d.ops[d.n_ops++] = o;
+    }
+    err = "unterminated tape";
+    return false;
+}
+
+std::string parse_system(const std::string& text, HostSystem& out) {
+    // strip comments
+    std::string clean; clean.reserve(text.size());
+    bool incomment = false;
+    for (size_t i = 0; i < text.size(); ++i) {
+        char ch = text[i];
+        if (ch == '#') incomment = true;
+        if (ch == '\n') incomment = false;
+        if (!incomment) clean.push_back(ch);
+    }
+    std::istringstream in(clean);
+    memset(&out.desc, 0, sizeof(SystemDesc));
+    out.loc_names.clear(); out.event_names.clear();
+    std::string tok, err;
+    int cur_loc = -1, cur_ev = -1;
+    while (in >> tok) {
+        if (tok == "system") { in >> out.name; }
+        else if (tok == "locations") {
+            int L; in >> L;
+            if (L < 1 || L > AB_MAXLOC) return "unsupported number of locations";
+            out.desc.n_locs = L; out.loc_names.resize(L); out.event_names.resize(L);
+        } else if (tok == "location") {
+            std::string name, k1, k2; int idx, n, E;
+            in >> idx >> name >> k1 >> n >> k2 >> E;
+            if (idx < 0 || idx >= out.desc.n_locs || k1 != "n" || k2 != "events") return "bad location header";
+            if (n < 1 || n > AB_MAXN) return "unsupported dimension";
+            if (E < 0 || E > AB_MAXEV) return "too many events in a location";
+            cur_loc = idx; cur_ev = -1;
+            out.loc_names[idx] = name; out.event_names[idx].resize(E);
+            out.desc.loc[idx].n = n; out.desc.loc[idx].n_events = E;
+        } else if (tok == "dyn") {
+            int i; in >> i;
+            if (cur_loc < 0 || i < 0 || i >= out.desc.loc[cur_loc].n) return "bad dyn index";
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].dyn[i], err)) return err;
+        } else if (tok == "event") {
+            int k, target, id; std::string name, kk, kind, kt, ki;
+            in >> k >> name >> kk >> kind >> kt >> target >> ki >> id;
+            if (cur_loc < 0 || k < 0 || k >= out.desc.loc[cur_loc].n_events || kk != "kind" || kt != "target" || ki != "id") return "bad event header";
+            EventDesc& e = out.desc.loc[cur_loc].ev[k];
+            e.kind = kind == "invariant" ? EV_INVARIANT : kind == "urgent" ? EV_URGENT : kind == "permissive" ? EV_PERMISSIVE : -1;
+            if (e.kind < 0) return "bad event kind " + kind;
+            e.target = target; e.id = id;
+            out.event_names[cur_loc][k] = name;
+            cur_ev = k;
+        } else if (tok == "guard") {
+            if (cur_loc < 0 || cur_ev < 0) return "guard outside event";
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].guard, err)) return err;
+        } else if (tok == "reset") {
+            int i; in >> i;
+            if (cur_loc < 0 || cur_ev < 0 || i < 0 || i >= AB_MAXN) return "reset outside event";
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].reset[i], err)) return err;
+        } else {
+            return "unknown token '" + tok + "'";
+        }
+    }
+    if (out.desc.n_locs == 0) return "no locations";
+    return "";
+}
+
+} // namespace ab200

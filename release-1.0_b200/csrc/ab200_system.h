@@ -1,0 +1,34 @@
+// ab200_system.h -- host-side construction of the flat op-tape system description (SystemDesc).
+//
+// The reference rebuilds ScalarFunction/VectorFunction objects from expression trees on every call
+// (src/hybrid_io_automaton.cpp:938-1026) and interprets them with dynamic_cast dispatch
+// (src/expression.cpp:766-779). Here every DiscreteLocation's dynamics, guards, invariants and resets are
+// compiled ONCE into postfix tapes that the kernels read from constant memory.
+//
+// Text form accepted by parse_system() (one token stream, '#' starts a comment):
+//   system <name>
+//   locations <L>
+//   location <idx> <name> n <n> events <E>
+//     dyn <i> <tape...> ;
+//     event <k> <name> kind <invariant|urgent|permissive> target <loc idx> id <int>
+//       guard <tape...> ;
+//       reset <i> <tape...> ;            (transitions only)
+//   tape tokens: V<j> | C<lo>,<hi> (hex or decimal doubles) | ADD SUB MUL DIV NEG POS REC SQR SQRT EXP LOG SIN COS TAN ABS MAX MIN
+#pragma once
+#include <string>
+#include <vector>
+#include "ab200_calc.cuh"
+
+namespace ab200 {
+
+struct HostSystem {
+    std::string name;
+    std::vector<std::string> loc_names;
+    std::vector<std::vector<std::string> > event_names;
+    SystemDesc desc;
+};
+
+// Returns an empty string on success, else an error message.
+std::string parse_system(const std::string& text, HostSystem& out);
+
+} // namespace ab200

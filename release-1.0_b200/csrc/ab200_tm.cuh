@@ -1,0 +1,452 @@
+// ab200_tm.cuh -- TaylorModel primitives on a per-cell scratch arena.
+//
+// A TaylorModel is a sparse polynomial on [-1,1]^as with a uniform error bound (reference:
+// include/taylor_model.h:170-190, include/expansion.h, include/multi_index.h). Here a model is a handle
+// {offset,count,as,error,accuracy} into a per-cell arena of 64-bit words; terms are [key words | coefficient]
+// records kept in the reference's graded order (include/multi_index.h:346-358).
+//
+// MultiIndex packing: AB_KW 64-bit words per key. Word 0 = degree byte (bits 56..63) followed by the exponents of
+// variables 0..6, most significant first; word 1 = exponents of variables 7..14. Adding two keys is a plain
+// integer add per word; the reference order is "degree ascending, then the key whose first differing exponent is
+// LARGER comes first", i.e. ascending (w0 ^ 0x00FF..FF) then descending w1.
+//
+// Arena layout in HBM: one arena per cell, word i of cell c lives at base[(i * AB_STRIDE)] with base already offset
+// by the lane; with AB_STRIDE=32 the 32 cells of a warp interleave word-by-word so that lanes walking their models
+// in lock step touch one 256-byte line per access.
+//
+// Every accumulator keeps the reference's association order (error sums round upward term by term), so results
+// are bit-identical to the CPU library; see DESIGN.md "Numerical contract".
+#pragma once
+#include "ab200_fp.cuh"
+
+#ifndef AB_KW
+#define AB_KW 1
+#endif
+#ifndef AB_STRIDE
+#if defined(__CUDA_ARCH__)
+#define AB_STRIDE 32
+#else
+#define AB_STRIDE 1
+#endif
+#endif
+
+namespace ab200 {
+
+#define AB_TW (AB_KW + 1)   // words per term
+#define AB_MAXARGS (AB_KW == 1 ? 7 : 15)
+
+struct Key {
+    uint64_t w[AB_KW];
+};
+
+AB_HD Key key_zero() { Key k; for (int i = 0; i < AB_KW; ++i) k.w[i] = 0; return k; }
+AB_HD int key_deg(const Key& k) { return (int)(k.w[0] >> 56); }
+AB_HD int key_get(const Key& k, int j) {
+    if (j < 7) return (int)((k.w[0] >> (8 * (6 - j))) & 0xFF);
+#if AB_KW > 1
+    return (int)((k.w[1] >> (8 * (14 - j))) & 0xFF);
+#else
+    return 0;
+#endif
+}
+// add d (possibly negative) to exponent j, maintaining the degree byte
+AB_HD void key_inc(Key& k, int j, int d) {
+    if (j < 7) k.w[0] += (uint64_t)((int64_t)d) * ((1ull << (8 * (6 - j))) + (1ull << 56));
+#if AB_KW > 1
+    else { k.w[1] += (uint64_t)((int64_t)d) << (8 * (14 - j)); k.w[0] += (uint64_t)((int64_t)d) << 56; }
+#endif
+}
+AB_HD Key key_unit(int j) { Key k = key_zero(); key_inc(k, j, 1); return k; }
+AB_HD Key key_add(const Key& a, const Key& b) { Key r; for (int i = 0; i < AB_KW; ++i) r.w[i] = a.w[i] + b.w[i]; return r; }
+AB_HD bool key_eq(const Key& a, const Key& b) {
+    bool e = a.w[0] == b.w[0];
+#if AB_KW > 1
+    e = e && a.w[1] == b.w[1];
+#endif
+    return e;
+}
+AB_HD bool key_less(const Key& a, const Key& b) {   // include/multi_index.h:346-358
+    const uint64_t M = 0x00FFFFFFFFFFFFFFull;
+    uint64_t sa = a.w[0] ^ M, sb = b.w[0] ^ M;
+    if (sa != sb) return sa < sb;
+#if AB_KW > 1
+    return a.w[1] > b.w[1];
+#else
+    return false;
+#endif
+}
+// remove variable k (shift later variables down); degree byte reduced by the removed exponent
+AB_HD Key key_remove(const Key& a, int k, int as) {
+    Key r = key_zero();
+    int jj = 0;
+    for (int j = 0; j < as; ++j) { if (j == k) continue; int e = key_get(a, j); if (e) key_inc(r, jj, e); ++jj; }
+    return r;
+}
+
+struct Acc {          // TaylorModel::Accuracy (include/taylor_model.h:178-190)
+    double sweep;
+    int maxdeg;
+};
+AB_HD Acc acc_default() { Acc a; a.sweep = 1e-18; a.maxdeg = 16; return a; }   // src/taylor_model.cpp:46-47
+AB_HD bool acc_discard(const Acc& a, const Key& k, double v) { return dabs(v) < a.sweep || key_deg(k) > a.maxdeg; }
+
+struct Arena {
+    uint64_t* base;   // already offset by lane; word i at base[i*AB_STRIDE]
+    int top;
+    int limit;
+    int peak;
+};
+
+struct Ctx {
+    Arena A;
+    int rnd;       // ambient rounding mode left behind by the last routine (mirrors MXCSR in the reference)
+    int status;    // sticky first error
+};
+
+AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[(size_t)i * AB_STRIDE]; }
+AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
+
+struct TM {
+    int off;      // first word in the arena
+    int n;        // number of terms
+    int as;       // argument size
+    double e;     // uniform error
+    Acc acc;
+};
+
+AB_HD Key tm_key(Ctx& c, const TM& x, int i) { Key k; for (int j = 0; j < AB_KW; ++j) k.w[j] = aw(c, x.off + i * AB_TW + j); return k; }
+AB_HD double tm_val(Ctx& c, const TM& x, int i) { return u2d(aw(c, x.off + i * AB_TW + AB_KW)); }
+AB_HD void tm_set_val(Ctx& c, const TM& x, int i, double v) { aw(c, x.off + i * AB_TW + AB_KW) = d2u(v); }
+AB_HD void tm_set_key(Ctx& c, const TM& x, int i, const Key& k) { for (int j = 0; j < AB_KW; ++j) aw(c, x.off + i * AB_TW + j) = k.w[j]; }
+AB_HD int tm_end(const TM& x) { return x.off + x.n * AB_TW; }
+
+// Begin a model at the arena top; append() grows it. Only the most recently begun model may be appended to.
+AB_HD TM tm_begin(Ctx& c, int as, Acc acc) { TM r; r.off = c.A.top; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc; return r; }
+AB_HD void tm_append(Ctx& c, TM& r, const Key& k, double v) {
+    int o = r.off + r.n * AB_TW;
+    if (o + AB_TW > c.A.limit) { fail(c, ST_ARENA); return; }
+    for (int j = 0; j < AB_KW; ++j) aw(c, o + j) = k.w[j];
+    aw(c, o + AB_KW) = d2u(v);
+    r.n++;
+    c.A.top = o + AB_TW;
+    if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+}
+// Move model x (anywhere at or above dst) down to word offset dst and set the arena top just past it.
+AB_HD void tm_slide(Ctx& c, TM& x, int dst) {
+    if (x.off != dst) {
+        int nw = x.n * AB_TW;
+        for (int i = 0; i < nw; ++i) aw(c, dst + i) = aw(c, x.off + i);
+        x.off = dst;
+    }
+    c.A.top = dst + x.n * AB_TW;
+}
+AB_HD TM tm_copy(Ctx& c, const TM& x) {
+    TM r = tm_begin(c, x.as, x.acc);
+    int nw = x.n * AB_TW;
+    if (r.off + nw > c.A.limit) { fail(c, ST_ARENA); return r; }
+    for (int i = 0; i < nw; ++i) aw(c, r.off + i) = aw(c, x.off + i);
+    r.n = x.n; r.e = x.e;
+    c.A.top = r.off + nw;
+    if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+    return r;
+}
+AB_HD TM tm_zero(Ctx& c, int as, Acc acc) { return tm_begin(c, as, acc); }
+AB_HD int tm_degree(Ctx& c, const TM& x) { return x.n == 0 ? 0 : key_deg(tm_key(c, x, x.n - 1)); }   // taylor_model.h:361
+
+// ---- in-place scalar operations -------------------------------------------------------------------------------
+
+// _scal(TaylorModel&, Float) src/taylor_model.cpp:241-273
+AB_HDN void tm_scal(Ctx& c, TM& r, double s) {
+    if (s == 0) { r.n = 0; r.e = 0; return; }     // (arena words stay allocated; harmless)
+    if (s == 1) return;
+    if (s == 2 || s == 0.5) {
+        for (int i = 0; i < r.n; ++i) tm_set_val(c, r, i, mul_m(c.rnd, tm_val(c, r, i), s));
+        r.e = mul_m(c.rnd, r.e, dabs(s));
+        return;
+    }
+    double te = 0, ms = -s;
+    for (int i = 0; i < r.n; ++i) {
+        double rv = tm_val(c, r, i);
+        double u = mul_ru(rv, s), ml = mul_ru(rv, ms);
+        te = add_ru(te, add_ru(u, ml));
+    }
+    r.e = mul_ru(r.e, dabs(s));
+    r.e = add_ru(r.e, te / 2);
+    for (int i = 0; i < r.n; ++i) tm_set_val(c, r, i, mul_rn(tm_val(c, r, i), s));
+    c.rnd = RN;
+}
+// _scal(TaylorModel&, Interval) src/taylor_model.cpp:276-314
+AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) {
+    double te = 0, cu = s.u, mcl = -s.l;
+    for (int i = 0; i < r.n; ++i) {
+        double rv = tm_val(c, r, i), u, ml;
+        if (rv >= 0) { u = mul_ru(rv, cu); ml = mul_ru(rv, mcl); }
+        else { double mrv = -rv; u = mul_ru(mrv, mcl); ml = mul_ru(mrv, cu); }
+        te = add_ru(te, add_ru(u, ml));
+    }
+    r.e = mul_ru(r.e, ivl_mag(s));
+    r.e = add_ru(r.e, te / 2);
+    double m = add_rn(s.u, s.l) / 2;
+    for (int i = 0; i < r.n; ++i) tm_set_val(c, r, i, mul_rn(tm_val(c, r, i), m));
+    c.rnd = RN;
+}
+// Insert a constant term in front of a model that is the LAST thing on the arena.
+AB_HD void tm_prepend_top(Ctx& c, TM& r, double v) {
+    int nw = r.n * AB_TW;
+    if (r.off + nw + AB_TW > c.A.limit) { fail(c, ST_ARENA); return; }
+    for (int i = nw - 1; i >= 0; --i) aw(c, r.off + AB_TW + i) = aw(c, r.off + i);
+    Key z = key_zero();
+    for (int j = 0; j < AB_KW; ++j) aw(c, r.off + j) = z.w[j];
+    aw(c, r.off + AB_KW) = d2u(v);
+    r.n++;
+    c.A.top = r.off + r.n * AB_TW;
+    if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+}
+// _acc(TaylorModel&, Float) src/taylor_model.cpp:370-392. r must be the top model on the arena.
+AB_HDN void tm_acc(Ctx& c, TM& r, double s) {
+    if (s == 0) return;
+    if (r.n == 0 || key_deg(tm_key(c, r, 0)) > 0) { tm_prepend_top(c, r, s); return; }
+    double rv = tm_val(c, r, 0);
+    double rvu = add_ru(rv, s), mrvl = sub_ru(-rv, s);
+    r.e = add_ru(r.e, add_ru(rvu, mrvl) / 2);
+    tm_set_val(c, r, 0, add_rn(rv, s));
+    c.rnd = RN;
+}
+// _acc(TaylorModel&, Interval) src/taylor_model.cpp:397-422. r must be the top model on the arena.
+AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) {
+    if (s.l == -s.u) { r.e = add_ru(r.e, s.u); c.rnd = RN; return; }
+    if (r.n == 0 || key_deg(tm_key(c, r, 0)) > 0) tm_prepend_top(c, r, 0.0);
+    double rv = tm_val(c, r, 0);
+    double rvu = add_ru(rv, s.u), mrvl = sub_ru(-rv, s.l);
+    r.e = add_ru(r.e, add_ru(rvu, mrvl) / 2);
+    double m = add_rn(s.u, s.l) / 2;
+    tm_set_val(c, r, 0, add_rn(rv, m));
+    c.rnd = RN;
+}
+
+// ---- binary operations: results are begun at the arena top ------------------------------------------------------
+
+// _add2 (src/taylor_model.cpp:487-530): merge by key; rounding error of coincident terms accumulated upward in
+// key order. Result accuracy is supplied by the caller (the reference's operator+ uses a fresh default).
+AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) {
+    TM r = tm_begin(c, x.as, acc);
+    double te = 0.0;
+    int i = 0, j = 0;
+    bool coincident = false;
+    while (i < x.n && j < y.n) {
+        Key xa = tm_key(c, x, i), ya = tm_key(c, y, j);
+        if (key_less(xa, ya)) { tm_append(c, r, xa, tm_val(c, x, i)); ++i; }
+        else if (key_less(ya, xa)) { tm_append(c, r, ya, tm_val(c, y, j)); ++j; }
+        else {
+            double xv = tm_val(c, x, i), yv = tm_val(c, y, j);
+            double u = add_ru(xv, yv), ml = sub_ru(-xv, yv);
+            te = add_ru(te, add_ru(u, ml));
+            double s = add_rn(xv, yv);
+            if (s != 0) tm_append(c, r, xa, s);
+            ++i; ++j; coincident = true;
+        }
+    }
+    while (i < x.n) { tm_append(c, r, tm_key(c, x, i), tm_val(c, x, i)); ++i; }
+    while (j < y.n) { tm_append(c, r, tm_key(c, y, j), tm_val(c, y, j)); ++j; }
+    (void)coincident;
+    r.e = add_ru(add_ru(x.e, y.e), te / 2);
+    c.rnd = RN;
+    return r;
+}
+// neg (src/taylor_model.cpp:1530-1537): fresh default accuracy
+AB_HDN TM tm_neg(Ctx& c, const TM& x) {
+    TM r = tm_begin(c, x.as, acc_default());
+    for (int i = 0; i < x.n; ++i) tm_append(c, r, tm_key(c, x, i), -tm_val(c, x, i));
+    r.e = x.e;
+    return r;
+}
+// operator+(x,y) src/taylor_model.cpp:1253-1256
+AB_HD TM tm_add(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x, y, acc_default()); }
+// operator-(x,y) src/taylor_model.cpp:1258-1262: r=neg(y); _acc(r,x) == _add2(s,r,x) with r keeping neg's accuracy
+AB_HDN TM tm_sub(Ctx& c, const TM& x, const TM& y) {
+    int m = c.A.top;
+    TM ny = tm_neg(c, y);
+    TM s = tm_add2(c, ny, x, acc_default());
+    tm_slide(c, s, m);
+    return s;
+}
+// x+=y (src/taylor_model.cpp:1150-1156,538-541): result keeps x's accuracy. Returns a new model at the top.
+AB_HD TM tm_plus_assign(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x, y, x.acc); }
+
+// _mul4 (src/taylor_model.cpp:763-824) with accuracy `acc` (operator* passes the RIGHT operand's, :1265-1268).
+// Result at the arena top.
+AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
+    int m = c.A.top;
+    TM r = tm_begin(c, x.as, acc);          // empty accumulator at m
+    for (int i = 0; i < x.n; ++i) {
+        Key xa = tm_key(c, x, i);
+        double xv = tm_val(c, x, i), axv = dabs(xv);
+        double tte = 0.0;
+        c.A.top = r.off + r.n * AB_TW;
+        TM t = tm_begin(c, x.as, acc);
+        for (int j = 0; j < y.n; ++j) {
+            Key ta = key_add(xa, tm_key(c, y, j));
+            double yv = tm_val(c, y, j);
+            double tv = mul_rn(xv, yv);
+            if (acc_discard(acc, ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
+            else tm_append(c, t, ta, tv);
+        }
+        // t.error()=tte+(tte/2): evaluated in the mode left by the inner loop (upward; ambient if y is empty)
+        int md = (y.n > 0) ? RU : c.rnd;
+        t.e = add_m(md, tte, div_m(md, tte, 2.0));
+        TM s = tm_add2(c, r, t, acc);
+        tm_slide(c, s, m);
+        r = s;
+    }
+    double xs = 0, ys = 0;
+    for (int i = 0; i < x.n; ++i) xs = add_ru(xs, dabs(tm_val(c, x, i)));
+    for (int j = 0; j < y.n; ++j) ys = add_ru(ys, dabs(tm_val(c, y, j)));
+    r.e = add_ru(r.e, add_ru(add_ru(mul_ru(xs, y.e), mul_ru(ys, x.e)), mul_ru(x.e, y.e)));
+    c.rnd = RN;
+    c.A.top = r.off + r.n * AB_TW;
+    return r;
+}
+AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc); }
+
+// sweep(m) src/taylor_model.cpp:972-989 -- in place; leaves the ambient mode UPWARD (sic).
+AB_HDN void tm_sweep(Ctx& c, TM& x, double m) {
+    int k = 0;
+    for (int i = 0; i < x.n; ++i) {
+        double v = tm_val(c, x, i);
+        if (dabs(v) >= m) { if (k != i) { tm_set_key(c, x, k, tm_key(c, x, i)); tm_set_val(c, x, k, v); } ++k; }
+        else x.e = add_ru(x.e, dabs(v));
+    }
+    x.n = k;
+    c.rnd = RU;
+}
+// clean(accuracy) src/taylor_model.cpp:895-913 -- in place
+AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) {
+    int k = 0;
+    for (int i = 0; i < x.n; ++i) {
+        Key a = tm_key(c, x, i); double v = tm_val(c, x, i);
+        if (acc_discard(acc, a, v)) x.e = add_ru(x.e, dabs(v));
+        else { if (k != i) { tm_set_key(c, x, k, a); tm_set_val(c, x, k, v); } ++k; }
+    }
+    x.n = k;
+    c.rnd = RN;
+}
+// range() = _range1 src/taylor_model.cpp:1566-1579
+AB_HDN Ivl tm_range(Ctx& c, const TM& x) {
+    double t = x.e, v = 0.0;
+    for (int i = 0; i < x.n; ++i) {
+        if (key_deg(tm_key(c, x, i)) == 0) v = tm_val(c, x, i);
+        else t = add_ru(t, dabs(tm_val(c, x, i)));
+    }
+    c.rnd = RN;
+    return ivl(add_rd(-t, v), add_ru(t, v));
+}
+// norm() src/taylor_model.cpp:2592-2600
+AB_HDN double tm_norm(Ctx& c, const TM& x) {
+    double r = x.e;
+    for (int i = 0; i < x.n; ++i) r = add_ru(r, dabs(tm_val(c, x, i)));
+    c.rnd = RN;
+    return r;
+}
+// TaylorModel::operator=(Float) src/taylor_model.cpp:183-191 -> constant model begun at the top
+AB_HD TM tm_const(Ctx& c, int as, double v, Acc acc) {
+    TM r = tm_begin(c, as, acc);
+    if (v != 0) tm_append(c, r, key_zero(), v);
+    return r;
+}
+// TaylorModel::variable(as,j) include/taylor_model.h:232 -- default accuracy
+AB_HD TM tm_variable(Ctx& c, int as, int j) {
+    TM r = tm_begin(c, as, acc_default());
+    tm_append(c, r, key_unit(j), 1.0);
+    return r;
+}
+// rescale(ocd,ncd) src/taylor_model.cpp:2092-2112; x must be the top model
+AB_HDN void tm_rescale(Ctx& c, TM& x, Ivl ocd, Ivl ncd) {
+    double a = ocd.l, b = ocd.u, cc = ncd.l, d = ncd.u;
+    int st = ST_OK;
+    Ivl tmp = ivl_div(1.0, sub_ivl(b, a), &st);
+    if (st != ST_OK) fail(c, st);
+    Ivl alpha = ivl_mul(sub_ivl(d, cc), tmp);
+    Ivl beta = ivl_mul(ivl_sub(mul_ivl(cc, b), mul_ivl(a, d)), tmp);
+    tm_scal(c, x, alpha);
+    tm_acc(c, x, beta);
+}
+// TaylorModel::scaling(as,j,d) include/taylor_model.h:234 -- default accuracy, at the top
+AB_HD TM tm_scaling(Ctx& c, int as, int j, Ivl d) {
+    TM r = tm_variable(c, as, j);
+    tm_rescale(c, r, ivl(-1, 1), d);
+    return r;
+}
+// unscale(tv,ivl) src/taylor_model.cpp:2554-2569 -- copy at the top
+AB_HDN TM tm_unscale(Ctx& c, const TM& tv, Ivl d) {
+    TM r = tm_copy(c, tv);
+    Ivl cc = ivl_add(ivl(d.l / 2), ivl(d.u / 2));
+    int st = ST_OK;
+    Ivl s = ivl_div(2.0, ivl_sub(ivl(d.u), ivl(d.l)), &st);
+    if (st != ST_OK) fail(c, st);
+    tm_acc(c, r, ivl_neg(cc));
+    tm_scal(c, r, s);
+    return r;
+}
+// rescale(tv,ivl) (free function "scale") src/taylor_model.cpp:2570-2585
+AB_HDN TM tm_scale_to(Ctx& c, const TM& tv, Ivl d) {
+    TM r = tm_copy(c, tv);
+    Ivl cc = add_ivl(d.l / 2, d.u / 2);
+    Ivl s = sub_ivl(d.u / 2, d.l / 2);
+    tm_scal(c, r, s);
+    tm_acc(c, r, cc);
+    return r;
+}
+// embed(x,as) src/taylor_model.cpp:2630-2633: append `extra` trailing variables. Keys are unchanged because the
+// packed layout is positional (variable j always sits in the same byte).
+AB_HD TM tm_embed(Ctx& c, const TM& x, int extra) { TM r = tm_copy(c, x); r.as = x.as + extra; return r; }
+
+// antidifferentiate(k) src/taylor_model.cpp:2251-2284 -- in place
+AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) {
+    double tre = 0;
+    for (int i = 0; i < x.n; ++i) {
+        Key a = tm_key(c, x, i);
+        double xv = tm_val(c, x, i), mxv = -xv, u, ml;
+        double cc = (double)(key_get(a, k) + 1);
+        if (xv >= 0) { u = div_ru(xv, cc); ml = div_ru(mxv, cc); }
+        else { u = div_ru(mxv, cc); ml = div_ru(xv, cc); }
+        tre = add_ru(tre, add_ru(u, ml));
+        key_inc(a, k, 1);
+        tm_set_key(c, x, i, a);
+        tm_set_val(c, x, i, div_rn(xv, cc));
+    }
+    x.e = add_ru(x.e, tre / 2);
+    c.rnd = RN;
+}
+// intersection(x,y) src/taylor_model.cpp:2883-2954. Returns false (and leaves the ambient mode upward, as the
+// reference's throw does) when the models are disjoint; the caller then keeps y, as unchecked_flow does.
+AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
+    TM r = tm_begin(c, x.as, x.acc);
+    double tme = 0.0;
+    int i = 0, j = 0;
+    while (i < x.n || j < y.n) {
+        Key a; double xv, yv;
+        if (i == x.n) { a = tm_key(c, y, j); yv = tm_val(c, y, j); xv = 0.0; ++j; }
+        else if (j == y.n) { a = tm_key(c, x, i); xv = tm_val(c, x, i); yv = 0.0; ++i; }
+        else {
+            Key xa = tm_key(c, x, i), ya = tm_key(c, y, j);
+            if (key_eq(xa, ya)) { a = xa; xv = tm_val(c, x, i); yv = tm_val(c, y, j); ++i; ++j; }
+            else if (key_less(xa, ya)) { a = xa; xv = tm_val(c, x, i); yv = 0.0; ++i; }
+            else { a = ya; yv = tm_val(c, y, j); xv = 0.0; ++j; }
+        }
+        double xu = add_ru(xv, x.e), yu = add_ru(yv, y.e), mxl = sub_ru(x.e, xv), myl = sub_ru(y.e, yv);
+        double u = dmin(xu, yu), ml = dmin(mxl, myl);
+        double s = add_ru(u, ml);
+        if (s < 0) { c.rnd = RU; c.A.top = r.off; return false; }
+        tme = dmax(tme, s);
+        xu = add_rn(xv, x.e); yu = add_rn(yv, y.e); mxl = sub_rn(x.e, xv); myl = sub_rn(y.e, yv);
+        u = dmin(xu, yu); ml = dmin(mxl, myl);
+        double rv = sub_rn(u, ml) / 2;
+        if (rv != 0.0) tm_append(c, r, a, rv);
+        c.rnd = RN;
+    }
+    r.e = tme / 2;
+    out = r;
+    return true;
+}
+
+} // namespace ab200

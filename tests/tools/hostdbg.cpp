@@ -1,0 +1,100 @@
+// tests/tools/hostdbg.cpp -- development aid only (never shipped, never imported by the product path).
+// Compiles the kernel headers for the HOST (AB_STRIDE=1, fenv rounding) so the per-cell algorithm can be
+// single-stepped in a GPU-less container, and compares its reach/final boxes with an oracle dump produced by
+// `oracle/_ref/ref_harness <config> cells ...`.
+//
+//   hostdbg <system.sys> <oracle cells dump> [maxcells] [verbose]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include <map>
+#include "../../release-1.0_b200/csrc/ab200_evolve.cuh"
+#include "../../release-1.0_b200/csrc/ab200_system.h"
+
+using namespace ab200;
+
+struct RefCell { int loc; std::vector<double> box; std::vector<std::vector<double> > reach, fin; std::vector<int> rloc, floc; std::string err; };
+
+int main(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: hostdbg <system.sys> <cells dump> [maxcells] [verbose]\n"); return 2; }
+    std::ifstream sf(argv[1]); std::stringstream ss; ss << sf.rdbuf();
+    static HostSystem hs;
+    std::string err = parse_system(ss.str(), hs);
+    if (!err.empty()) { fprintf(stderr, "parse error: %s\n", err.c_str()); return 2; }
+    int maxcells = argc > 3 ? atoi(argv[3]) : 1 << 30;
+    int verbose = argc > 4 ? atoi(argv[4]) : 0;
+    std::ifstream df(argv[2]);
+    std::string line;
+    double T = 0; int events = 5, ignore_act = 0, chain = 0;
+    std::map<std::string, int> locidx;
+    for (size_t i = 0; i < hs.loc_names.size(); ++i) locidx[hs.loc_names[i]] = (int)i;
+    std::vector<RefCell> cells;
+    while (std::getline(df, line)) {
+        std::istringstream in(line); std::string t; in >> t;
+        if (t == "config") { std::string k, name, v; in >> name; while (in >> k >> v) { if (k == "T") T = strtod(v.c_str(), 0); if (k == "events") events = atoi(v.c_str()); if (k == "chain") chain = atoi(v.c_str()); } }
+        else if (t == "grid") {
+            std::string k, name; in >> k >> name; int li = locidx[name]; LocDesc& L = hs.desc.loc[li];
+            int n = 0; in >> k >> n;
+            in >> k; for (int i = 0; i < n; ++i) { std::string v; in >> v; L.grid_origin[i] = strtod(v.c_str(), 0); }
+            in >> k; for (int i = 0; i < n; ++i) { std::string v; in >> v; L.grid_length[i] = strtod(v.c_str(), 0); }
+            in >> k; for (int i = 0; i < n; ++i) { std::string v; in >> v; }
+            in >> k; { std::string v; in >> v; L.max_step = strtod(v.c_str(), 0); }
+            in >> k; for (int i = 0; i < n; ++i) { std::string v; in >> v; L.ref_width[i] = strtod(v.c_str(), 0); }
+        }
+        else if (t == "frontier") { std::string k; int nf; in >> nf >> k >> ignore_act; }
+        else if (t == "cell") { RefCell c; int id; std::string k, name; in >> id >> k >> name >> k; c.loc = locidx[name]; std::string v; while (in >> v) c.box.push_back(strtod(v.c_str(), 0)); cells.push_back(c); }
+        else if (t == "r" || t == "f") { std::string name, v; in >> name; std::vector<double> b; while (in >> v) b.push_back(strtod(v.c_str(), 0)); if (t == "r") { cells.back().reach.push_back(b); cells.back().rloc.push_back(locidx[name]); } else { cells.back().fin.push_back(b); cells.back().floc.push_back(locidx[name]); } }
+        else if (t == "x") { cells.back().err = line; }
+    }
+    printf("T=%a events=%d ignore_activations=%d chain=%d cells=%zu\n", T, events, ignore_act, chain, cells.size());
+    const int ARENA = 1 << 20;
+    std::vector<uint64_t> arena(ARENA);
+    const int MAXB = 4096;
+    std::vector<double> reach(MAXB * 2 * AB_MAXN), fin(MAXB * 2 * AB_MAXN);
+    std::vector<int32_t> rloc(MAXB), floc(MAXB);
+    int bad = 0, done = 0; long total_steps = 0; int peak = 0;
+    for (size_t ci = 0; ci < cells.size() && (int)ci < maxcells; ++ci) {
+        RefCell& rc = cells[ci];
+        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = ARENA; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        EvolveParams P; P.T = T; P.max_events = chain ? 1 : events; P.ignore_activations = ignore_act; P.max_boxes = MAXB; P.temporal_order = 6;
+        P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
+        CellOutput O; O.reach = reach.data(); O.reach_loc = rloc.data(); O.n_reach = 0; O.final_ = fin.data(); O.final_loc = floc.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        evolve_cell(c, hs.desc, rc.loc, rc.box.data(), P, O);
+        total_steps += O.steps; if (c.A.peak > peak) peak = c.A.peak;
+        ++done;
+        int n = hs.desc.loc[rc.loc].n;
+        bool ok = (c.status == ST_OK) && rc.err.empty() && O.n_reach == (int)rc.reach.size() && O.n_final == (int)rc.fin.size();
+        int first_bad = -1;
+        if (ok) {
+            for (int k = 0; k < O.n_reach && ok; ++k) for (int j = 0; j < 2 * n; ++j) if (memcmp(&reach[k * O.stride + j], &rc.reach[k][j], 8) != 0) { ok = false; first_bad = k; break; }
+            for (int k = 0; k < O.n_final && ok; ++k) for (int j = 0; j < 2 * n; ++j) if (memcmp(&fin[k * O.stride + j], &rc.fin[k][j], 8) != 0) { ok = false; first_bad = 100000 + k; break; }
+        }
+        if (!ok && verbose >= 2) {
+            printf("cell %zu mismatching reach idx:", ci);
+            for (int k = 0; k < O.n_reach && k < (int)rc.reach.size(); ++k) { bool e = true; for (int j = 0; j < 2 * n; ++j) if (memcmp(&reach[k * O.stride + j], &rc.reach[k][j], 8) != 0) e = false; if (!e) printf(" %d", k); }
+            printf(" | final:");
+            for (int k = 0; k < O.n_final && k < (int)rc.fin.size(); ++k) { bool e = true; for (int j = 0; j < 2 * n; ++j) if (memcmp(&fin[k * O.stride + j], &rc.fin[k][j], 8) != 0) e = false; if (!e) printf(" %d", k); }
+            printf("\n");
+        }
+        if (!ok) {
+            ++bad;
+            if (bad <= 5 || verbose) {
+                printf("cell %zu MISMATCH status=%d reach %d vs %zu final %d vs %zu first_bad=%d referr='%s'\n", ci, c.status, O.n_reach, rc.reach.size(), O.n_final, rc.fin.size(), first_bad, rc.err.c_str());
+                int k = first_bad >= 100000 ? -1 : (first_bad >= 0 ? first_bad : 0);
+                if (k >= 0 && k < O.n_reach && k < (int)rc.reach.size()) {
+                    printf("  ours r[%d]:", k); for (int j = 0; j < 2 * n; ++j) printf(" %a", reach[k * O.stride + j]); printf("\n");
+                    printf("  ref  r[%d]:", k); for (int j = 0; j < 2 * n; ++j) printf(" %a", rc.reach[k][j]); printf("\n");
+                }
+                if (first_bad >= 100000) { int q = first_bad - 100000;
+                    printf("  ours f[%d]:", q); for (int j = 0; j < 2 * n; ++j) printf(" %a", fin[q * O.stride + j]); printf("\n");
+                    printf("  ref  f[%d]:", q); for (int j = 0; j < 2 * n; ++j) printf(" %a", rc.fin[q][j]); printf("\n"); }
+            }
+        } else if (verbose) printf("cell %zu ok: %d reach, %d final, %d steps\n", ci, O.n_reach, O.n_final, O.steps);
+    }
+    printf("cells compared %d, mismatching %d, steps %ld, arena peak words %d\n", done, bad, total_steps, peak);
+    return bad ? 1 : 0;
+}
