@@ -1,0 +1,148 @@
+/* ariadne_b200.h -- C ABI of libariadne_b200.so, the B200 implementation of Ariadne 1.0's grid-reachability lap.
+ *
+ * The reference has no FFI: its seams are C++ virtual interfaces. Each entry point below names
+ * the reference interface it replaces (paths relative to the reference tree). Conventions: every call returns
+ * AB200_OK or an AB200_E_* code; inputs are borrowed for the duration of the call; outputs are library-owned until
+ * the matching *_free; one host thread drives a context; all GPU work is stream-ordered. There is no CPU fallback:
+ * every compute entry point fails with AB200_E_CUDA when no sm_100 device is usable.
+ *
+ * Boxes are passed as [lo0,hi0,lo1,hi1,...] with AB200_BOX_STRIDE doubles per box regardless of the dimension.
+ */
+#ifndef ARIADNE_B200_H
+#define ARIADNE_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB200_MAX_DIM 5
+#define AB200_BOX_STRIDE (2 * AB200_MAX_DIM)
+
+/* Error codes and the reference exception each one stands for (include/exceptions.h, include/workers.h:129-139). */
+enum {
+    AB200_OK = 0,
+    AB200_E_SQRT = 1,          /* SqrtNumericException          src/numeric.cpp:251-253 */
+    AB200_E_DIVZERO = 2,       /* DivideByZeroException         src/numeric.cpp:744,829,858 */
+    AB200_E_DOMAIN = 3,        /* DomainException               src/taylor_model.cpp:1847 */
+    AB200_E_BOUNDER = 4,       /* ARIADNE_ASSERT in flow_bounds src/taylor_calculus.cpp:87,108,123-130 -> std::runtime_error */
+    AB200_E_ARENA = 5,         /* per-cell scratch exhausted: raise ab200_settings.arena_words */
+    AB200_E_OUTPUT = 6,        /* per-cell box list exhausted: raise ab200_settings.max_boxes */
+    AB200_E_UNSUPPORTED = 7,   /* operator or event path not implemented on the device yet */
+    AB200_E_IMPLICIT = 8,      /* ImplicitFunctionException     src/taylor_model.cpp:3562-3665 */
+    AB200_E_WORKING_SETS = 9,  /* WorkingSetTooLargeException   src/hybrid_evolver-image.cpp:280 */
+    AB200_E_CUDA = 100,        /* CUDA runtime failure or no usable GPU */
+    AB200_E_ARGUMENT = 101,    /* malformed argument */
+    AB200_E_KEYSPACE = 102,    /* a reached cell fell outside the packed-key window */
+    AB200_E_TIMEOUT = 103      /* TimeoutException              include/interruptible.h:56-63 */
+};
+
+typedef struct ab200_ctx ab200_ctx;
+typedef struct ab200_cellset ab200_cellset;   /* sorted, duplicate-free packed cell keys */
+typedef struct ab200_boxlist ab200_boxlist;   /* per-enclosure bounding boxes (parity / debugging) */
+typedef struct ab200_analyser ab200_analyser;
+
+/* ImageSetHybridEvolverSettings + TaylorCalculus orders (src/hybrid_evolver-image.cpp:1347-1359,
+ * src/taylor_calculus.cpp:136-146) plus device sizing. ab200_default_settings fills the reference defaults. */
+typedef struct ab200_settings {
+    int32_t temporal_order;             /* 6 */
+    int32_t spacial_order;              /* 6 */
+    double  sweep_threshold;            /* 1e-12 */
+    double  maximum_enclosure_widths_ratio;   /* 5.0 */
+    int32_t max_boxes;                  /* capacity of each per-cell reach / final list */
+    int32_t arena_words;                /* 64-bit words of scratch per cell */
+    int32_t hash_log2;                  /* log2 of the de-duplication table size */
+    int32_t batch_cells;                /* cells per launch */
+    double  ttl_seconds;                /* Interruptible::ttl; <=0 disables */
+} ab200_settings;
+
+typedef struct ab200_status {
+    int32_t code;             /* first failing cell's code (first error wins, include/workers.h:129-139) */
+    int64_t cell;             /* index of that cell in the batch, -1 if none */
+    int64_t steps;            /* total _evolution_step calls executed */
+    int64_t keys_emitted;     /* lattice cells written by the rasteriser before de-duplication */
+    int32_t arena_peak;       /* largest per-cell scratch use, words */
+    double  evolve_ms;        /* device time of the evolution kernel(s) */
+    double  raster_ms;        /* device time of rasterise + compact + sort */
+} ab200_status;
+
+void ab200_default_settings(ab200_settings* s);
+
+/* Lifetime. One context per GPU (device = CUDA ordinal). Replaces the evolver object created by
+ * HybridReachabilityAnalyser::_get_tuned_evolver (src/reachability_analyser.cpp:125-142). */
+int  ab200_ctx_create(ab200_ctx** out, int device);
+void ab200_ctx_destroy(ab200_ctx* ctx);
+const char* ab200_last_error(const ab200_ctx* ctx);
+
+/* System upload: flat op tapes of every location's dynamics, guards, invariants and resets, in the text form
+ * documented in release-1.0_b200/csrc/ab200_system.h. Replaces the per-call function reconstruction of
+ * HybridAutomatonInterface::dynamic_function/guard_function/invariant_function/reset_function
+ * (include/hybrid_automaton_interface.h:96-141, src/hybrid_io_automaton.cpp:938-1026). */
+int  ab200_set_system_text(ab200_ctx* ctx, const char* text);
+int  ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims /* [n_locations] or NULL */);
+int  ab200_location_index(const ab200_ctx* ctx, const char* name);
+
+int  ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s);
+
+/* ImageSetHybridEvolver::tune_settings (src/hybrid_evolver-image.cpp:99-113): per-location maximum step size and
+ * reference enclosure widths, and the grid + accuracy used by outer_approximation. */
+int  ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max_step, const double* ref_widths,
+                               const double* grid_origin, const double* grid_lengths);
+int  ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy);
+
+/* The hot call == UpperReachEvolveWorker::get_result() (include/workers.h:51-81,102-153): evolve every enclosure for
+ * (t_continuous, max_events), discretise reach and final sets at the context's accuracy. */
+int  ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes,
+                              double t_continuous, int32_t max_events, int ignore_activations, int direction,
+                              ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status);
+int  ab200_cellset_view(const ab200_cellset* cs, const uint64_t** keys, uint64_t* count);
+void ab200_cellset_free(ab200_cellset* cs);
+/* Decode a packed key into (location, lattice index per coordinate at resolution 2^-accuracy of the base grid). */
+int  ab200_key_decode(const ab200_ctx* ctx, uint64_t key, int32_t* loc, int64_t* idx);
+
+/* == EvolverInterface::reach_evolve (include/evolver_interface.h:114-124) for a batch, returning what the
+ * discretiser consumes: the bounding box of every reach and final enclosure (include/hybrid_set.h:976-996). */
+int  ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes,
+                              double t_continuous, int32_t max_events, int ignore_activations, int direction,
+                              ab200_boxlist** reach_out, ab200_boxlist** final_out, ab200_status* status);
+/* offsets has n_cells+1 entries; boxes/locs have offsets[n_cells] entries. */
+int  ab200_boxlist_view(const ab200_boxlist* bl, const uint64_t** offsets, const double** boxes, const int32_t** locs);
+void ab200_boxlist_free(ab200_boxlist* bl);
+
+/* == IntegratorInterface::flow_bounds (include/integrator_interface.h:45-50) with the TaylorCalculus constants
+ * (src/taylor_calculus.cpp:55-133,584-600). */
+int  ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
+                       double* h_out, double* bounds_out, int32_t* status_out);
+
+/* Host mirror of HybridReachabilityAnalyser (include/reachability_analyser.h:122-172): grid, lock-to-grid time and
+ * evolver tuning derived from the domain exactly as HybridReachabilityAnalyser(system,domain,accuracy) does
+ * (src/reachability_analyser.cpp:83-100,1028-1170; src/hybrid_set.cpp:485-515), laps driven through
+ * ab200_upper_reach_evolve, set algebra on sorted key arrays. domain: one box per location. */
+int  ab200_analyser_create(ab200_analyser** out, ab200_ctx* ctx, const double* domain_boxes, int32_t accuracy);
+void ab200_analyser_destroy(ab200_analyser* an);
+int  ab200_analyser_info(const ab200_analyser* an, double* lock_to_grid_time, double* grid_origin /* [L][MAX_DIM] */,
+                         double* grid_lengths, double* max_step /* [L] */);
+int  ab200_analyser_set_lock_time(ab200_analyser* an, double lock_to_grid_time);
+/* upper_reach_evolve (src/reachability_analyser.cpp:309-377). initial: n_init boxes with their locations.
+ * mince != 0 enumerates the initial set as uniform cells (BDDTreeSet::mince) instead of merged cells. */
+int  ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                       double t_continuous, int32_t max_events, int mince,
+                                       ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status);
+/* outer_chain_reach (src/reachability_analyser.cpp:380-493). */
+int  ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                      ab200_cellset** reach_out, ab200_status* status);
+/* Number of frontier enclosures consumed by the evolver in the last analyser call (the metric's unit of work). */
+int64_t ab200_analyser_cells_evolved(const ab200_analyser* an);
+/* Enumerate a cell set as the reference does (maximal dyadic cells, boxes by bisection, src/bdd_set.cpp:800-891).
+ * Pass boxes==NULL to query the count. */
+int  ab200_analyser_enumerate(const ab200_analyser* an, const ab200_cellset* cs, int mince, uint64_t* count,
+                              int32_t* locs, double* boxes);
+
+/* Device probes used by bench.py for the roofline denominators. */
+int  ab200_probe_fp64(ab200_ctx* ctx, double* gflops_rounded_ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -166,7 +166,11 @@ int main(int argc, char** argv) {
     HybridFloatVector hmad=getHybridMidpointAbsoluteDerivatives(c.sys,c.domain);
     HybridGrid grid=getHybridGrid(hmad,c.domain,false);
     ImageSetHybridEvolver evolver(c.sys);
-    evolver.tune_settings(c.domain,grid,c.acc);
+    // The analyser tunes its evolver on ReachabilityRestriction::bounding_box(), i.e. the domain widened by one cell
+    // while the domain has not been discretised (src/reachability_analyser.cpp:125-142,
+    // src/reachability_restriction.cpp:597-621); outer=0 tunes on the plain domain instead.
+    if(geti(kv,"outer",1)) { ReachabilityRestriction rr(c.domain,grid,c.acc); evolver.tune_settings(rr.bounding_box(),grid,c.acc); }
+    else evolver.tune_settings(c.domain,grid,c.acc);
 
     fprintf(out,"config %s acc %d T %a lock %a events %d chain %d\n",c.name.c_str(),c.acc,T,lock,c.events,(int)c.chain);
     for(HybridGrid::locations_const_iterator gi=grid.locations_begin(); gi!=grid.locations_end(); ++gi) {
@@ -194,6 +198,7 @@ int main(int argc, char** argv) {
         bool ignore_act=geti(kv,"ignore_activations",c.chain?1:0)!=0;
         HybridTime ht(T,c.chain?1:c.events);
         fprintf(out,"frontier %lu ignore_activations %d\n",(unsigned long)encl.size(),(int)ignore_act);
+        HybridDenotableSet ureach(grid), ufinal(grid);
         int k=0, done=0;
         // to_enclosures (src/reachability_analyser.cpp:1244-1253) walks the set in this same order; the cell box itself
         // is printed (the enclosure's bounding box is the range of scalings(box), which is a few ulps wider).
@@ -208,10 +213,17 @@ int main(int argc, char** argv) {
                     fprintf(out,"r %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
                 for(HEnclList::const_iterator r=re.second.begin(); r!=re.second.end(); ++r) {
                     fprintf(out,"f %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
+                if(geti(kv,"disc",0)) {
+                    // what UpperReachEvolveWorker adjoins for this enclosure (include/workers.h:144-148)
+                    dump_set(out,"dreach",outer_approximation(re.first,grid,c.acc));
+                    dump_set(out,"dfinal",outer_approximation(re.second,grid,c.acc));
+                    ureach.adjoin(outer_approximation(re.first,grid,c.acc)); ufinal.adjoin(outer_approximation(re.second,grid,c.acc));
+                }
             } catch(std::exception& e) {
                 fprintf(out,"x %s\n",e.what());
             }
         }
+        if(geti(kv,"disc",0)) { fprintf(out,"union\n"); dump_set(out,"ureach",ureach); dump_set(out,"ufinal",ufinal); }
         return 0;
     }
 

@@ -1,0 +1,340 @@
+"""ctypes binding of libariadne_b200.so (include/ariadne_b200.h) plus thin classes named after the reference's
+interfaces for the grid-reachability path:
+
+  HybridReachabilityAnalyser.upper_reach / upper_evolve / upper_reach_evolve / outer_chain_reach
+      (reference: include/reachability_analyser.h:122-172, src/reachability_analyser.cpp:278-493)
+  Evolver.reach_evolve        (reference: include/evolver_interface.h:114-124; batch form of include/workers.h:51-81)
+  Evolver.flow_bounds         (reference: include/integrator_interface.h:45-50)
+
+There is no CPU fallback: loading fails if the shared library has not been built, and every compute call fails with
+Ab200Error(AB200_E_CUDA) when no B200 is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_DIM = 5
+BOX_STRIDE = 2 * MAX_DIM
+
+E_NAMES = {
+    0: "OK", 1: "SqrtNumericException", 2: "DivideByZeroException", 3: "DomainException", 4: "BounderAssertion",
+    5: "ArenaExhausted", 6: "OutputExhausted", 7: "Unsupported", 8: "ImplicitFunctionException",
+    9: "WorkingSetTooLargeException", 100: "CudaError", 101: "ArgumentError", 102: "KeySpaceError", 103: "TimeoutException",
+}
+
+EXPORTS = [
+    "ab200_default_settings", "ab200_ctx_create", "ab200_ctx_destroy", "ab200_last_error", "ab200_set_system_text",
+    "ab200_system_info", "ab200_location_index", "ab200_set_settings", "ab200_set_location_tuning", "ab200_set_accuracy",
+    "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
+    "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
+    "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
+    "ab200_analyser_outer_chain_reach", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64",
+]
+
+
+class Settings(C.Structure):
+    _fields_ = [("temporal_order", C.c_int32), ("spacial_order", C.c_int32), ("sweep_threshold", C.c_double),
+                ("maximum_enclosure_widths_ratio", C.c_double), ("max_boxes", C.c_int32), ("arena_words", C.c_int32),
+                ("hash_log2", C.c_int32), ("batch_cells", C.c_int32), ("ttl_seconds", C.c_double)]
+
+
+class Status(C.Structure):
+    _fields_ = [("code", C.c_int32), ("cell", C.c_int64), ("steps", C.c_int64), ("keys_emitted", C.c_int64),
+                ("arena_peak", C.c_int32), ("evolve_ms", C.c_double), ("raster_ms", C.c_double)]
+
+
+class Ab200Error(RuntimeError):
+    def __init__(self, code, message=""):
+        self.code = code
+        RuntimeError.__init__(self, "%s (%d): %s" % (E_NAMES.get(code, "error"), code, message))
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libariadne_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libariadne_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise FileNotFoundError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    lib = C.CDLL(path)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    P = C.POINTER
+    lib.ab200_default_settings.argtypes = [P(Settings)]; lib.ab200_default_settings.restype = None
+    lib.ab200_ctx_create.argtypes = [P(vp), C.c_int]; lib.ab200_ctx_create.restype = C.c_int
+    lib.ab200_ctx_destroy.argtypes = [vp]; lib.ab200_ctx_destroy.restype = None
+    lib.ab200_last_error.argtypes = [vp]; lib.ab200_last_error.restype = C.c_char_p
+    lib.ab200_set_system_text.argtypes = [vp, C.c_char_p]; lib.ab200_set_system_text.restype = C.c_int
+    lib.ab200_system_info.argtypes = [vp, P(i32), P(i32)]; lib.ab200_system_info.restype = C.c_int
+    lib.ab200_location_index.argtypes = [vp, C.c_char_p]; lib.ab200_location_index.restype = C.c_int
+    lib.ab200_set_settings.argtypes = [vp, P(Settings)]; lib.ab200_set_settings.restype = C.c_int
+    lib.ab200_set_location_tuning.argtypes = [vp, i32, dbl, P(dbl), P(dbl), P(dbl)]; lib.ab200_set_location_tuning.restype = C.c_int
+    lib.ab200_set_accuracy.argtypes = [vp, i32]; lib.ab200_set_accuracy.restype = C.c_int
+    lib.ab200_upper_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, C.c_int, C.c_int, P(vp), P(vp), P(Status)]
+    lib.ab200_upper_reach_evolve.restype = C.c_int
+    lib.ab200_cellset_view.argtypes = [vp, P(P(u64)), P(u64)]; lib.ab200_cellset_view.restype = C.c_int
+    lib.ab200_cellset_free.argtypes = [vp]; lib.ab200_cellset_free.restype = None
+    lib.ab200_key_decode.argtypes = [vp, u64, P(i32), P(i64)]; lib.ab200_key_decode.restype = C.c_int
+    lib.ab200_reach_evolve_boxes.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, C.c_int, C.c_int, P(vp), P(vp), P(Status)]
+    lib.ab200_reach_evolve_boxes.restype = C.c_int
+    lib.ab200_boxlist_view.argtypes = [vp, P(P(u64)), P(P(dbl)), P(P(i32))]; lib.ab200_boxlist_view.restype = C.c_int
+    lib.ab200_boxlist_free.argtypes = [vp]; lib.ab200_boxlist_free.restype = None
+    lib.ab200_flow_bounds.argtypes = [vp, u64, P(i32), P(dbl), dbl, P(dbl), P(dbl), P(i32)]; lib.ab200_flow_bounds.restype = C.c_int
+    lib.ab200_analyser_create.argtypes = [P(vp), vp, P(dbl), i32]; lib.ab200_analyser_create.restype = C.c_int
+    lib.ab200_analyser_destroy.argtypes = [vp]; lib.ab200_analyser_destroy.restype = None
+    lib.ab200_analyser_info.argtypes = [vp, P(dbl), P(dbl), P(dbl), P(dbl)]; lib.ab200_analyser_info.restype = C.c_int
+    lib.ab200_analyser_set_lock_time.argtypes = [vp, dbl]; lib.ab200_analyser_set_lock_time.restype = C.c_int
+    lib.ab200_analyser_upper_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, C.c_int, P(vp), P(vp), P(Status)]
+    lib.ab200_analyser_upper_reach_evolve.restype = C.c_int
+    lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), P(vp), P(Status)]
+    lib.ab200_analyser_outer_chain_reach.restype = C.c_int
+    lib.ab200_analyser_cells_evolved.argtypes = [vp]; lib.ab200_analyser_cells_evolved.restype = i64
+    lib.ab200_analyser_enumerate.argtypes = [vp, vp, C.c_int, P(u64), P(i32), P(dbl)]; lib.ab200_analyser_enumerate.restype = C.c_int
+    lib.ab200_probe_fp64.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def pack_boxes(boxes, dim):
+    """[[lo0,hi0,lo1,hi1,...], ...] -> contiguous float64 array with BOX_STRIDE doubles per box."""
+    b = np.asarray(boxes, dtype=np.float64).reshape(-1, 2 * dim)
+    out = np.zeros((b.shape[0], BOX_STRIDE), dtype=np.float64)
+    out[:, :2 * dim] = b
+    return np.ascontiguousarray(out)
+
+
+class CellSet(object):
+    """Sorted, duplicate-free packed cell keys of a HybridDenotableSet (host copy)."""
+
+    def __init__(self, keys):
+        self.keys = keys
+
+    def __len__(self):
+        return int(self.keys.shape[0])
+
+
+def _take_cellset(lib, handle):
+    keys = C.POINTER(C.c_uint64)(); n = C.c_uint64(0)
+    lib.ab200_cellset_view(handle, C.byref(keys), C.byref(n))
+    arr = np.ctypeslib.as_array(keys, shape=(n.value,)).copy() if n.value else np.zeros((0,), dtype=np.uint64)
+    lib.ab200_cellset_free(handle)
+    return CellSet(arr)
+
+
+def _take_boxlist(lib, handle, n_cells):
+    off = C.POINTER(C.c_uint64)(); bx = C.POINTER(C.c_double)(); lc = C.POINTER(C.c_int32)()
+    lib.ab200_boxlist_view(handle, C.byref(off), C.byref(bx), C.byref(lc))
+    offsets = np.ctypeslib.as_array(off, shape=(n_cells + 1,)).copy()
+    total = int(offsets[-1])
+    boxes = np.ctypeslib.as_array(bx, shape=(total, BOX_STRIDE)).copy() if total else np.zeros((0, BOX_STRIDE))
+    locs = np.ctypeslib.as_array(lc, shape=(total,)).copy() if total else np.zeros((0,), dtype=np.int32)
+    lib.ab200_boxlist_free(handle)
+    return offsets, boxes, locs
+
+
+class Evolver(object):
+    """Device evolver for one system (the role of ImageSetHybridEvolver behind EvolverInterface)."""
+
+    def __init__(self, system_text, device=0, settings=None):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        rc = self.lib.ab200_ctx_create(C.byref(self.handle), device)
+        if rc != 0:
+            self.handle = None
+            raise Ab200Error(rc, "no usable sm_100 GPU (this library has no CPU path)")
+        self._check(self.lib.ab200_set_system_text(self.handle, system_text.encode()))
+        n = C.c_int32(0)
+        self.lib.ab200_system_info(self.handle, C.byref(n), None)
+        dims = (C.c_int32 * n.value)()
+        self.lib.ab200_system_info(self.handle, C.byref(n), dims)
+        self.n_locations = n.value
+        self.dims = list(dims)
+        self.settings = Settings()
+        self.lib.ab200_default_settings(C.byref(self.settings))
+        if settings:
+            for k, v in settings.items():
+                setattr(self.settings, k, v)
+            self._check(self.lib.ab200_set_settings(self.handle, C.byref(self.settings)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Ab200Error(rc, self.lib.ab200_last_error(self.handle).decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.ab200_ctx_destroy(self.handle)
+            self.handle = None
+
+    def location(self, name):
+        i = self.lib.ab200_location_index(self.handle, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def set_settings(self, **kw):
+        for k, v in kw.items():
+            setattr(self.settings, k, v)
+        self._check(self.lib.ab200_set_settings(self.handle, C.byref(self.settings)))
+
+    def tune_settings(self, loc, max_step, ref_widths, grid_origin, grid_lengths):
+        """ImageSetHybridEvolver::tune_settings for one location (src/hybrid_evolver-image.cpp:99-113)."""
+        a = [np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for v in (ref_widths, grid_origin, grid_lengths)]
+        self._check(self.lib.ab200_set_location_tuning(self.handle, loc, float(max_step), _dptr(a[0]), _dptr(a[1]), _dptr(a[2])))
+
+    def set_accuracy(self, accuracy):
+        self._check(self.lib.ab200_set_accuracy(self.handle, accuracy))
+
+    def reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False):
+        """Batch EvolverInterface::reach_evolve: returns (reach, final) as (offsets, boxes, locs) triples."""
+        locs = np.ascontiguousarray(np.asarray(locs, dtype=np.int32))
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64))
+        n = locs.shape[0]
+        r = C.c_void_p(); f = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_reach_evolve_boxes(self.handle, n, _iptr(locs), _dptr(boxes), float(time), int(max_events),
+                                               int(bool(ignore_activations)), 0, C.byref(r), C.byref(f), C.byref(st))
+        self.last_status = st
+        self._check(rc)
+        return _take_boxlist(self.lib, r, n), _take_boxlist(self.lib, f, n)
+
+    def upper_reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False):
+        """UpperReachEvolveWorker::get_result(): (reach CellSet, evolve CellSet)."""
+        locs = np.ascontiguousarray(np.asarray(locs, dtype=np.int32))
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64))
+        r = C.c_void_p(); e = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_upper_reach_evolve(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), float(time), int(max_events),
+                                               int(bool(ignore_activations)), 0, C.byref(r), C.byref(e), C.byref(st))
+        self.last_status = st
+        self._check(rc)
+        return _take_cellset(self.lib, r), _take_cellset(self.lib, e)
+
+    def flow_bounds(self, locs, boxes, hmax):
+        locs = np.ascontiguousarray(np.asarray(locs, dtype=np.int32))
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64))
+        n = locs.shape[0]
+        h = np.zeros((n,), dtype=np.float64); b = np.zeros((n, BOX_STRIDE), dtype=np.float64); s = np.zeros((n,), dtype=np.int32)
+        self._check(self.lib.ab200_flow_bounds(self.handle, n, _iptr(locs), _dptr(boxes), float(hmax), _dptr(h), _dptr(b), _iptr(s)))
+        return h, b, s
+
+    def decode(self, keys):
+        out = np.zeros((len(keys), 1 + max(self.dims)), dtype=np.int64)
+        loc = C.c_int32(0); idx = (C.c_int64 * MAX_DIM)()
+        for k, key in enumerate(keys):
+            self.lib.ab200_key_decode(self.handle, int(key), C.byref(loc), idx)
+            out[k, 0] = loc.value
+            for i in range(self.dims[0]):
+                out[k, 1 + i] = idx[i]
+        return out
+
+    def probe_fp64(self):
+        g = C.c_double(0)
+        self._check(self.lib.ab200_probe_fp64(self.handle, C.byref(g)))
+        return g.value
+
+
+class HybridReachabilityAnalyser(object):
+    """HybridReachabilityAnalyser(system, domain, accuracy) (src/reachability_analyser.cpp:83-100)."""
+
+    def __init__(self, system_text, domain, accuracy, device=0, settings=None):
+        self.evolver = Evolver(system_text, device=device, settings=settings)
+        self.lib = self.evolver.lib
+        dim = self.evolver.dims[0]
+        if isinstance(domain, dict):
+            dom = np.zeros((self.evolver.n_locations, BOX_STRIDE))
+            for name, box in domain.items():
+                dom[self.evolver.location(name), :2 * dim] = box
+        else:
+            dom = np.tile(pack_boxes([domain], dim), (self.evolver.n_locations, 1))
+        dom = np.ascontiguousarray(dom)
+        self.handle = C.c_void_p()
+        self.evolver._check(self.lib.ab200_analyser_create(C.byref(self.handle), self.evolver.handle, _dptr(dom), int(accuracy)))
+        self.accuracy = accuracy
+        self.dim = dim
+        lock = C.c_double(0)
+        L = self.evolver.n_locations
+        self.grid_origin = np.zeros((L, MAX_DIM)); self.grid_lengths = np.zeros((L, MAX_DIM)); self.max_step = np.zeros((L,))
+        self.lib.ab200_analyser_info(self.handle, C.byref(lock), _dptr(self.grid_origin), _dptr(self.grid_lengths), _dptr(self.max_step))
+        self.lock_to_grid_time = lock.value
+        self.last_status = None
+
+    def close(self):
+        if self.handle:
+            self.lib.ab200_analyser_destroy(self.handle)
+            self.handle = None
+        self.evolver.close()
+
+    def set_lock_to_grid_time(self, t):
+        self.evolver._check(self.lib.ab200_analyser_set_lock_time(self.handle, float(t)))
+        self.lock_to_grid_time = float(t)
+
+    def _initial(self, initial_set):
+        locs, boxes = [], []
+        for name, box in initial_set.items():
+            locs.append(self.evolver.location(name) if isinstance(name, str) else int(name))
+            boxes.append(box)
+        return np.ascontiguousarray(np.asarray(locs, dtype=np.int32)), pack_boxes(boxes, self.dim)
+
+    def upper_reach_evolve(self, initial_set, time, max_events=5, mince=False):
+        locs, boxes = self._initial(initial_set)
+        r = C.c_void_p(); e = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_analyser_upper_reach_evolve(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), float(time), int(max_events),
+                                                        int(bool(mince)), C.byref(r), C.byref(e), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
+        return self._wrap(r), self._wrap(e)
+
+    def upper_reach(self, initial_set, time, max_events=5, mince=False):
+        return self.upper_reach_evolve(initial_set, time, max_events, mince)[0]
+
+    def upper_evolve(self, initial_set, time, max_events=5, mince=False):
+        return self.upper_reach_evolve(initial_set, time, max_events, mince)[1]
+
+    def outer_chain_reach(self, initial_set):
+        locs, boxes = self._initial(initial_set)
+        r = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_analyser_outer_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), C.byref(r), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
+        return self._wrap(r)
+
+    def cells_evolved(self):
+        return int(self.lib.ab200_analyser_cells_evolved(self.handle))
+
+    def _wrap(self, handle):
+        # keep the library object alive for enumerate(); copy the keys for numpy users
+        keys = C.POINTER(C.c_uint64)(); n = C.c_uint64(0)
+        self.lib.ab200_cellset_view(handle, C.byref(keys), C.byref(n))
+        arr = np.ctypeslib.as_array(keys, shape=(n.value,)).copy() if n.value else np.zeros((0,), dtype=np.uint64)
+        cs = CellSet(arr)
+        cs._handle = handle
+        cs._owner = self
+        return cs
+
+    def enumerate(self, cellset, mince=False):
+        """Cells of a set as the reference iterates them: (locs, boxes[count, 2*dim])."""
+        n = C.c_uint64(0)
+        self.evolver._check(self.lib.ab200_analyser_enumerate(self.handle, cellset._handle, int(bool(mince)), C.byref(n), None, None))
+        locs = np.zeros((n.value,), dtype=np.int32); boxes = np.zeros((n.value, BOX_STRIDE))
+        if n.value:
+            self.evolver._check(self.lib.ab200_analyser_enumerate(self.handle, cellset._handle, int(bool(mince)), C.byref(n), _iptr(locs), _dptr(boxes)))
+        return locs, boxes[:, :2 * self.dim]
+
+    def free(self, cellset):
+        if getattr(cellset, "_handle", None):
+            self.lib.ab200_cellset_free(cellset._handle)
+            cellset._handle = None

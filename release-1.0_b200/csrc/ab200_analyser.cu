@@ -1,0 +1,344 @@
+// ab200_analyser.cu -- host mirror of HybridReachabilityAnalyser over the C ABI lap.
+//
+// Reference: HybridReachabilityAnalyser(system,domain,accuracy) src/reachability_analyser.cpp:83-100;
+// getHybridMidpointAbsoluteDerivatives src/hybrid_set.cpp:485-515; getHybridGrid src/reachability_analyser.cpp:1028-1089;
+// getLockToGridTime :1141-1170; ImageSetHybridEvolver::tune_settings src/hybrid_evolver-image.cpp:99-113,1506-1555;
+// upper_reach_evolve :309-377; outer_chain_reach :380-493; ReachabilityRestriction src/reachability_restriction.cpp.
+// These are one-off host computations per analyser; the per-cell work is all on the device.
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <cstring>
+#include <cmath>
+#include <limits>
+#include "../../include/ariadne_b200.h"
+#include "ab200_calc.cuh"
+#include "ab200_system.h"
+#include "ab200_paving.h"
+
+using namespace ab200;
+
+const HostSystem* ab200_ctx_system(const ab200_ctx* ctx);
+const KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx);
+void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg);
+std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs);
+ab200_cellset* ab200_cellset_new();
+
+struct ab200_analyser {
+    ab200_ctx* ctx;
+    int accuracy;
+    int n_locs, dim;
+    std::vector<GridDesc> grid;
+    std::vector<std::vector<double> > domain;     // [loc][2*dim]
+    std::vector<double> max_step;
+    double lock_time;
+    KeyLayout K;
+    std::vector<CellSet> restriction;              // domain discretisation per location (lazy)
+    std::vector<char> discretised;
+    int64_t cells_evolved;
+};
+
+typedef std::vector<CellSet> HybridCells;          // one CellSet per location
+
+static HybridCells empty_cells(const ab200_analyser* an) {
+    HybridCells h;
+    for (int l = 0; l < an->n_locs; ++l) h.push_back(CellSet(an->grid[l], an->K, l));
+    return h;
+}
+static bool all_empty(const HybridCells& h) { for (size_t l = 0; l < h.size(); ++l) if (!h[l].empty()) return false; return true; }
+static void split_keys(const ab200_analyser* an, const std::vector<uint64_t>& keys, HybridCells& out) {
+    // keys are sorted and the location is the top field, so each location is one contiguous run
+    int shift = 0; for (int i = 0; i < an->K.dim; ++i) shift += an->K.bits[i];
+    size_t i = 0;
+    while (i < keys.size()) {
+        int l = (int)(keys[i] >> shift);
+        size_t j = i; while (j < keys.size() && (int)(keys[j] >> shift) == l) ++j;
+        out[l].keys.assign(keys.begin() + i, keys.begin() + j);
+        i = j;
+    }
+}
+static void join_keys(const HybridCells& h, std::vector<uint64_t>& keys) {
+    keys.clear();
+    for (size_t l = 0; l < h.size(); ++l) keys.insert(keys.end(), h[l].keys.begin(), h[l].keys.end());
+}
+
+// ReachabilityRestriction::apply_to (src/reachability_restriction.cpp:162-187): intersect with the outer
+// approximation of the domain box.
+static bool ensure_restriction(ab200_analyser* an, int l) {
+    if (an->discretised[l]) return true;
+    CellSet s(an->grid[l], an->K, l);
+    bool ok = s.adjoin_outer_approximation(an->domain[l].data());
+    an->restriction[l] = s; an->discretised[l] = 1;
+    return ok;
+}
+static bool apply_restriction(ab200_analyser* an, HybridCells& h) {
+    bool ok = true;
+    const double divider = (double)(1 << an->accuracy);
+    for (int l = 0; l < an->n_locs; ++l) {
+        if (h[l].empty()) continue;
+        if (!an->discretised[l]) {
+            // "If the domain covers the result, no restriction is required" -- and the domain stays undiscretised,
+            // which matters because the evolver tuning depends on it (see tune_evolver).
+            double sb[2 * AB_GRID_MAXN];
+            bool covers = h[l].bounding_box(sb);
+            for (int i = 0; covers && i < an->dim; ++i) {
+                double inaccuracy = an->grid[l].lengths[i] / divider;
+                double lo = an->domain[l][2 * i] - inaccuracy, hi = an->domain[l][2 * i + 1] + inaccuracy;
+                if (!(sb[2 * i] > lo && sb[2 * i + 1] < hi)) covers = false;        // Box::covers is strict
+            }
+            if (covers) continue;
+        }
+        ok = ensure_restriction(an, l) && ok;
+        h[l].restrict(an->restriction[l]);
+    }
+    return ok;
+}
+
+extern "C" int ab200_analyser_create(ab200_analyser** out, ab200_ctx* ctx, const double* domain_boxes, int32_t accuracy) {
+    if (!out || !ctx || !domain_boxes) return AB200_E_ARGUMENT;
+    *out = 0;
+    const HostSystem* hs = ab200_ctx_system(ctx);
+    if (!hs) { ab200_ctx_set_error(ctx, "no system uploaded"); return AB200_E_ARGUMENT; }
+    const SystemDesc& S = hs->desc;
+    const int L = S.n_locs, dim = S.loc[0].n;
+    ab200_analyser* an = new ab200_analyser();
+    an->ctx = ctx; an->accuracy = accuracy; an->n_locs = L; an->dim = dim; an->cells_evolved = 0;
+    an->domain.resize(L); an->grid.resize(L); an->max_step.resize(L);
+    std::vector<std::vector<double> > hmad(L, std::vector<double>(dim, 0.0));
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    double lock = 0.0;
+    for (int l = 0; l < L; ++l) {
+        an->domain[l].assign(domain_boxes + (size_t)l * AB200_BOX_STRIDE, domain_boxes + (size_t)l * AB200_BOX_STRIDE + 2 * dim);
+        Ivl d[AB_MAXN];
+        bool empty = false;
+        for (int i = 0; i < dim; ++i) { d[i] = ivl(an->domain[l][2 * i], an->domain[l][2 * i + 1]); if (d[i].l > d[i].u) empty = true; }
+        if (empty) continue;
+        for (int i = 0; i < dim; ++i) {
+            Ivl der = eval_ivl(c, S.ops, S.loc[l].dyn[i], d);
+            Ivl a = ivl_abs(der);
+            hmad[l][i] = ivl_mid(a);                                   // abs(der_bbx[i]).midpoint()
+            double maxAbsDer = a.u;                                    // getLockToGridTime
+            if (maxAbsDer > 0) lock = std::max(lock, ivl_width(d[i]) / maxAbsDer);
+        }
+    }
+    if (c.status != ST_OK) { delete an; ab200_ctx_set_error(ctx, "dynamics cannot be evaluated on the domain"); return c.status; }
+    an->lock_time = lock;
+    // getHybridGrid(hmad,domain)
+    std::vector<double> minDom(dim, std::numeric_limits<double>::infinity());
+    for (int l = 0; l < L; ++l) for (int i = 0; i < dim; ++i) minDom[i] = std::min(minDom[i], ivl_width(ivl(an->domain[l][2 * i], an->domain[l][2 * i + 1])));
+    std::vector<double> minNonZero = minDom;
+    double maxratio = 0.0;
+    for (int l = 0; l < L; ++l) for (int i = 0; i < dim; ++i) maxratio = std::max(maxratio, hmad[l][i] / minDom[i]);
+    for (int l = 0; l < L; ++l) for (int i = 0; i < dim; ++i) if (hmad[l][i] > 0) minNonZero[i] = std::min(minNonZero[i], hmad[l][i] / maxratio);
+    const double divider = (double)(1 << accuracy);
+    for (int l = 0; l < L; ++l) {
+        GridDesc g; g.dim = dim;
+        for (int i = 0; i < dim; ++i) {
+            g.lengths[i] = (hmad[l][i] > 0) ? hmad[l][i] / maxratio : minNonZero[i];
+            g.origin[i] = ivl_mid(ivl(an->domain[l][2 * i], an->domain[l][2 * i + 1]));     // domain centre
+        }
+        an->grid[l] = g;
+        // getHybridMaximumStepSize
+        double mss = 0.0;
+        for (int i = 0; i < dim; ++i) if (hmad[l][i] > 0) mss = std::max(mss, g.lengths[i] / divider / hmad[l][i]);
+        if (mss == 0) mss = std::numeric_limits<double>::infinity();
+        an->max_step[l] = 2.0 * mss;
+        double refw[AB_MAXN];
+        for (int i = 0; i < dim; ++i) refw[i] = g.lengths[i] / divider;                      // getMinimumGridCellWidths
+        int rc = ab200_set_location_tuning(ctx, l, an->max_step[l], refw, g.origin, g.lengths);
+        if (rc != AB200_OK) { delete an; return rc; }
+    }
+    int rc = ab200_set_accuracy(ctx, accuracy);
+    if (rc != AB200_OK) { delete an; return rc; }
+    an->K = *ab200_ctx_layout(ctx);
+    an->restriction.resize(L); an->discretised.assign(L, 0);
+    *out = an;
+    return AB200_OK;
+}
+extern "C" void ab200_analyser_destroy(ab200_analyser* an) { delete an; }
+extern "C" int ab200_analyser_info(const ab200_analyser* an, double* lock, double* origin, double* lengths, double* max_step) {
+    if (!an) return AB200_E_ARGUMENT;
+    if (lock) *lock = an->lock_time;
+    for (int l = 0; l < an->n_locs; ++l) {
+        for (int i = 0; i < an->dim; ++i) { if (origin) origin[l * AB200_MAX_DIM + i] = an->grid[l].origin[i]; if (lengths) lengths[l * AB200_MAX_DIM + i] = an->grid[l].lengths[i]; }
+        if (max_step) max_step[l] = an->max_step[l];
+    }
+    return AB200_OK;
+}
+extern "C" int ab200_analyser_set_lock_time(ab200_analyser* an, double t) { if (!an || !(t > 0)) return AB200_E_ARGUMENT; an->lock_time = t; return AB200_OK; }
+extern "C" int64_t ab200_analyser_cells_evolved(const ab200_analyser* an) { return an ? an->cells_evolved : 0; }
+
+// _get_tuned_evolver (src/reachability_analyser.cpp:125-142): every lap builds a fresh evolver tuned on
+// ReachabilityRestriction::bounding_box(), which is the domain widened by one cell per side until the domain has been
+// discretised and the bounding box of the discretised cells afterwards (src/reachability_restriction.cpp:597-621).
+static int tune_evolver(ab200_analyser* an) {
+    const HostSystem* hs = ab200_ctx_system(an->ctx);
+    const SystemDesc& S = hs->desc;
+    const int dim = an->dim;
+    const double divider = (double)(1 << an->accuracy);
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    for (int l = 0; l < an->n_locs; ++l) {
+        double bb[2 * AB_GRID_MAXN];
+        bool have = false;
+        if (an->discretised[l]) have = an->restriction[l].bounding_box(bb);
+        if (!have) {
+            for (int i = 0; i < dim; ++i) {
+                double inaccuracy = an->grid[l].lengths[i] / divider;
+                bb[2 * i] = an->domain[l][2 * i] - inaccuracy; bb[2 * i + 1] = an->domain[l][2 * i + 1] + inaccuracy;
+            }
+        }
+        Ivl d[AB_MAXN]; bool empty = false;
+        for (int i = 0; i < dim; ++i) { d[i] = ivl(bb[2 * i], bb[2 * i + 1]); if (d[i].l > d[i].u) empty = true; }
+        double mss = 0.0;
+        if (!empty) {
+            for (int i = 0; i < dim; ++i) {
+                Ivl der = eval_ivl(c, S.ops, S.loc[l].dyn[i], d);
+                double hm = ivl_mid(ivl_abs(der));
+                if (hm > 0) mss = std::max(mss, an->grid[l].lengths[i] / divider / hm);
+            }
+        }
+        if (c.status != ST_OK) { ab200_ctx_set_error(an->ctx, "dynamics cannot be evaluated on the restriction box"); return c.status; }
+        if (mss == 0) mss = std::numeric_limits<double>::infinity();
+        an->max_step[l] = 2.0 * mss;
+        double refw[AB_MAXN];
+        for (int i = 0; i < dim; ++i) refw[i] = an->grid[l].lengths[i] / divider;
+        int rc = ab200_set_location_tuning(an->ctx, l, an->max_step[l], refw, an->grid[l].origin, an->grid[l].lengths);
+        if (rc != AB200_OK) return rc;
+    }
+    return AB200_OK;
+}
+
+// to_enclosures (src/reachability_analyser.cpp:1244-1253) + UpperReachEvolveWorker::get_result.
+static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, double T, int events, int ignore_activations,
+               HybridCells& reach, HybridCells& evolve, ab200_status* st_acc) {
+    std::vector<int32_t> locs; std::vector<double> boxes;
+    for (int l = 0; l < an->n_locs; ++l) {
+        std::vector<CellBox> cells;
+        frontier[l].enumerate(cells, mince ? an->dim * an->accuracy : -1);
+        for (size_t k = 0; k < cells.size(); ++k) {
+            locs.push_back(l);
+            size_t o = boxes.size(); boxes.resize(o + AB200_BOX_STRIDE, 0.0);
+            for (int i = 0; i < 2 * an->dim; ++i) boxes[o + i] = cells[k].b[i];
+        }
+    }
+    an->cells_evolved += (int64_t)locs.size();
+    { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
+    ab200_cellset *r = 0, *e = 0; ab200_status st; memset(&st, 0, sizeof(st));
+    int rc = ab200_upper_reach_evolve(an->ctx, locs.size(), locs.data(), boxes.data(), T, events, ignore_activations, 0, &r, &e, &st);
+    if (st_acc) {
+        st_acc->steps += st.steps; st_acc->keys_emitted += st.keys_emitted; st_acc->evolve_ms += st.evolve_ms; st_acc->raster_ms += st.raster_ms;
+        st_acc->arena_peak = std::max(st_acc->arena_peak, st.arena_peak);
+        if (rc != AB200_OK) { st_acc->code = st.code ? st.code : rc; st_acc->cell = st.cell; }
+    }
+    if (rc != AB200_OK) return rc;
+    reach = empty_cells(an); evolve = empty_cells(an);
+    split_keys(an, ab200_cellset_keys(r), reach);
+    split_keys(an, ab200_cellset_keys(e), evolve);
+    ab200_cellset_free(r); ab200_cellset_free(e);
+    return AB200_OK;
+}
+
+// ReachabilityRestriction::outer_intersection_with(HybridBoundedConstraintSet) for box-only sets
+// (src/reachability_restriction.cpp:522-535).
+static int discretise_initial(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, HybridCells& initial) {
+    initial = empty_cells(an);
+    bool ok = true;
+    for (uint64_t k = 0; k < n_init; ++k) {
+        if (loc[k] < 0 || loc[k] >= an->n_locs) return AB200_E_ARGUMENT;
+        CellSet s(an->grid[loc[k]], an->K, loc[k]);
+        ok = s.adjoin_outer_approximation(boxes + k * AB200_BOX_STRIDE) && ok;
+        initial[loc[k]].adjoin(s);
+    }
+    ok = apply_restriction(an, initial) && ok;
+    if (!ok) { ab200_ctx_set_error(an->ctx, "initial set or domain lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    return AB200_OK;
+}
+
+static ab200_cellset* to_cellset(const HybridCells& h) { ab200_cellset* cs = ab200_cellset_new(); join_keys(h, ab200_cellset_keys(cs)); return cs; }
+
+extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                                 double T, int32_t max_events, int mince,
+                                                 ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    if (!an || !reach_out || !evolve_out) return AB200_E_ARGUMENT;
+    *reach_out = 0; *evolve_out = 0;
+    an->cells_evolved = 0;
+    ab200_status st; memset(&st, 0, sizeof(st)); st.cell = -1;
+    double lock = an->lock_time;
+    unsigned time_steps = (unsigned)(T / lock);
+    double remaining = T - time_steps * lock;
+    if (time_steps == 0) { time_steps = 1; remaining = 0.0; lock = T; }
+    HybridCells initial;
+    int rc = discretise_initial(an, n_init, loc, boxes, initial);
+    if (rc != AB200_OK) return rc;
+    HybridCells reach = empty_cells(an), evolve = empty_cells(an), found, next;
+    // first lap: evolver->orbit per initial enclosure (:348-353)
+    rc = lap(an, initial, mince, lock, max_events, 0, found, next, &st);
+    if (rc != AB200_OK) { if (status) *status = st; return rc; }
+    for (int l = 0; l < an->n_locs; ++l) { reach[l].adjoin(found[l]); evolve[l].adjoin(next[l]); }
+    for (unsigned i = 1; i < time_steps; ++i) {
+        rc = lap(an, evolve, 0, lock, max_events, 0, found, next, &st);
+        if (rc != AB200_OK) { if (status) *status = st; return rc; }
+        evolve = next;
+        for (int l = 0; l < an->n_locs; ++l) reach[l].adjoin(found[l]);
+    }
+    if (!all_empty(evolve) && remaining > 0) {
+        rc = lap(an, evolve, 0, remaining, max_events, 0, found, next, &st);
+        if (rc != AB200_OK) { if (status) *status = st; return rc; }
+        evolve = next;
+        for (int l = 0; l < an->n_locs; ++l) reach[l].adjoin(found[l]);
+    }
+    apply_restriction(an, reach);
+    apply_restriction(an, evolve);
+    *reach_out = to_cellset(reach); *evolve_out = to_cellset(evolve);
+    if (status) *status = st;
+    return AB200_OK;
+}
+
+extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                                ab200_cellset** reach_out, ab200_status* status) {
+    if (!an || !reach_out) return AB200_E_ARGUMENT;
+    *reach_out = 0;
+    an->cells_evolved = 0;
+    const HostSystem* hs = ab200_ctx_system(an->ctx);
+    for (int l = 0; l < hs->desc.n_locs; ++l)
+        for (int e = 0; e < hs->desc.loc[l].n_events; ++e)
+            if (hs->desc.loc[l].ev[e].kind != EV_INVARIANT) {
+                ab200_ctx_set_error(an->ctx, "outer_chain_reach: grid-side jump sets (forward_jump_set) are not implemented yet");
+                return AB200_E_UNSUPPORTED;
+            }
+    ab200_status st; memset(&st, 0, sizeof(st)); st.cell = -1;
+    HybridCells current;
+    int rc = discretise_initial(an, n_init, loc, boxes, current);
+    if (rc != AB200_OK) return rc;
+    HybridCells reach = empty_cells(an), fin = empty_cells(an), new_reach, new_final;
+    int guard = 0;
+    while (!all_empty(current) && guard++ < 100000) {
+        rc = lap(an, current, 0, an->lock_time, 1, 1, new_reach, new_final, &st);       // lock_to_grid_steps=1, ignore_activations
+        if (rc != AB200_OK) { if (status) *status = st; return rc; }
+        for (int l = 0; l < an->n_locs; ++l) { new_final[l].remove(fin[l]); new_reach[l].remove(reach[l]); }
+        apply_restriction(an, new_final); apply_restriction(an, new_reach);
+        for (int l = 0; l < an->n_locs; ++l) { reach[l].adjoin(new_reach[l]); fin[l].adjoin(new_final[l]); }
+        current = new_final;      // forward_jump_set(new_reach) is empty without transitions
+    }
+    *reach_out = to_cellset(reach);
+    if (status) *status = st;
+    return AB200_OK;
+}
+
+extern "C" int ab200_analyser_enumerate(const ab200_analyser* an, const ab200_cellset* cs, int mince, uint64_t* count,
+                                        int32_t* locs, double* boxes) {
+    if (!an || !cs || !count) return AB200_E_ARGUMENT;
+    HybridCells h = empty_cells(an);
+    split_keys(an, ab200_cellset_keys(const_cast<ab200_cellset*>(cs)), h);
+    uint64_t n = 0;
+    for (int l = 0; l < an->n_locs; ++l) {
+        std::vector<CellBox> cells; h[l].enumerate(cells, mince ? an->dim * an->accuracy : -1);
+        for (size_t k = 0; k < cells.size(); ++k) {
+            if (locs) locs[n] = l;
+            if (boxes) { for (int i = 0; i < AB200_BOX_STRIDE; ++i) boxes[n * AB200_BOX_STRIDE + i] = (i < 2 * an->dim) ? cells[k].b[i] : 0.0; }
+            ++n;
+        }
+    }
+    *count = n;
+    return AB200_OK;
+}

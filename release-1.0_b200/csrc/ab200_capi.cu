@@ -1,0 +1,385 @@
+// ab200_capi.cu -- C ABI (include/ariadne_b200.h): context, device buffers, the lap pipeline.
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <cstdio>
+#include "../../include/ariadne_b200.h"
+#include "ab200_device.h"
+#include "ab200_system.h"
+#include "ab200_paving.h"
+
+using namespace ab200;
+
+static_assert(AB200_MAX_DIM == AB_MAXN, "header / kernel dimension mismatch");
+
+template<class T> struct DevBuf {
+    T* p; size_t n;
+    DevBuf() : p(0), n(0) { }
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = 0; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = 0; n = 0; }
+};
+
+struct ab200_cellset { std::vector<uint64_t> keys; };
+struct ab200_boxlist { std::vector<uint64_t> offsets; std::vector<double> boxes; std::vector<int32_t> locs; };
+
+struct ab200_ctx {
+    int device;
+    cudaStream_t stream;
+    HostSystem sys;
+    bool have_system;
+    ab200_settings settings;
+    int accuracy;
+    KeyLayout K;
+    bool have_layout;
+    std::string err;
+    // device buffers
+    DevBuf<int32_t> d_loc, d_nreach, d_nfin, d_status, d_steps, d_peak, d_rloc, d_floc;
+    DevBuf<double> d_box, d_reach, d_fin;
+    DevBuf<uint64_t> d_arena, d_table, d_keys, d_tmp;
+    DevBuf<unsigned> d_hist;
+    DevBuf<unsigned long long> d_counters;
+    cudaEvent_t ev0, ev1;
+};
+
+#define CTX_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return AB200_E_CUDA; } } while (0)
+#define DEV_CK(x) do { char eb_[256]; eb_[0] = 0; int r_ = (x); if (r_ != 0) { ctx->err = eb_; return AB200_E_CUDA; } } while (0)
+
+extern "C" void ab200_default_settings(ab200_settings* s) {
+    s->temporal_order = 6; s->spacial_order = 6; s->sweep_threshold = 1e-12; s->maximum_enclosure_widths_ratio = 5.0;
+    s->max_boxes = 192; s->arena_words = 16384; s->hash_log2 = 24; s->batch_cells = 1 << 17; s->ttl_seconds = 0.0;
+}
+
+extern "C" int ab200_ctx_create(ab200_ctx** out, int device) {
+    if (!out) return AB200_E_ARGUMENT;
+    *out = 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return AB200_E_CUDA;   // no GPU: fail loudly
+    if (cudaSetDevice(device) != cudaSuccess) return AB200_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AB200_E_CUDA;
+    if (prop.major != 10) return AB200_E_CUDA;    // kernels are built for sm_100a only
+    ab200_ctx* ctx = new ab200_ctx();
+    ctx->device = device; ctx->have_system = false; ctx->have_layout = false; ctx->accuracy = 0;
+    ab200_default_settings(&ctx->settings);
+    if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return AB200_E_CUDA; }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    char eb[256];
+    if (dev_set_stack(32 * 1024, eb, sizeof(eb)) != 0) { delete ctx; return AB200_E_CUDA; }
+    *out = ctx;
+    return AB200_OK;
+}
+extern "C" void ab200_ctx_destroy(ab200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->d_loc.release(); ctx->d_nreach.release(); ctx->d_nfin.release(); ctx->d_status.release(); ctx->d_steps.release(); ctx->d_peak.release();
+    ctx->d_rloc.release(); ctx->d_floc.release(); ctx->d_box.release(); ctx->d_reach.release(); ctx->d_fin.release();
+    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release();
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char* ab200_last_error(const ab200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int ab200_set_system_text(ab200_ctx* ctx, const char* text) {
+    if (!ctx || !text) return AB200_E_ARGUMENT;
+    std::string e = parse_system(text, ctx->sys);
+    if (!e.empty()) { ctx->err = "system description: " + e; return AB200_E_ARGUMENT; }
+    ctx->have_system = true;
+    CTX_CK(cudaSetDevice(ctx->device));
+    DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
+    return AB200_OK;
+}
+extern "C" int ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims) {
+    if (!ctx || !ctx->have_system) return AB200_E_ARGUMENT;
+    if (n_locations) *n_locations = ctx->sys.desc.n_locs;
+    if (dims) for (int i = 0; i < ctx->sys.desc.n_locs; ++i) dims[i] = ctx->sys.desc.loc[i].n;
+    return AB200_OK;
+}
+extern "C" int ab200_location_index(const ab200_ctx* ctx, const char* name) {
+    if (!ctx || !ctx->have_system || !name) return -1;
+    for (size_t i = 0; i < ctx->sys.loc_names.size(); ++i) if (ctx->sys.loc_names[i] == name) return (int)i;
+    return -1;
+}
+extern "C" int ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s) {
+    if (!ctx || !s) return AB200_E_ARGUMENT;
+    if (s->max_boxes < 1 || s->arena_words < 256 || s->hash_log2 < 8 || s->hash_log2 > 32 || s->batch_cells < 32) { ctx->err = "bad settings"; return AB200_E_ARGUMENT; }
+    ctx->settings = *s;
+    return AB200_OK;
+}
+extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max_step, const double* ref_widths,
+                                         const double* grid_origin, const double* grid_lengths) {
+    if (!ctx || !ctx->have_system || loc < 0 || loc >= ctx->sys.desc.n_locs) return AB200_E_ARGUMENT;
+    LocDesc& L = ctx->sys.desc.loc[loc];
+    L.max_step = max_step;
+    for (int i = 0; i < L.n; ++i) { L.ref_width[i] = ref_widths[i]; L.grid_origin[i] = grid_origin[i]; L.grid_length[i] = grid_lengths[i]; }
+    CTX_CK(cudaSetDevice(ctx->device));
+    DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
+    return AB200_OK;
+}
+// Key window: equal share of the 64 bits after the location field, centred on the grid origin.
+extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
+    if (!ctx || !ctx->have_system || accuracy < 0 || accuracy > 24) return AB200_E_ARGUMENT;
+    const SystemDesc& S = ctx->sys.desc;
+    int dim = S.loc[0].n;
+    for (int l = 1; l < S.n_locs; ++l) if (S.loc[l].n != dim) { ctx->err = "locations of different dimension are not supported"; return AB200_E_UNSUPPORTED; }
+    KeyLayout K; K.dim = dim; K.acc = accuracy;
+    int lb = 0; while ((1 << lb) < S.n_locs) ++lb;
+    K.loc_bits = lb;
+    int per = (63 - lb) / dim; if (per > 40) per = 40;
+    if (per < accuracy + 3) { ctx->err = "accuracy too fine for 64-bit cell keys"; return AB200_E_KEYSPACE; }
+    for (int i = 0; i < dim; ++i) { K.bits[i] = per; K.bias[i] = 1LL << (per - 1); }
+    for (int i = dim; i < AB_GRID_MAXN; ++i) { K.bits[i] = 0; K.bias[i] = 0; }
+    ctx->K = K; ctx->accuracy = accuracy; ctx->have_layout = true;
+    return AB200_OK;
+}
+extern "C" int ab200_key_decode(const ab200_ctx* ctx, uint64_t key, int32_t* loc, int64_t* idx) {
+    if (!ctx || !ctx->have_layout) return AB200_E_ARGUMENT;
+    long long v[AB_GRID_MAXN]; int l;
+    key_unpack(ctx->K, key, &l, v);
+    if (loc) *loc = l;
+    if (idx) for (int i = 0; i < ctx->K.dim; ++i) idx[i] = v[i];
+    return AB200_OK;
+}
+
+// ---- the lap ---------------------------------------------------------------------------------------------------------
+static int map_status(int st) { return st; }   // device ST_* codes coincide with AB200_E_* 1..9
+
+struct LapOut {
+    std::vector<uint64_t>* reach_keys; std::vector<uint64_t>* fin_keys;   // sorted unique (may be null)
+    ab200_boxlist* reach_boxes; ab200_boxlist* fin_boxes;                 // (may be null)
+};
+
+static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T, int32_t max_events,
+                       int ignore_activations, int direction, LapOut& out, ab200_status* status) {
+    if (!ctx || !ctx->have_system) return AB200_E_ARGUMENT;
+    if (direction != 0) { ctx->err = "backward evolution is not supported"; return AB200_E_UNSUPPORTED; }
+    const bool want_keys = out.reach_keys || out.fin_keys;
+    if (want_keys && !ctx->have_layout) { ctx->err = "ab200_set_accuracy must be called first"; return AB200_E_ARGUMENT; }
+    CTX_CK(cudaSetDevice(ctx->device));
+    const ab200_settings& S = ctx->settings;
+    const int stride = AB200_BOX_STRIDE;
+    ab200_status stl; memset(&stl, 0, sizeof(stl)); stl.cell = -1;
+    for (uint64_t i = 0; i < n_cells; ++i) if (loc[i] < 0 || loc[i] >= ctx->sys.desc.n_locs) { ctx->err = "bad location index"; return AB200_E_ARGUMENT; }
+    EvolveParams P;
+    P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations ? 1 : 0; P.max_boxes = S.max_boxes;
+    P.temporal_order = S.temporal_order; P.ratio = S.maximum_enclosure_widths_ratio; P.spacial_sweep = S.sweep_threshold;
+    P.spacial_order = S.spacial_order; P.max_working_sets = 16;
+    const size_t table_n = want_keys ? ((size_t)1 << S.hash_log2) : 0;
+    std::vector<uint64_t> acc_keys[2];
+    if (out.reach_boxes) { out.reach_boxes->offsets.assign(1, 0); }
+    if (out.fin_boxes) { out.fin_boxes->offsets.assign(1, 0); }
+    if (want_keys) {
+        CTX_CK(ctx->d_table.ensure(table_n * 2));
+        CTX_CK(ctx->d_counters.ensure(8));
+        DEV_CK(dev_launch_fill(ctx->stream, ctx->d_table.p, table_n * 2, ~0ull, eb_, sizeof(eb_)));
+        CTX_CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    }
+    float evolve_ms = 0, raster_ms = 0;
+    std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
+    for (uint64_t b0 = 0; b0 < n_cells; b0 += (uint64_t)S.batch_cells) {
+        if (S.ttl_seconds > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > S.ttl_seconds) {
+            ctx->err = "time to live exceeded"; if (status) *status = stl; return AB200_E_TIMEOUT; }
+        const int nb = (int)std::min<uint64_t>(S.batch_cells, n_cells - b0);
+        const int nwarps = (nb + 31) / 32;
+        CTX_CK(ctx->d_loc.ensure(nb)); CTX_CK(ctx->d_box.ensure((size_t)nb * stride));
+        CTX_CK(ctx->d_nreach.ensure(nb)); CTX_CK(ctx->d_nfin.ensure(nb)); CTX_CK(ctx->d_status.ensure(nb)); CTX_CK(ctx->d_steps.ensure(nb)); CTX_CK(ctx->d_peak.ensure(nb));
+        CTX_CK(ctx->d_reach.ensure((size_t)nb * S.max_boxes * stride)); CTX_CK(ctx->d_fin.ensure((size_t)nb * S.max_boxes * stride));
+        CTX_CK(ctx->d_rloc.ensure((size_t)nb * S.max_boxes)); CTX_CK(ctx->d_floc.ensure((size_t)nb * S.max_boxes));
+        CTX_CK(ctx->d_arena.ensure((size_t)nwarps * 32 * S.arena_words));
+        CTX_CK(cudaMemcpyAsync(ctx->d_loc.p, loc + b0, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CTX_CK(cudaMemcpyAsync(ctx->d_box.p, boxes + b0 * stride, (size_t)nb * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        DEV_CK(dev_launch_evolve(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        std::vector<int32_t> h_status(nb), h_steps(nb), h_peak(nb), h_nreach(nb), h_nfin(nb);
+        CTX_CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CK(cudaMemcpyAsync(h_steps.data(), ctx->d_steps.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CK(cudaMemcpyAsync(h_peak.data(), ctx->d_peak.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CK(cudaMemcpyAsync(h_nreach.data(), ctx->d_nreach.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CK(cudaMemcpyAsync(h_nfin.data(), ctx->d_nfin.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); evolve_ms += ms;
+        for (int i = 0; i < nb; ++i) {
+            stl.steps += h_steps[i];
+            if (h_peak[i] > stl.arena_peak) stl.arena_peak = h_peak[i];
+            if (h_status[i] != ST_OK && stl.code == AB200_OK) { stl.code = map_status(h_status[i]); stl.cell = (int64_t)(b0 + i); }
+        }
+        if (stl.code != AB200_OK) {
+            // first failure aborts the lap and discards its results (include/workers.h:129-139,159-166)
+            char msg[160]; snprintf(msg, sizeof(msg), "cell %lld failed with code %d", (long long)stl.cell, stl.code);
+            ctx->err = msg; stl.evolve_ms = evolve_ms; if (status) *status = stl; return stl.code;
+        }
+        if (out.reach_boxes || out.fin_boxes) {
+            for (int which = 0; which < 2; ++which) {
+                ab200_boxlist* bl = which ? out.fin_boxes : out.reach_boxes;
+                if (!bl) continue;
+                const std::vector<int32_t>& cnt = which ? h_nfin : h_nreach;
+                std::vector<double> hb((size_t)nb * S.max_boxes * stride); std::vector<int32_t> hl((size_t)nb * S.max_boxes);
+                CTX_CK(cudaMemcpy(hb.data(), which ? ctx->d_fin.p : ctx->d_reach.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+                CTX_CK(cudaMemcpy(hl.data(), which ? ctx->d_floc.p : ctx->d_rloc.p, hl.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+                for (int i = 0; i < nb; ++i) {
+                    for (int k = 0; k < cnt[i]; ++k) {
+                        const double* src = &hb[((size_t)i * S.max_boxes + k) * stride];
+                        bl->boxes.insert(bl->boxes.end(), src, src + stride);
+                        bl->locs.push_back(hl[(size_t)i * S.max_boxes + k]);
+                    }
+                    bl->offsets.push_back(bl->locs.size());
+                }
+            }
+        }
+        if (want_keys) {
+            CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            const uint64_t mask = (uint64_t)table_n - 1;
+            DEV_CK(dev_launch_raster(ctx->stream, nb, S.max_boxes, ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->K, ctx->sys.desc.n_locs,
+                                     ctx->d_table.p, mask, ctx->d_counters.p, eb_, sizeof(eb_)));
+            DEV_CK(dev_launch_raster(ctx->stream, nb, S.max_boxes, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p, ctx->K, ctx->sys.desc.n_locs,
+                                     ctx->d_table.p + table_n, mask, ctx->d_counters.p + 3, eb_, sizeof(eb_)));
+            CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CTX_CK(cudaStreamSynchronize(ctx->stream));
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); raster_ms += ms;
+        }
+    }
+    if (want_keys) {
+        unsigned long long hc[8];
+        CTX_CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
+        stl.keys_emitted = (int64_t)(hc[2] + hc[5]);
+        if (hc[0] || hc[3]) { ctx->err = "cell de-duplication table full: raise ab200_settings.hash_log2"; if (status) *status = stl; return AB200_E_KEYSPACE; }
+        if (hc[1] || hc[4]) { ctx->err = "a reached cell lies outside the packed-key window"; if (status) *status = stl; return AB200_E_KEYSPACE; }
+        CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        int total_bits = ctx->K.loc_bits; for (int i = 0; i < ctx->K.dim; ++i) total_bits += ctx->K.bits[i];
+        for (int which = 0; which < 2; ++which) {
+            std::vector<uint64_t>* dst = which ? out.fin_keys : out.reach_keys;
+            CTX_CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, sizeof(unsigned long long), ctx->stream));
+            CTX_CK(ctx->d_keys.ensure(table_n)); CTX_CK(ctx->d_tmp.ensure(table_n));
+            DEV_CK(dev_launch_compact(ctx->stream, ctx->d_table.p + (size_t)which * table_n, table_n, ctx->d_keys.p, ctx->d_counters.p + 6, eb_, sizeof(eb_)));
+            unsigned long long cnt = 0;
+            CTX_CK(cudaMemcpyAsync(&cnt, ctx->d_counters.p + 6, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+            CTX_CK(cudaStreamSynchronize(ctx->stream));
+            int in_tmp = 0;
+            if (cnt > 1) {
+                size_t nblocks = (cnt + dev_sort_tile() - 1) / dev_sort_tile();
+                CTX_CK(ctx->d_hist.ensure(256 * nblocks));
+                DEV_CK(dev_radix_sort(ctx->stream, ctx->d_keys.p, ctx->d_tmp.p, cnt, total_bits, ctx->d_hist.p, &in_tmp, eb_, sizeof(eb_)));
+            }
+            if (dst) {
+                dst->resize(cnt);
+                if (cnt) CTX_CK(cudaMemcpyAsync(dst->data(), in_tmp ? ctx->d_tmp.p : ctx->d_keys.p, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            CTX_CK(cudaStreamSynchronize(ctx->stream));
+        }
+        CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CTX_CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); raster_ms += ms;
+    }
+    stl.evolve_ms = evolve_ms; stl.raster_ms = raster_ms;
+    if (status) *status = stl;
+    return AB200_OK;
+}
+
+extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes,
+                                        double t_continuous, int32_t max_events, int ignore_activations, int direction,
+                                        ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    if (!ctx || !reach_out || !evolve_out || (n_cells && (!loc || !boxes))) return AB200_E_ARGUMENT;
+    *reach_out = 0; *evolve_out = 0;
+    ab200_cellset* r = new ab200_cellset(); ab200_cellset* e = new ab200_cellset();
+    LapOut out; out.reach_keys = &r->keys; out.fin_keys = &e->keys; out.reach_boxes = 0; out.fin_boxes = 0;
+    int rc = run_batches(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
+    if (rc != AB200_OK) { delete r; delete e; return rc; }
+    *reach_out = r; *evolve_out = e;
+    return AB200_OK;
+}
+extern "C" int ab200_cellset_view(const ab200_cellset* cs, const uint64_t** keys, uint64_t* count) {
+    if (!cs) return AB200_E_ARGUMENT;
+    if (keys) *keys = cs->keys.empty() ? 0 : cs->keys.data();
+    if (count) *count = cs->keys.size();
+    return AB200_OK;
+}
+extern "C" void ab200_cellset_free(ab200_cellset* cs) { delete cs; }
+
+extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes,
+                                        double t_continuous, int32_t max_events, int ignore_activations, int direction,
+                                        ab200_boxlist** reach_out, ab200_boxlist** final_out, ab200_status* status) {
+    if (!ctx || !reach_out || !final_out || (n_cells && (!loc || !boxes))) return AB200_E_ARGUMENT;
+    *reach_out = 0; *final_out = 0;
+    ab200_boxlist* r = new ab200_boxlist(); ab200_boxlist* f = new ab200_boxlist();
+    LapOut out; out.reach_keys = 0; out.fin_keys = 0; out.reach_boxes = r; out.fin_boxes = f;
+    int rc = run_batches(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
+    if (rc != AB200_OK) { delete r; delete f; return rc; }
+    *reach_out = r; *final_out = f;
+    return AB200_OK;
+}
+extern "C" int ab200_boxlist_view(const ab200_boxlist* bl, const uint64_t** offsets, const double** boxes, const int32_t** locs) {
+    if (!bl) return AB200_E_ARGUMENT;
+    if (offsets) *offsets = bl->offsets.data();
+    if (boxes) *boxes = bl->boxes.empty() ? 0 : bl->boxes.data();
+    if (locs) *locs = bl->locs.empty() ? 0 : bl->locs.data();
+    return AB200_OK;
+}
+extern "C" void ab200_boxlist_free(ab200_boxlist* bl) { delete bl; }
+
+extern "C" int ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
+                                 double* h_out, double* bounds_out, int32_t* status_out) {
+    if (!ctx || !ctx->have_system || !loc || !boxes || !h_out || !bounds_out) return AB200_E_ARGUMENT;
+    CTX_CK(cudaSetDevice(ctx->device));
+    const int stride = AB200_BOX_STRIDE;
+    DevBuf<double> d_h, d_b;
+    CTX_CK(ctx->d_loc.ensure(n)); CTX_CK(ctx->d_box.ensure(n * stride)); CTX_CK(ctx->d_status.ensure(n));
+    cudaError_t e1 = d_h.ensure(n), e2 = d_b.ensure(n * stride);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { d_h.release(); d_b.release(); ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
+    cudaMemcpyAsync(ctx->d_loc.p, loc, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_box.p, boxes, n * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    char eb[256]; eb[0] = 0;
+    int rc = dev_launch_flow_bounds(ctx->stream, (int)n, ctx->d_loc.p, ctx->d_box.p, hmax, d_h.p, d_b.p, ctx->d_status.p, eb, sizeof(eb));
+    if (rc == 0) {
+        cudaMemcpyAsync(h_out, d_h.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(bounds_out, d_b.p, n * stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (status_out) cudaMemcpyAsync(status_out, ctx->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    d_h.release(); d_b.release();
+    if (rc != 0) { ctx->err = eb; return AB200_E_CUDA; }
+    if (es != cudaSuccess) { ctx->err = cudaGetErrorString(es); return AB200_E_CUDA; }
+    return AB200_OK;
+}
+
+extern "C" int ab200_probe_fp64(ab200_ctx* ctx, double* gflops) {
+    if (!ctx || !gflops) return AB200_E_ARGUMENT;
+    CTX_CK(cudaSetDevice(ctx->device));
+    const int blocks = 148 * 8, threads = 256, iters = 20000;
+    DevBuf<double> scratch;
+    if (scratch.ensure((size_t)blocks * threads) != cudaSuccess) { ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
+    char eb[256];
+    dev_fp64_peak(ctx->stream, scratch.p, blocks, threads, 100, eb, sizeof(eb));   // warm-up
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    dev_fp64_peak(ctx->stream, scratch.p, blocks, threads, iters, eb, sizeof(eb));
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    scratch.release();
+    if (es != cudaSuccess) { ctx->err = cudaGetErrorString(es); return AB200_E_CUDA; }
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    double ops = (double)blocks * threads * (double)iters * 16.0;   // 8 accumulators x (1 mul + 1 add), directed rounding
+    *gflops = ops / (ms * 1e-3) / 1e9;
+    return AB200_OK;
+}
+
+// the analyser entry points live in ab200_analyser.cu and use these two accessors
+const ab200::HostSystem* ab200_ctx_system(const ab200_ctx* ctx) { return ctx && ctx->have_system ? &ctx->sys : 0; }
+const ab200::KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return ctx && ctx->have_layout ? &ctx->K : 0; }
+void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg) { if (ctx) ctx->err = msg; }
+std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs) { return cs->keys; }
+ab200_cellset* ab200_cellset_new() { return new ab200_cellset(); }

@@ -1,0 +1,27 @@
+// ab200_device.h -- launcher prototypes between the C-ABI host code and ab200_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ab200_evolve.cuh"
+#include "ab200_grid.cuh"
+
+#define AB_EVOLVE_BLOCK 64
+
+namespace ab200 {
+int dev_upload_system(const SystemDesc* s, char* errbuf, int errlen);
+int dev_set_stack(size_t bytes, char* errbuf, int errlen);
+int dev_launch_evolve(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const EvolveParams& P,
+                      uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
+                      double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
+                      char* errbuf, int errlen);
+int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
+                           double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen);
+int dev_launch_fill(cudaStream_t st, uint64_t* p, size_t n, uint64_t v, char* errbuf, int errlen);
+int dev_launch_raster(cudaStream_t st, int n_cells, int max_boxes, const double* boxes, const int32_t* box_loc, const int32_t* n_boxes,
+                      const KeyLayout& K, int n_locs, uint64_t* table, uint64_t mask, unsigned long long* counters, char* errbuf, int errlen);
+int dev_launch_compact(cudaStream_t st, const uint64_t* table, size_t n, uint64_t* out, unsigned long long* count, char* errbuf, int errlen);
+int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned* hist, int* result_in_tmp,
+                   char* errbuf, int errlen);
+int dev_sort_tile();
+int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, char* errbuf, int errlen);
+}

@@ -1,0 +1,279 @@
+// ab200_kernels.cu -- sm_100a kernels for the grid-reachability lap:
+//   K_evolve    one frontier cell per lane; the whole working-set loop of ImageSetHybridEvolver::_evolution
+//               (ab200_evolve.cuh) in directed-rounding FP64. Per-cell scratch arenas live in HBM, interleaved
+//               word-by-word across the 32 lanes of a warp so lock-step model walks hit one 256-byte line.
+//   K_raster    per cell: outer_approximation of its reach / final boxes (ab200_grid.cuh) streamed straight into an
+//               open-addressing hash set of packed cell keys (dedupes the ~100x overlap between neighbouring cells
+//               before anything is sorted).
+//   K_compact / radix sort: unique keys -> sorted array, the form the host cell sets merge.
+// The op tapes of the system sit in __constant__ memory (SystemDesc), as every lane reads the same op at the same
+// time.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include "ab200_evolve.cuh"
+#include "ab200_grid.cuh"
+#include "ab200_device.h"
+
+namespace ab200 {
+
+__constant__ SystemDesc c_sys;
+
+// ---- evolve -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AB_EVOLVE_BLOCK)
+K_evolve(int n_cells, const int32_t* __restrict__ cell_loc, const double* __restrict__ cell_box, EvolveParams P,
+         uint64_t* __restrict__ arena, int arena_words,
+         double* __restrict__ reach, int32_t* __restrict__ reach_loc, int32_t* __restrict__ n_reach,
+         double* __restrict__ fin, int32_t* __restrict__ fin_loc, int32_t* __restrict__ n_fin,
+         int32_t* __restrict__ status, int32_t* __restrict__ steps, int32_t* __restrict__ peak) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const int warp = cell >> 5, lane = cell & 31;
+    Ctx c;
+    c.A.base = arena + (size_t)warp * (size_t)arena_words * 32 + lane;
+    c.A.top = 0; c.A.limit = arena_words; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    const int stride = 2 * AB_MAXN;
+    CellOutput O;
+    O.reach = reach + (size_t)cell * P.max_boxes * stride; O.reach_loc = reach_loc + (size_t)cell * P.max_boxes; O.n_reach = 0;
+    O.final_ = fin + (size_t)cell * P.max_boxes * stride; O.final_loc = fin_loc + (size_t)cell * P.max_boxes; O.n_final = 0;
+    O.stride = stride; O.steps = 0;
+    double box[2 * AB_MAXN];
+    for (int i = 0; i < stride; ++i) box[i] = cell_box[(size_t)cell * stride + i];
+    evolve_cell(c, c_sys, cell_loc[cell], box, P, O);
+    n_reach[cell] = O.n_reach; n_fin[cell] = O.n_final; status[cell] = c.status; steps[cell] = O.steps; peak[cell] = c.A.peak;
+}
+
+// ---- flow bounds facade (IntegratorInterface::flow_bounds parity, include/integrator_interface.h:45-62) -----------
+__global__ void K_flow_bounds(int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
+                              double* h_out, double* b_out, int32_t* status) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    const LocDesc& L = c_sys.loc[cell_loc[cell]];
+    Ivl r[AB_MAXN], b[AB_MAXN];
+    for (int i = 0; i < L.n; ++i) r[i] = ivl(cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i], cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i + 1]);
+    double h = flow_bounds(c, c_sys.ops, L.dyn, L.n, r, hmax, b);
+    h_out[cell] = h;
+    for (int i = 0; i < L.n; ++i) { b_out[(size_t)cell * 2 * AB_MAXN + 2 * i] = b[i].l; b_out[(size_t)cell * 2 * AB_MAXN + 2 * i + 1] = b[i].u; }
+    status[cell] = c.status;
+}
+
+// ---- rasterise + hash-set insert ------------------------------------------------------------------------------------
+#define AB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ void hash_insert(uint64_t* table, uint64_t mask, uint64_t key, unsigned long long* overflow) {
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    uint64_t slot = h & mask;
+    for (uint64_t probe = 0; probe <= mask; ++probe) {
+        uint64_t cur = table[slot];
+        if (cur == key) return;
+        if (cur == AB_EMPTY_KEY) {
+            uint64_t old = atomicCAS((unsigned long long*)&table[slot], (unsigned long long)AB_EMPTY_KEY, (unsigned long long)key);
+            if (old == AB_EMPTY_KEY || old == key) return;
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicAdd(overflow, 1ull);
+}
+
+__global__ void K_fill(uint64_t* p, size_t n, uint64_t v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stridex = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stridex) p[i] = v;
+}
+
+// One lane per cell: walks the cell's box list sequentially (the running root depends on the previous boxes), emits
+// the covered lattice cells into the hash set of the list (which = 0 reach, 1 final).
+__global__ void K_raster(int n_cells, int max_boxes, const double* __restrict__ boxes, const int32_t* __restrict__ box_loc,
+                         const int32_t* __restrict__ n_boxes, KeyLayout K, int n_locs,
+                         uint64_t* table, uint64_t mask, unsigned long long* counters /* [0]=overflow [1]=out of window [2]=emitted */) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const int stride = 2 * AB_MAXN;
+    const int nb = n_boxes[cell];
+    unsigned long long emitted = 0;
+    // a fresh running set per location, as outer_approximation builds one DenotableSet per location
+    for (int loc = 0; loc < n_locs; ++loc) {
+        const LocDesc& L = c_sys.loc[loc];
+        const int dim = L.n;
+        RunningSet rs; running_init(rs, dim);
+        for (int k = 0; k < nb; ++k) {
+            if (box_loc[(size_t)cell * max_boxes + k] != loc) continue;
+            const double* bp = boxes + ((size_t)cell * max_boxes + k) * stride;
+            Ivl b[AB_GRID_MAXN];
+            for (int i = 0; i < dim; ++i) b[i] = ivl(bp[2 * i], bp[2 * i + 1]);
+            long long lo[AB_GRID_MAXN], hi[AB_GRID_MAXN], idx[AB_GRID_MAXN];
+            if (!raster_box(L.grid_origin, L.grid_length, dim, K.acc, rs, b, lo, hi)) { atomicAdd(&counters[1], 1ull); continue; }
+            for (int i = 0; i < dim; ++i) idx[i] = lo[i];
+            for (;;) {
+                uint64_t key;
+                if (key_pack(K, loc, idx, &key)) { hash_insert(table, mask, key, &counters[0]); ++emitted; }
+                else atomicAdd(&counters[1], 1ull);
+                int d = dim - 1;
+                while (d >= 0) { if (++idx[d] <= hi[d]) break; idx[d] = lo[d]; --d; }
+                if (d < 0) break;
+            }
+        }
+    }
+    atomicAdd(&counters[2], emitted);
+}
+
+__global__ void K_compact(const uint64_t* __restrict__ table, size_t n, uint64_t* __restrict__ out, unsigned long long* count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stridex = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stridex) {
+        uint64_t k = table[i];
+        bool live = (k != AB_EMPTY_KEY);
+        unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+        // warp-aggregated append
+        int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (m) {
+            int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (live) out[base + __popc(m & ((1u << lane) - 1))] = k;
+        }
+    }
+}
+
+// ---- LSD radix sort (8-bit digits), stable, one warp per tile -------------------------------------------------------
+#define AB_SORT_TILE 2048
+__global__ void K_sort_hist(const uint64_t* __restrict__ in, size_t n, int shift, unsigned* __restrict__ hist /* [256][nblocks] */, int nblocks) {
+    __shared__ unsigned h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    size_t start = (size_t)blockIdx.x * AB_SORT_TILE, end = start + AB_SORT_TILE; if (end > n) end = n;
+    for (size_t i = start + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&h[(in[i] >> shift) & 0xFF], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[(size_t)i * nblocks + blockIdx.x] = h[i];
+}
+// exclusive scan of hist in (digit-major, block-minor) order; single block.
+__global__ void K_sort_scan(unsigned* hist, size_t total) {
+    __shared__ unsigned carry;
+    __shared__ unsigned buf[1024];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < total; base += 1024) {
+        size_t i = base + threadIdx.x;
+        unsigned v = (i < total) ? hist[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            unsigned t = (threadIdx.x >= off) ? buf[threadIdx.x - off] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += t;
+            __syncthreads();
+        }
+        unsigned incl = buf[threadIdx.x];
+        if (i < total) hist[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+}
+__global__ void K_sort_scatter(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, size_t n, int shift,
+                               const unsigned* __restrict__ hist, int nblocks) {
+    __shared__ unsigned offs[256];
+    for (int i = threadIdx.x; i < 256; i += 32) offs[i] = hist[(size_t)i * nblocks + blockIdx.x];
+    __syncwarp();
+    size_t start = (size_t)blockIdx.x * AB_SORT_TILE, end = start + AB_SORT_TILE; if (end > n) end = n;
+    const int lane = threadIdx.x;
+    for (size_t base = start; base < end; base += 32) {
+        size_t i = base + lane;
+        bool live = i < end;
+        uint64_t k = live ? in[i] : 0;
+        unsigned d = live ? (unsigned)((k >> shift) & 0xFF) : 0x100u + lane;   // distinct dummy digits for dead lanes
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned rank = __popc(peers & ((1u << lane) - 1));
+        unsigned pos = 0;
+        if (live) pos = offs[d] + rank;
+        __syncwarp();
+        if (live && rank == 0) offs[d] += __popc(peers);
+        __syncwarp();
+        if (live) out[pos] = k;
+    }
+}
+
+// ---- FP64 pipe peak probe (reported beside the roofline) -------------------------------------------------
+__global__ void K_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+    const double m = 1.0000001, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __dadd_ru(__dmul_rd(a0, m), b); a1 = __dadd_ru(__dmul_rd(a1, m), b); a2 = __dadd_ru(__dmul_rd(a2, m), b); a3 = __dadd_ru(__dmul_rd(a3, m), b);
+        a4 = __dadd_ru(__dmul_rd(a4, m), b); a5 = __dadd_ru(__dmul_rd(a5, m), b); a6 = __dadd_ru(__dmul_rd(a6, m), b); a7 = __dadd_ru(__dmul_rd(a7, m), b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---- host-callable launchers ------------------------------------------------------------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(errbuf, errlen, "%s: %s", #x, cudaGetErrorString(e_)); return (int)e_; } } while (0)
+
+int dev_upload_system(const SystemDesc* s, char* errbuf, int errlen) {
+    CK(cudaMemcpyToSymbol(c_sys, s, sizeof(SystemDesc)));
+    return 0;
+}
+int dev_set_stack(size_t bytes, char* errbuf, int errlen) {
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, bytes));
+    return 0;
+}
+int dev_launch_evolve(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const EvolveParams& P,
+                      uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
+                      double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
+                      char* errbuf, int errlen) {
+    if (n_cells == 0) return 0;
+    int blocks = (n_cells + AB_EVOLVE_BLOCK - 1) / AB_EVOLVE_BLOCK;
+    K_evolve<<<blocks, AB_EVOLVE_BLOCK, 0, st>>>(n_cells, cell_loc, cell_box, P, arena, arena_words, reach, reach_loc, n_reach, fin, fin_loc, n_fin, status, steps, peak);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
+                           double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen) {
+    if (n_cells == 0) return 0;
+    K_flow_bounds<<<(n_cells + 127) / 128, 128, 0, st>>>(n_cells, cell_loc, cell_box, hmax, h_out, b_out, status);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_fill(cudaStream_t st, uint64_t* p, size_t n, uint64_t v, char* errbuf, int errlen) {
+    if (n == 0) return 0;
+    K_fill<<<148 * 8, 256, 0, st>>>(p, n, v);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_raster(cudaStream_t st, int n_cells, int max_boxes, const double* boxes, const int32_t* box_loc, const int32_t* n_boxes,
+                      const KeyLayout& K, int n_locs, uint64_t* table, uint64_t mask, unsigned long long* counters, char* errbuf, int errlen) {
+    if (n_cells == 0) return 0;
+    K_raster<<<(n_cells + 127) / 128, 128, 0, st>>>(n_cells, max_boxes, boxes, box_loc, n_boxes, K, n_locs, table, mask, counters);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_compact(cudaStream_t st, const uint64_t* table, size_t n, uint64_t* out, unsigned long long* count, char* errbuf, int errlen) {
+    K_compact<<<148 * 8, 256, 0, st>>>(table, n, out, count);
+    CK(cudaGetLastError());
+    return 0;
+}
+// Sorts keys[0..n) ascending on the low `bits` bits; tmp and hist are scratch (hist: 256*ceil(n/TILE) unsigned).
+int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned* hist, int* result_in_tmp,
+                   char* errbuf, int errlen) {
+    *result_in_tmp = 0;
+    if (n <= 1) return 0;
+    int nblocks = (int)((n + AB_SORT_TILE - 1) / AB_SORT_TILE);
+    uint64_t* src = keys; uint64_t* dst = tmp;
+    for (int shift = 0; shift < bits; shift += 8) {
+        K_sort_hist<<<nblocks, 256, 0, st>>>(src, n, shift, hist, nblocks);
+        K_sort_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblocks);
+        K_sort_scatter<<<nblocks, 32, 0, st>>>(src, dst, n, shift, hist, nblocks);
+        CK(cudaGetLastError());
+        uint64_t* t = src; src = dst; dst = t;
+        *result_in_tmp ^= 1;
+    }
+    return 0;
+}
+int dev_sort_tile() { return AB_SORT_TILE; }
+int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, char* errbuf, int errlen) {
+    K_fp64_peak<<<blocks, threads, 0, st>>>(scratch, iters);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+} // namespace ab200

@@ -1,0 +1,156 @@
+// ab200_paving.cpp -- host cell sets (see ab200_paving.h).
+#include "ab200_paving.h"
+#include <algorithm>
+#include <iterator>
+
+namespace ab200 {
+
+void CellSet::adjoin(const std::vector<uint64_t>& o) {
+    if (o.empty()) return;
+    std::vector<uint64_t> r; r.reserve(keys.size() + o.size());
+    std::set_union(keys.begin(), keys.end(), o.begin(), o.end(), std::back_inserter(r));
+    keys.swap(r);
+}
+void CellSet::remove(const CellSet& o) {
+    std::vector<uint64_t> r; r.reserve(keys.size());
+    std::set_difference(keys.begin(), keys.end(), o.keys.begin(), o.keys.end(), std::back_inserter(r));
+    keys.swap(r);
+}
+void CellSet::restrict(const CellSet& o) {
+    std::vector<uint64_t> r; r.reserve(std::min(keys.size(), o.keys.size()));
+    std::set_intersection(keys.begin(), keys.end(), o.keys.begin(), o.keys.end(), std::back_inserter(r));
+    keys.swap(r);
+}
+
+Root CellSet::minimal_root() const {
+    const int dim = grid.dim;
+    long long lo[AB_GRID_MAXN], hi[AB_GRID_MAXN], idx[AB_GRID_MAXN];
+    bool first = true;
+    for (size_t k = 0; k < keys.size(); ++k) {
+        int l; key_unpack(K, keys[k], &l, idx);
+        for (int i = 0; i < dim; ++i) { if (first || idx[i] < lo[i]) lo[i] = idx[i]; if (first || idx[i] > hi[i]) hi[i] = idx[i]; }
+        first = false;
+    }
+    // start from the height-0 root containing the first corner and grow until both corners are inside
+    Root r; r.height = 0;
+    for (int i = 0; i < dim; ++i) { long long c = lo[i] >> K.acc; r.coord[i] = (int)c; }   // floor division by 2^acc
+    for (;;) {
+        int l2[AB_GRID_MAXN]; long long lower[AB_GRID_MAXN];
+        root_extent(r, dim, l2, lower);
+        bool ok = true;
+        for (int i = 0; i < dim; ++i) {
+            long long base = lower[i] * (1LL << K.acc), side = 1LL << (l2[i] + K.acc);
+            if (lo[i] < base || hi[i] >= base + side) ok = false;
+        }
+        if (ok) break;
+        root_grow(r, dim);
+    }
+    return r;
+}
+
+namespace {
+typedef unsigned __int128 Path;
+struct PathCell { Path p; };
+}
+
+// Path (sequence of left/right choices from the root to the leaf) of a cell given its root-relative leaf indices.
+static Path make_path(const Root& root, int dim, int acc, const long long* rel, const int* nsplit) {
+    int used[AB_GRID_MAXN];
+    for (int i = 0; i < dim; ++i) used[i] = 0;
+    int depth = root.height + dim * acc;
+    int s = splitting_coordinate(root.height, dim);
+    Path p = 0;
+    for (int d = 0; d < depth; ++d) {
+        int bit = (int)((rel[s] >> (nsplit[s] - 1 - used[s])) & 1);
+        used[s]++;
+        p = (p << 1) | (Path)bit;
+        s = (s + 1) % dim;
+    }
+    return p;
+}
+
+static void enum_rec(const std::vector<Path>& P, size_t lo, size_t hi, int level, int depth, int split, int dim,
+                     CellBox box, int mince_levels, std::vector<CellBox>& out) {
+    if (hi == lo) return;
+    size_t full = (depth - level >= 63) ? (size_t)-1 : ((size_t)1 << (depth - level));
+    if (hi - lo == full && level >= mince_levels) { out.push_back(box); return; }
+    if (level == depth) { out.push_back(box); return; }
+    // first index whose bit at this level is 1
+    int shift = depth - 1 - level;
+    size_t a = lo, b = hi;
+    while (a < b) { size_t m = (a + b) / 2; if ((P[m] >> shift) & 1) b = m; else a = m + 1; }
+    double l = box.b[2 * split], u = box.b[2 * split + 1];
+    double c = (l + u) / 2.0;                      // tail.cell[i].set_upper((lower+upper)/2.0)  bdd_set.cpp:833,877
+    CellBox left = box, right = box;
+    left.b[2 * split + 1] = c; right.b[2 * split] = c;
+    enum_rec(P, lo, a, level + 1, depth, (split + 1) % dim, dim, left, mince_levels, out);
+    enum_rec(P, a, hi, level + 1, depth, (split + 1) % dim, dim, right, mince_levels, out);
+}
+
+void CellSet::enumerate(std::vector<CellBox>& out, int mince_levels) const {
+    if (keys.empty()) return;
+    const int dim = grid.dim;
+    Root root = minimal_root();
+    int l2[AB_GRID_MAXN], ns[AB_GRID_MAXN]; long long lower[AB_GRID_MAXN];
+    root_extent(root, dim, l2, lower);
+    for (int i = 0; i < dim; ++i) ns[i] = l2[i] + K.acc;
+    std::vector<Path> P(keys.size());
+    long long idx[AB_GRID_MAXN], rel[AB_GRID_MAXN];
+    for (size_t k = 0; k < keys.size(); ++k) {
+        int l; key_unpack(K, keys[k], &l, idx);
+        for (int i = 0; i < dim; ++i) rel[i] = idx[i] - lower[i] * (1LL << K.acc);
+        P[k] = make_path(root, dim, K.acc, rel, ns);
+    }
+    std::sort(P.begin(), P.end());
+    Ivl rc[AB_GRID_MAXN];
+    root_box(grid.origin, grid.lengths, dim, root, rc);
+    CellBox rb;
+    for (int i = 0; i < dim; ++i) { rb.b[2 * i] = rc[i].l; rb.b[2 * i + 1] = rc[i].u; }
+    int depth = root.height + dim * K.acc;
+    enum_rec(P, 0, P.size(), 0, depth, splitting_coordinate(root.height, dim), dim, rb, mince_levels, out);
+}
+
+bool CellSet::adjoin_outer_approximation(const double* box) {
+    const int dim = grid.dim;
+    // The reference grows the CURRENT root of the set to cover the box, rasterises, then minimises; the leaf indices
+    // produced depend on the root only through the floating-point cell bounds.
+    RunningSet rs; running_init(rs, dim);
+    if (!keys.empty()) {
+        rs.root = minimal_root(); rs.empty = 0;
+        long long idx[AB_GRID_MAXN]; bool first = true;
+        for (size_t k = 0; k < keys.size(); ++k) {
+            int l; key_unpack(K, keys[k], &l, idx);
+            for (int i = 0; i < dim; ++i) { if (first || idx[i] < rs.lo[i]) rs.lo[i] = idx[i]; if (first || idx[i] > rs.hi[i]) rs.hi[i] = idx[i]; }
+            first = false;
+        }
+    }
+    Ivl b[AB_GRID_MAXN];
+    for (int i = 0; i < dim; ++i) b[i] = ivl(box[2 * i], box[2 * i + 1]);
+    long long lo[AB_GRID_MAXN], hi[AB_GRID_MAXN], idx[AB_GRID_MAXN];
+    if (!raster_box(grid.origin, grid.lengths, dim, K.acc, rs, b, lo, hi)) return true;
+    std::vector<uint64_t> add;
+    bool ok = true;
+    for (int i = 0; i < dim; ++i) idx[i] = lo[i];
+    for (;;) {
+        uint64_t key;
+        if (key_pack(K, loc, idx, &key)) add.push_back(key); else ok = false;
+        int d = dim - 1;
+        while (d >= 0) { if (++idx[d] <= hi[d]) break; idx[d] = lo[d]; --d; }
+        if (d < 0) break;
+    }
+    std::sort(add.begin(), add.end());
+    adjoin(add);
+    return ok;
+}
+
+bool CellSet::bounding_box(double* box) const {
+    std::vector<CellBox> cells; enumerate(cells);
+    if (cells.empty()) return false;
+    const int dim = grid.dim;
+    for (int i = 0; i < dim; ++i) { box[2 * i] = cells[0].b[2 * i]; box[2 * i + 1] = cells[0].b[2 * i + 1]; }
+    for (size_t k = 1; k < cells.size(); ++k)
+        for (int i = 0; i < dim; ++i) { box[2 * i] = std::min(box[2 * i], cells[k].b[2 * i]); box[2 * i + 1] = std::max(box[2 * i + 1], cells[k].b[2 * i + 1]); }
+    return true;
+}
+
+} // namespace ab200

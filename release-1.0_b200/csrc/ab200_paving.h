@@ -1,0 +1,60 @@
+// ab200_paving.h -- host-side cell sets on a dyadic grid (the counterpart of the reference's BDDTreeSet).
+//
+// A CellSet is a sorted, duplicate-free array of packed lattice keys (ab200_grid.cuh: KeyLayout) for ONE location,
+// i.e. exactly what the GPU sort emits, plus the grid. Union / difference / intersection are linear merges over the
+// sorted arrays (reference: BDDTreeSet::adjoin/remove/restrict = bdd_or / bddop_diff / bdd_and after
+// _equalize_root_cell, src/bdd_set.cpp:1472-1520). The root cell of the reference representation is canonical
+// (minimal covering dyadic cell of height >= 0, because every mutating operation ends with minimize_height), so it
+// is recomputed from the keys when cells have to be enumerated.
+//
+// Enumeration (reference: BDDTreeConstIterator / _compute_next_cell, src/bdd_set.cpp:800-891) yields the MAXIMAL
+// dyadic cells contained in the set, left-first, with boxes obtained by bisecting the root cell.
+#pragma once
+#include <vector>
+#include <stdint.h>
+#include "ab200_grid.cuh"
+
+namespace ab200 {
+
+struct GridDesc {
+    int dim;
+    double origin[AB_GRID_MAXN];
+    double lengths[AB_GRID_MAXN];
+};
+
+struct CellBox { double b[2 * AB_GRID_MAXN]; };
+
+class CellSet {
+  public:
+    CellSet() : loc(0) { grid.dim = 0; }
+    CellSet(const GridDesc& g, const KeyLayout& k, int location) : grid(g), K(k), loc(location) { }
+
+    GridDesc grid;
+    KeyLayout K;
+    int loc;
+    std::vector<uint64_t> keys;      // sorted ascending, unique
+
+    bool empty() const { return keys.empty(); }
+    size_t leaf_count() const { return keys.size(); }
+
+    void adjoin(const std::vector<uint64_t>& sorted_unique);
+    void adjoin(const CellSet& o) { adjoin(o.keys); }
+    void remove(const CellSet& o);
+    void restrict(const CellSet& o);
+
+    // adjoin_outer_approximation(Box,accuracy) (src/bdd_set.cpp:1548-1574), returns false if a cell fell outside
+    // the key window.
+    bool adjoin_outer_approximation(const double* box /* lo,hi per coordinate */);
+
+    // Minimal root (height>=0) covering all cells; undefined for the empty set.
+    Root minimal_root() const;
+    // Maximal dyadic cells, left-first. If mince_levels >= 0, cells are split down to at least that many levels
+    // below the root (BDDTreeSet::mince, src/bdd_set.cpp:1367-1369).
+    void enumerate(std::vector<CellBox>& out, int mince_levels = -1) const;
+    // BDDTreeSet::size(): number of maximal cells (src/bdd_set.cpp:117-148).
+    size_t size() const { std::vector<CellBox> v; enumerate(v); return v.size(); }
+    // bounding box of the set as the reference computes it (src/bdd_set.cpp:893-928): hull of the leaf boxes.
+    bool bounding_box(double* box) const;
+};
+
+} // namespace ab200

@@ -1,0 +1,14 @@
+#!/bin/sh
+# Regenerates the golden vectors from the compiled reference (oracle/_ref/ref_harness, built by `make -C oracle all
+# harness` from the unmodified sources under /root/reference). Run from the repository root in the build container.
+set -e
+H=oracle/_ref/ref_harness
+G=tests/golden
+# per-enclosure reach/final boxes + per-enclosure discretisation, van der Pol, accuracy 6, 24 cells spread over the domain
+$H vanderpol cells acc=6 mince=1 ncells=24 stride=1050 disc=1 out=$G/vanderpol_cells_acc6.txt
+# same at accuracy 3 (large cells: long models, early termination on enclosure size)
+$H vanderpol cells acc=3 init=1.0,1.3,1.0,1.6 disc=1 out=$G/vanderpol_cells_acc3.txt
+# analyser level: upper_reach_evolve over 2 laps, merged frontier between laps
+$H vanderpol reach acc=3 init=1.0,1.3,1.0,1.6 laps=2 out=$G/vanderpol_reach_acc3.txt
+$H vanderpol reach acc=4 init=-1.6,-1.3,0.3,0.8 laps=1 out=$G/vanderpol_reach_acc4.txt
+gzip -9 -f -n $G/vanderpol_cells_acc6.txt

@@ -1,0 +1,100 @@
+"""Parity of the CUDA path (through the C ABI) against golden vectors produced by the compiled reference.
+Integer / index work (cell sets) and every box endpoint must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+def _system():
+    return open(os.path.join(golden_io.GOLDEN, "vanderpol.sys")).read()
+
+
+def _evolver(pkg, dump, **settings):
+    ev = pkg.Evolver(_system(), settings=settings or None)
+    for name, g in dump["grid"].items():
+        ev.tune_settings(ev.location(name), g["maxstep"], g["refw"], g["origin"], g["lengths"])
+    ev.set_accuracy(dump["config"]["acc"])
+    return ev
+
+
+@pytest.mark.parametrize("name,arena", [("vanderpol_cells_acc6.txt.gz", 16384), ("vanderpol_cells_acc3.txt", 131072)])
+def test_reach_evolve_boxes_bit_exact(pkg, name, arena):
+    d = golden_io.load_dump(name)
+    ev = _evolver(pkg, d, arena_words=arena)
+    try:
+        dim = ev.dims[0]
+        locs = [ev.location(c["loc"]) for c in d["cells"]]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
+        (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, d["config"]["T"], d["config"]["events"], d["config"]["ignore_activations"])
+        for i, c in enumerate(d["cells"]):
+            mine_r = rbox[roff[i]:roff[i + 1], :2 * dim]
+            mine_f = fbox[foff[i]:foff[i + 1], :2 * dim]
+            assert golden_io.boxes_equal_bits(mine_r, c["reach"]), "reach boxes of cell %d" % c["id"]
+            assert golden_io.boxes_equal_bits(mine_f, c["final"]), "final boxes of cell %d" % c["id"]
+        assert ev.last_status.steps == sum(len(c["reach"]) for c in d["cells"])
+    finally:
+        ev.close()
+
+
+def _leaf_set(an, cellset):
+    return set(int(k) for k in cellset.keys)
+
+
+@pytest.mark.parametrize("name,init,laps", [("vanderpol_reach_acc3.txt", [1.0, 1.3, 1.0, 1.6], 2),
+                                              ("vanderpol_reach_acc4.txt", [-1.6, -1.3, 0.3, 0.8], 1)])
+def test_analyser_upper_reach_evolve_identical_cells(pkg, name, init, laps):
+    d = golden_io.load_dump(name)
+    an = pkg.HybridReachabilityAnalyser(_system(), [-3.0, 3.0, -3.0, 3.0], d["config"]["acc"], settings={"arena_words": 131072})
+    try:
+        assert an.lock_to_grid_time == d["config"]["lock"]
+        g = d["grid"]["loc"]
+        assert list(an.grid_lengths[0][:2]) == g["lengths"] and list(an.grid_origin[0][:2]) == g["origin"]
+        reach, evolve = an.upper_reach_evolve({"loc": init}, d["config"]["T"], d["config"]["events"])
+        _, rb = an.enumerate(reach)
+        _, eb = an.enumerate(evolve)
+        assert golden_io.boxes_equal_bits(rb, d["sets"]["reach"]["loc"])
+        assert golden_io.boxes_equal_bits(eb, d["sets"]["evolve"]["loc"])
+    finally:
+        an.close()
+
+
+def test_lap_cell_sets_match_union_of_reference_discretisations(pkg):
+    d = golden_io.load_dump("vanderpol_cells_acc3.txt")
+    ev = _evolver(pkg, d, arena_words=131072)
+    try:
+        dim = ev.dims[0]
+        locs = [ev.location(c["loc"]) for c in d["cells"]]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
+        reach, evolve = ev.upper_reach_evolve(locs, boxes, d["config"]["T"], d["config"]["events"])
+        # sortedness / uniqueness of the emitted keys
+        assert np.all(reach.keys[1:] > reach.keys[:-1]) and np.all(evolve.keys[1:] > evolve.keys[:-1])
+        # leaf-cell counts equal the area of the reference's merged cells
+        g = d["grid"]["loc"]; acc = d["config"]["acc"]
+        def leaves(cells):
+            tot = 0
+            for b in cells:
+                tot += round((b[1] - b[0]) / (g["lengths"][0] / 2 ** acc)) * round((b[3] - b[2]) / (g["lengths"][1] / 2 ** acc))
+            return tot
+        assert len(reach) == leaves(d["sets"]["ureach"]["loc"])
+        assert len(evolve) == leaves(d["sets"]["ufinal"]["loc"])
+    finally:
+        ev.close()
+
+
+def test_flow_bounds_facade(pkg):
+    d = golden_io.load_dump("vanderpol_cells_acc6.txt.gz")
+    ev = _evolver(pkg, d)
+    try:
+        dim = ev.dims[0]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
+        h, b, s = ev.flow_bounds([0] * len(d["cells"]), boxes, d["grid"]["loc"]["maxstep"])
+        assert np.all(s == 0) and np.all(h > 0) and np.all(h <= d["grid"]["loc"]["maxstep"])
+        # the bounding box contains the starting box (ARIADNE_ASSERT(subset(d,b)), src/taylor_calculus.cpp:125)
+        assert np.all(b[:, 0] <= boxes[:, 0]) and np.all(b[:, 1] >= boxes[:, 1])
+    finally:
+        ev.close()

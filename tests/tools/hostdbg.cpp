@@ -14,10 +14,12 @@
 #include <map>
 #include "../../release-1.0_b200/csrc/ab200_evolve.cuh"
 #include "../../release-1.0_b200/csrc/ab200_system.h"
+#include "../../release-1.0_b200/csrc/ab200_paving.h"
+#include <algorithm>
 
 using namespace ab200;
 
-struct RefCell { int loc; std::vector<double> box; std::vector<std::vector<double> > reach, fin; std::vector<int> rloc, floc; std::string err; };
+struct RefCell { std::vector<std::vector<double> > dreach, dfinal; int have_disc = 0; int loc; std::vector<double> box; std::vector<std::vector<double> > reach, fin; std::vector<int> rloc, floc; std::string err; };
 
 int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: hostdbg <system.sys> <cells dump> [maxcells] [verbose]\n"); return 2; }
@@ -32,10 +34,10 @@ int main(int argc, char** argv) {
     double T = 0; int events = 5, ignore_act = 0, chain = 0;
     std::map<std::string, int> locidx;
     for (size_t i = 0; i < hs.loc_names.size(); ++i) locidx[hs.loc_names[i]] = (int)i;
-    std::vector<RefCell> cells;
+    std::vector<RefCell> cells; std::vector<std::vector<double> >* dcur = 0; int ACC = 0;
     while (std::getline(df, line)) {
         std::istringstream in(line); std::string t; in >> t;
-        if (t == "config") { std::string k, name, v; in >> name; while (in >> k >> v) { if (k == "T") T = strtod(v.c_str(), 0); if (k == "events") events = atoi(v.c_str()); if (k == "chain") chain = atoi(v.c_str()); } }
+        if (t == "config") { std::string k, name, v; in >> name; while (in >> k >> v) { if (k == "T") T = strtod(v.c_str(), 0); if (k == "events") events = atoi(v.c_str()); if (k == "chain") chain = atoi(v.c_str()); if (k == "acc") ACC = atoi(v.c_str()); } }
         else if (t == "grid") {
             std::string k, name; in >> k >> name; int li = locidx[name]; LocDesc& L = hs.desc.loc[li];
             int n = 0; in >> k >> n;
@@ -49,6 +51,10 @@ int main(int argc, char** argv) {
         else if (t == "cell") { RefCell c; int id; std::string k, name; in >> id >> k >> name >> k; c.loc = locidx[name]; std::string v; while (in >> v) c.box.push_back(strtod(v.c_str(), 0)); cells.push_back(c); }
         else if (t == "r" || t == "f") { std::string name, v; in >> name; std::vector<double> b; while (in >> v) b.push_back(strtod(v.c_str(), 0)); if (t == "r") { cells.back().reach.push_back(b); cells.back().rloc.push_back(locidx[name]); } else { cells.back().fin.push_back(b); cells.back().floc.push_back(locidx[name]); } }
         else if (t == "x") { cells.back().err = line; }
+        else if (t == "dreach") { dcur = &cells.back().dreach; cells.back().have_disc = 1; }
+        else if (t == "dfinal") { dcur = &cells.back().dfinal; }
+        else if (t == "c" && dcur) { std::vector<double> b; std::string v; while (in >> v) b.push_back(strtod(v.c_str(), 0)); dcur->push_back(b); }
+        else if (t == "config") { }
     }
     printf("T=%a events=%d ignore_activations=%d chain=%d cells=%zu\n", T, events, ignore_act, chain, cells.size());
     const int ARENA = 1 << 20;
@@ -72,6 +78,31 @@ int main(int argc, char** argv) {
         if (ok) {
             for (int k = 0; k < O.n_reach && ok; ++k) for (int j = 0; j < 2 * n; ++j) if (memcmp(&reach[k * O.stride + j], &rc.reach[k][j], 8) != 0) { ok = false; first_bad = k; break; }
             for (int k = 0; k < O.n_final && ok; ++k) for (int j = 0; j < 2 * n; ++j) if (memcmp(&fin[k * O.stride + j], &rc.fin[k][j], 8) != 0) { ok = false; first_bad = 100000 + k; break; }
+        }
+        if (rc.have_disc && c.status == ST_OK) {
+            const LocDesc& L = hs.desc.loc[rc.loc];
+            KeyLayout K; K.dim = n; K.acc = ACC; K.loc_bits = 0; for (int i = 0; i < n; ++i) { K.bits[i] = 30; K.bias[i] = 1LL << 29; }
+            GridDesc g; g.dim = n; for (int i = 0; i < n; ++i) { g.origin[i] = L.grid_origin[i]; g.lengths[i] = L.grid_length[i]; }
+            for (int which = 0; which < 2; ++which) {
+                RunningSet rs; running_init(rs, n);
+                int cnt = which ? O.n_final : O.n_reach; const double* src = which ? fin.data() : reach.data();
+                std::vector<uint64_t> keys;
+                for (int k = 0; k < cnt; ++k) {
+                    Ivl b[AB_GRID_MAXN]; for (int i = 0; i < n; ++i) b[i] = ivl(src[k * O.stride + 2 * i], src[k * O.stride + 2 * i + 1]);
+                    long long lo[AB_GRID_MAXN], hi[AB_GRID_MAXN], idx[AB_GRID_MAXN];
+                    if (!raster_box(g.origin, g.lengths, n, ACC, rs, b, lo, hi)) continue;
+                    for (int i = 0; i < n; ++i) idx[i] = lo[i];
+                    for (;;) { uint64_t key; if (key_pack(K, 0, idx, &key)) keys.push_back(key); int d = n - 1; while (d >= 0) { if (++idx[d] <= hi[d]) break; idx[d] = lo[d]; --d; } if (d < 0) break; }
+                }
+                std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+                CellSet cs(g, K, 0); cs.keys = keys;
+                std::vector<CellBox> mine; cs.enumerate(mine);
+                const std::vector<std::vector<double> >& ref = which ? rc.dfinal : rc.dreach;
+                bool same = mine.size() == ref.size();
+                for (size_t k = 0; same && k < mine.size(); ++k) for (int j = 0; j < 2 * n; ++j) if (memcmp(&mine[k].b[j], &ref[k][j], 8)) same = false;
+                if (!same) { ok = false; printf("cell %zu %s discretisation differs: mine %zu cells (leaf %zu) ref %zu\n", ci, which ? "final" : "reach", mine.size(), keys.size(), ref.size());
+                    if (verbose >= 3) { for (size_t k = 0; k < mine.size(); ++k) printf("  mine %a %a %a %a\n", mine[k].b[0], mine[k].b[1], mine[k].b[2], mine[k].b[3]); for (size_t k = 0; k < ref.size(); ++k) printf("  ref  %a %a %a %a\n", ref[k][0], ref[k][1], ref[k][2], ref[k][3]); } }
+            }
         }
         if (!ok && verbose >= 2) {
             printf("cell %zu mismatching reach idx:", ci);
