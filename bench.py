@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- grid cells evolved / second for the upper_reach lap (BASELINE.json metric).
+
+A "step" is one lock-to-grid lap of HybridReachabilityAnalyser::upper_reach over one frontier: every frontier cell is
+evolved for lock_to_grid_time by the evolution kernel, its reach/final boxes are rasterised, de-duplicated and
+sorted on the device. Workload = BASELINE.json configs[2]: van der Pol (mu=1), Taylor orders 6/6, >= 10^5 initial grid
+cells (initial box [-2.2,2.2]x[-2.8,2.8] minced at accuracy 7 -> 101,400 cells), domain [-3,3]^2.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA)
+  python bench.py --impl reference ...                     the reference's own CPU analyser (oracle/_ref), host cores
+
+One JSON line is printed by rank 0. See DESIGN.md "Measurement" for the roofline arithmetic.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "grid cells evolved/sec (upper_reach)"
+UNIT = "cells/s"
+SYSTEM = "vanderpol"
+DOMAIN = [-3.0, 3.0, -3.0, 3.0]
+INIT = [-2.2, 2.2, -2.8, 2.8]
+ACC = 7
+EVENTS = 5
+
+
+def read_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self)
+        self.index = index; self.stop_flag = False; self.sm = []; self.max = 0; self.reasons = set()
+        self.daemon = True
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                o = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], timeout=5).decode()
+                p = [x.strip() for x in o.strip().split(",")]
+                self.sm.append(float(p[0])); self.max = float(p[1])
+                for n, v in zip(names, p[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max or None, "reasons": sorted(self.reasons)}
+
+
+def frontier_cells(pkg, an, n_cells):
+    """The minced initial frontier (uniform accuracy-ACC cells) exactly as the analyser enumerates it
+    (outer_intersection_with + BDDTreeSet::mince), optionally sub-sampled in warp-sized blocks."""
+    import numpy as np
+    initial = an.discretise({0: INIT})
+    _, cells = an.enumerate(initial, mince=True)
+    an.free(initial)
+    if n_cells and n_cells < cells.shape[0]:
+        nb = cells.shape[0] // 32
+        want = max(1, n_cells // 32)
+        sel = np.linspace(0, nb - 1, want).astype(np.int64)
+        idx = (sel[:, None] * 32 + np.arange(32)[None, :]).reshape(-1)
+        cells = cells[idx]
+    return np.ascontiguousarray(cells)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from conftest import load_pkg
+    pkg = load_pkg()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this benchmark has no CPU path; use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    system = open(os.path.join(ROOT, "tests", "golden", SYSTEM + ".sys")).read()
+    an = pkg.HybridReachabilityAnalyser(system, DOMAIN, ACC, device=local, settings={"arena_words": args.arena_words, "max_boxes": args.max_boxes, "hash_log2": 25})
+    ev = an.evolver
+    all_cells = frontier_cells(pkg, an, args.cells)
+    # frontier cells shard across ranks (independent units, no data-path collective until the key exchange)
+    per = (all_cells.shape[0] + world - 1) // world
+    per = (per + 31) // 32 * 32
+    mine = all_cells[rank * per:(rank + 1) * per]
+    n_mine = mine.shape[0]
+    boxes = pkg.pack_boxes(mine, 2)
+    locs = np.zeros((n_mine,), dtype=np.int32)
+    T = an.lock_to_grid_time
+    # tune exactly as the analyser's lap does (restriction bounding box)
+    an.lib.ab200_analyser_set_lock_time(an.handle, T)
+    import ctypes as C
+    # one throw-away analyser call on a tiny set performs the tuning upload (tune_evolver)
+    an.upper_reach_evolve({0: [1.0, 1.0 + 1e-3, 1.0, 1.0 + 1e-3]}, 1e-3, EVENTS)
+
+    def lap():
+        r, e = ev.upper_reach_evolve(locs, boxes, T, EVENTS)
+        return r, e, ev.last_status
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        lap()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    ev_ms = 0.0; ra_ms = 0.0; steps = 0; keys = 0; reach_n = 0
+    for _ in range(args.steps):
+        r, e, st = lap()
+        ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r)
+        if world > 1:
+            # newly reached cell ids are exchanged so every rank holds the lap's reach set
+            kt = torch.from_numpy(r.keys.astype(np.int64)).cuda()
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([kt.numel()], dtype=torch.int64, device="cuda"))
+            mx = int(max(int(s.item()) for s in sizes))
+            pad = torch.full((mx,), -1, dtype=torch.int64, device="cuda"); pad[:kt.numel()] = kt
+            out = [torch.empty(mx, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(out, pad)
+            allk = torch.cat([o[:int(s.item())] for o, s in zip(out, sizes)])
+            reach_n = int(torch.unique(allk).numel())
+    barrier()
+    t1 = time.perf_counter()
+    sampler.stop_flag = True; sampler.join()
+    wall = t1 - t0
+    times = torch.tensor([wall, ev_ms, ra_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_mine), float(steps), float(keys)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    wall, ev_ms, ra_ms = [float(x) for x in times.tolist()]
+    n_total, steps_total, keys_total = [float(x) for x in tot.tolist()]
+    e2e_value = n_total * args.steps / wall
+    dev_value = n_total * args.steps / ((ev_ms + ra_ms) * 1e-3)
+    # roofline of the dominant kernel (K_evolve). The per-cell loop is latency/FP64 work on per-cell scratch in HBM;
+    # the contract's "bound" keys are hbm|tensor, so the HBM view is reported: algorithmic bytes = the words each
+    # _evolution_step must move through its scratch (2 x arena peak words x 8 B per step).
+    peaks = read_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    arena_peak_words = st.arena_peak
+    alg_bytes_per_step = 2.0 * arena_peak_words * 8.0
+    achieved = (steps_total / args.steps) * alg_bytes_per_step / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
+    fp64 = None
+    try:
+        fp64 = ev.probe_fp64()
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": dev_value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak" if args.cells else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %d frontier cells (configs[2])" % (ACC, int(n_total)),
+                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "lap_time": T,
+                   "l2_policy": "per-cell scratch arenas (%.1f GB) exceed L2; no flush needed" % (n_total / world * args.arena_words * 8 / 1e9)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_mine * (80 + 4)), "d2h_bytes_per_step": int(8 * (reach_n + 0) + 24 * n_mine)},
+        "gpu_launches": int(args.steps * 9),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
+                     "traffic": None, "kernel": "K_evolve", "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
+                     "evolution_steps_per_s": steps_total / (ev_ms * 1e-3) if ev_ms > 0 else None,
+                     "fp64_directed_gflops_peak_measured": fp64, "peak_source": "measured" if peaks else "fallback"},
+        "reach_cells": reach_n,
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_cells)
+        print(json.dumps(line))
+    an.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(n_cells, threads=None):
+    """The reference's own CPU implementation (oracle/_ref/ref_harness, unmodified reference sources) on a bounded
+    sample of the same workload: `n_cells` frontier cells of the same minced frontier, one lap."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_harness missing"}
+    cores = threads or os.cpu_count() or 1
+    # run `cores` independent single-thread processes, each over its own stride of the frontier
+    per = max(1, n_cells // cores)
+    procs = []
+    t0 = time.perf_counter()
+    total_frontier = 101400
+    stride = max(1, total_frontier // (per * cores))
+    for k in range(cores):
+        cmd = [harness, SYSTEM, "cells", "acc=%d" % ACC, "mince=1", "ncells=%d" % per, "stride=%d" % (stride * cores), "offset=%d" % (k * stride),
+               "init=%s" % ",".join(str(x) for x in INIT), "out=/dev/null"]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for p in procs:
+        p.wait()
+    dt = time.perf_counter() - t0
+    done = per * cores
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%d of the %d frontier cells (stride %d), one lap each, %d single-thread processes of the compiled reference evolver, %.1f s" % (done, total_frontier, stride, cores, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(max(8, args.cpu_cells // 4))
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline(args.cpu_cells)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, bounded sample of the 101400-cell frontier" % ACC,
+                       "system": SYSTEM, "accuracy": ACC},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cells", type=int, default=0, help="subsample the frontier (0 = the full 101,400 cells)")
+    ap.add_argument("--cpu-cells", type=int, default=32)
+    ap.add_argument("--arena-words", type=int, default=12288)
+    ap.add_argument("--max-boxes", type=int, default=320)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,10 @@ void ab200_analyser_destroy(ab200_analyser* an);
 int  ab200_analyser_info(const ab200_analyser* an, double* lock_to_grid_time, double* grid_origin /* [L][MAX_DIM] */,
                          double* grid_lengths, double* max_step /* [L] */);
 int  ab200_analyser_set_lock_time(ab200_analyser* an, double lock_to_grid_time);
+/* ReachabilityRestriction::outer_intersection_with(initial set) (src/reachability_restriction.cpp:522-535): the
+ * discretised initial set the first lap starts from. */
+int  ab200_analyser_discretise(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                               ab200_cellset** out);
 /* upper_reach_evolve (src/reachability_analyser.cpp:309-377). initial: n_init boxes with their locations.
  * mince != 0 enumerates the initial set as uniform cells (BDDTreeSet::mince) instead of merged cells. */
 int  ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,

@@ -194,7 +194,7 @@ int main(int argc, char** argv) {
         int mince=geti(kv,"mince",0);
         if(mince) { for(HybridDenotableSet::locations_iterator li=initial.locations_begin(); li!=initial.locations_end(); ++li) li->second.mince(c.acc); }
         std::list<HEncl> encl=to_enclosures(initial);
-        int ncells=geti(kv,"ncells",1<<30); int stride=geti(kv,"stride",1);
+        int ncells=geti(kv,"ncells",1<<30); int stride=geti(kv,"stride",1); int offset=geti(kv,"offset",0);
         bool ignore_act=geti(kv,"ignore_activations",c.chain?1:0)!=0;
         HybridTime ht(T,c.chain?1:c.events);
         fprintf(out,"frontier %lu ignore_activations %d\n",(unsigned long)encl.size(),(int)ignore_act);
@@ -204,7 +204,7 @@ int main(int argc, char** argv) {
         // is printed (the enclosure's bounding box is the range of scalings(box), which is a few ulps wider).
         HybridDenotableSet::const_iterator cell_it=initial.begin();
         for(std::list<HEncl>::const_iterator it=encl.begin(); it!=encl.end() && done<ncells; ++it,++k,++cell_it) {
-            if(k%stride) continue;
+            if(k<offset || (k-offset)%stride) continue;
             ++done;
             fprintf(out,"cell %d loc %s box",k,it->first.name().c_str()); dump_box(out,cell_it->second); fprintf(out,"\n");
             try {

@@ -29,7 +29,7 @@ EXPORTS = [
     "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
-    "ab200_analyser_outer_chain_reach", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64",
+    "ab200_analyser_outer_chain_reach", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library():
     lib.ab200_analyser_upper_reach_evolve.restype = C.c_int
     lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), P(vp), P(Status)]
     lib.ab200_analyser_outer_chain_reach.restype = C.c_int
+    lib.ab200_analyser_discretise.argtypes = [vp, u64, P(i32), P(dbl), P(vp)]; lib.ab200_analyser_discretise.restype = C.c_int
     lib.ab200_analyser_cells_evolved.argtypes = [vp]; lib.ab200_analyser_cells_evolved.restype = i64
     lib.ab200_analyser_enumerate.argtypes = [vp, vp, C.c_int, P(u64), P(i32), P(dbl)]; lib.ab200_analyser_enumerate.restype = C.c_int
     lib.ab200_probe_fp64.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64.restype = C.c_int
@@ -310,6 +311,13 @@ class HybridReachabilityAnalyser(object):
         rc = self.lib.ab200_analyser_outer_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), C.byref(r), C.byref(st))
         self.last_status = st
         self.evolver._check(rc)
+        return self._wrap(r)
+
+    def discretise(self, initial_set):
+        """The discretised initial set (outer_intersection_with) as a CellSet."""
+        locs, boxes = self._initial(initial_set)
+        r = C.c_void_p()
+        self.evolver._check(self.lib.ab200_analyser_discretise(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), C.byref(r)))
         return self._wrap(r)
 
     def cells_evolved(self):

@@ -214,7 +214,7 @@ static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, doubl
     std::vector<int32_t> locs; std::vector<double> boxes;
     for (int l = 0; l < an->n_locs; ++l) {
         std::vector<CellBox> cells;
-        frontier[l].enumerate(cells, mince ? an->dim * an->accuracy : -1);
+        frontier[l].enumerate(cells, mince ? (1 << 30) : -1);   // mince(accuracy): down to the leaves (bdd_set.cpp:1881-1883)
         for (size_t k = 0; k < cells.size(); ++k) {
             locs.push_back(l);
             size_t o = boxes.size(); boxes.resize(o + AB200_BOX_STRIDE, 0.0);
@@ -254,6 +254,15 @@ static int discretise_initial(ab200_analyser* an, uint64_t n_init, const int32_t
     return AB200_OK;
 }
 
+static ab200_cellset* to_cellset(const HybridCells& h);
+extern "C" int ab200_analyser_discretise(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, ab200_cellset** out) {
+    if (!an || !out || (n_init && (!loc || !boxes))) return AB200_E_ARGUMENT;
+    HybridCells initial;
+    int rc = discretise_initial(an, n_init, loc, boxes, initial);
+    if (rc != AB200_OK) return rc;
+    *out = to_cellset(initial);
+    return AB200_OK;
+}
 static ab200_cellset* to_cellset(const HybridCells& h) { ab200_cellset* cs = ab200_cellset_new(); join_keys(h, ab200_cellset_keys(cs)); return cs; }
 
 extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
@@ -332,7 +341,7 @@ extern "C" int ab200_analyser_enumerate(const ab200_analyser* an, const ab200_ce
     split_keys(an, ab200_cellset_keys(const_cast<ab200_cellset*>(cs)), h);
     uint64_t n = 0;
     for (int l = 0; l < an->n_locs; ++l) {
-        std::vector<CellBox> cells; h[l].enumerate(cells, mince ? an->dim * an->accuracy : -1);
+        std::vector<CellBox> cells; h[l].enumerate(cells, mince ? (1 << 30) : -1);
         for (size_t k = 0; k < cells.size(); ++k) {
             if (locs) locs[n] = l;
             if (boxes) { for (int i = 0; i < AB200_BOX_STRIDE; ++i) boxes[n * AB200_BOX_STRIDE + i] = (i < 2 * an->dim) ? cells[k].b[i] : 0.0; }
