@@ -237,6 +237,7 @@ AB_HD TM ph_load(Ctx& c, int slot, int as, Acc acc) {
 // _compose2 (src/taylor_model.cpp:3187-3240): r[i] = x[i] o ys, nx models in xas=nys variables.
 // Results are written to r[0..nx) packed from the arena top recorded on entry.
 AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r) {
+    AB_SECTION(1);
     const int m0 = c.A.top;
     const int as = ys[0].as;
     const Acc acc0 = ys[0].acc;
@@ -264,25 +265,32 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     }
     const int mr = c.A.top;     // results start here; slid down to m0 at the end
     for (int i = 0; i < nx; ++i) {
-        int ri = c.A.top;
+        const int ri = c.A.top;
         TM ra = tm_begin(c, as, acc0);
         ra.e = x[i].e;
-        for (int t = 0; t < x[i].n; ++t) {
-            Key a = tm_key(c, x[i], t);
-            double cv = tm_val(c, x[i], t);
+        for (int t0 = 0; t0 < x[i].n; t0 += AB_MAXSTREAMS) {
+            const int B = (x[i].n - t0 < AB_MAXSTREAMS) ? (x[i].n - t0) : AB_MAXSTREAMS;
+            TM st[AB_MAXSTREAMS];
             c.A.top = ra.off + ra.n * AB_TW;
-            int mt = c.A.top;
-            TM tt = tm_const(c, as, cv, acc0);           // t=c
-            for (int j = 0; j < nys; ++j) {
-                int e = key_get(a, j);
-                if (e > 0) {
-                    TM pw = ph_load(c, tab[j] + 2 * e, as, ys[j].acc);
-                    TM pr = tm_mul(c, tt, pw, ys[j].acc);
-                    tm_slide(c, pr, mt);
-                    tt = pr;
+            for (int b = 0; b < B; ++b) {
+                const int t = t0 + b;
+                Key a = tm_key(c, x[i], t);
+                double cv = tm_val(c, x[i], t);
+                const int mt = c.A.top;
+                TM tt = tm_const(c, as, cv, acc0);           // t=c
+                for (int j = 0; j < nys; ++j) {
+                    int e = key_get(a, j);
+                    if (e > 0) {
+                        TM pw = ph_load(c, tab[j] + 2 * e, as, ys[j].acc);
+                        TM pr = tm_mul(c, tt, pw, ys[j].acc);
+                        tm_slide(c, pr, mt);
+                        tt = pr;
+                    }
                 }
+                c.A.top = tt.off + tt.n * AB_TW;
+                st[b] = tt;
             }
-            TM s = tm_add2(c, ra, tt, acc0);              // r[i]+=t
+            TM s = tm_add_many(c, ra, st, B, acc0);          // r[i]+=t for the B terms, in order
             tm_slide(c, s, ri);
             ra = s;
         }
@@ -295,6 +303,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
 
 // _split1(tm,k,true/false) src/taylor_model.cpp:2497-2544. Result at the arena top recorded on entry.
 AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
+    AB_SECTION(2);
     const int m0 = c.A.top;
     const int deg = tm_degree(c, tm);
     TM r = tm_copy(c, tm);
@@ -318,20 +327,30 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     const int mr = c.A.top;
     TM res = tm_begin(c, tm.as, tm.acc);
     res.e = r.e;
+    TM st[AB_MAXSTREAMS];
+    int B = 0;
     for (int i = 0; i <= deg; ++i) {
         for (int j = i; j <= deg; ++j) {
             // sf=bin(j,i), sign flipped for the lower half when j-i is odd
             long long bn_ = 1; for (int q = 1; q <= i; ++q) bn_ = bn_ * (long long)(j - i + q) / (long long)q;
             double sf = (double)bn_;
             if (!upper && ((j - i) % 2 == 1)) sf = -sf;
-            TM bj; bj.off = boff[j]; bj.n = bn[j]; bj.as = tm.as; bj.e = 0.0; bj.acc = acc_default();
-            c.A.top = res.off + res.n * AB_TW;
-            TM t = tm_copy(c, bj);
-            tm_scal(c, t, sf);                         // ary[j]*sf
-            TM s = tm_add2(c, res, t, tm.acc);          // r+=...
-            tm_slide(c, s, mr);
-            res = s;
-            for (int q = 0; q < bj.n; ++q) { Key a = tm_key(c, bj, q); key_inc(a, k, 1); tm_set_key(c, bj, q, a); }
+            if (B == 0) c.A.top = res.off + res.n * AB_TW;
+            // ary[j]*sf with the k-exponent of ary[j] already incremented i times
+            TM t = tm_begin(c, tm.as, acc_default());
+            for (int q = 0; q < bn[j]; ++q) {
+                Key a; for (int w = 0; w < AB_KW; ++w) a.w[w] = aw(c, boff[j] + q * AB_TW + w);
+                key_inc(a, k, i);
+                tm_append(c, t, a, u2d(aw(c, boff[j] + q * AB_TW + AB_KW)));
+            }
+            tm_scal(c, t, sf);
+            st[B++] = t;
+            if (B == AB_MAXSTREAMS || (i == deg && j == deg)) {
+                TM s = tm_add_many(c, res, st, B, tm.acc);   // r+=... for the B (i,j) pairs, in loop order
+                tm_slide(c, s, mr);
+                res = s;
+                B = 0;
+            }
         }
     }
     tm_slide(c, res, m0);
@@ -373,6 +392,7 @@ AB_HDN TM tm_partial_evaluate_one(Ctx& c, const TM& x, int k) {
 // variables (domain ibx x [0,h]) packed at the arena top recorded on entry; dom[] receives the flow domain.
 AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const Ivl* ibx, double h, const Ivl* bb,
                        int order, TM* flow, Ivl* dom) {
+    AB_SECTION(3);
     const int m0 = c.A.top;
     const double EPS = 1e-16;
     Ivl bx[AB_MAXN];
@@ -448,6 +468,7 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
 // time = ScalarTaylorFunction::variable([-h,h],0)  (src/hybrid_evolver-image.cpp:764-765; src/taylor_set.cpp:366-369).
 // set: n models in p variables. Output: n models in p+1 variables at the arena top recorded on entry.
 AB_HDN void flow_apply(Ctx& c, const TM* flow, int n, const Ivl* dom, const TM* set, int p, double h, TM* out) {
+    AB_SECTION(4);
     const int m0 = c.A.top;
     TM ys[AB_MAXN + 1];
     for (int i = 0; i < n; ++i) {
@@ -478,6 +499,7 @@ AB_HD void compose_at(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* ou
 // integration_step(flow_set_model, scaled_time_model) src/taylor_calculus.cpp:234-245
 // flow_set: n models in p+1 variables; tau: model in p variables. Output: n models in p variables, accuracy spacial.
 AB_HDN void integration_step(Ctx& c, const TM* flow_set, int n, int p, const TM& tau, Acc spacial, TM* out) {
+    AB_SECTION(5);
     const int m0 = c.A.top;
     TM ys[AB_MAXARGS + 1];
     for (int j = 0; j < p; ++j) ys[j] = tm_variable(c, p, j);      // BaseModelType::variables(p): default accuracy
@@ -489,6 +511,7 @@ AB_HDN void integration_step(Ctx& c, const TM* flow_set, int n, int p, const TM&
 
 // reachability_step(flow_set_model, t0, t1) src/taylor_calculus.cpp:248-267. Output: n models in p+1 variables.
 AB_HDN void reachability_step(Ctx& c, const TM* flow_set, int n, int p, const TM& t0, const TM& t1, Acc spacial, TM* out) {
+    AB_SECTION(6);
     const int m0 = c.A.top;
     TM ys[AB_MAXARGS + 1];
     for (int j = 0; j <= p; ++j) { ys[j] = tm_variable(c, p + 1, j); ys[j].acc = spacial; }

@@ -103,7 +103,16 @@ struct Ctx {
     int status;    // sticky first error
 };
 
+#ifdef AB_COUNT_ACCESS
+extern long long g_aw_count;
+extern long long g_sec[16];
+struct SecTimer { int id; long long start; SecTimer(int i) : id(i), start(g_aw_count) { } ~SecTimer() { g_sec[id] += g_aw_count - start; } };
+#define AB_SECTION(id) SecTimer sec_timer_##id(id)
+AB_HD uint64_t& aw(Ctx& c, int i) { ++g_aw_count; return c.A.base[(size_t)i * AB_STRIDE]; }
+#else
+#define AB_SECTION(id)
 AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[(size_t)i * AB_STRIDE]; }
+#endif
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 
 struct TM {
@@ -253,6 +262,55 @@ AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) {
     c.rnd = RN;
     return r;
 }
+// r' = ((r + t[0]) + t[1]) + ... + t[B-1] with the exact semantics of B successive _add2 calls
+// (src/taylor_model.cpp:487-530), computed in ONE pass over r: a (B+1)-way merge in key order in which, for every
+// key, the streams are folded in index order. Each stream keeps its own upward-rounded gap sum te[s] (visited in key
+// order, as in the reference), and the error chain e <- up(up(e + t[s].e) + te[s]/2) is applied in stream order.
+// A coefficient that cancels to exactly zero is dropped, as _add2 does, and a later stream re-creates the term.
+// This removes the O(#streams x |r|) re-copying of the accumulator that dominates the reference's _mul4/_compose2.
+#define AB_MAXSTREAMS 8
+AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
+    TM out = tm_begin(c, r.as, acc);
+    int ri = 0;
+    int ti[AB_MAXSTREAMS];
+    double te[AB_MAXSTREAMS];
+    Key hk[AB_MAXSTREAMS];
+    bool live[AB_MAXSTREAMS];
+    for (int s = 0; s < B; ++s) { ti[s] = 0; te[s] = 0.0; live[s] = t[s].n > 0; if (live[s]) hk[s] = tm_key(c, t[s], 0); }
+    bool rlive = r.n > 0;
+    Key rk = key_zero();
+    if (rlive) rk = tm_key(c, r, 0);
+    for (;;) {
+        // smallest key among the heads
+        bool any = rlive;
+        Key mk = rk;
+        for (int s = 0; s < B; ++s) if (live[s] && (!any || key_less(hk[s], mk))) { mk = hk[s]; any = true; }
+        if (!any) break;
+        bool present = false;
+        double cur = 0.0;
+        if (rlive && key_eq(rk, mk)) {
+            cur = tm_val(c, r, ri); present = true;
+            ++ri; rlive = ri < r.n; if (rlive) rk = tm_key(c, r, ri);
+        }
+        for (int s = 0; s < B; ++s) {
+            if (!live[s] || !key_eq(hk[s], mk)) continue;
+            double tv = tm_val(c, t[s], ti[s]);
+            if (present) {
+                double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
+                te[s] = add_ru(te[s], add_ru(u, ml));
+                cur = add_rn(cur, tv);
+                if (cur == 0) present = false;
+            } else { cur = tv; present = true; }
+            ++ti[s]; live[s] = ti[s] < t[s].n; if (live[s]) hk[s] = tm_key(c, t[s], ti[s]);
+        }
+        if (present) tm_append(c, out, mk, cur);
+    }
+    double e = r.e;
+    for (int s = 0; s < B; ++s) e = add_ru(add_ru(e, t[s].e), te[s] / 2);
+    out.e = e;
+    c.rnd = RN;
+    return out;
+}
 // neg (src/taylor_model.cpp:1530-1537): fresh default accuracy
 AB_HDN TM tm_neg(Ctx& c, const TM& x) {
     TM r = tm_begin(c, x.as, acc_default());
@@ -275,28 +333,59 @@ AB_HD TM tm_plus_assign(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x,
 
 // _mul4 (src/taylor_model.cpp:763-824) with accuracy `acc` (operator* passes the RIGHT operand's, :1265-1268).
 // Result at the arena top.
+// Product stream b of a block is x-term (i0+b) times y; its head is the next product that is not discarded.
+// Discarded products are folded into the stream's truncation error while the cursor advances, in y order, exactly
+// as the inner loop of _mul4 does.
+#define AB_MULSTREAMS 16
 AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
-    int m = c.A.top;
+    AB_SECTION(0);
+    const int m = c.A.top;
     TM r = tm_begin(c, x.as, acc);          // empty accumulator at m
-    for (int i = 0; i < x.n; ++i) {
-        Key xa = tm_key(c, x, i);
-        double xv = tm_val(c, x, i), axv = dabs(xv);
-        double tte = 0.0;
-        c.A.top = r.off + r.n * AB_TW;
-        TM t = tm_begin(c, x.as, acc);
-        for (int j = 0; j < y.n; ++j) {
-            Key ta = key_add(xa, tm_key(c, y, j));
-            double yv = tm_val(c, y, j);
-            double tv = mul_rn(xv, yv);
-            if (acc_discard(acc, ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
-            else tm_append(c, t, ta, tv);
+    for (int i0 = 0; i0 < x.n; i0 += AB_MULSTREAMS) {
+        const int B = (x.n - i0 < AB_MULSTREAMS) ? (x.n - i0) : AB_MULSTREAMS;
+        Key xa[AB_MULSTREAMS], hk[AB_MULSTREAMS];
+        double xv[AB_MULSTREAMS], hv[AB_MULSTREAMS], tte[AB_MULSTREAMS], te[AB_MULSTREAMS];
+        int cur[AB_MULSTREAMS];        // index of the y term AFTER the head; y.n+1 when the stream is exhausted
+        bool live[AB_MULSTREAMS];
+        for (int b = 0; b < B; ++b) {
+            xa[b] = tm_key(c, x, i0 + b); xv[b] = tm_val(c, x, i0 + b); tte[b] = 0.0; te[b] = 0.0; cur[b] = 0; live[b] = false;
         }
-        // t.error()=tte+(tte/2): evaluated in the mode left by the inner loop (upward; ambient if y is empty)
-        int md = (y.n > 0) ? RU : c.rnd;
-        t.e = add_m(md, tte, div_m(md, tte, 2.0));
-        TM s = tm_add2(c, r, t, acc);
-        tm_slide(c, s, m);
-        r = s;
+        // advance stream b to its next surviving product
+        #define AB_ADVANCE(b) do { live[b] = false; const double axv_ = dabs(xv[b]); \
+            while (cur[b] < y.n) { Key ta_ = key_add(xa[b], tm_key(c, y, cur[b])); double yv_ = tm_val(c, y, cur[b]); ++cur[b]; \
+                double tv_ = mul_rn(xv[b], yv_); \
+                if (acc_discard(acc, ta_, tv_)) tte[b] = add_ru(tte[b], mul_ru(axv_, dabs(yv_))); \
+                else { hk[b] = ta_; hv[b] = tv_; live[b] = true; break; } } } while (0)
+        for (int b = 0; b < B; ++b) AB_ADVANCE(b);
+        c.A.top = r.off + r.n * AB_TW;
+        TM out = tm_begin(c, x.as, acc);
+        int ri = 0; bool rlive = r.n > 0; Key rk = key_zero(); if (rlive) rk = tm_key(c, r, 0);
+        for (;;) {
+            bool any = rlive; Key mk = rk;
+            for (int b = 0; b < B; ++b) if (live[b] && (!any || key_less(hk[b], mk))) { mk = hk[b]; any = true; }
+            if (!any) break;
+            bool present = false; double cv = 0.0;
+            if (rlive && key_eq(rk, mk)) { cv = tm_val(c, r, ri); present = true; ++ri; rlive = ri < r.n; if (rlive) rk = tm_key(c, r, ri); }
+            for (int b = 0; b < B; ++b) {
+                if (!live[b] || !key_eq(hk[b], mk)) continue;
+                const double tv = hv[b];
+                if (present) {
+                    double u = add_ru(cv, tv), ml = sub_ru(-cv, tv);
+                    te[b] = add_ru(te[b], add_ru(u, ml));
+                    cv = add_rn(cv, tv);
+                    if (cv == 0) present = false;
+                } else { cv = tv; present = true; }
+                AB_ADVANCE(b);
+            }
+            if (present) tm_append(c, out, mk, cv);
+        }
+        #undef AB_ADVANCE
+        // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
+        double e = r.e;
+        for (int b = 0; b < B; ++b) { double tev = add_ru(tte[b], tte[b] / 2); e = add_ru(add_ru(e, tev), te[b] / 2); }
+        out.e = e;
+        tm_slide(c, out, m);
+        r = out;
     }
     double xs = 0, ys = 0;
     for (int i = 0; i < x.n; ++i) xs = add_ru(xs, dabs(tm_val(c, x, i)));

@@ -18,6 +18,10 @@
 #include <algorithm>
 
 using namespace ab200;
+#ifdef AB_COUNT_ACCESS
+long long ab200::g_aw_count = 0;
+long long ab200::g_sec[16] = {0};
+#endif
 
 struct RefCell { std::vector<std::vector<double> > dreach, dfinal; int have_disc = 0; int loc; std::vector<double> box; std::vector<std::vector<double> > reach, fin; std::vector<int> rloc, floc; std::string err; };
 
@@ -127,5 +131,10 @@ int main(int argc, char** argv) {
         } else if (verbose) printf("cell %zu ok: %d reach, %d final, %d steps\n", ci, O.n_reach, O.n_final, O.steps);
     }
     printf("cells compared %d, mismatching %d, steps %ld, arena peak words %d\n", done, bad, total_steps, peak);
+#ifdef AB_COUNT_ACCESS
+    printf("arena word accesses: %lld (%.0f per step)\n", g_aw_count, (double)g_aw_count / total_steps);
+    const char* names[] = {"tm_mul(incl)", "tm_compose(incl)", "tm_split", "flow_model(incl)", "flow_apply(incl)", "integration_step", "reachability_step"};
+    for (int i = 0; i < 7; ++i) printf("  %-22s %.0f per step\n", names[i], (double)g_sec[i] / total_steps);
+#endif
     return bad ? 1 : 0;
 }
