@@ -126,10 +126,10 @@ def run_ours(args):
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t0 = time.perf_counter()
-    ev_ms = 0.0; ra_ms = 0.0; steps = 0; keys = 0; reach_n = 0
+    ev_ms = 0.0; ra_ms = 0.0; steps = 0; keys = 0; reach_n = 0; launches = 0
     for _ in range(args.steps):
         r, e, st = lap()
-        ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r)
+        ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r); launches += st.launches
         if world > 1:
             # newly reached cell ids are exchanged so every rank holds the lap's reach set
             kt = torch.from_numpy(r.keys.astype(np.int64)).cuda()
@@ -174,7 +174,7 @@ def run_ours(args):
                    "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "lap_time": T,
                    "l2_policy": "per-cell scratch arenas (%.1f GB) exceed L2; no flush needed" % (n_total / world * args.arena_words * 8 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_mine * (80 + 4)), "d2h_bytes_per_step": int(8 * (reach_n + 0) + 24 * n_mine)},
-        "gpu_launches": int(args.steps * 9),
+        "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
                      "traffic": None, "kernel": "K_evolve", "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
@@ -184,7 +184,7 @@ def run_ours(args):
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_cells)
+            line["cpu_baseline"] = cpu_baseline(args.cpu_cells or 3 * (os.cpu_count() or 1))
         print(json.dumps(line))
     an.close()
     if world > 1:
@@ -192,28 +192,22 @@ def run_ours(args):
 
 
 def cpu_baseline(n_cells, threads=None):
-    """The reference's own CPU implementation (oracle/_ref/ref_harness, unmodified reference sources) on a bounded
-    sample of the same workload: `n_cells` frontier cells of the same minced frontier, one lap."""
+    """The reference's own CPU implementation at the same seam as ab200_upper_reach_evolve:
+    UpperReachEvolveWorker::get_result() (include/workers.h:51-81) of the compiled, unmodified reference
+    (oracle/_ref/ref_harness worker), with all host threads, on a strided sample of the same minced frontier."""
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(harness):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_harness missing"}
     cores = threads or os.cpu_count() or 1
-    # run `cores` independent single-thread processes, each over its own stride of the frontier
-    per = max(1, n_cells // cores)
-    procs = []
-    t0 = time.perf_counter()
+    env = dict(os.environ); env["ORACLE_THREADS"] = str(cores)
     total_frontier = 101400
-    stride = max(1, total_frontier // (per * cores))
-    for k in range(cores):
-        cmd = [harness, SYSTEM, "cells", "acc=%d" % ACC, "mince=1", "ncells=%d" % per, "stride=%d" % (stride * cores), "offset=%d" % (k * stride),
-               "init=%s" % ",".join(str(x) for x in INIT), "out=/dev/null"]
-        procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
-    for p in procs:
-        p.wait()
-    dt = time.perf_counter() - t0
-    done = per * cores
-    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d of the %d frontier cells (stride %d), one lap each, %d single-thread processes of the compiled reference evolver, %.1f s" % (done, total_frontier, stride, cores, dt)}
+    stride = max(1, total_frontier // n_cells)
+    cmd = [harness, SYSTEM, "worker", "acc=%d" % ACC, "ncells=%d" % n_cells, "stride=%d" % stride, "init=%s" % ",".join(str(x) for x in INIT)]
+    o = subprocess.check_output(cmd, env=env).decode()
+    f = [l for l in o.splitlines() if l.startswith("worker")][0].split()
+    secs = float(f[2]); done = int(f[4]); thr = int(f[-1])
+    return {"value": done / secs, "unit": UNIT, "cores": thr, "kind": "reference",
+            "sample": "UpperReachEvolveWorker::get_result() of the compiled reference on %d of the %s frontier cells (stride %d), one lap, %d threads, %.1f s" % (done, f[6], stride, thr, secs)}
 
 
 def run_reference(args):
@@ -221,12 +215,13 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    for _ in range(args.warmup):
-        cpu_baseline(max(8, args.cpu_cells // 4))
+    n = args.cpu_cells or 3 * (os.cpu_count() or 1)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(max(os.cpu_count() or 1, n // 3))
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
-        last = cpu_baseline(args.cpu_cells)
+        last = cpu_baseline(n)
         vals.append(last["value"])
     wall = time.perf_counter() - t0
     v = sum(vals) / len(vals)
@@ -246,7 +241,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", type=int, default=0, help="subsample the frontier (0 = the full 101,400 cells)")
-    ap.add_argument("--cpu-cells", type=int, default=32)
+    ap.add_argument("--cpu-cells", type=int, default=0, help="CPU sample size (0 = 3 cells per host thread)")
     ap.add_argument("--arena-words", type=int, default=12288)
     ap.add_argument("--max-boxes", type=int, default=320)
     ap.add_argument("--no-cpu-baseline", action="store_true")

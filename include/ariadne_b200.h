@@ -65,6 +65,7 @@ typedef struct ab200_status {
     int32_t arena_peak;       /* largest per-cell scratch use, words */
     double  evolve_ms;        /* device time of the evolution kernel(s) */
     double  raster_ms;        /* device time of rasterise + compact + sort */
+    int64_t launches;         /* kernels launched by this call */
 } ab200_status;
 
 void ab200_default_settings(ab200_settings* s);

@@ -26,6 +26,7 @@
 #include "hybrid_evolver-image.h"
 #include "logging.h"
 #include <boost/thread.hpp>
+#include "workers.h"
 #include "watertank-hysteresis.h"
 #include "springs.h"
 #include "boost-converter.h"
@@ -224,6 +225,31 @@ int main(int argc, char** argv) {
             }
         }
         if(geti(kv,"disc",0)) { fprintf(out,"union\n"); dump_set(out,"ureach",ureach); dump_set(out,"ufinal",ufinal); }
+        return 0;
+    }
+
+    if(mode=="worker") {
+        // The batch seam itself: UpperReachEvolveWorker::get_result() (include/workers.h:51-81,102-153) over a strided
+        // sample of the minced first-lap frontier, with boost::thread::hardware_concurrency() worker threads
+        // (ORACLE_THREADS overrides), including the mutex-protected discretisation. This is the CPU baseline of bench.py.
+        ReachabilityRestriction restriction(c.domain,grid,c.acc);
+        HybridDenotableSet initial=restriction.outer_intersection_with(c.initial);
+        if(geti(kv,"mince",1)) { for(HybridDenotableSet::locations_iterator li=initial.locations_begin(); li!=initial.locations_end(); ++li) li->second.mince(c.acc); }
+        std::list<HEncl> all=to_enclosures(initial);
+        int ncells=geti(kv,"ncells",64); int stride=geti(kv,"stride",1); int offset=geti(kv,"offset",0);
+        std::list<HEncl> sample; int k=0;
+        for(std::list<HEncl>::const_iterator it=all.begin(); it!=all.end() && (int)sample.size()<ncells; ++it,++k) { if(k<offset || (k-offset)%stride) continue; sample.push_back(*it); }
+        unsigned long n=sample.size();
+        boost::shared_ptr<EvolverInterface<HybridAutomatonInterface,HEncl> > evp(new ImageSetHybridEvolver(c.sys));
+        { ReachabilityRestriction rr(c.domain,grid,c.acc); evp->tune_settings(rr.bounding_box(),grid,c.acc); }
+        HybridTime ht(T,c.chain?1:c.events);
+        bool ignore_act=c.chain; ContinuousEvolutionDirection dir=DIRECTION_FORWARD;
+        std::chrono::steady_clock::time_point w0=std::chrono::steady_clock::now();
+        UpperReachEvolveWorker worker(evp,sample,ht,grid,c.acc,ignore_act,dir);
+        std::pair<HybridDenotableSet,HybridDenotableSet> res=worker.get_result();
+        double ws=std::chrono::duration<double>(std::chrono::steady_clock::now()-w0).count();
+        fprintf(out,"worker seconds %.6f cells %lu frontier %lu reach_cells %lu evolve_cells %lu threads %u\n",ws,n,(unsigned long)all.size(),
+                (unsigned long)res.first.size(),(unsigned long)res.second.size(),boost::thread::hardware_concurrency());
         return 0;
     }
 

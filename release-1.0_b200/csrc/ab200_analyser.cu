@@ -226,7 +226,7 @@ static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, doubl
     ab200_cellset *r = 0, *e = 0; ab200_status st; memset(&st, 0, sizeof(st));
     int rc = ab200_upper_reach_evolve(an->ctx, locs.size(), locs.data(), boxes.data(), T, events, ignore_activations, 0, &r, &e, &st);
     if (st_acc) {
-        st_acc->steps += st.steps; st_acc->keys_emitted += st.keys_emitted; st_acc->evolve_ms += st.evolve_ms; st_acc->raster_ms += st.raster_ms;
+        st_acc->steps += st.steps; st_acc->launches += st.launches; st_acc->keys_emitted += st.keys_emitted; st_acc->evolve_ms += st.evolve_ms; st_acc->raster_ms += st.raster_ms;
         st_acc->arena_peak = std::max(st_acc->arena_peak, st.arena_peak);
         if (rc != AB200_OK) { st_acc->code = st.code ? st.code : rc; st_acc->cell = st.cell; }
     }

@@ -183,7 +183,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
     if (want_keys) {
         CTX_CK(ctx->d_table.ensure(table_n * 2));
         CTX_CK(ctx->d_counters.ensure(8));
-        DEV_CK(dev_launch_fill(ctx->stream, ctx->d_table.p, table_n * 2, ~0ull, eb_, sizeof(eb_)));
+        DEV_CK(dev_launch_fill(ctx->stream, ctx->d_table.p, table_n * 2, ~0ull, eb_, sizeof(eb_))); stl.launches += 1;
         CTX_CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     }
     float evolve_ms = 0, raster_ms = 0;
@@ -203,7 +203,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         DEV_CK(dev_launch_evolve(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, P, ctx->d_arena.p, S.arena_words,
                                  ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_))); stl.launches += 1;
         CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         std::vector<int32_t> h_status(nb), h_steps(nb), h_peak(nb), h_nreach(nb), h_nfin(nb);
         CTX_CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -247,7 +247,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             DEV_CK(dev_launch_raster(ctx->stream, nb, S.max_boxes, ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->K, ctx->sys.desc.n_locs,
                                      ctx->d_table.p, mask, ctx->d_counters.p, eb_, sizeof(eb_)));
             DEV_CK(dev_launch_raster(ctx->stream, nb, S.max_boxes, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p, ctx->K, ctx->sys.desc.n_locs,
-                                     ctx->d_table.p + table_n, mask, ctx->d_counters.p + 3, eb_, sizeof(eb_)));
+                                     ctx->d_table.p + table_n, mask, ctx->d_counters.p + 3, eb_, sizeof(eb_))); stl.launches += 2;
             CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
             CTX_CK(cudaStreamSynchronize(ctx->stream));
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); raster_ms += ms;
@@ -265,7 +265,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             std::vector<uint64_t>* dst = which ? out.fin_keys : out.reach_keys;
             CTX_CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, sizeof(unsigned long long), ctx->stream));
             CTX_CK(ctx->d_keys.ensure(table_n)); CTX_CK(ctx->d_tmp.ensure(table_n));
-            DEV_CK(dev_launch_compact(ctx->stream, ctx->d_table.p + (size_t)which * table_n, table_n, ctx->d_keys.p, ctx->d_counters.p + 6, eb_, sizeof(eb_)));
+            DEV_CK(dev_launch_compact(ctx->stream, ctx->d_table.p + (size_t)which * table_n, table_n, ctx->d_keys.p, ctx->d_counters.p + 6, eb_, sizeof(eb_))); stl.launches += 1;
             unsigned long long cnt = 0;
             CTX_CK(cudaMemcpyAsync(&cnt, ctx->d_counters.p + 6, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
             CTX_CK(cudaStreamSynchronize(ctx->stream));
@@ -273,7 +273,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             if (cnt > 1) {
                 size_t nblocks = (cnt + dev_sort_tile() - 1) / dev_sort_tile();
                 CTX_CK(ctx->d_hist.ensure(256 * nblocks));
-                DEV_CK(dev_radix_sort(ctx->stream, ctx->d_keys.p, ctx->d_tmp.p, cnt, total_bits, ctx->d_hist.p, &in_tmp, eb_, sizeof(eb_)));
+                DEV_CK(dev_radix_sort(ctx->stream, ctx->d_keys.p, ctx->d_tmp.p, cnt, total_bits, ctx->d_hist.p, &in_tmp, eb_, sizeof(eb_))); stl.launches += 3 * ((total_bits + 7) / 8);
             }
             if (dst) {
                 dst->resize(cnt);
