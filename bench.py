@@ -99,9 +99,11 @@ def run_ours(args):
     ev = an.evolver
     all_cells = frontier_cells(pkg, an, args.cells)
     # frontier cells shard across ranks (independent units, no data-path collective until the key exchange)
-    per = (all_cells.shape[0] + world - 1) // world
-    per = (per + 31) // 32 * 32
-    mine = all_cells[rank * per:(rank + 1) * per]
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ab200_parallel", os.path.join(ROOT, "release-1.0_b200", "parallel.py"))
+    par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
+    a0, a1 = par.shard_frontier(all_cells.shape[0], rank, world)
+    mine = all_cells[a0:a1]
     n_mine = mine.shape[0]
     boxes = pkg.pack_boxes(mine, 2)
     locs = np.zeros((n_mine,), dtype=np.int32)
@@ -131,16 +133,8 @@ def run_ours(args):
         r, e, st = lap()
         ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r); launches += st.launches
         if world > 1:
-            # newly reached cell ids are exchanged so every rank holds the lap's reach set
-            kt = torch.from_numpy(r.keys.astype(np.int64)).cuda()
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([kt.numel()], dtype=torch.int64, device="cuda"))
-            mx = int(max(int(s.item()) for s in sizes))
-            pad = torch.full((mx,), -1, dtype=torch.int64, device="cuda"); pad[:kt.numel()] = kt
-            out = [torch.empty(mx, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(out, pad)
-            allk = torch.cat([o[:int(s.item())] for o, s in zip(out, sizes)])
-            reach_n = int(torch.unique(allk).numel())
+            # newly reached cell ids are exchanged so that every rank holds the lap's reach set (NCCL all-gather)
+            reach_n = int(par.exchange_keys(r.keys, dist, torch.device("cuda", local)).shape[0])
     barrier()
     t1 = time.perf_counter()
     sampler.stop_flag = True; sampler.join()

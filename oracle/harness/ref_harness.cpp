@@ -124,7 +124,7 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
         c.sys=getSpringsSystem();
         c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(5,0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0)));
         c.initial=HybridBoundedConstraintSet(c.sys.state_space());
-        c.initial[DiscreteLocation("free")]=box_from(kv,"init",Box(5,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,3.0,3.0));
+        c.initial[DiscreteLocation("free1,free2")]=box_from(kv,"init",Box(5,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,3.0,3.0));
         c.acc=geti(kv,"acc",3); c.T=getd(kv,"T",0.0);
     } else if(name=="boost") {
         c.sys=getBoostConverter();
@@ -137,6 +137,76 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
     }
     if(kv.count("chain")) c.chain=geti(kv,"chain",0)!=0;
     return c;
+}
+
+// ---- system -> op-tape text (release-1.0_b200/csrc/ab200_system.h) through the public expression API ----
+static void emit_tape(FILE* f, const RealExpression& e, const std::map<std::string,int>& var_index) {
+    Operator op=e.op();
+    if(op==VAR) {
+        std::stringstream ss; ss<<e; std::string name=ss.str();
+        std::map<std::string,int>::const_iterator it=var_index.find(name);
+        if(it==var_index.end()) { fprintf(stderr,"unknown variable '%s'\n",name.c_str()); exit(3); }
+        fprintf(f," V%d",it->second); return;
+    }
+    if(op==CNST || op==PAR) {
+        Interval v=evaluate(e,Vector<Interval>(1));
+        fprintf(f," C%a,%a",v.lower(),v.upper()); return;
+    }
+    List<RealExpression> sub=e.subexpressions();
+    for(uint i=0;i<sub.size();++i) emit_tape(f,sub[i],var_index);
+    const char* name=0;
+    switch(op) {
+        case ADD: name="ADD"; break; case SUB: name="SUB"; break; case MUL: name="MUL"; break; case DIV: name="DIV"; break;
+        case NEG: name="NEG"; break; case POS: name="POS"; break; case REC: name="REC"; break; case SQR: name="SQR"; break;
+        case SQRT: name="SQRT"; break; case EXP: name="EXP"; break; case LOG: name="LOG"; break; case SIN: name="SIN"; break;
+        case COS: name="COS"; break; case TAN: name="TAN"; break; case ABS: name="ABS"; break; case MAX: name="MAX"; break; case MIN: name="MIN"; break;
+        default: fprintf(stderr,"unsupported operator %d\n",int(op)); exit(3);
+    }
+    fprintf(f," %s",name);
+}
+
+static void dump_system(FILE* f, const HybridIOAutomaton& sys) {
+    HybridSpace space=sys.state_space();
+    std::map<std::string,int> loc_index; int L=0;
+    for(HybridSpace::const_iterator it=space.begin(); it!=space.end(); ++it) loc_index[it->first.name()]=L++;
+    fprintf(f,"system %s\nlocations %d\n",sys.name().c_str(),L);
+    for(HybridSpace::const_iterator it=space.begin(); it!=space.end(); ++it) {
+        DiscreteLocation loc=it->first;
+        RealSpace cs=sys.continuous_state_space(loc);
+        std::map<std::string,int> var_index;
+        for(uint i=0;i<cs.size();++i) var_index[cs.variable(i).name()]=i;
+        Set<DiscreteEvent> events=sys.events(loc);
+        fprintf(f,"location %d %s n %u events %lu\n",loc_index[loc.name()],loc.name().c_str(),(unsigned)cs.size(),(unsigned long)events.size());
+        for(std::list<DiscreteIOMode>::const_iterator m=sys.modes().begin(); m!=sys.modes().end(); ++m) {
+            if(!(m->location()==loc)) continue;
+            uint i=0;
+            for(std::map<RealVariable,RealExpression>::const_iterator d=m->dynamics().begin(); d!=m->dynamics().end(); ++d,++i) {
+                fprintf(f,"  dyn %u",i); emit_tape(f,d->second,var_index); fprintf(f," ;\n"); }
+        }
+        int k=0;
+        for(Set<DiscreteEvent>::const_iterator e=events.begin(); e!=events.end(); ++e,++k) {
+            EventKind kind=sys.event_kind(loc,*e);
+            const char* kn = kind==INVARIANT?"invariant":kind==URGENT?"urgent":"permissive";
+            int target = kind==INVARIANT ? loc_index[loc.name()] : loc_index[sys.target(loc,*e).name()];
+            fprintf(f,"  event %d %s kind %s target %d id %d\n",k,e->name().c_str(),kn,target,k);
+            if(kind==INVARIANT) {
+                for(std::list<DiscreteIOMode>::const_iterator m=sys.modes().begin(); m!=sys.modes().end(); ++m) {
+                    if(!(m->location()==loc)) continue;
+                    std::map<DiscreteEvent,RealExpression>::const_iterator inv=m->invariants().find(*e);
+                    fprintf(f,"    guard"); emit_tape(f,inv->second,var_index); fprintf(f," ;\n");
+                }
+            } else {
+                for(std::list<DiscreteIOTransition>::const_iterator t=sys.transitions().begin(); t!=sys.transitions().end(); ++t) {
+                    if(!(t->source()==loc && t->event()==*e)) continue;
+                    fprintf(f,"    guard"); emit_tape(f,t->activation(),var_index); fprintf(f," ;\n");
+                    uint i=0;
+                    for(std::map<RealVariable,RealExpression>::const_iterator r=t->reset().begin(); r!=t->reset().end(); ++r,++i) {
+                        fprintf(f,"    reset %u",i); emit_tape(f,r->second,var_index); fprintf(f," ;\n"); }
+                    break;
+                }
+            }
+        }
+    }
 }
 
 static void dump_box(FILE* f, const Box& b) { for(uint i=0;i<b.size();++i) fprintf(f," %a %a",b[i].lower(),b[i].upper()); }
@@ -157,6 +227,8 @@ int main(int argc, char** argv) {
     std::string mode(argv[2]);
     FILE* out=stdout; if(kv.count("out")) out=fopen(kv["out"].c_str(),"w");
     int verb=geti(kv,"verb",0);
+
+    if(mode=="system") { dump_system(out,c.sys); return 0; }
 
     HybridReachabilityAnalyser analyser(c.sys,c.domain,c.acc);
     analyser.verbosity=verb;

@@ -13,7 +13,7 @@
 #pragma once
 #include "ab200_tm.cuh"
 
-namespace ab200 {
+namespace ab200 { inline namespace AB_VARIANT {
 
 #ifdef AB_DEBUG_DUMP
 void ab_debug_dump(Ctx& c, const char* name, int idx, const TM& t);   // provided by tests/tools/hoststep.cpp
@@ -626,4 +626,4 @@ AB_HDN int kuhn_recondition(Ctx& c, TM* set, int n, int p, int* discarded) {
     return nd;
 }
 
-} // namespace ab200
+} } // namespace ab200

@@ -11,7 +11,7 @@
 #include "ab200_series.cuh"
 #include "ab200_events.cuh"
 
-namespace ab200 {
+namespace ab200 { inline namespace AB_VARIANT {
 
 struct EvolveParams {
     double T;                  // continuous time of the lap (HybridTime::continuous_time)
@@ -219,4 +219,4 @@ AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box
     }
 }
 
-} // namespace ab200
+} } // namespace ab200

@@ -29,7 +29,13 @@
 #include <string.h>
 #endif
 
-namespace ab200 {
+// The kernel sources are compiled once per MultiIndex width (AB_KW key words); each build lives in its own inline
+// namespace so both can be linked into one library.
+#ifndef AB_VARIANT
+#define AB_VARIANT kw1
+#endif
+
+namespace ab200 { inline namespace AB_VARIANT {
 
 enum { RN = 0, RU = 1, RD = 2 };
 
@@ -224,4 +230,4 @@ AB_HD Ivl ivl_sqrt(Ivl i, int* st) { return ivl(sqrt_m(RD, i.l, st), sqrt_m(RU, 
 AB_HD bool ivl_subset(Ivl a, Ivl b) { return a.l >= b.l && a.u <= b.u; }
 AB_HD bool ivl_disjoint(Ivl a, Ivl b) { return a.l > b.u || a.u < b.l; }
 
-} // namespace ab200
+} } // namespace ab200

@@ -12,7 +12,7 @@
 #pragma once
 #include "ab200_fp.cuh"
 
-namespace ab200 {
+namespace ab200 { inline namespace AB_VARIANT {
 
 #define AB_GRID_MAXN 5
 
@@ -180,4 +180,4 @@ AB_HD void key_unpack(const KeyLayout& K, uint64_t key, int* loc, long long* idx
     *loc = (int)key;
 }
 
-} // namespace ab200
+} } // namespace ab200

@@ -14,33 +14,9 @@
 #include "ab200_grid.cuh"
 #include "ab200_device.h"
 
-namespace ab200 {
+namespace ab200 { inline namespace AB_VARIANT {
 
-__constant__ SystemDesc c_sys;
-
-// ---- evolve -------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AB_EVOLVE_BLOCK)
-K_evolve(int n_cells, const int32_t* __restrict__ cell_loc, const double* __restrict__ cell_box, EvolveParams P,
-         uint64_t* __restrict__ arena, int arena_words,
-         double* __restrict__ reach, int32_t* __restrict__ reach_loc, int32_t* __restrict__ n_reach,
-         double* __restrict__ fin, int32_t* __restrict__ fin_loc, int32_t* __restrict__ n_fin,
-         int32_t* __restrict__ status, int32_t* __restrict__ steps, int32_t* __restrict__ peak) {
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    const int warp = cell >> 5, lane = cell & 31;
-    Ctx c;
-    c.A.base = arena + (size_t)warp * (size_t)arena_words * 32 + lane;
-    c.A.top = 0; c.A.limit = arena_words; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
-    const int stride = 2 * AB_MAXN;
-    CellOutput O;
-    O.reach = reach + (size_t)cell * P.max_boxes * stride; O.reach_loc = reach_loc + (size_t)cell * P.max_boxes; O.n_reach = 0;
-    O.final_ = fin + (size_t)cell * P.max_boxes * stride; O.final_loc = fin_loc + (size_t)cell * P.max_boxes; O.n_final = 0;
-    O.stride = stride; O.steps = 0;
-    double box[2 * AB_MAXN];
-    for (int i = 0; i < stride; ++i) box[i] = cell_box[(size_t)cell * stride + i];
-    evolve_cell(c, c_sys, cell_loc[cell], box, P, O);
-    n_reach[cell] = O.n_reach; n_fin[cell] = O.n_final; status[cell] = c.status; steps[cell] = O.steps; peak[cell] = c.A.peak;
-}
+#include "ab200_evolve_kernel.inc"
 
 // ---- flow bounds facade (IntegratorInterface::flow_bounds parity, include/integrator_interface.h:45-62) -----------
 __global__ void K_flow_bounds(int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
@@ -209,10 +185,7 @@ __global__ void K_fp64_peak(double* out, int iters) {
 // ---- host-callable launchers ------------------------------------------------------------------------------------------
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(errbuf, errlen, "%s: %s", #x, cudaGetErrorString(e_)); return (int)e_; } } while (0)
 
-int dev_upload_system(const SystemDesc* s, char* errbuf, int errlen) {
-    CK(cudaMemcpyToSymbol(c_sys, s, sizeof(SystemDesc)));
-    return 0;
-}
+int dev_upload_system(const SystemDesc* s, char* errbuf, int errlen) { return dev_upload_system_v(s, errbuf, errlen); }
 int dev_set_stack(size_t bytes, char* errbuf, int errlen) {
     CK(cudaDeviceSetLimit(cudaLimitStackSize, bytes));
     return 0;
@@ -221,11 +194,7 @@ int dev_launch_evolve(cudaStream_t st, int n_cells, const int32_t* cell_loc, con
                       uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
                       double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
                       char* errbuf, int errlen) {
-    if (n_cells == 0) return 0;
-    int blocks = (n_cells + AB_EVOLVE_BLOCK - 1) / AB_EVOLVE_BLOCK;
-    K_evolve<<<blocks, AB_EVOLVE_BLOCK, 0, st>>>(n_cells, cell_loc, cell_box, P, arena, arena_words, reach, reach_loc, n_reach, fin, fin_loc, n_fin, status, steps, peak);
-    CK(cudaGetLastError());
-    return 0;
+    return dev_launch_evolve_v(st, n_cells, cell_loc, cell_box, &P, arena, arena_words, reach, reach_loc, n_reach, fin, fin_loc, n_fin, status, steps, peak, errbuf, errlen);
 }
 int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
                            double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen) {
@@ -276,4 +245,4 @@ int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int
     return 0;
 }
 
-} // namespace ab200
+} } // namespace ab200

@@ -30,7 +30,7 @@
 #endif
 #endif
 
-namespace ab200 {
+namespace ab200 { inline namespace AB_VARIANT {
 
 #define AB_TW (AB_KW + 1)   // words per term
 #define AB_MAXARGS (AB_KW == 1 ? 7 : 15)
@@ -538,4 +538,4 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
     return true;
 }
 
-} // namespace ab200
+} } // namespace ab200

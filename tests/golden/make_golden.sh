@@ -6,6 +6,8 @@ H=oracle/_ref/ref_harness
 G=tests/golden
 # per-enclosure reach/final boxes + per-enclosure discretisation, van der Pol, accuracy 6, 24 cells spread over the domain
 $H vanderpol cells acc=6 mince=1 ncells=24 stride=1050 disc=1 out=$G/vanderpol_cells_acc6.txt
+# system descriptions (op tapes) extracted from the reference automata through the public expression API
+for s in vanderpol bouncingball watertank springs boost; do $H $s system out=$G/$s.sys; done
 # same at accuracy 3 (large cells: long models, early termination on enclosure size)
 $H vanderpol cells acc=3 init=1.0,1.3,1.0,1.6 disc=1 out=$G/vanderpol_cells_acc3.txt
 # analyser level: upper_reach_evolve over 2 laps, merged frontier between laps
