@@ -270,6 +270,7 @@ int main(int argc, char** argv) {
         int ncells=geti(kv,"ncells",1<<30); int stride=geti(kv,"stride",1); int offset=geti(kv,"offset",0);
         bool ignore_act=geti(kv,"ignore_activations",c.chain?1:0)!=0;
         HybridTime ht(T,c.chain?1:c.events);
+        evolver.verbosity=geti(kv,"everb",0);
         fprintf(out,"frontier %lu ignore_activations %d\n",(unsigned long)encl.size(),(int)ignore_act);
         HybridDenotableSet ureach(grid), ufinal(grid);
         int k=0, done=0;

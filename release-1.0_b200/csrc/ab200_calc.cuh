@@ -18,8 +18,10 @@ namespace ab200 { inline namespace AB_VARIANT {
 #ifdef AB_DEBUG_DUMP
 void ab_debug_dump(Ctx& c, const char* name, int idx, const TM& t);   // provided by tests/tools/hoststep.cpp
 #define AB_DUMP(c, name, idx, t) ab_debug_dump(c, name, idx, t)
+#define AB_DBG(...) printf(__VA_ARGS__)
 #else
 #define AB_DUMP(c, name, idx, t)
+#define AB_DBG(...)
 #endif
 
 // ---- system description (flat op tapes) -------------------------------------------------------------------------
@@ -54,6 +56,8 @@ struct EventDesc {
 struct LocDesc {
     int32_t n;
     int32_t n_events;
+    int32_t finishing_rank;     // number of events whose name sorts before the finishing event "e-2" (std::map order)
+    int32_t pad0;
     Func dyn[AB_MAXN];
     EventDesc ev[AB_MAXEV];
     double max_step;            // getHybridMaximumStepSize (src/hybrid_evolver-image.cpp:1522-1555)

@@ -16,6 +16,14 @@ using namespace ab200;
 
 // launchers of the two-word-key build (ab200_kernels_kw2.cu); plain signatures so that this file, compiled against
 // the AB_KW=1 headers, can call them
+#define AB_DECL_VARIANT(ns) namespace ab200 { namespace ns { \
+int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen); \
+int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
+                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach, \
+                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
+                        char* errbuf, int errlen); } }
+AB_DECL_VARIANT(t12)
+AB_DECL_VARIANT(t16)
 namespace ab200 { namespace kw2 {
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen);
 int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
@@ -110,6 +118,8 @@ extern "C" int ab200_set_system_text(ab200_ctx* ctx, const char* text) {
     CTX_CK(cudaSetDevice(ctx->device));
     DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
     DEV_CK(ab200::kw2::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t12::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
 extern "C" int ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims) {
@@ -138,6 +148,8 @@ extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max
     CTX_CK(cudaSetDevice(ctx->device));
     DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
     DEV_CK(ab200::kw2::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t12::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
 // Key window: equal share of the 64 bits after the location field, centred on the grid origin.
@@ -215,7 +227,14 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         // set models have up to max(2n+1,3n) variables: one-word keys hold 7, two-word keys 15
         const bool wide = ctx->sys.desc.loc[0].n > 2;
-        if (!wide) DEV_CK(dev_launch_evolve(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, P, ctx->d_arena.p, S.arena_words,
+        const char* tune = getenv("AB200_TUNE");
+        if (!wide && tune && !strcmp(tune, "t12")) DEV_CK(ab200::t12::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        else if (!wide && tune && !strcmp(tune, "t16")) DEV_CK(ab200::t16::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        else if (!wide) DEV_CK(dev_launch_evolve(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, P, ctx->d_arena.p, S.arena_words,
                                  ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
                                  ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
         else DEV_CK(ab200::kw2::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,

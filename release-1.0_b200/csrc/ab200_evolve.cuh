@@ -74,45 +74,51 @@ AB_HD bool enclosure_too_large(Ctx& c, const LocDesc& L, const Ivl* range, const
     return false;
 }
 
-// Evolve one enclosure (a box in location loc0) for time P.T. Mirrors _evolution with a FIFO of working sets.
+#define AB_MAXQ 12     // pending working sets per cell (device limit; WorkingSetTooLarge beyond it)
+
+// Slide the models of working set w (set[0..n), time; stored in ascending arena order) down to dst, packed.
+AB_HD int ws_pack(Ctx& c, WorkingSet& w, int n, int dst) {
+    for (int i = 0; i < n; ++i) { tm_slide(c, w.set[i], dst); dst = c.A.top; }
+    tm_slide(c, w.time, dst);
+    return c.A.top;
+}
+
+// Evolve one enclosure (a box in location loc0) for time P.T. Mirrors _evolution: a FIFO of working sets
+// (std::list<EvolutionData>, popped from the front, successors pushed at the back), kept packed at the bottom of the
+// cell's arena in queue order; everything above the last queued set is scratch.
 AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O) {
     Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
     const int n0 = S.loc[loc0].n;
-
+    const int base0 = c.A.top;
+    WorkingSet q[AB_MAXQ];
+    int nq = 1;
     // ---- _evolution_add_initialSet: set_model(box)=scalings(box) with spacial accuracy; time_model(0.0)
-    WorkingSet ws;
-    ws.loc = loc0; ws.n_events = 0; ws.p = n0;
-    for (int i = 0; i < n0; ++i) { ws.set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); ws.set[i].acc = spacial; }
-    ws.time = tm_const(c, n0, 0.0, spacial);
+    q[0].loc = loc0; q[0].n_events = 0; q[0].p = n0;
+    for (int i = 0; i < n0; ++i) { q[0].set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); q[0].set[i].acc = spacial; }
+    q[0].time = tm_begin(c, n0, spacial); tm_append(c, q[0].time, key_zero(), 0.0);          // constant(as,0.0): explicit zero term
     double init_w[AB_MAXN];
-    for (int i = 0; i < n0; ++i) init_w[i] = ivl_width(tm_range(c, ws.set[i]));   // _indexed_set_models_widths
-
-    // FIFO of pending working sets beyond the current one lives above; `qbase` is where the current set starts.
-    WsQueue Q; wsq_init(Q);
+    for (int i = 0; i < n0; ++i) init_w[i] = ivl_width(tm_range(c, q[0].set[i]));   // _indexed_set_models_widths
     int guard_iter = 0;
-    bool have = true;
-    while (have && c.status == ST_OK) {
+    while (nq > 0 && c.status == ST_OK) {
         if (++guard_iter > 100000) { fail(c, ST_OUTPUT); break; }
-        const int base = ws.set[0].off;               // current working set occupies [base, top)
+        WorkingSet ws = q[0];
+        const int qend = c.A.top;                      // end of the last queued set; scratch starts here
         const LocDesc& L = S.loc[ws.loc];
         const int n = L.n, p = ws.p;
+        WorkingSet succ[AB_MAXEV + 1];
+        int ns = 0;
         Ivl range[AB_MAXN];
         for (int i = 0; i < n; ++i) range[i] = tm_range(c, ws.set[i]);
         Ivl trange = tm_range(c, ws.time);
         bool too_large = enclosure_too_large(c, L, range, init_w, P.ratio);
-        bool done = false;
         if (trange.l >= P.T || ws.n_events >= P.max_events) {
             out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
-            done = true;
         } else if (too_large) {
             // premature termination on enclosure size; UPPER semantics keeps the set as final (:308-313)
             out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
-            done = true;
-        }
-        if (!done) {
+        } else {
             // ---- _evolution_step ------------------------------------------------------------------------------
             O.steps++;
-            const int mstep = c.A.top;
 #ifdef AB_DEBUG_DUMP
             printf("STEP %d\n", O.steps - 1);
             for (int i = 0; i < n; ++i) AB_DUMP(c, "set", i, ws.set[i]);
@@ -130,21 +136,18 @@ AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box
             printf("h %a bb", h); for (int i = 0; i < n; ++i) printf(" %a %a", bb[i].l, bb[i].u); printf("\n");
             for (int i = 0; i < n; ++i) AB_DUMP(c, "flow", i, flow[i]);
 #endif
-            vec_slide(c, fset, n, mstep);             // drop the flow model, keep the flow set model
+            vec_slide(c, fset, n, qend);              // drop the flow model, keep the flow set model
             for (int i = 0; i < n; ++i) AB_DUMP(c, "fset", i, fset[i]);
             if (c.status != ST_OK) break;
 
             // blocking info (src/hybrid_evolver-image.cpp:1085-1127)
-            TM tstep = tm_const(c, p, 1.0, spacial);  // time_model(1.0,Box(p))
-            TM zero_t = tm_const(c, p, 0.0, spacial); // time_model(0.0,Box(p)) (no storage: empty expansion)
+            TM tstep = tm_begin(c, p, spacial); tm_append(c, tstep, key_zero(), 1.0);     // time_model(1.0,Box(p))
+            TM zero_t = tm_begin(c, p, spacial); tm_append(c, zero_t, key_zero(), 0.0);   // time_model(0.0,Box(p))
             BlockingInfo B;
             compute_blocking_info(c, S, L, fset, n, p, tstep, spacial, B);
             if (c.status != ST_OK) break;
-            if (enclosure_to_be_discarded(c, S, L, ws.set, n, p)) {
-                // the working set is dropped (:532-533)
-                c.A.top = mstep;
-                done = true;
-            } else {
+            if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p)) {
+                if (c.status != ST_OK) break;
                 if (!P.ignore_activations && has_permissive_or_nontransverse(L, B)) { fail(c, ST_UNSUPPORTED); break; }
                 // reachable set (:1159-1178)
                 {
@@ -182,40 +185,46 @@ AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box
                         np = 2 * n;
                     }
                 }
-                // successors
-                bool pushed_next = false;
-                WorkingSet next;
-                if (B.finishing) {
-                    next.loc = ws.loc; next.n_events = ws.n_events; next.p = np;
-                    for (int i = 0; i < n; ++i) next.set[i] = ev[i];
-                    next.time = ft;
-                    pushed_next = true;
-                } else if (!P.ignore_activations && blocking_has_transition(L, B)) {
-                    fail(c, ST_UNSUPPORTED); break;      // jumps inside the evolver (upper_reach with transitions)
-                }
-                if (pushed_next) {
-                    // compact: slide the successor down over the consumed working set
-                    TM pack[AB_MAXN + 1];
-                    // models may be in any arena order after reconditioning: copy to the top in canonical order first
-                    const int mt = c.A.top;
-                    for (int i = 0; i < n; ++i) pack[i] = tm_copy(c, next.set[i]);
-                    pack[n] = tm_copy(c, next.time);
-                    (void)mt;
-                    vec_slide(c, pack, n + 1, base);
-                    for (int i = 0; i < n; ++i) next.set[i] = pack[i];
-                    next.time = pack[n];
-                    ws = next;
-                } else {
-                    c.A.top = base;
-                    done = true;
+                // successors, in the order of the blocking_events set (std::set<DiscreteEvent>: by name, with the
+                // finishing event "e-2" at its rank)
+                bool fin_done = false;
+                for (int k = 0; k <= B.n_blocking && c.status == ST_OK; ++k) {
+                    const int e = (k < B.n_blocking) ? B.blocking[k] : -1;
+                    if (B.finishing && !fin_done && (e < 0 || e >= L.finishing_rank)) {
+                        WorkingSet& w = succ[ns++];
+                        w.loc = ws.loc; w.n_events = ws.n_events; w.p = np;
+                        for (int i = 0; i < n; ++i) w.set[i] = ev[i];
+                        w.time = ft;
+                        fin_done = true;
+                    }
+                    if (e < 0) break;
+                    const EventDesc& E = L.ev[e];
+                    if (E.kind != EV_INVARIANT && !P.ignore_activations) {
+                        // jump: apply(reset,evolved_set_model) into the target location (:1049-1058)
+                        WorkingSet& w = succ[ns++];
+                        const int nt = S.loc[E.target].n;
+                        w.loc = E.target; w.n_events = ws.n_events + 1; w.p = np;
+                        for (int i = 0; i < nt; ++i) w.set[i] = eval_tm(c, S.ops, E.reset[i], ev);
+                        w.time = ft;
+                    }
                 }
             }
-        } else {
-            c.A.top = base;
         }
-        if (done) {
-            have = wsq_pop(c, Q, ws);
+        if (c.status != ST_OK) break;
+        // ---- pop the front, push the successors at the back, re-pack the queue at the bottom of the arena
+        if (nq - 1 + ns > AB_MAXQ) { fail(c, ST_WORKING_SETS); break; }
+        // 1. copy the successors to the top in canonical order (their models may be anywhere above qend)
+        for (int k = 0; k < ns; ++k) {
+            const int nn = S.loc[succ[k].loc].n;
+            for (int i = 0; i < nn; ++i) succ[k].set[i] = tm_copy(c, succ[k].set[i]);
+            succ[k].time = tm_copy(c, succ[k].time);
         }
+        // 2. slide everything after the front set down over it
+        int dst = base0;
+        for (int k = 1; k < nq; ++k) { dst = ws_pack(c, q[k], S.loc[q[k].loc].n, dst); q[k - 1] = q[k]; }
+        for (int k = 0; k < ns; ++k) { dst = ws_pack(c, succ[k], S.loc[succ[k].loc].n, dst); q[nq - 1 + k] = succ[k]; }
+        nq = nq - 1 + ns;
+        c.A.top = dst;
     }
 }
 

@@ -226,6 +226,18 @@ AB_HD double sqrt_m(int m, double x, int* st) {
 }
 AB_HD Ivl ivl_sqrt(Ivl i, int* st) { return ivl(sqrt_m(RD, i.l, st), sqrt_m(RU, i.u, st)); }   // numeric.cpp:905-910
 
+// pow_rnd(double,uint) in rounding mode m (src/numeric.cpp:228-238) and pow(Interval,uint) (:892-902)
+AB_HD double pow_m(int md, double x, unsigned m) {
+    if (m == 0) return 1.0;
+    if (x == 0) return 0.0;
+    if (x > 0.0 || (m % 2 == 0)) { double r = 1.0, p = dabs(x); while (m) { if (m % 2) r = mul_m(md, r, p); p = mul_m(md, p, p); m /= 2; } return r; }
+    double r = -1.0, p = x; while (m) { if (m % 2) r = mul_m(md, -r, p); p = mul_m(md, -p, p); m /= 2; } return r;
+}
+AB_HD Ivl ivl_pow(Ivl i, unsigned m) {
+    if (m % 2 == 0) i = ivl_abs(i);
+    return ivl(pow_m(RD, i.l, m), pow_m(RU, i.u, m));
+}
+
 // closed-interval predicates (include/numeric.h:376-383)
 AB_HD bool ivl_subset(Ivl a, Ivl b) { return a.l >= b.l && a.u <= b.u; }
 AB_HD bool ivl_disjoint(Ivl a, Ivl b) { return a.l > b.u || a.u < b.l; }

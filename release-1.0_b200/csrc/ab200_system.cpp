@@ -91,6 +91,13 @@ std::string parse_system(const std::string& text, HostSystem& out) {
         }
     }
     if (out.desc.n_locs == 0) return "no locations";
+    // DiscreteEvent orders by its string id and the evolver's finishing event is DiscreteEvent(-2) == "e-2"
+    // (include/discrete_event.h:39-48, src/hybrid_evolver-image.cpp:86-88)
+    for (int l = 0; l < out.desc.n_locs; ++l) {
+        int r = 0;
+        for (int e = 0; e < out.desc.loc[l].n_events; ++e) if (out.event_names[l][e] < std::string("e-2")) ++r;
+        out.desc.loc[l].finishing_rank = r;
+    }
     return "";
 }
 

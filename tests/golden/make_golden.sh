@@ -14,3 +14,6 @@ $H vanderpol cells acc=3 init=1.0,1.3,1.0,1.6 disc=1 out=$G/vanderpol_cells_acc3
 $H vanderpol reach acc=3 init=1.0,1.3,1.0,1.6 laps=2 out=$G/vanderpol_reach_acc3.txt
 $H vanderpol reach acc=4 init=-1.6,-1.3,0.3,0.8 laps=1 out=$G/vanderpol_reach_acc4.txt
 gzip -9 -f -n $G/vanderpol_cells_acc6.txt
+# bouncing ball, chain-reach mode (ignore_activations, 1 event): urgent guard, touching-time and implicit crossing steps
+$H bouncingball cells acc=5 init=-3.0,3.0,0.0,2.0 ncells=60 stride=37 out=$G/bouncingball_cells_acc5.txt
+$H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 out=$G/bouncingball_cells_acc4.txt

@@ -10,27 +10,31 @@ import golden_io
 pytestmark = pytest.mark.gpu
 
 
-def _system():
-    return open(os.path.join(golden_io.GOLDEN, "vanderpol.sys")).read()
+def _system(name="vanderpol"):
+    return open(os.path.join(golden_io.GOLDEN, name + ".sys")).read()
 
 
-def _evolver(pkg, dump, **settings):
-    ev = pkg.Evolver(_system(), settings=settings or None)
+def _evolver(pkg, dump, system="vanderpol", **settings):
+    ev = pkg.Evolver(_system(system), settings=settings or None)
     for name, g in dump["grid"].items():
         ev.tune_settings(ev.location(name), g["maxstep"], g["refw"], g["origin"], g["lengths"])
     ev.set_accuracy(dump["config"]["acc"])
     return ev
 
 
-@pytest.mark.parametrize("name,arena", [("vanderpol_cells_acc6.txt.gz", 16384), ("vanderpol_cells_acc3.txt", 131072)])
-def test_reach_evolve_boxes_bit_exact(pkg, name, arena):
+@pytest.mark.parametrize("system,name,arena", [("vanderpol", "vanderpol_cells_acc6.txt.gz", 16384), ("vanderpol", "vanderpol_cells_acc3.txt", 131072),
+                                               ("bouncingball", "bouncingball_cells_acc4.txt", 16384), ("bouncingball", "bouncingball_cells_acc5.txt", 16384)])
+def test_reach_evolve_boxes_bit_exact(pkg, system, name, arena):
+    """Per-enclosure reach / final boxes. The bouncing-ball vectors run in chain-reach mode (ignore_activations) and
+    exercise the urgent-guard path: activity tests, touching-time bisection and implicit crossing-time models."""
     d = golden_io.load_dump(name)
-    ev = _evolver(pkg, d, arena_words=arena)
+    ev = _evolver(pkg, d, system=system, arena_words=arena)
     try:
         dim = ev.dims[0]
         locs = [ev.location(c["loc"]) for c in d["cells"]]
         boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
-        (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, d["config"]["T"], d["config"]["events"], d["config"]["ignore_activations"])
+        events = 1 if d["config"]["chain"] else d["config"]["events"]
+        (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, d["config"]["T"], events, d["config"]["ignore_activations"])
         for i, c in enumerate(d["cells"]):
             mine_r = rbox[roff[i]:roff[i + 1], :2 * dim]
             mine_f = fbox[foff[i]:foff[i + 1], :2 * dim]
