@@ -107,7 +107,7 @@ def run_ours(args):
     n_mine = mine.shape[0]
     boxes = pkg.pack_boxes(mine, 2)
     locs = np.zeros((n_mine,), dtype=np.int32)
-    T = an.lock_to_grid_time
+    T = an.lock_to_grid_time * args.lap_scale
     # tune exactly as the analyser's lap does (restriction bounding box)
     an.lib.ab200_analyser_set_lock_time(an.handle, T)
     import ctypes as C
@@ -165,7 +165,7 @@ def run_ours(args):
         "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak" if args.cells else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %d frontier cells (configs[2])" % (ACC, int(n_total)),
-                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "lap_time": T,
+                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "lap_time": T, "tune": os.environ.get("AB200_TUNE", "default"),
                    "l2_policy": "per-cell scratch arenas (%.1f GB) exceed L2; no flush needed" % (n_total / world * args.arena_words * 8 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_mine * (80 + 4)), "d2h_bytes_per_step": int(8 * (reach_n + 0) + 24 * n_mine)},
         "gpu_launches": int(launches),
@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--arena-words", type=int, default=12288)
     ap.add_argument("--max-boxes", type=int, default=320)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lap-scale", type=float, default=1.0, help="PROFILING ONLY: shorten the lap so that ncu can replay the kernel; not a bench value")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

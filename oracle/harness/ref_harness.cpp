@@ -199,6 +199,23 @@ static void dump_system(FILE* f, const HybridIOAutomaton& sys) {
                 for(std::list<DiscreteIOTransition>::const_iterator t=sys.transitions().begin(); t!=sys.transitions().end(); ++t) {
                     if(!(t->source()==loc && t->event()==*e)) continue;
                     fprintf(f,"    guard"); emit_tape(f,t->activation(),var_index); fprintf(f," ;\n");
+                    {
+                        // lie_derivative(activation,dynamic) as ScalarFunction arithmetic builds it (src/function.cpp:1308-1331,
+                        // :863-909): r=dg/dx0*f0; r=r+dg/dxi*fi, with Ariadne::derivative on the expressions
+                        // (src/function.cpp:118). Used by the grid-side jump test (src/set_checker.cpp:148-161).
+                        const std::map<RealVariable,RealExpression>* dyn=0;
+                        for(std::list<DiscreteIOMode>::const_iterator m=sys.modes().begin(); m!=sys.modes().end(); ++m) if(m->location()==loc) dyn=&m->dynamics();
+                        std::map<RealVariable,RealExpression>::const_iterator d=dyn->begin();
+                        try {
+                            RealExpression lie=derivative(t->activation(),cs.variable(0))*d->second; ++d;
+                            for(uint i=1;i<cs.size();++i,++d) lie=lie+derivative(t->activation(),cs.variable(i))*d->second;
+                            fprintf(f,"    lie"); emit_tape(f,lie,var_index); fprintf(f," ;\n");
+                        } catch(std::exception& ex) {
+                            // the reference itself cannot differentiate this guard (e.g. min(-iL,iL)): its grid-side jump
+                            // test would fail with "Failed to compute Lie derivative" (src/function.cpp:1329)
+                            fprintf(f,"    # lie derivative not computable in the reference: %s\n","derivative() throws");
+                        }
+                    }
                     uint i=0;
                     for(std::map<RealVariable,RealExpression>::const_iterator r=t->reset().begin(); r!=t->reset().end(); ++r,++i) {
                         fprintf(f,"    reset %u",i); emit_tape(f,r->second,var_index); fprintf(f," ;\n"); }

@@ -51,6 +51,7 @@ struct EventDesc {
     int32_t id;                 // event id (ordering of std::map<DiscreteEvent,...>)
     int32_t pad;
     Func guard;                 // guard or invariant function
+    Func lie;                   // lie_derivative(guard,dynamic) (transitions only; grid-side jump test)
     Func reset[AB_MAXN];
 };
 struct LocDesc {

@@ -82,6 +82,9 @@ std::string parse_system(const std::string& text, HostSystem& out) {
         } else if (tok == "guard") {
             if (cur_loc < 0 || cur_ev < 0) return "guard outside event";
             if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].guard, err)) return err;
+        } else if (tok == "lie") {
+            if (cur_loc < 0 || cur_ev < 0) return "lie outside event";
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].lie, err)) return err;
         } else if (tok == "reset") {
             int i; in >> i;
             if (cur_loc < 0 || cur_ev < 0 || i < 0 || i >= AB_MAXN) return "reset outside event";

@@ -12,6 +12,7 @@
 //     dyn <i> <tape...> ;
 //     event <k> <name> kind <invariant|urgent|permissive> target <loc idx> id <int>
 //       guard <tape...> ;
+//       lie <tape...> ;                  (transitions only: Lie derivative of the guard along the dynamics)
 //       reset <i> <tape...> ;            (transitions only)
 //   tape tokens: V<j> | C<lo>,<hi> (hex or decimal doubles) | ADD SUB MUL DIV NEG POS REC SQR SQRT EXP LOG SIN COS TAN ABS MAX MIN
 #pragma once

@@ -276,7 +276,12 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
     double te[AB_MAXSTREAMS];
     Key hk[AB_MAXSTREAMS];
     bool live[AB_MAXSTREAMS];
-    for (int s = 0; s < B; ++s) { ti[s] = 0; te[s] = 0.0; live[s] = t[s].n > 0; if (live[s]) hk[s] = tm_key(c, t[s], 0); }
+    int toff[AB_MAXSTREAMS], tn[AB_MAXSTREAMS];
+    #pragma unroll
+    for (int s = 0; s < AB_MAXSTREAMS; ++s) {
+        ti[s] = 0; te[s] = 0.0; live[s] = false; hk[s] = key_zero(); toff[s] = 0; tn[s] = 0;
+        if (s < B) { toff[s] = t[s].off; tn[s] = t[s].n; live[s] = tn[s] > 0; if (live[s]) { for (int w = 0; w < AB_KW; ++w) hk[s].w[w] = aw(c, toff[s] + w); } }
+    }
     bool rlive = r.n > 0;
     Key rk = key_zero();
     if (rlive) rk = tm_key(c, r, 0);
@@ -284,7 +289,8 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
         // smallest key among the heads
         bool any = rlive;
         Key mk = rk;
-        for (int s = 0; s < B; ++s) if (live[s] && (!any || key_less(hk[s], mk))) { mk = hk[s]; any = true; }
+        #pragma unroll
+        for (int s = 0; s < AB_MAXSTREAMS; ++s) if (live[s] && (!any || key_less(hk[s], mk))) { mk = hk[s]; any = true; }
         if (!any) break;
         bool present = false;
         double cur = 0.0;
@@ -292,16 +298,17 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
             cur = tm_val(c, r, ri); present = true;
             ++ri; rlive = ri < r.n; if (rlive) rk = tm_key(c, r, ri);
         }
-        for (int s = 0; s < B; ++s) {
+        #pragma unroll
+        for (int s = 0; s < AB_MAXSTREAMS; ++s) {
             if (!live[s] || !key_eq(hk[s], mk)) continue;
-            double tv = tm_val(c, t[s], ti[s]);
+            double tv = u2d(aw(c, toff[s] + ti[s] * AB_TW + AB_KW));
             if (present) {
                 double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
                 te[s] = add_ru(te[s], add_ru(u, ml));
                 cur = add_rn(cur, tv);
                 if (cur == 0) present = false;
             } else { cur = tv; present = true; }
-            ++ti[s]; live[s] = ti[s] < t[s].n; if (live[s]) hk[s] = tm_key(c, t[s], ti[s]);
+            ++ti[s]; live[s] = ti[s] < tn[s]; if (live[s]) { for (int w = 0; w < AB_KW; ++w) hk[s].w[w] = aw(c, toff[s] + ti[s] * AB_TW + w); }
         }
         if (present) tm_append(c, out, mk, cur);
     }
@@ -336,7 +343,7 @@ AB_HD TM tm_plus_assign(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x,
 // Product stream b of a block is x-term (i0+b) times y; its head is the next product that is not discarded.
 // Discarded products are folded into the stream's truncation error while the cursor advances, in y order, exactly
 // as the inner loop of _mul4 does.
-#define AB_MULSTREAMS 16
+#define AB_MULSTREAMS 8
 AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     AB_SECTION(0);
     const int m = c.A.top;
@@ -347,8 +354,11 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         double xv[AB_MULSTREAMS], hv[AB_MULSTREAMS], tte[AB_MULSTREAMS], te[AB_MULSTREAMS];
         int cur[AB_MULSTREAMS];        // index of the y term AFTER the head; y.n+1 when the stream is exhausted
         bool live[AB_MULSTREAMS];
-        for (int b = 0; b < B; ++b) {
-            xa[b] = tm_key(c, x, i0 + b); xv[b] = tm_val(c, x, i0 + b); tte[b] = 0.0; te[b] = 0.0; cur[b] = 0; live[b] = false;
+        // all per-stream state is indexed with compile-time constants (fully unrolled loops) so it stays in registers
+        #pragma unroll
+        for (int b = 0; b < AB_MULSTREAMS; ++b) {
+            tte[b] = 0.0; te[b] = 0.0; cur[b] = 0; live[b] = false; xv[b] = 0.0; xa[b] = key_zero(); hk[b] = key_zero(); hv[b] = 0.0;
+            if (b < B) { xa[b] = tm_key(c, x, i0 + b); xv[b] = tm_val(c, x, i0 + b); }
         }
         // advance stream b to its next surviving product
         #define AB_ADVANCE(b) do { live[b] = false; const double axv_ = dabs(xv[b]); \
@@ -356,17 +366,20 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 double tv_ = mul_rn(xv[b], yv_); \
                 if (acc_discard(acc, ta_, tv_)) tte[b] = add_ru(tte[b], mul_ru(axv_, dabs(yv_))); \
                 else { hk[b] = ta_; hv[b] = tv_; live[b] = true; break; } } } while (0)
-        for (int b = 0; b < B; ++b) AB_ADVANCE(b);
+        #pragma unroll
+        for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) AB_ADVANCE(b);
         c.A.top = r.off + r.n * AB_TW;
         TM out = tm_begin(c, x.as, acc);
         int ri = 0; bool rlive = r.n > 0; Key rk = key_zero(); if (rlive) rk = tm_key(c, r, 0);
         for (;;) {
             bool any = rlive; Key mk = rk;
-            for (int b = 0; b < B; ++b) if (live[b] && (!any || key_less(hk[b], mk))) { mk = hk[b]; any = true; }
+            #pragma unroll
+            for (int b = 0; b < AB_MULSTREAMS; ++b) if (live[b] && (!any || key_less(hk[b], mk))) { mk = hk[b]; any = true; }
             if (!any) break;
             bool present = false; double cv = 0.0;
             if (rlive && key_eq(rk, mk)) { cv = tm_val(c, r, ri); present = true; ++ri; rlive = ri < r.n; if (rlive) rk = tm_key(c, r, ri); }
-            for (int b = 0; b < B; ++b) {
+            #pragma unroll
+            for (int b = 0; b < AB_MULSTREAMS; ++b) {
                 if (!live[b] || !key_eq(hk[b], mk)) continue;
                 const double tv = hv[b];
                 if (present) {
@@ -382,7 +395,8 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         #undef AB_ADVANCE
         // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
         double e = r.e;
-        for (int b = 0; b < B; ++b) { double tev = add_ru(tte[b], tte[b] / 2); e = add_ru(add_ru(e, tev), te[b] / 2); }
+        #pragma unroll
+        for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) { double tev = add_ru(tte[b], tte[b] / 2); e = add_ru(add_ru(e, tev), te[b] / 2); }
         out.e = e;
         tm_slide(c, out, m);
         r = out;

@@ -68,4 +68,6 @@ def load_dump(name):
 
 def boxes_equal_bits(a, b):
     a = np.ascontiguousarray(np.asarray(a, dtype=np.float64)); b = np.ascontiguousarray(np.asarray(b, dtype=np.float64))
+    if a.size == 0 and b.size == 0:
+        return True
     return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
