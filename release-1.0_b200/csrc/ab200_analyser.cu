@@ -12,7 +12,8 @@
 #include <cmath>
 #include <limits>
 #include "../../include/ariadne_b200.h"
-#include "ab200_calc.cuh"
+#include "ab200_events.cuh"
+#include "ab200_series.cuh"
 #include "ab200_system.h"
 #include "ab200_paving.h"
 
@@ -238,6 +239,171 @@ static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, doubl
     return AB200_OK;
 }
 
+// ---- grid-side jump sets -------------------------------------------------------------------------------------------
+// ReachabilityRestriction::forward_jump_set (src/reachability_restriction.cpp:340-375) with
+// ForwardDiscreteJumpSetChecker (src/set_checker.cpp:50-226). One-off host work per lap over the cell sets (the
+// per-cell flows stay on the device); it uses the same Taylor-model routines as the kernel, compiled for the host.
+namespace {
+struct JumpCalc {
+    const SystemDesc& S;
+    std::vector<uint64_t> arena;
+    Ctx c;
+    explicit JumpCalc(const SystemDesc& s) : S(s), arena(1u << 22) {
+        c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    }
+    static int tri_not(int t) { return t == TRI_INDET ? TRI_INDET : (t == TRI_TRUE ? TRI_FALSE : TRI_TRUE); }
+    static int tri_and(int a, int b) { if (a == TRI_FALSE || b == TRI_FALSE) return TRI_FALSE; if (a == TRI_TRUE && b == TRI_TRUE) return TRI_TRUE; return TRI_INDET; }
+
+    // _is_outside_any_invariant (src/set_checker.cpp:111-135)
+    int outside_any_invariant(int l, const Ivl* bx) {
+        const LocDesc& L = S.loc[l];
+        int result = TRI_FALSE;
+        for (int e = 0; e < L.n_events; ++e) {
+            if (L.ev[e].kind != EV_INVARIANT && L.ev[e].kind != EV_URGENT) continue;
+            int act = tribool_of(eval_ivl(c, S.ops, L.ev[e].guard, bx));
+            if (act == TRI_TRUE) return TRI_TRUE;
+            if (act == TRI_INDET) result = TRI_INDET;
+        }
+        return result;
+    }
+    // TaylorSet(Box) (src/taylor_set.cpp:69-72)
+    void box_set(const Ivl* bx, int n, TM* set) { for (int i = 0; i < n; ++i) set[i] = tm_scaling(c, n, i, bx[i]); }
+    // _is_transition_taken (src/set_checker.cpp:66-108)
+    int transition_taken(int l, int e, const TM* src, int n) {
+        const EventDesc& E = S.loc[l].ev[e];
+        const bool urgent = (E.kind == EV_URGENT);
+        int act = guard_active(c, S, E.guard, src);
+        if (act == TRI_TRUE && urgent) return TRI_FALSE;
+        if (act != TRI_FALSE && !urgent) return act;
+        if (act != TRI_FALSE && urgent) {
+            // _is_positively_crossing: Lie derivative of the guard over the enclosure's bounding box
+            if (E.lie.end <= E.lie.begin) { fail(c, ST_UNSUPPORTED); return TRI_INDET; }
+            Ivl bb[AB_MAXN];
+            for (int i = 0; i < n; ++i) bb[i] = tm_range(c, src[i]);
+            Ivl d = eval_ivl(c, S.ops, E.lie, bb);
+            if (d.u < 0) return TRI_FALSE;
+            return TRI_INDET;
+        }
+        return TRI_FALSE;
+    }
+    // ForwardDiscreteJumpSetChecker::check (src/set_checker.cpp:171-203)
+    int check(int l, int e, const double* box) {
+        const int n = S.loc[l].n;
+        const int m = c.A.top;
+        Ivl bx[AB_MAXN];
+        for (int i = 0; i < n; ++i) bx[i] = ivl(box[2 * i], box[2 * i + 1]);
+        int out_src = outside_any_invariant(l, bx);
+        if (out_src == TRI_TRUE) return TRI_FALSE;
+        int result = TRI_FALSE;
+        TM src[AB_MAXN]; box_set(bx, n, src);
+        int taken = transition_taken(l, e, src, n);
+        if (taken != TRI_FALSE) {
+            const EventDesc& E = S.loc[l].ev[e];
+            const int nt = S.loc[E.target].n;
+            Ivl tb[AB_MAXN];
+            for (int i = 0; i < nt; ++i) { TM t = eval_tm(c, S.ops, E.reset[i], src); tb[i] = tm_range(c, t); }
+            int out_trg = outside_any_invariant(E.target, tb);
+            result = tri_and(tri_and(tri_not(out_src), taken), tri_not(out_trg));
+        }
+        c.A.top = m;
+        return result;
+    }
+
+    // TaylorSet::split() (src/taylor_set.cpp:408-452) into two sets begun at the arena top.
+    void split(const TM* set, int n, TM* a, TM* b) {
+        const int ng = set[0].as;
+        double rmax = 0.0; int armax = 0;
+        for (int j = 0; j < ng; ++j) {
+            double r = 0.0; Key u = key_unit(j);
+            for (int i = 0; i < n; ++i) {
+                double g = 0.0;
+                for (int t = 0; t < set[i].n; ++t) { Key k = tm_key(c, set[i], t); if (key_eq(k, u)) { g = tm_val(c, set[i], t); break; } if (key_deg(k) > 1) break; }
+                r = add_m(c.rnd, r, dabs(g));
+            }
+            if (r > rmax) { rmax = r; armax = j; }
+        }
+        double emax = 0.0; int aemax = 0;
+        for (int i = 0; i < n; ++i) if (set[i].e > emax) { emax = set[i].e; aemax = i; }
+        if (emax > rmax) {
+            for (int i = 0; i < n; ++i) if (i != aemax) { a[i] = set[i]; b[i] = set[i]; }
+            a[aemax] = tm_copy(c, set[aemax]); a[aemax].e = emax / 2; tm_acc(c, a[aemax], -(emax / 2));
+            b[aemax] = tm_copy(c, set[aemax]); b[aemax].e = emax / 2; tm_acc(c, b[aemax], emax / 2);
+        } else {
+            for (int i = 0; i < n; ++i) { a[i] = tm_split(c, set[i], armax, false); b[i] = tm_split(c, set[i], armax, true); }
+        }
+    }
+    // TaylorSet::disjoint(Box) (src/taylor_set.cpp:170-207). Note the box handed down the recursion is the one already
+    // widened by the errors (as the reference does).
+    int disjoint(const TM* set, int n, const Ivl* bx, int level = 0) {
+        Ivl ebx[AB_MAXN], bbx[AB_MAXN];
+        for (int i = 0; i < n; ++i) ebx[i] = ivl_add(bx[i], ivl(-set[i].e, set[i].e));
+        for (int i = 0; i < n; ++i) { TM ef = set[i]; ef.e = 0.0; bbx[i] = tm_range(c, ef); }
+        bool dis = false, sub = true, cen = true;
+        double rb = 0.0, re = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (bbx[i].l > ebx[i].u || bbx[i].u < ebx[i].l) dis = true;
+            if (!(bbx[i].l >= ebx[i].l && bbx[i].u <= ebx[i].u)) sub = false;
+            double v = (set[i].n > 0 && key_deg(tm_key(c, set[i], 0)) == 0) ? tm_val(c, set[i], 0) : 0.0;
+            if (!(ebx[i].l <= v && v <= ebx[i].u)) cen = false;
+            rb = dmax(rb, sub_ru(bbx[i].u, bbx[i].l)); re = dmax(re, sub_ru(ebx[i].u, ebx[i].l));
+        }
+        if (dis) return TRI_TRUE;
+        if (sub) return TRI_FALSE;
+        if (cen) return TRI_FALSE;
+        if ((rb / 2) * 2.0 < re / 2) return TRI_INDET;
+        if (level > 64 || c.status != ST_OK) { fail(c, ST_UNSUPPORTED); return TRI_INDET; }
+        const int m = c.A.top;
+        TM a[AB_MAXN], b[AB_MAXN];
+        split(set, n, a, b);
+        int ra = disjoint(a, n, ebx, level + 1), rbb = disjoint(b, n, ebx, level + 1);
+        c.A.top = m;
+        return tri_and(ra, rbb);
+    }
+};
+}
+
+static int forward_jump_set(ab200_analyser* an, const HybridCells& reach, HybridCells& result) {
+    const HostSystem* hs = ab200_ctx_system(an->ctx);
+    const SystemDesc& S = hs->desc;
+    result = empty_cells(an);
+    JumpCalc J(S);
+    bool ok = true;
+    for (int l = 0; l < an->n_locs; ++l) {
+        const LocDesc& L = S.loc[l];
+        for (int e = 0; e < L.n_events; ++e) {
+            if (L.ev[e].kind != EV_URGENT && L.ev[e].kind != EV_PERMISSIVE) continue;
+            if (reach[l].empty()) continue;
+            const int trg = L.ev[e].target;
+            const int n = L.n, nt = S.loc[trg].n;
+            CellSet feasible = reach[l];
+            feasible.outer_restrict([&](const double* box) { return J.check(l, e, box); });
+            // get_reset (src/set_checker.cpp:206-226)
+            CellSet image(an->grid[trg], an->K, trg);
+            std::vector<CellBox> cells; feasible.enumerate(cells);
+            for (size_t k = 0; k < cells.size() && J.c.status == ST_OK; ++k) {
+                J.c.A.top = 0;
+                Ivl bx[AB_MAXN]; TM src[AB_MAXN], t[AB_MAXN];
+                for (int i = 0; i < n; ++i) bx[i] = ivl(cells[k].b[2 * i], cells[k].b[2 * i + 1]);
+                J.box_set(bx, n, src);
+                double bb[2 * AB_MAXN];
+                for (int i = 0; i < nt; ++i) { t[i] = eval_tm(J.c, S.ops, L.ev[e].reset[i], src); Ivl r = tm_range(J.c, t[i]); bb[2 * i] = r.l; bb[2 * i + 1] = r.u; }
+                ok = image.adjoin_outer_approximation(bb, [&](const double* cb) {
+                    Ivl cx[AB_MAXN]; for (int i = 0; i < nt; ++i) cx[i] = ivl(cb[2 * i], cb[2 * i + 1]);
+                    return J.disjoint(t, nt, cx);
+                }) && ok;
+            }
+            if (J.c.status != ST_OK) {
+                ab200_ctx_set_error(an->ctx, "forward_jump_set: guard/reset cannot be evaluated on the host (unsupported function or arena)");
+                return J.c.status == ST_OK ? AB200_E_UNSUPPORTED : J.c.status;
+            }
+            result[trg].adjoin(image);
+        }
+    }
+    ok = apply_restriction(an, result) && ok;
+    if (!ok) { ab200_ctx_set_error(an->ctx, "jump set lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    return AB200_OK;
+}
+
 // ReachabilityRestriction::outer_intersection_with(HybridBoundedConstraintSet) for box-only sets
 // (src/reachability_restriction.cpp:522-535).
 static int discretise_initial(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, HybridCells& initial) {
@@ -308,13 +474,6 @@ extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_i
     if (!an || !reach_out) return AB200_E_ARGUMENT;
     *reach_out = 0;
     an->cells_evolved = 0;
-    const HostSystem* hs = ab200_ctx_system(an->ctx);
-    for (int l = 0; l < hs->desc.n_locs; ++l)
-        for (int e = 0; e < hs->desc.loc[l].n_events; ++e)
-            if (hs->desc.loc[l].ev[e].kind != EV_INVARIANT) {
-                ab200_ctx_set_error(an->ctx, "outer_chain_reach: grid-side jump sets (forward_jump_set) are not implemented yet");
-                return AB200_E_UNSUPPORTED;
-            }
     ab200_status st; memset(&st, 0, sizeof(st)); st.cell = -1;
     HybridCells current;
     int rc = discretise_initial(an, n_init, loc, boxes, current);
@@ -327,7 +486,9 @@ extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_i
         for (int l = 0; l < an->n_locs; ++l) { new_final[l].remove(fin[l]); new_reach[l].remove(reach[l]); }
         apply_restriction(an, new_final); apply_restriction(an, new_reach);
         for (int l = 0; l < an->n_locs; ++l) { reach[l].adjoin(new_reach[l]); fin[l].adjoin(new_final[l]); }
-        current = new_final;      // forward_jump_set(new_reach) is empty without transitions
+        rc = forward_jump_set(an, new_reach, current);
+        if (rc != AB200_OK) { if (status) { *status = st; status->code = rc; } return rc; }
+        for (int l = 0; l < an->n_locs; ++l) current[l].adjoin(new_final[l]);
     }
     *reach_out = to_cellset(reach);
     if (status) *status = st;

@@ -143,6 +143,94 @@ bool CellSet::adjoin_outer_approximation(const double* box) {
     return ok;
 }
 
+namespace {
+struct PathKey { Path p; uint64_t key; bool operator<(const PathKey& o) const { return p < o.p; } };
+}
+static void restrict_rec(const std::vector<PathKey>& P, size_t lo, size_t hi, int level, int depth, int split, int dim,
+                         const CellBox& box, const CellSet::BoxTest& check, std::vector<uint64_t>& out) {
+    if (hi == lo) return;                                   // enabled_cells == bddfalse
+    int prop = check(box.b);
+    if (prop == 0) return;
+    if (prop == 1 || level == depth) { for (size_t k = lo; k < hi; ++k) out.push_back(P[k].key); return; }
+    int shift = depth - 1 - level;
+    size_t a = lo, b = hi;
+    while (a < b) { size_t m = (a + b) / 2; if ((P[m].p >> shift) & 1) b = m; else a = m + 1; }
+    double c = (box.b[2 * split] + box.b[2 * split + 1]) / 2.0;          // Box::split -> midpoint (src/vector.cpp:246-253)
+    CellBox left = box, right = box;
+    left.b[2 * split + 1] = c; right.b[2 * split] = c;
+    restrict_rec(P, lo, a, level + 1, depth, (split + 1) % dim, dim, left, check, out);
+    restrict_rec(P, a, hi, level + 1, depth, (split + 1) % dim, dim, right, check, out);
+}
+
+void CellSet::outer_restrict(const BoxTest& check) {
+    if (keys.empty()) return;
+    const int dim = grid.dim;
+    Root root = minimal_root();
+    int l2[AB_GRID_MAXN], ns[AB_GRID_MAXN]; long long lower[AB_GRID_MAXN];
+    root_extent(root, dim, l2, lower);
+    for (int i = 0; i < dim; ++i) ns[i] = l2[i] + K.acc;
+    std::vector<PathKey> P(keys.size());
+    long long idx[AB_GRID_MAXN], rel[AB_GRID_MAXN];
+    for (size_t k = 0; k < keys.size(); ++k) {
+        int l; key_unpack(K, keys[k], &l, idx);
+        for (int i = 0; i < dim; ++i) rel[i] = idx[i] - lower[i] * (1LL << K.acc);
+        P[k].p = make_path(root, dim, K.acc, rel, ns); P[k].key = keys[k];
+    }
+    std::sort(P.begin(), P.end());
+    Ivl rc[AB_GRID_MAXN];
+    root_box(grid.origin, grid.lengths, dim, root, rc);
+    CellBox rb;
+    for (int i = 0; i < dim; ++i) { rb.b[2 * i] = rc[i].l; rb.b[2 * i + 1] = rc[i].u; }
+    std::vector<uint64_t> out;
+    restrict_rec(P, 0, P.size(), 0, root.height + dim * K.acc, splitting_coordinate(root.height, dim), dim, rb, check, out);
+    std::sort(out.begin(), out.end());
+    keys.swap(out);
+}
+
+namespace {
+struct AdjoinCtx {
+    const CellSet* cs; const CellSet::BoxTest* disjoint; int dim, depth; long long base[AB_GRID_MAXN];
+    std::vector<uint64_t> add; bool ok;
+};
+}
+static void adjoin_rec(AdjoinCtx& A, int level, int split, const CellBox& box, long long* rel) {
+    if ((*A.disjoint)(box.b) == 1) return;
+    if (level == A.depth) {
+        long long idx[AB_GRID_MAXN]; uint64_t key;
+        for (int i = 0; i < A.dim; ++i) idx[i] = A.base[i] + rel[i];
+        if (key_pack(A.cs->K, A.cs->loc, idx, &key)) A.add.push_back(key); else A.ok = false;
+        return;
+    }
+    double c = (box.b[2 * split] + box.b[2 * split + 1]) / 2.0;
+    CellBox left = box, right = box;
+    left.b[2 * split + 1] = c; right.b[2 * split] = c;
+    long long save = rel[split];
+    rel[split] = 2 * save;     adjoin_rec(A, level + 1, (split + 1) % A.dim, left, rel);
+    rel[split] = 2 * save + 1; adjoin_rec(A, level + 1, (split + 1) % A.dim, right, rel);
+    rel[split] = save;
+}
+
+bool CellSet::adjoin_outer_approximation(const double* bbox, const BoxTest& disjoint) {
+    const int dim = grid.dim;
+    Ivl b[AB_GRID_MAXN];
+    for (int i = 0; i < dim; ++i) { b[i] = ivl(bbox[2 * i], bbox[2 * i + 1]); if (b[i].l > b[i].u) return true; }   // bbox.empty()
+    Root root; root.height = 0; for (int i = 0; i < dim; ++i) root.coord[i] = 0;
+    if (!keys.empty()) root = minimal_root();
+    root_cover(grid.origin, grid.lengths, dim, root, b, 60);
+    Ivl rc[AB_GRID_MAXN];
+    root_box(grid.origin, grid.lengths, dim, root, rc);
+    int l2[AB_GRID_MAXN]; long long lower[AB_GRID_MAXN];
+    root_extent(root, dim, l2, lower);
+    AdjoinCtx A; A.cs = this; A.disjoint = &disjoint; A.dim = dim; A.depth = root.height + dim * K.acc; A.ok = true;
+    for (int i = 0; i < dim; ++i) A.base[i] = lower[i] * (1LL << K.acc);
+    CellBox rb; long long rel[AB_GRID_MAXN];
+    for (int i = 0; i < dim; ++i) { rb.b[2 * i] = rc[i].l; rb.b[2 * i + 1] = rc[i].u; rel[i] = 0; }
+    adjoin_rec(A, 0, splitting_coordinate(root.height, dim), rb, rel);
+    std::sort(A.add.begin(), A.add.end());
+    adjoin(A.add);
+    return A.ok;
+}
+
 bool CellSet::bounding_box(double* box) const {
     std::vector<CellBox> cells; enumerate(cells);
     if (cells.empty()) return false;

@@ -12,6 +12,7 @@
 #pragma once
 #include <vector>
 #include <stdint.h>
+#include <functional>
 #include "ab200_grid.cuh"
 
 namespace ab200 {
@@ -45,6 +46,17 @@ class CellSet {
     // adjoin_outer_approximation(Box,accuracy) (src/bdd_set.cpp:1548-1574), returns false if a cell fell outside
     // the key window.
     bool adjoin_outer_approximation(const double* box /* lo,hi per coordinate */);
+
+    // A three-valued test on a cell box (lo,hi per coordinate): 0 false, 1 true, 2 indeterminate.
+    typedef std::function<int(const double*)> BoxTest;
+    // outer_restrict(SetCheckerInterface,accuracy) (src/bdd_set.cpp:1706-1721 -> _approximate_restrict :640-690, AS_OUTER):
+    // descend from the minimal root; a subtree is dropped where the check is false, kept whole where it is true,
+    // and kept at the leaves where it stays indeterminate.
+    void outer_restrict(const BoxTest& check);
+    // adjoin_outer_approximation(CompactSetInterface,accuracy) (src/bdd_set.cpp:1548-1574,455-493): grow the root over
+    // `bbox`, then mark every leaf reached without meeting a cell the set is definitely disjoint from
+    // (`disjoint` returns 1 only for "definitely disjoint"). Returns false if a cell fell outside the key window.
+    bool adjoin_outer_approximation(const double* bbox, const BoxTest& disjoint);
 
     // Minimal root (height>=0) covering all cells; undefined for the empty set.
     Root minimal_root() const;

@@ -17,3 +17,6 @@ gzip -9 -f -n $G/vanderpol_cells_acc6.txt
 # bouncing ball, chain-reach mode (ignore_activations, 1 event): urgent guard, touching-time and implicit crossing steps
 $H bouncingball cells acc=5 init=-3.0,3.0,0.0,2.0 ncells=60 stride=37 out=$G/bouncingball_cells_acc5.txt
 $H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 out=$G/bouncingball_cells_acc4.txt
+# bouncing ball, full outer_chain_reach (laps + grid-side jump sets through the urgent bounce), configs[1]
+$H bouncingball reach acc=5 out=$G/bouncingball_chain_acc5.txt
+$H bouncingball reach acc=6 init=-2.0,0.5,0.5,1.5 out=$G/bouncingball_chain_acc6.txt

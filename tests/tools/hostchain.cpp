@@ -1,0 +1,154 @@
+// tests/tools/hostchain.cpp -- development aid only (never shipped, never imported by the product path).
+// Compiles the analyser mirror (ab200_analyser.cu is plain host C++) against a stand-in for the device lap that runs
+// evolve_cell on the CPU, so outer_chain_reach / upper_reach_evolve incl. the grid-side jump sets can be compared
+// with an oracle `reach` dump without a GPU.
+//   hostchain <system.sys> <oracle reach dump> <chain|upper> acc=A domain=l,u,.. init=l,u,.. [T=..] [events=..]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include "../../release-1.0_b200/csrc/ab200_evolve.cuh"
+#include "../../release-1.0_b200/csrc/ab200_system.h"
+#include "../../release-1.0_b200/csrc/ab200_paving.h"
+#include "../../include/ariadne_b200.h"
+
+using namespace ab200;
+
+struct ab200_cellset { std::vector<uint64_t> keys; };
+struct ab200_ctx { HostSystem sys; KeyLayout K; bool have_layout; std::string err; int accuracy; };
+
+const HostSystem* ab200_ctx_system(const ab200_ctx* ctx) { return &ctx->sys; }
+const KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return &ctx->K; }
+void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg) { ctx->err = msg; }
+std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs) { return cs->keys; }
+ab200_cellset* ab200_cellset_new() { return new ab200_cellset(); }
+extern "C" void ab200_cellset_free(ab200_cellset* cs) { delete cs; }
+extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max_step, const double* ref_widths,
+                                         const double* grid_origin, const double* grid_lengths) {
+    LocDesc& L = ctx->sys.desc.loc[loc];
+    L.max_step = max_step;
+    for (int i = 0; i < L.n; ++i) { L.ref_width[i] = ref_widths[i]; L.grid_origin[i] = grid_origin[i]; L.grid_length[i] = grid_lengths[i]; }
+    return AB200_OK;
+}
+extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
+    const SystemDesc& S = ctx->sys.desc;
+    int dim = S.loc[0].n;
+    KeyLayout K; K.dim = dim; K.acc = accuracy;
+    int lb = 0; while ((1 << lb) < S.n_locs) ++lb;
+    K.loc_bits = lb;
+    int per = (63 - lb) / dim; if (per > 40) per = 40;
+    for (int i = 0; i < dim; ++i) { K.bits[i] = per; K.bias[i] = 1LL << (per - 1); }
+    for (int i = dim; i < AB_GRID_MAXN; ++i) { K.bits[i] = 0; K.bias[i] = 0; }
+    ctx->K = K; ctx->accuracy = accuracy; ctx->have_layout = true;
+    return AB200_OK;
+}
+
+static std::vector<uint64_t> arena(1 << 22);
+static long g_cells = 0, g_steps = 0;
+
+extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T,
+                                        int32_t max_events, int32_t ignore_activations, int32_t direction,
+                                        ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status) {
+    (void)direction;
+    const SystemDesc& S = ctx->sys.desc;
+    const int MAXB = 4096;
+    std::vector<double> rb(MAXB * 2 * AB_MAXN), fb(MAXB * 2 * AB_MAXN); std::vector<int32_t> rl(MAXB), fl(MAXB);
+    std::vector<uint64_t> rkeys, fkeys;
+    for (uint64_t ci = 0; ci < n_cells; ++ci) {
+        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        EvolveParams P; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
+        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
+        g_cells++; g_steps += O.steps;
+        if (c.status != ST_OK) { printf("cell %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
+        for (int which = 0; which < 2; ++which) {
+            int cnt = which ? O.n_final : O.n_reach; const double* src = which ? fb.data() : rb.data(); const int32_t* sl = which ? fl.data() : rl.data();
+            std::vector<uint64_t>& dst = which ? fkeys : rkeys;
+            for (int l = 0; l < S.n_locs; ++l) {
+                const LocDesc& L = S.loc[l]; const int n = L.n;
+                RunningSet rs; running_init(rs, n);
+                for (int k = 0; k < cnt; ++k) {
+                    if (sl[k] != l) continue;
+                    Ivl b[AB_GRID_MAXN]; for (int i = 0; i < n; ++i) b[i] = ivl(src[k * O.stride + 2 * i], src[k * O.stride + 2 * i + 1]);
+                    long long lo[AB_GRID_MAXN], hi[AB_GRID_MAXN], idx[AB_GRID_MAXN];
+                    if (!raster_box(L.grid_origin, L.grid_length, n, ctx->K.acc, rs, b, lo, hi)) continue;
+                    for (int i = 0; i < n; ++i) idx[i] = lo[i];
+                    for (;;) { uint64_t key; if (key_pack(ctx->K, l, idx, &key)) dst.push_back(key); int d = n - 1; while (d >= 0) { if (++idx[d] <= hi[d]) break; idx[d] = lo[d]; --d; } if (d < 0) break; }
+                }
+            }
+        }
+    }
+    std::sort(rkeys.begin(), rkeys.end()); rkeys.erase(std::unique(rkeys.begin(), rkeys.end()), rkeys.end());
+    std::sort(fkeys.begin(), fkeys.end()); fkeys.erase(std::unique(fkeys.begin(), fkeys.end()), fkeys.end());
+    *reach = new ab200_cellset(); (*reach)->keys = rkeys;
+    *evolve = new ab200_cellset(); (*evolve)->keys = fkeys;
+    if (status) memset(status, 0, sizeof(*status));
+    return AB200_OK;
+}
+
+#include "../../release-1.0_b200/csrc/ab200_analyser.cu"
+
+static std::vector<double> csv(const char* s) { std::vector<double> v; std::stringstream ss(s); std::string t; while (std::getline(ss, t, ',')) v.push_back(strtod(t.c_str(), 0)); return v; }
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage\n"); return 2; }
+    static ab200_ctx ctx;
+    std::ifstream sf(argv[1]); std::stringstream ss; ss << sf.rdbuf();
+    std::string err = parse_system(ss.str(), ctx.sys); if (!err.empty()) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    const bool chain = !strcmp(argv[3], "chain");
+    int acc = 4, events = 5, mince = 0; double T = 1.0, lock = 0; std::vector<double> dom, init; int init_loc = 0;
+    for (int a = 4; a < argc; ++a) {
+        if (!strncmp(argv[a], "acc=", 4)) acc = atoi(argv[a] + 4);
+        if (!strncmp(argv[a], "events=", 7)) events = atoi(argv[a] + 7);
+        if (!strncmp(argv[a], "mince=", 6)) mince = atoi(argv[a] + 6);
+        if (!strncmp(argv[a], "T=", 2)) T = atof(argv[a] + 2);
+        if (!strncmp(argv[a], "lock=", 5)) lock = strtod(argv[a] + 5, 0);
+        if (!strncmp(argv[a], "domain=", 7)) dom = csv(argv[a] + 7);
+        if (!strncmp(argv[a], "init=", 5)) init = csv(argv[a] + 5);
+        if (!strncmp(argv[a], "loc=", 4)) init_loc = atoi(argv[a] + 4);
+    }
+    const int L = ctx.sys.desc.n_locs, n = ctx.sys.desc.loc[0].n;
+    std::vector<double> domain_boxes((size_t)L * AB200_BOX_STRIDE, 0.0), init_box(AB200_BOX_STRIDE, 0.0);
+    for (int l = 0; l < L; ++l) for (int i = 0; i < 2 * n; ++i) domain_boxes[(size_t)l * AB200_BOX_STRIDE + i] = dom[(dom.size() >= (size_t)(l + 1) * 2 * n ? l * 2 * n : 0) + i];
+    for (int i = 0; i < 2 * n; ++i) init_box[i] = init[i];
+    ab200_analyser* an = 0;
+    int rc = ab200_analyser_create(&an, &ctx, domain_boxes.data(), acc);
+    if (rc) { printf("create rc=%d %s\n", rc, ctx.err.c_str()); return 1; }
+    if (lock > 0) ab200_analyser_set_lock_time(an, lock);
+    printf("lock %a\n", an->lock_time);
+    ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
+    int32_t il = init_loc;
+    if (chain) rc = ab200_analyser_outer_chain_reach(an, 1, &il, init_box.data(), &reach, &st);
+    else rc = ab200_analyser_upper_reach_evolve(an, 1, &il, init_box.data(), T, events, mince, &reach, &evolve, &st);
+    if (rc) { printf("rc=%d %s\n", rc, ctx.err.c_str()); return 1; }
+    printf("cells evolved %ld steps %ld\n", g_cells, g_steps);
+    // compare with the oracle dump: lines "reach"/"evolve" followed by "c <loc?> boxes"
+    std::ifstream df(argv[2]); std::string line;
+    std::vector<std::vector<double> > ref_reach, ref_evolve; std::vector<std::vector<double> >* cur = 0;
+    while (std::getline(df, line)) {
+        std::istringstream in(line); std::string t; in >> t;
+        if (t == "reach") cur = &ref_reach; else if (t == "evolve") cur = &ref_evolve;
+        else if (t == "c" && cur) { std::vector<double> b; std::string v; while (in >> v) b.push_back(strtod(v.c_str(), 0)); cur->push_back(b); }
+    }
+    int bad = 0;
+    for (int which = 0; which < (chain ? 1 : 2); ++which) {
+        uint64_t cnt = 0; ab200_analyser_enumerate(an, which ? evolve : reach, 0, &cnt, 0, 0);
+        std::vector<int32_t> locs(cnt); std::vector<double> boxes(cnt * AB200_BOX_STRIDE);
+        ab200_analyser_enumerate(an, which ? evolve : reach, 0, &cnt, locs.data(), boxes.data());
+        const std::vector<std::vector<double> >& ref = which ? ref_evolve : ref_reach;
+        printf("%s merged cells %llu (ref %zu)\n", which ? "evolve" : "reach", (unsigned long long)cnt, ref.size());
+        if (cnt != ref.size()) bad = 1;
+        for (size_t k = 0; k < cnt && k < ref.size(); ++k) {
+            size_t off = ref[k].size() - 2 * n;     // optional leading location index
+            if (off == 1 && (int)ref[k][0] != locs[k]) { if (!bad) printf("cell %zu location differs\n", k); bad = 1; }
+            for (int j = 0; j < 2 * n; ++j) if (memcmp(&boxes[k * AB200_BOX_STRIDE + j], &ref[k][off + j], 8)) { if (!bad) printf("%s cell %zu differs: %a vs %a\n", which ? "evolve" : "reach", k, boxes[k * AB200_BOX_STRIDE + j], ref[k][off + j]); bad = 1; }
+        }
+        if (getenv("HOSTCHAIN_DUMP")) for (size_t k = 0; k < cnt; ++k) { printf("m %d", locs[k]); for (int j = 0; j < 2 * n; ++j) printf(" %a", boxes[k * AB200_BOX_STRIDE + j]); printf("\n"); }
+    }
+    printf(bad ? "MISMATCH\n" : "cell sets identical (bit-exact boxes)\n");
+    return bad;
+}
