@@ -21,6 +21,7 @@ struct BlockingInfo {
     int n_blocking;    // number of blocking events other than finishing
     int blocking[AB_MAXEV];
     int n_nontransverse;
+    int nontransverse[AB_MAXEV];
 };
 
 enum { TRI_FALSE = 0, TRI_TRUE = 1, TRI_INDET = 2 };
@@ -283,7 +284,7 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
                     TM lt = tm_begin(c, p, spacial); tm_append(c, lt, key_zero(), tti.l);  // time_model(lower,space_domain)
                     // event_blocking_times[finishing_event]=lower_touching_time_model
                     fin_override = lt; have_fin_override = true;
-                } else B.n_nontransverse++;
+                } else B.nontransverse[B.n_nontransverse++] = e;
             }
         }
     }
@@ -339,11 +340,77 @@ AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc
     }
     return blocking_active == TRI_TRUE;
 }
-AB_HD bool has_permissive_or_nontransverse(const LocDesc& L, const BlockingInfo& B) {
-    if (B.n_nontransverse > 0) return true;
-    for (int e = 0; e < L.n_events; ++e) if (L.ev[e].kind == EV_PERMISSIVE) return true;
-    return false;
+// ---- activation times of non-blocking events -----------------------------------------------------------------------
+// _compute_activation_info + compute_activationTimes (src/hybrid_evolver-image.cpp:884-975,1130-1157), UPPER semantics:
+// permissive events, plus urgent transitions whose crossing was non-transverse, get a [lower,upper] window of scaled
+// times during which the jump may be taken. Events are visited in name order (std::map<DiscreteEvent,..>).
+struct Activation { int ev; TM lower, upper; };
+
+AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& L, const BlockingInfo& B, const TM* fset,
+                                    int n, int p, Activation* act) {
+    bool wanted[AB_MAXEV]; bool any = false;
+    for (int e = 0; e < L.n_events; ++e) { wanted[e] = (L.ev[e].kind == EV_PERMISSIVE); any = any || wanted[e]; }
+    for (int k = 0; k < B.n_nontransverse; ++k) if (L.ev[B.nontransverse[k]].kind != EV_INVARIANT) { wanted[B.nontransverse[k]] = true; any = true; }
+    const int m0 = c.A.top;
+    // the reference builds these even when the activation map is empty; they leave no trace except the rounding mode
+    TM init[AB_MAXN], fin[AB_MAXN];
+    for (int i = 0; i < n; ++i) {                                   // partial_evaluate(models,p,0.0): terms free of the time variable
+        TM r = tm_begin(c, p, fset[i].acc);
+        for (int t = 0; t < fset[i].n; ++t) { Key a = tm_key(c, fset[i], t); if (key_get(a, p) == 0) tm_append(c, r, key_remove(a, p, p + 1), tm_val(c, fset[i], t)); }
+        r.e = fset[i].e;
+        init[i] = r;
+    }
+    for (int i = 0; i < n; ++i) fin[i] = tm_partial_evaluate_one(c, fset[i], p);
+    TM zero = B.time; zero.n = 0; zero.e = 0.0;                     // blocking_time_model*0.0
+    int na = 0;
+    if (!any) { c.A.top = m0; return 0; }
+    for (int e = 0; e < L.n_events && c.status == ST_OK; ++e) {
+        if (!wanted[e]) continue;
+        int active = guard_active(c, S, L.ev[e].guard, fset);
+        if (active == TRI_TRUE) { act[na].ev = e; act[na].lower = zero; act[na].upper = B.time; ++na; continue; }
+        if (active == TRI_FALSE) continue;
+        int ia = guard_active(c, S, L.ev[e].guard, init);
+        int fa = guard_active(c, S, L.ev[e].guard, fin);
+        // crossing_time (:548-566): implicit crossing, or the touching-time interval for a degenerate crossing
+        TM gf = eval_tm(c, S.ops, L.ev[e].guard, fset);
+        gf.as = p + 1;
+        TM cross;
+        if (!tm_implicit(c, gf, cross)) {
+            if (c.status != ST_OK) break;
+            Ivl tti = touching_time_interval(c, gf);
+            cross = tm_const(c, p, 1.0, fset[0].acc); tm_scal(c, cross, tti);
+        }
+        TM lo = tm_copy(c, cross); tm_acc(c, lo, -cross.e); lo.e = 0.0;
+        TM up = tm_copy(c, cross); tm_acc(c, up, cross.e); up.e = 0.0;
+        act[na].ev = e;
+        act[na].lower = (ia == TRI_FALSE) ? lo : zero;
+        act[na].upper = (fa == TRI_FALSE) ? up : B.time;
+        ++na;
+    }
+    if (c.status != ST_OK) return 0;
+    // keep only the windows: copy them to the top in order, then slide the block down to m0
+    TM keep[2 * AB_MAXEV];
+    for (int k = 0; k < na; ++k) { keep[2 * k] = tm_copy(c, act[k].lower); keep[2 * k + 1] = tm_copy(c, act[k].upper); }
+    vec_slide(c, keep, 2 * na, m0);
+    for (int k = 0; k < na; ++k) { act[k].lower = keep[2 * k]; act[k].upper = keep[2 * k + 1]; }
+    return na;
 }
+
+// reachability_time (src/taylor_calculus.cpp:278-296): t0 + s*(t1-t0) with s the new last variable scaled to [0,1].
+// Result (p+1 variables) at the arena top recorded on entry.
+AB_HDN TM reachability_time(Ctx& c, const TM& t0, const TM& t1, int p, Acc spacial) {
+    const int m0 = c.A.top;
+    TM a = t0; a.as = p + 1;
+    TM b = t1; b.as = p + 1;
+    TM s = tm_scaling(c, p + 1, p, ivl(0.0, 1.0));
+    TM d = tm_sub(c, b, a);
+    TM sd = tm_mul(c, s, d);
+    TM r = tm_add(c, a, sd);
+    tm_slide(c, r, m0);
+    r.acc = spacial;
+    return r;
+}
+
 AB_HD bool blocking_has_transition(const LocDesc& L, const BlockingInfo& B) {
     for (int k = 0; k < B.n_blocking; ++k) if (L.ev[B.blocking[k]].kind != EV_INVARIANT) return true;
     return false;

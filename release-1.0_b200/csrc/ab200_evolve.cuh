@@ -148,7 +148,12 @@ AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box
             if (c.status != ST_OK) break;
             if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p)) {
                 if (c.status != ST_OK) break;
-                if (!P.ignore_activations && has_permissive_or_nontransverse(L, B)) { fail(c, ST_UNSUPPORTED); break; }
+                Activation acts[AB_MAXEV]; int na = 0;
+                if (!P.ignore_activations) {
+                    if (p + 2 > AB_MAXARGS) { fail(c, ST_UNSUPPORTED); break; }     // parameter count beyond the packed key width
+                    na = compute_activation_times(c, S, L, B, fset, n, p, acts);
+                    if (c.status != ST_OK) break;
+                }
                 // reachable set (:1159-1178)
                 {
                     const int m = c.A.top;
@@ -207,6 +212,23 @@ AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box
                         for (int i = 0; i < nt; ++i) w.set[i] = eval_tm(c, S.ops, E.reset[i], ev);
                         w.time = ft;
                     }
+                }
+                // non-blocking events (:1060-1081): jump from the part of the flow tube inside the activation window;
+                // the new working set carries one more parameter (the time within the window) and is not reconditioned
+                for (int a = 0; a < na && c.status == ST_OK; ++a) {
+                    const EventDesc& E = L.ev[acts[a].ev];
+                    const int nt = S.loc[E.target].n;
+                    TM aset[AB_MAXN];
+                    reachability_step(c, fset, n, p, acts[a].lower, acts[a].upper, spacial, aset);
+                    WorkingSet& w = succ[ns++];
+                    w.loc = E.target; w.n_events = ws.n_events + 1; w.p = p + 1;
+                    for (int i = 0; i < nt; ++i) w.set[i] = eval_tm(c, S.ops, E.reset[i], aset);
+                    const int m = c.A.top;
+                    TM up = tm_copy(c, acts[a].upper); tm_scal(c, up, h); TM t1 = tm_add(c, ws.time, up);
+                    TM lo = tm_copy(c, acts[a].lower); tm_scal(c, lo, h); TM t0 = tm_add(c, ws.time, lo);
+                    TM at = reachability_time(c, t0, t1, p, spacial);
+                    tm_slide(c, at, m);
+                    w.time = at;
                 }
             }
         }
