@@ -117,8 +117,8 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
         c.sys=getWatertankHysteresis();
         c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,0.0,1.0,4.5,9.0)));
         c.initial=HybridBoundedConstraintSet(c.sys.state_space());
-        c.initial[DiscreteLocation("flow,idle,rising")]=Box(2,1.0,1.0,6.0,7.5);
-        c.initial[DiscreteLocation("flow,idle,falling")]=Box(2,0.0,0.0,6.0,7.5);
+        c.initial[DiscreteLocation("flow,idle,rising")]=box_from(kv,"initr",Box(2,1.0,1.0,6.0,7.5));
+        c.initial[DiscreteLocation("flow,idle,falling")]=box_from(kv,"initf",Box(2,0.0,0.0,6.0,7.5));
         c.acc=geti(kv,"acc",6); c.T=getd(kv,"T",0.0);
     } else if(name=="springs") {
         c.sys=getSpringsSystem();
@@ -241,6 +241,7 @@ int main(int argc, char** argv) {
     if(argc<3) { fprintf(stderr,"usage: ref_harness <config> <mode> [key=value...]\n"); return 2; }
     std::map<std::string,std::string> kv=parse_kv(argc,argv,3);
     Config c=make_config(argv[1],kv);
+    if(kv.count("chain")) c.chain=geti(kv,"chain",0)!=0;
     std::string mode(argv[2]);
     FILE* out=stdout; if(kv.count("out")) out=fopen(kv["out"].c_str(),"w");
     int verb=geti(kv,"verb",0);

@@ -248,7 +248,8 @@ struct JumpCalc {
     const SystemDesc& S;
     std::vector<uint64_t> arena;
     Ctx c;
-    explicit JumpCalc(const SystemDesc& s) : S(s), arena(1u << 22) {
+    bool lie_missing;
+    explicit JumpCalc(const SystemDesc& s) : S(s), arena(1u << 22), lie_missing(false) {
         c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
     }
     static int tri_not(int t) { return t == TRI_INDET ? TRI_INDET : (t == TRI_TRUE ? TRI_FALSE : TRI_TRUE); }
@@ -277,7 +278,7 @@ struct JumpCalc {
         if (act != TRI_FALSE && !urgent) return act;
         if (act != TRI_FALSE && urgent) {
             // _is_positively_crossing: Lie derivative of the guard over the enclosure's bounding box
-            if (E.lie.end <= E.lie.begin) { fail(c, ST_UNSUPPORTED); return TRI_INDET; }
+            if (E.lie.end <= E.lie.begin) { lie_missing = true; fail(c, ST_UNSUPPORTED); return TRI_INDET; }
             Ivl bb[AB_MAXN];
             for (int i = 0; i < n; ++i) bb[i] = tm_range(c, src[i]);
             Ivl d = eval_ivl(c, S.ops, E.lie, bb);
@@ -393,7 +394,9 @@ static int forward_jump_set(ab200_analyser* an, const HybridCells& reach, Hybrid
                 }) && ok;
             }
             if (J.c.status != ST_OK) {
-                ab200_ctx_set_error(an->ctx, "forward_jump_set: guard/reset cannot be evaluated on the host (unsupported function or arena)");
+                ab200_ctx_set_error(an->ctx, J.lie_missing
+                    ? "forward_jump_set: Failed to compute Lie derivative of a guard (the reference throws here too, src/function.cpp:1329)"
+                    : "forward_jump_set: guard/reset cannot be evaluated on the host (unsupported function or arena)");
                 return J.c.status == ST_OK ? AB200_E_UNSUPPORTED : J.c.status;
             }
             result[trg].adjoin(image);

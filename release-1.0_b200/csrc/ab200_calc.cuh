@@ -113,6 +113,7 @@ struct TmSlot { TM v; int mark; };
 AB_HDN TM tm_rec(Ctx& c, const TM& x);
 AB_HDN TM tm_sqrt(Ctx& c, const TM& x);
 AB_HDN TM tm_max(Ctx& c, const TM& x, const TM& y);
+AB_HDN TM tm_abs(Ctx& c, const TM& x);
 
 // Evaluate f over models x[0..nx); the result is left at the arena top position recorded on entry.
 AB_HDN TM eval_tm(Ctx& c, const TapeOp* ops, Func f, const TM* x) {
@@ -162,6 +163,7 @@ AB_HDN TM eval_tm(Ctx& c, const TapeOp* ops, Func f, const TM* x) {
                     tm_scal(c, r, ivl_div(ivl(1.0), 1.0));
                 } break;
                 case OP_SQRT: r = tm_sqrt(c, a); break;
+                case OP_ABS: r = tm_abs(c, a); break;
                 default: fail(c, ST_UNSUPPORTED); r = a; break;
             }
             if (o.op != OP_POS) tm_slide(c, r, st[sp - 1].mark);

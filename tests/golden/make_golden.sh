@@ -20,3 +20,11 @@ $H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 out=$G/bouncingball_cells_acc4.
 # bouncing ball, full outer_chain_reach (laps + grid-side jump sets through the urgent bounce), configs[1]
 $H bouncingball reach acc=5 out=$G/bouncingball_chain_acc5.txt
 $H bouncingball reach acc=6 init=-2.0,0.5,0.5,1.5 out=$G/bouncingball_chain_acc6.txt
+# watertank (configs[0] system, short horizon): sqrt dynamics, invariants, permissive open/close jumps through the
+# activation-time windows, 4 locations
+$H watertank reach acc=3 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5.8 out=$G/watertank_reach_acc3.txt
+# springs (configs[3] system): 5 variables (wide keys), urgent sticking with non-transverse crossings
+$H springs reach acc=2 out=$G/springs_reach_acc2.txt && gzip -9 -f -n $G/springs_reach_acc2.txt
+# boost converter (configs[4] system): 3 locations, min() guard, urgent resets; upper reach over 3 laps. Its
+# outer_chain_reach throws in the reference itself (Lie derivative of min(), src/function.cpp:1329)
+$H boost reach acc=4 chain=0 T=0.011 out=$G/boost_reach_acc4.txt

@@ -84,6 +84,49 @@ def test_outer_chain_reach_with_jumps_identical_cells(pkg, name, init):
         an.close()
 
 
+HYBRID_CASES = [
+    # (system, golden, domain, initial set, arena words)
+    ("watertank", "watertank_reach_acc3.txt", [0.0, 1.0, 4.5, 9.0],
+     {"flow,idle,rising": [1.0, 1.0, 7.6, 7.7], "flow,idle,falling": [0.0, 0.0, 5.7, 5.8]}, 131072),
+    ("springs", "springs_reach_acc2.txt.gz", [0.0, 40.0, -2.0, 2.0, -3.0, 3.0, -1.0, 3.0, 0.0, 4.0],
+     {"free1,free2": [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 3.0, 3.0]}, 131072),
+    ("boost", "boost_reach_acc4.txt", [0.0, 0.001, 0.0, 3.0, 0.0, 6.0],
+     {"incr,below_duty": [0.0, 0.0, 1.0, 1.0, 1.0, 1.0]}, 32768),
+]
+
+
+@pytest.mark.parametrize("system,name,domain,init,arena", HYBRID_CASES)
+def test_upper_reach_evolve_hybrid_systems_identical_cells(pkg, system, name, domain, init, arena):
+    """upper_reach_evolve with transitions taken inside the evolver (ignore_activations=false): blocking urgent jumps,
+    activation windows of permissive / non-transverse events, sqrt and min() dynamics, several locations."""
+    d = golden_io.load_dump(name)
+    an = pkg.HybridReachabilityAnalyser(_system(system), domain, d["config"]["acc"], settings={"arena_words": arena})
+    try:
+        assert an.lock_to_grid_time == d["config"]["lock"]
+        reach, evolve = an.upper_reach_evolve(init, d["config"]["T"], d["config"]["events"])
+        rl, rb = an.enumerate(reach)
+        el, eb = an.enumerate(evolve)
+        for which, locs, boxes in (("reach", rl, rb), ("evolve", el, eb)):
+            for lname, ref in d["sets"][which].items():
+                mine = boxes[locs == an.evolver.location(lname)]
+                assert golden_io.boxes_equal_bits(mine, ref), "%s cells of %s in %s" % (which, system, lname)
+    finally:
+        an.close()
+
+
+def test_boost_outer_chain_reach_fails_like_the_reference(pkg):
+    """configs[4]: the reference's own outer_chain_reach on the boost converter throws in forward_jump_set because
+    lie_derivative cannot differentiate the min() guard (src/function.cpp:1329). Same laps, same failure here."""
+    an = pkg.HybridReachabilityAnalyser(_system("boost"), [0.0, 0.001, 0.0, 3.0, 0.0, 6.0], 1, settings={"arena_words": 32768})
+    try:
+        with pytest.raises(pkg.Ab200Error) as ei:
+            an.outer_chain_reach({"incr,below_duty": [0.0, 0.0, 1.0, 1.0, 1.0, 1.0]})
+        assert "Lie derivative" in str(ei.value)
+        assert an.last_status.launches > 0
+    finally:
+        an.close()
+
+
 def test_lap_cell_sets_match_union_of_reference_discretisations(pkg):
     d = golden_io.load_dump("vanderpol_cells_acc3.txt")
     ev = _evolver(pkg, d, arena_words=131072)

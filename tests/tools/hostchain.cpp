@@ -48,12 +48,14 @@ extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
 }
 
 static std::vector<uint64_t> arena(1 << 22);
-static long g_cells = 0, g_steps = 0;
+static long g_cells = 0, g_steps = 0; static int g_peak = 0, g_maxboxes = 0;
 
 extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T,
                                         int32_t max_events, int32_t ignore_activations, int32_t direction,
                                         ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status) {
     (void)direction;
+    static int lapno = 0; long steps0 = g_steps;
+    struct LapLog { int no; uint64_t n; long* s; long s0; ~LapLog() { if (getenv("HOSTCHAIN_LAPS")) printf("lap %d cells %llu steps %ld\n", no, (unsigned long long)n, *s - s0); } } laplog = { lapno++, n_cells, &g_steps, steps0 };
     const SystemDesc& S = ctx->sys.desc;
     const int MAXB = 4096;
     std::vector<double> rb(MAXB * 2 * AB_MAXN), fb(MAXB * 2 * AB_MAXN); std::vector<int32_t> rl(MAXB), fl(MAXB);
@@ -63,7 +65,7 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
         EvolveParams P; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
-        g_cells++; g_steps += O.steps;
+        g_cells++; g_steps += O.steps; if (c.A.peak > g_peak) g_peak = c.A.peak; if (O.n_reach > g_maxboxes) g_maxboxes = O.n_reach;
         if (c.status != ST_OK) { printf("cell %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
         for (int which = 0; which < 2; ++which) {
             int cnt = which ? O.n_final : O.n_reach; const double* src = which ? fb.data() : rb.data(); const int32_t* sl = which ? fl.data() : rl.data();
@@ -100,7 +102,7 @@ int main(int argc, char** argv) {
     std::ifstream sf(argv[1]); std::stringstream ss; ss << sf.rdbuf();
     std::string err = parse_system(ss.str(), ctx.sys); if (!err.empty()) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
     const bool chain = !strcmp(argv[3], "chain");
-    int acc = 4, events = 5, mince = 0; double T = 1.0, lock = 0; std::vector<double> dom, init; int init_loc = 0;
+    int acc = 4, events = 5, mince = 0; double T = 1.0, lock = 0; std::vector<double> dom; std::vector<std::vector<double> > inits; std::vector<int32_t> init_locs; int init_loc = 0;
     for (int a = 4; a < argc; ++a) {
         if (!strncmp(argv[a], "acc=", 4)) acc = atoi(argv[a] + 4);
         if (!strncmp(argv[a], "events=", 7)) events = atoi(argv[a] + 7);
@@ -108,24 +110,23 @@ int main(int argc, char** argv) {
         if (!strncmp(argv[a], "T=", 2)) T = atof(argv[a] + 2);
         if (!strncmp(argv[a], "lock=", 5)) lock = strtod(argv[a] + 5, 0);
         if (!strncmp(argv[a], "domain=", 7)) dom = csv(argv[a] + 7);
-        if (!strncmp(argv[a], "init=", 5)) init = csv(argv[a] + 5);
+        if (!strncmp(argv[a], "init=", 5)) { inits.push_back(csv(argv[a] + 5)); init_locs.push_back(init_loc); }   // loc= precedes its init=
         if (!strncmp(argv[a], "loc=", 4)) init_loc = atoi(argv[a] + 4);
     }
     const int L = ctx.sys.desc.n_locs, n = ctx.sys.desc.loc[0].n;
-    std::vector<double> domain_boxes((size_t)L * AB200_BOX_STRIDE, 0.0), init_box(AB200_BOX_STRIDE, 0.0);
+    std::vector<double> domain_boxes((size_t)L * AB200_BOX_STRIDE, 0.0), init_box(inits.size() * AB200_BOX_STRIDE, 0.0);
     for (int l = 0; l < L; ++l) for (int i = 0; i < 2 * n; ++i) domain_boxes[(size_t)l * AB200_BOX_STRIDE + i] = dom[(dom.size() >= (size_t)(l + 1) * 2 * n ? l * 2 * n : 0) + i];
-    for (int i = 0; i < 2 * n; ++i) init_box[i] = init[i];
+    for (size_t k = 0; k < inits.size(); ++k) for (int i = 0; i < 2 * n; ++i) init_box[k * AB200_BOX_STRIDE + i] = inits[k][i];
     ab200_analyser* an = 0;
     int rc = ab200_analyser_create(&an, &ctx, domain_boxes.data(), acc);
     if (rc) { printf("create rc=%d %s\n", rc, ctx.err.c_str()); return 1; }
     if (lock > 0) ab200_analyser_set_lock_time(an, lock);
     printf("lock %a\n", an->lock_time);
     ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
-    int32_t il = init_loc;
-    if (chain) rc = ab200_analyser_outer_chain_reach(an, 1, &il, init_box.data(), &reach, &st);
-    else rc = ab200_analyser_upper_reach_evolve(an, 1, &il, init_box.data(), T, events, mince, &reach, &evolve, &st);
-    if (rc) { printf("rc=%d %s\n", rc, ctx.err.c_str()); return 1; }
-    printf("cells evolved %ld steps %ld\n", g_cells, g_steps);
+    if (chain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), &reach, &st);
+    else rc = ab200_analyser_upper_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, mince, &reach, &evolve, &st);
+    if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld\n", rc, ctx.err.c_str(), g_cells, g_steps); return 1; }
+    printf("cells evolved %ld steps %ld arena peak %d words, max reach boxes per cell %d\n", g_cells, g_steps, g_peak, g_maxboxes);
     // compare with the oracle dump: lines "reach"/"evolve" followed by "c <loc?> boxes"
     std::ifstream df(argv[2]); std::string line;
     std::vector<std::vector<double> > ref_reach, ref_evolve; std::vector<std::vector<double> >* cur = 0;
