@@ -117,7 +117,7 @@ def test_upper_reach_evolve_hybrid_systems_identical_cells(pkg, system, name, do
 def test_boost_outer_chain_reach_fails_like_the_reference(pkg):
     """configs[4]: the reference's own outer_chain_reach on the boost converter throws in forward_jump_set because
     lie_derivative cannot differentiate the min() guard (src/function.cpp:1329). Same laps, same failure here."""
-    an = pkg.HybridReachabilityAnalyser(_system("boost"), [0.0, 0.001, 0.0, 3.0, 0.0, 6.0], 1, settings={"arena_words": 32768})
+    an = pkg.HybridReachabilityAnalyser(_system("boost"), [0.0, 0.001, 0.0, 3.0, 0.0, 6.0], 1, settings={"arena_words": 524288})
     try:
         with pytest.raises(pkg.Ab200Error) as ei:
             an.outer_chain_reach({"incr,below_duty": [0.0, 0.0, 1.0, 1.0, 1.0, 1.0]})

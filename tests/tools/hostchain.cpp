@@ -125,7 +125,7 @@ int main(int argc, char** argv) {
     ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
     if (chain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), &reach, &st);
     else rc = ab200_analyser_upper_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, mince, &reach, &evolve, &st);
-    if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld\n", rc, ctx.err.c_str(), g_cells, g_steps); return 1; }
+    if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld arena peak %d\n", rc, ctx.err.c_str(), g_cells, g_steps, g_peak); return 1; }
     printf("cells evolved %ld steps %ld arena peak %d words, max reach boxes per cell %d\n", g_cells, g_steps, g_peak, g_maxboxes);
     // compare with the oracle dump: lines "reach"/"evolve" followed by "c <loc?> boxes"
     std::ifstream df(argv[2]); std::string line;
