@@ -22,8 +22,12 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, c
                         uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach, \
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
-AB_DECL_VARIANT(t12)
-AB_DECL_VARIANT(t16)
+AB_DECL_VARIANT(t6)
+AB_DECL_VARIANT(t8)
+AB_DECL_VARIANT(s4)
+AB_DECL_VARIANT(c4)
+AB_DECL_VARIANT(s4c4)
+AB_DECL_VARIANT(s4c16)
 namespace ab200 { namespace kw2 {
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen);
 int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
@@ -118,8 +122,12 @@ extern "C" int ab200_set_system_text(ab200_ctx* ctx, const char* text) {
     CTX_CK(cudaSetDevice(ctx->device));
     DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
     DEV_CK(ab200::kw2::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t12::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t6::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t8::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::s4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::s4c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::s4c16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
 extern "C" int ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims) {
@@ -137,6 +145,7 @@ extern "C" int ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s) {
     if (!ctx || !s) return AB200_E_ARGUMENT;
     if (s->max_boxes < 1 || s->arena_words < 256 || s->hash_log2 < 8 || s->hash_log2 > 32 || s->batch_cells < 32) { ctx->err = "bad settings"; return AB200_E_ARGUMENT; }
     ctx->settings = *s;
+    ctx->settings.arena_words = (s->arena_words + 15) & ~15;       // whole 128-byte chunks per lane (AB_CHUNK layouts)
     return AB200_OK;
 }
 extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max_step, const double* ref_widths,
@@ -148,8 +157,12 @@ extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max
     CTX_CK(cudaSetDevice(ctx->device));
     DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
     DEV_CK(ab200::kw2::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t12::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t6::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::t8::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::s4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::s4c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::s4c16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
 // Key window: equal share of the 64 bits after the location field, centred on the grid origin.
@@ -228,10 +241,22 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         // set models have up to max(2n+1,3n) variables: one-word keys hold 7, two-word keys 15
         const bool wide = ctx->sys.desc.loc[0].n > 2;
         const char* tune = getenv("AB200_TUNE");
-        if (!wide && tune && !strcmp(tune, "t12")) DEV_CK(ab200::t12::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+        if (!wide && tune && !strcmp(tune, "t6")) DEV_CK(ab200::t6::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
                                  ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
                                  ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide && tune && !strcmp(tune, "t16")) DEV_CK(ab200::t16::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+        else if (!wide && tune && !strcmp(tune, "t8")) DEV_CK(ab200::t8::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        else if (!wide && tune && !strcmp(tune, "s4")) DEV_CK(ab200::s4::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        else if (!wide && tune && !strcmp(tune, "c4")) DEV_CK(ab200::c4::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        else if (!wide && tune && !strcmp(tune, "s4c4")) DEV_CK(ab200::s4c4::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        else if (!wide && tune && !strcmp(tune, "s4c16")) DEV_CK(ab200::s4c16::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
                                  ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
                                  ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
         else if (!wide) DEV_CK(dev_launch_evolve(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, P, ctx->d_arena.p, S.arena_words,

@@ -352,7 +352,13 @@ AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& 
     for (int e = 0; e < L.n_events; ++e) { wanted[e] = (L.ev[e].kind == EV_PERMISSIVE); any = any || wanted[e]; }
     for (int k = 0; k < B.n_nontransverse; ++k) if (L.ev[B.nontransverse[k]].kind != EV_INVARIANT) { wanted[B.nontransverse[k]] = true; any = true; }
     const int m0 = c.A.top;
-    // the reference builds these even when the activation map is empty; they leave no trace except the rounding mode
+    // The reference builds the initial/final set models even when the activation map is empty; their only lasting
+    // effect then is the rounding mode left by partial_evaluate's additions (round-to-nearest once a model has degree
+    // >= 1), so without candidates only that is reproduced.
+    if (!any) {
+        for (int i = 0; i < n; ++i) if (tm_degree(c, fset[i]) >= 1) c.rnd = RN;
+        return 0;
+    }
     TM init[AB_MAXN], fin[AB_MAXN];
     for (int i = 0; i < n; ++i) {                                   // partial_evaluate(models,p,0.0): terms free of the time variable
         TM r = tm_begin(c, p, fset[i].acc);
@@ -363,7 +369,6 @@ AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& 
     for (int i = 0; i < n; ++i) fin[i] = tm_partial_evaluate_one(c, fset[i], p);
     TM zero = B.time; zero.n = 0; zero.e = 0.0;                     // blocking_time_model*0.0
     int na = 0;
-    if (!any) { c.A.top = m0; return 0; }
     for (int e = 0; e < L.n_events && c.status == ST_OK; ++e) {
         if (!wanted[e]) continue;
         int active = guard_active(c, S, L.ev[e].guard, fset);

@@ -30,6 +30,18 @@
 #endif
 #endif
 
+// AB_CHUNK consecutive words of one lane are kept together (AB_CHUNK=4: one 32-byte sector, 16: one 128-byte line)
+// and the chunks of the 32 lanes interleave. AB_CHUNK=1 is the plain word-by-word interleave. A larger chunk keeps a
+// fetched sector useful to the lane that fetched it when the lanes of a warp have drifted apart in their models.
+#ifndef AB_CHUNK
+#define AB_CHUNK 1
+#endif
+#if AB_CHUNK == 1 || AB_STRIDE == 1
+#define AB_WORD_INDEX(i) ((size_t)(i) * AB_STRIDE)
+#else
+#define AB_WORD_INDEX(i) ((size_t)((i) / AB_CHUNK) * (AB_STRIDE * AB_CHUNK) + (size_t)((i) % AB_CHUNK))
+#endif
+
 namespace ab200 { inline namespace AB_VARIANT {
 
 #define AB_TW (AB_KW + 1)   // words per term
@@ -108,10 +120,10 @@ extern long long g_aw_count;
 extern long long g_sec[16];
 struct SecTimer { int id; long long start; SecTimer(int i) : id(i), start(g_aw_count) { } ~SecTimer() { g_sec[id] += g_aw_count - start; } };
 #define AB_SECTION(id) SecTimer sec_timer_##id(id)
-AB_HD uint64_t& aw(Ctx& c, int i) { ++g_aw_count; return c.A.base[(size_t)i * AB_STRIDE]; }
+AB_HD uint64_t& aw(Ctx& c, int i) { ++g_aw_count; return c.A.base[AB_WORD_INDEX(i)]; }
 #else
 #define AB_SECTION(id)
-AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[(size_t)i * AB_STRIDE]; }
+AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[AB_WORD_INDEX(i)]; }
 #endif
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 
@@ -268,7 +280,9 @@ AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) {
 // order, as in the reference), and the error chain e <- up(up(e + t[s].e) + te[s]/2) is applied in stream order.
 // A coefficient that cancels to exactly zero is dropped, as _add2 does, and a later stream re-creates the term.
 // This removes the O(#streams x |r|) re-copying of the accumulator that dominates the reference's _mul4/_compose2.
+#ifndef AB_MAXSTREAMS
 #define AB_MAXSTREAMS 8
+#endif
 AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
     TM out = tm_begin(c, r.as, acc);
     int ri = 0;
@@ -343,7 +357,9 @@ AB_HD TM tm_plus_assign(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x,
 // Product stream b of a block is x-term (i0+b) times y; its head is the next product that is not discarded.
 // Discarded products are folded into the stream's truncation error while the cursor advances, in y order, exactly
 // as the inner loop of _mul4 does.
+#ifndef AB_MULSTREAMS
 #define AB_MULSTREAMS 8
+#endif
 AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     AB_SECTION(0);
     const int m = c.A.top;
