@@ -14,27 +14,37 @@
 
 using namespace ab200;
 
-// launchers of the two-word-key build (ab200_kernels_kw2.cu); plain signatures so that this file, compiled against
-// the AB_KW=1 headers, can call them
+// Builds of the evolution kernel (one translation unit each, inline namespace = variant name). Plain signatures, so
+// that this file, compiled against the AB_KW=1 headers, can call the two-word-key build as well.
+//   kw1   one-word MultiIndex keys (<= 7 set parameters), 255 registers, 8-way merges: lowest latency per cell
+//   s4    one-word keys, 80 registers (24 resident warps per SM), 4-way merges: best for frontiers that fill the device
+//   kw2   two-word keys (<= 15 set parameters) for systems with more than 2 state variables
+//   t6, t8, c4, s4c4, s4c16   tuning builds kept for the measurements in profiles/ (AB200_TUNE=<name>)
 #define AB_DECL_VARIANT(ns) namespace ab200 { namespace ns { \
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen); \
-int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
-                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach, \
+int dev_evolve_slots_v(int n_cells, int quarter_waves, char* errbuf, int errlen); \
+int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
+                        uint64_t* arena, int arena_words, unsigned int* next_cell, double* reach, int32_t* reach_loc, int32_t* n_reach, \
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
+AB_DECL_VARIANT(kw2)
 AB_DECL_VARIANT(t6)
 AB_DECL_VARIANT(t8)
 AB_DECL_VARIANT(s4)
 AB_DECL_VARIANT(c4)
 AB_DECL_VARIANT(s4c4)
 AB_DECL_VARIANT(s4c16)
-namespace ab200 { namespace kw2 {
-int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen);
-int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
-                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
-                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
-                        char* errbuf, int errlen);
-} }
+struct EvolveBuild {
+    const char* name;
+    int (*upload)(const void*, char*, int);
+    int (*slots)(int, int, char*, int);
+    int (*launch)(cudaStream_t, int, int, const int32_t*, const double*, const void*, uint64_t*, int, unsigned int*, double*, int32_t*, int32_t*,
+                  double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
+};
+#define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_slots_v, ab200::ns::dev_launch_evolve_v }
+static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(t6), AB_BUILD(t8), AB_BUILD(c4), AB_BUILD(s4c4), AB_BUILD(s4c16) };
+static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
+static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
 
 static_assert(AB200_MAX_DIM == AB_MAXN, "header / kernel dimension mismatch");
 
@@ -120,14 +130,7 @@ extern "C" int ab200_set_system_text(ab200_ctx* ctx, const char* text) {
     if (!e.empty()) { ctx->err = "system description: " + e; return AB200_E_ARGUMENT; }
     ctx->have_system = true;
     CTX_CK(cudaSetDevice(ctx->device));
-    DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::kw2::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t6::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t8::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::s4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::s4c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::s4c16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
 extern "C" int ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims) {
@@ -155,14 +158,7 @@ extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max
     L.max_step = max_step;
     for (int i = 0; i < L.n; ++i) { L.ref_width[i] = ref_widths[i]; L.grid_origin[i] = grid_origin[i]; L.grid_length[i] = grid_lengths[i]; }
     CTX_CK(cudaSetDevice(ctx->device));
-    DEV_CK(dev_upload_system(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::kw2::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t6::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::t8::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::s4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::s4c4::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
-    DEV_CK(ab200::s4c16::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
+    for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
 // Key window: equal share of the 64 bits after the location field, centred on the grid origin.
@@ -229,42 +225,33 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         if (S.ttl_seconds > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > S.ttl_seconds) {
             ctx->err = "time to live exceeded"; if (status) *status = stl; return AB200_E_TIMEOUT; }
         const int nb = (int)std::min<uint64_t>(S.batch_cells, n_cells - b0);
-        const int nwarps = (nb + 31) / 32;
         CTX_CK(ctx->d_loc.ensure(nb)); CTX_CK(ctx->d_box.ensure((size_t)nb * stride));
         CTX_CK(ctx->d_nreach.ensure(nb)); CTX_CK(ctx->d_nfin.ensure(nb)); CTX_CK(ctx->d_status.ensure(nb)); CTX_CK(ctx->d_steps.ensure(nb)); CTX_CK(ctx->d_peak.ensure(nb));
         CTX_CK(ctx->d_reach.ensure((size_t)nb * S.max_boxes * stride)); CTX_CK(ctx->d_fin.ensure((size_t)nb * S.max_boxes * stride));
         CTX_CK(ctx->d_rloc.ensure((size_t)nb * S.max_boxes)); CTX_CK(ctx->d_floc.ensure((size_t)nb * S.max_boxes));
-        CTX_CK(ctx->d_arena.ensure((size_t)nwarps * 32 * S.arena_words));
+        // Build selection: set models have up to max(2n+1,3n) parameters -- one-word keys hold 7, two-word keys 15. Of the
+        // one-word builds, the 255-register one has the lowest latency per cell and wins while the frontier does not fill
+        // the device; beyond that the 80-register build keeps three times as many cells in flight (profiles/r01_variants.md).
+        const bool wide = ctx->sys.desc.loc[0].n > 2;
+        const EvolveBuild* build = find_build(wide ? "kw2" : "kw1");
+        const char* tune = getenv("AB200_TUNE");
+        int quarter_waves = 0;
+        if (const char* qw = getenv("AB200_QUARTER_WAVES")) quarter_waves = atoi(qw);
+        if (!wide) {
+            if (tune && find_build(tune) && strcmp(tune, "kw2")) build = find_build(tune);
+            else if (!tune) {
+                int cap; DEV_CK((cap = build->slots(1 << 30, 0, eb_, sizeof(eb_))) < 0);
+                if (nb > 2 * cap) build = find_build("s4");
+            }
+        }
+        int slots; DEV_CK((slots = build->slots(nb, quarter_waves, eb_, sizeof(eb_))) < 0);
+        CTX_CK(ctx->d_arena.ensure((size_t)slots * S.arena_words));
         CTX_CK(cudaMemcpyAsync(ctx->d_loc.p, loc + b0, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_box.p, boxes + b0 * stride, (size_t)nb * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        // set models have up to max(2n+1,3n) variables: one-word keys hold 7, two-word keys 15
-        const bool wide = ctx->sys.desc.loc[0].n > 2;
-        const char* tune = getenv("AB200_TUNE");
-        if (!wide && tune && !strcmp(tune, "t6")) DEV_CK(ab200::t6::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide && tune && !strcmp(tune, "t8")) DEV_CK(ab200::t8::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide && tune && !strcmp(tune, "s4")) DEV_CK(ab200::s4::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide && tune && !strcmp(tune, "c4")) DEV_CK(ab200::c4::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide && tune && !strcmp(tune, "s4c4")) DEV_CK(ab200::s4c4::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide && tune && !strcmp(tune, "s4c16")) DEV_CK(ab200::s4c16::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else if (!wide) DEV_CK(dev_launch_evolve(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        else DEV_CK(ab200::kw2::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
-                                 ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                 ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+        DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, (unsigned int*)(ctx->d_counters.p + 7),
+                             ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                             ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
         stl.launches += 1;
         CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         std::vector<int32_t> h_status(nb), h_steps(nb), h_peak(nb), h_nreach(nb), h_nfin(nb);

@@ -83,24 +83,44 @@ AB_HD int ws_pack(Ctx& c, WorkingSet& w, int n, int dst) {
     return c.A.top;
 }
 
-// Evolve one enclosure (a box in location loc0) for time P.T. Mirrors _evolution: a FIFO of working sets
+// Evolution of one enclosure (a box in location loc0) for time P.T mirrors _evolution: a FIFO of working sets
 // (std::list<EvolutionData>, popped from the front, successors pushed at the back), kept packed at the bottom of the
-// cell's arena in queue order; everything above the last queued set is scratch.
-AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O) {
+// cell's arena in queue order; everything above the last queued set is scratch. The loop is split into cell_begin /
+// cell_advance (one queue iteration = at most one _evolution_step) so that the kernel can hand a lane its next
+// cell at a step boundary while the other lanes of the warp carry on with theirs.
+struct CellState {
+    WorkingSet q[AB_MAXQ];
+    int nq;
+    int base0;
+    int guard_iter;
+    double init_w[AB_MAXN];
+};
+
+AB_HDN void cell_begin(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellState& st) {
     Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
     const int n0 = S.loc[loc0].n;
-    const int base0 = c.A.top;
-    WorkingSet q[AB_MAXQ];
-    int nq = 1;
+    WorkingSet* q = st.q;
+    st.base0 = c.A.top;
+    st.nq = 1;
     // ---- _evolution_add_initialSet: set_model(box)=scalings(box) with spacial accuracy; time_model(0.0)
     q[0].loc = loc0; q[0].n_events = 0; q[0].p = n0;
     for (int i = 0; i < n0; ++i) { q[0].set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); q[0].set[i].acc = spacial; }
     q[0].time = tm_begin(c, n0, spacial); tm_append(c, q[0].time, key_zero(), 0.0);          // constant(as,0.0): explicit zero term
-    double init_w[AB_MAXN];
-    for (int i = 0; i < n0; ++i) init_w[i] = ivl_width(tm_range(c, q[0].set[i]));   // _indexed_set_models_widths
-    int guard_iter = 0;
-    while (nq > 0 && c.status == ST_OK) {
-        if (++guard_iter > 100000) { fail(c, ST_OUTPUT); break; }
+    for (int i = 0; i < n0; ++i) st.init_w[i] = ivl_width(tm_range(c, q[0].set[i]));   // _indexed_set_models_widths
+    st.guard_iter = 0;
+}
+
+// Pops the front working set: emits it as a final set or takes one _evolution_step. Returns false once the cell is
+// finished (queue empty) or has failed (c.status).
+AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, CellState& st, CellOutput& O) {
+    if (st.nq <= 0 || c.status != ST_OK) return false;
+    if (++st.guard_iter > 100000) { fail(c, ST_OUTPUT); return false; }
+    Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
+    WorkingSet* q = st.q;
+    int& nq = st.nq;
+    const double* init_w = st.init_w;
+    const int base0 = st.base0;
+    do {
         WorkingSet ws = q[0];
         const int qend = c.A.top;                      // end of the last queued set; scratch starts here
         const LocDesc& L = S.loc[ws.loc];
@@ -247,7 +267,14 @@ AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box
         for (int k = 0; k < ns; ++k) { dst = ws_pack(c, succ[k], S.loc[succ[k].loc].n, dst); q[nq - 1 + k] = succ[k]; }
         nq = nq - 1 + ns;
         c.A.top = dst;
-    }
+    } while (0);
+    return nq > 0 && c.status == ST_OK;
+}
+
+AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O) {
+    CellState st;
+    cell_begin(c, S, loc0, box, P, st);
+    while (cell_advance(c, S, P, st, O)) { }
 }
 
 } } // namespace ab200

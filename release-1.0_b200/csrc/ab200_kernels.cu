@@ -190,12 +190,6 @@ int dev_set_stack(size_t bytes, char* errbuf, int errlen) {
     CK(cudaDeviceSetLimit(cudaLimitStackSize, bytes));
     return 0;
 }
-int dev_launch_evolve(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const EvolveParams& P,
-                      uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
-                      double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
-                      char* errbuf, int errlen) {
-    return dev_launch_evolve_v(st, n_cells, cell_loc, cell_box, &P, arena, arena_words, reach, reach_loc, n_reach, fin, fin_loc, n_fin, status, steps, peak, errbuf, errlen);
-}
 int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
                            double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen) {
     if (n_cells == 0) return 0;
