@@ -22,9 +22,9 @@ using namespace ab200;
 //   t6, t8, c4, s4c4, s4c16   tuning builds kept for the measurements in profiles/ (AB200_TUNE=<name>)
 #define AB_DECL_VARIANT(ns) namespace ab200 { namespace ns { \
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen); \
-int dev_evolve_slots_v(int n_cells, int quarter_waves, char* errbuf, int errlen); \
-int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
-                        uint64_t* arena, int arena_words, unsigned int* next_cell, double* reach, int32_t* reach_loc, int32_t* n_reach, \
+int dev_evolve_capacity_v(char* errbuf, int errlen); \
+int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
+                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach, \
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
@@ -37,11 +37,11 @@ AB_DECL_VARIANT(s4c16)
 struct EvolveBuild {
     const char* name;
     int (*upload)(const void*, char*, int);
-    int (*slots)(int, int, char*, int);
-    int (*launch)(cudaStream_t, int, int, const int32_t*, const double*, const void*, uint64_t*, int, unsigned int*, double*, int32_t*, int32_t*,
+    int (*capacity)(char*, int);
+    int (*launch)(cudaStream_t, int, const int32_t*, const double*, const void*, uint64_t*, int, double*, int32_t*, int32_t*,
                   double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
 };
-#define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_slots_v, ab200::ns::dev_launch_evolve_v }
+#define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
 static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(t6), AB_BUILD(t8), AB_BUILD(c4), AB_BUILD(s4c4), AB_BUILD(s4c16) };
 static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
 static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
@@ -235,21 +235,19 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         const bool wide = ctx->sys.desc.loc[0].n > 2;
         const EvolveBuild* build = find_build(wide ? "kw2" : "kw1");
         const char* tune = getenv("AB200_TUNE");
-        int quarter_waves = 0;
-        if (const char* qw = getenv("AB200_QUARTER_WAVES")) quarter_waves = atoi(qw);
         if (!wide) {
             if (tune && find_build(tune) && strcmp(tune, "kw2")) build = find_build(tune);
             else if (!tune) {
-                int cap; DEV_CK((cap = build->slots(1 << 30, 0, eb_, sizeof(eb_))) < 0);
+                int cap; DEV_CK((cap = build->capacity(eb_, sizeof(eb_))) < 0);
                 if (nb > 2 * cap) build = find_build("s4");
             }
         }
-        int slots; DEV_CK((slots = build->slots(nb, quarter_waves, eb_, sizeof(eb_))) < 0);
-        CTX_CK(ctx->d_arena.ensure((size_t)slots * S.arena_words));
+        const int nwarps = (nb + 31) / 32;
+        CTX_CK(ctx->d_arena.ensure((size_t)nwarps * 32 * S.arena_words));
         CTX_CK(cudaMemcpyAsync(ctx->d_loc.p, loc + b0, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_box.p, boxes + b0 * stride, (size_t)nb * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, (unsigned int*)(ctx->d_counters.p + 7),
+        DEV_CK(build->launch(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
                              ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
                              ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
         stl.launches += 1;
