@@ -181,7 +181,7 @@ def run_ours(args):
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_cells or 3 * (os.cpu_count() or 1))
+            line["cpu_baseline"] = cpu_baseline(args.cpu_cells or 32 * (os.cpu_count() or 1))
         print(json.dumps(line))
     an.close()
     if world > 1:
@@ -212,7 +212,7 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    n = args.cpu_cells or 3 * (os.cpu_count() or 1)
+    n = args.cpu_cells or 32 * (os.cpu_count() or 1)
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(max(os.cpu_count() or 1, n // 3))
     t0 = time.perf_counter()
