@@ -157,7 +157,8 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     arena_peak_words = st.arena_peak
     alg_bytes_per_step = 2.0 * arena_peak_words * 8.0
-    achieved = (steps_total / args.steps) * alg_bytes_per_step / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
+    # per launch on ONE GPU (this rank's steps; ev_ms is the max over ranks), so that frac is against one GPU's peak
+    achieved = (steps / args.steps) * alg_bytes_per_step / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
     fp64 = None
     try:
         fp64 = ev.probe_fp64()

@@ -23,6 +23,11 @@ E_NAMES = {
     9: "WorkingSetTooLargeException", 100: "CudaError", 101: "ArgumentError", 102: "KeySpaceError", 103: "TimeoutException",
 }
 
+AB200_OK = 0
+AB200_E_SQRT, AB200_E_DIVZERO, AB200_E_DOMAIN, AB200_E_BOUNDER, AB200_E_ARENA, AB200_E_OUTPUT, AB200_E_UNSUPPORTED, \
+    AB200_E_IMPLICIT, AB200_E_WORKING_SETS = 1, 2, 3, 4, 5, 6, 7, 8, 9
+AB200_E_CUDA, AB200_E_ARGUMENT, AB200_E_KEYSPACE, AB200_E_TIMEOUT = 100, 101, 102, 103
+
 EXPORTS = [
     "ab200_default_settings", "ab200_ctx_create", "ab200_ctx_destroy", "ab200_last_error", "ab200_set_system_text",
     "ab200_system_info", "ab200_location_index", "ab200_set_settings", "ab200_set_location_tuning", "ab200_set_accuracy",

@@ -162,3 +162,71 @@ def test_flow_bounds_facade(pkg):
         assert np.all(b[:, 0] <= boxes[:, 0]) and np.all(b[:, 1] >= boxes[:, 1])
     finally:
         ev.close()
+
+
+def test_edge_cases_and_error_codes(pkg):
+    """Empty frontier, first-failing-cell error reporting (include/workers.h:129-139,159-166) and device capacity limits."""
+    d = golden_io.load_dump("vanderpol_cells_acc3.txt")
+    ev = _evolver(pkg, d, arena_words=131072)
+    try:
+        T, events = d["config"]["T"], d["config"]["events"]
+        # empty frontier -> two empty sets, no launch of the evolution kernel needed
+        r, e = ev.upper_reach_evolve(np.zeros((0,), dtype=np.int32), np.zeros((0, pkg.BOX_STRIDE)), T, events)
+        assert len(r) == 0 and len(e) == 0
+        cells = d["cells"][:3]
+        locs = np.zeros((len(cells),), dtype=np.int32)
+        boxes = pkg.pack_boxes([c["box"] for c in cells], 2)
+        # an unknown location is rejected before anything is launched
+        with pytest.raises(pkg.Ab200Error) as ei:
+            ev.upper_reach_evolve(np.array([0, 7, 0], dtype=np.int32), boxes, T, events)
+        assert ei.value.code == pkg.AB200_E_ARGUMENT
+        # a scratch arena that is too small fails the lap with the index of the first failing cell, no partial result
+        ev.set_settings(arena_words=512)
+        with pytest.raises(pkg.Ab200Error) as ei:
+            ev.upper_reach_evolve(locs, boxes, T, events)
+        assert ei.value.code == pkg.AB200_E_ARENA and ev.last_status.cell == 0
+        # too few output boxes per cell
+        ev.set_settings(arena_words=131072, max_boxes=2)
+        with pytest.raises(pkg.Ab200Error) as ei:
+            ev.upper_reach_evolve(locs, boxes, T, events)
+        assert ei.value.code == pkg.AB200_E_OUTPUT
+        # and the same context still works afterwards
+        ev.set_settings(max_boxes=192)
+        r, e = ev.upper_reach_evolve(locs, boxes, T, events)
+        assert len(r) > 0 and len(e) > 0
+        # a degenerate (point) cell is a valid enclosure (the bounder widens singleton coordinates by 1e-16)
+        r1, e1 = ev.upper_reach_evolve(np.zeros((1,), dtype=np.int32), pkg.pack_boxes([[1.0, 1.0, 1.0, 1.0]], 2), T, events)
+        assert len(r1) > 0
+    finally:
+        ev.close()
+
+
+def test_round_trip_properties_at_scale(pkg):
+    """Size-independent properties on a frontier the oracle could not finish in test time: (1) the lap of a union of
+    frontiers is the union of the laps (cells are independent units); (2) evolving a frontier in one call or in small
+    batches gives identical key arrays; (3) keys come back sorted and duplicate-free; (4) every frontier cell is
+    contained in the reach set of its own lap (the flow tube starts on the cell)."""
+    an = pkg.HybridReachabilityAnalyser(_system(), [-3.0, 3.0, -3.0, 3.0], 6, settings={"arena_words": 16384})
+    try:
+        own = an.discretise({"loc": [-0.8, 0.8, -0.8, 0.8]})
+        _, cells = an.enumerate(own, mince=True)
+        n = cells.shape[0]
+        assert n == len(own) and n > 2000
+        locs = np.zeros((n,), dtype=np.int32)
+        boxes = pkg.pack_boxes(cells, 2)
+        an.upper_reach_evolve({"loc": [1.0, 1.001, 1.0, 1.001]}, 1e-3, 5)       # uploads the evolver tuning of a lap
+        T = an.lock_to_grid_time / 4
+        ev = an.evolver
+        r_all, e_all = ev.upper_reach_evolve(locs, boxes, T, 5)
+        assert np.all(np.diff(r_all.keys) > 0) and np.all(np.diff(e_all.keys) > 0)
+        half = n // 2
+        r_a, e_a = ev.upper_reach_evolve(locs[:half], boxes[:half], T, 5)
+        r_b, e_b = ev.upper_reach_evolve(locs[half:], boxes[half:], T, 5)
+        assert np.array_equal(np.union1d(r_a.keys, r_b.keys), r_all.keys)
+        assert np.array_equal(np.union1d(e_a.keys, e_b.keys), e_all.keys)
+        ev.set_settings(batch_cells=256)
+        r_c, e_c = ev.upper_reach_evolve(locs, boxes, T, 5)
+        assert np.array_equal(r_c.keys, r_all.keys) and np.array_equal(e_c.keys, e_all.keys)
+        assert np.isin(own.keys, r_all.keys).all()
+    finally:
+        an.close()
