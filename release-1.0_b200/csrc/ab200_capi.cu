@@ -31,6 +31,8 @@ AB_DECL_VARIANT(kw2)
 AB_DECL_VARIANT(t6)
 AB_DECL_VARIANT(t8)
 AB_DECL_VARIANT(s4)
+AB_DECL_VARIANT(s4m16)
+AB_DECL_VARIANT(s2)
 AB_DECL_VARIANT(c4)
 AB_DECL_VARIANT(s4c4)
 AB_DECL_VARIANT(s4c16)
@@ -42,7 +44,7 @@ struct EvolveBuild {
                   double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
-static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(t6), AB_BUILD(t8), AB_BUILD(c4), AB_BUILD(s4c4), AB_BUILD(s4c16) };
+static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(s4m16), AB_BUILD(s2), AB_BUILD(t6), AB_BUILD(t8), AB_BUILD(c4), AB_BUILD(s4c4), AB_BUILD(s4c16) };
 static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
 static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
 
