@@ -19,7 +19,7 @@ using namespace ab200;
 //   kw1   one-word MultiIndex keys (<= 7 set parameters), 255 registers, 8-way merges: lowest latency per cell
 //   s4    one-word keys, 80 registers (24 resident warps per SM), 4-way merges: best for frontiers that fill the device
 //   kw2   two-word keys (<= 15 set parameters) for systems with more than 2 state variables
-//   t6, t8, c4, s4c4, s4c16   tuning builds kept for the measurements in profiles/ (AB200_TUNE=<name>)
+// AB200_TUNE=<name> forces a one-word build (measurements in profiles/r01_variants.md).
 #define AB_DECL_VARIANT(ns) namespace ab200 { namespace ns { \
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen); \
 int dev_evolve_capacity_v(char* errbuf, int errlen); \
@@ -28,14 +28,7 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, c
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
-AB_DECL_VARIANT(t6)
-AB_DECL_VARIANT(t8)
 AB_DECL_VARIANT(s4)
-AB_DECL_VARIANT(s4m16)
-AB_DECL_VARIANT(s2)
-AB_DECL_VARIANT(c4)
-AB_DECL_VARIANT(s4c4)
-AB_DECL_VARIANT(s4c16)
 struct EvolveBuild {
     const char* name;
     int (*upload)(const void*, char*, int);
@@ -44,7 +37,7 @@ struct EvolveBuild {
                   double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
-static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(s4m16), AB_BUILD(s2), AB_BUILD(t6), AB_BUILD(t8), AB_BUILD(c4), AB_BUILD(s4c4), AB_BUILD(s4c16) };
+static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4) };
 static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
 static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
 
