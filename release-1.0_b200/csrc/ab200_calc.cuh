@@ -283,15 +283,14 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                 const int t = t0 + b;
                 Key a = tm_key(c, x[i], t);
                 double cv = tm_val(c, x[i], t);
-                const int mt = c.A.top;
                 TM tt = tm_const(c, as, cv, acc0);           // t=c
                 for (int j = 0; j < nys; ++j) {
                     int e = key_get(a, j);
                     if (e > 0) {
+                        // t=t*powers[j][e]; the factor just consumed stays below as dead space until the slide
+                        // after tm_add_many reclaims the whole batch (cheaper than moving every product down)
                         TM pw = ph_load(c, tab[j] + 2 * e, as, ys[j].acc);
-                        TM pr = tm_mul(c, tt, pw, ys[j].acc);
-                        tm_slide(c, pr, mt);
-                        tt = pr;
+                        tt = tm_mul(c, tt, pw, ys[j].acc);
                     }
                 }
                 c.A.top = tt.off + tt.n * AB_TW;

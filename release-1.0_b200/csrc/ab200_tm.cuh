@@ -127,6 +127,13 @@ AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[AB_WORD_INDEX(i)]; }
 #endif
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 
+#ifdef AB_MUL_HIST
+extern long long g_calls[16], g_words[16];   // development counters (tests/tools/hostdbg.cpp)
+#define AB_CALL(id, w) do { g_calls[id]++; g_words[id] += (w); } while (0)
+#else
+#define AB_CALL(id, w)
+#endif
+
 struct TM {
     int off;      // first word in the arena
     int n;        // number of terms
@@ -153,7 +160,7 @@ AB_HD void tm_append(Ctx& c, TM& r, const Key& k, double v) {
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
 }
 // Move model x (anywhere at or above dst) down to word offset dst and set the arena top just past it.
-AB_HD void tm_slide(Ctx& c, TM& x, int dst) {
+AB_HD void tm_slide(Ctx& c, TM& x, int dst) { AB_CALL(2, x.off == dst ? 0 : x.n);
     if (x.off != dst) {
         int nw = x.n * AB_TW;
         for (int i = 0; i < nw; ++i) aw(c, dst + i) = aw(c, x.off + i);
@@ -161,7 +168,7 @@ AB_HD void tm_slide(Ctx& c, TM& x, int dst) {
     }
     c.A.top = dst + x.n * AB_TW;
 }
-AB_HD TM tm_copy(Ctx& c, const TM& x) {
+AB_HD TM tm_copy(Ctx& c, const TM& x) { AB_CALL(3, x.n);
     TM r = tm_begin(c, x.as, x.acc);
     int nw = x.n * AB_TW;
     if (r.off + nw > c.A.limit) { fail(c, ST_ARENA); return r; }
@@ -177,7 +184,7 @@ AB_HD int tm_degree(Ctx& c, const TM& x) { return x.n == 0 ? 0 : key_deg(tm_key(
 // ---- in-place scalar operations -------------------------------------------------------------------------------
 
 // _scal(TaylorModel&, Float) src/taylor_model.cpp:241-273
-AB_HDN void tm_scal(Ctx& c, TM& r, double s) {
+AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_CALL(4, r.n);
     if (s == 0) { r.n = 0; r.e = 0; return; }     // (arena words stay allocated; harmless)
     if (s == 1) return;
     if (s == 2 || s == 0.5) {
@@ -197,7 +204,7 @@ AB_HDN void tm_scal(Ctx& c, TM& r, double s) {
     c.rnd = RN;
 }
 // _scal(TaylorModel&, Interval) src/taylor_model.cpp:276-314
-AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) {
+AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_CALL(5, r.n);
     double te = 0, cu = s.u, mcl = -s.l;
     for (int i = 0; i < r.n; ++i) {
         double rv = tm_val(c, r, i), u, ml;
@@ -249,7 +256,7 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) {
 
 // _add2 (src/taylor_model.cpp:487-530): merge by key; rounding error of coincident terms accumulated upward in
 // key order. Result accuracy is supplied by the caller (the reference's operator+ uses a fresh default).
-AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) {
+AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_CALL(0, x.n + y.n);
     TM r = tm_begin(c, x.as, acc);
     double te = 0.0;
     int i = 0, j = 0;
@@ -283,7 +290,7 @@ AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) {
 #ifndef AB_MAXSTREAMS
 #define AB_MAXSTREAMS 8
 #endif
-AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
+AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B);
     TM out = tm_begin(c, r.as, acc);
     int ri = 0;
     int ti[AB_MAXSTREAMS];
@@ -333,7 +340,7 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) {
     return out;
 }
 // neg (src/taylor_model.cpp:1530-1537): fresh default accuracy
-AB_HDN TM tm_neg(Ctx& c, const TM& x) {
+AB_HDN TM tm_neg(Ctx& c, const TM& x) { AB_CALL(6, x.n);
     TM r = tm_begin(c, x.as, acc_default());
     for (int i = 0; i < x.n; ++i) tm_append(c, r, tm_key(c, x, i), -tm_val(c, x, i));
     r.e = x.e;
@@ -360,10 +367,64 @@ AB_HD TM tm_plus_assign(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x,
 #ifndef AB_MULSTREAMS
 #define AB_MULSTREAMS 8
 #endif
+#ifdef AB_MUL_HIST
+extern long long g_mul_hist[8][8];   // [log2 bucket of x.n][log2 bucket of y.n]
+extern long long g_mul_prod[8][8];
+#endif
 AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     AB_SECTION(0);
+#ifdef AB_MUL_HIST
+    { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
+#endif
     const int m = c.A.top;
     TM r = tm_begin(c, x.as, acc);          // empty accumulator at m
+    if (x.n == 1 || y.n == 1) {
+        // A single-term factor (constants, variables and monomials of the op tapes: about 1400 of the 1600 products
+        // of a van der Pol step). Adding a fixed key keeps the key order, so the product streams never meet: the
+        // result is written directly and the error chain of the general path reduces to the truncation terms.
+        double e = 0.0, xs = 0.0, ys = 0.0;
+        if (x.n == 1) {
+            const Key xa = tm_key(c, x, 0); const double xv = tm_val(c, x, 0), axv = dabs(xv);
+            double tte = 0.0;
+            for (int j = 0; j < y.n; ++j) {
+                const double yv = tm_val(c, y, j); const Key ta = key_add(xa, tm_key(c, y, j));
+                const double tv = mul_rn(xv, yv);
+                ys = add_ru(ys, dabs(yv));
+                if (acc_discard(acc, ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
+                else tm_append(c, r, ta, tv);
+            }
+            e = add_ru(tte, tte / 2);
+            xs = axv;
+        } else {
+            const Key ya = tm_key(c, y, 0); const double yv = tm_val(c, y, 0), ayv = dabs(yv);
+            for (int i = 0; i < x.n; ++i) {
+                const double xv = tm_val(c, x, i); const Key ta = key_add(tm_key(c, x, i), ya);
+                const double tv = mul_rn(xv, yv);
+                xs = add_ru(xs, dabs(xv));
+                if (acc_discard(acc, ta, tv)) { const double tte = mul_ru(dabs(xv), ayv); e = add_ru(e, add_ru(tte, tte / 2)); }
+                else tm_append(c, r, ta, tv);
+            }
+            ys = ayv;
+        }
+        r.e = add_ru(e, add_ru(add_ru(mul_ru(xs, y.e), mul_ru(ys, x.e)), mul_ru(x.e, y.e)));
+        c.rnd = RN;
+        c.A.top = r.off + r.n * AB_TW;
+        return r;
+    }
+    // Accumulator placement. Each batch reads the accumulator r and writes a new one; instead of building it above r and
+    // sliding it back down every time, two regions [m, H) and [H, ...) are used alternately. Both hold any possible
+    // accumulator: its keys are distinct monomials of degree <= min(maxdeg, deg x + deg y) in x.as variables, and there
+    // are at most x.n*y.n of them. If the arena cannot hold both regions the slide per batch is kept.
+    int H = -1;
+    {
+        int D = tm_degree(c, x) + tm_degree(c, y); if (D > acc.maxdeg) D = acc.maxdeg;
+        long long cap = 1;
+        for (int i = 1; i <= x.as && cap < (1LL << 24); ++i) cap = cap * (D + i) / i;
+        const long long prod = (long long)x.n * (long long)y.n;
+        if (prod < cap) cap = prod;
+        const long long words = cap * AB_TW;
+        if ((long long)m + 2 * words <= (long long)c.A.limit) H = m + (int)words;
+    }
     for (int i0 = 0; i0 < x.n; i0 += AB_MULSTREAMS) {
         const int B = (x.n - i0 < AB_MULSTREAMS) ? (x.n - i0) : AB_MULSTREAMS;
         Key xa[AB_MULSTREAMS], hk[AB_MULSTREAMS];
@@ -384,7 +445,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 else { hk[b] = ta_; hv[b] = tv_; live[b] = true; break; } } } while (0)
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) AB_ADVANCE(b);
-        c.A.top = r.off + r.n * AB_TW;
+        c.A.top = (H >= 0) ? ((r.n > 0 && r.off == m) ? H : m) : r.off + r.n * AB_TW;
         TM out = tm_begin(c, x.as, acc);
         int ri = 0; bool rlive = r.n > 0; Key rk = key_zero(); if (rlive) rk = tm_key(c, r, 0);
         for (;;) {
@@ -414,9 +475,10 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) { double tev = add_ru(tte[b], tte[b] / 2); e = add_ru(add_ru(e, tev), te[b] / 2); }
         out.e = e;
-        tm_slide(c, out, m);
+        if (H < 0) tm_slide(c, out, m);
         r = out;
     }
+    if (r.off != m) tm_slide(c, r, m);
     double xs = 0, ys = 0;
     for (int i = 0; i < x.n; ++i) xs = add_ru(xs, dabs(tm_val(c, x, i)));
     for (int j = 0; j < y.n; ++j) ys = add_ru(ys, dabs(tm_val(c, y, j)));
@@ -450,7 +512,7 @@ AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) {
     c.rnd = RN;
 }
 // range() = _range1 src/taylor_model.cpp:1566-1579
-AB_HDN Ivl tm_range(Ctx& c, const TM& x) {
+AB_HDN Ivl tm_range(Ctx& c, const TM& x) { AB_CALL(7, x.n);
     double t = x.e, v = 0.0;
     for (int i = 0; i < x.n; ++i) {
         if (key_deg(tm_key(c, x, i)) == 0) v = tm_val(c, x, i);

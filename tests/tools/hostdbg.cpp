@@ -18,6 +18,11 @@
 #include <algorithm>
 
 using namespace ab200;
+#ifdef AB_MUL_HIST
+long long ab200::g_mul_hist[8][8] = {{0}};
+long long ab200::g_calls[16] = {0}, ab200::g_words[16] = {0};
+long long ab200::g_mul_prod[8][8] = {{0}};
+#endif
 #ifdef AB_COUNT_ACCESS
 long long ab200::g_aw_count = 0;
 long long ab200::g_sec[16] = {0};
@@ -57,6 +62,7 @@ int main(int argc, char** argv) {
         else if (t == "x") { cells.back().err = line; }
         else if (t == "dreach") { dcur = &cells.back().dreach; cells.back().have_disc = 1; }
         else if (t == "dfinal") { dcur = &cells.back().dfinal; }
+        else if (t == "union" || t == "ureach" || t == "ufinal") { dcur = 0; }
         else if (t == "c" && dcur) { std::vector<double> b; std::string v; while (in >> v) b.push_back(strtod(v.c_str(), 0)); dcur->push_back(b); }
         else if (t == "config") { }
     }
@@ -131,6 +137,13 @@ int main(int argc, char** argv) {
         } else if (verbose) printf("cell %zu ok: %d reach, %d final, %d steps\n", ci, O.n_reach, O.n_final, O.steps);
     }
     printf("cells compared %d, mismatching %d, steps %ld, arena peak words %d\n", done, bad, total_steps, peak);
+#ifdef AB_MUL_HIST
+    { const char* nm[] = {"add2", "add_many(r terms)", "slide(moved)", "copy", "scal(Float)", "scal(Interval)", "neg", "range", "-", "add_many(streams)"};
+      for (int i = 0; i < 10; ++i) printf("  %-20s %8.1f calls/step %10.1f terms/step\n", nm[i], (double)g_calls[i] / total_steps, (double)g_words[i] / total_steps); }
+    printf("tm_mul calls by (x.n bucket rows, y.n bucket cols; bucket b = n<=2^b), per step; then products per step\n");
+    for (int a = 0; a < 8; ++a) { for (int b = 0; b < 8; ++b) printf(" %7.1f", (double)g_mul_hist[a][b] / total_steps); printf("\n"); }
+    for (int a = 0; a < 8; ++a) { for (int b = 0; b < 8; ++b) printf(" %7.0f", (double)g_mul_prod[a][b] / total_steps); printf("\n"); }
+#endif
 #ifdef AB_COUNT_ACCESS
     printf("arena word accesses: %lld (%.0f per step)\n", g_aw_count, (double)g_aw_count / total_steps);
     const char* names[] = {"tm_mul(incl)", "tm_compose(incl)", "tm_split", "flow_model(incl)", "flow_apply(incl)", "integration_step", "reachability_step"};
