@@ -249,12 +249,14 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         std::vector<int32_t> h_status(nb), h_steps(nb), h_peak(nb), h_nreach(nb), h_nfin(nb);
         CTX_CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        const char* dump_steps = getenv("AB200_DUMP_STEPS");      // profiling aid: per-cell _evolution_step counts of the last lap
         CTX_CK(cudaMemcpyAsync(h_steps.data(), ctx->d_steps.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_peak.data(), ctx->d_peak.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_nreach.data(), ctx->d_nreach.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_nfin.data(), ctx->d_nfin.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); evolve_ms += ms;
+        if (dump_steps) { if (FILE* f = fopen(dump_steps, b0 == 0 ? "wb" : "ab")) { fwrite(h_steps.data(), sizeof(int32_t), (size_t)nb, f); fclose(f); } }
         for (int i = 0; i < nb; ++i) {
             stl.steps += h_steps[i];
             if (h_peak[i] > stl.arena_peak) stl.arena_peak = h_peak[i];
