@@ -29,6 +29,8 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, c
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
 AB_DECL_VARIANT(s4)
+AB_DECL_VARIANT(m16)
+AB_DECL_VARIANT(m8)
 struct EvolveBuild {
     const char* name;
     int (*upload)(const void*, char*, int);
@@ -37,7 +39,7 @@ struct EvolveBuild {
                   double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
-static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4) };
+static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(m16), AB_BUILD(m8) };
 static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
 static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
 

@@ -172,7 +172,6 @@ AB_HD uint64_t& aw(Ctx& c, int i) { ++g_aw_count; return c.A.base[AB_WORD_INDEX(
 AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[AB_WORD_INDEX(i)]; }
 #endif
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
-
 #ifdef AB_MUL_HIST
 extern long long g_calls[16], g_words[16];   // development counters (tests/tools/hostdbg.cpp)
 #define AB_CALL(id, w) do { g_calls[id]++; g_words[id] += (w); } while (0)
@@ -193,6 +192,12 @@ AB_HD double tm_val(Ctx& c, const TM& x, int i) { return u2d(aw(c, x.off + i * A
 AB_HD void tm_set_val(Ctx& c, const TM& x, int i, double v) { aw(c, x.off + i * AB_TW + AB_KW) = d2u(v); }
 AB_HD void tm_set_key(Ctx& c, const TM& x, int i, const Key& k) { for (int j = 0; j < AB_KW; ++j) aw(c, x.off + i * AB_TW + j) = k.w[j]; }
 AB_HD int tm_end(const TM& x) { return x.off + x.n * AB_TW; }
+
+// The hot loops below work on copies of the context and handle fields (arena base, limit, offsets, counts, accuracy)
+// held in locals: through `Ctx&` / `const TM&` the compiler reloads them from the stack around every scratch access.
+AB_HD Key bkey(const uint64_t* base, int w) { Key k; for (int j = 0; j < AB_KW; ++j) k.w[j] = base[AB_WORD_INDEX(w + j)]; return k; }
+AB_HD double bval(const uint64_t* base, int w) { return u2d(base[AB_WORD_INDEX(w + AB_KW)]); }
+AB_HD void bput(uint64_t* base, int w, const Key& k, double v) { for (int j = 0; j < AB_KW; ++j) base[AB_WORD_INDEX(w + j)] = k.w[j]; base[AB_WORD_INDEX(w + AB_KW)] = d2u(v); }
 
 // Begin a model at the arena top; append() grows it. Only the most recently begun model may be appended to.
 AB_HD TM tm_begin(Ctx& c, int as, Acc acc) { TM r; r.off = c.A.top; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc; return r; }
@@ -219,8 +224,9 @@ AB_HD void arena_mark_peak(Ctx& c) { if (c.A.top > c.A.peak) c.A.peak = c.A.top;
 // Move model x (anywhere at or above dst) down to word offset dst and set the arena top just past it.
 AB_HD void tm_slide(Ctx& c, TM& x, int dst) { AB_CALL(2, x.off == dst ? 0 : x.n);
     if (x.off != dst) {
-        int nw = x.n * AB_TW;
-        for (int i = 0; i < nw; ++i) aw(c, dst + i) = aw(c, x.off + i);
+        const int nw = x.n * AB_TW, src = x.off;
+        uint64_t* const base = c.A.base;
+        for (int i = 0; i < nw; ++i) base[AB_WORD_INDEX(dst + i)] = base[AB_WORD_INDEX(src + i)];
         x.off = dst;
     }
     c.A.top = dst + x.n * AB_TW;
@@ -229,7 +235,8 @@ AB_HD TM tm_copy(Ctx& c, const TM& x) { AB_CALL(3, x.n);
     TM r = tm_begin(c, x.as, x.acc);
     int nw = x.n * AB_TW;
     if (r.off + nw > c.A.limit) { fail(c, ST_ARENA); return r; }
-    for (int i = 0; i < nw; ++i) aw(c, r.off + i) = aw(c, x.off + i);
+    { uint64_t* const base = c.A.base; const int dst = r.off, src = x.off;
+      for (int i = 0; i < nw; ++i) base[AB_WORD_INDEX(dst + i)] = base[AB_WORD_INDEX(src + i)]; }
     r.n = x.n; r.e = x.e;
     c.A.top = r.off + nw;
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
@@ -348,18 +355,21 @@ AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_CALL(0, x.n + 
 #define AB_MAXSTREAMS 8
 #endif
 AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B);
-    TM out = tm_begin(c, r.as, acc);
-    int ri = 0;
-    int ti[AB_MAXSTREAMS];
+    uint64_t* const base = c.A.base;
+    const int limit = c.A.limit;
+    const int ooff = c.A.top;
+    int on = 0;
+    bool overflow = false;
+    int tw[AB_MAXSTREAMS], tend[AB_MAXSTREAMS];      // word cursor and end of every stream
     double te[AB_MAXSTREAMS];
     SKey hs[AB_MAXSTREAMS];
-    int toff[AB_MAXSTREAMS], tn[AB_MAXSTREAMS];
     #pragma unroll
     for (int s = 0; s < AB_MAXSTREAMS; ++s) {
-        ti[s] = 0; te[s] = 0.0; hs[s] = skey_dead(); toff[s] = 0; tn[s] = 0;
-        if (s < B) { toff[s] = t[s].off; tn[s] = t[s].n; if (tn[s] > 0) { Key k; for (int w = 0; w < AB_KW; ++w) k.w[w] = aw(c, toff[s] + w); hs[s] = skey(k); } }
+        te[s] = 0.0; hs[s] = skey_dead(); tw[s] = 0; tend[s] = 0;
+        if (s < B) { tw[s] = t[s].off; tend[s] = t[s].off + t[s].n * AB_TW; if (tw[s] < tend[s]) hs[s] = skey(bkey(base, tw[s])); }
     }
-    SKey rs = r.n > 0 ? skey(tm_key(c, r, 0)) : skey_dead();
+    int rw = r.off; const int rend = r.off + r.n * AB_TW;
+    SKey rs = rw < rend ? skey(bkey(base, rw)) : skey_dead();
     for (;;) {
         // smallest key among the heads
         SKey mk = rs;
@@ -369,25 +379,28 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CAL
         bool present = false;
         double cur = 0.0;
         if (skey_eq(rs, mk)) {
-            cur = tm_val(c, r, ri); present = true;
-            ++ri; rs = ri < r.n ? skey(tm_key(c, r, ri)) : skey_dead();
+            cur = bval(base, rw); present = true;
+            rw += AB_TW; rs = rw < rend ? skey(bkey(base, rw)) : skey_dead();
         }
         #pragma unroll
         for (int s = 0; s < AB_MAXSTREAMS; ++s) {
             if (!skey_eq(hs[s], mk)) continue;
-            double tv = u2d(aw(c, toff[s] + ti[s] * AB_TW + AB_KW));
+            double tv = bval(base, tw[s]);
             if (present) {
                 double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
                 te[s] = add_ru(te[s], add_ru(u, ml));
                 cur = add_rn(cur, tv);
                 if (cur == 0) present = false;
             } else { cur = tv; present = true; }
-            ++ti[s];
-            if (ti[s] < tn[s]) { Key k; for (int w = 0; w < AB_KW; ++w) k.w[w] = aw(c, toff[s] + ti[s] * AB_TW + w); hs[s] = skey(k); } else hs[s] = skey_dead();
+            tw[s] += AB_TW;
+            hs[s] = tw[s] < tend[s] ? skey(bkey(base, tw[s])) : skey_dead();
         }
-        if (present) tm_append_quick(c, out, skey_key(mk), cur);
+        if (present) { const int o = ooff + on * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, skey_key(mk), cur); ++on; } }
     }
+    TM out; out.off = ooff; out.n = on; out.as = r.as; out.acc = acc;
+    c.A.top = ooff + on * AB_TW;
     arena_mark_peak(c);
+    if (overflow) fail(c, ST_ARENA);
     double e = r.e;
     for (int s = 0; s < B; ++s) e = add_ru(add_ru(e, t[s].e), te[s] / 2);
     out.e = e;
@@ -431,40 +444,52 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
 #ifdef AB_MUL_HIST
     { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
 #endif
+    uint64_t* const base = c.A.base;
+    const int limit = c.A.limit;
     const int m = c.A.top;
-    TM r = tm_begin(c, x.as, acc);          // empty accumulator at m
-    if (x.n == 1 || y.n == 1) {
+    const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
+    const double xe = x.e, ye = y.e;
+    const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
+    #define AB_DISCARD(k, v) (dabs(v) < sweep || key_deg(k) > maxdeg)
+    bool overflow = false;
+    TM r; r.off = m; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc;          // empty accumulator at m
+    if (xn == 1 || yn == 1) {
         // A single-term factor (constants, variables and monomials of the op tapes: about 1400 of the 1600 products
         // of a van der Pol step). Adding a fixed key keeps the key order, so the product streams never meet: the
         // result is written directly and the error chain of the general path reduces to the truncation terms.
         double e = 0.0, xs = 0.0, ys = 0.0;
-        if (x.n == 1) {
-            const Key xa = tm_key(c, x, 0); const double xv = tm_val(c, x, 0), axv = dabs(xv);
+        int rn = 0;
+        if (xn == 1) {
+            const Key xa = bkey(base, xoff); const double xv = bval(base, xoff), axv = dabs(xv);
             double tte = 0.0;
-            for (int j = 0; j < y.n; ++j) {
-                const double yv = tm_val(c, y, j); const Key ta = key_add(xa, tm_key(c, y, j));
+            for (int j = 0; j < yn; ++j) {
+                const int w = yoff + j * AB_TW;
+                const double yv = bval(base, w); const Key ta = key_add(xa, bkey(base, w));
                 const double tv = mul_rn(xv, yv);
                 ys = add_ru(ys, dabs(yv));
-                if (acc_discard(acc, ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
-                else tm_append_quick(c, r, ta, tv);
+                if (AB_DISCARD(ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
+                else { const int o = m + rn * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, ta, tv); ++rn; } }
             }
             e = add_ru(tte, tte / 2);
             xs = axv;
         } else {
-            const Key ya = tm_key(c, y, 0); const double yv = tm_val(c, y, 0), ayv = dabs(yv);
-            for (int i = 0; i < x.n; ++i) {
-                const double xv = tm_val(c, x, i); const Key ta = key_add(tm_key(c, x, i), ya);
+            const Key ya = bkey(base, yoff); const double yv = bval(base, yoff), ayv = dabs(yv);
+            for (int i = 0; i < xn; ++i) {
+                const int w = xoff + i * AB_TW;
+                const double xv = bval(base, w); const Key ta = key_add(bkey(base, w), ya);
                 const double tv = mul_rn(xv, yv);
                 xs = add_ru(xs, dabs(xv));
-                if (acc_discard(acc, ta, tv)) { const double tte = mul_ru(dabs(xv), ayv); e = add_ru(e, add_ru(tte, tte / 2)); }
-                else tm_append_quick(c, r, ta, tv);
+                if (AB_DISCARD(ta, tv)) { const double tte = mul_ru(dabs(xv), ayv); e = add_ru(e, add_ru(tte, tte / 2)); }
+                else { const int o = m + rn * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, ta, tv); ++rn; } }
             }
             ys = ayv;
         }
-        r.e = add_ru(e, add_ru(add_ru(mul_ru(xs, y.e), mul_ru(ys, x.e)), mul_ru(x.e, y.e)));
+        r.n = rn;
+        r.e = add_ru(e, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
         c.rnd = RN;
-        c.A.top = r.off + r.n * AB_TW;
+        c.A.top = m + rn * AB_TW;
         arena_mark_peak(c);
+        if (overflow) fail(c, ST_ARENA);
         return r;
     }
     // Accumulator placement. Each batch reads the accumulator r and writes a new one; instead of building it above r and
@@ -473,46 +498,50 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     // are at most x.n*y.n of them. If the arena cannot hold both regions the slide per batch is kept.
     int H = -1;
     {
-        int D = tm_degree(c, x) + tm_degree(c, y); if (D > acc.maxdeg) D = acc.maxdeg;
+        int D = tm_degree(c, x) + tm_degree(c, y); if (D > maxdeg) D = maxdeg;
         long long cap = 1;
-        for (int i = 1; i <= x.as && cap < (1LL << 24); ++i) cap = cap * (D + i) / i;
-        const long long prod = (long long)x.n * (long long)y.n;
+        for (int i = 1; i <= as && cap < (1LL << 24); ++i) cap = cap * (D + i) / i;
+        const long long prod = (long long)xn * (long long)yn;
         if (prod < cap) cap = prod;
         const long long words = cap * AB_TW;
-        if ((long long)m + 2 * words <= (long long)c.A.limit) H = m + (int)words;
+        if ((long long)m + 2 * words <= (long long)limit) H = m + (int)words;
     }
-    const int nbatch = (x.n + AB_MULSTREAMS - 1) / AB_MULSTREAMS;
-    for (int i0 = 0; i0 < x.n; i0 += AB_MULSTREAMS) {
-        const int B = (x.n - i0 < AB_MULSTREAMS) ? (x.n - i0) : AB_MULSTREAMS;
+    const int nbatch = (xn + AB_MULSTREAMS - 1) / AB_MULSTREAMS;
+    int roff = m, rn = 0, top_max = m;
+    double re = 0.0;
+    for (int i0 = 0; i0 < xn; i0 += AB_MULSTREAMS) {
+        const int B = (xn - i0 < AB_MULSTREAMS) ? (xn - i0) : AB_MULSTREAMS;
         Key xa[AB_MULSTREAMS];
         SKey hs[AB_MULSTREAMS];
         double xv[AB_MULSTREAMS], hv[AB_MULSTREAMS], tte[AB_MULSTREAMS], te[AB_MULSTREAMS];
-        int cur[AB_MULSTREAMS];        // index of the y term AFTER the head
+        int cur[AB_MULSTREAMS];        // word offset of the y term AFTER the head
         // all per-stream state is indexed with compile-time constants (fully unrolled loops) so it stays in registers
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) {
-            tte[b] = 0.0; te[b] = 0.0; cur[b] = 0; xv[b] = 0.0; xa[b] = key_zero(); hs[b] = skey_dead(); hv[b] = 0.0;
-            if (b < B) { xa[b] = tm_key(c, x, i0 + b); xv[b] = tm_val(c, x, i0 + b); }
+            tte[b] = 0.0; te[b] = 0.0; cur[b] = yoff; xv[b] = 0.0; xa[b] = key_zero(); hs[b] = skey_dead(); hv[b] = 0.0;
+            if (b < B) { xa[b] = bkey(base, xoff + (i0 + b) * AB_TW); xv[b] = bval(base, xoff + (i0 + b) * AB_TW); }
         }
+        const int yend = yoff + yn * AB_TW;
         // advance stream b to its next surviving product
         #define AB_ADVANCE(b) do { hs[b] = skey_dead(); const double axv_ = dabs(xv[b]); \
-            while (cur[b] < y.n) { Key ta_ = key_add(xa[b], tm_key(c, y, cur[b])); double yv_ = tm_val(c, y, cur[b]); ++cur[b]; \
-                double tv_ = mul_rn(xv[b], yv_); \
-                if (acc_discard(acc, ta_, tv_)) tte[b] = add_ru(tte[b], mul_ru(axv_, dabs(yv_))); \
+            while (cur[b] < yend) { const Key ta_ = key_add(xa[b], bkey(base, cur[b])); const double yv_ = bval(base, cur[b]); cur[b] += AB_TW; \
+                const double tv_ = mul_rn(xv[b], yv_); \
+                if (AB_DISCARD(ta_, tv_)) tte[b] = add_ru(tte[b], mul_ru(axv_, dabs(yv_))); \
                 else { hs[b] = skey(ta_); hv[b] = tv_; break; } } } while (0)
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) AB_ADVANCE(b);
         // regions alternate, arranged so that the last batch lands at m and no final move is needed
-        c.A.top = (H >= 0) ? ((((nbatch - 1 - i0 / AB_MULSTREAMS) & 1) == 0) ? m : H) : r.off + r.n * AB_TW;
-        TM out = tm_begin(c, x.as, acc);
-        int ri = 0; SKey rs = r.n > 0 ? skey(tm_key(c, r, 0)) : skey_dead();
+        const int ooff = (H >= 0) ? ((((nbatch - 1 - i0 / AB_MULSTREAMS) & 1) == 0) ? m : H) : roff + rn * AB_TW;
+        int on = 0;
+        int rw = roff; const int rend = roff + rn * AB_TW;
+        SKey rs = rn > 0 ? skey(bkey(base, rw)) : skey_dead();
         for (;;) {
             SKey mk = rs;
             #pragma unroll
             for (int b = 0; b < AB_MULSTREAMS; ++b) if (skey_less(hs[b], mk)) mk = hs[b];
             if (skey_is_dead(mk)) break;
             bool present = false; double cv = 0.0;
-            if (skey_eq(rs, mk)) { cv = tm_val(c, r, ri); present = true; ++ri; rs = ri < r.n ? skey(tm_key(c, r, ri)) : skey_dead(); }
+            if (skey_eq(rs, mk)) { cv = bval(base, rw); present = true; rw += AB_TW; rs = rw < rend ? skey(bkey(base, rw)) : skey_dead(); }
             #pragma unroll
             for (int b = 0; b < AB_MULSTREAMS; ++b) {
                 if (!skey_eq(hs[b], mk)) continue;
@@ -525,25 +554,28 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 } else { cv = tv; present = true; }
                 AB_ADVANCE(b);
             }
-            if (present) tm_append_quick(c, out, skey_key(mk), cv);
+            if (present) { const int o = ooff + on * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, skey_key(mk), cv); ++on; } }
         }
-        arena_mark_peak(c);
         #undef AB_ADVANCE
+        if (ooff + on * AB_TW > top_max) top_max = ooff + on * AB_TW;
         // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
-        double e = r.e;
+        double e = re;
         #pragma unroll
         for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) { double tev = add_ru(tte[b], tte[b] / 2); e = add_ru(add_ru(e, tev), te[b] / 2); }
-        out.e = e;
-        if (H < 0) tm_slide(c, out, m);
-        r = out;
+        re = e; roff = ooff; rn = on;
+        if (H < 0 && roff != m) { for (int i = 0; i < rn * AB_TW; ++i) base[AB_WORD_INDEX(m + i)] = base[AB_WORD_INDEX(roff + i)]; roff = m; }
     }
-    if (r.off != m) tm_slide(c, r, m);
+    #undef AB_DISCARD
+    if (roff != m) { for (int i = 0; i < rn * AB_TW; ++i) base[AB_WORD_INDEX(m + i)] = base[AB_WORD_INDEX(roff + i)]; roff = m; }
+    if (top_max > c.A.peak) c.A.peak = top_max;
+    if (overflow) fail(c, ST_ARENA);
+    r.off = m; r.n = rn; r.e = re;
     double xs = 0, ys = 0;
-    for (int i = 0; i < x.n; ++i) xs = add_ru(xs, dabs(tm_val(c, x, i)));
-    for (int j = 0; j < y.n; ++j) ys = add_ru(ys, dabs(tm_val(c, y, j)));
-    r.e = add_ru(r.e, add_ru(add_ru(mul_ru(xs, y.e), mul_ru(ys, x.e)), mul_ru(x.e, y.e)));
+    for (int i = 0; i < xn; ++i) xs = add_ru(xs, dabs(bval(base, xoff + i * AB_TW)));
+    for (int j = 0; j < yn; ++j) ys = add_ru(ys, dabs(bval(base, yoff + j * AB_TW)));
+    r.e = add_ru(r.e, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
     c.rnd = RN;
-    c.A.top = r.off + r.n * AB_TW;
+    c.A.top = m + rn * AB_TW;
     return r;
 }
 AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc); }
