@@ -17,7 +17,7 @@ using namespace ab200;
 // Builds of the evolution kernel (one translation unit each, inline namespace = variant name). Plain signatures, so
 // that this file, compiled against the AB_KW=1 headers, can call the two-word-key build as well.
 //   kw1   one-word MultiIndex keys (<= 7 set parameters), 255 registers, 8-way merges: lowest latency per cell
-//   s4    one-word keys, 80 registers (24 resident warps per SM), 4-way merges: best for frontiers that fill the device
+//   r128  one-word keys, 128 registers (16 resident warps per SM), 8-way merges: best for frontiers that fill the device
 //   kw2   two-word keys (<= 15 set parameters) for systems with more than 2 state variables
 // AB200_TUNE=<name> forces a one-word build (measurements in profiles/r01_variants.md).
 #define AB_DECL_VARIANT(ns) namespace ab200 { namespace ns { \
@@ -28,9 +28,7 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, c
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
-AB_DECL_VARIANT(s4)
-AB_DECL_VARIANT(m16)
-AB_DECL_VARIANT(m8)
+AB_DECL_VARIANT(r128)
 struct EvolveBuild {
     const char* name;
     int (*upload)(const void*, char*, int);
@@ -39,7 +37,7 @@ struct EvolveBuild {
                   double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
-static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(s4), AB_BUILD(m16), AB_BUILD(m8) };
+static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(r128) };
 static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
 static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
 
@@ -228,7 +226,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(ctx->d_rloc.ensure((size_t)nb * S.max_boxes)); CTX_CK(ctx->d_floc.ensure((size_t)nb * S.max_boxes));
         // Build selection: set models have up to max(2n+1,3n) parameters -- one-word keys hold 7, two-word keys 15. Of the
         // one-word builds, the 255-register one has the lowest latency per cell and wins while the frontier does not fill
-        // the device; beyond that the 80-register build keeps three times as many cells in flight (profiles/r01_variants.md).
+        // the device; beyond that the 128-register build keeps twice as many cells in flight (profiles/r01_variants.md).
         const bool wide = ctx->sys.desc.loc[0].n > 2;
         const EvolveBuild* build = find_build(wide ? "kw2" : "kw1");
         const char* tune = getenv("AB200_TUNE");
@@ -236,7 +234,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             if (tune && find_build(tune) && strcmp(tune, "kw2")) build = find_build(tune);
             else if (!tune) {
                 int cap; DEV_CK((cap = build->capacity(eb_, sizeof(eb_))) < 0);
-                if (nb > 2 * cap) build = find_build("s4");
+                if (nb > 2 * cap) build = find_build("r128");
             }
         }
         const int nwarps = (nb + 31) / 32;
