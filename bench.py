@@ -174,6 +174,11 @@ def run_ours(args):
         fp64 = ev.probe_fp64()
     except Exception:
         pass
+    # Algorithmic FP64 work: operations of the REFERENCE algorithm by its per-primitive formulas, counted on
+    # 64 cells of this frontier (tests/golden/vanderpol_cells_acc7.txt.gz, 8,842 steps) with the instrumented host build
+    # of the kernel headers: 299,860 operations per evolution step.
+    FLOPS_PER_STEP = 299860.0
+    alg_gflops = (steps / args.steps) * FLOPS_PER_STEP / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": dev_value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -187,7 +192,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
                      "traffic": traffic, "kernel": "K_evolve", "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
                      "evolution_steps_per_s": steps_total / (ev_ms * 1e-3) if ev_ms > 0 else None,
-                     "fp64_directed_gflops_peak_measured": fp64, "peak_source": "measured" if peaks else "fallback"},
+                     "fp64_directed_gflops_peak_measured": fp64, "peak_source": "measured" if peaks else "fallback",
+                     "fp64_algorithmic": {"achieved_gflops": alg_gflops, "peak_gflops": fp64, "frac": (alg_gflops / fp64) if fp64 else None,
+                                          "flops_per_step": FLOPS_PER_STEP}},
         "reach_cells": reach_n,
     }
     if rank == 0:

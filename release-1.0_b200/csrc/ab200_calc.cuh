@@ -79,6 +79,7 @@ AB_HDN Ivl eval_ivl(Ctx& c, const TapeOp* ops, Func f, const Ivl* x) {
     int sp = 0;
     for (int p = f.begin; p < f.end; ++p) {
         const TapeOp o = ops[p];
+        if (o.op != OP_CNST && o.op != OP_VAR && o.op != OP_POS && o.op != OP_NEG) AB_FLOPS(o.op == OP_MUL ? 4 : 2);
         switch (o.op) {
             case OP_CNST: st[sp++] = ivl(o.lo, o.hi); break;     // x[0]*0 then r=c (src/expression.cpp:581,773)
             case OP_VAR: st[sp++] = x[o.arg]; break;

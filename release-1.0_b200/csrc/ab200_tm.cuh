@@ -175,8 +175,13 @@ AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 #ifdef AB_MUL_HIST
 extern long long g_calls[16], g_words[16];   // development counters (tests/tools/hostdbg.cpp)
 #define AB_CALL(id, w) do { g_calls[id]++; g_words[id] += (w); } while (0)
+// Algorithmic FP64 operations of the REFERENCE algorithm by the per-primitive formulas of SURVEY.md 8(d), evaluated on
+// the actual term counts (host development builds only; the figure bench.py quotes comes from these counters).
+extern double g_flops;
+#define AB_FLOPS(n) do { g_flops += (double)(n); } while (0)
 #else
 #define AB_CALL(id, w)
+#define AB_FLOPS(n)
 #endif
 
 struct TM {
@@ -248,7 +253,7 @@ AB_HD int tm_degree(Ctx& c, const TM& x) { return x.n == 0 ? 0 : key_deg(tm_key(
 // ---- in-place scalar operations -------------------------------------------------------------------------------
 
 // _scal(TaylorModel&, Float) src/taylor_model.cpp:241-273
-AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_CALL(4, r.n);
+AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_FLOPS(4 * r.n + 3); AB_CALL(4, r.n);
     if (s == 0) { r.n = 0; r.e = 0; return; }     // (arena words stay allocated; harmless)
     if (s == 1) return;
     if (s == 2 || s == 0.5) {
@@ -268,7 +273,7 @@ AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_CALL(4, r.n);
     c.rnd = RN;
 }
 // _scal(TaylorModel&, Interval) src/taylor_model.cpp:276-314
-AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_CALL(5, r.n);
+AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_FLOPS(5 * r.n + 4); AB_CALL(5, r.n);
     double te = 0, cu = s.u, mcl = -s.l;
     for (int i = 0; i < r.n; ++i) {
         double rv = tm_val(c, r, i), u, ml;
@@ -295,7 +300,7 @@ AB_HD void tm_prepend_top(Ctx& c, TM& r, double v) {
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
 }
 // _acc(TaylorModel&, Float) src/taylor_model.cpp:370-392. r must be the top model on the arena.
-AB_HDN void tm_acc(Ctx& c, TM& r, double s) {
+AB_HDN void tm_acc(Ctx& c, TM& r, double s) { AB_FLOPS(5);
     if (s == 0) return;
     if (r.n == 0 || key_deg(tm_key(c, r, 0)) > 0) { tm_prepend_top(c, r, s); return; }
     double rv = tm_val(c, r, 0);
@@ -305,7 +310,7 @@ AB_HDN void tm_acc(Ctx& c, TM& r, double s) {
     c.rnd = RN;
 }
 // _acc(TaylorModel&, Interval) src/taylor_model.cpp:397-422. r must be the top model on the arena.
-AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) {
+AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
     if (s.l == -s.u) { r.e = add_ru(r.e, s.u); c.rnd = RN; return; }
     if (r.n == 0 || key_deg(tm_key(c, r, 0)) > 0) tm_prepend_top(c, r, 0.0);
     double rv = tm_val(c, r, 0);
@@ -320,7 +325,7 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) {
 
 // _add2 (src/taylor_model.cpp:487-530): merge by key; rounding error of coincident terms accumulated upward in
 // key order. Result accuracy is supplied by the caller (the reference's operator+ uses a fresh default).
-AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_CALL(0, x.n + y.n);
+AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_FLOPS(3); AB_CALL(0, x.n + y.n);
     TM r = tm_begin(c, x.as, acc);
     double te = 0.0;
     int i = 0, j = 0;
@@ -335,6 +340,7 @@ AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_CALL(0, x.n + 
             te = add_ru(te, add_ru(u, ml));
             double s = add_rn(xv, yv);
             if (s != 0) tm_append(c, r, xa, s);
+            AB_FLOPS(5);
             ++i; ++j; coincident = true;
         }
     }
@@ -354,7 +360,7 @@ AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_CALL(0, x.n + 
 #ifndef AB_MAXSTREAMS
 #define AB_MAXSTREAMS 8
 #endif
-AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B);
+AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B); AB_FLOPS(3 * B);
     uint64_t* const base = c.A.base;
     const int limit = c.A.limit;
     const int ooff = c.A.top;
@@ -387,6 +393,7 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CAL
             if (!skey_eq(hs[s], mk)) continue;
             double tv = bval(base, tw[s]);
             if (present) {
+                AB_FLOPS(5);
                 double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
                 te[s] = add_ru(te[s], add_ru(u, ml));
                 cur = add_rn(cur, tv);
@@ -444,6 +451,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
 #ifdef AB_MUL_HIST
     { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
 #endif
+    AB_FLOPS((double)x.n * (5.0 * y.n + 3.0) + 2.0 * (x.n + y.n) + 6.0);
     uint64_t* const base = c.A.base;
     const int limit = c.A.limit;
     const int m = c.A.top;
@@ -547,6 +555,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 if (!skey_eq(hs[b], mk)) continue;
                 const double tv = hv[b];
                 if (present) {
+                    AB_FLOPS(5);
                     double u = add_ru(cv, tv), ml = sub_ru(-cv, tv);
                     te[b] = add_ru(te[b], add_ru(u, ml));
                     cv = add_rn(cv, tv);
@@ -581,7 +590,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
 AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc); }
 
 // sweep(m) src/taylor_model.cpp:972-989 -- in place; leaves the ambient mode UPWARD (sic).
-AB_HDN void tm_sweep(Ctx& c, TM& x, double m) {
+AB_HDN void tm_sweep(Ctx& c, TM& x, double m) { AB_FLOPS(x.n + 2);
     int k = 0;
     for (int i = 0; i < x.n; ++i) {
         double v = tm_val(c, x, i);
@@ -592,7 +601,7 @@ AB_HDN void tm_sweep(Ctx& c, TM& x, double m) {
     c.rnd = RU;
 }
 // clean(accuracy) src/taylor_model.cpp:895-913 -- in place
-AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) {
+AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) { AB_FLOPS(x.n + 2);
     int k = 0;
     for (int i = 0; i < x.n; ++i) {
         Key a = tm_key(c, x, i); double v = tm_val(c, x, i);
@@ -603,7 +612,7 @@ AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) {
     c.rnd = RN;
 }
 // range() = _range1 src/taylor_model.cpp:1566-1579
-AB_HDN Ivl tm_range(Ctx& c, const TM& x) { AB_CALL(7, x.n);
+AB_HDN Ivl tm_range(Ctx& c, const TM& x) { AB_FLOPS(x.n + 2); AB_CALL(7, x.n);
     double t = x.e, v = 0.0;
     for (int i = 0; i < x.n; ++i) {
         if (key_deg(tm_key(c, x, i)) == 0) v = tm_val(c, x, i);
@@ -613,7 +622,7 @@ AB_HDN Ivl tm_range(Ctx& c, const TM& x) { AB_CALL(7, x.n);
     return ivl(add_rd(-t, v), add_ru(t, v));
 }
 // norm() src/taylor_model.cpp:2592-2600
-AB_HDN double tm_norm(Ctx& c, const TM& x) {
+AB_HDN double tm_norm(Ctx& c, const TM& x) { AB_FLOPS(x.n + 2);
     double r = x.e;
     for (int i = 0; i < x.n; ++i) r = add_ru(r, dabs(tm_val(c, x, i)));
     c.rnd = RN;
@@ -673,7 +682,7 @@ AB_HDN TM tm_scale_to(Ctx& c, const TM& tv, Ivl d) {
 AB_HD TM tm_embed(Ctx& c, const TM& x, int extra) { TM r = tm_copy(c, x); r.as = x.as + extra; return r; }
 
 // antidifferentiate(k) src/taylor_model.cpp:2251-2284 -- in place
-AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) {
+AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) { AB_FLOPS(4 * x.n + 2);
     double tre = 0;
     for (int i = 0; i < x.n; ++i) {
         Key a = tm_key(c, x, i);
@@ -695,7 +704,8 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
     TM r = tm_begin(c, x.as, x.acc);
     double tme = 0.0;
     int i = 0, j = 0;
-    while (i < x.n || j < y.n) {
+    AB_FLOPS(1);
+    while (i < x.n || j < y.n) { AB_FLOPS(12);
         Key a; double xv, yv;
         if (i == x.n) { a = tm_key(c, y, j); yv = tm_val(c, y, j); xv = 0.0; ++j; }
         else if (j == y.n) { a = tm_key(c, x, i); xv = tm_val(c, x, i); yv = 0.0; ++i; }

@@ -28,3 +28,6 @@ $H springs reach acc=2 out=$G/springs_reach_acc2.txt && gzip -9 -f -n $G/springs
 # boost converter (configs[4] system): 3 locations, min() guard, urgent resets; upper reach over 3 laps. Its
 # outer_chain_reach throws in the reference itself (Lie derivative of min(), src/function.cpp:1329)
 $H boost reach acc=4 chain=0 T=0.011 out=$G/boost_reach_acc4.txt
+# the bench workload itself (configs[2], accuracy 7): 64 frontier cells spread over the 101,520-cell frontier; also the
+# sample the algorithmic FP64 operation count of bench.py is taken from (tests/tools/hostdbg.cpp built with -DAB_MUL_HIST)
+$H vanderpol cells acc=7 mince=1 ncells=64 stride=1580 init=-2.2,2.2,-2.8,2.8 out=$G/vanderpol_cells_acc7.txt && gzip -9 -f -n $G/vanderpol_cells_acc7.txt
