@@ -2,6 +2,7 @@
 // __launch_bounds__(64,8), i.e. <=128 registers and 16 resident warps per SM, 8-way merges. Twice the cells in flight of
 // the 255-register build at the same merge width (profiles/r01_variants.md). AB200_TUNE=r128 forces it.
 #define AB_KW 1
+#define AB_STREAMING_ACC 1   // accumulator traffic of products marked evict-first (+2 % at bench scale)
 #define AB_VARIANT r128
 #define AB_MINBLOCKS 8
 #define AB_MAXSTREAMS 8

@@ -202,6 +202,33 @@ AB_HD int tm_end(const TM& x) { return x.off + x.n * AB_TW; }
 // held in locals: through `Ctx&` / `const TM&` the compiler reloads them from the stack around every scratch access.
 AB_HD Key bkey(const uint64_t* base, int w) { Key k; for (int j = 0; j < AB_KW; ++j) k.w[j] = base[AB_WORD_INDEX(w + j)]; return k; }
 AB_HD double bval(const uint64_t* base, int w) { return u2d(base[AB_WORD_INDEX(w + AB_KW)]); }
+// Streaming variants for the accumulator of a product: it is written once and read once per batch, whereas the factor y is
+// re-read by every stream of every batch, so the accumulator is marked evict-first to leave the caches to y.
+AB_HD Key bkey_cs(const uint64_t* base, int w) {
+    Key k;
+#if defined(__CUDA_ARCH__) && defined(AB_STREAMING_ACC)
+    for (int j = 0; j < AB_KW; ++j) k.w[j] = __ldcs((const unsigned long long*)&base[AB_WORD_INDEX(w + j)]);
+#else
+    for (int j = 0; j < AB_KW; ++j) k.w[j] = base[AB_WORD_INDEX(w + j)];
+#endif
+    return k;
+}
+AB_HD double bval_cs(const uint64_t* base, int w) {
+#if defined(__CUDA_ARCH__) && defined(AB_STREAMING_ACC)
+    return u2d(__ldcs((const unsigned long long*)&base[AB_WORD_INDEX(w + AB_KW)]));
+#else
+    return u2d(base[AB_WORD_INDEX(w + AB_KW)]);
+#endif
+}
+AB_HD void bput_cs(uint64_t* base, int w, const Key& k, double v) {
+#if defined(__CUDA_ARCH__) && defined(AB_STREAMING_ACC)
+    for (int j = 0; j < AB_KW; ++j) __stcs((unsigned long long*)&base[AB_WORD_INDEX(w + j)], (unsigned long long)k.w[j]);
+    __stcs((unsigned long long*)&base[AB_WORD_INDEX(w + AB_KW)], (unsigned long long)d2u(v));
+#else
+    for (int j = 0; j < AB_KW; ++j) base[AB_WORD_INDEX(w + j)] = k.w[j];
+    base[AB_WORD_INDEX(w + AB_KW)] = d2u(v);
+#endif
+}
 AB_HD void bput(uint64_t* base, int w, const Key& k, double v) { for (int j = 0; j < AB_KW; ++j) base[AB_WORD_INDEX(w + j)] = k.w[j]; base[AB_WORD_INDEX(w + AB_KW)] = d2u(v); }
 
 // Begin a model at the arena top; append() grows it. Only the most recently begun model may be appended to.
@@ -542,14 +569,14 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         const int ooff = (H >= 0) ? ((((nbatch - 1 - i0 / AB_MULSTREAMS) & 1) == 0) ? m : H) : roff + rn * AB_TW;
         int on = 0;
         int rw = roff; const int rend = roff + rn * AB_TW;
-        SKey rs = rn > 0 ? skey(bkey(base, rw)) : skey_dead();
+        SKey rs = rn > 0 ? skey(bkey_cs(base, rw)) : skey_dead();
         for (;;) {
             SKey mk = rs;
             #pragma unroll
             for (int b = 0; b < AB_MULSTREAMS; ++b) if (skey_less(hs[b], mk)) mk = hs[b];
             if (skey_is_dead(mk)) break;
             bool present = false; double cv = 0.0;
-            if (skey_eq(rs, mk)) { cv = bval(base, rw); present = true; rw += AB_TW; rs = rw < rend ? skey(bkey(base, rw)) : skey_dead(); }
+            if (skey_eq(rs, mk)) { cv = bval_cs(base, rw); present = true; rw += AB_TW; rs = rw < rend ? skey(bkey_cs(base, rw)) : skey_dead(); }
             #pragma unroll
             for (int b = 0; b < AB_MULSTREAMS; ++b) {
                 if (!skey_eq(hs[b], mk)) continue;
@@ -563,7 +590,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
                 } else { cv = tv; present = true; }
                 AB_ADVANCE(b);
             }
-            if (present) { const int o = ooff + on * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, skey_key(mk), cv); ++on; } }
+            if (present) { const int o = ooff + on * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput_cs(base, o, skey_key(mk), cv); ++on; } }
         }
         #undef AB_ADVANCE
         if (ooff + on * AB_TW > top_max) top_max = ooff + on * AB_TW;
