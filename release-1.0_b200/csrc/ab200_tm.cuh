@@ -594,6 +594,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         }
         #undef AB_ADVANCE
         if (ooff + on * AB_TW > top_max) top_max = ooff + on * AB_TW;
+        AB_CALL(10, on); AB_CALL(11, B * yn);
         // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
         double e = re;
         #pragma unroll

@@ -139,8 +139,8 @@ int main(int argc, char** argv) {
     }
     printf("cells compared %d, mismatching %d, steps %ld, arena peak words %d\n", done, bad, total_steps, peak);
 #ifdef AB_MUL_HIST
-    { const char* nm[] = {"add2", "add_many(r terms)", "slide(moved)", "copy", "scal(Float)", "scal(Interval)", "neg", "range", "-", "add_many(streams)"};
-      for (int i = 0; i < 10; ++i) printf("  %-20s %8.1f calls/step %10.1f terms/step\n", nm[i], (double)g_calls[i] / total_steps, (double)g_words[i] / total_steps); }
+    { const char* nm[] = {"add2", "add_many(r terms)", "slide(moved)", "copy", "scal(Float)", "scal(Interval)", "neg", "range", "-", "add_many(streams)", "mul batches(outputs)", "mul batches(products)"};
+      for (int i = 0; i < 12; ++i) printf("  %-20s %8.1f calls/step %10.1f terms/step\n", nm[i], (double)g_calls[i] / total_steps, (double)g_words[i] / total_steps); }
     printf("algorithmic FP64 operations (SURVEY 8d formulas): %.0f total, %.0f per step, %.0f per cell\n", g_flops, g_flops / total_steps, g_flops / done);
     printf("tm_mul calls by (x.n bucket rows, y.n bucket cols; bucket b = n<=2^b), per step; then products per step\n");
     for (int a = 0; a < 8; ++a) { for (int b = 0; b < 8; ++b) printf(" %7.1f", (double)g_mul_hist[a][b] / total_steps); printf("\n"); }
