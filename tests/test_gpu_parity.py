@@ -29,7 +29,7 @@ def test_reach_evolve_boxes_bit_exact(pkg, system, name, arena):
     """Per-enclosure reach / final boxes. The bouncing-ball vectors run in chain-reach mode (ignore_activations) and
     exercise the urgent-guard path: activity tests, touching-time bisection and implicit crossing-time models."""
     d = golden_io.load_dump(name)
-    ev = _evolver(pkg, d, system=system, arena_words=arena)
+    ev = _evolver(pkg, d, system=system, arena_words=arena, max_boxes=320)
     try:
         dim = ev.dims[0]
         locs = [ev.location(c["loc"]) for c in d["cells"]]
