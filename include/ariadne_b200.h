@@ -82,6 +82,10 @@ const char* ab200_last_error(const ab200_ctx* ctx);
  * (include/hybrid_automaton_interface.h:96-141, src/hybrid_io_automaton.cpp:938-1026). */
 int  ab200_set_system_text(ab200_ctx* ctx, const char* text);
 int  ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims /* [n_locations] or NULL */);
+/* Host-only validation of a system text (no context, no GPU): parses it exactly as ab200_set_system_text does and
+ * reports the number of locations, events and tape operations, or the parser's message. Lets the adapter that walks
+ * HybridIOAutomaton::modes()/transitions() be checked on a machine without a device. */
+int  ab200_system_check(const char* text, int32_t* n_locations, int32_t* n_events, int32_t* n_ops, char* err, int32_t errlen);
 int  ab200_location_index(const ab200_ctx* ctx, const char* name);
 
 int  ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s);

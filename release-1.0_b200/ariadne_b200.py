@@ -30,7 +30,7 @@ AB200_E_CUDA, AB200_E_ARGUMENT, AB200_E_KEYSPACE, AB200_E_TIMEOUT = 100, 101, 10
 
 EXPORTS = [
     "ab200_default_settings", "ab200_ctx_create", "ab200_ctx_destroy", "ab200_last_error", "ab200_set_system_text",
-    "ab200_system_info", "ab200_location_index", "ab200_set_settings", "ab200_set_location_tuning", "ab200_set_accuracy",
+    "ab200_system_info", "ab200_system_check", "ab200_location_index", "ab200_set_settings", "ab200_set_location_tuning", "ab200_set_accuracy",
     "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
@@ -105,6 +105,7 @@ def load_library():
     lib.ab200_analyser_cells_evolved.argtypes = [vp]; lib.ab200_analyser_cells_evolved.restype = i64
     lib.ab200_analyser_enumerate.argtypes = [vp, vp, C.c_int, P(u64), P(i32), P(dbl)]; lib.ab200_analyser_enumerate.restype = C.c_int
     lib.ab200_probe_fp64.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64.restype = C.c_int
+    lib.ab200_system_check.argtypes = [C.c_char_p, P(i32), P(i32), P(i32), C.c_char_p, i32]; lib.ab200_system_check.restype = C.c_int
     _lib = lib
     return lib
 
@@ -152,6 +153,17 @@ def _take_boxlist(lib, handle, n_cells):
     locs = np.ctypeslib.as_array(lc, shape=(total,)).copy() if total else np.zeros((0,), dtype=np.int32)
     lib.ab200_boxlist_free(handle)
     return offsets, boxes, locs
+
+
+def system_check(system_text):
+    """Parse a system text on the host (no GPU): returns (n_locations, n_events, n_ops) or raises Ab200Error."""
+    lib = load_library()
+    nl = C.c_int32(0); ne = C.c_int32(0); no = C.c_int32(0)
+    err = C.create_string_buffer(512)
+    rc = lib.ab200_system_check(system_text.encode(), C.byref(nl), C.byref(ne), C.byref(no), err, 512)
+    if rc != 0:
+        raise Ab200Error(rc, err.value.decode())
+    return nl.value, ne.value, no.value
 
 
 class Evolver(object):

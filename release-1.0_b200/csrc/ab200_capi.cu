@@ -128,6 +128,22 @@ extern "C" int ab200_set_system_text(ab200_ctx* ctx, const char* text) {
     for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
     return AB200_OK;
 }
+extern "C" int ab200_system_check(const char* text, int32_t* n_locations, int32_t* n_events, int32_t* n_ops, char* err, int32_t errlen) {
+    if (err && errlen > 0) err[0] = 0;
+    if (!text) return AB200_E_ARGUMENT;
+    HostSystem* hs = new HostSystem();
+    std::string e = parse_system(text, *hs);
+    int rc = AB200_OK;
+    if (!e.empty()) { if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.c_str()); rc = AB200_E_ARGUMENT; }
+    else {
+        int ev = 0; for (int l = 0; l < hs->desc.n_locs; ++l) ev += hs->desc.loc[l].n_events;
+        if (n_locations) *n_locations = hs->desc.n_locs;
+        if (n_events) *n_events = ev;
+        if (n_ops) *n_ops = hs->desc.n_ops;
+    }
+    delete hs;
+    return rc;
+}
 extern "C" int ab200_system_info(const ab200_ctx* ctx, int32_t* n_locations, int32_t* dims) {
     if (!ctx || !ctx->have_system) return AB200_E_ARGUMENT;
     if (n_locations) *n_locations = ctx->sys.desc.n_locs;

@@ -12,11 +12,17 @@ static int opcode(const std::string& t) {
     return -1;
 }
 
-static bool parse_tape(std::istringstream& in, SystemDesc& d, Func& f, std::string& err) {
+// A tape is a postfix expression over the nvars state variables of its location; it must leave exactly one value and
+// never need more than AB_STACK slots (the evaluators index fixed-size stacks and the variable array unchecked).
+static bool parse_tape(std::istringstream& in, SystemDesc& d, Func& f, int nvars, std::string& err) {
     f.begin = d.n_ops;
     std::string t;
+    int depth = 0;
     while (in >> t) {
-        if (t == ";") { f.end = d.n_ops; return true; }
+        if (t == ";") {
+            if (depth != 1) { err = "tape does not evaluate to one value"; return false; }
+            f.end = d.n_ops; return true;
+        }
         if (d.n_ops >= AB_MAXOPS) { err = "too many tape ops"; return false; }
         TapeOp o; o.op = 0; o.arg = 0; o.lo = 0; o.hi = 0;
         if (t[0] == 'V' && t.size() > 1 && isdigit(t[1])) { o.op = OP_VAR; o.arg = atoi(t.c_str() + 1); }
@@ -29,6 +35,14 @@ static bool parse_tape(std::istringstream& in, SystemDesc& d, Func& f, std::stri
             if (oc < 2) { err = "bad tape token " + t; return false; }
             o.op = oc;
         }
+        if (o.op == OP_VAR && (o.arg < 0 || o.arg >= nvars)) { err = "variable index out of range in " + t; return false; }
+        if (o.op == OP_CNST || o.op == OP_VAR) ++depth;
+        else {
+            const bool binary = (o.op == OP_ADD || o.op == OP_SUB || o.op == OP_MUL || o.op == OP_DIV || o.op == OP_MAX || o.op == OP_MIN);
+            if (depth < (binary ? 2 : 1)) { err = "operator " + t + " without operands"; return false; }
+            if (binary) --depth;
+        }
+        if (depth > AB_STACK) { err = "tape needs too deep a stack"; return false; }
         d.ops[d.n_ops++] = o;
     }
     err = "unterminated tape";
@@ -68,7 +82,7 @@ std::string parse_system(const std::string& text, HostSystem& out) {
         } else if (tok == "dyn") {
             int i; in >> i;
             if (cur_loc < 0 || i < 0 || i >= out.desc.loc[cur_loc].n) return "bad dyn index";
-            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].dyn[i], err)) return err;
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].dyn[i], out.desc.loc[cur_loc].n, err)) return err;
         } else if (tok == "event") {
             int k, target, id; std::string name, kk, kind, kt, ki;
             in >> k >> name >> kk >> kind >> kt >> target >> ki >> id;
@@ -81,19 +95,31 @@ std::string parse_system(const std::string& text, HostSystem& out) {
             cur_ev = k;
         } else if (tok == "guard") {
             if (cur_loc < 0 || cur_ev < 0) return "guard outside event";
-            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].guard, err)) return err;
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].guard, out.desc.loc[cur_loc].n, err)) return err;
         } else if (tok == "lie") {
             if (cur_loc < 0 || cur_ev < 0) return "lie outside event";
-            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].lie, err)) return err;
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].lie, out.desc.loc[cur_loc].n, err)) return err;
         } else if (tok == "reset") {
             int i; in >> i;
             if (cur_loc < 0 || cur_ev < 0 || i < 0 || i >= AB_MAXN) return "reset outside event";
-            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].reset[i], err)) return err;
+            if (!parse_tape(in, out.desc, out.desc.loc[cur_loc].ev[cur_ev].reset[i], out.desc.loc[cur_loc].n, err)) return err;
         } else {
             return "unknown token '" + tok + "'";
         }
     }
     if (out.desc.n_locs == 0) return "no locations";
+    for (int l = 0; l < out.desc.n_locs; ++l) {
+        const LocDesc& L = out.desc.loc[l];
+        if (L.n == 0) return "location without a header";
+        for (int i = 0; i < L.n; ++i) if (L.dyn[i].end <= L.dyn[i].begin) return "missing dynamics in location " + out.loc_names[l];
+        for (int e = 0; e < L.n_events; ++e) {
+            const EventDesc& E = L.ev[e];
+            if (E.guard.end <= E.guard.begin) return "event without a guard in location " + out.loc_names[l];
+            if (E.target < 0 || E.target >= out.desc.n_locs) return "event target out of range in location " + out.loc_names[l];
+            if (E.kind != EV_INVARIANT)
+                for (int i = 0; i < out.desc.loc[E.target].n; ++i) if (E.reset[i].end <= E.reset[i].begin) return "transition without a complete reset in location " + out.loc_names[l];
+        }
+    }
     // DiscreteEvent orders by its string id and the evolver's finishing event is DiscreteEvent(-2) == "e-2"
     // (include/discrete_event.h:39-48, src/hybrid_evolver-image.cpp:86-88)
     for (int l = 0; l < out.desc.n_locs; ++l) {

@@ -46,3 +46,17 @@ def test_golden_vectors_well_formed():
         assert len(c["dreach"]) >= 1
     r = golden_io.load_dump("vanderpol_reach_acc3.txt")
     assert len(r["sets"]["reach"]["loc"]) == 22 and len(r["sets"]["evolve"]["loc"]) == 15
+
+
+def test_system_texts_parse_on_the_host(pkg):
+    """The op-tape parser (release-1.0_b200/csrc/ab200_system.cpp) runs without a device: every system of the five
+    BASELINE configs is accepted with the expected shape, malformed input is rejected with a message."""
+    expect = {"vanderpol": (1, 0), "bouncingball": (1, 1), "watertank": (4, 8), "springs": (2, 2), "boost": (3, 4)}
+    for name, (nloc, nev) in expect.items():
+        text = open(os.path.join(golden_io.GOLDEN, name + ".sys")).read()
+        got = pkg.system_check(text)
+        assert got[:2] == (nloc, nev) and got[2] > 0, (name, got)
+    with pytest.raises(pkg.Ab200Error):
+        pkg.system_check("system broken\nlocations 1\nlocation 0 a n 2 events 0\n  dyn 0 V7 ;\n")
+    with pytest.raises(pkg.Ab200Error):
+        pkg.system_check("system broken\nlocations 1\nlocation 0 a n 1 events 0\n  dyn 0 V0 FROB ;\n")

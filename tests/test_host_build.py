@@ -1,0 +1,44 @@
+"""CPU-side parity of the algorithm itself: the kernel headers and the analyser mirror are compiled for the HOST (a
+development build, tests/tools/hostchain.cpp, with the device lap replaced by a serial loop over the same
+evolve_cell code) and replayed against the goldens of the compiled reference. This is test infrastructure only -- the
+shipped library has no such path -- but it pins the host logic (paving, jump sets, laps) and the arithmetic of the
+kernels bit for bit without a GPU."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "build")
+SRC = [os.path.join(ROOT, "tests", "tools", "hostchain.cpp"),
+       os.path.join(ROOT, "release-1.0_b200", "csrc", "ab200_system.cpp"),
+       os.path.join(ROOT, "release-1.0_b200", "csrc", "ab200_paving.cpp")]
+
+
+@pytest.fixture(scope="module")
+def hostchain():
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no host compiler")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "hostchain_test")
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-frounding-math", "-w", "-x", "c++", "-o", exe] + SRC, timeout=600)
+    return exe
+
+
+CASES = [
+    ("bouncingball", "bouncingball_chain_acc5.txt", ["chain", "acc=5", "domain=-10.1,10.1,-0.1,2.1", "init=0.0,0.001,1.999,2.0"]),
+    ("bouncingball", "bouncingball_chain_acc6.txt", ["chain", "acc=6", "domain=-10.1,10.1,-0.1,2.1", "init=-2.0,0.5,0.5,1.5"]),
+    ("watertank", "watertank_reach_acc3.txt", ["upper", "acc=3", "T=0.5", "domain=0.0,1.0,4.5,9.0", "loc=2", "init=1.0,1.0,7.6,7.7",
+                                               "loc=1", "init=0.0,0.0,5.7,5.8"]),
+    ("vanderpol", "vanderpol_reach_acc4.txt", ["upper", "acc=4", "T=2.0", "domain=-3,3,-3,3", "init=-1.6,-1.3,0.3,0.8"]),
+]
+
+
+@pytest.mark.parametrize("system,golden,args", CASES)
+def test_host_build_reproduces_reference_cell_sets(hostchain, system, golden, args):
+    g = os.path.join(ROOT, "tests", "golden")
+    out = subprocess.run([hostchain, os.path.join(g, system + ".sys"), os.path.join(g, golden)] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600).stdout.decode()
+    assert "cell sets identical (bit-exact boxes)" in out, out[-2000:]
