@@ -55,6 +55,9 @@ typedef struct ab200_settings {
     int32_t hash_log2;                  /* log2 of the de-duplication table size */
     int32_t batch_cells;                /* cells per launch */
     double  ttl_seconds;                /* Interruptible::ttl; <=0 disables */
+    int32_t semantics;                  /* 0 = UPPER_SEMANTICS (default), 1 = LOWER_SEMANTICS: the Semantics argument of
+                                           EvolverInterface::reach_evolve / orbit (include/evolver_interface.h:46-49,114-124) */
+    int32_t reserved;
 } ab200_settings;
 
 typedef struct ab200_status {

@@ -194,6 +194,16 @@ static void dump_system(FILE* f, const HybridIOAutomaton& sys) {
                     if(!(m->location()==loc)) continue;
                     std::map<DiscreteEvent,RealExpression>::const_iterator inv=m->invariants().find(*e);
                     fprintf(f,"    guard"); emit_tape(f,inv->second,var_index); fprintf(f," ;\n");
+                    // lie derivative of the invariant function: used by the lower-semantics discard test
+                    // (has_nonnegative_crossing, src/hybrid_evolver-image.cpp:612-632)
+                    std::map<RealVariable,RealExpression>::const_iterator d=m->dynamics().begin();
+                    try {
+                        RealExpression lie=derivative(inv->second,cs.variable(0))*d->second; ++d;
+                        for(uint i=1;i<cs.size();++i,++d) lie=lie+derivative(inv->second,cs.variable(i))*d->second;
+                        fprintf(f,"    lie"); emit_tape(f,lie,var_index); fprintf(f," ;\n");
+                    } catch(std::exception& ex) {
+                        fprintf(f,"    # lie derivative not computable in the reference: %s\n","derivative() throws");
+                    }
                 }
             } else {
                 for(std::list<DiscreteIOTransition>::const_iterator t=sys.transitions().begin(); t!=sys.transitions().end(); ++t) {
@@ -289,7 +299,7 @@ int main(int argc, char** argv) {
         bool ignore_act=geti(kv,"ignore_activations",c.chain?1:0)!=0;
         HybridTime ht(T,c.chain?1:c.events);
         evolver.verbosity=geti(kv,"everb",0);
-        fprintf(out,"frontier %lu ignore_activations %d\n",(unsigned long)encl.size(),(int)ignore_act);
+        fprintf(out,"frontier %lu ignore_activations %d lower %d\n",(unsigned long)encl.size(),(int)ignore_act,geti(kv,"lower",0));
         HybridDenotableSet ureach(grid), ufinal(grid);
         int k=0, done=0;
         // to_enclosures (src/reachability_analyser.cpp:1244-1253) walks the set in this same order; the cell box itself
@@ -300,7 +310,7 @@ int main(int argc, char** argv) {
             ++done;
             fprintf(out,"cell %d loc %s box",k,it->first.name().c_str()); dump_box(out,cell_it->second); fprintf(out,"\n");
             try {
-                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(*it,ht,ignore_act,DIRECTION_FORWARD,UPPER_SEMANTICS);
+                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(*it,ht,ignore_act,DIRECTION_FORWARD,geti(kv,"lower",0)?LOWER_SEMANTICS:UPPER_SEMANTICS);
                 for(HEnclList::const_iterator r=re.first.begin(); r!=re.first.end(); ++r) {
                     fprintf(out,"r %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
                 for(HEnclList::const_iterator r=re.second.begin(); r!=re.second.end(); ++r) {

@@ -319,8 +319,10 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
     B.time = bt;
 }
 
-// is_enclosure_to_be_discarded (:652-681) for UPPER semantics: a blocking event definitely active on the starting set.
-AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc& L, const TM* set, int n, int p) {
+// is_enclosure_to_be_discarded (:652-681): a blocking event definitely active on the starting set; with LOWER semantics
+// also a possibly active one whose guard may be crossed in the positive direction (has_nonnegative_crossing :612-632,
+// positively_crossing :637-650: the Lie derivative of the guard over the set's bounding box).
+AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc& L, const TM* set, int n, int p, int lower) {
     (void)p;
     int blocking_active = TRI_FALSE;
     for (int e = 0; e < L.n_events; ++e) {
@@ -338,8 +340,26 @@ AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc
             else if (act == TRI_INDET || blocking_active == TRI_INDET) blocking_active = TRI_INDET;
         }
     }
-    return blocking_active == TRI_TRUE;
+    if (blocking_active == TRI_TRUE) return true;
+    if (blocking_active == TRI_INDET && lower) {
+        Ivl bb[AB_MAXN];
+        for (int i = 0; i < n; ++i) bb[i] = tm_range(c, set[i]);
+        for (int e = 0; e < L.n_events; ++e) {
+            if (!is_urgent(L.ev[e])) continue;
+            int act = tribool_of(eval_ivl(c, S.ops, L.ev[e].guard, bb));
+            if (L.ev[e].lie.end <= L.ev[e].lie.begin) { fail(c, ST_UNSUPPORTED); return true; }   // lie_derivative throws in the reference
+            Ivl d = eval_ivl(c, S.ops, L.ev[e].lie, bb);
+            int pc = d.l > 0 ? TRI_TRUE : (d.u < 0 ? TRI_FALSE : TRI_INDET);
+            if (tri_possibly(act) && tri_possibly(pc)) return true;
+        }
+    }
+    return false;
 }
+AB_HD bool blocking_has_transition(const LocDesc& L, const BlockingInfo& B) {
+    for (int k = 0; k < B.n_blocking; ++k) if (L.ev[B.blocking[k]].kind != EV_INVARIANT) return true;
+    return false;
+}
+
 // ---- activation times of non-blocking events -----------------------------------------------------------------------
 // _compute_activation_info + compute_activationTimes (src/hybrid_evolver-image.cpp:884-975,1130-1157), UPPER semantics:
 // permissive events, plus urgent transitions whose crossing was non-transverse, get a [lower,upper] window of scaled
@@ -347,7 +367,7 @@ AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc
 struct Activation { int ev; TM lower, upper; };
 
 AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& L, const BlockingInfo& B, const TM* fset,
-                                    int n, int p, Activation* act) {
+                                    int n, int p, int lower, Activation* act) {
     bool wanted[AB_MAXEV]; bool any = false;
     for (int e = 0; e < L.n_events; ++e) { wanted[e] = (L.ev[e].kind == EV_PERMISSIVE); any = any || wanted[e]; }
     for (int k = 0; k < B.n_nontransverse; ++k) if (L.ev[B.nontransverse[k]].kind != EV_INVARIANT) { wanted[B.nontransverse[k]] = true; any = true; }
@@ -388,9 +408,16 @@ AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& 
         TM lo = tm_copy(c, cross); tm_acc(c, lo, -cross.e); lo.e = 0.0;
         TM up = tm_copy(c, cross); tm_acc(c, up, cross.e); up.e = 0.0;
         act[na].ev = e;
-        act[na].lower = (ia == TRI_FALSE) ? lo : zero;
-        act[na].upper = (fa == TRI_FALSE) ? up : B.time;
-        ++na;
+        if (!lower) {
+            act[na].lower = (ia == TRI_FALSE) ? lo : zero;
+            act[na].upper = (fa == TRI_FALSE) ? up : B.time;
+            ++na;
+        } else {
+            // LOWER semantics (:927-969): the window shrinks to what is certainly active, and is kept only if non-empty
+            act[na].lower = (ia == TRI_TRUE) ? zero : up;
+            act[na].upper = (fa == TRI_FALSE) ? lo : ((fa == TRI_TRUE) ? B.time : up);
+            if (tm_less(c, act[na].lower, act[na].upper) == TRI_TRUE) ++na;
+        }
     }
     if (c.status != ST_OK) return 0;
     // keep only the windows: copy them to the top in order, then slide the block down to m0
@@ -416,9 +443,5 @@ AB_HDN TM reachability_time(Ctx& c, const TM& t0, const TM& t1, int p, Acc spaci
     return r;
 }
 
-AB_HD bool blocking_has_transition(const LocDesc& L, const BlockingInfo& B) {
-    for (int k = 0; k < B.n_blocking; ++k) if (L.ev[B.blocking[k]].kind != EV_INVARIANT) return true;
-    return false;
-}
 
 } } // namespace ab200

@@ -23,6 +23,8 @@ struct EvolveParams {
     double spacial_sweep;      // 1e-12
     int32_t spacial_order;     // 6
     int32_t max_working_sets;  // per-cell queue capacity (device limit, not a reference setting)
+    int32_t lower;             // Semantics: 0 = UPPER_SEMANTICS, 1 = LOWER_SEMANTICS (include/evolver_interface.h:46-49)
+    int32_t pad;
 };
 
 struct CellOutput {
@@ -134,8 +136,8 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
         if (trange.l >= P.T || ws.n_events >= P.max_events) {
             out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
         } else if (too_large) {
-            // premature termination on enclosure size; UPPER semantics keeps the set as final (:308-313)
-            out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
+            // premature termination on enclosure size; UPPER semantics keeps the set as final, LOWER drops it (:308-313)
+            if (!P.lower) out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
         } else {
             // ---- _evolution_step ------------------------------------------------------------------------------
             O.steps++;
@@ -166,12 +168,12 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             BlockingInfo B;
             compute_blocking_info(c, S, L, fset, n, p, tstep, spacial, B);
             if (c.status != ST_OK) break;
-            if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p)) {
+            if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p, P.lower)) {
                 if (c.status != ST_OK) break;
                 Activation acts[AB_MAXEV]; int na = 0;
                 if (!P.ignore_activations) {
                     if (p + 2 > AB_MAXARGS) { fail(c, ST_UNSUPPORTED); break; }     // parameter count beyond the packed key width
-                    na = compute_activation_times(c, S, L, B, fset, n, p, acts);
+                    na = compute_activation_times(c, S, L, B, fset, n, p, P.lower, acts);
                     if (c.status != ST_OK) break;
                 }
                 // reachable set (:1159-1178)
@@ -185,7 +187,8 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                     out_box(c, O.reach, O.reach_loc, O.n_reach, P.max_boxes, O.stride, ws.loc, rb, n);
                     c.A.top = m;
                 }
-                // _computeEvolutionForEvents (:1000-1082)
+                // _computeEvolutionForEvents (:1000-1082); with LOWER semantics only when the blocking event is unique (:544)
+                if (!P.lower || ((B.finishing ? 1 : 0) + B.n_blocking) == 1) {
                 TM ev[AB_MAXN];
                 integration_step(c, fset, n, p, B.time, spacial, ev);
                 for (int i = 0; i < n; ++i) AB_DUMP(c, "evolved", i, ev[i]);
@@ -249,6 +252,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                     TM at = reachability_time(c, t0, t1, p, spacial);
                     tm_slide(c, at, m);
                     w.time = at;
+                }
                 }
             }
         }

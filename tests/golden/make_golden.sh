@@ -31,3 +31,8 @@ $H boost reach acc=4 chain=0 T=0.011 out=$G/boost_reach_acc4.txt
 # the bench workload itself (configs[2], accuracy 7): 64 frontier cells spread over the 101,520-cell frontier; also the
 # sample the algorithmic FP64 operation count of bench.py is taken from (tests/tools/hostdbg.cpp built with -DAB_MUL_HIST)
 $H vanderpol cells acc=7 mince=1 ncells=64 stride=1580 init=-2.2,2.2,-2.8,2.8 out=$G/vanderpol_cells_acc7.txt && gzip -9 -f -n $G/vanderpol_cells_acc7.txt
+# LOWER_SEMANTICS (EvolverInterface::reach_evolve's Semantics argument): discard on possibly active blocking events with a
+# non-negative crossing, no final set on enclosure-size termination, unique blocking event, shrunken activation windows
+$H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 lower=1 out=$G/bouncingball_cells_acc4_lower.txt
+$H bouncingball cells acc=4 chain=0 T=1.5 init=0.0,0.5,1.0,2.0 lower=1 out=$G/bouncingball_cells_acc4_lower_events.txt
+$H watertank cells acc=3 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5.8 lower=1 out=$G/watertank_cells_acc3_lower.txt

@@ -46,6 +46,32 @@ def test_reach_evolve_boxes_bit_exact(pkg, system, name, arena):
         ev.close()
 
 
+@pytest.mark.parametrize("system,name", [("bouncingball", "bouncingball_cells_acc4_lower.txt"),
+                                         ("bouncingball", "bouncingball_cells_acc4_lower_events.txt"),
+                                         ("watertank", "watertank_cells_acc3_lower.txt")])
+def test_reach_evolve_lower_semantics_bit_exact(pkg, system, name):
+    """EvolverInterface::reach_evolve(..., LOWER_SEMANTICS): per-enclosure reach / final boxes, location by location (the
+    reference's list sets are grouped by location, within a location in insertion order)."""
+    d = golden_io.load_dump(name)
+    ev = _evolver(pkg, d, system=system, arena_words=131072, max_boxes=320, semantics=1)
+    try:
+        dim = ev.dims[0]
+        locs = [ev.location(c["loc"]) for c in d["cells"]]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
+        (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, d["config"]["T"], d["config"]["events"],
+                                                                  ignore_activations=bool(d["config"]["ignore_activations"]))
+        for i, c in enumerate(d["cells"]):
+            for mine_b, mine_l, ref_b, ref_l, what in ((rbox[roff[i]:roff[i + 1], :2 * dim], rloc[roff[i]:roff[i + 1]], c["reach"], c["reach_loc"], "reach"),
+                                                       (fbox[foff[i]:foff[i + 1], :2 * dim], floc[foff[i]:foff[i + 1]], c["final"], c["final_loc"], "final")):
+                ref_l = np.array([ev.location(x) for x in ref_l], dtype=np.int32)
+                ref_b = np.array(ref_b, dtype=np.float64).reshape(-1, 2 * dim)
+                assert len(mine_l) == len(ref_l), "%s count of cell %d" % (what, c["id"])
+                for l in range(ev.n_locations):
+                    assert golden_io.boxes_equal_bits(mine_b[mine_l == l], ref_b[ref_l == l]), "%s boxes of cell %d in location %d" % (what, c["id"], l)
+    finally:
+        ev.close()
+
+
 def _leaf_set(an, cellset):
     return set(int(k) for k in cellset.keys)
 
