@@ -92,6 +92,7 @@ int  ab200_system_check(const char* text, int32_t* n_locations, int32_t* n_event
 int  ab200_location_index(const ab200_ctx* ctx, const char* name);
 
 int  ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s);
+int  ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s);
 
 /* ImageSetHybridEvolver::tune_settings (src/hybrid_evolver-image.cpp:99-113): per-location maximum step size and
  * reference enclosure widths, and the grid + accuracy used by outer_approximation. */
@@ -142,6 +143,12 @@ int  ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, cons
                                        double t_continuous, int32_t max_events, int mince,
                                        ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status);
 /* outer_chain_reach (src/reachability_analyser.cpp:380-493). */
+/* HybridReachabilityAnalyser::lower_reach_evolve (src/reachability_analyser.cpp:230-275): midpoints of the discretised
+ * initial cells evolved with LOWER_SEMANTICS for the whole time; AB200_E_DOMAIN if an orbit leaves the widened domain
+ * (the reference's DomainException). lower_reach / lower_evolve are its two halves (:208-227). */
+int  ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                       double T, int32_t max_events,
+                                       ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status);
 int  ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
                                       ab200_cellset** reach_out, ab200_status* status);
 /* Number of frontier enclosures consumed by the evolver in the last analyser call (the metric's unit of work). */

@@ -361,7 +361,8 @@ int main(int argc, char** argv) {
     HybridDenotableSet reach, evolve;
     std::string err;
     try {
-        if(c.chain) { reach=analyser.outer_chain_reach(c.initial); }
+        if(geti(kv,"lower",0)) { make_lpair(reach,evolve)=analyser.lower_reach_evolve(c.initial,HybridTime(T,c.events)); }
+        else if(c.chain) { reach=analyser.outer_chain_reach(c.initial); }
         else { make_lpair(reach,evolve)=analyser.upper_reach_evolve(c.initial,HybridTime(T,c.events)); }
     } catch(std::exception& e) { err=e.what(); }
     std::chrono::steady_clock::time_point t1=std::chrono::steady_clock::now();

@@ -34,7 +34,7 @@ EXPORTS = [
     "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
-    "ab200_analyser_outer_chain_reach", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64",
+    "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64",
 ]
 
 
@@ -100,6 +100,9 @@ def load_library():
     lib.ab200_analyser_set_lock_time.argtypes = [vp, dbl]; lib.ab200_analyser_set_lock_time.restype = C.c_int
     lib.ab200_analyser_upper_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, C.c_int, P(vp), P(vp), P(Status)]
     lib.ab200_analyser_upper_reach_evolve.restype = C.c_int
+    lib.ab200_analyser_lower_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, P(vp), P(vp), P(Status)]
+    lib.ab200_analyser_lower_reach_evolve.restype = C.c_int
+    lib.ab200_ctx_get_settings.argtypes = [vp, P(Settings)]; lib.ab200_ctx_get_settings.restype = C.c_int
     lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), P(vp), P(Status)]
     lib.ab200_analyser_outer_chain_reach.restype = C.c_int
     lib.ab200_analyser_discretise.argtypes = [vp, u64, P(i32), P(dbl), P(vp)]; lib.ab200_analyser_discretise.restype = C.c_int
@@ -322,6 +325,22 @@ class HybridReachabilityAnalyser(object):
 
     def upper_evolve(self, initial_set, time, max_events=5, mince=False):
         return self.upper_reach_evolve(initial_set, time, max_events, mince)[1]
+
+    def lower_reach_evolve(self, initial_set, time, max_events=5):
+        """HybridReachabilityAnalyser::lower_reach_evolve (src/reachability_analyser.cpp:230-275)."""
+        locs, boxes = self._initial(initial_set)
+        r = C.c_void_p(); e = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_analyser_lower_reach_evolve(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), float(time), int(max_events),
+                                                        C.byref(r), C.byref(e), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
+        return self._wrap(r), self._wrap(e)
+
+    def lower_reach(self, initial_set, time, max_events=5):
+        return self.lower_reach_evolve(initial_set, time, max_events)[0]
+
+    def lower_evolve(self, initial_set, time, max_events=5):
+        return self.lower_reach_evolve(initial_set, time, max_events)[1]
 
     def outer_chain_reach(self, initial_set):
         locs, boxes = self._initial(initial_set)

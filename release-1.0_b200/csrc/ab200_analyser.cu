@@ -472,6 +472,87 @@ extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_
     return AB200_OK;
 }
 
+// lower_reach_evolve (src/reachability_analyser.cpp:230-275): the midpoints of the discretised initial cells
+// (_enclosures_from_discretised_initial_set_midpoints :1218-1243, box-only initial sets) are evolved for the whole time
+// with LOWER_SEMANTICS; every orbit is discretised on its own, checked against the outer domain widened by
+// get_epsilon (:1255-1275) and restricted (the evolve set is not). The evolution runs on the device; the per-orbit
+// discretisation and the domain check are host work on the returned enclosure boxes -- this is not the hot path.
+extern "C" int ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s);
+extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                                 double T, int32_t max_events,
+                                                 ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    if (!an || !reach_out || !evolve_out) return AB200_E_ARGUMENT;
+    *reach_out = 0; *evolve_out = 0;
+    an->cells_evolved = 0;
+    HybridCells initial;
+    int rc = discretise_initial(an, n_init, loc, boxes, initial);
+    if (rc != AB200_OK) return rc;
+    const int dim = an->dim;
+    std::vector<int32_t> elocs; std::vector<double> eboxes;
+    for (int l = 0; l < an->n_locs; ++l) {
+        const double* ib = 0;
+        for (uint64_t k = 0; k < n_init; ++k) if (loc[k] == l) { ib = boxes + k * AB200_BOX_STRIDE; break; }
+        if (!ib) continue;
+        std::vector<CellBox> cells; initial[l].enumerate(cells);
+        for (size_t k = 0; k < cells.size(); ++k) {
+            elocs.push_back(l);
+            size_t o = eboxes.size(); eboxes.resize(o + AB200_BOX_STRIDE, 0.0);
+            for (int i = 0; i < dim; ++i) {
+                double lo = std::max(cells[k].b[2 * i], ib[2 * i]), hi = std::min(cells[k].b[2 * i + 1], ib[2 * i + 1]);   // intersection(cell,domain)
+                double mid = (lo + hi) / 2;                                                                          // Box::centre
+                eboxes[o + 2 * i] = mid; eboxes[o + 2 * i + 1] = mid;
+            }
+        }
+    }
+    an->cells_evolved = (int64_t)elocs.size();
+    { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
+    ab200_settings saved, low;
+    ab200_ctx_get_settings(an->ctx, &saved);
+    low = saved; low.semantics = 1;
+    rc = ab200_set_settings(an->ctx, &low);
+    if (rc != AB200_OK) return rc;
+    ab200_boxlist *rb = 0, *fb = 0; ab200_status st; memset(&st, 0, sizeof(st));
+    rc = ab200_reach_evolve_boxes(an->ctx, elocs.size(), elocs.data(), eboxes.data(), T, max_events, 0, 0, &rb, &fb, &st);
+    ab200_set_settings(an->ctx, &saved);
+    if (status) *status = st;
+    if (rc != AB200_OK) return rc;
+    HybridCells reach = empty_cells(an), evolve = empty_cells(an);
+    const double divider = (double)(1 << an->accuracy);
+    bool ok = true; int result = AB200_OK;
+    const uint64_t *roff, *foff; const double *rbx, *fbx; const int32_t *rl, *fl;
+    ab200_boxlist_view(rb, &roff, &rbx, &rl); ab200_boxlist_view(fb, &foff, &fbx, &fl);
+    for (size_t e = 0; e < elocs.size() && result == AB200_OK; ++e) {
+        HybridCells local_reach = empty_cells(an), local_evolve = empty_cells(an);
+        std::vector<std::vector<double> > eps(an->n_locs, std::vector<double>(dim, 0.0));
+        for (uint64_t k = roff[e]; k < roff[e + 1]; ++k) {
+            const double* b = rbx + k * AB200_BOX_STRIDE;
+            ok = local_reach[rl[k]].adjoin_outer_approximation(b) && ok;
+            for (int i = 0; i < dim; ++i) eps[rl[k]][i] = std::max(eps[rl[k]][i], ivl_width(ivl(b[2 * i], b[2 * i + 1])));
+        }
+        for (uint64_t k = foff[e]; k < foff[e + 1]; ++k) ok = local_evolve[fl[k]].adjoin_outer_approximation(fbx + k * AB200_BOX_STRIDE) && ok;
+        for (int l = 0; l < an->n_locs; ++l) {
+            double bb[2 * AB_GRID_MAXN];
+            if (!local_reach[l].bounding_box(bb)) continue;
+            for (int i = 0; i < dim; ++i) {
+                const double cell = an->grid[l].lengths[i] / divider;
+                const double e_i = eps[l][i] + cell;                                   // get_epsilon
+                const double lo = (an->domain[l][2 * i] - cell) - e_i, hi = (an->domain[l][2 * i + 1] + cell) + e_i;   // widen(outer_domain_box)
+                if (!(bb[2 * i] >= lo && bb[2 * i + 1] <= hi)) {
+                    ab200_ctx_set_error(an->ctx, "The lower reach is not inside the over-approximated domain. Check the domain used for variables.");
+                    result = AB200_E_DOMAIN;
+                }
+            }
+        }
+        apply_restriction(an, local_reach);
+        for (int l = 0; l < an->n_locs; ++l) { reach[l].adjoin(local_reach[l]); evolve[l].adjoin(local_evolve[l]); }
+    }
+    ab200_boxlist_free(rb); ab200_boxlist_free(fb);
+    if (result != AB200_OK) return result;
+    if (!ok) { ab200_ctx_set_error(an->ctx, "a reached cell lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    *reach_out = to_cellset(reach); *evolve_out = to_cellset(evolve);
+    return AB200_OK;
+}
+
 extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
                                                 ab200_cellset** reach_out, ab200_status* status) {
     if (!an || !reach_out) return AB200_E_ARGUMENT;

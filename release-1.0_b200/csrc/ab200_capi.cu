@@ -162,6 +162,11 @@ extern "C" int ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s) {
     ctx->settings.arena_words = (s->arena_words + 15) & ~15;       // whole 128-byte chunks per lane (AB_CHUNK layouts)
     return AB200_OK;
 }
+extern "C" int ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s) {
+    if (!ctx || !s) return AB200_E_ARGUMENT;
+    *s = ctx->settings;
+    return AB200_OK;
+}
 extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max_step, const double* ref_widths,
                                          const double* grid_origin, const double* grid_lengths) {
     if (!ctx || !ctx->have_system || loc < 0 || loc >= ctx->sys.desc.n_locs) return AB200_E_ARGUMENT;

@@ -36,3 +36,7 @@ $H vanderpol cells acc=7 mince=1 ncells=64 stride=1580 init=-2.2,2.2,-2.8,2.8 ou
 $H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 lower=1 out=$G/bouncingball_cells_acc4_lower.txt
 $H bouncingball cells acc=4 chain=0 T=1.5 init=0.0,0.5,1.0,2.0 lower=1 out=$G/bouncingball_cells_acc4_lower_events.txt
 $H watertank cells acc=3 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5.8 lower=1 out=$G/watertank_cells_acc3_lower.txt
+# analyser level: lower_reach_evolve (midpoints of the initial cells, whole horizon, LOWER_SEMANTICS)
+$H bouncingball reach acc=4 chain=0 lower=1 T=1.5 init=0.0,0.5,1.0,2.0 out=$G/bouncingball_lower_reach_acc4.txt
+$H vanderpol reach acc=4 lower=1 T=1.5 init=1.0,1.5,1.0,1.6 out=$G/vanderpol_lower_reach_acc4.txt
+$H watertank reach acc=3 lower=1 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5.8 out=$G/watertank_lower_reach_acc3.txt

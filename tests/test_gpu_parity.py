@@ -141,6 +141,32 @@ def test_upper_reach_evolve_hybrid_systems_identical_cells(pkg, system, name, do
         an.close()
 
 
+LOWER_CASES = [
+    ("bouncingball", "bouncingball_lower_reach_acc4.txt", [-10.1, 10.1, -0.1, 2.1], {"freefall": [0.0, 0.5, 1.0, 2.0]}),
+    ("vanderpol", "vanderpol_lower_reach_acc4.txt", [-3.0, 3.0, -3.0, 3.0], {"loc": [1.0, 1.5, 1.0, 1.6]}),
+    ("watertank", "watertank_lower_reach_acc3.txt", [0.0, 1.0, 4.5, 9.0],
+     {"flow,idle,rising": [1.0, 1.0, 7.6, 7.7], "flow,idle,falling": [0.0, 0.0, 5.7, 5.8]}),
+]
+
+
+@pytest.mark.parametrize("system,name,domain,init", LOWER_CASES)
+def test_lower_reach_evolve_identical_cells(pkg, system, name, domain, init):
+    """HybridReachabilityAnalyser::lower_reach_evolve (src/reachability_analyser.cpp:230-275)."""
+    d = golden_io.load_dump(name)
+    an = pkg.HybridReachabilityAnalyser(_system(system), domain, d["config"]["acc"], settings={"arena_words": 131072, "max_boxes": 512})
+    try:
+        reach, evolve = an.lower_reach_evolve(init, d["config"]["T"], d["config"]["events"])
+        rl, rb = an.enumerate(reach)
+        el, eb = an.enumerate(evolve)
+        for which, locs, boxes in (("reach", rl, rb), ("evolve", el, eb)):
+            for lname, ref in d["sets"][which].items():
+                mine = boxes[locs == an.evolver.location(lname)]
+                assert golden_io.boxes_equal_bits(mine, ref), "%s cells of %s in %s" % (which, system, lname)
+        assert an.evolver.settings.semantics == 0
+    finally:
+        an.close()
+
+
 def test_boost_outer_chain_reach_fails_like_the_reference(pkg):
     """configs[4]: the reference's own outer_chain_reach on the boost converter throws in forward_jump_set because
     lie_derivative cannot differentiate the min() guard (src/function.cpp:1329). Same laps, same failure here."""

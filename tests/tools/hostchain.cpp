@@ -19,7 +19,13 @@
 using namespace ab200;
 
 struct ab200_cellset { std::vector<uint64_t> keys; };
-struct ab200_ctx { HostSystem sys; KeyLayout K; bool have_layout; std::string err; int accuracy; };
+struct ab200_boxlist { std::vector<uint64_t> offsets; std::vector<double> boxes; std::vector<int32_t> locs; };
+struct ab200_ctx { HostSystem sys; KeyLayout K; bool have_layout; std::string err; int accuracy; ab200_settings settings; };
+extern "C" int ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s) { ctx->settings = *s; return AB200_OK; }
+extern "C" int ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s) { *s = ctx->settings; return AB200_OK; }
+extern "C" int ab200_boxlist_view(const ab200_boxlist* bl, const uint64_t** offsets, const double** boxes, const int32_t** locs) {
+    *offsets = bl->offsets.data(); *boxes = bl->boxes.data(); *locs = bl->locs.data(); return AB200_OK; }
+extern "C" void ab200_boxlist_free(ab200_boxlist* bl) { delete bl; }
 
 const HostSystem* ab200_ctx_system(const ab200_ctx* ctx) { return &ctx->sys; }
 const KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return &ctx->K; }
@@ -92,6 +98,31 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
     return AB200_OK;
 }
 
+extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T,
+                                        int32_t max_events, int32_t ignore_activations, int32_t direction,
+                                        ab200_boxlist** reach, ab200_boxlist** fin, ab200_status* status) {
+    (void)direction;
+    const SystemDesc& S = ctx->sys.desc;
+    const int MAXB = 4096;
+    std::vector<double> rb(MAXB * 2 * AB_MAXN), fb(MAXB * 2 * AB_MAXN); std::vector<int32_t> rl(MAXB), fl(MAXB);
+    ab200_boxlist* R = new ab200_boxlist(); ab200_boxlist* F = new ab200_boxlist();
+    R->offsets.push_back(0); F->offsets.push_back(0);
+    for (uint64_t ci = 0; ci < n_cells; ++ci) {
+        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        EvolveParams P; P.lower = ctx->settings.semantics; P.pad = 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
+        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
+        g_cells++; g_steps += O.steps;
+        if (c.status != ST_OK) { printf("cell %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
+        for (int k = 0; k < O.n_reach; ++k) { for (int j = 0; j < AB200_BOX_STRIDE; ++j) R->boxes.push_back(rb[k * O.stride + j]); R->locs.push_back(rl[k]); }
+        for (int k = 0; k < O.n_final; ++k) { for (int j = 0; j < AB200_BOX_STRIDE; ++j) F->boxes.push_back(fb[k * O.stride + j]); F->locs.push_back(fl[k]); }
+        R->offsets.push_back(R->locs.size()); F->offsets.push_back(F->locs.size());
+    }
+    *reach = R; *fin = F;
+    if (status) memset(status, 0, sizeof(*status));
+    return AB200_OK;
+}
+
 #include "../../release-1.0_b200/csrc/ab200_analyser.cu"
 
 static std::vector<double> csv(const char* s) { std::vector<double> v; std::stringstream ss(s); std::string t; while (std::getline(ss, t, ',')) v.push_back(strtod(t.c_str(), 0)); return v; }
@@ -102,6 +133,8 @@ int main(int argc, char** argv) {
     std::ifstream sf(argv[1]); std::stringstream ss; ss << sf.rdbuf();
     std::string err = parse_system(ss.str(), ctx.sys); if (!err.empty()) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
     const bool chain = !strcmp(argv[3], "chain");
+    const bool lower = !strcmp(argv[3], "lower");
+    memset(&ctx.settings, 0, sizeof(ctx.settings));
     int acc = 4, events = 5, mince = 0; double T = 1.0, lock = 0; std::vector<double> dom; std::vector<std::vector<double> > inits; std::vector<int32_t> init_locs; int init_loc = 0;
     for (int a = 4; a < argc; ++a) {
         if (!strncmp(argv[a], "acc=", 4)) acc = atoi(argv[a] + 4);
@@ -123,7 +156,8 @@ int main(int argc, char** argv) {
     if (lock > 0) ab200_analyser_set_lock_time(an, lock);
     printf("lock %a\n", an->lock_time);
     ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
-    if (chain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), &reach, &st);
+    if (lower) rc = ab200_analyser_lower_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, &reach, &evolve, &st);
+    else if (chain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), &reach, &st);
     else rc = ab200_analyser_upper_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, mince, &reach, &evolve, &st);
     if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld arena peak %d\n", rc, ctx.err.c_str(), g_cells, g_steps, g_peak); return 1; }
     printf("cells evolved %ld steps %ld arena peak %d words, max reach boxes per cell %d\n", g_cells, g_steps, g_peak, g_maxboxes);
