@@ -299,7 +299,7 @@ int main(int argc, char** argv) {
         bool ignore_act=geti(kv,"ignore_activations",c.chain?1:0)!=0;
         HybridTime ht(T,c.chain?1:c.events);
         evolver.verbosity=geti(kv,"everb",0);
-        fprintf(out,"frontier %lu ignore_activations %d lower %d\n",(unsigned long)encl.size(),(int)ignore_act,geti(kv,"lower",0));
+        fprintf(out,"frontier %lu ignore_activations %d lower %d backward %d\n",(unsigned long)encl.size(),(int)ignore_act,geti(kv,"lower",0),geti(kv,"backward",0));
         HybridDenotableSet ureach(grid), ufinal(grid);
         int k=0, done=0;
         // to_enclosures (src/reachability_analyser.cpp:1244-1253) walks the set in this same order; the cell box itself
@@ -310,7 +310,7 @@ int main(int argc, char** argv) {
             ++done;
             fprintf(out,"cell %d loc %s box",k,it->first.name().c_str()); dump_box(out,cell_it->second); fprintf(out,"\n");
             try {
-                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(*it,ht,ignore_act,DIRECTION_FORWARD,geti(kv,"lower",0)?LOWER_SEMANTICS:UPPER_SEMANTICS);
+                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(*it,ht,ignore_act,geti(kv,"backward",0)?DIRECTION_BACKWARD:DIRECTION_FORWARD,geti(kv,"lower",0)?LOWER_SEMANTICS:UPPER_SEMANTICS);
                 for(HEnclList::const_iterator r=re.first.begin(); r!=re.first.end(); ++r) {
                     fprintf(out,"r %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
                 for(HEnclList::const_iterator r=re.second.begin(); r!=re.second.end(); ++r) {

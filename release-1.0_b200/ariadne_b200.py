@@ -222,25 +222,25 @@ class Evolver(object):
     def set_accuracy(self, accuracy):
         self._check(self.lib.ab200_set_accuracy(self.handle, accuracy))
 
-    def reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False):
+    def reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False, backward=False):
         """Batch EvolverInterface::reach_evolve: returns (reach, final) as (offsets, boxes, locs) triples."""
         locs = np.ascontiguousarray(np.asarray(locs, dtype=np.int32))
         boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64))
         n = locs.shape[0]
         r = C.c_void_p(); f = C.c_void_p(); st = Status()
         rc = self.lib.ab200_reach_evolve_boxes(self.handle, n, _iptr(locs), _dptr(boxes), float(time), int(max_events),
-                                               int(bool(ignore_activations)), 0, C.byref(r), C.byref(f), C.byref(st))
+                                               int(bool(ignore_activations)), int(bool(backward)), C.byref(r), C.byref(f), C.byref(st))
         self.last_status = st
         self._check(rc)
         return _take_boxlist(self.lib, r, n), _take_boxlist(self.lib, f, n)
 
-    def upper_reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False):
+    def upper_reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False, backward=False):
         """UpperReachEvolveWorker::get_result(): (reach CellSet, evolve CellSet)."""
         locs = np.ascontiguousarray(np.asarray(locs, dtype=np.int32))
         boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64))
         r = C.c_void_p(); e = C.c_void_p(); st = Status()
         rc = self.lib.ab200_upper_reach_evolve(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), float(time), int(max_events),
-                                               int(bool(ignore_activations)), 0, C.byref(r), C.byref(e), C.byref(st))
+                                               int(bool(ignore_activations)), int(bool(backward)), C.byref(r), C.byref(e), C.byref(st))
         self.last_status = st
         self._check(rc)
         return _take_cellset(self.lib, r), _take_cellset(self.lib, e)

@@ -60,6 +60,7 @@ struct LocDesc {
     int32_t finishing_rank;     // number of events whose name sorts before the finishing event "e-2" (std::map order)
     int32_t pad0;
     Func dyn[AB_MAXN];
+    Func dyn_back[AB_MAXN];     // get_directed_dynamic(dynamic,DIRECTION_BACKWARD) = dynamic*constant(-1) (include/evolver_base.h:85-90)
     EventDesc ev[AB_MAXEV];
     double max_step;            // getHybridMaximumStepSize (src/hybrid_evolver-image.cpp:1522-1555)
     double ref_width[AB_MAXN];  // getMinimumGridCellWidths (:1506-1519)

@@ -213,7 +213,6 @@ struct LapOut {
 static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T, int32_t max_events,
                        int ignore_activations, int direction, LapOut& out, ab200_status* status) {
     if (!ctx || !ctx->have_system) return AB200_E_ARGUMENT;
-    if (direction != 0) { ctx->err = "backward evolution is not supported"; return AB200_E_UNSUPPORTED; }
     const bool want_keys = out.reach_keys || out.fin_keys;
     if (want_keys && !ctx->have_layout) { ctx->err = "ab200_set_accuracy must be called first"; return AB200_E_ARGUMENT; }
     CTX_CK(cudaSetDevice(ctx->device));
@@ -224,7 +223,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
     EvolveParams P;
     P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations ? 1 : 0; P.max_boxes = S.max_boxes;
     P.temporal_order = S.temporal_order; P.ratio = S.maximum_enclosure_widths_ratio; P.spacial_sweep = S.sweep_threshold;
-    P.spacial_order = S.spacial_order; P.max_working_sets = 16; P.lower = S.semantics ? 1 : 0; P.pad = 0;
+    P.spacial_order = S.spacial_order; P.max_working_sets = 16; P.lower = S.semantics ? 1 : 0; P.backward = direction ? 1 : 0;
     const size_t table_n = want_keys ? ((size_t)1 << S.hash_log2) : 0;
     std::vector<uint64_t> acc_keys[2];
     if (out.reach_boxes) { out.reach_boxes->offsets.assign(1, 0); }

@@ -322,7 +322,7 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
 // is_enclosure_to_be_discarded (:652-681): a blocking event definitely active on the starting set; with LOWER semantics
 // also a possibly active one whose guard may be crossed in the positive direction (has_nonnegative_crossing :612-632,
 // positively_crossing :637-650: the Lie derivative of the guard over the set's bounding box).
-AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc& L, const TM* set, int n, int p, int lower) {
+AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc& L, const TM* set, int n, int p, int lower, int backward) {
     (void)p;
     int blocking_active = TRI_FALSE;
     for (int e = 0; e < L.n_events; ++e) {
@@ -349,6 +349,7 @@ AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc
             int act = tribool_of(eval_ivl(c, S.ops, L.ev[e].guard, bb));
             if (L.ev[e].lie.end <= L.ev[e].lie.begin) { fail(c, ST_UNSUPPORTED); return true; }   // lie_derivative throws in the reference
             Ivl d = eval_ivl(c, S.ops, L.ev[e].lie, bb);
+            if (backward) d = ivl_neg(d);                 // Lie derivative along dynamic*(-1)
             int pc = d.l > 0 ? TRI_TRUE : (d.u < 0 ? TRI_FALSE : TRI_INDET);
             if (tri_possibly(act) && tri_possibly(pc)) return true;
         }

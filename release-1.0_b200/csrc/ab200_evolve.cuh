@@ -24,7 +24,7 @@ struct EvolveParams {
     int32_t spacial_order;     // 6
     int32_t max_working_sets;  // per-cell queue capacity (device limit, not a reference setting)
     int32_t lower;             // Semantics: 0 = UPPER_SEMANTICS, 1 = LOWER_SEMANTICS (include/evolver_interface.h:46-49)
-    int32_t pad;
+    int32_t backward;          // ContinuousEvolutionDirection: 0 = DIRECTION_FORWARD, 1 = DIRECTION_BACKWARD
 };
 
 struct CellOutput {
@@ -149,10 +149,11 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             double remaining = sub_m(c.rnd, P.T, trange.l);
             double hprop = dmin(remaining, L.max_step);
             Ivl bb[AB_MAXN], dom[AB_MAXN + 1];
-            double h = flow_bounds(c, S.ops, L.dyn, n, range, hprop, bb);
+            const Func* vf = P.backward ? L.dyn_back : L.dyn;      // get_directed_dynamic (:470)
+            double h = flow_bounds(c, S.ops, vf, n, range, hprop, bb);
             if (c.status != ST_OK) break;
             TM flow[AB_MAXN], fset[AB_MAXN];
-            flow_model(c, S.ops, L.dyn, n, range, h, bb, P.temporal_order, flow, dom);
+            flow_model(c, S.ops, vf, n, range, h, bb, P.temporal_order, flow, dom);
             flow_apply(c, flow, n, dom, ws.set, p, h, fset);
 #ifdef AB_DEBUG_DUMP
             printf("h %a bb", h); for (int i = 0; i < n; ++i) printf(" %a %a", bb[i].l, bb[i].u); printf("\n");
@@ -168,7 +169,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             BlockingInfo B;
             compute_blocking_info(c, S, L, fset, n, p, tstep, spacial, B);
             if (c.status != ST_OK) break;
-            if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p, P.lower)) {
+            if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p, P.lower, P.backward)) {
                 if (c.status != ST_OK) break;
                 Activation acts[AB_MAXEV]; int na = 0;
                 if (!P.ignore_activations) {

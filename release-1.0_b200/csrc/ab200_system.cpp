@@ -108,6 +108,21 @@ std::string parse_system(const std::string& text, HostSystem& out) {
         }
     }
     if (out.desc.n_locs == 0) return "no locations";
+    // backward dynamics: every component followed by "* constant(-1)", which is how the reference builds it
+    // (VectorFunction*ScalarFunction::constant(n,-1): f(x) times the model/interval of the constant polynomial -1)
+    for (int l = 0; l < out.desc.n_locs; ++l) {
+        LocDesc& L = out.desc.loc[l];
+        for (int i = 0; i < L.n; ++i) {
+            const int len = L.dyn[i].end - L.dyn[i].begin;
+            if (len <= 0) continue;
+            if (out.desc.n_ops + len + 2 > AB_MAXOPS) return "too many tape ops";
+            L.dyn_back[i].begin = out.desc.n_ops;
+            for (int k = 0; k < len; ++k) out.desc.ops[out.desc.n_ops++] = out.desc.ops[L.dyn[i].begin + k];
+            TapeOp c; c.op = OP_CNST; c.arg = 0; c.lo = -1.0; c.hi = -1.0; out.desc.ops[out.desc.n_ops++] = c;
+            TapeOp m; m.op = OP_MUL; m.arg = 0; m.lo = 0; m.hi = 0; out.desc.ops[out.desc.n_ops++] = m;
+            L.dyn_back[i].end = out.desc.n_ops;
+        }
+    }
     for (int l = 0; l < out.desc.n_locs; ++l) {
         const LocDesc& L = out.desc.loc[l];
         if (L.n == 0) return "location without a header";

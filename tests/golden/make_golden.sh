@@ -40,3 +40,6 @@ $H watertank cells acc=3 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5.8 lower
 $H bouncingball reach acc=4 chain=0 lower=1 T=1.5 init=0.0,0.5,1.0,2.0 out=$G/bouncingball_lower_reach_acc4.txt
 $H vanderpol reach acc=4 lower=1 T=1.5 init=1.0,1.5,1.0,1.6 out=$G/vanderpol_lower_reach_acc4.txt
 $H watertank reach acc=3 lower=1 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5.8 out=$G/watertank_lower_reach_acc3.txt
+# DIRECTION_BACKWARD (the dynamics times constant(-1), include/evolver_base.h:85-90)
+$H vanderpol cells acc=4 init=1.0,1.5,1.0,1.6 backward=1 out=$G/vanderpol_cells_acc4_backward.txt
+$H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 backward=1 out=$G/bouncingball_cells_acc4_backward.txt

@@ -44,6 +44,8 @@ def load_dump(name):
                 out["grid"][loc] = g
             elif k == "frontier":
                 out["config"]["frontier"] = int(t[1]); out["config"]["ignore_activations"] = int(t[3])
+                for a, b in zip(t[4::2], t[5::2]):          # optional "lower L backward B"
+                    out["config"][a] = int(b)
             elif k == "cell":
                 cur_cell = {"id": int(t[1]), "loc": t[3], "box": [_f(x) for x in t[5:]], "reach": [], "final": [],
                             "reach_loc": [], "final_loc": [], "dreach": [], "dfinal": [], "error": None}

@@ -48,18 +48,21 @@ def test_reach_evolve_boxes_bit_exact(pkg, system, name, arena):
 
 @pytest.mark.parametrize("system,name", [("bouncingball", "bouncingball_cells_acc4_lower.txt"),
                                          ("bouncingball", "bouncingball_cells_acc4_lower_events.txt"),
-                                         ("watertank", "watertank_cells_acc3_lower.txt")])
-def test_reach_evolve_lower_semantics_bit_exact(pkg, system, name):
+                                         ("watertank", "watertank_cells_acc3_lower.txt"),
+                                         ("vanderpol", "vanderpol_cells_acc4_backward.txt"),
+                                         ("bouncingball", "bouncingball_cells_acc4_backward.txt")])
+def test_reach_evolve_lower_semantics_and_backward_bit_exact(pkg, system, name):
     """EvolverInterface::reach_evolve(..., LOWER_SEMANTICS): per-enclosure reach / final boxes, location by location (the
     reference's list sets are grouped by location, within a location in insertion order)."""
     d = golden_io.load_dump(name)
-    ev = _evolver(pkg, d, system=system, arena_words=131072, max_boxes=320, semantics=1)
+    ev = _evolver(pkg, d, system=system, arena_words=131072, max_boxes=320, semantics=d["config"].get("lower", 0))
     try:
         dim = ev.dims[0]
         locs = [ev.location(c["loc"]) for c in d["cells"]]
         boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
         (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, d["config"]["T"], d["config"]["events"],
-                                                                  ignore_activations=bool(d["config"]["ignore_activations"]))
+                                                                  ignore_activations=bool(d["config"]["ignore_activations"]),
+                                                                  backward=bool(d["config"].get("backward", 0)))
         for i, c in enumerate(d["cells"]):
             for mine_b, mine_l, ref_b, ref_l, what in ((rbox[roff[i]:roff[i + 1], :2 * dim], rloc[roff[i]:roff[i + 1]], c["reach"], c["reach_loc"], "reach"),
                                                        (fbox[foff[i]:foff[i + 1], :2 * dim], floc[foff[i]:foff[i + 1]], c["final"], c["final_loc"], "final")):

@@ -41,7 +41,7 @@ int main(int argc, char** argv) {
     int verbose = argc > 4 ? atoi(argv[4]) : 0;
     std::ifstream df(argv[2]);
     std::string line;
-    double T = 0; int events = 5, ignore_act = 0, chain = 0, lower_sem = 0;
+    double T = 0; int events = 5, ignore_act = 0, chain = 0, lower_sem = 0, backward_dir = 0;
     std::map<std::string, int> locidx;
     for (size_t i = 0; i < hs.loc_names.size(); ++i) locidx[hs.loc_names[i]] = (int)i;
     std::vector<RefCell> cells; std::vector<std::vector<double> >* dcur = 0; int ACC = 0;
@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
             in >> k; { std::string v; in >> v; L.max_step = strtod(v.c_str(), 0); }
             in >> k; for (int i = 0; i < n; ++i) { std::string v; in >> v; L.ref_width[i] = strtod(v.c_str(), 0); }
         }
-        else if (t == "frontier") { std::string k; int nf; in >> nf >> k >> ignore_act; if (in >> k) in >> lower_sem; }
+        else if (t == "frontier") { std::string k; int nf; in >> nf >> k >> ignore_act; if (in >> k) in >> lower_sem; if (in >> k) in >> backward_dir; }
         else if (t == "cell") { RefCell c; int id; std::string k, name; in >> id >> k >> name >> k; c.loc = locidx[name]; std::string v; while (in >> v) c.box.push_back(strtod(v.c_str(), 0)); cells.push_back(c); }
         else if (t == "r" || t == "f") { std::string name, v; in >> name; std::vector<double> b; while (in >> v) b.push_back(strtod(v.c_str(), 0)); if (t == "r") { cells.back().reach.push_back(b); cells.back().rloc.push_back(locidx[name]); } else { cells.back().fin.push_back(b); cells.back().floc.push_back(locidx[name]); } }
         else if (t == "x") { cells.back().err = line; }
@@ -77,7 +77,7 @@ int main(int argc, char** argv) {
     for (size_t ci = 0; ci < cells.size() && (int)ci < maxcells; ++ci) {
         RefCell& rc = cells[ci];
         Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = ARENA; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
-        EvolveParams P; P.lower = lower_sem; P.pad = 0; P.T = T; P.max_events = chain ? 1 : events; P.ignore_activations = ignore_act; P.max_boxes = MAXB; P.temporal_order = 6;
+        EvolveParams P; P.lower = lower_sem; P.backward = backward_dir; P.T = T; P.max_events = chain ? 1 : events; P.ignore_activations = ignore_act; P.max_boxes = MAXB; P.temporal_order = 6;
         P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = reach.data(); O.reach_loc = rloc.data(); O.n_reach = 0; O.final_ = fin.data(); O.final_loc = floc.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         evolve_cell(c, hs.desc, rc.loc, rc.box.data(), P, O);
