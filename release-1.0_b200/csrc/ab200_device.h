@@ -5,7 +5,9 @@
 #include "ab200_evolve.cuh"
 #include "ab200_grid.cuh"
 
+#ifndef AB_EVOLVE_BLOCK
 #define AB_EVOLVE_BLOCK 64
+#endif
 
 namespace ab200 { inline namespace AB_VARIANT {
 int dev_upload_system(const SystemDesc* s, char* errbuf, int errlen);
