@@ -43,3 +43,6 @@ $H watertank reach acc=3 lower=1 T=0.5 initr=1.0,1.0,7.6,7.7 initf=0.0,0.0,5.7,5
 # DIRECTION_BACKWARD (the dynamics times constant(-1), include/evolver_base.h:85-90)
 $H vanderpol cells acc=4 init=1.0,1.5,1.0,1.6 backward=1 out=$G/vanderpol_cells_acc4_backward.txt
 $H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 backward=1 out=$G/bouncingball_cells_acc4_backward.txt
+# configs[0] as examples/watertank-hysteresis.cc sets it up (both idle locations, x in [6,7.5]), horizon 2: several
+# transitions per trajectory; replayed by the host-build CPU test (too slow per cell for the GPU suite)
+$H watertank reach acc=3 T=2 out=$G/watertank_reach_acc3_T2.txt
