@@ -46,3 +46,4 @@ $H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 backward=1 out=$G/bouncingball_
 # configs[0] as examples/watertank-hysteresis.cc sets it up (both idle locations, x in [6,7.5]), horizon 2: several
 # transitions per trajectory; replayed by the host-build CPU test (too slow per cell for the GPU suite)
 $H watertank reach acc=3 T=2 out=$G/watertank_reach_acc3_T2.txt
+$H springs reach acc=3 out=$G/springs_reach_acc3.txt && gzip -9 -f -n $G/springs_reach_acc3.txt

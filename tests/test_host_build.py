@@ -16,6 +16,22 @@ SRC = [os.path.join(ROOT, "tests", "tools", "hostchain.cpp"),
        os.path.join(ROOT, "release-1.0_b200", "csrc", "ab200_paving.cpp")]
 
 
+def _build(name, extra):
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no host compiler")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, name)
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-frounding-math", "-w"] + extra + ["-x", "c++", "-o", exe] + SRC, timeout=600)
+    return exe
+
+
+@pytest.fixture(scope="module")
+def hostchain_wide():
+    """The same tool with two-word MultiIndex keys (systems with more than two state variables)."""
+    return _build("hostchain_test_kw2", ["-DAB_KW=2"])
+
+
 @pytest.fixture(scope="module")
 def hostchain():
     cxx = shutil.which("g++")
@@ -46,4 +62,25 @@ def test_host_build_reproduces_reference_cell_sets(hostchain, system, golden, ar
     g = os.path.join(ROOT, "tests", "golden")
     out = subprocess.run([hostchain, os.path.join(g, system + ".sys"), os.path.join(g, golden)] + args,
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600).stdout.decode()
+    assert "cell sets identical (bit-exact boxes)" in out, out[-2000:]
+
+
+WIDE_CASES = [
+    ("springs", "springs_reach_acc3.txt.gz", ["upper", "acc=3", "T=40", "domain=0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0",
+                                              "init=0,0,0,0,0,0,0,0,3,3"]),
+    ("boost", "boost_reach_acc4.txt", ["upper", "acc=4", "T=0.011", "domain=0.0,0.001,0.0,3.0,0.0,6.0", "loc=1", "init=0.0,0.0,1.0,1.0,1.0,1.0"]),
+]
+
+
+@pytest.mark.parametrize("system,golden,args", WIDE_CASES)
+def test_host_build_wide_keys_reproduces_reference_cell_sets(hostchain_wide, system, golden, args, tmp_path):
+    import gzip
+    g = os.path.join(ROOT, "tests", "golden")
+    path = os.path.join(g, golden)
+    if golden.endswith(".gz"):
+        path = str(tmp_path / golden[:-3])
+        with open(path, "wb") as f:
+            f.write(gzip.open(os.path.join(g, golden)).read())
+    out = subprocess.run([hostchain_wide, os.path.join(g, system + ".sys"), path] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900).stdout.decode()
     assert "cell sets identical (bit-exact boxes)" in out, out[-2000:]
