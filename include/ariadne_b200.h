@@ -149,8 +149,10 @@ int  ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, cons
 int  ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
                                        double T, int32_t max_events,
                                        ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status);
+/* direction: 0 = DIRECTION_FORWARD (forward_jump_set between laps), 1 = DIRECTION_BACKWARD (backward_jump_set,
+ * src/reachability_restriction.cpp:381-408, src/set_checker.cpp:229-352). */
 int  ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
-                                      ab200_cellset** reach_out, ab200_status* status);
+                                      int32_t direction, ab200_cellset** reach_out, ab200_status* status);
 /* Number of frontier enclosures consumed by the evolver in the last analyser call (the metric's unit of work). */
 int64_t ab200_analyser_cells_evolved(const ab200_analyser* an);
 /* Enumerate a cell set as the reference does (maximal dyadic cells, boxes by bisection, src/bdd_set.cpp:800-891).

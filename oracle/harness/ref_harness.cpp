@@ -362,7 +362,7 @@ int main(int argc, char** argv) {
     std::string err;
     try {
         if(geti(kv,"lower",0)) { make_lpair(reach,evolve)=analyser.lower_reach_evolve(c.initial,HybridTime(T,c.events)); }
-        else if(c.chain) { reach=analyser.outer_chain_reach(c.initial); }
+        else if(c.chain) { reach=analyser.outer_chain_reach(c.initial,geti(kv,"backward",0)?DIRECTION_BACKWARD:DIRECTION_FORWARD); }
         else { make_lpair(reach,evolve)=analyser.upper_reach_evolve(c.initial,HybridTime(T,c.events)); }
     } catch(std::exception& e) { err=e.what(); }
     std::chrono::steady_clock::time_point t1=std::chrono::steady_clock::now();

@@ -103,7 +103,7 @@ def load_library():
     lib.ab200_analyser_lower_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, P(vp), P(vp), P(Status)]
     lib.ab200_analyser_lower_reach_evolve.restype = C.c_int
     lib.ab200_ctx_get_settings.argtypes = [vp, P(Settings)]; lib.ab200_ctx_get_settings.restype = C.c_int
-    lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), P(vp), P(Status)]
+    lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), i32, P(vp), P(Status)]
     lib.ab200_analyser_outer_chain_reach.restype = C.c_int
     lib.ab200_analyser_discretise.argtypes = [vp, u64, P(i32), P(dbl), P(vp)]; lib.ab200_analyser_discretise.restype = C.c_int
     lib.ab200_analyser_cells_evolved.argtypes = [vp]; lib.ab200_analyser_cells_evolved.restype = i64
@@ -342,10 +342,10 @@ class HybridReachabilityAnalyser(object):
     def lower_evolve(self, initial_set, time, max_events=5):
         return self.lower_reach_evolve(initial_set, time, max_events)[1]
 
-    def outer_chain_reach(self, initial_set):
+    def outer_chain_reach(self, initial_set, backward=False):
         locs, boxes = self._initial(initial_set)
         r = C.c_void_p(); st = Status()
-        rc = self.lib.ab200_analyser_outer_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), C.byref(r), C.byref(st))
+        rc = self.lib.ab200_analyser_outer_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), int(bool(backward)), C.byref(r), C.byref(st))
         self.last_status = st
         self.evolver._check(rc)
         return self._wrap(r)

@@ -210,7 +210,7 @@ static int tune_evolver(ab200_analyser* an) {
 }
 
 // to_enclosures (src/reachability_analyser.cpp:1244-1253) + UpperReachEvolveWorker::get_result.
-static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, double T, int events, int ignore_activations,
+static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, double T, int events, int ignore_activations, int direction,
                HybridCells& reach, HybridCells& evolve, ab200_status* st_acc) {
     std::vector<int32_t> locs; std::vector<double> boxes;
     for (int l = 0; l < an->n_locs; ++l) {
@@ -225,7 +225,7 @@ static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, doubl
     an->cells_evolved += (int64_t)locs.size();
     { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
     ab200_cellset *r = 0, *e = 0; ab200_status st; memset(&st, 0, sizeof(st));
-    int rc = ab200_upper_reach_evolve(an->ctx, locs.size(), locs.data(), boxes.data(), T, events, ignore_activations, 0, &r, &e, &st);
+    int rc = ab200_upper_reach_evolve(an->ctx, locs.size(), locs.data(), boxes.data(), T, events, ignore_activations, direction, &r, &e, &st);
     if (st_acc) {
         st_acc->steps += st.steps; st_acc->launches += st.launches; st_acc->keys_emitted += st.keys_emitted; st_acc->evolve_ms += st.evolve_ms; st_acc->raster_ms += st.raster_ms;
         st_acc->arena_peak = std::max(st_acc->arena_peak, st.arena_peak);
@@ -305,6 +305,58 @@ struct JumpCalc {
             for (int i = 0; i < nt; ++i) { TM t = eval_tm(c, S.ops, E.reset[i], src); tb[i] = tm_range(c, t); }
             int out_trg = outside_any_invariant(E.target, tb);
             result = tri_and(tri_and(tri_not(out_src), taken), tri_not(out_trg));
+        }
+        c.A.top = m;
+        return result;
+    }
+
+    // BackwardDiscreteJumpSetChecker (src/set_checker.cpp:229-352): a source cell is kept if some transition may be taken
+    // from it into the set reached so far (`start`, one tree per location, with the bounding boxes of its cells).
+    bool has_feasible_transitions(int l, const TM* src, int n, const std::vector<CellTree>& start, const std::vector<std::vector<double> >& start_bb) {
+        const LocDesc& L = S.loc[l];
+        for (int e = 0; e < L.n_events; ++e) {
+            const EventDesc& E = L.ev[e];
+            if (E.kind != EV_URGENT && E.kind != EV_PERMISSIVE) continue;
+            if (start[E.target].empty()) continue;
+            const int nt = S.loc[E.target].n;
+            const int m = c.A.top;
+            bool overlap = true;
+            for (int i = 0; i < nt; ++i) {
+                TM t = eval_tm(c, S.ops, E.reset[i], src); Ivl r = tm_range(c, t);
+                const double bl = start_bb[E.target][2 * i], bu = start_bb[E.target][2 * i + 1];
+                if (!(bl < r.u && bu > r.l)) overlap = false;                     // Box::overlaps (open)
+            }
+            c.A.top = m;
+            (void)n;
+            if (overlap) return true;
+        }
+        return false;
+    }
+    int check_backward(int l, const double* box, const std::vector<CellTree>& start, const std::vector<std::vector<double> >& start_bb) {
+        const LocDesc& L = S.loc[l];
+        const int n = L.n;
+        const int m = c.A.top;
+        Ivl bx[AB_MAXN];
+        for (int i = 0; i < n; ++i) bx[i] = ivl(box[2 * i], box[2 * i + 1]);
+        int out_src = outside_any_invariant(l, bx);
+        if (out_src == TRI_TRUE) return TRI_FALSE;
+        TM src[AB_MAXN]; box_set(bx, n, src);
+        if (!has_feasible_transitions(l, src, n, start, start_bb)) { c.A.top = m; return TRI_FALSE; }
+        int result = TRI_FALSE;
+        for (int e = 0; e < L.n_events && c.status == ST_OK; ++e) {
+            const EventDesc& E = L.ev[e];
+            if (E.kind != EV_URGENT && E.kind != EV_PERMISSIVE) continue;
+            int taken = transition_taken(l, e, src, n);
+            if (taken == TRI_FALSE) continue;
+            const int nt = S.loc[E.target].n;
+            Ivl tb[AB_MAXN]; double tbox[2 * AB_MAXN];
+            for (int i = 0; i < nt; ++i) { TM t = eval_tm(c, S.ops, E.reset[i], src); tb[i] = tm_range(c, t); tbox[2 * i] = tb[i].l; tbox[2 * i + 1] = tb[i].u; }
+            int out_trg = outside_any_invariant(E.target, tb);
+            if (tri_not(out_trg) == TRI_FALSE) continue;                         // possibly(!is_outside_any_trg_invariant)
+            int covered = start[E.target].superset(tbox) ? TRI_TRUE : (start[E.target].disjoint(tbox) ? TRI_FALSE : TRI_INDET);
+            int ok = tri_and(tri_and(tri_not(out_src), taken), tri_and(covered, tri_not(out_trg)));
+            if (ok == TRI_TRUE) { c.A.top = m; return TRI_TRUE; }
+            if (ok == TRI_INDET) result = TRI_INDET;
         }
         c.A.top = m;
         return result;
@@ -407,6 +459,33 @@ static int forward_jump_set(ab200_analyser* an, const HybridCells& reach, Hybrid
     return AB200_OK;
 }
 
+// ReachabilityRestriction::backward_jump_set (src/reachability_restriction.cpp:381-408): every location's domain
+// discretisation (created now if it was still lazy, which also changes what later laps are tuned on) restricted to the
+// cells from which a transition may lead into `reach`.
+static int backward_jump_set(ab200_analyser* an, const HybridCells& reach, HybridCells& result) {
+    const HostSystem* hs = ab200_ctx_system(an->ctx);
+    const SystemDesc& S = hs->desc;
+    result = empty_cells(an);
+    JumpCalc J(S);
+    std::vector<CellTree> start; std::vector<std::vector<double> > start_bb(an->n_locs, std::vector<double>(2 * AB_GRID_MAXN, 0.0));
+    for (int l = 0; l < an->n_locs; ++l) { start.push_back(CellTree(reach[l])); if (!reach[l].empty()) reach[l].bounding_box(start_bb[l].data()); }
+    bool ok = true;
+    for (int l = 0; l < an->n_locs; ++l) {
+        ok = ensure_restriction(an, l) && ok;
+        CellSet src = an->restriction[l];
+        src.outer_restrict([&](const double* box) { return J.check_backward(l, box, start, start_bb); });
+        if (J.c.status != ST_OK) {
+            ab200_ctx_set_error(an->ctx, J.lie_missing
+                ? "backward_jump_set: Failed to compute Lie derivative of a guard (the reference throws here too, src/function.cpp:1329)"
+                : "backward_jump_set: guard/reset cannot be evaluated on the host (unsupported function or arena)");
+            return J.c.status;
+        }
+        result[l] = src;
+    }
+    if (!ok) { ab200_ctx_set_error(an->ctx, "domain lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    return AB200_OK;
+}
+
 // ReachabilityRestriction::outer_intersection_with(HybridBoundedConstraintSet) for box-only sets
 // (src/reachability_restriction.cpp:522-535).
 static int discretise_initial(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, HybridCells& initial) {
@@ -450,17 +529,17 @@ extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_
     if (rc != AB200_OK) return rc;
     HybridCells reach = empty_cells(an), evolve = empty_cells(an), found, next;
     // first lap: evolver->orbit per initial enclosure (:348-353)
-    rc = lap(an, initial, mince, lock, max_events, 0, found, next, &st);
+    rc = lap(an, initial, mince, lock, max_events, 0, 0, found, next, &st);
     if (rc != AB200_OK) { if (status) *status = st; return rc; }
     for (int l = 0; l < an->n_locs; ++l) { reach[l].adjoin(found[l]); evolve[l].adjoin(next[l]); }
     for (unsigned i = 1; i < time_steps; ++i) {
-        rc = lap(an, evolve, 0, lock, max_events, 0, found, next, &st);
+        rc = lap(an, evolve, 0, lock, max_events, 0, 0, found, next, &st);
         if (rc != AB200_OK) { if (status) *status = st; return rc; }
         evolve = next;
         for (int l = 0; l < an->n_locs; ++l) reach[l].adjoin(found[l]);
     }
     if (!all_empty(evolve) && remaining > 0) {
-        rc = lap(an, evolve, 0, remaining, max_events, 0, found, next, &st);
+        rc = lap(an, evolve, 0, remaining, max_events, 0, 0, found, next, &st);
         if (rc != AB200_OK) { if (status) *status = st; return rc; }
         evolve = next;
         for (int l = 0; l < an->n_locs; ++l) reach[l].adjoin(found[l]);
@@ -554,7 +633,7 @@ extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_
 }
 
 extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
-                                                ab200_cellset** reach_out, ab200_status* status) {
+                                                int32_t direction, ab200_cellset** reach_out, ab200_status* status) {
     if (!an || !reach_out) return AB200_E_ARGUMENT;
     *reach_out = 0;
     an->cells_evolved = 0;
@@ -565,12 +644,12 @@ extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_i
     HybridCells reach = empty_cells(an), fin = empty_cells(an), new_reach, new_final;
     int guard = 0;
     while (!all_empty(current) && guard++ < 100000) {
-        rc = lap(an, current, 0, an->lock_time, 1, 1, new_reach, new_final, &st);       // lock_to_grid_steps=1, ignore_activations
+        rc = lap(an, current, 0, an->lock_time, 1, 1, direction, new_reach, new_final, &st);       // lock_to_grid_steps=1, ignore_activations
         if (rc != AB200_OK) { if (status) *status = st; return rc; }
         for (int l = 0; l < an->n_locs; ++l) { new_final[l].remove(fin[l]); new_reach[l].remove(reach[l]); }
         apply_restriction(an, new_final); apply_restriction(an, new_reach);
         for (int l = 0; l < an->n_locs; ++l) { reach[l].adjoin(new_reach[l]); fin[l].adjoin(new_final[l]); }
-        rc = forward_jump_set(an, new_reach, current);
+        rc = direction ? backward_jump_set(an, new_reach, current) : forward_jump_set(an, new_reach, current);
         if (rc != AB200_OK) { if (status) { *status = st; status->code = rc; } return rc; }
         for (int l = 0; l < an->n_locs; ++l) current[l].adjoin(new_final[l]);
     }

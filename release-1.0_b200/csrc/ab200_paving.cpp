@@ -231,6 +231,88 @@ bool CellSet::adjoin_outer_approximation(const double* bbox, const BoxTest& disj
     return A.ok;
 }
 
+namespace {
+struct TreeQuery {
+    const std::vector<Path>* P; int depth, dim;
+};
+}
+static void sorted_paths(const CellSet& cs, Root& root, std::vector<Path>& P, CellBox& rb) {
+    const int dim = cs.grid.dim;
+    root = cs.minimal_root();
+    int l2[AB_GRID_MAXN], ns[AB_GRID_MAXN]; long long lower[AB_GRID_MAXN];
+    root_extent(root, dim, l2, lower);
+    for (int i = 0; i < dim; ++i) ns[i] = l2[i] + cs.K.acc;
+    P.resize(cs.keys.size());
+    long long idx[AB_GRID_MAXN], rel[AB_GRID_MAXN];
+    for (size_t k = 0; k < cs.keys.size(); ++k) {
+        int l; key_unpack(cs.K, cs.keys[k], &l, idx);
+        for (int i = 0; i < dim; ++i) rel[i] = idx[i] - lower[i] * (1LL << cs.K.acc);
+        P[k] = make_path(root, dim, cs.K.acc, rel, ns);
+    }
+    std::sort(P.begin(), P.end());
+    Ivl rc[AB_GRID_MAXN];
+    root_box(cs.grid.origin, cs.grid.lengths, dim, root, rc);
+    for (int i = 0; i < dim; ++i) { rb.b[2 * i] = rc[i].l; rb.b[2 * i + 1] = rc[i].u; }
+}
+static bool superset_rec(const TreeQuery& Q, size_t lo, size_t hi, int level, int split, const CellBox& cell, CellBox box) {
+    if (hi == lo) return false;                                           // bddfalse
+    size_t full = (Q.depth - level >= 63) ? (size_t)-1 : ((size_t)1 << (Q.depth - level));
+    if (hi - lo == full) return true;                                     // bddtrue
+    const std::vector<Path>& P = *Q.P;
+    int shift = Q.depth - 1 - level;
+    size_t a = lo, b = hi;
+    while (a < b) { size_t m = (a + b) / 2; if ((P[m] >> shift) & 1) b = m; else a = m + 1; }
+    double c = (cell.b[2 * split] + cell.b[2 * split + 1]) / 2.0;
+    CellBox left = cell, right = cell;
+    left.b[2 * split + 1] = c; right.b[2 * split] = c;
+    CellBox lb = box, rb = box;                                           // intersection of the box with the two subcells
+    lb.b[2 * split] = std::max(box.b[2 * split], left.b[2 * split]); lb.b[2 * split + 1] = std::min(box.b[2 * split + 1], left.b[2 * split + 1]);
+    rb.b[2 * split] = std::max(box.b[2 * split], right.b[2 * split]); rb.b[2 * split + 1] = std::min(box.b[2 * split + 1], right.b[2 * split + 1]);
+    const int next = (split + 1) % Q.dim;
+    if (!(lb.b[2 * split] > lb.b[2 * split + 1])) { if (!superset_rec(Q, lo, a, level + 1, next, left, lb)) return false; }
+    if (!(rb.b[2 * split] > rb.b[2 * split + 1])) return superset_rec(Q, a, hi, level + 1, next, right, rb);
+    return true;
+}
+CellTree::CellTree(const CellSet& cs) : depth(0), dim(cs.grid.dim), first_split(0) {
+    if (cs.keys.empty()) return;
+    Root root;
+    sorted_paths(cs, root, paths, root_cell);
+    depth = root.height + dim * cs.K.acc;
+    first_split = splitting_coordinate(root.height, dim);
+}
+bool CellTree::superset(const double* box) const {
+    for (int i = 0; i < dim; ++i) if (box[2 * i] > box[2 * i + 1]) return true;                  // empty box
+    if (paths.empty()) return false;       // an empty set: outside its unit root the subset test fails, inside it meets bddfalse
+    for (int i = 0; i < dim; ++i) if (!(box[2 * i] >= root_cell.b[2 * i] && box[2 * i + 1] <= root_cell.b[2 * i + 1])) return false;   // box.subset(root_cell)
+    TreeQuery Q; Q.P = &paths; Q.depth = depth; Q.dim = dim;
+    CellBox bx; for (int i = 0; i < 2 * dim; ++i) bx.b[i] = box[i];
+    return superset_rec(Q, 0, paths.size(), 0, first_split, root_cell, bx);
+}
+static bool disjoint_rec(const TreeQuery& Q, size_t lo, size_t hi, int level, int split, const CellBox& cell, const double* box) {
+    if (hi == lo) return true;                                            // bddfalse
+    bool dis = false;
+    for (int i = 0; i < Q.dim; ++i) if (box[2 * i] > cell.b[2 * i + 1] || box[2 * i + 1] < cell.b[2 * i]) dis = true;   // Box::disjoint (closed)
+    if (dis) return true;
+    size_t full = (Q.depth - level >= 63) ? (size_t)-1 : ((size_t)1 << (Q.depth - level));
+    if (hi - lo == full) return false;                                    // bddtrue: the (false) result of the test
+    const std::vector<Path>& P = *Q.P;
+    int shift = Q.depth - 1 - level;
+    size_t a = lo, b = hi;
+    while (a < b) { size_t m = (a + b) / 2; if ((P[m] >> shift) & 1) b = m; else a = m + 1; }
+    double c = (cell.b[2 * split] + cell.b[2 * split + 1]) / 2.0;
+    CellBox left = cell, right = cell;
+    left.b[2 * split + 1] = c; right.b[2 * split] = c;
+    const int next = (split + 1) % Q.dim;
+    if (!disjoint_rec(Q, lo, a, level + 1, next, left, box)) return false;
+    return disjoint_rec(Q, a, hi, level + 1, next, right, box);
+}
+bool CellTree::disjoint(const double* box) const {
+    for (int i = 0; i < dim; ++i) if (box[2 * i] > box[2 * i + 1]) return true;
+    if (paths.empty()) return true;
+    TreeQuery Q; Q.P = &paths; Q.depth = depth; Q.dim = dim;
+    return disjoint_rec(Q, 0, paths.size(), 0, first_split, root_cell, box);
+}
+
 bool CellSet::bounding_box(double* box) const {
     std::vector<CellBox> cells; enumerate(cells);
     if (cells.empty()) return false;

@@ -58,6 +58,7 @@ class CellSet {
     // (`disjoint` returns 1 only for "definitely disjoint"). Returns false if a cell fell outside the key window.
     bool adjoin_outer_approximation(const double* bbox, const BoxTest& disjoint);
 
+
     // Minimal root (height>=0) covering all cells; undefined for the empty set.
     Root minimal_root() const;
     // Maximal dyadic cells, left-first. If mince_levels >= 0, cells are split down to at least that many levels
@@ -67,6 +68,23 @@ class CellSet {
     size_t size() const { std::vector<CellBox> v; enumerate(v); return v.size(); }
     // bounding box of the set as the reference computes it (src/bdd_set.cpp:893-928): hull of the leaf boxes.
     bool bounding_box(double* box) const;
+};
+
+// Box queries against a fixed cell set (the tree of root-to-leaf paths is built once).
+//   superset(box): BDDTreeSet::superset(Box) (src/bdd_set.cpp:1325-1343,340-383) -- the box lies in the root cell and every
+//                  subtree it reaches (splitting the box with the cells, closed intervals) is full;
+//   disjoint(box): BDDTreeSet::disjoint(Box) (src/bdd_set.cpp:1346-1361,386-415) -- no maximal full subtree whose closed cell
+//                  meets the closed box.
+class CellTree {
+  public:
+    explicit CellTree(const CellSet& cs);
+    bool superset(const double* box) const;
+    bool disjoint(const double* box) const;
+    bool empty() const { return paths.empty(); }
+  private:
+    std::vector<unsigned __int128> paths;
+    CellBox root_cell;
+    int depth, dim, first_split;
 };
 
 } // namespace ab200

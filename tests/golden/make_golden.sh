@@ -47,3 +47,5 @@ $H bouncingball cells acc=4 init=0.0,0.5,1.0,2.0 backward=1 out=$G/bouncingball_
 # transitions per trajectory; replayed by the host-build CPU test (too slow per cell for the GPU suite)
 $H watertank reach acc=3 T=2 out=$G/watertank_reach_acc3_T2.txt
 $H springs reach acc=3 out=$G/springs_reach_acc3.txt && gzip -9 -f -n $G/springs_reach_acc3.txt
+# outer_chain_reach(initial, DIRECTION_BACKWARD): backward laps plus backward_jump_set between them
+$H bouncingball reach acc=5 backward=1 init=2.0,4.0,0.0,0.3 out=$G/bouncingball_backward_chain_acc5.txt

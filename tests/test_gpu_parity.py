@@ -98,7 +98,8 @@ def test_analyser_upper_reach_evolve_identical_cells(pkg, name, init, laps):
 
 
 @pytest.mark.parametrize("name,init", [("bouncingball_chain_acc5.txt", [0.0, 0.001, 1.999, 2.0]),
-                                         ("bouncingball_chain_acc6.txt", [-2.0, 0.5, 0.5, 1.5])])
+                                         ("bouncingball_chain_acc6.txt", [-2.0, 0.5, 0.5, 1.5]),
+                                         ("bouncingball_backward_chain_acc5.txt", [2.0, 4.0, 0.0, 0.3])])
 def test_outer_chain_reach_with_jumps_identical_cells(pkg, name, init):
     """BASELINE configs[1]: outer_chain_reach of the bouncing ball -- device laps (ignore_activations, urgent guard) plus
     the grid-side jump sets of src/reachability_restriction.cpp:340-375 between laps."""
@@ -106,7 +107,7 @@ def test_outer_chain_reach_with_jumps_identical_cells(pkg, name, init):
     an = pkg.HybridReachabilityAnalyser(_system("bouncingball"), [-10.1, 10.1, -0.1, 2.1], d["config"]["acc"], settings={"arena_words": 65536})
     try:
         assert an.lock_to_grid_time == d["config"]["lock"]
-        reach = an.outer_chain_reach({"freefall": init})
+        reach = an.outer_chain_reach({"freefall": init}, backward="backward" in name)
         _, rb = an.enumerate(reach)
         assert golden_io.boxes_equal_bits(rb, d["sets"]["reach"]["freefall"])
         assert an.last_status.launches > 0

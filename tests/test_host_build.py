@@ -51,6 +51,7 @@ CASES = [
     ("vanderpol", "vanderpol_reach_acc4.txt", ["upper", "acc=4", "T=2.0", "domain=-3,3,-3,3", "init=-1.6,-1.3,0.3,0.8"]),
     ("watertank", "watertank_reach_acc3_T2.txt", ["upper", "acc=3", "T=2", "domain=0.0,1.0,4.5,9.0", "loc=2", "init=1.0,1.0,6.0,7.5",
                                                   "loc=1", "init=0.0,0.0,6.0,7.5"]),
+    ("bouncingball", "bouncingball_backward_chain_acc5.txt", ["bchain", "acc=5", "domain=-10.1,10.1,-0.1,2.1", "init=2.0,4.0,0.0,0.3"]),
     ("bouncingball", "bouncingball_lower_reach_acc4.txt", ["lower", "acc=4", "T=1.5", "domain=-10.1,10.1,-0.1,2.1", "init=0.0,0.5,1.0,2.0"]),
     ("watertank", "watertank_lower_reach_acc3.txt", ["lower", "acc=3", "T=0.5", "domain=0.0,1.0,4.5,9.0", "loc=2", "init=1.0,1.0,7.6,7.7",
                                                      "loc=1", "init=0.0,0.0,5.7,5.8"]),

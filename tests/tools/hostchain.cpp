@@ -59,7 +59,6 @@ static long g_cells = 0, g_steps = 0; static int g_peak = 0, g_maxboxes = 0;
 extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T,
                                         int32_t max_events, int32_t ignore_activations, int32_t direction,
                                         ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status) {
-    (void)direction;
     static int lapno = 0; long steps0 = g_steps;
     struct LapLog { int no; uint64_t n; long* s; long s0; ~LapLog() { if (getenv("HOSTCHAIN_LAPS")) printf("lap %d cells %llu steps %ld\n", no, (unsigned long long)n, *s - s0); } } laplog = { lapno++, n_cells, &g_steps, steps0 };
     const SystemDesc& S = ctx->sys.desc;
@@ -68,7 +67,7 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
     std::vector<uint64_t> rkeys, fkeys;
     for (uint64_t ci = 0; ci < n_cells; ++ci) {
         Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
-        EvolveParams P; P.lower = 0; P.backward = 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
+        EvolveParams P; P.lower = 0; P.backward = direction ? 1 : 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
         g_cells++; g_steps += O.steps; if (c.A.peak > g_peak) g_peak = c.A.peak; if (O.n_reach > g_maxboxes) g_maxboxes = O.n_reach;
@@ -134,6 +133,7 @@ int main(int argc, char** argv) {
     std::string err = parse_system(ss.str(), ctx.sys); if (!err.empty()) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
     const bool chain = !strcmp(argv[3], "chain");
     const bool lower = !strcmp(argv[3], "lower");
+    const bool bchain = !strcmp(argv[3], "bchain");
     memset(&ctx.settings, 0, sizeof(ctx.settings));
     int acc = 4, events = 5, mince = 0; double T = 1.0, lock = 0; std::vector<double> dom; std::vector<std::vector<double> > inits; std::vector<int32_t> init_locs; int init_loc = 0;
     for (int a = 4; a < argc; ++a) {
@@ -157,7 +157,7 @@ int main(int argc, char** argv) {
     printf("lock %a\n", an->lock_time);
     ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
     if (lower) rc = ab200_analyser_lower_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, &reach, &evolve, &st);
-    else if (chain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), &reach, &st);
+    else if (chain || bchain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), bchain ? 1 : 0, &reach, &st);
     else rc = ab200_analyser_upper_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, mince, &reach, &evolve, &st);
     if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld arena peak %d\n", rc, ctx.err.c_str(), g_cells, g_steps, g_peak); return 1; }
     printf("cells evolved %ld steps %ld arena peak %d words, max reach boxes per cell %d\n", g_cells, g_steps, g_peak, g_maxboxes);
@@ -170,7 +170,7 @@ int main(int argc, char** argv) {
         else if (t == "c" && cur) { std::vector<double> b; std::string v; while (in >> v) b.push_back(strtod(v.c_str(), 0)); cur->push_back(b); }
     }
     int bad = 0;
-    for (int which = 0; which < (chain ? 1 : 2); ++which) {
+    for (int which = 0; which < ((chain || bchain) ? 1 : 2); ++which) {
         uint64_t cnt = 0; ab200_analyser_enumerate(an, which ? evolve : reach, 0, &cnt, 0, 0);
         std::vector<int32_t> locs(cnt); std::vector<double> boxes(cnt * AB200_BOX_STRIDE);
         ab200_analyser_enumerate(an, which ? evolve : reach, 0, &cnt, locs.data(), boxes.data());
