@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", type=int, default=0, help="subsample the frontier (0 = the full 101,400 cells)")
     ap.add_argument("--cpu-cells", type=int, default=0, help="CPU sample size (0 = 3 cells per host thread)")
-    ap.add_argument("--arena-words", type=int, default=12288)
+    ap.add_argument("--arena-words", type=int, default=32768)
     ap.add_argument("--max-boxes", type=int, default=320)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lap-scale", type=float, default=1.0, help="PROFILING ONLY: shorten the lap so that ncu can replay the kernel; not a bench value")

@@ -106,7 +106,7 @@ extern "C" int ab200_analyser_create(ab200_analyser** out, ab200_ctx* ctx, const
     an->ctx = ctx; an->accuracy = accuracy; an->n_locs = L; an->dim = dim; an->cells_evolved = 0;
     an->domain.resize(L); an->grid.resize(L); an->max_step.resize(L);
     std::vector<std::vector<double> > hmad(L, std::vector<double>(dim, 0.0));
-    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    Ctx c; ctx_init_host(c, 0, 0);
     double lock = 0.0;
     for (int l = 0; l < L; ++l) {
         an->domain[l].assign(domain_boxes + (size_t)l * AB200_BOX_STRIDE, domain_boxes + (size_t)l * AB200_BOX_STRIDE + 2 * dim);
@@ -177,7 +177,7 @@ static int tune_evolver(ab200_analyser* an) {
     const SystemDesc& S = hs->desc;
     const int dim = an->dim;
     const double divider = (double)(1 << an->accuracy);
-    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    Ctx c; ctx_init_host(c, 0, 0);
     for (int l = 0; l < an->n_locs; ++l) {
         double bb[2 * AB_GRID_MAXN];
         bool have = false;
@@ -250,7 +250,7 @@ struct JumpCalc {
     Ctx c;
     bool lie_missing;
     explicit JumpCalc(const SystemDesc& s) : S(s), arena(1u << 22), lie_missing(false) {
-        c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        ctx_init_host(c, arena.data(), (int)arena.size());
     }
     static int tri_not(int t) { return t == TRI_INDET ? TRI_INDET : (t == TRI_TRUE ? TRI_FALSE : TRI_TRUE); }
     static int tri_and(int a, int b) { if (a == TRI_FALSE || b == TRI_FALSE) return TRI_FALSE; if (a == TRI_TRUE && b == TRI_TRUE) return TRI_TRUE; return TRI_INDET; }

@@ -251,9 +251,15 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     const int as = ys[0].as;
     const Acc acc0 = ys[0].acc;
     int maxp[AB_MAXARGS + 1];
-    for (int j = 0; j < nys; ++j) maxp[j] = 1;
-    for (int i = 0; i < nx; ++i)
-        for (int t = 0; t < x[i].n; ++t) { Key a = tm_key(c, x[i], t); for (int j = 0; j < nys; ++j) { int e = key_get(a, j); if (e > maxp[j]) maxp[j] = e; } }
+    {   // largest exponent of every variable: per-byte maximum of the key words, lanes over terms, then across the lanes
+        const int W = AB_W, lane = c.lane;
+        uint64_t mx[AB_KW]; for (int w = 0; w < AB_KW; ++w) mx[w] = 0;
+        for (int i = 0; i < nx; ++i)
+            for (int t = lane; t < x[i].n; t += W) { Key a = tm_key(c, x[i], t); for (int w = 0; w < AB_KW; ++w) mx[w] = bytes_max(mx[w], a.w[w]); }
+        for (int d = 1; d < W; d <<= 1) for (int w = 0; w < AB_KW; ++w) mx[w] = bytes_max(mx[w], wshfl(mx[w], lane ^ d));
+        Key km; for (int w = 0; w < AB_KW; ++w) km.w[w] = mx[w];
+        for (int j = 0; j < nys; ++j) { const int e = key_get(km, j); maxp[j] = e > 1 ? e : 1; }
+    }
     // handle table
     int tab[AB_MAXARGS + 1];
     int slot = m0;
@@ -310,58 +316,112 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
 }
 
 // _split1(tm,k,true/false) src/taylor_model.cpp:2497-2544. Result at the arena top recorded on entry.
+// The reference computes r = sum_i sum_{j>=i} ary[j] * (+-bin(j,i)) x_k^i as (deg+1)(deg+2)/2 scaled copies added one after
+// another. Stream (i,j) only meets keys whose exponent of x_k is i, and such a key receives its contributions in j order, so
+// the streams are fed to one accumulator bucket by bucket (j), all i of a bucket side by side; each stream's two
+// upward-rounded sums (the scaling gaps of _scal and the coincidence gaps of _add2, both in term order) are recorded as
+// exponent codes and summed by one lane per stream, and the error chain e <- up(up(e + t.e) + te/2) is applied at the end
+// in the reference's (i major, j minor) order.
 AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     AB_SECTION(2);
     const int m0 = c.A.top;
     const int deg = tm_degree(c, tm);
-    TM r = tm_copy(c, tm);
-    for (int i = 0; i < r.n; ++i) {
-        int ak = key_get(tm_key(c, r, i), k);
-        tm_set_val(c, r, i, div_m(c.rnd, tm_val(c, r, i), (double)(1 << ak)));
-    }
-    // buckets by exponent of variable k, with that exponent cleared
-    int boff[AB_MAXPOW], bn[AB_MAXPOW];
-    if (deg + 1 > AB_MAXPOW) { fail(c, ST_ARENA); return r; }
-    for (int b = 0; b <= deg; ++b) {
-        boff[b] = c.A.top; bn[b] = 0;
-        TM bt = tm_begin(c, tm.as, acc_default());
-        for (int i = 0; i < r.n; ++i) {
-            Key a = tm_key(c, r, i);
-            int ak = key_get(a, k);
-            if (ak == b) { key_inc(a, k, -ak); tm_append(c, bt, a, tm_val(c, r, i)); }
-        }
-        bn[b] = bt.n;
-    }
-    const int mr = c.A.top;
+    const int W = AB_W, lane = c.lane;
+    uint64_t* const base = c.A.base;
     TM res = tm_begin(c, tm.as, tm.acc);
-    res.e = r.e;
-    TM st[AB_MAXSTREAMS];
-    int B = 0;
-    for (int i = 0; i <= deg; ++i) {
-        for (int j = i; j <= deg; ++j) {
-            // sf=bin(j,i), sign flipped for the lower half when j-i is odd
-            long long bn_ = 1; for (int q = 1; q <= i; ++q) bn_ = bn_ * (long long)(j - i + q) / (long long)q;
-            double sf = (double)bn_;
-            if (!upper && ((j - i) % 2 == 1)) sf = -sf;
-            if (B == 0) c.A.top = res.off + res.n * AB_TW;
-            // ary[j]*sf with the k-exponent of ary[j] already incremented i times
-            TM t = tm_begin(c, tm.as, acc_default());
-            for (int q = 0; q < bn[j]; ++q) {
-                Key a; for (int w = 0; w < AB_KW; ++w) a.w[w] = aw(c, boff[j] + q * AB_TW + w);
-                key_inc(a, k, i);
-                tm_append(c, t, a, u2d(aw(c, boff[j] + q * AB_TW + AB_KW)));
-            }
-            tm_scal(c, t, sf);
-            st[B++] = t;
-            if (B == AB_MAXSTREAMS || (i == deg && j == deg)) {
-                TM s = tm_add_many(c, res, st, B, tm.acc);   // r+=... for the B (i,j) pairs, in loop order
-                tm_slide(c, s, mr);
-                res = s;
-                B = 0;
+    res.e = tm.e;
+    if (deg + 1 > AB_MAXPOW) { fail(c, ST_ARENA); return res; }
+    // buckets by exponent of variable k, with that exponent cleared and the coefficient divided by 2^exponent
+    int boff[AB_MAXPOW], bn[AB_MAXPOW];
+    const int md = c.rnd;
+    long long want = 0;
+    for (int b = 0; b <= deg; ++b) {
+        boff[b] = c.A.top;
+        TM bt = tm_begin(c, tm.as, acc_default());
+        AB_FILTER_COPY(c, bt, tm, key_get(a, k) == b, key_with(a, k, 0), div_m(md, v, (double)(1 << b)));
+        bn[b] = bt.n;
+        want += (long long)bt.n * (b + 1);
+    }
+    { const long long R = monomial_count(c.binom, deg, tm.as); if (want > R) want = R; }
+    const int mr = c.A.top;
+    // per-stream sums ts[i][j], te[i][j], kept above the buckets
+    const int npair = (deg + 1) * (deg + 1);
+    if (!arena_room(c, mr, npair + 2)) return res;
+    double* const TS = (double*)(base + mr); double* const TE = TS + npair;
+    const int sums_end = mr + 2 * npair;
+    if (sums_end > c.A.peak) c.A.peak = sums_end;
+    AccTab T;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!acc_open(c, T, attempt, sums_end + (int)want * AB_TW, want)) return res;
+        // gap codes of one bucket: one 32-bit cell per (i, term): low half scaling gap, high half coincidence gap
+        uint32_t* G; int gcap;
+        if (c.sm) { G = (uint32_t*)(c.sm + AB_SM_OFF_G16); gcap = AB_SM_G16 / 2; }
+        else {
+            const long long at = (T.val + T.cap) - base; int mx = 1; for (int b = 0; b <= deg; ++b) if (bn[b] > mx) mx = bn[b];
+            if (at + (mx + 1) / 2 + 1 > (long long)c.A.limit) { fail(c, ST_ARENA); return res; }
+            G = (uint32_t*)(base + at); gcap = mx;
+        }
+        bool badgap = false;
+        for (int j = 0; j <= deg && !T.overflow; ++j) {
+            const int nb = bn[j];
+            if (nb == 0) continue;
+            int ib = gcap / nb; if (ib < 1) { fail(c, ST_ARENA); return res; }
+            for (int ia = 0; ia <= j && !T.overflow; ia += ib) {
+                const int ni = (j + 1 - ia < ib) ? (j + 1 - ia) : ib;
+                const int nitems = ni * nb;
+                for (int w0 = 0; w0 < nitems; w0 += W) {
+                    const int w = w0 + lane; const bool act = w < nitems;
+                    Key key = key_zero(); double tv = 0.0, gs = 0.0;
+                    if (act) {
+                        const int ii = w / nb, q = w - ii * nb, i = ia + ii;
+                        const Key a = bkey(base, boff[j] + q * AB_TW); const double v = bval(base, boff[j] + q * AB_TW);
+                        key = key_with(a, k, i);
+                        // sf=bin(j,i), sign flipped for the lower half when j-i is odd; t=ary[j]*sf is _scal(Float)
+                        double sf;
+                        if (j <= 33 && c.binom) sf = (double)binom_at(c.binom, j, (i < j - i) ? i : j - i);
+                        else { long long bn_ = 1; for (int z = 1; z <= i; ++z) bn_ = bn_ * (long long)(j - i + z) / (long long)z; sf = (double)bn_; }
+                        if (!upper && ((j - i) % 2 == 1)) sf = -sf;
+                        if (sf == 1) tv = v;
+                        else if (sf == 2 || sf == 0.5) tv = mul_m(md, v, sf);
+                        else { gs = add_ru(mul_ru(v, sf), mul_ru(v, -sf)); tv = mul_rn(v, sf); }
+                    }
+                    const int slot = acc_slot(T, act, key, lane);
+                    if (T.overflow) break;
+                    if (act) {
+                        const double ga = acc_fold(T, slot, tv);
+                        G[w] = gap_code(gs, &badgap) | (gap_code(ga, &badgap) << 16);
+                    }
+                }
+                wsync();
+                if (T.overflow) break;
+                for (int ii = lane; ii < ni; ii += W) {
+                    double ts = 0.0, te = 0.0;
+                    const uint32_t* row = G + ii * nb;
+                    for (int q = 0; q < nb; ++q) { const uint32_t cd = row[q]; if (cd & 0xFFFFu) ts = add_ru(ts, gap_value(cd & 0xFFFFu)); if (cd >> 16) te = add_ru(te, gap_value(cd >> 16)); }
+                    TS[(ia + ii) * (deg + 1) + j] = ts; TE[(ia + ii) * (deg + 1) + j] = te;
+                }
+                wsync();
             }
         }
+        if (wany(badgap)) fail(c, ST_UNSUPPORTED);
+        if (!T.overflow) break;
+        if (attempt == 1) { fail(c, ST_ARENA); return res; }
     }
-    tm_slide(c, res, m0);
+    // error chain in the reference's stream order; an empty bucket contributes nothing
+    double e = tm.e;
+    for (int i = 0; i <= deg; ++i)
+        for (int j = i; j <= deg; ++j) {
+            if (bn[j] == 0) continue;
+            const double ts = TS[i * (deg + 1) + j], te = TE[i * (deg + 1) + j];
+            e = add_ru(add_ru(e, ts / 2), te / 2);       // t.error() = ts/2 (zero for the exact scalings), then _add2's chain
+        }
+    wsync();
+    res.off = m0;
+    res.n = acc_emit(c, T, tm.as, deg, m0);           // the buckets are no longer needed: the result lands at m0
+    res.e = e;
+    c.A.top = m0 + res.n * AB_TW;
+    arena_mark_peak(c);
+    c.rnd = RN;
     return res;
 }
 
@@ -374,10 +434,7 @@ AB_HDN TM tm_partial_evaluate_one(Ctx& c, const TM& x, int k) {
     for (int b = 0; b <= deg; ++b) {
         boff[b] = c.A.top;
         TM bt = tm_begin(c, x.as - 1, x.acc);
-        for (int i = 0; i < x.n; ++i) {
-            Key a = tm_key(c, x, i);
-            if (key_get(a, k) == b) tm_append(c, bt, key_remove(a, k, x.as), tm_val(c, x, i));
-        }
+        AB_FILTER_COPY(c, bt, x, key_get(a, k) == b, key_remove(a, k, x.as), v);
         bn[b] = bt.n;
     }
     const int mr = c.A.top;

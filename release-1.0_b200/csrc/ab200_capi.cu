@@ -16,30 +16,32 @@ using namespace ab200;
 
 // Builds of the evolution kernel (one translation unit each, inline namespace = variant name). Plain signatures, so
 // that this file, compiled against the AB_KW=1 headers, can call the two-word-key build as well.
-//   kw1   one-word MultiIndex keys (<= 7 set parameters), 255 registers, 8-way merges: lowest latency per cell
-//   r128  one-word keys, 128 registers (16 resident warps per SM), 8-way merges: best for frontiers that fill the device
+//   kw1   one-word MultiIndex keys (<= 7 set parameters): systems with up to 2 state variables
 //   kw2   two-word keys (<= 15 set parameters) for systems with more than 2 state variables
-// AB200_TUNE=<name> forces a one-word build (measurements in profiles/r01_variants.md).
 #define AB_DECL_VARIANT(ns) namespace ab200 { namespace ns { \
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen); \
 int dev_evolve_capacity_v(char* errbuf, int errlen); \
-int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
-                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach, \
+int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
+                        uint64_t* arena, int arena_words, const uint32_t* binom, int* next_cell, double* reach, int32_t* reach_loc, int32_t* n_reach, \
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
-AB_DECL_VARIANT(r128)
 struct EvolveBuild {
     const char* name;
     int (*upload)(const void*, char*, int);
     int (*capacity)(char*, int);
-    int (*launch)(cudaStream_t, int, const int32_t*, const double*, const void*, uint64_t*, int, double*, int32_t*, int32_t*,
+    int (*launch)(cudaStream_t, int, int, const int32_t*, const double*, const void*, uint64_t*, int, const uint32_t*, int*, double*, int32_t*, int32_t*,
                   double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
-static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2), AB_BUILD(r128) };
+static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2) };
 static const int kNumBuilds = (int)(sizeof(kBuilds) / sizeof(kBuilds[0]));
 static const EvolveBuild* find_build(const char* name) { for (int i = 0; i < kNumBuilds; ++i) if (!strcmp(kBuilds[i].name, name)) return &kBuilds[i]; return 0; }
+
+// The system tapes live in per-device __constant__ memory; the context that uploaded last owns them. A context that finds
+// another owner re-uploads before it launches, so several contexts can share a device.
+static const void* g_sys_owner[64] = {0};
+static unsigned long long g_sys_generation = 0;
 
 static_assert(AB200_MAX_DIM == AB_MAXN, "header / kernel dimension mismatch");
 
@@ -76,6 +78,9 @@ struct ab200_ctx {
     DevBuf<uint64_t> d_arena, d_table, d_keys, d_tmp;
     DevBuf<unsigned> d_hist;
     DevBuf<unsigned long long> d_counters;
+    DevBuf<uint32_t> d_binom;
+    DevBuf<int> d_next;
+    unsigned long long sys_generation;     // bumped by every change of the system description or tuning
     cudaEvent_t ev0, ev1;
 };
 
@@ -84,7 +89,7 @@ struct ab200_ctx {
 
 extern "C" void ab200_default_settings(ab200_settings* s) {
     s->temporal_order = 6; s->spacial_order = 6; s->sweep_threshold = 1e-12; s->maximum_enclosure_widths_ratio = 5.0;
-    s->max_boxes = 192; s->arena_words = 16384; s->hash_log2 = 24; s->batch_cells = 1 << 17; s->ttl_seconds = 0.0; s->semantics = 0; s->reserved = 0;
+    s->max_boxes = 192; s->arena_words = 32768; s->hash_log2 = 24; s->batch_cells = 1 << 17; s->ttl_seconds = 0.0; s->semantics = 0; s->reserved = 0;
 }
 
 extern "C" int ab200_ctx_create(ab200_ctx** out, int device) {
@@ -98,12 +103,17 @@ extern "C" int ab200_ctx_create(ab200_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AB200_E_CUDA;
     if (prop.major != 10) return AB200_E_CUDA;    // kernels are built for sm_100a only
     ab200_ctx* ctx = new ab200_ctx();
-    ctx->device = device; ctx->have_system = false; ctx->have_layout = false; ctx->accuracy = 0;
+    ctx->device = device; ctx->have_system = false; ctx->have_layout = false; ctx->accuracy = 0; ctx->sys_generation = 0;
     ab200_default_settings(&ctx->settings);
     if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return AB200_E_CUDA; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     char eb[256];
     if (dev_set_stack(32 * 1024, eb, sizeof(eb)) != 0) { delete ctx; return AB200_E_CUDA; }
+    {   // binomial table for monomial ranks (ab200_tm.cuh key_rank) and the work counter of the persistent grid
+        std::vector<uint32_t> bt(AB_BINOM_N * AB_BINOM_K); binom_fill(bt.data());
+        if (ctx->d_binom.ensure(bt.size()) != cudaSuccess || ctx->d_next.ensure(4) != cudaSuccess ||
+            cudaMemcpy(ctx->d_binom.p, bt.data(), bt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { delete ctx; return AB200_E_CUDA; }
+    }
     *out = ctx;
     return AB200_OK;
 }
@@ -112,21 +122,30 @@ extern "C" void ab200_ctx_destroy(ab200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_loc.release(); ctx->d_nreach.release(); ctx->d_nfin.release(); ctx->d_status.release(); ctx->d_steps.release(); ctx->d_peak.release();
     ctx->d_rloc.release(); ctx->d_floc.release(); ctx->d_box.release(); ctx->d_reach.release(); ctx->d_fin.release();
-    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release();
+    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release();
+    if (ctx->device >= 0 && ctx->device < 64 && g_sys_owner[ctx->device] == ctx) g_sys_owner[ctx->device] = 0;
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 extern "C" const char* ab200_last_error(const ab200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// Make this context's tapes and tuning the ones in the device's constant memory.
+static int upload_system(ab200_ctx* ctx, bool changed) {
+    CTX_CK(cudaSetDevice(ctx->device));
+    if (changed) ctx->sys_generation = ++g_sys_generation;
+    if (!changed && ctx->device < 64 && g_sys_owner[ctx->device] == ctx) return AB200_OK;
+    CTX_CK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
+    if (ctx->device < 64) g_sys_owner[ctx->device] = ctx;
+    return AB200_OK;
+}
 extern "C" int ab200_set_system_text(ab200_ctx* ctx, const char* text) {
     if (!ctx || !text) return AB200_E_ARGUMENT;
     std::string e = parse_system(text, ctx->sys);
     if (!e.empty()) { ctx->err = "system description: " + e; return AB200_E_ARGUMENT; }
     ctx->have_system = true;
-    CTX_CK(cudaSetDevice(ctx->device));
-    for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
-    return AB200_OK;
+    return upload_system(ctx, true);
 }
 extern "C" int ab200_system_check(const char* text, int32_t* n_locations, int32_t* n_events, int32_t* n_ops, char* err, int32_t errlen) {
     if (err && errlen > 0) err[0] = 0;
@@ -173,9 +192,7 @@ extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max
     LocDesc& L = ctx->sys.desc.loc[loc];
     L.max_step = max_step;
     for (int i = 0; i < L.n; ++i) { L.ref_width[i] = ref_widths[i]; L.grid_origin[i] = grid_origin[i]; L.grid_length[i] = grid_lengths[i]; }
-    CTX_CK(cudaSetDevice(ctx->device));
-    for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
-    return AB200_OK;
+    return upload_system(ctx, true);
 }
 // Key window: equal share of the 64 bits after the location field, centred on the grid origin.
 extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
@@ -215,7 +232,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
     if (!ctx || !ctx->have_system) return AB200_E_ARGUMENT;
     const bool want_keys = out.reach_keys || out.fin_keys;
     if (want_keys && !ctx->have_layout) { ctx->err = "ab200_set_accuracy must be called first"; return AB200_E_ARGUMENT; }
-    CTX_CK(cudaSetDevice(ctx->device));
+    { int rc_ = upload_system(ctx, false); if (rc_ != AB200_OK) return rc_; }
     const ab200_settings& S = ctx->settings;
     const int stride = AB200_BOX_STRIDE;
     ab200_status stl; memset(&stl, 0, sizeof(stl)); stl.cell = -1;
@@ -244,25 +261,22 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(ctx->d_nreach.ensure(nb)); CTX_CK(ctx->d_nfin.ensure(nb)); CTX_CK(ctx->d_status.ensure(nb)); CTX_CK(ctx->d_steps.ensure(nb)); CTX_CK(ctx->d_peak.ensure(nb));
         CTX_CK(ctx->d_reach.ensure((size_t)nb * S.max_boxes * stride)); CTX_CK(ctx->d_fin.ensure((size_t)nb * S.max_boxes * stride));
         CTX_CK(ctx->d_rloc.ensure((size_t)nb * S.max_boxes)); CTX_CK(ctx->d_floc.ensure((size_t)nb * S.max_boxes));
-        // Build selection: set models have up to max(2n+1,3n) parameters -- one-word keys hold 7, two-word keys 15. Of the
-        // one-word builds, the 255-register one has the lowest latency per cell and wins while the frontier does not fill
-        // the device; beyond that the 128-register build keeps twice as many cells in flight (profiles/r01_variants.md).
+        // Build selection: set models have up to max(2n+1,3n) parameters -- one-word keys hold 7, two-word keys 15.
+        // AB200_TUNE=kw2 forces the two-word build for a system that would fit one word (test hook).
         const bool wide = ctx->sys.desc.loc[0].n > 2;
         const EvolveBuild* build = find_build(wide ? "kw2" : "kw1");
-        const char* tune = getenv("AB200_TUNE");
-        if (!wide) {
-            if (tune && find_build(tune) && strcmp(tune, "kw2")) build = find_build(tune);
-            else if (!tune) {
-                int cap; DEV_CK((cap = build->capacity(eb_, sizeof(eb_))) < 0);
-                if (nb > 2 * cap) build = find_build("r128");
-            }
+        if (const char* tune = getenv("AB200_TUNE")) {
+            if (!find_build(tune) || (wide && strcmp(tune, "kw2"))) { ctx->err = std::string("AB200_TUNE: no such build for this system: ") + tune; return AB200_E_ARGUMENT; }
+            build = find_build(tune);
         }
-        const int nwarps = (nb + 31) / 32;
-        CTX_CK(ctx->d_arena.ensure((size_t)nwarps * 32 * S.arena_words));
+        int slots; DEV_CK((slots = build->capacity(eb_, sizeof(eb_))) < 0);
+        if (slots > nb) slots = nb;
+        CTX_CK(ctx->d_arena.ensure((size_t)slots * S.arena_words));
+        CTX_CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_loc.p, loc + b0, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_box.p, boxes + b0 * stride, (size_t)nb * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        DEV_CK(build->launch(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words,
+        DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, ctx->d_binom.p, ctx->d_next.p,
                              ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
                              ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
         stl.launches += 1;
@@ -398,7 +412,7 @@ extern "C" void ab200_boxlist_free(ab200_boxlist* bl) { delete bl; }
 extern "C" int ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
                                  double* h_out, double* bounds_out, int32_t* status_out) {
     if (!ctx || !ctx->have_system || !loc || !boxes || !h_out || !bounds_out) return AB200_E_ARGUMENT;
-    CTX_CK(cudaSetDevice(ctx->device));
+    { int rc_ = upload_system(ctx, false); if (rc_ != AB200_OK) return rc_; }
     const int stride = AB200_BOX_STRIDE;
     DevBuf<double> d_h, d_b;
     CTX_CK(ctx->d_loc.ensure(n)); CTX_CK(ctx->d_box.ensure(n * stride)); CTX_CK(ctx->d_status.ensure(n));

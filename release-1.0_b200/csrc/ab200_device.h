@@ -5,17 +5,15 @@
 #include "ab200_evolve.cuh"
 #include "ab200_grid.cuh"
 
-#ifndef AB_EVOLVE_BLOCK
-#define AB_EVOLVE_BLOCK 64
-#endif
 
 namespace ab200 { inline namespace AB_VARIANT {
 int dev_upload_system(const SystemDesc* s, char* errbuf, int errlen);
 // variant-independent signatures (used to reach the AB_KW=2 build from host code compiled against the AB_KW=1 headers)
 int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen);
 int dev_evolve_capacity_v(char* errbuf, int errlen);
-int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
-                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
+int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
+                        uint64_t* arena, int arena_words, const uint32_t* binom, int* next_cell,
+                        double* reach, int32_t* reach_loc, int32_t* n_reach,
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
                         char* errbuf, int errlen);
 int dev_set_stack(size_t bytes, char* errbuf, int errlen);

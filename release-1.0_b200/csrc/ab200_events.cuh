@@ -9,12 +9,6 @@ namespace ab200 { inline namespace AB_VARIANT {
 
 struct WorkingSet;
 
-// Pending working sets of one cell (std::list<EvolutionData> in the reference, popped from the front). Jumps inside
-// the evolver are not built yet, so the queue never holds more than the current set.
-struct WsQueue { int count; };
-AB_HD void wsq_init(WsQueue& q) { q.count = 0; }
-AB_HD bool wsq_pop(Ctx& c, WsQueue& q, WorkingSet& ws) { (void)c; (void)q; (void)ws; return false; }
-
 struct BlockingInfo {
     TM time;           // blocking_time_model (scaled to [0,1])
     bool finishing;    // blocking_events == {finishing_event}
@@ -237,8 +231,8 @@ AB_HDN int tm_less(Ctx& c, const TM& time, const TM& blocking) {
 
 // _compute_blocking_info (src/hybrid_evolver-image.cpp:1085-1127) with
 // compute_eventBlockingTimes_and_nonTransverseEvents (:770-843) and compute_blockingTime_and_relatedEvents (:846-883).
-// Non-transverse (degenerate) crossings, which the reference handles by bisection on the touching time
-// (src/taylor_calculus.cpp:524-578), are not built yet and report UNSUPPORTED.
+// Non-transverse (degenerate) crossings are handled by bisection on the touching time, as the reference does
+// (src/taylor_calculus.cpp:524-578).
 AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L, const TM* fset, int n, int p,
                                   const TM& tstep, Acc spacial, BlockingInfo& B) {
     (void)spacial;
@@ -383,7 +377,7 @@ AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& 
     TM init[AB_MAXN], fin[AB_MAXN];
     for (int i = 0; i < n; ++i) {                                   // partial_evaluate(models,p,0.0): terms free of the time variable
         TM r = tm_begin(c, p, fset[i].acc);
-        for (int t = 0; t < fset[i].n; ++t) { Key a = tm_key(c, fset[i], t); if (key_get(a, p) == 0) tm_append(c, r, key_remove(a, p, p + 1), tm_val(c, fset[i], t)); }
+        AB_FILTER_COPY(c, r, fset[i], key_get(a, p) == 0, key_remove(a, p, p + 1), v);
         r.e = fset[i].e;
         init[i] = r;
     }

@@ -1,45 +1,35 @@
-// ab200_tm.cuh -- TaylorModel primitives on a per-cell scratch arena.
+// ab200_tm.cuh -- TaylorModel primitives, one warp per frontier cell.
 //
 // A TaylorModel is a sparse polynomial on [-1,1]^as with a uniform error bound (reference:
-// include/taylor_model.h:170-190, include/expansion.h, include/multi_index.h). Here a model is a handle
-// {offset,count,as,error,accuracy} into a per-cell arena of 64-bit words; terms are [key words | coefficient]
-// records kept in the reference's graded order (include/multi_index.h:346-358).
+// include/taylor_model.h:170-190, include/expansion.h, include/multi_index.h). Here a model is a warp-uniform handle
+// {offset,count,as,error,accuracy} into the cell's scratch arena of 64-bit words (global memory; a few thousand cells
+// are in flight, so the arenas stay resident in L2); terms are [key words | coefficient] records kept in the
+// reference's graded order (include/multi_index.h:346-358). Loops over terms are strided over the lanes of the warp.
+//
+// Sums of models -- the x-term streams of a product (_mul4), the batched additions of _compose2 and _split1, _add2,
+// intersection -- go through ONE mechanism, a sparse accumulator staged in shared memory (AccTab): a structure-of-arrays
+// list of (MultiIndex key, coefficient) plus a hash index from key to list position. A stream is added by all lanes at
+// once (the keys of one stream are distinct, so no two lanes touch the same entry); streams are added one after another,
+// which is the reference's fold order for every coefficient. The accumulator is finally written to the arena in key
+// order. This replaces the reference's re-merge of the whole accumulator per x-term (src/taylor_model.cpp:772-804).
+//
+// Error bounds: every rounding gap up(u+ml) of a coincident term is either 0 or a power of two (u and -ml are equal or
+// adjacent doubles), so the gaps of a product are recorded as 16-bit exponent codes per (x-term, y-term) and summed
+// afterwards by one lane per x-term, upward and in y order -- exactly the reference's te of each _add2 -- while the lanes
+// run side by side. Discarded products are flagged in the same code and their truncation error |x||y| is recomputed.
 //
 // MultiIndex packing: AB_KW 64-bit words per key. Word 0 = degree byte (bits 56..63) followed by the exponents of
-// variables 0..6, most significant first; word 1 = exponents of variables 7..14. Adding two keys is a plain
-// integer add per word; the reference order is "degree ascending, then the key whose first differing exponent is
-// LARGER comes first", i.e. ascending (w0 ^ 0x00FF..FF) then descending w1.
+// variables 0..6, most significant first; word 1 = exponents of variables 7..14. Adding two keys is a plain integer add
+// per word; the reference order is "degree ascending, then the key whose first differing exponent is LARGER comes
+// first", i.e. ascending (w0 ^ 0x00FF..FF) then descending w1.
 //
-// Arena layout in HBM: one arena per cell, word i of cell c lives at base[(i * AB_STRIDE)] with base already offset
-// by the lane; with AB_STRIDE=32 the 32 cells of a warp interleave word-by-word so that lanes walking their models
-// in lock step touch one 256-byte line per access.
-//
-// Every accumulator keeps the reference's association order (error sums round upward term by term), so results
-// are bit-identical to the CPU library; see DESIGN.md "Numerical contract".
+// Every accumulator keeps the reference's association order, so results are bit-identical to the CPU library; see
+// DESIGN.md "Numerical contract".
 #pragma once
-#include "ab200_fp.cuh"
+#include "ab200_warp.cuh"
 
 #ifndef AB_KW
 #define AB_KW 1
-#endif
-#ifndef AB_STRIDE
-#if defined(__CUDA_ARCH__)
-#define AB_STRIDE 32
-#else
-#define AB_STRIDE 1
-#endif
-#endif
-
-// AB_CHUNK consecutive words of one lane are kept together (AB_CHUNK=4: one 32-byte sector, 16: one 128-byte line)
-// and the chunks of the 32 lanes interleave. AB_CHUNK=1 is the plain word-by-word interleave. A larger chunk keeps a
-// fetched sector useful to the lane that fetched it when the lanes of a warp have drifted apart in their models.
-#ifndef AB_CHUNK
-#define AB_CHUNK 1
-#endif
-#if AB_CHUNK == 1 || AB_STRIDE == 1
-#define AB_WORD_INDEX(i) ((size_t)(i) * AB_STRIDE)
-#else
-#define AB_WORD_INDEX(i) ((size_t)((i) / AB_CHUNK) * (AB_STRIDE * AB_CHUNK) + (size_t)((i) % AB_CHUNK))
 #endif
 
 namespace ab200 { inline namespace AB_VARIANT {
@@ -68,6 +58,15 @@ AB_HD void key_inc(Key& k, int j, int d) {
     else { k.w[1] += (uint64_t)((int64_t)d) << (8 * (14 - j)); k.w[0] += (uint64_t)((int64_t)d) << 56; }
 #endif
 }
+// the key with exponent j set to e (e >= 0)
+AB_HD Key key_with(const Key& a, int j, int e) { Key r = a; key_inc(r, j, e - key_get(a, j)); return r; }
+// per-byte maximum of two packed words (exponents are below 128, so the top bit of every byte is free)
+AB_HD uint64_t bytes_max(uint64_t x, uint64_t y) {
+    const uint64_t H = 0x8080808080808080ull;
+    const uint64_t ge = (((x | H) - y) & H) >> 7;      // 1 in every byte where x >= y
+    const uint64_t m = ge * 0xFFull;
+    return (x & m) | (y & ~m);
+}
 AB_HD Key key_unit(int j) { Key k = key_zero(); key_inc(k, j, 1); return k; }
 AB_HD Key key_add(const Key& a, const Key& b) { Key r; for (int i = 0; i < AB_KW; ++i) r.w[i] = a.w[i] + b.w[i]; return r; }
 AB_HD bool key_eq(const Key& a, const Key& b) {
@@ -95,52 +94,6 @@ AB_HD Key key_remove(const Key& a, int k, int as) {
     return r;
 }
 
-// Sortable form of a key for the merge loops: unsigned comparison of (s, then t) is the graded order of key_less, and
-// the all-ones value, which no monomial maps to (it would need degree 255 with all exponents 0), marks an exhausted
-// stream, so that "smallest live head" is a plain running minimum.
-struct SKey {
-    uint64_t s;
-#if AB_KW > 1
-    uint64_t t;
-#endif
-};
-AB_HD SKey skey(const Key& k) {
-    SKey r; r.s = k.w[0] ^ 0x00FFFFFFFFFFFFFFull;
-#if AB_KW > 1
-    r.t = ~k.w[1];
-#endif
-    return r;
-}
-AB_HD SKey skey_dead() {
-    SKey r; r.s = ~0ull;
-#if AB_KW > 1
-    r.t = ~0ull;
-#endif
-    return r;
-}
-AB_HD bool skey_is_dead(const SKey& a) { return a.s == ~0ull; }
-AB_HD Key skey_key(const SKey& a) {
-    Key k; k.w[0] = a.s ^ 0x00FFFFFFFFFFFFFFull;
-#if AB_KW > 1
-    k.w[1] = ~a.t;
-#endif
-    return k;
-}
-AB_HD bool skey_less(const SKey& a, const SKey& b) {
-#if AB_KW > 1
-    return a.s < b.s || (a.s == b.s && a.t < b.t);
-#else
-    return a.s < b.s;
-#endif
-}
-AB_HD bool skey_eq(const SKey& a, const SKey& b) {
-#if AB_KW > 1
-    return a.s == b.s && a.t == b.t;
-#else
-    return a.s == b.s;
-#endif
-}
-
 struct Acc {          // TaylorModel::Accuracy (include/taylor_model.h:178-190)
     double sweep;
     int maxdeg;
@@ -149,7 +102,7 @@ AB_HD Acc acc_default() { Acc a; a.sweep = 1e-18; a.maxdeg = 16; return a; }   /
 AB_HD bool acc_discard(const Acc& a, const Key& k, double v) { return dabs(v) < a.sweep || key_deg(k) > a.maxdeg; }
 
 struct Arena {
-    uint64_t* base;   // already offset by lane; word i at base[i*AB_STRIDE]
+    uint64_t* base;   // the cell's scratch words (global memory)
     int top;
     int limit;
     int peak;
@@ -159,30 +112,42 @@ struct Ctx {
     Arena A;
     int rnd;       // ambient rounding mode left behind by the last routine (mirrors MXCSR in the reference)
     int status;    // sticky first error
+    int lane;      // this thread's lane in the warp
+    uint64_t* sm;  // the warp's shared-memory staging area (AB_SM_WORDS words); null in host-side callers
+    const uint32_t* binom;   // binomial table for monomial ranks (binom_fill)
 };
+#define AB_BINOM_N 64
+#define AB_BINOM_K 24
+// C(n,k) for n < AB_BINOM_N, k < AB_BINOM_K, saturated; filled on the host and handed to the kernels in global memory.
+inline void binom_fill(uint32_t* t) {
+    for (int n = 0; n < AB_BINOM_N; ++n) for (int k = 0; k < AB_BINOM_K; ++k) {
+        unsigned long long v = (k == 0) ? 1 : (n == 0 ? 0 : (unsigned long long)t[(n - 1) * AB_BINOM_K + k - 1] + t[(n - 1) * AB_BINOM_K + k]);
+        t[n * AB_BINOM_K + k] = v > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)v; }
+}
+struct BinomTab { uint32_t t[AB_BINOM_N * AB_BINOM_K]; BinomTab() { binom_fill(t); } };
+inline const uint32_t* binom_host() { static BinomTab b; return b.t; }
+AB_HD void ctx_init(Ctx& c, uint64_t* arena, int limit, uint64_t* sm, const uint32_t* binom) {
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom;
+}
+// host-side callers (no warp, no shared area)
+inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host();
+}
 
-#ifdef AB_COUNT_ACCESS
-extern long long g_aw_count;
-extern long long g_sec[16];
-struct SecTimer { int id; long long start; SecTimer(int i) : id(i), start(g_aw_count) { } ~SecTimer() { g_sec[id] += g_aw_count - start; } };
-#define AB_SECTION(id) SecTimer sec_timer_##id(id)
-AB_HD uint64_t& aw(Ctx& c, int i) { ++g_aw_count; return c.A.base[AB_WORD_INDEX(i)]; }
-#else
-#define AB_SECTION(id)
-AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[AB_WORD_INDEX(i)]; }
-#endif
+AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[i]; }
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 #ifdef AB_MUL_HIST
 extern long long g_calls[16], g_words[16];   // development counters (tests/tools/hostdbg.cpp)
-#define AB_CALL(id, w) do { g_calls[id]++; g_words[id] += (w); } while (0)
+#define AB_CALL(id, w) do { if (c.lane == 0) { g_calls[id]++; g_words[id] += (w); } } while (0)
 // Algorithmic FP64 operations of the REFERENCE algorithm by the per-primitive formulas of SURVEY.md 8(d), evaluated on
 // the actual term counts (host development builds only; the figure bench.py quotes comes from these counters).
 extern double g_flops;
-#define AB_FLOPS(n) do { g_flops += (double)(n); } while (0)
+#define AB_FLOPS(n) do { if (c.lane == 0) g_flops += (double)(n); } while (0)
 #else
 #define AB_CALL(id, w)
 #define AB_FLOPS(n)
 #endif
+#define AB_SECTION(id)
 
 struct TM {
     int off;      // first word in the arena
@@ -192,86 +157,64 @@ struct TM {
     Acc acc;
 };
 
-AB_HD Key tm_key(Ctx& c, const TM& x, int i) { Key k; for (int j = 0; j < AB_KW; ++j) k.w[j] = aw(c, x.off + i * AB_TW + j); return k; }
-AB_HD double tm_val(Ctx& c, const TM& x, int i) { return u2d(aw(c, x.off + i * AB_TW + AB_KW)); }
-AB_HD void tm_set_val(Ctx& c, const TM& x, int i, double v) { aw(c, x.off + i * AB_TW + AB_KW) = d2u(v); }
-AB_HD void tm_set_key(Ctx& c, const TM& x, int i, const Key& k) { for (int j = 0; j < AB_KW; ++j) aw(c, x.off + i * AB_TW + j) = k.w[j]; }
+AB_HD Key bkey(const uint64_t* base, int w) { Key k; for (int j = 0; j < AB_KW; ++j) k.w[j] = base[w + j]; return k; }
+AB_HD double bval(const uint64_t* base, int w) { return u2d(base[w + AB_KW]); }
+AB_HD void bput(uint64_t* base, int w, const Key& k, double v) { for (int j = 0; j < AB_KW; ++j) base[w + j] = k.w[j]; base[w + AB_KW] = d2u(v); }
+
+AB_HD Key tm_key(Ctx& c, const TM& x, int i) { return bkey(c.A.base, x.off + i * AB_TW); }
+AB_HD double tm_val(Ctx& c, const TM& x, int i) { return bval(c.A.base, x.off + i * AB_TW); }
+AB_HD void tm_set_val(Ctx& c, const TM& x, int i, double v) { c.A.base[x.off + i * AB_TW + AB_KW] = d2u(v); }
+AB_HD void tm_set_key(Ctx& c, const TM& x, int i, const Key& k) { for (int j = 0; j < AB_KW; ++j) c.A.base[x.off + i * AB_TW + j] = k.w[j]; }
 AB_HD int tm_end(const TM& x) { return x.off + x.n * AB_TW; }
 
-// The hot loops below work on copies of the context and handle fields (arena base, limit, offsets, counts, accuracy)
-// held in locals: through `Ctx&` / `const TM&` the compiler reloads them from the stack around every scratch access.
-AB_HD Key bkey(const uint64_t* base, int w) { Key k; for (int j = 0; j < AB_KW; ++j) k.w[j] = base[AB_WORD_INDEX(w + j)]; return k; }
-AB_HD double bval(const uint64_t* base, int w) { return u2d(base[AB_WORD_INDEX(w + AB_KW)]); }
-// Streaming variants for the accumulator of a product: it is written once and read once per batch, whereas the factor y is
-// re-read by every stream of every batch, so the accumulator is marked evict-first to leave the caches to y.
-AB_HD Key bkey_cs(const uint64_t* base, int w) {
-    Key k;
-#if defined(__CUDA_ARCH__) && defined(AB_STREAMING_ACC)
-    for (int j = 0; j < AB_KW; ++j) k.w[j] = __ldcs((const unsigned long long*)&base[AB_WORD_INDEX(w + j)]);
-#else
-    for (int j = 0; j < AB_KW; ++j) k.w[j] = base[AB_WORD_INDEX(w + j)];
-#endif
-    return k;
+AB_HD void arena_mark_peak(Ctx& c) { if (c.A.top > c.A.peak) c.A.peak = c.A.top; }
+// Reserve room for `terms` more terms above `from`; false (and ST_ARENA) if the arena cannot hold them.
+AB_HD bool arena_room(Ctx& c, int from, int terms) {
+    if ((long long)from + (long long)terms * AB_TW > (long long)c.A.limit) { fail(c, ST_ARENA); return false; }
+    return true;
 }
-AB_HD double bval_cs(const uint64_t* base, int w) {
-#if defined(__CUDA_ARCH__) && defined(AB_STREAMING_ACC)
-    return u2d(__ldcs((const unsigned long long*)&base[AB_WORD_INDEX(w + AB_KW)]));
-#else
-    return u2d(base[AB_WORD_INDEX(w + AB_KW)]);
-#endif
-}
-AB_HD void bput_cs(uint64_t* base, int w, const Key& k, double v) {
-#if defined(__CUDA_ARCH__) && defined(AB_STREAMING_ACC)
-    for (int j = 0; j < AB_KW; ++j) __stcs((unsigned long long*)&base[AB_WORD_INDEX(w + j)], (unsigned long long)k.w[j]);
-    __stcs((unsigned long long*)&base[AB_WORD_INDEX(w + AB_KW)], (unsigned long long)d2u(v));
-#else
-    for (int j = 0; j < AB_KW; ++j) base[AB_WORD_INDEX(w + j)] = k.w[j];
-    base[AB_WORD_INDEX(w + AB_KW)] = d2u(v);
-#endif
-}
-AB_HD void bput(uint64_t* base, int w, const Key& k, double v) { for (int j = 0; j < AB_KW; ++j) base[AB_WORD_INDEX(w + j)] = k.w[j]; base[AB_WORD_INDEX(w + AB_KW)] = d2u(v); }
 
 // Begin a model at the arena top; append() grows it. Only the most recently begun model may be appended to.
+// tm_append is a warp-uniform operation: every lane writes the same term (one transaction), so the term is visible to
+// each lane without a barrier.
 AB_HD TM tm_begin(Ctx& c, int as, Acc acc) { TM r; r.off = c.A.top; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc; return r; }
 AB_HD void tm_append(Ctx& c, TM& r, const Key& k, double v) {
     int o = r.off + r.n * AB_TW;
     if (o + AB_TW > c.A.limit) { fail(c, ST_ARENA); return; }
-    for (int j = 0; j < AB_KW; ++j) aw(c, o + j) = k.w[j];
-    aw(c, o + AB_KW) = d2u(v);
+    bput(c.A.base, o, k, v);
     r.n++;
     c.A.top = o + AB_TW;
-    if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+    arena_mark_peak(c);
 }
-// append() for the merge loops: the high-water mark is not maintained per term; the caller calls arena_mark_peak()
-// once the model is complete (the top only grows while a model is being appended to).
-AB_HD void tm_append_quick(Ctx& c, TM& r, const Key& k, double v) {
-    int o = r.off + r.n * AB_TW;
-    if (o + AB_TW > c.A.limit) { fail(c, ST_ARENA); return; }
-    for (int j = 0; j < AB_KW; ++j) aw(c, o + j) = k.w[j];
-    aw(c, o + AB_KW) = d2u(v);
-    r.n++;
-    c.A.top = o + AB_TW;
-}
-AB_HD void arena_mark_peak(Ctx& c) { if (c.A.top > c.A.peak) c.A.peak = c.A.top; }
 // Move model x (anywhere at or above dst) down to word offset dst and set the arena top just past it.
-AB_HD void tm_slide(Ctx& c, TM& x, int dst) { AB_CALL(2, x.off == dst ? 0 : x.n);
+AB_HDN void tm_slide(Ctx& c, TM& x, int dst) { AB_CALL(2, x.off == dst ? 0 : x.n);
     if (x.off != dst) {
-        const int nw = x.n * AB_TW, src = x.off;
+        wsync();
+        const int nw = x.n * AB_TW, src = x.off, W = AB_W, lane = c.lane;
         uint64_t* const base = c.A.base;
-        for (int i = 0; i < nw; ++i) base[AB_WORD_INDEX(dst + i)] = base[AB_WORD_INDEX(src + i)];
+        if (src - dst >= nw) { for (int i = lane; i < nw; i += W) base[dst + i] = base[src + i]; }
+        else for (int i0 = 0; i0 < nw; i0 += W) {      // overlapping: a chunk is read by all lanes before it is written
+            const int i = i0 + lane; uint64_t v = 0;
+            if (i < nw) v = base[src + i];
+            wsync();
+            if (i < nw) base[dst + i] = v;
+        }
+        wsync();
         x.off = dst;
     }
     c.A.top = dst + x.n * AB_TW;
 }
-AB_HD TM tm_copy(Ctx& c, const TM& x) { AB_CALL(3, x.n);
+AB_HDN TM tm_copy(Ctx& c, const TM& x) { AB_CALL(3, x.n);
+    wsync();
     TM r = tm_begin(c, x.as, x.acc);
-    int nw = x.n * AB_TW;
-    if (r.off + nw > c.A.limit) { fail(c, ST_ARENA); return r; }
-    { uint64_t* const base = c.A.base; const int dst = r.off, src = x.off;
-      for (int i = 0; i < nw; ++i) base[AB_WORD_INDEX(dst + i)] = base[AB_WORD_INDEX(src + i)]; }
+    const int nw = x.n * AB_TW;
+    if (!arena_room(c, r.off, x.n)) return r;
+    { uint64_t* const base = c.A.base; const int dst = r.off, src = x.off, W = AB_W;
+      for (int i = c.lane; i < nw; i += W) base[dst + i] = base[src + i]; }
+    wsync();
     r.n = x.n; r.e = x.e;
     c.A.top = r.off + nw;
-    if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+    arena_mark_peak(c);
     return r;
 }
 AB_HD TM tm_zero(Ctx& c, int as, Acc acc) { return tm_begin(c, as, acc); }
@@ -283,54 +226,76 @@ AB_HD int tm_degree(Ctx& c, const TM& x) { return x.n == 0 ? 0 : key_deg(tm_key(
 AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_FLOPS(4 * r.n + 3); AB_CALL(4, r.n);
     if (s == 0) { r.n = 0; r.e = 0; return; }     // (arena words stay allocated; harmless)
     if (s == 1) return;
+    const int W = AB_W, lane = c.lane, n = r.n;
+    wsync();
     if (s == 2 || s == 0.5) {
-        for (int i = 0; i < r.n; ++i) tm_set_val(c, r, i, mul_m(c.rnd, tm_val(c, r, i), s));
+        const int m = c.rnd;
+        for (int i = lane; i < n; i += W) tm_set_val(c, r, i, mul_m(m, tm_val(c, r, i), s));
+        wsync();
         r.e = mul_m(c.rnd, r.e, dabs(s));
         return;
     }
-    double te = 0, ms = -s;
-    for (int i = 0; i < r.n; ++i) {
-        double rv = tm_val(c, r, i);
-        double u = mul_ru(rv, s), ml = mul_ru(rv, ms);
-        te = add_ru(te, add_ru(u, ml));
+    double te = 0; const double ms = -s;
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + lane; double g = 0.0;
+        if (i < n) {
+            const double rv = tm_val(c, r, i);
+            g = add_ru(mul_ru(rv, s), mul_ru(rv, ms));
+            tm_set_val(c, r, i, mul_rn(rv, s));
+        }
+        te = chain_ru(te, g, (n - i0 < W) ? n - i0 : W);
     }
+    wsync();
     r.e = mul_ru(r.e, dabs(s));
     r.e = add_ru(r.e, te / 2);
-    for (int i = 0; i < r.n; ++i) tm_set_val(c, r, i, mul_rn(tm_val(c, r, i), s));
     c.rnd = RN;
 }
 // _scal(TaylorModel&, Interval) src/taylor_model.cpp:276-314
 AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_FLOPS(5 * r.n + 4); AB_CALL(5, r.n);
-    double te = 0, cu = s.u, mcl = -s.l;
-    for (int i = 0; i < r.n; ++i) {
-        double rv = tm_val(c, r, i), u, ml;
-        if (rv >= 0) { u = mul_ru(rv, cu); ml = mul_ru(rv, mcl); }
-        else { double mrv = -rv; u = mul_ru(mrv, mcl); ml = mul_ru(mrv, cu); }
-        te = add_ru(te, add_ru(u, ml));
+    const int W = AB_W, lane = c.lane, n = r.n;
+    wsync();
+    double te = 0; const double cu = s.u, mcl = -s.l;
+    const double m = add_rn(s.u, s.l) / 2;
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + lane; double g = 0.0;
+        if (i < n) {
+            const double rv = tm_val(c, r, i); double u, ml;
+            if (rv >= 0) { u = mul_ru(rv, cu); ml = mul_ru(rv, mcl); }
+            else { double mrv = -rv; u = mul_ru(mrv, mcl); ml = mul_ru(mrv, cu); }
+            g = add_ru(u, ml);
+            tm_set_val(c, r, i, mul_rn(rv, m));
+        }
+        te = chain_ru(te, g, (n - i0 < W) ? n - i0 : W);
     }
+    wsync();
     r.e = mul_ru(r.e, ivl_mag(s));
     r.e = add_ru(r.e, te / 2);
-    double m = add_rn(s.u, s.l) / 2;
-    for (int i = 0; i < r.n; ++i) tm_set_val(c, r, i, mul_rn(tm_val(c, r, i), m));
     c.rnd = RN;
 }
 // Insert a constant term in front of a model that is the LAST thing on the arena.
-AB_HD void tm_prepend_top(Ctx& c, TM& r, double v) {
-    int nw = r.n * AB_TW;
-    if (r.off + nw + AB_TW > c.A.limit) { fail(c, ST_ARENA); return; }
-    for (int i = nw - 1; i >= 0; --i) aw(c, r.off + AB_TW + i) = aw(c, r.off + i);
-    Key z = key_zero();
-    for (int j = 0; j < AB_KW; ++j) aw(c, r.off + j) = z.w[j];
-    aw(c, r.off + AB_KW) = d2u(v);
+AB_HDN void tm_prepend_top(Ctx& c, TM& r, double v) {
+    const int nw = r.n * AB_TW, W = AB_W, lane = c.lane;
+    if (!arena_room(c, r.off, r.n + 1)) return;
+    uint64_t* const base = c.A.base;
+    wsync();
+    for (int i0 = nw > 0 ? ((nw - 1) / W) * W : -1; i0 >= 0; i0 -= W) {     // shift up, last chunk first
+        const int i = i0 + lane; uint64_t t = 0;
+        if (i < nw) t = base[r.off + i];
+        wsync();
+        if (i < nw) base[r.off + AB_TW + i] = t;
+    }
+    wsync();
+    bput(base, r.off, key_zero(), v);
     r.n++;
     c.A.top = r.off + r.n * AB_TW;
-    if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+    arena_mark_peak(c);
 }
 // _acc(TaylorModel&, Float) src/taylor_model.cpp:370-392. r must be the top model on the arena.
 AB_HDN void tm_acc(Ctx& c, TM& r, double s) { AB_FLOPS(5);
     if (s == 0) return;
     if (r.n == 0 || key_deg(tm_key(c, r, 0)) > 0) { tm_prepend_top(c, r, s); return; }
-    double rv = tm_val(c, r, 0);
+    const double rv = tm_val(c, r, 0);
+    wsync();                                   // every lane has read the old constant before it is replaced
     double rvu = add_ru(rv, s), mrvl = sub_ru(-rv, s);
     r.e = add_ru(r.e, add_ru(rvu, mrvl) / 2);
     tm_set_val(c, r, 0, add_rn(rv, s));
@@ -340,7 +305,8 @@ AB_HDN void tm_acc(Ctx& c, TM& r, double s) { AB_FLOPS(5);
 AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
     if (s.l == -s.u) { r.e = add_ru(r.e, s.u); c.rnd = RN; return; }
     if (r.n == 0 || key_deg(tm_key(c, r, 0)) > 0) tm_prepend_top(c, r, 0.0);
-    double rv = tm_val(c, r, 0);
+    const double rv = tm_val(c, r, 0);
+    wsync();
     double rvu = add_ru(rv, s.u), mrvl = sub_ru(-rv, s.l);
     r.e = add_ru(r.e, add_ru(rvu, mrvl) / 2);
     double m = add_rn(s.u, s.l) / 2;
@@ -348,104 +314,313 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
     c.rnd = RN;
 }
 
-// ---- binary operations: results are begun at the arena top ------------------------------------------------------
+// ---- the sparse accumulator ----------------------------------------------------------------------------------------
+// Shared-memory staging area of one warp, in 64-bit words:
+//   [ hash index: AB_SM_NIDX uint32 | keys: AB_KW x AB_SM_CAP | coefficients: AB_SM_CAP | gap codes: AB_SM_G16 uint16 |
+//     staged factor: keys AB_KW x AB_SM_YCAP, coefficients AB_SM_YCAP ]
+// When an accumulator outgrows the shared area it is rebuilt in the free part of the arena (same code, generic pointers).
+#ifndef AB_SM_NIDX
+#define AB_SM_NIDX 1024
+#endif
+#ifndef AB_SM_CAP
+#define AB_SM_CAP 448
+#endif
+#ifndef AB_SM_G16
+#define AB_SM_G16 4096
+#endif
+#ifndef AB_SM_YCAP
+#define AB_SM_YCAP 128
+#endif
+#define AB_SM_OFF_IDX 0
+#define AB_SM_OFF_KEY (AB_SM_NIDX / 2)
+#define AB_SM_OFF_VAL (AB_SM_OFF_KEY + AB_KW * AB_SM_CAP)
+#define AB_SM_OFF_G16 (AB_SM_OFF_VAL + AB_SM_CAP)
+#define AB_SM_OFF_YK (AB_SM_OFF_G16 + AB_SM_G16 / 4)
+#define AB_SM_OFF_YV (AB_SM_OFF_YK + AB_KW * AB_SM_YCAP)
+#define AB_SM_WORDS (AB_SM_OFF_YV + AB_SM_YCAP)
 
-// _add2 (src/taylor_model.cpp:487-530): merge by key; rounding error of coincident terms accumulated upward in
-// key order. Result accuracy is supplied by the caller (the reference's operator+ uses a fresh default).
-AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_FLOPS(3); AB_CALL(0, x.n + y.n);
-    TM r = tm_begin(c, x.as, acc);
-    double te = 0.0;
-    int i = 0, j = 0;
-    bool coincident = false;
-    while (i < x.n && j < y.n) {
-        Key xa = tm_key(c, x, i), ya = tm_key(c, y, j);
-        if (key_less(xa, ya)) { tm_append(c, r, xa, tm_val(c, x, i)); ++i; }
-        else if (key_less(ya, xa)) { tm_append(c, r, ya, tm_val(c, y, j)); ++j; }
-        else {
-            double xv = tm_val(c, x, i), yv = tm_val(c, y, j);
-            double u = add_ru(xv, yv), ml = sub_ru(-xv, yv);
-            te = add_ru(te, add_ru(u, ml));
-            double s = add_rn(xv, yv);
-            if (s != 0) tm_append(c, r, xa, s);
-            AB_FLOPS(5);
-            ++i; ++j; coincident = true;
+#define AB_IDX_EMPTY 0xFFFFFFFFu
+#define AB_ABSENT 0x7FF8AB200AB200ABull      // coefficient slot of a key whose sum cancelled to zero (dropped, as _add2 does)
+
+struct AccTab {
+    uint32_t* idx; uint32_t mask;   // hash index (power-of-two size), cell = position in the dense list or AB_IDX_EMPTY
+    int shift;                      // 64 - log2(size)
+    uint64_t* key;                  // word w of entry s at key[w*cap+s]
+    uint64_t* val;                  // coefficient bits, or AB_ABSENT
+    int cap;
+    int nd;                         // entries in use (warp-uniform)
+    bool overflow;
+};
+AB_HD uint32_t acc_hash(const AccTab& T, const Key& k) {
+    uint64_t h = k.w[0];
+#if AB_KW > 1
+    h ^= k.w[1] * 0xC2B2AE3D27D4EB4Full;
+#endif
+    h *= 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(h >> T.shift);
+}
+// Place the accumulator in the warp's shared area (attempt 0) or above `above` in the arena with room for `want` entries.
+AB_HDN bool acc_open(Ctx& c, AccTab& T, int attempt, int above, long long want) {
+    const int W = AB_W, lane = c.lane;
+    wsync();
+    if (attempt == 0 && c.sm) {
+        uint32_t nidx = 64; while (nidx < AB_SM_NIDX && (long long)nidx < 2 * want) nidx <<= 1;      // small sums clear a small index
+        T.idx = (uint32_t*)(c.sm + AB_SM_OFF_IDX); T.mask = nidx - 1; T.key = c.sm + AB_SM_OFF_KEY; T.val = c.sm + AB_SM_OFF_VAL;
+        T.cap = (int)(nidx / 2) < AB_SM_CAP ? (int)(nidx / 2) : AB_SM_CAP;
+    } else {
+        if (want < 64) want = 64;
+        { const long long room = ((long long)c.A.limit - above - 2) / (AB_KW + 5);      // index (<= 4 cells per entry) + keys + coefficient
+          if (want > room) want = room; if (want < 1) { fail(c, ST_ARENA); return false; } }
+        long long nidx = 128; while (nidx < 2 * want) nidx <<= 1;
+        const long long words = nidx / 2 + (long long)(AB_KW + 1) * want;
+        const long long at = (above + 1) & ~1LL;
+        if (at + words > (long long)c.A.limit) { fail(c, ST_ARENA); return false; }
+        T.idx = (uint32_t*)(c.A.base + at); T.mask = (uint32_t)(nidx - 1); T.key = c.A.base + at + nidx / 2; T.val = T.key + (long long)AB_KW * want; T.cap = (int)want;
+        if ((int)(at + words) > c.A.peak) c.A.peak = (int)(at + words);
+    }
+    int lg = 0; while ((1u << lg) <= T.mask) ++lg;
+    T.shift = 64 - lg;
+    T.nd = 0; T.overflow = false;
+    for (uint32_t i = (uint32_t)lane; i <= T.mask; i += (uint32_t)W) T.idx[i] = AB_IDX_EMPTY;
+    wsync();
+    return true;
+}
+// Collective: every lane calls it; a lane with `active` set brings a key, and the keys of the active lanes are distinct.
+// Returns the key's position in the dense list, inserting it (coefficient AB_ABSENT) if it is new.
+AB_HD int acc_slot(AccTab& T, bool active, const Key& k, int lane) {
+    int slot = -1; uint32_t h = 0; bool isnew = false;
+    if (active) {
+        h = acc_hash(T, k);
+        for (;;) {
+            const uint32_t id = T.idx[h];
+            if (id == AB_IDX_EMPTY) { isnew = true; break; }
+            bool eq = T.key[id] == k.w[0];
+#if AB_KW > 1
+            eq = eq && T.key[T.cap + id] == k.w[1];
+#endif
+            if (eq) { slot = (int)id; break; }
+            h = (h + 1) & T.mask;
         }
     }
-    while (i < x.n) { tm_append(c, r, tm_key(c, x, i), tm_val(c, x, i)); ++i; }
-    while (j < y.n) { tm_append(c, r, tm_key(c, y, j), tm_val(c, y, j)); ++j; }
-    (void)coincident;
-    r.e = add_ru(add_ru(x.e, y.e), te / 2);
-    c.rnd = RN;
+    const unsigned nm = wballot(isnew);
+    if (nm) {
+        const int cnt = popc32(nm);
+        if (T.nd + cnt > T.cap) { T.overflow = true; return active ? (isnew ? 0 : slot) : -1; }   // caller checks T.overflow (uniform)
+        if (isnew) {
+            slot = T.nd + popc32(nm & lanemask_lt(lane));
+            T.key[slot] = k.w[0];
+#if AB_KW > 1
+            T.key[T.cap + slot] = k.w[1];
+#endif
+            T.val[slot] = AB_ABSENT;
+            for (;;) {          // claim an empty index cell; the other new keys of this call differ from this one
+                const uint32_t old = cas32(&T.idx[h], AB_IDX_EMPTY, (uint32_t)slot);
+                if (old == AB_IDX_EMPTY) break;
+                h = (h + 1) & T.mask;
+            }
+        }
+        T.nd += cnt;
+        wsync();
+    }
+    return slot;
+}
+// Fold one coefficient into its entry, as one step of _add2 does (src/taylor_model.cpp:505-512): returns the rounding gap
+// up(u+ml) of a coincident term, 0 for a new one; a sum that cancels to zero drops the term.
+AB_HD double acc_fold(AccTab& T, int slot, double tv) {
+    const uint64_t cb = T.val[slot];
+    if (cb == AB_ABSENT) { T.val[slot] = d2u(tv); return 0.0; }
+    const double cur = u2d(cb);
+    const double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
+    const double nv = add_rn(cur, tv);
+    T.val[slot] = (nv == 0) ? AB_ABSENT : d2u(nv);
+    return add_ru(u, ml);
+}
+// Add the terms of model t as one stream; returns te, the upward sum of the rounding gaps in key order.
+AB_HDN double acc_add_model(Ctx& c, AccTab& T, const TM& t) {
+    const int W = AB_W, lane = c.lane, n = t.n;
+    const uint64_t* const base = c.A.base;
+    double te = 0.0;
+    for (int j0 = 0; j0 < n; j0 += W) {
+        const int j = j0 + lane; const bool act = j < n;
+        Key k = key_zero(); double tv = 0.0;
+        if (act) { k = bkey(base, t.off + j * AB_TW); tv = bval(base, t.off + j * AB_TW); }
+        const int slot = acc_slot(T, act, k, lane);
+        if (T.overflow) return te;
+        double g = 0.0;
+        if (act) g = acc_fold(T, slot, tv);
+        const unsigned gm = wballot(g != 0.0);
+        te = chain_ru_masked(te, g, gm);
+    }
+    wsync();
+    return te;
+}
+
+// Number of monomials of degree <= D in `as` variables, saturated at 2^31-1 (also when the table is too small).
+AB_HD long long monomial_count(const uint32_t* tab, int D, int as) {
+    if (!tab || D + as >= AB_BINOM_N || as >= AB_BINOM_K) {
+        if (!tab && D + as < 40 && as < AB_BINOM_K) { long long R = 1; for (int i = 1; i <= as && R < (1LL << 40); ++i) R = R * (D + i) / i; return R > 0x7FFFFFFFLL ? 0x7FFFFFFFLL : R; }
+        return 0x7FFFFFFFLL;
+    }
+    return (long long)tab[(D + as) * AB_BINOM_K + as];
+}
+AB_HD uint32_t binom_at(const uint32_t* tab, int n, int k) { return (n < 0 || k < 0 || n >= AB_BINOM_N || k >= AB_BINOM_K) ? 0u : tab[n * AB_BINOM_K + k]; }
+// Position of a monomial among all monomials in `as` variables in the graded order of include/multi_index.h:346-358.
+AB_HD uint32_t key_rank(const uint32_t* tab, const Key& k, int as) {
+    int R = key_deg(k);
+    uint32_t r = (R > 0) ? binom_at(tab, R - 1 + as, as) : 0u;     // monomials of smaller degree
+    for (int t = 0; t + 1 < as; ++t) {
+        const int e = key_get(k, t), m = as - t;
+        r += binom_at(tab, R - e - 1 + m - 1, m - 1);              // same prefix, larger exponent here
+        R -= e;
+    }
     return r;
 }
+// Write the accumulator to the arena at word `dst` in key order, skipping dropped entries; returns the number of terms.
+// `scratch` is shared (or arena) memory free for the ordering: gap-code and staging areas when the table is in shared memory.
+AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
+    const int W = AB_W, lane = c.lane, nd = T.nd;
+    uint64_t* const base = c.A.base;
+    if (nd == 0) return 0;
+    if (!arena_room(c, dst, nd)) return 0;
+    // rank bitmap: a bit per monomial of degree <= maxdeg; positions are prefix popcounts
+    const long long R = monomial_count(c.binom, maxdeg, as);
+    uint32_t* bits = 0; uint32_t* pre = 0; long long nwords = (R + 31) / 32;
+    const bool in_sm = c.sm && (T.val == c.sm + AB_SM_OFF_VAL);
+    if (c.binom && maxdeg + as < AB_BINOM_N && as < AB_BINOM_K && R < (1LL << 30)) {
+        if (in_sm && 2 * nwords * 4 <= (long long)(AB_SM_WORDS - AB_SM_OFF_G16) * 8) { bits = (uint32_t*)(c.sm + AB_SM_OFF_G16); pre = bits + nwords; }
+        else if (!in_sm) {
+            // table lives in the arena: put the bitmap above it
+            uint64_t* endp = T.val + T.cap;
+            long long at = (endp - base); at = (at + 1) & ~1LL;
+            if (nwords <= 65536 && at + nwords + 2 <= (long long)c.A.limit) { bits = (uint32_t*)(base + at); pre = bits + nwords; if ((int)(at + nwords + 2) > c.A.peak) c.A.peak = (int)(at + nwords + 2); }
+        }
+    }
+    if (bits) {
+        const uint32_t* tab = c.binom;
+        for (long long i = lane; i < nwords; i += W) bits[i] = 0;
+        wsync();
+        for (int s = lane; s < nd; s += W) if (T.val[s] != AB_ABSENT) {
+            Key k; k.w[0] = T.key[s];
+#if AB_KW > 1
+            k.w[1] = T.key[T.cap + s];
+#endif
+            const uint32_t r = key_rank(tab, k, as);
+            or32(&bits[r >> 5], 1u << (r & 31));
+        }
+        wsync();
+        int total = 0;
+        for (long long i0 = 0; i0 < nwords; i0 += W) {        // exclusive prefix of the word popcounts
+            const long long i = i0 + lane; int pc = (i < nwords) ? popc32(bits[i]) : 0;
+            int incl = pc;
+            for (int d = 1; d < W; d <<= 1) { int o = wshfl(incl, lane - d < 0 ? lane : lane - d); if (lane >= d) incl += o; }
+            if (i < nwords) pre[i] = (uint32_t)(total + incl - pc);
+            total += wshfl(incl, W - 1);
+        }
+        wsync();
+        for (int s = lane; s < nd; s += W) if (T.val[s] != AB_ABSENT) {
+            Key k; k.w[0] = T.key[s];
+#if AB_KW > 1
+            k.w[1] = T.key[T.cap + s];
+#endif
+            const uint32_t r = key_rank(tab, k, as);
+            const int pos = (int)pre[r >> 5] + popc32(bits[r >> 5] & ((1u << (r & 31)) - 1u));
+            bput(base, dst + pos * AB_TW, k, u2d(T.val[s]));
+        }
+        wsync();
+        return total;
+    }
+    // general ordering: bitonic sort of the entry numbers by key (uses the hash index area, no longer needed)
+    int P = 1; while (P < nd) P <<= 1;
+    uint32_t* perm = T.idx;                       // index area holds >= 2*cap cells
+    for (int i = lane; i < P; i += W) perm[i] = (i < nd && T.val[i] != AB_ABSENT) ? (uint32_t)i : AB_IDX_EMPTY;
+    wsync();
+    for (int kk = 2; kk <= P; kk <<= 1) for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < P; t += W) {
+            const int o = t ^ j;
+            if (o > t) {
+                const uint32_t a = perm[t], b = perm[o];
+                bool b_lt_a;
+                if (b == AB_IDX_EMPTY) b_lt_a = false; else if (a == AB_IDX_EMPTY) b_lt_a = true;
+                else {
+                    Key ka, kb; ka.w[0] = T.key[a]; kb.w[0] = T.key[b];
+#if AB_KW > 1
+                    ka.w[1] = T.key[T.cap + a]; kb.w[1] = T.key[T.cap + b];
+#endif
+                    b_lt_a = key_less(kb, ka);
+                }
+                const bool asc = (t & kk) == 0;
+                if (b_lt_a == asc) { perm[t] = b; perm[o] = a; }
+            }
+        }
+        wsync();
+    }
+    int total = 0;
+    for (int i0 = 0; i0 < nd; i0 += W) {
+        const int i = i0 + lane; const uint32_t s = (i < nd) ? perm[i] : AB_IDX_EMPTY;
+        const unsigned m = wballot(s != AB_IDX_EMPTY);
+        if (s != AB_IDX_EMPTY) {
+            Key k; k.w[0] = T.key[s];
+#if AB_KW > 1
+            k.w[1] = T.key[T.cap + s];
+#endif
+            bput(base, dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW, k, u2d(T.val[s]));
+        }
+        total += popc32(m);
+    }
+    wsync();
+    return total;
+}
+
+// ---- binary operations: results are begun at the arena top ------------------------------------------------------
+
 // r' = ((r + t[0]) + t[1]) + ... + t[B-1] with the exact semantics of B successive _add2 calls
-// (src/taylor_model.cpp:487-530), computed in ONE pass over r: a (B+1)-way merge in key order in which, for every
-// key, the streams are folded in index order. Each stream keeps its own upward-rounded gap sum te[s] (visited in key
-// order, as in the reference), and the error chain e <- up(up(e + t[s].e) + te[s]/2) is applied in stream order.
-// A coefficient that cancels to exactly zero is dropped, as _add2 does, and a later stream re-creates the term.
-// This removes the O(#streams x |r|) re-copying of the accumulator that dominates the reference's _mul4/_compose2.
+// (src/taylor_model.cpp:487-530): every coefficient is folded in stream order; each stream has its own upward-rounded
+// gap sum te[s] (visited in key order, as in the reference), and the error chain e <- up(up(e + t[s].e) + te[s]/2) is
+// applied in stream order. A coefficient that cancels to exactly zero is dropped, as _add2 does, and a later stream
+// re-creates the term. Result at the arena top.
 #ifndef AB_MAXSTREAMS
 #define AB_MAXSTREAMS 8
 #endif
 AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B); AB_FLOPS(3 * B);
-    uint64_t* const base = c.A.base;
-    const int limit = c.A.limit;
-    const int ooff = c.A.top;
-    int on = 0;
-    bool overflow = false;
-    int tw[AB_MAXSTREAMS], tend[AB_MAXSTREAMS];      // word cursor and end of every stream
+    const int m = c.A.top;
+    TM out; out.off = m; out.n = 0; out.as = r.as; out.acc = acc; out.e = r.e;
+    long long want = r.n; int maxdeg = tm_degree(c, r);
+    for (int s = 0; s < B; ++s) { want += t[s].n; const int d = tm_degree(c, t[s]); if (d > maxdeg) maxdeg = d; }
     double te[AB_MAXSTREAMS];
-    SKey hs[AB_MAXSTREAMS];
-    #pragma unroll
-    for (int s = 0; s < AB_MAXSTREAMS; ++s) {
-        te[s] = 0.0; hs[s] = skey_dead(); tw[s] = 0; tend[s] = 0;
-        if (s < B) { tw[s] = t[s].off; tend[s] = t[s].off + t[s].n * AB_TW; if (tw[s] < tend[s]) hs[s] = skey(bkey(base, tw[s])); }
+    AccTab T;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!acc_open(c, T, attempt, m + (int)want * AB_TW, want)) return out;
+        acc_add_model(c, T, r);
+        for (int s = 0; s < B && !T.overflow; ++s) te[s] = acc_add_model(c, T, t[s]);
+        if (!T.overflow) break;
+        if (attempt == 1) { fail(c, ST_ARENA); return out; }
     }
-    int rw = r.off; const int rend = r.off + r.n * AB_TW;
-    SKey rs = rw < rend ? skey(bkey(base, rw)) : skey_dead();
-    for (;;) {
-        // smallest key among the heads
-        SKey mk = rs;
-        #pragma unroll
-        for (int s = 0; s < AB_MAXSTREAMS; ++s) if (skey_less(hs[s], mk)) mk = hs[s];
-        if (skey_is_dead(mk)) break;
-        bool present = false;
-        double cur = 0.0;
-        if (skey_eq(rs, mk)) {
-            cur = bval(base, rw); present = true;
-            rw += AB_TW; rs = rw < rend ? skey(bkey(base, rw)) : skey_dead();
-        }
-        #pragma unroll
-        for (int s = 0; s < AB_MAXSTREAMS; ++s) {
-            if (!skey_eq(hs[s], mk)) continue;
-            double tv = bval(base, tw[s]);
-            if (present) {
-                AB_FLOPS(5);
-                double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
-                te[s] = add_ru(te[s], add_ru(u, ml));
-                cur = add_rn(cur, tv);
-                if (cur == 0) present = false;
-            } else { cur = tv; present = true; }
-            tw[s] += AB_TW;
-            hs[s] = tw[s] < tend[s] ? skey(bkey(base, tw[s])) : skey_dead();
-        }
-        if (present) { const int o = ooff + on * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, skey_key(mk), cur); ++on; } }
-    }
-    TM out; out.off = ooff; out.n = on; out.as = r.as; out.acc = acc;
-    c.A.top = ooff + on * AB_TW;
+    out.n = acc_emit(c, T, r.as, maxdeg, m);
+    c.A.top = m + out.n * AB_TW;
     arena_mark_peak(c);
-    if (overflow) fail(c, ST_ARENA);
     double e = r.e;
     for (int s = 0; s < B; ++s) e = add_ru(add_ru(e, t[s].e), te[s] / 2);
     out.e = e;
     c.rnd = RN;
     return out;
 }
+// _add2 (src/taylor_model.cpp:487-530). Result accuracy is supplied by the caller (the reference's operator+ uses a
+// fresh default).
+AB_HDN TM tm_add2(Ctx& c, const TM& x, const TM& y, Acc acc) { AB_CALL(0, x.n + y.n);
+    TM r = tm_add_many(c, x, &y, 1, acc);
+    return r;
+}
 // neg (src/taylor_model.cpp:1530-1537): fresh default accuracy
 AB_HDN TM tm_neg(Ctx& c, const TM& x) { AB_CALL(6, x.n);
+    wsync();
     TM r = tm_begin(c, x.as, acc_default());
-    for (int i = 0; i < x.n; ++i) tm_append(c, r, tm_key(c, x, i), -tm_val(c, x, i));
-    r.e = x.e;
+    if (!arena_room(c, r.off, x.n)) return r;
+    uint64_t* const base = c.A.base; const int W = AB_W;
+    for (int i = c.lane; i < x.n; i += W) bput(base, r.off + i * AB_TW, bkey(base, x.off + i * AB_TW), -bval(base, x.off + i * AB_TW));
+    wsync();
+    r.n = x.n; r.e = x.e;
+    c.A.top = r.off + r.n * AB_TW;
+    arena_mark_peak(c);
     return r;
 }
 // operator+(x,y) src/taylor_model.cpp:1253-1256
@@ -461,198 +636,265 @@ AB_HDN TM tm_sub(Ctx& c, const TM& x, const TM& y) {
 // x+=y (src/taylor_model.cpp:1150-1156,538-541): result keeps x's accuracy. Returns a new model at the top.
 AB_HD TM tm_plus_assign(Ctx& c, const TM& x, const TM& y) { return tm_add2(c, x, y, x.acc); }
 
+// Gap codes of a product: bit 15 = the product was discarded (its truncation error |x||y| is recomputed by the summing
+// lane), else the biased exponent of the rounding gap (0 = no gap). A gap that is not 0 or a power of two cannot occur
+// for coefficients in the normal range; it is reported rather than mis-encoded.
+#define AB_G16_DISCARD 0x8000u
+AB_HD uint32_t gap_code(double g, bool* bad) {
+    const uint64_t b = d2u(g);
+    if (b & 0x000FFFFFFFFFFFFFull) *bad = true;
+    return (uint32_t)(b >> 52);
+}
+AB_HD double gap_value(uint32_t code) { return u2d((uint64_t)code << 52); }
+
 // _mul4 (src/taylor_model.cpp:763-824) with accuracy `acc` (operator* passes the RIGHT operand's, :1265-1268).
-// Result at the arena top.
-// Product stream b of a block is x-term (i0+b) times y; its head is the next product that is not discarded.
-// Discarded products are folded into the stream's truncation error while the cursor advances, in y order, exactly
-// as the inner loop of _mul4 does.
-#ifndef AB_MULSTREAMS
-#define AB_MULSTREAMS 8
-#endif
+// Result at the arena top. The x-terms are the streams: stream i is x[i]*y, its discarded products go to the stream's
+// truncation error tte[i] (t.error()=tte+tte/2), its coincident products to te[i].
 #ifdef AB_MUL_HIST
 extern long long g_mul_hist[8][8];   // [log2 bucket of x.n][log2 bucket of y.n]
 extern long long g_mul_prod[8][8];
 #endif
 AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
-    AB_SECTION(0);
 #ifdef AB_MUL_HIST
-    { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
+    if (c.lane == 0) { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
 #endif
     AB_FLOPS((double)x.n * (5.0 * y.n + 3.0) + 2.0 * (x.n + y.n) + 6.0);
     uint64_t* const base = c.A.base;
-    const int limit = c.A.limit;
+    const int W = AB_W, lane = c.lane;
     const int m = c.A.top;
     const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
     const double xe = x.e, ye = y.e;
     const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
     #define AB_DISCARD(k, v) (dabs(v) < sweep || key_deg(k) > maxdeg)
-    bool overflow = false;
-    TM r; r.off = m; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc;          // empty accumulator at m
+    TM r; r.off = m; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc;
+    if (xn == 0 || yn == 0) {
+        // an empty factor: no streams; only the error cross terms remain (norms of the other factor)
+        double xs = 0, ys = 0;
+        for (int i0 = 0; i0 < xn; i0 += W) { const int i = i0 + lane; xs = chain_ru(xs, i < xn ? dabs(bval(base, xoff + i * AB_TW)) : 0.0, (xn - i0 < W) ? xn - i0 : W); }
+        for (int j0 = 0; j0 < yn; j0 += W) { const int j = j0 + lane; ys = chain_ru(ys, j < yn ? dabs(bval(base, yoff + j * AB_TW)) : 0.0, (yn - j0 < W) ? yn - j0 : W); }
+        r.e = add_ru(0.0, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
+        c.rnd = RN;
+        return r;
+    }
     if (xn == 1 || yn == 1) {
-        // A single-term factor (constants, variables and monomials of the op tapes: about 1400 of the 1600 products
-        // of a van der Pol step). Adding a fixed key keeps the key order, so the product streams never meet: the
-        // result is written directly and the error chain of the general path reduces to the truncation terms.
+        // A single-term factor (constants, variables and monomials of the op tapes). Adding a fixed key keeps the key
+        // order, so the product streams never meet: the result is written directly, compacted over the discarded
+        // products, and the error chain of the general path reduces to the truncation terms.
         double e = 0.0, xs = 0.0, ys = 0.0;
         int rn = 0;
-        if (xn == 1) {
-            const Key xa = bkey(base, xoff); const double xv = bval(base, xoff), axv = dabs(xv);
-            double tte = 0.0;
-            for (int j = 0; j < yn; ++j) {
-                const int w = yoff + j * AB_TW;
-                const double yv = bval(base, w); const Key ta = key_add(xa, bkey(base, w));
-                const double tv = mul_rn(xv, yv);
-                ys = add_ru(ys, dabs(yv));
-                if (AB_DISCARD(ta, tv)) tte = add_ru(tte, mul_ru(axv, dabs(yv)));
-                else { const int o = m + rn * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, ta, tv); ++rn; } }
+        const bool one_x = (xn == 1);
+        const int n = one_x ? yn : xn, soff = one_x ? yoff : xoff;
+        wsync();
+        const Key fa = bkey(base, one_x ? xoff : yoff); const double fv = bval(base, one_x ? xoff : yoff), afv = dabs(fv);
+        const double oe = one_x ? xe : ye;          // error of the single-term factor multiplies the norm of the other
+        if (!arena_room(c, m, n)) return r;
+        double tte = 0.0, norm = 0.0;
+        for (int j0 = 0; j0 < n; j0 += W) {
+            const int j = j0 + lane; const bool act = j < n;
+            Key ta = key_zero(); double sv = 0.0, tv = 0.0; bool disc = false;
+            if (act) {
+                const int w = soff + j * AB_TW;
+                sv = bval(base, w); ta = key_add(fa, bkey(base, w));
+                tv = one_x ? mul_rn(fv, sv) : mul_rn(sv, fv);
+                disc = AB_DISCARD(ta, tv);
             }
-            e = add_ru(tte, tte / 2);
-            xs = axv;
-        } else {
-            const Key ya = bkey(base, yoff); const double yv = bval(base, yoff), ayv = dabs(yv);
-            for (int i = 0; i < xn; ++i) {
-                const int w = xoff + i * AB_TW;
-                const double xv = bval(base, w); const Key ta = key_add(bkey(base, w), ya);
-                const double tv = mul_rn(xv, yv);
-                xs = add_ru(xs, dabs(xv));
-                if (AB_DISCARD(ta, tv)) { const double tte = mul_ru(dabs(xv), ayv); e = add_ru(e, add_ru(tte, tte / 2)); }
-                else { const int o = m + rn * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput(base, o, ta, tv); ++rn; } }
+            const unsigned dm = wballot(disc), km = wballot(act && !disc);
+            if (act && !disc) bput(base, m + (rn + popc32(km & lanemask_lt(lane))) * AB_TW, ta, tv);
+            rn += popc32(km);
+            if (dm) {
+                if (one_x) tte = chain_ru_masked(tte, mul_ru(afv, dabs(sv)), dm);
+                else { const double t1 = mul_ru(dabs(sv), afv); e = chain_ru_masked(e, add_ru(t1, t1 / 2), dm); }
             }
-            ys = ayv;
+            if (oe != 0.0) norm = chain_ru(norm, act ? dabs(sv) : 0.0, (n - j0 < W) ? n - j0 : W);
         }
+        wsync();
+        if (one_x) { e = add_ru(tte, tte / 2); xs = afv; ys = norm; } else { xs = norm; ys = afv; }
         r.n = rn;
         r.e = add_ru(e, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
         c.rnd = RN;
         c.A.top = m + rn * AB_TW;
         arena_mark_peak(c);
-        if (overflow) fail(c, ST_ARENA);
         return r;
     }
-    // Accumulator placement. Each batch reads the accumulator r and writes a new one; instead of building it above r and
-    // sliding it back down every time, two regions [m, H) and [H, ...) are used alternately. Both hold any possible
-    // accumulator: its keys are distinct monomials of degree <= min(maxdeg, deg x + deg y) in x.as variables, and there
-    // are at most x.n*y.n of them. If the arena cannot hold both regions the slide per batch is kept.
-    int H = -1;
-    {
-        int D = tm_degree(c, x) + tm_degree(c, y); if (D > maxdeg) D = maxdeg;
-        long long cap = 1;
-        for (int i = 1; i <= as && cap < (1LL << 24); ++i) cap = cap * (D + i) / i;
-        const long long prod = (long long)xn * (long long)yn;
-        if (prod < cap) cap = prod;
-        const long long words = cap * AB_TW;
-        if ((long long)m + 2 * words <= (long long)limit) H = m + (int)words;
-    }
-    const int nbatch = (xn + AB_MULSTREAMS - 1) / AB_MULSTREAMS;
-    int roff = m, rn = 0, top_max = m;
+    // ---- general product ------------------------------------------------------------------------------------------
+    // An upper bound of the number of result terms: distinct monomials of degree <= min(maxdeg, deg x + deg y).
+    int D = tm_degree(c, x) + tm_degree(c, y); if (D > maxdeg) D = maxdeg;
+    long long bound = monomial_count(c.binom, D, as);
+    { const long long prod = (long long)xn * (long long)yn; if (prod < bound) bound = prod; }
     double re = 0.0;
-    for (int i0 = 0; i0 < xn; i0 += AB_MULSTREAMS) {
-        const int B = (xn - i0 < AB_MULSTREAMS) ? (xn - i0) : AB_MULSTREAMS;
-        Key xa[AB_MULSTREAMS];
-        SKey hs[AB_MULSTREAMS];
-        double xv[AB_MULSTREAMS], hv[AB_MULSTREAMS], tte[AB_MULSTREAMS], te[AB_MULSTREAMS];
-        int cur[AB_MULSTREAMS];        // word offset of the y term AFTER the head
-        // all per-stream state is indexed with compile-time constants (fully unrolled loops) so it stays in registers
-        #pragma unroll
-        for (int b = 0; b < AB_MULSTREAMS; ++b) {
-            tte[b] = 0.0; te[b] = 0.0; cur[b] = yoff; xv[b] = 0.0; xa[b] = key_zero(); hs[b] = skey_dead(); hv[b] = 0.0;
-            if (b < B) { xa[b] = bkey(base, xoff + (i0 + b) * AB_TW); xv[b] = bval(base, xoff + (i0 + b) * AB_TW); }
+    AccTab T;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // factor y staged in shared memory as structure-of-arrays (keys | coefficients) when it fits
+        const uint64_t* yk; const uint64_t* yv; int ystr, ykw;      // word j of y: yk[j*ystr] (+ykw for the second key word), yv[j*ystr]
+        if (c.sm && yn <= AB_SM_YCAP) {
+            uint64_t* sk = c.sm + AB_SM_OFF_YK; uint64_t* sv = c.sm + AB_SM_OFF_YV;
+            for (int j = lane; j < yn; j += W) { for (int w = 0; w < AB_KW; ++w) sk[w * AB_SM_YCAP + j] = base[yoff + j * AB_TW + w]; sv[j] = base[yoff + j * AB_TW + AB_KW]; }
+            yk = sk; yv = sv; ystr = 1; ykw = AB_SM_YCAP;
+        } else { yk = base + yoff; yv = base + yoff + AB_KW; ystr = AB_TW; ykw = 1; }
+        // gap codes: rows of `gs` codes, one row per x-term of a batch
+        uint16_t* g16; int gcap;
+        int gs = yn + ((2 - (yn & 3)) & 3); if (gs < 2) gs = 2;      // row stride = 2 mod 4: conflict-free column reads
+        const bool g_in_sm = c.sm && gs <= AB_SM_G16 / 2;
+        // without a shared area (host-side callers) or for a very long factor the gap codes go to the arena
+        const long long gwords = g_in_sm ? 0 : ((long long)gs * (W < 8 ? W : 8) + 3) / 4;
+        long long cap1 = ((long long)c.A.limit - m - gwords - 8) / (2 * AB_KW + 5);   // result region + table + index
+        if (cap1 > bound) cap1 = bound;
+        if (cap1 < 1) { fail(c, ST_ARENA); return r; }
+        int tab_above = m + (int)cap1 * AB_TW;
+        if (g_in_sm) { g16 = (uint16_t*)(c.sm + AB_SM_OFF_G16); gcap = AB_SM_G16; }
+        else {
+            const long long at = ((long long)tab_above + 1) & ~1LL;
+            if (at + gwords > (long long)c.A.limit) { fail(c, ST_ARENA); return r; }
+            g16 = (uint16_t*)(base + at); gcap = (int)(gwords * 4); tab_above = (int)(at + gwords);
+            if (tab_above > c.A.peak) c.A.peak = tab_above;
         }
-        const int yend = yoff + yn * AB_TW;
-        // advance stream b to its next surviving product
-        #define AB_ADVANCE(b) do { hs[b] = skey_dead(); const double axv_ = dabs(xv[b]); \
-            while (cur[b] < yend) { const Key ta_ = key_add(xa[b], bkey(base, cur[b])); const double yv_ = bval(base, cur[b]); cur[b] += AB_TW; \
-                const double tv_ = mul_rn(xv[b], yv_); \
-                if (AB_DISCARD(ta_, tv_)) tte[b] = add_ru(tte[b], mul_ru(axv_, dabs(yv_))); \
-                else { hs[b] = skey(ta_); hv[b] = tv_; break; } } } while (0)
-        #pragma unroll
-        for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) AB_ADVANCE(b);
-        // regions alternate, arranged so that the last batch lands at m and no final move is needed
-        const int ooff = (H >= 0) ? ((((nbatch - 1 - i0 / AB_MULSTREAMS) & 1) == 0) ? m : H) : roff + rn * AB_TW;
-        int on = 0;
-        int rw = roff; const int rend = roff + rn * AB_TW;
-        SKey rs = rn > 0 ? skey(bkey_cs(base, rw)) : skey_dead();
-        for (;;) {
-            SKey mk = rs;
-            #pragma unroll
-            for (int b = 0; b < AB_MULSTREAMS; ++b) if (skey_less(hs[b], mk)) mk = hs[b];
-            if (skey_is_dead(mk)) break;
-            bool present = false; double cv = 0.0;
-            if (skey_eq(rs, mk)) { cv = bval_cs(base, rw); present = true; rw += AB_TW; rs = rw < rend ? skey(bkey_cs(base, rw)) : skey_dead(); }
-            #pragma unroll
-            for (int b = 0; b < AB_MULSTREAMS; ++b) {
-                if (!skey_eq(hs[b], mk)) continue;
-                const double tv = hv[b];
-                if (present) {
-                    AB_FLOPS(5);
-                    double u = add_ru(cv, tv), ml = sub_ru(-cv, tv);
-                    te[b] = add_ru(te[b], add_ru(u, ml));
-                    cv = add_rn(cv, tv);
-                    if (cv == 0) present = false;
-                } else { cv = tv; present = true; }
-                AB_ADVANCE(b);
+        int Bi = gcap / gs; if (Bi > W) Bi = W; if (Bi < 1) Bi = 1;
+        if (!acc_open(c, T, attempt, tab_above, cap1)) return r;
+        re = 0.0;
+        bool badgap = false;
+        for (int i0 = 0; i0 < xn && !T.overflow; i0 += Bi) {
+            const int nb = (xn - i0 < Bi) ? (xn - i0) : Bi;
+            // lane b holds x-term i0+b
+            Key mxa = key_zero(); double mxv = 0.0;
+            if (lane < nb) { mxa = bkey(base, xoff + (i0 + lane) * AB_TW); mxv = bval(base, xoff + (i0 + lane) * AB_TW); }
+            for (int b = 0; b < nb && !T.overflow; ++b) {
+                Key xa; xa.w[0] = wshfl(mxa.w[0], b);
+#if AB_KW > 1
+                xa.w[1] = wshfl(mxa.w[1], b);
+#endif
+                const double xv = wshfl(mxv, b);
+                uint16_t* row = g16 + b * gs;
+                for (int j0 = 0; j0 < yn; j0 += W) {
+                    const int j = j0 + lane; const bool act = j < yn;
+                    Key ta = key_zero(); double tv = 0.0; bool disc = false;
+                    if (act) {
+                        Key ya; ya.w[0] = yk[j * ystr];
+#if AB_KW > 1
+                        ya.w[1] = yk[j * ystr + ykw];
+#endif
+                        ta = key_add(xa, ya); tv = mul_rn(xv, u2d(yv[j * ystr]));
+                        disc = AB_DISCARD(ta, tv);
+                    }
+                    const int slot = acc_slot(T, act && !disc, ta, lane);
+                    if (T.overflow) break;
+                    if (act) {
+                        uint32_t code = AB_G16_DISCARD;
+                        if (!disc) { AB_FLOPS(5); code = gap_code(acc_fold(T, slot, tv), &badgap); }
+                        row[j] = (uint16_t)code;
+                    }
+                }
+                wsync();          // the next x-term may meet the entries this one wrote
             }
-            if (present) { const int o = ooff + on * AB_TW; if (o + AB_TW > limit) overflow = true; else { bput_cs(base, o, skey_key(mk), cv); ++on; } }
+            if (T.overflow) break;
+            // per x-term sums, upward and in y order: lane b sums the row of x-term i0+b
+            double tte = 0.0, te = 0.0;
+            if (lane < nb) {
+                const double axv = dabs(mxv);
+                const uint16_t* row = g16 + lane * gs;
+                for (int j = 0; j < yn; ++j) {
+                    const uint32_t code = row[j];
+                    if (code & AB_G16_DISCARD) tte = add_ru(tte, mul_ru(axv, dabs(u2d(yv[j * ystr]))));
+                    else if (code) te = add_ru(te, gap_value(code));
+                }
+            }
+            wsync();
+            // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
+            for (int b = 0; b < nb; ++b) {
+                const double tt = wshfl(tte, b), ee = wshfl(te, b);
+                const double tev = add_ru(tt, tt / 2);
+                re = add_ru(add_ru(re, tev), ee / 2);
+            }
         }
-        #undef AB_ADVANCE
-        if (ooff + on * AB_TW > top_max) top_max = ooff + on * AB_TW;
-        AB_CALL(10, on); AB_CALL(11, B * yn);
-        // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
-        double e = re;
-        #pragma unroll
-        for (int b = 0; b < AB_MULSTREAMS; ++b) if (b < B) { double tev = add_ru(tte[b], tte[b] / 2); e = add_ru(add_ru(e, tev), te[b] / 2); }
-        re = e; roff = ooff; rn = on;
-        if (H < 0 && roff != m) { for (int i = 0; i < rn * AB_TW; ++i) base[AB_WORD_INDEX(m + i)] = base[AB_WORD_INDEX(roff + i)]; roff = m; }
+        if (wany(badgap)) fail(c, ST_UNSUPPORTED);
+        if (!T.overflow) break;
+        if (attempt == 1) { fail(c, ST_ARENA); return r; }
     }
     #undef AB_DISCARD
-    if (roff != m) { for (int i = 0; i < rn * AB_TW; ++i) base[AB_WORD_INDEX(m + i)] = base[AB_WORD_INDEX(roff + i)]; roff = m; }
-    if (top_max > c.A.peak) c.A.peak = top_max;
-    if (overflow) fail(c, ST_ARENA);
-    r.off = m; r.n = rn; r.e = re;
+    r.n = acc_emit(c, T, as, D, m);
     double xs = 0, ys = 0;
-    for (int i = 0; i < xn; ++i) xs = add_ru(xs, dabs(bval(base, xoff + i * AB_TW)));
-    for (int j = 0; j < yn; ++j) ys = add_ru(ys, dabs(bval(base, yoff + j * AB_TW)));
-    r.e = add_ru(r.e, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
+    for (int i0 = 0; i0 < xn; i0 += W) { const int i = i0 + lane; xs = chain_ru(xs, i < xn ? dabs(bval(base, xoff + i * AB_TW)) : 0.0, (xn - i0 < W) ? xn - i0 : W); }
+    for (int j0 = 0; j0 < yn; j0 += W) { const int j = j0 + lane; ys = chain_ru(ys, j < yn ? dabs(bval(base, yoff + j * AB_TW)) : 0.0, (yn - j0 < W) ? yn - j0 : W); }
+    r.e = add_ru(re, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
     c.rnd = RN;
-    c.A.top = m + rn * AB_TW;
+    c.A.top = m + r.n * AB_TW;
+    arena_mark_peak(c);
     return r;
 }
 AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc); }
 
+// Order-preserving removal of the terms flagged by the caller's predicate, in place; the magnitudes of the removed terms
+// are added to the error upward, in term order. Returns through x.
+#define AB_FILTER_IN_PLACE(c, x, DROP_EXPR)                                                                        \
+    do {                                                                                                           \
+        const int W_ = AB_W, lane_ = (c).lane, n_ = (x).n; int k_ = 0; double e_ = (x).e;                         \
+        wsync();                                                                                                   \
+        for (int i0_ = 0; i0_ < n_; i0_ += W_) {                                                                   \
+            const int i_ = i0_ + lane_; const bool act_ = i_ < n_;                                                 \
+            Key a = key_zero(); double v = 0.0; bool drop_ = false;                                                \
+            if (act_) { a = tm_key(c, x, i_); v = tm_val(c, x, i_); drop_ = (DROP_EXPR); }                         \
+            const unsigned dm_ = wballot(act_ && drop_), km_ = wballot(act_ && !drop_);                           \
+            wsync();                                                                                               \
+            if (act_ && !drop_) { const int p_ = k_ + popc32(km_ & lanemask_lt(lane_)); if (p_ != i_) { tm_set_key(c, x, p_, a); tm_set_val(c, x, p_, v); } } \
+            k_ += popc32(km_);                                                                                     \
+            if (dm_) e_ = chain_ru_masked(e_, dabs(v), dm_);                                                       \
+        }                                                                                                          \
+        wsync();                                                                                                   \
+        (x).n = k_; (x).e = e_;                                                                                    \
+    } while (0)
+
+// Append to model r (begun at the arena top, still the top model) the terms of x for which KEEP_EXPR holds, in order, with
+// key KEY_EXPR and coefficient VAL_EXPR; the expressions see the source term as `a` (Key) and `v` (double).
+#define AB_FILTER_COPY(c, r, x, KEEP_EXPR, KEY_EXPR, VAL_EXPR)                                                     \
+    do {                                                                                                           \
+        const int W_ = AB_W, lane_ = (c).lane, n_ = (x).n; int k_ = (r).n;                                        \
+        wsync();                                                                                                   \
+        if (arena_room(c, (r).off, k_ + n_)) {                                                                     \
+            for (int i0_ = 0; i0_ < n_; i0_ += W_) {                                                               \
+                const int i_ = i0_ + lane_; const bool act_ = i_ < n_;                                             \
+                Key a = key_zero(); double v = 0.0; bool keep_ = false;                                            \
+                if (act_) { a = tm_key(c, x, i_); v = tm_val(c, x, i_); keep_ = (KEEP_EXPR); }                     \
+                const unsigned km_ = wballot(keep_);                                                               \
+                if (keep_) bput((c).A.base, (r).off + (k_ + popc32(km_ & lanemask_lt(lane_))) * AB_TW, (KEY_EXPR), (VAL_EXPR)); \
+                k_ += popc32(km_);                                                                                 \
+            }                                                                                                      \
+            wsync();                                                                                               \
+            (r).n = k_; (c).A.top = (r).off + k_ * AB_TW; arena_mark_peak(c);                                      \
+        }                                                                                                          \
+    } while (0)
+
 // sweep(m) src/taylor_model.cpp:972-989 -- in place; leaves the ambient mode UPWARD (sic).
 AB_HDN void tm_sweep(Ctx& c, TM& x, double m) { AB_FLOPS(x.n + 2);
-    int k = 0;
-    for (int i = 0; i < x.n; ++i) {
-        double v = tm_val(c, x, i);
-        if (dabs(v) >= m) { if (k != i) { tm_set_key(c, x, k, tm_key(c, x, i)); tm_set_val(c, x, k, v); } ++k; }
-        else x.e = add_ru(x.e, dabs(v));
-    }
-    x.n = k;
+    AB_FILTER_IN_PLACE(c, x, !(dabs(v) >= m));
     c.rnd = RU;
 }
 // clean(accuracy) src/taylor_model.cpp:895-913 -- in place
 AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) { AB_FLOPS(x.n + 2);
-    int k = 0;
-    for (int i = 0; i < x.n; ++i) {
-        Key a = tm_key(c, x, i); double v = tm_val(c, x, i);
-        if (acc_discard(acc, a, v)) x.e = add_ru(x.e, dabs(v));
-        else { if (k != i) { tm_set_key(c, x, k, a); tm_set_val(c, x, k, v); } ++k; }
-    }
-    x.n = k;
+    AB_FILTER_IN_PLACE(c, x, acc_discard(acc, a, v));
     c.rnd = RN;
+}
+// upward sum of the coefficient magnitudes of the terms of positive degree (all terms if with_constant), starting from s
+AB_HD double tm_abs_sum(Ctx& c, const TM& x, double s, bool with_constant, double* constant) {
+    const int W = AB_W, lane = c.lane, n = x.n;
+    double cv = 0.0;
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + lane; double g = 0.0;
+        if (i < n) { const double v = tm_val(c, x, i); if (!with_constant && key_deg(tm_key(c, x, i)) == 0) cv = v; else g = dabs(v); }
+        s = chain_ru(s, g, (n - i0 < W) ? n - i0 : W);
+        if (i0 == 0 && !with_constant) cv = wshfl(cv, 0);          // a constant term, if any, is the first term
+    }
+    if (constant) *constant = cv;
+    return s;
 }
 // range() = _range1 src/taylor_model.cpp:1566-1579
 AB_HDN Ivl tm_range(Ctx& c, const TM& x) { AB_FLOPS(x.n + 2); AB_CALL(7, x.n);
-    double t = x.e, v = 0.0;
-    for (int i = 0; i < x.n; ++i) {
-        if (key_deg(tm_key(c, x, i)) == 0) v = tm_val(c, x, i);
-        else t = add_ru(t, dabs(tm_val(c, x, i)));
-    }
+    double v = 0.0;
+    const double t = tm_abs_sum(c, x, x.e, false, &v);
     c.rnd = RN;
     return ivl(add_rd(-t, v), add_ru(t, v));
 }
 // norm() src/taylor_model.cpp:2592-2600
 AB_HDN double tm_norm(Ctx& c, const TM& x) { AB_FLOPS(x.n + 2);
-    double r = x.e;
-    for (int i = 0; i < x.n; ++i) r = add_ru(r, dabs(tm_val(c, x, i)));
+    const double r = tm_abs_sum(c, x, x.e, true, 0);
     c.rnd = RN;
     return r;
 }
@@ -711,50 +953,93 @@ AB_HD TM tm_embed(Ctx& c, const TM& x, int extra) { TM r = tm_copy(c, x); r.as =
 
 // antidifferentiate(k) src/taylor_model.cpp:2251-2284 -- in place
 AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) { AB_FLOPS(4 * x.n + 2);
+    const int W = AB_W, lane = c.lane, n = x.n;
+    wsync();
     double tre = 0;
-    for (int i = 0; i < x.n; ++i) {
-        Key a = tm_key(c, x, i);
-        double xv = tm_val(c, x, i), mxv = -xv, u, ml;
-        double cc = (double)(key_get(a, k) + 1);
-        if (xv >= 0) { u = div_ru(xv, cc); ml = div_ru(mxv, cc); }
-        else { u = div_ru(mxv, cc); ml = div_ru(xv, cc); }
-        tre = add_ru(tre, add_ru(u, ml));
-        key_inc(a, k, 1);
-        tm_set_key(c, x, i, a);
-        tm_set_val(c, x, i, div_rn(xv, cc));
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + lane; double g = 0.0;
+        if (i < n) {
+            Key a = tm_key(c, x, i);
+            double xv = tm_val(c, x, i), mxv = -xv, u, ml;
+            double cc = (double)(key_get(a, k) + 1);
+            if (xv >= 0) { u = div_ru(xv, cc); ml = div_ru(mxv, cc); }
+            else { u = div_ru(mxv, cc); ml = div_ru(xv, cc); }
+            g = add_ru(u, ml);
+            key_inc(a, k, 1);
+            tm_set_key(c, x, i, a);
+            tm_set_val(c, x, i, div_rn(xv, cc));
+        }
+        tre = chain_ru(tre, g, (n - i0 < W) ? n - i0 : W);
     }
+    wsync();
     x.e = add_ru(x.e, tre / 2);
     c.rnd = RN;
 }
 // intersection(x,y) src/taylor_model.cpp:2883-2954. Returns false (and leaves the ambient mode upward, as the
 // reference's throw does) when the models are disjoint; the caller then keeps y, as unchecked_flow does.
+// The union of the two key sets is built in the accumulator (x's coefficient in the entry, y's beside it); every key is
+// then treated independently, and the result error is a maximum, which does not depend on the order.
 AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
+    const int W = AB_W, lane = c.lane;
+    uint64_t* const base = c.A.base;
+    const int m = c.A.top;
     TM r = tm_begin(c, x.as, x.acc);
-    double tme = 0.0;
-    int i = 0, j = 0;
-    AB_FLOPS(1);
-    while (i < x.n || j < y.n) { AB_FLOPS(12);
-        Key a; double xv, yv;
-        if (i == x.n) { a = tm_key(c, y, j); yv = tm_val(c, y, j); xv = 0.0; ++j; }
-        else if (j == y.n) { a = tm_key(c, x, i); xv = tm_val(c, x, i); yv = 0.0; ++i; }
-        else {
-            Key xa = tm_key(c, x, i), ya = tm_key(c, y, j);
-            if (key_eq(xa, ya)) { a = xa; xv = tm_val(c, x, i); yv = tm_val(c, y, j); ++i; ++j; }
-            else if (key_less(xa, ya)) { a = xa; xv = tm_val(c, x, i); yv = 0.0; ++i; }
-            else { a = ya; yv = tm_val(c, y, j); xv = 0.0; ++j; }
+    AB_FLOPS(1 + 12 * (x.n + y.n));
+    const long long want = (long long)x.n + y.n;
+    int maxdeg = tm_degree(c, x); { const int d = tm_degree(c, y); if (d > maxdeg) maxdeg = d; }
+    const double xe = x.e, ye = y.e;
+    AccTab T;
+    bool disjoint = false; double tme = 0.0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // y's coefficients beside the entries: in the gap-code area (shared) or above the table (arena)
+        const long long yv_words = (attempt == 0 && c.sm) ? 0 : ((want < 64) ? 64 : want);
+        const int above = m + (int)want * AB_TW + (int)yv_words + 2;
+        if (!acc_open(c, T, attempt, above, want)) return false;
+        uint64_t* yval;
+        if (yv_words == 0) { if (T.cap > (AB_SM_WORDS - AB_SM_OFF_G16)) { T.overflow = true; continue; } yval = c.sm + AB_SM_OFF_G16; }
+        else { const long long at = ((long long)m + want * AB_TW + 1) & ~1LL; if (at + yv_words > c.A.limit) { fail(c, ST_ARENA); return false; } yval = base + at; }
+        for (int pass = 0; pass < 2 && !T.overflow; ++pass) {
+            const TM& t = pass ? y : x;
+            for (int j0 = 0; j0 < t.n; j0 += W) {
+                const int j = j0 + lane; const bool act = j < t.n;
+                Key k = key_zero(); double tv = 0.0;
+                if (act) { k = bkey(base, t.off + j * AB_TW); tv = bval(base, t.off + j * AB_TW); }
+                const int before = T.nd;
+                const int slot = acc_slot(T, act, k, lane);
+                if (T.overflow) break;
+                if (act) {
+                    if (pass == 0) { T.val[slot] = d2u(tv); yval[slot] = d2u(0.0); }
+                    else { if (slot >= before) T.val[slot] = d2u(0.0); yval[slot] = d2u(tv); }
+                }
+            }
+            wsync();
         }
-        double xu = add_ru(xv, x.e), yu = add_ru(yv, y.e), mxl = sub_ru(x.e, xv), myl = sub_ru(y.e, yv);
-        double u = dmin(xu, yu), ml = dmin(mxl, myl);
-        double s = add_ru(u, ml);
-        if (s < 0) { c.rnd = RU; c.A.top = r.off; return false; }
-        tme = dmax(tme, s);
-        xu = add_rn(xv, x.e); yu = add_rn(yv, y.e); mxl = sub_rn(x.e, xv); myl = sub_rn(y.e, yv);
-        u = dmin(xu, yu); ml = dmin(mxl, myl);
-        double rv = sub_rn(u, ml) / 2;
-        if (rv != 0.0) tm_append(c, r, a, rv);
-        c.rnd = RN;
+        if (T.overflow) { if (attempt == 1) { fail(c, ST_ARENA); return false; } continue; }
+        // per key: src/taylor_model.cpp:2905-2945
+        double lmax = 0.0; bool bad = false;
+        for (int s = lane; s < T.nd; s += W) {
+            const double xv = u2d(T.val[s]), yv = u2d(yval[s]);
+            double xu = add_ru(xv, xe), yu = add_ru(yv, ye), mxl = sub_ru(xe, xv), myl = sub_ru(ye, yv);
+            double u = dmin(xu, yu), ml = dmin(mxl, myl);
+            const double sg = add_ru(u, ml);
+            if (sg < 0) bad = true;
+            lmax = dmax(lmax, sg);
+            xu = add_rn(xv, xe); yu = add_rn(yv, ye); mxl = sub_rn(xe, xv); myl = sub_rn(ye, yv);
+            u = dmin(xu, yu); ml = dmin(mxl, myl);
+            const double rv = sub_rn(u, ml) / 2;
+            T.val[s] = (rv != 0.0) ? d2u(rv) : AB_ABSENT;
+        }
+        wsync();
+        disjoint = wany(bad);
+        for (int l = 0; l < W; ++l) tme = dmax(tme, wshfl(lmax, l));
+        break;
     }
+    if (disjoint) { c.rnd = RU; c.A.top = r.off; return false; }
+    r.n = acc_emit(c, T, x.as, maxdeg, m);
+    c.A.top = m + r.n * AB_TW;
+    arena_mark_peak(c);
     r.e = tme / 2;
+    c.rnd = RN;
     out = r;
     return true;
 }

@@ -66,7 +66,7 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
     std::vector<double> rb(MAXB * 2 * AB_MAXN), fb(MAXB * 2 * AB_MAXN); std::vector<int32_t> rl(MAXB), fl(MAXB);
     std::vector<uint64_t> rkeys, fkeys;
     for (uint64_t ci = 0; ci < n_cells; ++ci) {
-        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
         EvolveParams P; P.lower = 0; P.backward = direction ? 1 : 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
@@ -107,7 +107,7 @@ extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const 
     ab200_boxlist* R = new ab200_boxlist(); ab200_boxlist* F = new ab200_boxlist();
     R->offsets.push_back(0); F->offsets.push_back(0);
     for (uint64_t ci = 0; ci < n_cells; ++ci) {
-        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
         EvolveParams P; P.lower = ctx->settings.semantics; P.backward = 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);

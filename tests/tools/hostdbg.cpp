@@ -12,6 +12,10 @@
 #include <fstream>
 #include <sstream>
 #include <map>
+#ifndef AB_NO_EMU
+#define AB_WARP_EMU 1
+#include "warp_emu.h"
+#endif
 #include "../../release-1.0_b200/csrc/ab200_evolve.cuh"
 #include "../../release-1.0_b200/csrc/ab200_system.h"
 #include "../../release-1.0_b200/csrc/ab200_paving.h"
@@ -76,11 +80,27 @@ int main(int argc, char** argv) {
     int bad = 0, done = 0; long total_steps = 0; int peak = 0;
     for (size_t ci = 0; ci < cells.size() && (int)ci < maxcells; ++ci) {
         RefCell& rc = cells[ci];
-        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = ARENA; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
         EvolveParams P; P.lower = lower_sem; P.backward = backward_dir; P.T = T; P.max_events = chain ? 1 : events; P.ignore_activations = ignore_act; P.max_boxes = MAXB; P.temporal_order = 6;
         P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = reach.data(); O.reach_loc = rloc.data(); O.n_reach = 0; O.final_ = fin.data(); O.final_loc = floc.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        Ctx c;
+#ifndef AB_NO_EMU
+        {   // one fiber per lane; every lane holds the same (warp-uniform) state, lane 0's copy is reported
+            static std::vector<uint64_t> smem(AB_SM_WORDS);
+            const int lanes = getenv("AB_EMU_W") ? atoi(getenv("AB_EMU_W")) : 32;
+            CellOutput O0 = O; Ctx c0;
+            wemu::run(lanes, [&](int lane) {
+                Ctx cl; ctx_init(cl, arena.data(), ARENA, getenv("AB_EMU_NOSM") ? 0 : smem.data(), binom_host());
+                CellOutput Ol = O;
+                evolve_cell(cl, hs.desc, rc.loc, rc.box.data(), P, Ol);
+                if (lane == 0) { O0 = Ol; c0 = cl; }
+            });
+            O = O0; c = c0;
+        }
+#else
+        ctx_init_host(c, arena.data(), ARENA);
         evolve_cell(c, hs.desc, rc.loc, rc.box.data(), P, O);
+#endif
         total_steps += O.steps; if (c.A.peak > peak) peak = c.A.peak;
         ++done;
         int n = hs.desc.loc[rc.loc].n;

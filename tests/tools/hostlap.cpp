@@ -29,7 +29,7 @@ static void host_lap(const CellSet& frontier, int mince, double T, int events, C
     std::vector<double> rb(MAXB * 2 * AB_MAXN), fb(MAXB * 2 * AB_MAXN); std::vector<int32_t> rl(MAXB), fl(MAXB);
     std::vector<uint64_t> rkeys, fkeys;
     for (size_t ci = 0; ci < cells.size(); ++ci) {
-        Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = (int)arena.size(); c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+        Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
         EvolveParams P; P.lower = 0; P.backward = 0; P.T = T; P.max_events = events; P.ignore_activations = 0; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         evolve_cell(c, hs.desc, 0, cells[ci].b, P, O);

@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
     static HostSystem hs; std::string err = parse_system(ss.str(), hs); if (!err.empty()) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
     const LocDesc& L = hs.desc.loc[0]; int n = L.n;
     std::vector<uint64_t> arena(1 << 20);
-    Ctx c; c.A.base = arena.data(); c.A.top = 0; c.A.limit = 1 << 20; c.A.peak = 0; c.rnd = RN; c.status = ST_OK;
+    Ctx c; ctx_init_host(c, arena.data(), 1 << 20);
     Acc spacial; spacial.sweep = 1e-12; spacial.maxdeg = 6;
     TM set[AB_MAXN];
     for (int i = 0; i < n; ++i) { set[i] = tm_scaling(c, n, i, ivl(strtod(argv[2 + 2 * i], 0), strtod(argv[3 + 2 * i], 0))); set[i].acc = spacial; }
