@@ -57,7 +57,10 @@ typedef struct ab200_settings {
     double  ttl_seconds;                /* Interruptible::ttl; <=0 disables */
     int32_t semantics;                  /* 0 = UPPER_SEMANTICS (default), 1 = LOWER_SEMANTICS: the Semantics argument of
                                            EvolverInterface::reach_evolve / orbit (include/evolver_interface.h:46-49,114-124) */
-    int32_t reserved;
+    int32_t max_working_sets;           /* ImageSetHybridEvolverSettings::maximum_number_of_working_sets
+                                           (src/hybrid_evolver-image.cpp:280,1358). The reference default 0 means unlimited; here 0
+                                           means the device default of 64 pending sets per cell, and the largest accepted value
+                                           is 256 (the handles live in the cell's arena). AB200_E_WORKING_SETS beyond it. */
 } ab200_settings;
 
 typedef struct ab200_status {

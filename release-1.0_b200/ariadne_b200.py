@@ -42,7 +42,7 @@ class Settings(C.Structure):
     _fields_ = [("temporal_order", C.c_int32), ("spacial_order", C.c_int32), ("sweep_threshold", C.c_double),
                 ("maximum_enclosure_widths_ratio", C.c_double), ("max_boxes", C.c_int32), ("arena_words", C.c_int32),
                 ("hash_log2", C.c_int32), ("batch_cells", C.c_int32), ("ttl_seconds", C.c_double),
-                ("semantics", C.c_int32), ("reserved", C.c_int32)]
+                ("semantics", C.c_int32), ("max_working_sets", C.c_int32)]
 
 
 class Status(C.Structure):

@@ -78,6 +78,7 @@ struct SystemDesc {
 AB_HDN Ivl eval_ivl(Ctx& c, const TapeOp* ops, Func f, const Ivl* x) {
     Ivl st[AB_STACK];
     int sp = 0;
+    #pragma unroll 1
     for (int p = f.begin; p < f.end; ++p) {
         const TapeOp o = ops[p];
         if (o.op != OP_CNST && o.op != OP_VAR && o.op != OP_POS && o.op != OP_NEG) AB_FLOPS(o.op == OP_MUL ? 4 : 2);
@@ -105,6 +106,7 @@ AB_HDN Ivl eval_ivl(Ctx& c, const TapeOp* ops, Func f, const Ivl* x) {
 // ---- vectors of models ------------------------------------------------------------------------------------------
 // Slide models v[0..m) (stored in ascending arena order) down to dst, packed; sets the arena top.
 AB_HD void vec_slide(Ctx& c, TM* v, int m, int dst) {
+    #pragma unroll 1
     for (int i = 0; i < m; ++i) { tm_slide(c, v[i], dst); dst = c.A.top; }
     c.A.top = dst;
 }
@@ -122,6 +124,7 @@ AB_HDN TM eval_tm(Ctx& c, const TapeOp* ops, Func f, const TM* x) {
     TmSlot st[AB_STACK];
     int sp = 0;
     int m0 = c.A.top;
+    #pragma unroll 1
     for (int p = f.begin; p < f.end; ++p) {
         const TapeOp o = ops[p];
         if (o.op == OP_CNST) {
@@ -190,21 +193,30 @@ AB_HDN double flow_bounds(Ctx& c, const TapeOp* ops, const Func* vf, int n, cons
     const int EXPANSION_STEPS = 8, REDUCTION_STEPS = 16, REFINEMENT_STEPS = 8;
     const double EPS = 1e-16;
     Ivl d[AB_MAXN], delta[AB_MAXN], b[AB_MAXN], nb[AB_MAXN], df[AB_MAXN], dd[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) { d[i] = r[i]; if (d[i].l == d[i].u) d[i] = ivl_add(d[i], ivl(-EPS, EPS)); }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) delta[i] = ivl_mul(ivl_sub(d[i], ivl_mid(d[i])), BOX_RADIUS_MULTIPLIER - 1);
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) dd[i] = ivl_add(d[i], delta[i]);
     double hmin = hmax / (1 << REDUCTION_STEPS);
     double h = hmax;
     bool success = false;
     Ivl ih = ivl(0, h);
+    #pragma unroll 1
     while (!success) {
         if (!(h > hmin)) { fail(c, ST_BOUNDER); return h; }
         Ivl m2 = ivl_mul(ih, INITIAL_MULTIPLIER);
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) df[i] = eval_ivl(c, ops, vf[i], d);
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) b[i] = ivl_add(ivl_add(d[i], ivl_mul(m2, df[i])), delta[i]);
+        #pragma unroll 1
         for (int s = 0; s < EXPANSION_STEPS; ++s) {
+            #pragma unroll 1
             for (int i = 0; i < n; ++i) df[i] = eval_ivl(c, ops, vf[i], b);
             bool bounded = true, sub = true;
+            #pragma unroll 1
             for (int i = 0; i < n; ++i) {
                 nb[i] = ivl_add(dd[i], ivl_mul(ih, df[i]));
                 if (!(dabs(nb[i].l) <= DBL_MAX && dabs(nb[i].u) <= DBL_MAX)) bounded = false;
@@ -214,20 +226,26 @@ AB_HDN double flow_bounds(Ctx& c, const TapeOp* ops, const Func* vf, int n, cons
             else if (sub) { success = true; break; }
             else {
                 Ivl mi = ivl_mul(ih, MULTIPLIER);
+                #pragma unroll 1
                 for (int i = 0; i < n; ++i) b[i] = ivl_add(dd[i], ivl_mul(mi, df[i]));
             }
         }
         if (!success) { h /= 2; ih = ivl(0, h); }
         if (c.status != ST_OK) return h;
     }
+    #pragma unroll 1
     for (int s = 0; s < REFINEMENT_STEPS; ++s) {
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) b[i] = nb[i];
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) df[i] = eval_ivl(c, ops, vf[i], b);
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) {
             nb[i] = ivl_add(dd[i], ivl_mul(ih, df[i]));
             if (!ivl_subset(nb[i], b[i])) fail(c, ST_BOUNDER);
         }
     }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) { bout[i] = nb[i]; if (!ivl_subset(d[i], nb[i])) fail(c, ST_BOUNDER); }
     return h;
 }
@@ -243,6 +261,66 @@ AB_HD TM ph_load(Ctx& c, int slot, int as, Acc acc) {
     TM t; uint64_t w = aw(c, slot); t.off = (int)(w >> 32); t.n = (int)(w & 0xFFFFFFFFu); t.e = u2d(aw(c, slot + 1)); t.as = as; t.acc = acc; return t;
 }
 
+// {cv} * p with accuracy acc, where {cv} is the constant model of a nonzero coefficient (error 0) and p has at least one
+// term: _mul4 (src/taylor_model.cpp:763-824) with a one-term left factor, i.e. one stream -- every term of p scaled
+// (nearest), products below the sweep threshold or above the degree limit dropped into the truncation error
+// tte (upward, in term order), error = up(tte+tte/2) + |cv|*p.e (the other cross terms vanish with the factor's error).
+// Result at the arena top.
+AB_HDN TM term_times_power(Ctx& c, double cv, const TM& p, Acc acc) {
+    const int W = AB_W, lane = c.lane, n = p.n, m = c.A.top, soff = p.off;
+    uint64_t* const base = c.A.base;
+    TM r; r.off = m; r.n = 0; r.as = p.as; r.e = 0.0; r.acc = acc;
+    if (!arena_room(c, m, n)) return r;
+    const double sweep = acc.sweep, acv = dabs(cv); const int maxdeg = acc.maxdeg;
+    wsync();
+    double tte = 0.0; int rn = 0;
+    #pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += W) {
+        const int j = j0 + lane; const bool act = j < n;
+        Key ta = key_zero(); double sv = 0.0, tv = 0.0; bool disc = false;
+        if (act) { const int w = soff + j * AB_TW; sv = bval(base, w); ta = bkey(base, w); tv = mul_rn(cv, sv); disc = dabs(tv) < sweep || key_deg(ta) > maxdeg; }
+        const unsigned dm = wballot(disc), km = wballot(act && !disc);
+        if (act && !disc) bput(base, m + (rn + popc32(km & lanemask_lt(lane))) * AB_TW, ta, tv);
+        rn += popc32(km);
+        if (dm) tte = chain_ru_masked(tte, mul_ru(acv, dabs(sv)), dm);
+    }
+    wsync();
+    r.n = rn;
+    r.e = add_ru(add_ru(tte, tte / 2), mul_ru(acv, p.e));
+    c.rnd = RN;
+    c.A.top = m + rn * AB_TW;
+    arena_mark_peak(c);
+    return r;
+}
+// t <- t * q with accuracy acc for a one-term q and t the top model on the arena (at least one term), in place: _mul4 with
+// a one-term right factor -- every x-term is its own stream {x_i*q}, a dropped product adds up(tte_i+tte_i/2) to the error
+// chain in x order, and the cross terms use the norm of t (needed only when q carries an error).
+AB_HDN void term_times_monomial(Ctx& c, TM& t, const TM& q, Acc acc) {
+    const int W = AB_W, lane = c.lane, n = t.n, off = t.off;
+    uint64_t* const base = c.A.base;
+    const Key qa = bkey(base, q.off); const double qv = bval(base, q.off), aqv = dabs(qv), qe = q.e, te0 = t.e;
+    const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
+    wsync();
+    double e = 0.0, norm = 0.0; int rn = 0;
+    #pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + lane; const bool act = i < n;
+        Key ta = key_zero(); double xv = 0.0, tv = 0.0; bool disc = false;
+        if (act) { const int w = off + i * AB_TW; xv = bval(base, w); ta = key_add(bkey(base, w), qa); tv = mul_rn(xv, qv); disc = dabs(tv) < sweep || key_deg(ta) > maxdeg; }
+        const unsigned dm = wballot(disc), km = wballot(act && !disc);
+        wsync();          // the chunk has been read by every lane before it is compacted over
+        if (act && !disc) bput(base, off + (rn + popc32(km & lanemask_lt(lane))) * AB_TW, ta, tv);
+        rn += popc32(km);
+        if (dm) { const double t1 = mul_ru(dabs(xv), aqv); e = chain_ru_masked(e, add_ru(t1, t1 / 2), dm); }
+        if (qe != 0.0) norm = chain_ru(norm, act ? dabs(xv) : 0.0, (n - i0 < W) ? n - i0 : W);
+    }
+    wsync();
+    t.n = rn; t.acc = acc;
+    t.e = add_ru(e, add_ru(add_ru(mul_ru(norm, qe), mul_ru(aqv, te0)), mul_ru(te0, qe)));
+    c.rnd = RN;
+    c.A.top = off + rn * AB_TW;
+}
+
 // _compose2 (src/taylor_model.cpp:3187-3240): r[i] = x[i] o ys, nx models in xas=nys variables.
 // Results are written to r[0..nx) packed from the arena top recorded on entry.
 AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r) {
@@ -254,23 +332,30 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     {   // largest exponent of every variable: per-byte maximum of the key words, lanes over terms, then across the lanes
         const int W = AB_W, lane = c.lane;
         uint64_t mx[AB_KW]; for (int w = 0; w < AB_KW; ++w) mx[w] = 0;
+        #pragma unroll 1
         for (int i = 0; i < nx; ++i)
+            #pragma unroll 1
             for (int t = lane; t < x[i].n; t += W) { Key a = tm_key(c, x[i], t); for (int w = 0; w < AB_KW; ++w) mx[w] = bytes_max(mx[w], a.w[w]); }
+        #pragma unroll 1
         for (int d = 1; d < W; d <<= 1) for (int w = 0; w < AB_KW; ++w) mx[w] = bytes_max(mx[w], wshfl(mx[w], lane ^ d));
         Key km; for (int w = 0; w < AB_KW; ++w) km.w[w] = mx[w];
+        #pragma unroll 1
         for (int j = 0; j < nys; ++j) { const int e = key_get(km, j); maxp[j] = e > 1 ? e : 1; }
     }
     // handle table
     int tab[AB_MAXARGS + 1];
     int slot = m0;
+    #pragma unroll 1
     for (int j = 0; j < nys; ++j) { tab[j] = slot; slot += 2 * (maxp[j] + 1); if (maxp[j] >= AB_MAXPOW) fail(c, ST_ARENA); }
     if (slot > c.A.limit) { fail(c, ST_ARENA); for (int i = 0; i < nx; ++i) r[i] = tm_begin(c, as, acc0); return; }
     c.A.top = slot;
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+    #pragma unroll 1
     for (int j = 0; j < nys; ++j) {
         TM p0 = tm_copy(c, ys[j]); tm_scal(c, p0, 0.0); c.A.top = p0.off;       // powers[j][0]=ys[j]*0
         ph_store(c, tab[j], p0);
         ph_store(c, tab[j] + 2, ys[j]);                                          // powers[j][1]=ys[j]
+        #pragma unroll 1
         for (int k = 2; k <= maxp[j]; ++k) {
             TM a = ph_load(c, tab[j] + 2 * (k / 2), as, ys[j].acc);
             TM b = ph_load(c, tab[j] + 2 * ((k + 1) / 2), as, ys[j].acc);
@@ -279,28 +364,46 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
         }
     }
     const int mr = c.A.top;     // results start here; slid down to m0 at the end
+#ifdef AB_COMPOSE_STATS
+    if (c.lane == 0) { extern long long g_cs[8]; g_cs[0]++; for (int i = 0; i < nx; ++i) g_cs[1] += x[i].n; }
+#endif
+    #pragma unroll 1
     for (int i = 0; i < nx; ++i) {
         const int ri = c.A.top;
         TM ra = tm_begin(c, as, acc0);
         ra.e = x[i].e;
+        #pragma unroll 1
         for (int t0 = 0; t0 < x[i].n; t0 += AB_MAXSTREAMS) {
             const int B = (x[i].n - t0 < AB_MAXSTREAMS) ? (x[i].n - t0) : AB_MAXSTREAMS;
             TM st[AB_MAXSTREAMS];
             c.A.top = ra.off + ra.n * AB_TW;
+            #pragma unroll 1
             for (int b = 0; b < B; ++b) {
                 const int t = t0 + b;
-                Key a = tm_key(c, x[i], t);
-                double cv = tm_val(c, x[i], t);
-                TM tt = tm_const(c, as, cv, acc0);           // t=c
+                const Key a = tm_key(c, x[i], t);
+                const double cv = tm_val(c, x[i], t);
+                // t=c; t=t*powers[j][e] for every variable with a positive exponent. The first product scales a power by the
+                // coefficient, and a product with a one-term power (powers of the time variable) only shifts and scales the
+                // terms: both are done without building the constant model or leaving a copy behind (same arithmetic as
+                // _mul4 on those operands, see term_times_power / term_times_monomial).
+                TM tt; bool started = false;
+                if (cv == 0.0) { tt = tm_const(c, as, cv, acc0); started = true; }
+                #pragma unroll 1
                 for (int j = 0; j < nys; ++j) {
-                    int e = key_get(a, j);
-                    if (e > 0) {
-                        // t=t*powers[j][e]; the factor just consumed stays below as dead space until the slide
-                        // after tm_add_many reclaims the whole batch (cheaper than moving every product down)
-                        TM pw = ph_load(c, tab[j] + 2 * e, as, ys[j].acc);
-                        tt = tm_mul(c, tt, pw, ys[j].acc);
-                    }
+                    const int e = key_get(a, j);
+                    if (e == 0) continue;
+                    const TM pw = ph_load(c, tab[j] + 2 * e, as, ys[j].acc);
+#ifdef AB_COMPOSE_STATS
+                    if (c.lane == 0) { extern long long g_cs[8]; g_cs[2]++; g_cs[3] += (long long)(started ? tt.n : 1) * pw.n; if (!started || tt.n <= 1 || pw.n <= 1) g_cs[4]++; }
+#endif
+                    if (!started) {
+                        if (pw.n == 0) { tt = tm_const(c, as, cv, acc0); tt = tm_mul(c, tt, pw, ys[j].acc); }
+                        else tt = term_times_power(c, cv, pw, ys[j].acc);
+                        started = true;
+                    } else if (pw.n == 1 && tt.n >= 1 && tm_end(tt) == c.A.top) term_times_monomial(c, tt, pw, ys[j].acc);
+                    else tt = tm_mul(c, tt, pw, ys[j].acc);      // the factor just consumed stays below as dead space until the slide
                 }
+                if (!started) tt = tm_const(c, as, cv, acc0);
                 c.A.top = tt.off + tt.n * AB_TW;
                 st[b] = tt;
             }
@@ -335,6 +438,7 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     int boff[AB_MAXPOW], bn[AB_MAXPOW];
     const int md = c.rnd;
     long long want = 0;
+    #pragma unroll 1
     for (int b = 0; b <= deg; ++b) {
         boff[b] = c.A.top;
         TM bt = tm_begin(c, tm.as, acc_default());
@@ -351,6 +455,7 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     const int sums_end = mr + 2 * npair;
     if (sums_end > c.A.peak) c.A.peak = sums_end;
     AccTab T;
+    #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!acc_open(c, T, attempt, sums_end + (int)want * AB_TW, want)) return res;
         // gap codes of one bucket: one 32-bit cell per (i, term): low half scaling gap, high half coincidence gap
@@ -362,13 +467,16 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
             G = (uint32_t*)(base + at); gcap = mx;
         }
         bool badgap = false;
+        #pragma unroll 1
         for (int j = 0; j <= deg && !T.overflow; ++j) {
             const int nb = bn[j];
             if (nb == 0) continue;
             int ib = gcap / nb; if (ib < 1) { fail(c, ST_ARENA); return res; }
+            #pragma unroll 1
             for (int ia = 0; ia <= j && !T.overflow; ia += ib) {
                 const int ni = (j + 1 - ia < ib) ? (j + 1 - ia) : ib;
                 const int nitems = ni * nb;
+                #pragma unroll 1
                 for (int w0 = 0; w0 < nitems; w0 += W) {
                     const int w = w0 + lane; const bool act = w < nitems;
                     Key key = key_zero(); double tv = 0.0, gs = 0.0;
@@ -394,9 +502,11 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
                 }
                 wsync();
                 if (T.overflow) break;
+                #pragma unroll 1
                 for (int ii = lane; ii < ni; ii += W) {
                     double ts = 0.0, te = 0.0;
                     const uint32_t* row = G + ii * nb;
+                    #pragma unroll 1
                     for (int q = 0; q < nb; ++q) { const uint32_t cd = row[q]; if (cd & 0xFFFFu) ts = add_ru(ts, gap_value(cd & 0xFFFFu)); if (cd >> 16) te = add_ru(te, gap_value(cd >> 16)); }
                     TS[(ia + ii) * (deg + 1) + j] = ts; TE[(ia + ii) * (deg + 1) + j] = te;
                 }
@@ -409,7 +519,9 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     }
     // error chain in the reference's stream order; an empty bucket contributes nothing
     double e = tm.e;
+    #pragma unroll 1
     for (int i = 0; i <= deg; ++i)
+        #pragma unroll 1
         for (int j = i; j <= deg; ++j) {
             if (bn[j] == 0) continue;
             const double ts = TS[i * (deg + 1) + j], te = TE[i * (deg + 1) + j];
@@ -431,6 +543,7 @@ AB_HDN TM tm_partial_evaluate_one(Ctx& c, const TM& x, int k) {
     const int deg = tm_degree(c, x);
     int boff[AB_MAXPOW], bn[AB_MAXPOW];
     if (deg + 1 > AB_MAXPOW) { fail(c, ST_ARENA); return tm_begin(c, x.as - 1, x.acc); }
+    #pragma unroll 1
     for (int b = 0; b <= deg; ++b) {
         boff[b] = c.A.top;
         TM bt = tm_begin(c, x.as - 1, x.acc);
@@ -441,6 +554,7 @@ AB_HDN TM tm_partial_evaluate_one(Ctx& c, const TM& x, int k) {
     TM r; r.off = boff[0]; r.n = bn[0]; r.as = x.as - 1; r.e = x.e; r.acc = x.acc;
     r = tm_copy(c, r);
     r.e = x.e;
+    #pragma unroll 1
     for (int b = 1; b <= deg; ++b) {
         TM pb; pb.off = boff[b]; pb.n = bn[b]; pb.as = x.as - 1; pb.e = 0.0; pb.acc = x.acc;
         TM s = tm_add2(c, r, pb, x.acc);
@@ -461,21 +575,27 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
     const int m0 = c.A.top;
     const double EPS = 1e-16;
     Ivl bx[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) { bx[i] = ibx[i]; if (bx[i].l == bx[i].u) bx[i] = ivl_add(bx[i], ivl(-EPS, EPS)); }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) dom[i] = bx[i];
     dom[n] = ivl(0.0, h);
     TM xs[AB_MAXN], usvf[AB_MAXN], yz[AB_MAXN], y[AB_MAXN], ny[AB_MAXN], outs[AB_MAXN];
     // vector-field model on bb: tape over scalings(bb), effectively at the default accuracy
+    #pragma unroll 1
     for (int j = 0; j < n; ++j) xs[j] = tm_scaling(c, n, j, bb[j]);
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         usvf[i] = eval_tm(c, ops, vf[i], xs);
         // unit_scaled_vf[i]=vf[i]*(hmag/rad_ivl(b[i]))
         tm_scal(c, usvf[i], ivl_div(h, rad_ivl(bb[i]), &c.status));
     }
     vec_slide(c, usvf, n, m0);
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) AB_DUMP(c, "usvf", i, usvf[i]);
     if (c.status != ST_OK) { for (int i = 0; i < n; ++i) flow[i] = tm_begin(c, n + 1, acc_default()); return; }
     // y0=scalings(d); unit_scaled_y0=embed(unscale(y0,b),1)
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         int m = c.A.top;
         TM y0 = tm_scaling(c, n, i, bx[i]);
@@ -484,18 +604,23 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
         u.as = n + 1;
         yz[i] = u;
     }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) AB_DUMP(c, "yz", i, yz[i]);
     // model-level flow: y[i]=constant(n+1, yz[i].range()+vf[i].range()*[-1,1])
     const int ybase = c.A.top;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         Ivl rg = ivl_add(tm_range(c, yz[i]), ivl_mul(tm_range(c, usvf[i]), ivl(-1, 1)));
         y[i] = tm_const(c, n + 1, 1.0, acc_default());
         tm_scal(c, y[i], rg);
     }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) AB_DUMP(c, "y0", i, y[i]);
+    #pragma unroll 1
     for (int it = 0; it < order; ++it) {
         tm_compose(c, usvf, n, y, n, ny);                 // new_y=compose(vf,y)
         int pout = c.A.top;
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) {
             c.A.top = pout;
             TM w = tm_copy(c, ny[i]);
@@ -508,14 +633,18 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
             outs[i] = out;
         }
         // new_y[i].swap(y[i]) swaps expansion and error only: y[i] keeps its own accuracy
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) { Acc a = y[i].acc; y[i] = outs[i]; y[i].acc = a; }
         vec_slide(c, y, n, ybase);
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) AB_DUMP(c, "y", (it + 1) * 10 + i, y[i]);
         if (c.status != ST_OK) break;
     }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) tm_sweep(c, y[i], 0.0);   // leaves the ambient mode upward
     // model_flow=scale(unit_scaled_flow,b); then split(model_flow,n,true) because the time interval is [0,h]
     int pout = c.A.top;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         c.A.top = pout;
         TM r = tm_copy(c, y[i]);
@@ -536,6 +665,7 @@ AB_HDN void flow_apply(Ctx& c, const TM* flow, int n, const Ivl* dom, const TM* 
     AB_SECTION(4);
     const int m0 = c.A.top;
     TM ys[AB_MAXN + 1];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         TM e = set[i]; e.as = p + 1;                       // embed(x1,1)
         ys[i] = tm_unscale(c, e, dom[i]);
@@ -548,6 +678,7 @@ AB_HDN void flow_apply(Ctx& c, const TM* flow, int n, const Ivl* dom, const TM* 
         ys[n] = u;
     }
     TM fl[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) { fl[i] = flow[i]; fl[i].as = n + 1; }
     tm_compose(c, fl, n, ys, n + 1, out);
     vec_slide(c, out, n, m0);
@@ -567,10 +698,12 @@ AB_HDN void integration_step(Ctx& c, const TM* flow_set, int n, int p, const TM&
     AB_SECTION(5);
     const int m0 = c.A.top;
     TM ys[AB_MAXARGS + 1];
+    #pragma unroll 1
     for (int j = 0; j < p; ++j) ys[j] = tm_variable(c, p, j);      // BaseModelType::variables(p): default accuracy
     ys[p] = tau;
     tm_compose(c, flow_set, n, ys, p + 1, out);
     vec_slide(c, out, n, m0);
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) out[i].acc = spacial;
 }
 
@@ -579,6 +712,7 @@ AB_HDN void reachability_step(Ctx& c, const TM* flow_set, int n, int p, const TM
     AB_SECTION(6);
     const int m0 = c.A.top;
     TM ys[AB_MAXARGS + 1];
+    #pragma unroll 1
     for (int j = 0; j <= p; ++j) { ys[j] = tm_variable(c, p + 1, j); ys[j].acc = spacial; }
     TM e0 = t0; e0.as = p + 1;                                     // embed(t0,1)
     TM e1 = t1; e1.as = p + 1;
@@ -594,6 +728,7 @@ AB_HDN void reachability_step(Ctx& c, const TM* flow_set, int n, int p, const TM
     ys[p] = s;
     tm_compose(c, flow_set, n, ys, p + 1, out);
     vec_slide(c, out, n, m0);
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) out[i].acc = spacial;
 }
 
@@ -601,13 +736,16 @@ AB_HDN void reachability_step(Ctx& c, const TM* flow_set, int n, int p, const TM
 // recorded on entry. Returns the new number of parameters.
 AB_HDN int uniform_error_recondition(Ctx& c, TM* set, int n, int p, const double* thresholds) {
     int idx[AB_MAXN], k = 0;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) if (set[i].e > thresholds[i]) idx[k++] = i;
     if (k == 0) return p;
     const int m0 = c.A.top;
     const int np = p + k;
     TM out[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         int which = -1;
+        #pragma unroll 1
         for (int q = 0; q < k; ++q) if (idx[q] == i) which = q;
         if (which < 0) { out[i] = tm_copy(c, set[i]); out[i].as = np; continue; }
         int m = c.A.top;
@@ -619,6 +757,7 @@ AB_HDN int uniform_error_recondition(Ctx& c, TM* set, int n, int p, const double
         tm_slide(c, s, m);
         out[i] = s;
     }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) set[i] = out[i];
     (void)m0;
     return np;
@@ -628,11 +767,14 @@ AB_HDN int uniform_error_recondition(Ctx& c, TM* set, int n, int p, const double
 AB_HDN TM tm_recondition(Ctx& c, const TM& tm, const int* discarded, int nd, int n_err, int index_of_error) {
     const int nv = tm.as, nk = nv - nd;
     int kept[AB_MAXARGS + 1], kk = 0;
+    #pragma unroll 1
     for (int j = 0; j < nv; ++j) { bool dsc = false; for (int q = 0; q < nd; ++q) if (discarded[q] == j) dsc = true; if (!dsc) kept[kk++] = j; }
     double error = tm.e;
     // pass 1 (reference iterates the terms in REVERSE order): accumulate discarded magnitudes in the ambient mode
+    #pragma unroll 1
     for (int i = tm.n - 1; i >= 0; --i) {
         Key a = tm_key(c, tm, i);
+        #pragma unroll 1
         for (int q = 0; q < nd; ++q) if (key_get(a, discarded[q]) != 0) { error = add_m(c.rnd, error, dabs(tm_val(c, tm, i))); break; }
     }
     TM r = tm_begin(c, nk + n_err, tm.acc);
@@ -641,18 +783,23 @@ AB_HDN TM tm_recondition(Ctx& c, const TM& tm, const int* discarded, int nd, int
     Key ra_error = key_zero();
     if (n_err != index_of_error) key_inc(ra_error, nk + index_of_error, 1);
     int last_kept = -1;
+    #pragma unroll 1
     for (int i = 0; i < tm.n; ++i) {
         Key a = tm_key(c, tm, i);
         bool keep = true;
+        #pragma unroll 1
         for (int q = 0; q < nd; ++q) if (key_get(a, discarded[q]) != 0) { keep = false; break; }
         if (keep) last_kept = i;
     }
+    #pragma unroll 1
     for (int i = 0; i < tm.n; ++i) {
         Key a = tm_key(c, tm, i);
         bool keep = true;
+        #pragma unroll 1
         for (int q = 0; q < nd; ++q) if (key_get(a, discarded[q]) != 0) { keep = false; break; }
         if (!keep) continue;
         Key ra = key_zero();
+        #pragma unroll 1
         for (int q = 0; q < nk; ++q) { int e = key_get(a, kept[q]); if (e) key_inc(ra, q, e); }
         if (!added && key_deg(ra) > 1 && n_err != index_of_error) { tm_append(c, r, ra_error, error); added = true; }
         tm_append(c, r, ra, tm_val(c, tm, i));
@@ -669,24 +816,35 @@ AB_HDN int kuhn_recondition(Ctx& c, TM* set, int n, int p, int* discarded) {
     if (p <= n_kept) return 0;
     const int nd = p - n_kept;
     double dep[AB_MAXN][AB_MAXARGS + 1];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) for (int j = 0; j < p; ++j) dep[i][j] = 0.0;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i)
+        #pragma unroll 1
         for (int t = 0; t < set[i].n; ++t) {
             Key a = tm_key(c, set[i], t); double av = dabs(tm_val(c, set[i], t));
+            #pragma unroll 1
             for (int j = 0; j < p; ++j) if (key_get(a, j) != 0) dep[i][j] = add_m(c.rnd, dep[i][j], av);
         }
     double cm[AB_MAXARGS + 1]; int ci[AB_MAXARGS + 1];
+    #pragma unroll 1
     for (int j = 0; j < p; ++j) { cm[j] = 0.0; ci[j] = j; for (int i = 0; i < n; ++i) cm[j] = dmax(cm[j], dep[i][j]); }
     // std::sort(..., std::greater<Pair<double,uint>>): descending by (value, index)
+    #pragma unroll 1
     for (int a = 1; a < p; ++a) {
         double v = cm[a]; int id = ci[a]; int b = a - 1;
+        #pragma unroll 1
         while (b >= 0 && (cm[b] < v || (cm[b] == v && ci[b] < id))) { cm[b + 1] = cm[b]; ci[b + 1] = ci[b]; --b; }
         cm[b + 1] = v; ci[b + 1] = id;
     }
+    #pragma unroll 1
     for (int j = 0; j < nd; ++j) discarded[j] = ci[n_kept + j];
+    #pragma unroll 1
     for (int a = 1; a < nd; ++a) { int v = discarded[a], b = a - 1; while (b >= 0 && discarded[b] > v) { discarded[b + 1] = discarded[b]; --b; } discarded[b + 1] = v; }
     TM out[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) out[i] = tm_recondition(c, set[i], discarded, nd, n_err, i);
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) set[i] = out[i];
     return nd;
 }

@@ -89,7 +89,7 @@ struct ab200_ctx {
 
 extern "C" void ab200_default_settings(ab200_settings* s) {
     s->temporal_order = 6; s->spacial_order = 6; s->sweep_threshold = 1e-12; s->maximum_enclosure_widths_ratio = 5.0;
-    s->max_boxes = 192; s->arena_words = 32768; s->hash_log2 = 24; s->batch_cells = 1 << 17; s->ttl_seconds = 0.0; s->semantics = 0; s->reserved = 0;
+    s->max_boxes = 192; s->arena_words = 32768; s->hash_log2 = 24; s->batch_cells = 1 << 17; s->ttl_seconds = 0.0; s->semantics = 0; s->max_working_sets = 0;
 }
 
 extern "C" int ab200_ctx_create(ab200_ctx** out, int device) {
@@ -240,7 +240,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
     EvolveParams P;
     P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations ? 1 : 0; P.max_boxes = S.max_boxes;
     P.temporal_order = S.temporal_order; P.ratio = S.maximum_enclosure_widths_ratio; P.spacial_sweep = S.sweep_threshold;
-    P.spacial_order = S.spacial_order; P.max_working_sets = 16; P.lower = S.semantics ? 1 : 0; P.backward = direction ? 1 : 0;
+    P.spacial_order = S.spacial_order; P.max_working_sets = S.max_working_sets > 0 ? S.max_working_sets : 64; P.lower = S.semantics ? 1 : 0; P.backward = direction ? 1 : 0;
     const size_t table_n = want_keys ? ((size_t)1 << S.hash_log2) : 0;
     std::vector<uint64_t> acc_keys[2];
     if (out.reach_boxes) { out.reach_boxes->offsets.assign(1, 0); }

@@ -41,6 +41,7 @@ AB_HDN int guard_active(Ctx& c, const SystemDesc& S, Func g, const TM* models) {
 AB_HDN Ivl tm_jacobian2_range(Ctx& c, const TM& f) {
     const int k = f.as - 1;
     Ivl J = ivl(0.0, 0.0);
+    #pragma unroll 1
     for (int t = 0; t < f.n; ++t) {
         Key a = tm_key(c, f, t);
         int e = key_get(a, k);
@@ -59,11 +60,14 @@ AB_HDN Ivl tm_jacobian2_at(Ctx& c, const TM& f, const Ivl* x) {
     const int as = f.as, k = as - 1;
     Ivl rv = ivl_mul(x[0], 0.0), rg = ivl(0.0, 0.0);          // zero = y[0]; zero*=0
     const Ivl onev = ivl_add(rv, 1.0);                          // one = zero; one+=1
+    #pragma unroll 1
     for (int t = 0; t < f.n; ++t) {
         Key a = tm_key(c, f, t);
         Ivl tv = onev, tg = ivl(0.0, 0.0);
+        #pragma unroll 1
         for (int j = 0; j < as; ++j) {
             int e = key_get(a, j);
+            #pragma unroll 1
             for (int l = 0; l < e; ++l) {
                 // t=t*y[j] with y[j]=(x[j], j==k ? 1 : absent)
                 Ivl nv = ivl_mul(tv, x[j]);
@@ -106,6 +110,7 @@ AB_HDN bool tm_implicit(Ctx& c, const TM& f, TM& out) {
     { Ivl D = tm_jacobian2_range(c, f); AB_DBG("implicit: J2range %a %a\n", D.l, D.u); if (D.l <= 0 && D.u >= 0) return false; }
     // ---- _implicit5(f,6)
     TM ys[AB_MAXARGS + 1];
+    #pragma unroll 1
     for (int j = 0; j < has; ++j) ys[j] = tm_variable(c, has, j);
     // D2f value = coefficient of the time variable
     double d2f = 0.0;
@@ -114,6 +119,7 @@ AB_HDN bool tm_implicit(Ctx& c, const TM& f, TM& out) {
     TM g = tm_begin(c, fas, acc_default());
     {
         Key u = key_unit(has); bool done = false;
+        #pragma unroll 1
         for (int t = 0; t < f.n; ++t) {
             Key a = tm_key(c, f, t);
             if (!done && !key_less(a, u)) { if (key_eq(a, u)) { tm_append(c, g, a, 0.0); done = true; continue; } tm_append(c, g, u, 0.0); done = true; }
@@ -131,6 +137,7 @@ AB_HDN bool tm_implicit(Ctx& c, const TM& f, TM& out) {
     TM h = tm_const(c, has, 1.0, acc_default());
     tm_scal(c, h, ivl(-1, 1));                                   // constants(has,[-1,1])
     bool contracting = false;
+    #pragma unroll 1
     for (int k = 0; k < 6; ++k) {
         const int mk = c.A.top;
         ys[has] = h;
@@ -150,8 +157,10 @@ AB_HDN bool tm_implicit(Ctx& c, const TM& f, TM& out) {
     }
     if (!contracting) { AB_DBG("implicit: not contracting\n"); c.A.top = m0; return false; }
     // ---- three Newton refinements
+    #pragma unroll 1
     for (int it = 0; it < 3; ++it) {
         Ivl x[AB_MAXARGS + 1];
+        #pragma unroll 1
         for (int j = 0; j < has; ++j) x[j] = ivl(-1, 1);
         x[has] = tm_range(c, h);
         Ivl D = tm_jacobian2_at(c, f, x);
@@ -180,9 +189,11 @@ AB_HDN bool tm_implicit(Ctx& c, const TM& f, TM& out) {
 // TaylorModel::evaluate(Vector<Interval>) src/taylor_model.cpp:1650-1666
 AB_HDN Ivl tm_evaluate(Ctx& c, const TM& f, const Ivl* v) {
     Ivl r = ivl_mul(ivl(-1, 1), f.e);
+    #pragma unroll 1
     for (int t = 0; t < f.n; ++t) {
         Key a = tm_key(c, f, t);
         Ivl tv = ivl(tm_val(c, f, t));
+        #pragma unroll 1
         for (int j = 0; j < f.as; ++j) tv = ivl_mul(tv, ivl_pow(v[j], (unsigned)key_get(a, j)));
         r = ivl_add(r, tv);
     }
@@ -193,6 +204,7 @@ AB_HDN Ivl tm_evaluate(Ctx& c, const TM& f, const Ivl* v) {
 AB_HDN Ivl touching_time_interval(Ctx& c, const TM& gf) {
     const int as = gf.as;
     Ivl x[AB_MAXARGS + 1];
+    #pragma unroll 1
     for (int j = 0; j < as - 1; ++j) x[j] = ivl(-1, 1);
     const double tmin = 0.0, tmax = 1.0;
     x[as - 1] = ivl(tmin);
@@ -201,6 +213,7 @@ AB_HDN Ivl touching_time_interval(Ctx& c, const TM& gf) {
     if (!(init.u < 0 || init.l > 0)) lower_time = tmin;                  // possibly(initial_guard_range==0)
     else {
         double mn = tmin, mx = tmax;
+        #pragma unroll 1
         for (int i = 0; i < 5; ++i) {
             double nt = add_rn(mn, mx) / 2;
             x[as - 1] = ivl(tmin, nt);
@@ -211,6 +224,7 @@ AB_HDN Ivl touching_time_interval(Ctx& c, const TM& gf) {
     if (init.l > 0 || init.u < 0) upper_time = tmax;
     else {
         double mn = tmin, mx = tmax;
+        #pragma unroll 1
         for (int i = 0; i < 5; ++i) {
             double nt = add_rn(mn, mx) / 2;
             x[as - 1] = ivl(nt);
@@ -238,14 +252,17 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
     (void)spacial;
     B.time = tstep; B.finishing = true; B.n_blocking = 0; B.n_nontransverse = 0;
     bool any = false;
+    #pragma unroll 1
     for (int e = 0; e < L.n_events; ++e) if (is_urgent(L.ev[e])) any = true;
     if (!any) return;
     // event_blocking_times in std::map<DiscreteEvent,...> order: events sorted by name, the finishing event "e-2" among them
     TM times[AB_MAXEV + 1]; int who[AB_MAXEV + 1]; int nt = 0;      // who: event index, -1 = finishing
     const int m = c.A.top;
     TM pos[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) pos[i] = tm_split(c, fset[i], n, true);   // split(models,dimension,1) (sic)
     bool fin_done = false, have_fin_override = false; TM fin_override = tstep; int fin_slot = -1;
+    #pragma unroll 1
     for (int e = 0; e <= L.n_events; ++e) {
         if (!fin_done && e == L.finishing_rank) { times[nt] = tstep; who[nt] = -1; fin_slot = nt; ++nt; fin_done = true; }
         if (e == L.n_events) break;
@@ -268,6 +285,7 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
             Ivl tti = touching_time_interval(c, gf);
             if (tti.u >= 0 && tti.l <= 1.0) {
                 TM fin[AB_MAXN];
+                #pragma unroll 1
                 for (int i = 0; i < n; ++i) fin[i] = tm_partial_evaluate_one(c, fset[i], n);   // partial_evaluate(models,dimension,1.0) (sic)
                 int fa = guard_active(c, S, L.ev[e].guard, fin);
                 if (c.status != ST_OK) return;
@@ -286,11 +304,13 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
     if (have_fin_override) times[fin_slot] = fin_override;
     // compute_blockingTime_and_relatedEvents
     unsigned bset = 1u << 0; TM bt = times[0];
+    #pragma unroll 1
     for (int k = 1; k < nt; ++k) {
         int first = tm_less(c, times[k], bt);
         if (first == TRI_TRUE) { bset = 1u << k; bt = times[k]; }
         else if (first == TRI_INDET) {
             unsigned nset = 1u << k;
+            #pragma unroll 1
             for (int q = 0; q < k; ++q) if ((bset >> q) & 1u) { if (tri_possibly(tm_less(c, times[q], times[k]))) nset |= 1u << q; }
             // blocking_time.swap(new_blocking_time): expansion and error of `time`, accuracy kept
             Acc a = bt.acc; bt = times[k]; bt.acc = a;
@@ -307,6 +327,7 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
         tm_scal(c, bt, 1 - SMALL);
     } else {
         B.finishing = false;
+        #pragma unroll 1
         for (int k = 0; k < nt; ++k) if ((bset >> k) & 1u) { if (who[k] < 0) B.finishing = true; else B.blocking[B.n_blocking++] = who[k]; }
     }
     tm_slide(c, bt, m);
@@ -319,9 +340,11 @@ AB_HDN void compute_blocking_info(Ctx& c, const SystemDesc& S, const LocDesc& L,
 AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc& L, const TM* set, int n, int p, int lower, int backward) {
     (void)p;
     int blocking_active = TRI_FALSE;
+    #pragma unroll 1
     for (int e = 0; e < L.n_events; ++e) {
         if (!is_urgent(L.ev[e])) continue;
         Ivl inf[AB_MAXN];
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) inf[i] = ivl(-DBL_MAX, DBL_MAX);
         int st = c.status;
         Ivl gr = eval_ivl(c, S.ops, L.ev[e].guard, inf);
@@ -337,7 +360,9 @@ AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc
     if (blocking_active == TRI_TRUE) return true;
     if (blocking_active == TRI_INDET && lower) {
         Ivl bb[AB_MAXN];
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) bb[i] = tm_range(c, set[i]);
+        #pragma unroll 1
         for (int e = 0; e < L.n_events; ++e) {
             if (!is_urgent(L.ev[e])) continue;
             int act = tribool_of(eval_ivl(c, S.ops, L.ev[e].guard, bb));
@@ -351,6 +376,7 @@ AB_HDN bool enclosure_to_be_discarded(Ctx& c, const SystemDesc& S, const LocDesc
     return false;
 }
 AB_HD bool blocking_has_transition(const LocDesc& L, const BlockingInfo& B) {
+    #pragma unroll 1
     for (int k = 0; k < B.n_blocking; ++k) if (L.ev[B.blocking[k]].kind != EV_INVARIANT) return true;
     return false;
 }
@@ -364,26 +390,32 @@ struct Activation { int ev; TM lower, upper; };
 AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& L, const BlockingInfo& B, const TM* fset,
                                     int n, int p, int lower, Activation* act) {
     bool wanted[AB_MAXEV]; bool any = false;
+    #pragma unroll 1
     for (int e = 0; e < L.n_events; ++e) { wanted[e] = (L.ev[e].kind == EV_PERMISSIVE); any = any || wanted[e]; }
+    #pragma unroll 1
     for (int k = 0; k < B.n_nontransverse; ++k) if (L.ev[B.nontransverse[k]].kind != EV_INVARIANT) { wanted[B.nontransverse[k]] = true; any = true; }
     const int m0 = c.A.top;
     // The reference builds the initial/final set models even when the activation map is empty; their only lasting
     // effect then is the rounding mode left by partial_evaluate's additions (round-to-nearest once a model has degree
     // >= 1), so without candidates only that is reproduced.
     if (!any) {
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) if (tm_degree(c, fset[i]) >= 1) c.rnd = RN;
         return 0;
     }
     TM init[AB_MAXN], fin[AB_MAXN];
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {                                   // partial_evaluate(models,p,0.0): terms free of the time variable
         TM r = tm_begin(c, p, fset[i].acc);
         AB_FILTER_COPY(c, r, fset[i], key_get(a, p) == 0, key_remove(a, p, p + 1), v);
         r.e = fset[i].e;
         init[i] = r;
     }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) fin[i] = tm_partial_evaluate_one(c, fset[i], p);
     TM zero = B.time; zero.n = 0; zero.e = 0.0;                     // blocking_time_model*0.0
     int na = 0;
+    #pragma unroll 1
     for (int e = 0; e < L.n_events && c.status == ST_OK; ++e) {
         if (!wanted[e]) continue;
         int active = guard_active(c, S, L.ev[e].guard, fset);
@@ -417,8 +449,10 @@ AB_HDN int compute_activation_times(Ctx& c, const SystemDesc& S, const LocDesc& 
     if (c.status != ST_OK) return 0;
     // keep only the windows: copy them to the top in order, then slide the block down to m0
     TM keep[2 * AB_MAXEV];
+    #pragma unroll 1
     for (int k = 0; k < na; ++k) { keep[2 * k] = tm_copy(c, act[k].lower); keep[2 * k + 1] = tm_copy(c, act[k].upper); }
     vec_slide(c, keep, 2 * na, m0);
+    #pragma unroll 1
     for (int k = 0; k < na; ++k) { act[k].lower = keep[2 * k]; act[k].upper = keep[2 * k + 1]; }
     return na;
 }

@@ -42,6 +42,7 @@ struct CellOutput {
 AB_HD void out_box(Ctx& c, double* dst, int32_t* dloc, int32_t& count, int cap, int stride, int loc, const Ivl* b, int n) {
     if (count >= cap) { fail(c, ST_OUTPUT); return; }
     double* p = dst + (size_t)count * stride;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const int m = c.A.top;
         TM s = tm_scaling(c, n, i, b[i]);
@@ -67,7 +68,9 @@ struct WorkingSet {
 AB_HD bool enclosure_too_large(Ctx& c, const LocDesc& L, const Ivl* range, const double* init_w, double ratio) {
     const int n = L.n;
     bool use_init = false;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) if (init_w[i] >= L.ref_width[i]) { use_init = true; break; }
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         double w = ivl_width(range[i]);
         if (use_init) { if (div_m(c.rnd, w, init_w[i]) >= ratio) return true; }
@@ -76,10 +79,36 @@ AB_HD bool enclosure_too_large(Ctx& c, const LocDesc& L, const Ivl* range, const
     return false;
 }
 
-#define AB_MAXQ 12     // pending working sets per cell (device limit; WorkingSetTooLarge beyond it)
+// Pending working sets of one cell (std::list<EvolutionData> in the reference, unbounded by default). Their handles live in
+// a table at the bottom of the cell's arena (AB_QW words each), so the capacity is a setting (EvolveParams::max_working_sets,
+// at most AB_MAXQ) rather than a register-file limit; WorkingSetTooLarge beyond it.
+#define AB_MAXQ 256
+#define AB_QW 26
+AB_HD void tmh_store(uint64_t* w, const TM& t) {
+    w[0] = ((uint64_t)(uint32_t)t.off << 32) | (uint32_t)t.n; w[1] = ((uint64_t)(uint32_t)t.as << 32) | (uint32_t)t.acc.maxdeg; w[2] = d2u(t.e); w[3] = d2u(t.acc.sweep);
+}
+AB_HD TM tmh_load(const uint64_t* w) {
+    TM t; t.off = (int)(w[0] >> 32); t.n = (int)(w[0] & 0xFFFFFFFFu); t.as = (int)(w[1] >> 32); t.acc.maxdeg = (int)(w[1] & 0xFFFFFFFFu); t.e = u2d(w[2]); t.acc.sweep = u2d(w[3]); return t;
+}
+// warp-uniform: every lane writes / reads the same words
+AB_HD void ws_store(Ctx& c, int qbase, int k, const WorkingSet& w) {
+    uint64_t* p = c.A.base + qbase + k * AB_QW;
+    p[0] = ((uint64_t)(uint32_t)w.loc << 32) | (uint32_t)w.n_events; p[1] = (uint64_t)(uint32_t)w.p;
+    #pragma unroll 1
+    for (int i = 0; i < AB_MAXN; ++i) tmh_store(p + 2 + 4 * i, w.set[i]);
+    tmh_store(p + 2 + 4 * AB_MAXN, w.time);
+}
+AB_HD void ws_load(Ctx& c, int qbase, int k, WorkingSet& w) {
+    const uint64_t* p = c.A.base + qbase + k * AB_QW;
+    w.loc = (int)(p[0] >> 32); w.n_events = (int)(p[0] & 0xFFFFFFFFu); w.p = (int)p[1];
+    #pragma unroll 1
+    for (int i = 0; i < AB_MAXN; ++i) w.set[i] = tmh_load(p + 2 + 4 * i);
+    w.time = tmh_load(p + 2 + 4 * AB_MAXN);
+}
 
 // Slide the models of working set w (set[0..n), time; stored in ascending arena order) down to dst, packed.
 AB_HD int ws_pack(Ctx& c, WorkingSet& w, int n, int dst) {
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) { tm_slide(c, w.set[i], dst); dst = c.A.top; }
     tm_slide(c, w.time, dst);
     return c.A.top;
@@ -88,12 +117,12 @@ AB_HD int ws_pack(Ctx& c, WorkingSet& w, int n, int dst) {
 // Evolution of one enclosure (a box in location loc0) for time P.T mirrors _evolution: a FIFO of working sets
 // (std::list<EvolutionData>, popped from the front, successors pushed at the back), kept packed at the bottom of the
 // cell's arena in queue order; everything above the last queued set is scratch. The loop is split into cell_begin /
-// cell_advance (one queue iteration = at most one _evolution_step) so that the kernel can hand a lane its next
-// cell at a step boundary while the other lanes of the warp carry on with theirs.
+// cell_advance (one queue iteration = at most one _evolution_step).
 struct CellState {
-    WorkingSet q[AB_MAXQ];
     int nq;
-    int base0;
+    int qcap;
+    int qbase;           // handle table
+    int base0;           // models of the queued sets start here
     int guard_iter;
     double init_w[AB_MAXN];
 };
@@ -101,14 +130,23 @@ struct CellState {
 AB_HDN void cell_begin(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellState& st) {
     Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
     const int n0 = S.loc[loc0].n;
-    WorkingSet* q = st.q;
+    st.qcap = (P.max_working_sets > 0 && P.max_working_sets < AB_MAXQ) ? P.max_working_sets : AB_MAXQ;
+    st.qbase = c.A.top;
+    if ((long long)st.qbase + (long long)(st.qcap + AB_MAXEV + 1) * AB_QW + 64 > (long long)c.A.limit) { fail(c, ST_ARENA); st.nq = 0; return; }
+    c.A.top = st.qbase + (st.qcap + AB_MAXEV + 1) * AB_QW;      // room for the successors of one step past the capacity check
     st.base0 = c.A.top;
     st.nq = 1;
     // ---- _evolution_add_initialSet: set_model(box)=scalings(box) with spacial accuracy; time_model(0.0)
-    q[0].loc = loc0; q[0].n_events = 0; q[0].p = n0;
-    for (int i = 0; i < n0; ++i) { q[0].set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); q[0].set[i].acc = spacial; }
-    q[0].time = tm_begin(c, n0, spacial); tm_append(c, q[0].time, key_zero(), 0.0);          // constant(as,0.0): explicit zero term
-    for (int i = 0; i < n0; ++i) st.init_w[i] = ivl_width(tm_range(c, q[0].set[i]));   // _indexed_set_models_widths
+    WorkingSet w0;
+    w0.loc = loc0; w0.n_events = 0; w0.p = n0;
+    #pragma unroll 1
+    for (int i = 0; i < AB_MAXN; ++i) { w0.set[i].off = 0; w0.set[i].n = 0; w0.set[i].as = 0; w0.set[i].e = 0.0; w0.set[i].acc = spacial; }
+    #pragma unroll 1
+    for (int i = 0; i < n0; ++i) { w0.set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); w0.set[i].acc = spacial; }
+    w0.time = tm_begin(c, n0, spacial); tm_append(c, w0.time, key_zero(), 0.0);          // constant(as,0.0): explicit zero term
+    #pragma unroll 1
+    for (int i = 0; i < n0; ++i) st.init_w[i] = ivl_width(tm_range(c, w0.set[i]));   // _indexed_set_models_widths
+    ws_store(c, st.qbase, 0, w0);
     st.guard_iter = 0;
 }
 
@@ -118,18 +156,20 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
     if (st.nq <= 0 || c.status != ST_OK) return false;
     if (++st.guard_iter > 100000) { fail(c, ST_OUTPUT); return false; }
     Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
-    WorkingSet* q = st.q;
     int& nq = st.nq;
     const double* init_w = st.init_w;
-    const int base0 = st.base0;
+    const int base0 = st.base0, qbase = st.qbase;
     do {
-        WorkingSet ws = q[0];
+        WorkingSet ws; ws_load(c, qbase, 0, ws);
         const int qend = c.A.top;                      // end of the last queued set; scratch starts here
         const LocDesc& L = S.loc[ws.loc];
         const int n = L.n, p = ws.p;
-        WorkingSet succ[AB_MAXEV + 1];
-        int ns = 0;
+        int ns = 0;                                    // successors are parked in the handle table past the queued sets
+        WorkingSet w;
+        #pragma unroll 1
+        for (int i = 0; i < AB_MAXN; ++i) { w.set[i].off = 0; w.set[i].n = 0; w.set[i].as = 0; w.set[i].e = 0.0; w.set[i].acc = spacial; }
         Ivl range[AB_MAXN];
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) range[i] = tm_range(c, ws.set[i]);
         Ivl trange = tm_range(c, ws.time);
         bool too_large = enclosure_too_large(c, L, range, init_w, P.ratio);
@@ -143,6 +183,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             O.steps++;
 #ifdef AB_DEBUG_DUMP
             printf("STEP %d\n", O.steps - 1);
+            #pragma unroll 1
             for (int i = 0; i < n; ++i) AB_DUMP(c, "set", i, ws.set[i]);
             AB_DUMP(c, "time", -1, ws.time);
 #endif
@@ -157,9 +198,11 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             flow_apply(c, flow, n, dom, ws.set, p, h, fset);
 #ifdef AB_DEBUG_DUMP
             printf("h %a bb", h); for (int i = 0; i < n; ++i) printf(" %a %a", bb[i].l, bb[i].u); printf("\n");
+            #pragma unroll 1
             for (int i = 0; i < n; ++i) AB_DUMP(c, "flow", i, flow[i]);
 #endif
             vec_slide(c, fset, n, qend);              // drop the flow model, keep the flow set model
+            #pragma unroll 1
             for (int i = 0; i < n; ++i) AB_DUMP(c, "fset", i, fset[i]);
             if (c.status != ST_OK) break;
 
@@ -183,7 +226,9 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                     TM reach[AB_MAXN];
                     reachability_step(c, fset, n, p, zero_t, B.time, spacial, reach);
                     Ivl rb[AB_MAXN];
+                    #pragma unroll 1
                     for (int i = 0; i < n; ++i) AB_DUMP(c, "reach", i, reach[i]);
+                    #pragma unroll 1
                     for (int i = 0; i < n; ++i) rb[i] = tm_range(c, reach[i]);
                     out_box(c, O.reach, O.reach_loc, O.n_reach, P.max_boxes, O.stride, ws.loc, rb, n);
                     c.A.top = m;
@@ -192,6 +237,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                 if (!P.lower || ((B.finishing ? 1 : 0) + B.n_blocking) == 1) {
                 TM ev[AB_MAXN];
                 integration_step(c, fset, n, p, B.time, spacial, ev);
+                #pragma unroll 1
                 for (int i = 0; i < n; ++i) AB_DUMP(c, "evolved", i, ev[i]);
                 // final_time_model=time_model+blocking_time_model*time_step
                 TM ft;
@@ -204,6 +250,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                 int np = p;
                 {   // reconditioning (enable_reconditioning)
                     double thr[AB_MAXN];
+                    #pragma unroll 1
                     for (int i = 0; i < n; ++i) thr[i] = div_m(c.rnd, L.ref_width[i], 4.0);
                     np = uniform_error_recondition(c, ev, n, p, thr);
                     if (np > p) ft.as = np;                                   // embed(final_time_model,diff)
@@ -217,35 +264,39 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                 // successors, in the order of the blocking_events set (std::set<DiscreteEvent>: by name, with the
                 // finishing event "e-2" at its rank)
                 bool fin_done = false;
+                #pragma unroll 1
                 for (int k = 0; k <= B.n_blocking && c.status == ST_OK; ++k) {
                     const int e = (k < B.n_blocking) ? B.blocking[k] : -1;
                     if (B.finishing && !fin_done && (e < 0 || e >= L.finishing_rank)) {
-                        WorkingSet& w = succ[ns++];
                         w.loc = ws.loc; w.n_events = ws.n_events; w.p = np;
+                        #pragma unroll 1
                         for (int i = 0; i < n; ++i) w.set[i] = ev[i];
                         w.time = ft;
+                        ws_store(c, qbase, nq + ns, w); ++ns;
                         fin_done = true;
                     }
                     if (e < 0) break;
                     const EventDesc& E = L.ev[e];
                     if (E.kind != EV_INVARIANT && !P.ignore_activations) {
                         // jump: apply(reset,evolved_set_model) into the target location (:1049-1058)
-                        WorkingSet& w = succ[ns++];
                         const int nt = S.loc[E.target].n;
                         w.loc = E.target; w.n_events = ws.n_events + 1; w.p = np;
+                        #pragma unroll 1
                         for (int i = 0; i < nt; ++i) w.set[i] = eval_tm(c, S.ops, E.reset[i], ev);
                         w.time = ft;
+                        ws_store(c, qbase, nq + ns, w); ++ns;
                     }
                 }
                 // non-blocking events (:1060-1081): jump from the part of the flow tube inside the activation window;
                 // the new working set carries one more parameter (the time within the window) and is not reconditioned
+                #pragma unroll 1
                 for (int a = 0; a < na && c.status == ST_OK; ++a) {
                     const EventDesc& E = L.ev[acts[a].ev];
                     const int nt = S.loc[E.target].n;
                     TM aset[AB_MAXN];
                     reachability_step(c, fset, n, p, acts[a].lower, acts[a].upper, spacial, aset);
-                    WorkingSet& w = succ[ns++];
                     w.loc = E.target; w.n_events = ws.n_events + 1; w.p = p + 1;
+                    #pragma unroll 1
                     for (int i = 0; i < nt; ++i) w.set[i] = eval_tm(c, S.ops, E.reset[i], aset);
                     const int m = c.A.top;
                     TM up = tm_copy(c, acts[a].upper); tm_scal(c, up, h); TM t1 = tm_add(c, ws.time, up);
@@ -253,25 +304,32 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                     TM at = reachability_time(c, t0, t1, p, spacial);
                     tm_slide(c, at, m);
                     w.time = at;
+                    ws_store(c, qbase, nq + ns, w); ++ns;
                 }
                 }
             }
         }
         if (c.status != ST_OK) break;
         // ---- pop the front, push the successors at the back, re-pack the queue at the bottom of the arena
-        if (nq - 1 + ns > AB_MAXQ) { fail(c, ST_WORKING_SETS); break; }
+        if (nq - 1 + ns > st.qcap) { fail(c, ST_WORKING_SETS); break; }
+        wsync();
         // 1. copy the successors to the top in canonical order (their models may be anywhere above qend)
+        #pragma unroll 1
         for (int k = 0; k < ns; ++k) {
-            const int nn = S.loc[succ[k].loc].n;
-            for (int i = 0; i < nn; ++i) succ[k].set[i] = tm_copy(c, succ[k].set[i]);
-            succ[k].time = tm_copy(c, succ[k].time);
+            ws_load(c, qbase, nq + k, w);
+            const int nn = S.loc[w.loc].n;
+            #pragma unroll 1
+            for (int i = 0; i < nn; ++i) w.set[i] = tm_copy(c, w.set[i]);
+            w.time = tm_copy(c, w.time);
+            ws_store(c, qbase, nq + k, w);
         }
         // 2. slide everything after the front set down over it
         int dst = base0;
-        for (int k = 1; k < nq; ++k) { dst = ws_pack(c, q[k], S.loc[q[k].loc].n, dst); q[k - 1] = q[k]; }
-        for (int k = 0; k < ns; ++k) { dst = ws_pack(c, succ[k], S.loc[succ[k].loc].n, dst); q[nq - 1 + k] = succ[k]; }
+        #pragma unroll 1
+        for (int k = 1; k < nq + ns; ++k) { ws_load(c, qbase, k, w); wsync(); dst = ws_pack(c, w, S.loc[w.loc].n, dst); ws_store(c, qbase, k - 1, w); }
         nq = nq - 1 + ns;
         c.A.top = dst;
+        wsync();
     } while (0);
     return nq > 0 && c.status == ST_OK;
 }
@@ -279,6 +337,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
 AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O) {
     CellState st;
     cell_begin(c, S, loc0, box, P, st);
+    #pragma unroll 1
     while (cell_advance(c, S, P, st, O)) { }
 }
 

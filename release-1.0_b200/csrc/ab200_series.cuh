@@ -28,6 +28,7 @@ AB_HDN TM tm_rec(Ctx& c, const TM& x) {
     // z=(-1)^d; z=1+z*y, d times
     TM z = tm_begin(c, x.as, x.acc);
     tm_acc(c, z, (d % 2) ? -1.0 : 1.0);
+    #pragma unroll 1
     for (unsigned i = 0; i < d; ++i) {
         TM p = tm_mul(c, z, y, y.acc);
         tm_acc(c, p, 1.0);
@@ -68,9 +69,11 @@ AB_HDN TM tm_sqrt(Ctx& c, const TM& x) {
     int st = ST_OK;
     ser[0] = ivl_sqrt(ivl(1.0), &st);
     Ivl mhr = ivl_div(-0.5, ivl(1.0), &st);
+    #pragma unroll 1
     for (unsigned i = 1; i <= d; ++i) ser[i] = ivl_mul(ivl_div(ivl_mul(mhr, (double)(2 * (int)i - 3)), (double)i), ser[i - 1]);
     TM z = tm_begin(c, x.as, x.acc);
     tm_acc(c, z, ser[d - 1]);
+    #pragma unroll 1
     for (unsigned i = 0; i < d; ++i) {
         TM p = tm_mul(c, z, y, y.acc);
         tm_acc(c, p, ser[d - i - 1]);
@@ -99,6 +102,7 @@ AB_HDN TM tm_abs(Ctx& c, const TM& x) {
     TM s = tm_mul(c, s0, s0, s0.acc);                           // sqr(s)
     TM r = tm_begin(c, x.as, acc_default());
     tm_append(c, r, key_zero(), p[6]);
+    #pragma unroll 1
     for (int i = 0; i < 6; ++i) {
         int j = 5 - i;
         TM t = tm_mul(c, s, r, r.acc);

@@ -90,6 +90,7 @@ AB_HD bool key_less(const Key& a, const Key& b) {   // include/multi_index.h:346
 AB_HD Key key_remove(const Key& a, int k, int as) {
     Key r = key_zero();
     int jj = 0;
+    #pragma unroll 1
     for (int j = 0; j < as; ++j) { if (j == k) continue; int e = key_get(a, j); if (e) key_inc(r, jj, e); ++jj; }
     return r;
 }
@@ -120,6 +121,7 @@ struct Ctx {
 #define AB_BINOM_K 24
 // C(n,k) for n < AB_BINOM_N, k < AB_BINOM_K, saturated; filled on the host and handed to the kernels in global memory.
 inline void binom_fill(uint32_t* t) {
+    #pragma unroll 1
     for (int n = 0; n < AB_BINOM_N; ++n) for (int k = 0; k < AB_BINOM_K; ++k) {
         unsigned long long v = (k == 0) ? 1 : (n == 0 ? 0 : (unsigned long long)t[(n - 1) * AB_BINOM_K + k - 1] + t[(n - 1) * AB_BINOM_K + k]);
         t[n * AB_BINOM_K + k] = v > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)v; }
@@ -210,6 +212,7 @@ AB_HDN TM tm_copy(Ctx& c, const TM& x) { AB_CALL(3, x.n);
     const int nw = x.n * AB_TW;
     if (!arena_room(c, r.off, x.n)) return r;
     { uint64_t* const base = c.A.base; const int dst = r.off, src = x.off, W = AB_W;
+      #pragma unroll 1
       for (int i = c.lane; i < nw; i += W) base[dst + i] = base[src + i]; }
     wsync();
     r.n = x.n; r.e = x.e;
@@ -230,12 +233,14 @@ AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_FLOPS(4 * r.n + 3); AB_CALL(4,
     wsync();
     if (s == 2 || s == 0.5) {
         const int m = c.rnd;
+        #pragma unroll 1
         for (int i = lane; i < n; i += W) tm_set_val(c, r, i, mul_m(m, tm_val(c, r, i), s));
         wsync();
         r.e = mul_m(c.rnd, r.e, dabs(s));
         return;
     }
     double te = 0; const double ms = -s;
+    #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += W) {
         const int i = i0 + lane; double g = 0.0;
         if (i < n) {
@@ -256,6 +261,7 @@ AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_FLOPS(5 * r.n + 4); AB_CALL(5, r.
     wsync();
     double te = 0; const double cu = s.u, mcl = -s.l;
     const double m = add_rn(s.u, s.l) / 2;
+    #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += W) {
         const int i = i0 + lane; double g = 0.0;
         if (i < n) {
@@ -278,6 +284,7 @@ AB_HDN void tm_prepend_top(Ctx& c, TM& r, double v) {
     if (!arena_room(c, r.off, r.n + 1)) return;
     uint64_t* const base = c.A.base;
     wsync();
+    #pragma unroll 1
     for (int i0 = nw > 0 ? ((nw - 1) / W) * W : -1; i0 >= 0; i0 -= W) {     // shift up, last chunk first
         const int i = i0 + lane; uint64_t t = 0;
         if (i < nw) t = base[r.off + i];
@@ -360,7 +367,7 @@ AB_HD uint32_t acc_hash(const AccTab& T, const Key& k) {
     return (uint32_t)(h >> T.shift);
 }
 // Place the accumulator in the warp's shared area (attempt 0) or above `above` in the arena with room for `want` entries.
-AB_HDN bool acc_open(Ctx& c, AccTab& T, int attempt, int above, long long want) {
+AB_HD bool acc_open(Ctx& c, AccTab& T, int attempt, int above, long long want) {
     const int W = AB_W, lane = c.lane;
     wsync();
     if (attempt == 0 && c.sm) {
@@ -381,7 +388,7 @@ AB_HDN bool acc_open(Ctx& c, AccTab& T, int attempt, int above, long long want) 
     int lg = 0; while ((1u << lg) <= T.mask) ++lg;
     T.shift = 64 - lg;
     T.nd = 0; T.overflow = false;
-    for (uint32_t i = (uint32_t)lane; i <= T.mask; i += (uint32_t)W) T.idx[i] = AB_IDX_EMPTY;
+    { uint32_t* const idx = T.idx; const uint32_t n = T.mask + 1u; for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)W) idx[i] = AB_IDX_EMPTY; }
     wsync();
     return true;
 }
@@ -391,6 +398,7 @@ AB_HD int acc_slot(AccTab& T, bool active, const Key& k, int lane) {
     int slot = -1; uint32_t h = 0; bool isnew = false;
     if (active) {
         h = acc_hash(T, k);
+        #pragma unroll 1
         for (;;) {
             const uint32_t id = T.idx[h];
             if (id == AB_IDX_EMPTY) { isnew = true; break; }
@@ -413,6 +421,7 @@ AB_HD int acc_slot(AccTab& T, bool active, const Key& k, int lane) {
             T.key[T.cap + slot] = k.w[1];
 #endif
             T.val[slot] = AB_ABSENT;
+            #pragma unroll 1
             for (;;) {          // claim an empty index cell; the other new keys of this call differ from this one
                 const uint32_t old = cas32(&T.idx[h], AB_IDX_EMPTY, (uint32_t)slot);
                 if (old == AB_IDX_EMPTY) break;
@@ -436,10 +445,11 @@ AB_HD double acc_fold(AccTab& T, int slot, double tv) {
     return add_ru(u, ml);
 }
 // Add the terms of model t as one stream; returns te, the upward sum of the rounding gaps in key order.
-AB_HDN double acc_add_model(Ctx& c, AccTab& T, const TM& t) {
+AB_HD double acc_add_model(Ctx& c, AccTab& T, const TM& t) {
     const int W = AB_W, lane = c.lane, n = t.n;
     const uint64_t* const base = c.A.base;
     double te = 0.0;
+    #pragma unroll 1
     for (int j0 = 0; j0 < n; j0 += W) {
         const int j = j0 + lane; const bool act = j < n;
         Key k = key_zero(); double tv = 0.0;
@@ -468,6 +478,7 @@ AB_HD uint32_t binom_at(const uint32_t* tab, int n, int k) { return (n < 0 || k 
 AB_HD uint32_t key_rank(const uint32_t* tab, const Key& k, int as) {
     int R = key_deg(k);
     uint32_t r = (R > 0) ? binom_at(tab, R - 1 + as, as) : 0u;     // monomials of smaller degree
+    #pragma unroll 1
     for (int t = 0; t + 1 < as; ++t) {
         const int e = key_get(k, t), m = as - t;
         r += binom_at(tab, R - e - 1 + m - 1, m - 1);              // same prefix, larger exponent here
@@ -477,7 +488,7 @@ AB_HD uint32_t key_rank(const uint32_t* tab, const Key& k, int as) {
 }
 // Write the accumulator to the arena at word `dst` in key order, skipping dropped entries; returns the number of terms.
 // `scratch` is shared (or arena) memory free for the ordering: gap-code and staging areas when the table is in shared memory.
-AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
+AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
     const int W = AB_W, lane = c.lane, nd = T.nd;
     uint64_t* const base = c.A.base;
     if (nd == 0) return 0;
@@ -497,8 +508,10 @@ AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
     }
     if (bits) {
         const uint32_t* tab = c.binom;
+        #pragma unroll 1
         for (long long i = lane; i < nwords; i += W) bits[i] = 0;
         wsync();
+        #pragma unroll 1
         for (int s = lane; s < nd; s += W) if (T.val[s] != AB_ABSENT) {
             Key k; k.w[0] = T.key[s];
 #if AB_KW > 1
@@ -509,14 +522,17 @@ AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
         }
         wsync();
         int total = 0;
+        #pragma unroll 1
         for (long long i0 = 0; i0 < nwords; i0 += W) {        // exclusive prefix of the word popcounts
             const long long i = i0 + lane; int pc = (i < nwords) ? popc32(bits[i]) : 0;
             int incl = pc;
+            #pragma unroll 1
             for (int d = 1; d < W; d <<= 1) { int o = wshfl(incl, lane - d < 0 ? lane : lane - d); if (lane >= d) incl += o; }
             if (i < nwords) pre[i] = (uint32_t)(total + incl - pc);
             total += wshfl(incl, W - 1);
         }
         wsync();
+        #pragma unroll 1
         for (int s = lane; s < nd; s += W) if (T.val[s] != AB_ABSENT) {
             Key k; k.w[0] = T.key[s];
 #if AB_KW > 1
@@ -532,9 +548,12 @@ AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
     // general ordering: bitonic sort of the entry numbers by key (uses the hash index area, no longer needed)
     int P = 1; while (P < nd) P <<= 1;
     uint32_t* perm = T.idx;                       // index area holds >= 2*cap cells
+    #pragma unroll 1
     for (int i = lane; i < P; i += W) perm[i] = (i < nd && T.val[i] != AB_ABSENT) ? (uint32_t)i : AB_IDX_EMPTY;
     wsync();
+    #pragma unroll 1
     for (int kk = 2; kk <= P; kk <<= 1) for (int j = kk >> 1; j > 0; j >>= 1) {
+        #pragma unroll 1
         for (int t = lane; t < P; t += W) {
             const int o = t ^ j;
             if (o > t) {
@@ -555,6 +574,7 @@ AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
         wsync();
     }
     int total = 0;
+    #pragma unroll 1
     for (int i0 = 0; i0 < nd; i0 += W) {
         const int i = i0 + lane; const uint32_t s = (i < nd) ? perm[i] : AB_IDX_EMPTY;
         const unsigned m = wballot(s != AB_IDX_EMPTY);
@@ -579,18 +599,21 @@ AB_HDN int acc_emit(Ctx& c, AccTab& T, int as, int maxdeg, int dst) {
 // applied in stream order. A coefficient that cancels to exactly zero is dropped, as _add2 does, and a later stream
 // re-creates the term. Result at the arena top.
 #ifndef AB_MAXSTREAMS
-#define AB_MAXSTREAMS 8
+#define AB_MAXSTREAMS 32
 #endif
 AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B); AB_FLOPS(3 * B);
     const int m = c.A.top;
     TM out; out.off = m; out.n = 0; out.as = r.as; out.acc = acc; out.e = r.e;
     long long want = r.n; int maxdeg = tm_degree(c, r);
+    #pragma unroll 1
     for (int s = 0; s < B; ++s) { want += t[s].n; const int d = tm_degree(c, t[s]); if (d > maxdeg) maxdeg = d; }
     double te[AB_MAXSTREAMS];
     AccTab T;
+    #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!acc_open(c, T, attempt, m + (int)want * AB_TW, want)) return out;
         acc_add_model(c, T, r);
+        #pragma unroll 1
         for (int s = 0; s < B && !T.overflow; ++s) te[s] = acc_add_model(c, T, t[s]);
         if (!T.overflow) break;
         if (attempt == 1) { fail(c, ST_ARENA); return out; }
@@ -599,6 +622,7 @@ AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CAL
     c.A.top = m + out.n * AB_TW;
     arena_mark_peak(c);
     double e = r.e;
+    #pragma unroll 1
     for (int s = 0; s < B; ++s) e = add_ru(add_ru(e, t[s].e), te[s] / 2);
     out.e = e;
     c.rnd = RN;
@@ -616,6 +640,7 @@ AB_HDN TM tm_neg(Ctx& c, const TM& x) { AB_CALL(6, x.n);
     TM r = tm_begin(c, x.as, acc_default());
     if (!arena_room(c, r.off, x.n)) return r;
     uint64_t* const base = c.A.base; const int W = AB_W;
+    #pragma unroll 1
     for (int i = c.lane; i < x.n; i += W) bput(base, r.off + i * AB_TW, bkey(base, x.off + i * AB_TW), -bval(base, x.off + i * AB_TW));
     wsync();
     r.n = x.n; r.e = x.e;
@@ -670,7 +695,9 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     if (xn == 0 || yn == 0) {
         // an empty factor: no streams; only the error cross terms remain (norms of the other factor)
         double xs = 0, ys = 0;
+        #pragma unroll 1
         for (int i0 = 0; i0 < xn; i0 += W) { const int i = i0 + lane; xs = chain_ru(xs, i < xn ? dabs(bval(base, xoff + i * AB_TW)) : 0.0, (xn - i0 < W) ? xn - i0 : W); }
+        #pragma unroll 1
         for (int j0 = 0; j0 < yn; j0 += W) { const int j = j0 + lane; ys = chain_ru(ys, j < yn ? dabs(bval(base, yoff + j * AB_TW)) : 0.0, (yn - j0 < W) ? yn - j0 : W); }
         r.e = add_ru(0.0, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
         c.rnd = RN;
@@ -689,6 +716,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         const double oe = one_x ? xe : ye;          // error of the single-term factor multiplies the norm of the other
         if (!arena_room(c, m, n)) return r;
         double tte = 0.0, norm = 0.0;
+        #pragma unroll 1
         for (int j0 = 0; j0 < n; j0 += W) {
             const int j = j0 + lane; const bool act = j < n;
             Key ta = key_zero(); double sv = 0.0, tv = 0.0; bool disc = false;
@@ -723,11 +751,13 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     { const long long prod = (long long)xn * (long long)yn; if (prod < bound) bound = prod; }
     double re = 0.0;
     AccTab T;
+    #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
         // factor y staged in shared memory as structure-of-arrays (keys | coefficients) when it fits
         const uint64_t* yk; const uint64_t* yv; int ystr, ykw;      // word j of y: yk[j*ystr] (+ykw for the second key word), yv[j*ystr]
         if (c.sm && yn <= AB_SM_YCAP) {
             uint64_t* sk = c.sm + AB_SM_OFF_YK; uint64_t* sv = c.sm + AB_SM_OFF_YV;
+            #pragma unroll 1
             for (int j = lane; j < yn; j += W) { for (int w = 0; w < AB_KW; ++w) sk[w * AB_SM_YCAP + j] = base[yoff + j * AB_TW + w]; sv[j] = base[yoff + j * AB_TW + AB_KW]; }
             yk = sk; yv = sv; ystr = 1; ykw = AB_SM_YCAP;
         } else { yk = base + yoff; yv = base + yoff + AB_KW; ystr = AB_TW; ykw = 1; }
@@ -752,11 +782,13 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         if (!acc_open(c, T, attempt, tab_above, cap1)) return r;
         re = 0.0;
         bool badgap = false;
+        #pragma unroll 1
         for (int i0 = 0; i0 < xn && !T.overflow; i0 += Bi) {
             const int nb = (xn - i0 < Bi) ? (xn - i0) : Bi;
             // lane b holds x-term i0+b
             Key mxa = key_zero(); double mxv = 0.0;
             if (lane < nb) { mxa = bkey(base, xoff + (i0 + lane) * AB_TW); mxv = bval(base, xoff + (i0 + lane) * AB_TW); }
+            #pragma unroll 1
             for (int b = 0; b < nb && !T.overflow; ++b) {
                 Key xa; xa.w[0] = wshfl(mxa.w[0], b);
 #if AB_KW > 1
@@ -764,6 +796,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
 #endif
                 const double xv = wshfl(mxv, b);
                 uint16_t* row = g16 + b * gs;
+                #pragma unroll 1
                 for (int j0 = 0; j0 < yn; j0 += W) {
                     const int j = j0 + lane; const bool act = j < yn;
                     Key ta = key_zero(); double tv = 0.0; bool disc = false;
@@ -791,6 +824,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
             if (lane < nb) {
                 const double axv = dabs(mxv);
                 const uint16_t* row = g16 + lane * gs;
+                #pragma unroll 1
                 for (int j = 0; j < yn; ++j) {
                     const uint32_t code = row[j];
                     if (code & AB_G16_DISCARD) tte = add_ru(tte, mul_ru(axv, dabs(u2d(yv[j * ystr]))));
@@ -799,6 +833,7 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
             }
             wsync();
             // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
+            #pragma unroll 1
             for (int b = 0; b < nb; ++b) {
                 const double tt = wshfl(tte, b), ee = wshfl(te, b);
                 const double tev = add_ru(tt, tt / 2);
@@ -812,7 +847,9 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     #undef AB_DISCARD
     r.n = acc_emit(c, T, as, D, m);
     double xs = 0, ys = 0;
+    #pragma unroll 1
     for (int i0 = 0; i0 < xn; i0 += W) { const int i = i0 + lane; xs = chain_ru(xs, i < xn ? dabs(bval(base, xoff + i * AB_TW)) : 0.0, (xn - i0 < W) ? xn - i0 : W); }
+    #pragma unroll 1
     for (int j0 = 0; j0 < yn; j0 += W) { const int j = j0 + lane; ys = chain_ru(ys, j < yn ? dabs(bval(base, yoff + j * AB_TW)) : 0.0, (yn - j0 < W) ? yn - j0 : W); }
     r.e = add_ru(re, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
     c.rnd = RN;
@@ -876,6 +913,7 @@ AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) { AB_FLOPS(x.n + 2);
 AB_HD double tm_abs_sum(Ctx& c, const TM& x, double s, bool with_constant, double* constant) {
     const int W = AB_W, lane = c.lane, n = x.n;
     double cv = 0.0;
+    #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += W) {
         const int i = i0 + lane; double g = 0.0;
         if (i < n) { const double v = tm_val(c, x, i); if (!with_constant && key_deg(tm_key(c, x, i)) == 0) cv = v; else g = dabs(v); }
@@ -956,6 +994,7 @@ AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) { AB_FLOPS(4 * x.n + 2);
     const int W = AB_W, lane = c.lane, n = x.n;
     wsync();
     double tre = 0;
+    #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += W) {
         const int i = i0 + lane; double g = 0.0;
         if (i < n) {
@@ -990,6 +1029,7 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
     const double xe = x.e, ye = y.e;
     AccTab T;
     bool disjoint = false; double tme = 0.0;
+    #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
         // y's coefficients beside the entries: in the gap-code area (shared) or above the table (arena)
         const long long yv_words = (attempt == 0 && c.sm) ? 0 : ((want < 64) ? 64 : want);
@@ -998,8 +1038,10 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
         uint64_t* yval;
         if (yv_words == 0) { if (T.cap > (AB_SM_WORDS - AB_SM_OFF_G16)) { T.overflow = true; continue; } yval = c.sm + AB_SM_OFF_G16; }
         else { const long long at = ((long long)m + want * AB_TW + 1) & ~1LL; if (at + yv_words > c.A.limit) { fail(c, ST_ARENA); return false; } yval = base + at; }
+        #pragma unroll 1
         for (int pass = 0; pass < 2 && !T.overflow; ++pass) {
             const TM& t = pass ? y : x;
+            #pragma unroll 1
             for (int j0 = 0; j0 < t.n; j0 += W) {
                 const int j = j0 + lane; const bool act = j < t.n;
                 Key k = key_zero(); double tv = 0.0;
@@ -1017,6 +1059,7 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
         if (T.overflow) { if (attempt == 1) { fail(c, ST_ARENA); return false; } continue; }
         // per key: src/taylor_model.cpp:2905-2945
         double lmax = 0.0; bool bad = false;
+        #pragma unroll 1
         for (int s = lane; s < T.nd; s += W) {
             const double xv = u2d(T.val[s]), yv = u2d(yval[s]);
             double xu = add_ru(xv, xe), yu = add_ru(yv, ye), mxl = sub_ru(xe, xv), myl = sub_ru(ye, yv);
@@ -1031,6 +1074,7 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
         }
         wsync();
         disjoint = wany(bad);
+        #pragma unroll 1
         for (int l = 0; l < W; ++l) tme = dmax(tme, wshfl(lmax, l));
         break;
     }

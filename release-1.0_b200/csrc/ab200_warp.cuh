@@ -70,25 +70,28 @@ AB_HD unsigned lanemask_lt(int lane) { return (lane >= 32) ? 0xFFFFFFFFu : ((1u 
 
 // s <- up(...up(up(s + v[0]) + v[1])... + v[cnt-1]) with v[k] the value lane k holds: the reference's term-by-term upward
 // sum, one dependent DADD per term. Every lane computes the same chain, so the result is warp-uniform. Adding +0 leaves a
-// non-negative sum unchanged, which lets callers pass 0 for terms that do not contribute.
-AB_HD double chain_ru(double s, double v, int cnt) {
-#if defined(__CUDA_ARCH__)
-    if (cnt >= 32) {
-        #pragma unroll
-        for (int k = 0; k < 32; ++k) s = add_ru(s, __shfl_sync(0xFFFFFFFFu, v, k));
-        return s;
+// non-negative sum unchanged, which lets callers pass 0 for terms that do not contribute. (One copy of each chain in the
+// kernel -- not inlined -- to keep the instruction footprint of the primitives small.)
+AB_HDN double chain_ru(double s, double v, int cnt) {
+    int k = 0;
+    #pragma unroll 1
+    for (; k + 4 <= cnt; k += 4) {
+        const double a = wshfl(v, k), b = wshfl(v, k + 1), cc = wshfl(v, k + 2), d = wshfl(v, k + 3);
+        s = add_ru(add_ru(add_ru(add_ru(s, a), b), cc), d);
     }
-#endif
-    for (int k = 0; k < cnt; ++k) s = add_ru(s, wshfl(v, k));
+    #pragma unroll 1
+    for (; k < cnt; ++k) s = add_ru(s, wshfl(v, k));
     return s;
 }
 // the same chain in a run-time rounding mode (the reference's ambient MXCSR state)
-AB_HD double chain_m(int m, double s, double v, int cnt) {
+AB_HDN double chain_m(int m, double s, double v, int cnt) {
+    #pragma unroll 1
     for (int k = 0; k < cnt; ++k) s = add_m(m, s, wshfl(v, k));
     return s;
 }
 // Chain over the lanes flagged in `mask` only, in lane order.
-AB_HD double chain_ru_masked(double s, double v, unsigned mask) {
+AB_HDN double chain_ru_masked(double s, double v, unsigned mask) {
+    #pragma unroll 1
     while (mask) { const int k = ffs32(mask) - 1; mask &= mask - 1; s = add_ru(s, wshfl(v, k)); }
     return s;
 }

@@ -22,6 +22,9 @@
 #include <algorithm>
 
 using namespace ab200;
+#ifdef AB_COMPOSE_STATS
+namespace ab200 { inline namespace AB_VARIANT { long long g_cs[8] = {0}; } }
+#endif
 #ifdef AB_MUL_HIST
 long long ab200::g_mul_hist[8][8] = {{0}};
 long long ab200::g_calls[16] = {0}, ab200::g_words[16] = {0};
@@ -170,6 +173,9 @@ int main(int argc, char** argv) {
         } else if (verbose) printf("cell %zu ok: %d reach, %d final, %d steps\n", ci, O.n_reach, O.n_final, O.steps);
     }
     printf("cells compared %d, mismatching %d, steps %ld, arena peak words %d\n", done, bad, total_steps, peak);
+#ifdef AB_COMPOSE_STATS
+    printf("per step: compose calls %.1f, x terms %.1f, term muls %.1f (products %.0f), of which single-term-factor %.1f\n", (double)g_cs[0] / total_steps, (double)g_cs[1] / total_steps, (double)g_cs[2] / total_steps, (double)g_cs[3] / total_steps, (double)g_cs[4] / total_steps);
+#endif
 #ifdef AB_MUL_HIST
     { const char* nm[] = {"add2", "add_many(r terms)", "slide(moved)", "copy", "scal(Float)", "scal(Interval)", "neg", "range", "-", "add_many(streams)", "mul batches(outputs)", "mul batches(products)"};
       for (int i = 0; i < 12; ++i) printf("  %-20s %8.1f calls/step %10.1f terms/step\n", nm[i], (double)g_calls[i] / total_steps, (double)g_words[i] / total_steps); }
