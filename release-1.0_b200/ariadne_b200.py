@@ -57,6 +57,8 @@ class Ab200Error(RuntimeError):
 
 
 def library_path():
+    if os.environ.get("AB200_LIBRARY"):      # development hook: a differently tuned build of the same sources
+        return os.environ["AB200_LIBRARY"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libariadne_b200.so")
 
 

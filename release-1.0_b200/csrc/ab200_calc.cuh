@@ -253,9 +253,21 @@ AB_HDN double flow_bounds(Ctx& c, const TapeOp* ops, const Func* vf, int n, cons
 // ---- compose ------------------------------------------------------------------------------------------------------
 // Power-table handles are kept in the arena (3 words each) to keep per-thread local memory small.
 #define AB_MAXPOW 40
+#define AB_PHW 3            // words per power-table handle: offset|count, error, norm (filled on first use)
+#define AB_NORM_UNSET 0x7FF8AB200AB20001ull
 AB_HD void ph_store(Ctx& c, int slot, const TM& t) {
     aw(c, slot) = ((uint64_t)(uint32_t)t.off << 32) | (uint32_t)t.n;
     aw(c, slot + 1) = d2u(t.e);
+    aw(c, slot + 2) = AB_NORM_UNSET;
+}
+// sum of the coefficient magnitudes of a power (upward, in term order, from zero: the `ys` of _mul4), computed once
+AB_HD double ph_norm(Ctx& c, int slot, const TM& t) {
+    const uint64_t w = aw(c, slot + 2);
+    if (w != AB_NORM_UNSET) return u2d(w);
+    const double nm = tm_abs_sum(c, t, 0.0, true, 0);
+    wsync();                       // every lane has read the slot before it is filled
+    aw(c, slot + 2) = d2u(nm);
+    return nm;
 }
 AB_HD TM ph_load(Ctx& c, int slot, int as, Acc acc) {
     TM t; uint64_t w = aw(c, slot); t.off = (int)(w >> 32); t.n = (int)(w & 0xFFFFFFFFu); t.e = u2d(aw(c, slot + 1)); t.as = as; t.acc = acc; return t;
@@ -346,7 +358,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     int tab[AB_MAXARGS + 1];
     int slot = m0;
     #pragma unroll 1
-    for (int j = 0; j < nys; ++j) { tab[j] = slot; slot += 2 * (maxp[j] + 1); if (maxp[j] >= AB_MAXPOW) fail(c, ST_ARENA); }
+    for (int j = 0; j < nys; ++j) { tab[j] = slot; slot += AB_PHW * (maxp[j] + 1); if (maxp[j] >= AB_MAXPOW) fail(c, ST_ARENA); }
     if (slot > c.A.limit) { fail(c, ST_ARENA); for (int i = 0; i < nx; ++i) r[i] = tm_begin(c, as, acc0); return; }
     c.A.top = slot;
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
@@ -354,13 +366,13 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     for (int j = 0; j < nys; ++j) {
         TM p0 = tm_copy(c, ys[j]); tm_scal(c, p0, 0.0); c.A.top = p0.off;       // powers[j][0]=ys[j]*0
         ph_store(c, tab[j], p0);
-        ph_store(c, tab[j] + 2, ys[j]);                                          // powers[j][1]=ys[j]
+        ph_store(c, tab[j] + AB_PHW, ys[j]);                                          // powers[j][1]=ys[j]
         #pragma unroll 1
         for (int k = 2; k <= maxp[j]; ++k) {
-            TM a = ph_load(c, tab[j] + 2 * (k / 2), as, ys[j].acc);
-            TM b = ph_load(c, tab[j] + 2 * ((k + 1) / 2), as, ys[j].acc);
+            TM a = ph_load(c, tab[j] + AB_PHW * (k / 2), as, ys[j].acc);
+            TM b = ph_load(c, tab[j] + AB_PHW * ((k + 1) / 2), as, ys[j].acc);
             TM pk = tm_mul(c, a, b, ys[j].acc);
-            ph_store(c, tab[j] + 2 * k, pk);
+            ph_store(c, tab[j] + AB_PHW * k, pk);
         }
     }
     const int mr = c.A.top;     // results start here; slid down to m0 at the end
@@ -371,6 +383,71 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     for (int i = 0; i < nx; ++i) {
         const int ri = c.A.top;
         TM ra = tm_begin(c, as, acc0);
+        ra.e = x[i].e;
+        // r[i] = sum over the terms of x[i], in term order, of t = c * prod_j powers[j][e_j]. The running sum stays in the
+        // shared-memory accumulator while the terms stream through it (no intermediate merges); a term whose product chain
+        // needs a general product -- which uses the accumulator itself -- first parks the sum in the arena at ri.
+        bool streamed = false;
+        if (c.sm && (long long)ri + (long long)(AB_SM_CAP + 8) * AB_TW < (long long)c.A.limit) {
+            const int sbase = ri + AB_SM_CAP * AB_TW;           // product chains are built above the room kept for the parked sum
+            AccTab T; bool open = false, failed = false; int dmax = 0; double e_run = x[i].e;
+            #pragma unroll 1
+            Key pk = key_zero(); double pv = 0.0;               // this lane's term of the current chunk of x[i]
+            const int W = AB_W, lane = c.lane;
+            #pragma unroll 1
+            for (int t = 0; t < x[i].n && !failed; ++t) {
+                if (t % W == 0) { const int q = t + lane; if (q < x[i].n) { pk = tm_key(c, x[i], q); pv = tm_val(c, x[i], q); } }
+                Key a; for (int w = 0; w < AB_KW; ++w) a.w[w] = wshfl(pk.w[w], t % W);
+                const double cv = wshfl(pv, t % W);
+                c.A.top = sbase;
+                TM tt; bool started = false;
+                if (cv == 0.0) { tt = tm_const(c, as, cv, acc0); started = true; }
+                #pragma unroll 1
+                for (int j = 0; j < nys; ++j) {
+                    const int e = key_get(a, j);
+                    if (e == 0) continue;
+                    const TM pw = ph_load(c, tab[j] + AB_PHW * e, as, ys[j].acc);
+                    if (!started) {
+                        if (pw.n == 0) { tt = tm_const(c, as, cv, acc0); tt = tm_mul(c, tt, pw, ys[j].acc); }
+                        else tt = term_times_power(c, cv, pw, ys[j].acc);
+                        started = true;
+                    } else if (pw.n == 1 && tt.n >= 1 && tm_end(tt) == c.A.top) term_times_monomial(c, tt, pw, ys[j].acc);
+                    else if (tt.n == 0) {
+                        // every product so far was discarded: _mul4 with an empty left factor leaves only the error cross terms
+                        const double nm = (tt.e != 0.0) ? ph_norm(c, tab[j] + AB_PHW * e, pw) : 0.0;
+                        tt.e = add_ru(0.0, add_ru(add_ru(mul_ru(0.0, pw.e), mul_ru(nm, tt.e)), mul_ru(tt.e, pw.e)));
+                        tt.acc = ys[j].acc; c.rnd = RN;
+                    } else {
+                        if (tt.n > 1 && pw.n > 1 && open) {      // general product ahead: it needs the accumulator
+                            ra.n = acc_emit(c, T, as, dmax, ri); ra.e = e_run; open = false;
+                        }
+                        tt = tm_mul(c, tt, pw, ys[j].acc);
+                    }
+                }
+                if (!started) tt = tm_const(c, as, cv, acc0);
+                if (c.status != ST_OK) { failed = true; break; }
+                if (!open) {
+                    const int keep = c.A.top;
+                    if (!acc_open(c, T, 0, keep, AB_SM_CAP)) { failed = true; break; }
+                    acc_add_model(c, T, ra);
+                    open = true;
+                }
+                const double te = T.overflow ? 0.0 : acc_add_model(c, T, tt);
+                if (T.overflow) { failed = true; break; }
+                { const int d = tm_degree(c, tt); if (d > dmax) dmax = d; }
+                e_run = add_ru(add_ru(e_run, tt.e), te / 2);
+            }
+            if (!failed) {
+                if (open) { ra.n = acc_emit(c, T, as, dmax, ri); }
+                ra.e = e_run; ra.off = ri;
+                c.rnd = RN;
+                streamed = true;
+            } else if (c.status != ST_OK) { for (int q = i; q < nx; ++q) r[q] = tm_begin(c, as, acc0); return; }
+        }
+        if (!streamed) {
+        // batched form (no shared area, or a sum too large for it): products of up to AB_MAXSTREAMS terms, then one addition
+        c.A.top = ri;
+        ra = tm_begin(c, as, acc0);
         ra.e = x[i].e;
         #pragma unroll 1
         for (int t0 = 0; t0 < x[i].n; t0 += AB_MAXSTREAMS) {
@@ -383,16 +460,16 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                 const Key a = tm_key(c, x[i], t);
                 const double cv = tm_val(c, x[i], t);
                 // t=c; t=t*powers[j][e] for every variable with a positive exponent. The first product scales a power by the
-                // coefficient, and a product with a one-term power (powers of the time variable) only shifts and scales the
-                // terms: both are done without building the constant model or leaving a copy behind (same arithmetic as
-                // _mul4 on those operands, see term_times_power / term_times_monomial).
+                // coefficient, and a product with a one-term power only shifts and scales the terms: both are done without
+                // building the constant model or leaving a copy behind (same arithmetic as _mul4 on those operands, see
+                // term_times_power / term_times_monomial).
                 TM tt; bool started = false;
                 if (cv == 0.0) { tt = tm_const(c, as, cv, acc0); started = true; }
                 #pragma unroll 1
                 for (int j = 0; j < nys; ++j) {
                     const int e = key_get(a, j);
                     if (e == 0) continue;
-                    const TM pw = ph_load(c, tab[j] + 2 * e, as, ys[j].acc);
+                    const TM pw = ph_load(c, tab[j] + AB_PHW * e, as, ys[j].acc);
 #ifdef AB_COMPOSE_STATS
                     if (c.lane == 0) { extern long long g_cs[8]; g_cs[2]++; g_cs[3] += (long long)(started ? tt.n : 1) * pw.n; if (!started || tt.n <= 1 || pw.n <= 1) g_cs[4]++; }
 #endif
@@ -410,6 +487,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
             TM s = tm_add_many(c, ra, st, B, acc0);          // r[i]+=t for the B terms, in order
             tm_slide(c, s, ri);
             ra = s;
+        }
         }
         c.A.top = ra.off + ra.n * AB_TW;
         r[i] = ra;

@@ -270,6 +270,10 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             build = find_build(tune);
         }
         int slots; DEV_CK((slots = build->capacity(eb_, sizeof(eb_))) < 0);
+        if (const char* e = getenv("AB200_SLOTS_PER_SM")) {     // development hook: fewer resident cells per SM than the occupancy allows
+            int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            if (atoi(e) > 0 && sms * atoi(e) < slots) slots = sms * atoi(e);
+        }
         if (slots > nb) slots = nb;
         CTX_CK(ctx->d_arena.ensure((size_t)slots * S.arena_words));
         CTX_CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream));

@@ -486,6 +486,55 @@ AB_HD uint32_t key_rank(const uint32_t* tab, const Key& k, int as) {
     }
     return r;
 }
+// Ordering of the accumulator for monomial spaces too large for the rank bitmap: bitonic sort of the entry numbers by key
+// (in the hash index area, which is no longer needed). Kept out of acc_emit so that the common path stays small.
+AB_HDN int acc_emit_sorted(Ctx& c, const AccTab T, int dst) {
+    const int W = AB_W, lane = c.lane, nd = T.nd;
+    uint64_t* const base = c.A.base;
+    int P = 1; while (P < nd) P <<= 1;
+    uint32_t* perm = T.idx;                       // index area holds >= 2*cap cells
+    #pragma unroll 1
+    for (int i = lane; i < P; i += W) perm[i] = (i < nd && T.val[i] != AB_ABSENT) ? (uint32_t)i : AB_IDX_EMPTY;
+    wsync();
+    #pragma unroll 1
+    for (int kk = 2; kk <= P; kk <<= 1) for (int j = kk >> 1; j > 0; j >>= 1) {
+        #pragma unroll 1
+        for (int t = lane; t < P; t += W) {
+            const int o = t ^ j;
+            if (o > t) {
+                const uint32_t a = perm[t], b = perm[o];
+                bool b_lt_a;
+                if (b == AB_IDX_EMPTY) b_lt_a = false; else if (a == AB_IDX_EMPTY) b_lt_a = true;
+                else {
+                    Key ka, kb; ka.w[0] = T.key[a]; kb.w[0] = T.key[b];
+#if AB_KW > 1
+                    ka.w[1] = T.key[T.cap + a]; kb.w[1] = T.key[T.cap + b];
+#endif
+                    b_lt_a = key_less(kb, ka);
+                }
+                const bool asc = (t & kk) == 0;
+                if (b_lt_a == asc) { perm[t] = b; perm[o] = a; }
+            }
+        }
+        wsync();
+    }
+    int total = 0;
+    #pragma unroll 1
+    for (int i0 = 0; i0 < nd; i0 += W) {
+        const int i = i0 + lane; const uint32_t s = (i < nd) ? perm[i] : AB_IDX_EMPTY;
+        const unsigned m = wballot(s != AB_IDX_EMPTY);
+        if (s != AB_IDX_EMPTY) {
+            Key k; k.w[0] = T.key[s];
+#if AB_KW > 1
+            k.w[1] = T.key[T.cap + s];
+#endif
+            bput(base, dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW, k, u2d(T.val[s]));
+        }
+        total += popc32(m);
+    }
+    wsync();
+    return total;
+}
 // Write the accumulator to the arena at word `dst` in key order, skipping dropped entries; returns the number of terms.
 // `scratch` is shared (or arena) memory free for the ordering: gap-code and staging areas when the table is in shared memory.
 AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
@@ -545,50 +594,7 @@ AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
         wsync();
         return total;
     }
-    // general ordering: bitonic sort of the entry numbers by key (uses the hash index area, no longer needed)
-    int P = 1; while (P < nd) P <<= 1;
-    uint32_t* perm = T.idx;                       // index area holds >= 2*cap cells
-    #pragma unroll 1
-    for (int i = lane; i < P; i += W) perm[i] = (i < nd && T.val[i] != AB_ABSENT) ? (uint32_t)i : AB_IDX_EMPTY;
-    wsync();
-    #pragma unroll 1
-    for (int kk = 2; kk <= P; kk <<= 1) for (int j = kk >> 1; j > 0; j >>= 1) {
-        #pragma unroll 1
-        for (int t = lane; t < P; t += W) {
-            const int o = t ^ j;
-            if (o > t) {
-                const uint32_t a = perm[t], b = perm[o];
-                bool b_lt_a;
-                if (b == AB_IDX_EMPTY) b_lt_a = false; else if (a == AB_IDX_EMPTY) b_lt_a = true;
-                else {
-                    Key ka, kb; ka.w[0] = T.key[a]; kb.w[0] = T.key[b];
-#if AB_KW > 1
-                    ka.w[1] = T.key[T.cap + a]; kb.w[1] = T.key[T.cap + b];
-#endif
-                    b_lt_a = key_less(kb, ka);
-                }
-                const bool asc = (t & kk) == 0;
-                if (b_lt_a == asc) { perm[t] = b; perm[o] = a; }
-            }
-        }
-        wsync();
-    }
-    int total = 0;
-    #pragma unroll 1
-    for (int i0 = 0; i0 < nd; i0 += W) {
-        const int i = i0 + lane; const uint32_t s = (i < nd) ? perm[i] : AB_IDX_EMPTY;
-        const unsigned m = wballot(s != AB_IDX_EMPTY);
-        if (s != AB_IDX_EMPTY) {
-            Key k; k.w[0] = T.key[s];
-#if AB_KW > 1
-            k.w[1] = T.key[T.cap + s];
-#endif
-            bput(base, dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW, k, u2d(T.val[s]));
-        }
-        total += popc32(m);
-    }
-    wsync();
-    return total;
+    return acc_emit_sorted(c, T, dst);
 }
 
 // ---- binary operations: results are begun at the arena top ------------------------------------------------------
@@ -679,11 +685,10 @@ AB_HD double gap_value(uint32_t code) { return u2d((uint64_t)code << 52); }
 extern long long g_mul_hist[8][8];   // [log2 bucket of x.n][log2 bucket of y.n]
 extern long long g_mul_prod[8][8];
 #endif
-AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
-#ifdef AB_MUL_HIST
-    if (c.lane == 0) { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
-#endif
-    AB_FLOPS((double)x.n * (5.0 * y.n + 3.0) + 2.0 * (x.n + y.n) + 6.0);
+// A product with an empty or one-term factor (constants, variables and monomials of the op tapes, nearly discarded terms of
+// a composition). Adding a fixed key keeps the key order, so the product streams never meet: the result is written directly,
+// compacted over the discarded products, and the error chain of the general path reduces to the truncation terms.
+AB_HDN TM tm_mul_simple(Ctx& c, const TM& x, const TM& y, Acc acc) {
     uint64_t* const base = c.A.base;
     const int W = AB_W, lane = c.lane;
     const int m = c.A.top;
@@ -704,9 +709,6 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         return r;
     }
     if (xn == 1 || yn == 1) {
-        // A single-term factor (constants, variables and monomials of the op tapes). Adding a fixed key keeps the key
-        // order, so the product streams never meet: the result is written directly, compacted over the discarded
-        // products, and the error chain of the general path reduces to the truncation terms.
         double e = 0.0, xs = 0.0, ys = 0.0;
         int rn = 0;
         const bool one_x = (xn == 1);
@@ -744,6 +746,18 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
         arena_mark_peak(c);
         return r;
     }
+    #undef AB_DISCARD
+    return r;
+}
+AB_HDN TM tm_mul_general(Ctx& c, const TM& x, const TM& y, Acc acc) {
+    uint64_t* const base = c.A.base;
+    const int W = AB_W, lane = c.lane;
+    const int m = c.A.top;
+    const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
+    const double xe = x.e, ye = y.e;
+    const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
+    #define AB_DISCARD(k, v) (dabs(v) < sweep || key_deg(k) > maxdeg)
+    TM r; r.off = m; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc;
     // ---- general product ------------------------------------------------------------------------------------------
     // An upper bound of the number of result terms: distinct monomials of degree <= min(maxdeg, deg x + deg y).
     int D = tm_degree(c, x) + tm_degree(c, y); if (D > maxdeg) D = maxdeg;
@@ -856,6 +870,13 @@ AB_HDN TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
     c.A.top = m + r.n * AB_TW;
     arena_mark_peak(c);
     return r;
+}
+AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
+#ifdef AB_MUL_HIST
+    if (c.lane == 0) { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
+#endif
+    AB_FLOPS((double)x.n * (5.0 * y.n + 3.0) + 2.0 * (x.n + y.n) + 6.0);
+    return (x.n <= 1 || y.n <= 1) ? tm_mul_simple(c, x, y, acc) : tm_mul_general(c, x, y, acc);
 }
 AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc); }
 

@@ -72,7 +72,14 @@ AB_HD unsigned lanemask_lt(int lane) { return (lane >= 32) ? 0xFFFFFFFFu : ((1u 
 // sum, one dependent DADD per term. Every lane computes the same chain, so the result is warp-uniform. Adding +0 leaves a
 // non-negative sum unchanged, which lets callers pass 0 for terms that do not contribute. (One copy of each chain in the
 // kernel -- not inlined -- to keep the instruction footprint of the primitives small.)
+#ifdef AB_COMPOSE_STATS
+extern long long g_cs[8];
+#define AB_CHAIN_STAT(i, n) do { if (wlane() == 0) { g_cs[i] += (n); } } while (0)
+#else
+#define AB_CHAIN_STAT(i, n)
+#endif
 AB_HDN double chain_ru(double s, double v, int cnt) {
+    AB_CHAIN_STAT(5, cnt);
     int k = 0;
     #pragma unroll 1
     for (; k + 4 <= cnt; k += 4) {
@@ -91,6 +98,7 @@ AB_HDN double chain_m(int m, double s, double v, int cnt) {
 }
 // Chain over the lanes flagged in `mask` only, in lane order.
 AB_HDN double chain_ru_masked(double s, double v, unsigned mask) {
+    AB_CHAIN_STAT(6, popc32(mask)); AB_CHAIN_STAT(7, 1);
     #pragma unroll 1
     while (mask) { const int k = ffs32(mask) - 1; mask &= mask - 1; s = add_ru(s, wshfl(v, k)); }
     return s;

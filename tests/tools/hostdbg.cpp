@@ -175,6 +175,7 @@ int main(int argc, char** argv) {
     printf("cells compared %d, mismatching %d, steps %ld, arena peak words %d\n", done, bad, total_steps, peak);
 #ifdef AB_COMPOSE_STATS
     printf("per step: compose calls %.1f, x terms %.1f, term muls %.1f (products %.0f), of which single-term-factor %.1f\n", (double)g_cs[0] / total_steps, (double)g_cs[1] / total_steps, (double)g_cs[2] / total_steps, (double)g_cs[3] / total_steps, (double)g_cs[4] / total_steps);
+    printf("per step: chain_ru elements %.0f, chain_ru_masked elements %.0f in %.0f calls\n", (double)g_cs[5] / total_steps, (double)g_cs[6] / total_steps, (double)g_cs[7] / total_steps);
 #endif
 #ifdef AB_MUL_HIST
     { const char* nm[] = {"add2", "add_many(r terms)", "slide(moved)", "copy", "scal(Float)", "scal(Interval)", "neg", "range", "-", "add_many(streams)", "mul batches(outputs)", "mul batches(products)"};
