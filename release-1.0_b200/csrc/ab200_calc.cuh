@@ -390,8 +390,10 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
         bool streamed = false;
         if (c.sm && (long long)ri + (long long)(AB_SM_CAP + 8) * AB_TW < (long long)c.A.limit) {
             const int sbase = ri + AB_SM_CAP * AB_TW;           // product chains are built above the room kept for the parked sum
-            AccTab T; bool open = false, failed = false; int dmax = 0; double e_run = x[i].e;
-            #pragma unroll 1
+            AccTab T; DAcc DA; bool open = false, failed = false; int dmax = 0; double e_run = x[i].e;
+            int Dc = 0; for (int j = 0; j < nys; ++j) if (ys[j].acc.maxdeg > Dc) Dc = ys[j].acc.maxdeg;
+            const bool dense = dacc_fits(c, as, Dc);             // every product is cut at its factor's degree limit
+            T.overflow = false;
             Key pk = key_zero(); double pv = 0.0;               // this lane's term of the current chunk of x[i]
             const int W = AB_W, lane = c.lane;
             #pragma unroll 1
@@ -419,7 +421,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                         tt.acc = ys[j].acc; c.rnd = RN;
                     } else {
                         if (tt.n > 1 && pw.n > 1 && open) {      // general product ahead: it needs the accumulator
-                            ra.n = acc_emit(c, T, as, dmax, ri); ra.e = e_run; open = false;
+                            ra.n = dense ? dacc_emit(c, DA, ri) : acc_emit(c, T, as, dmax, ri); ra.e = e_run; open = false;
                         }
                         tt = tm_mul(c, tt, pw, ys[j].acc);
                     }
@@ -428,17 +430,17 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                 if (c.status != ST_OK) { failed = true; break; }
                 if (!open) {
                     const int keep = c.A.top;
-                    if (!acc_open(c, T, 0, keep, AB_SM_CAP)) { failed = true; break; }
-                    acc_add_model(c, T, ra);
+                    if (dense) { dacc_open(c, DA, as, Dc); dacc_add_model(c, DA, ra, false); }
+                    else { if (!acc_open(c, T, 0, keep, AB_SM_CAP)) { failed = true; break; } acc_add_model(c, T, ra); }
                     open = true;
                 }
-                const double te = T.overflow ? 0.0 : acc_add_model(c, T, tt);
+                const double te = dense ? dacc_add_model(c, DA, tt, true) : (T.overflow ? 0.0 : acc_add_model(c, T, tt));
                 if (T.overflow) { failed = true; break; }
                 { const int d = tm_degree(c, tt); if (d > dmax) dmax = d; }
                 e_run = add_ru(add_ru(e_run, tt.e), te / 2);
             }
             if (!failed) {
-                if (open) { ra.n = acc_emit(c, T, as, dmax, ri); }
+                if (open) { ra.n = dense ? dacc_emit(c, DA, ri) : acc_emit(c, T, as, dmax, ri); }
                 ra.e = e_run; ra.off = ri;
                 c.rnd = RN;
                 streamed = true;
@@ -532,15 +534,18 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     double* const TS = (double*)(base + mr); double* const TE = TS + npair;
     const int sums_end = mr + 2 * npair;
     if (sums_end > c.A.peak) c.A.peak = sums_end;
-    AccTab T;
+    AccTab T; DAcc DA;
+    const bool dense = dacc_fits(c, tm.as, deg);
+    T.overflow = false;
     #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (!acc_open(c, T, attempt, sums_end + (int)want * AB_TW, want)) return res;
+        if (dense) dacc_open(c, DA, tm.as, deg);
+        else if (!acc_open(c, T, attempt, sums_end + (int)want * AB_TW, want)) return res;
         // gap codes of one bucket: one 32-bit cell per (i, term): low half scaling gap, high half coincidence gap
         uint32_t* G; int gcap;
         if (c.sm) { G = (uint32_t*)(c.sm + AB_SM_OFF_G16); gcap = AB_SM_G16 / 2; }
         else {
-            const long long at = (T.val + T.cap) - base; int mx = 1; for (int b = 0; b <= deg; ++b) if (bn[b] > mx) mx = bn[b];
+            const long long at = dense ? sums_end : (T.val + T.cap) - base; int mx = 1; for (int b = 0; b <= deg; ++b) if (bn[b] > mx) mx = bn[b];
             if (at + (mx + 1) / 2 + 1 > (long long)c.A.limit) { fail(c, ST_ARENA); return res; }
             G = (uint32_t*)(base + at); gcap = mx;
         }
@@ -571,10 +576,10 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
                         else if (sf == 2 || sf == 0.5) tv = mul_m(md, v, sf);
                         else { gs = add_ru(mul_ru(v, sf), mul_ru(v, -sf)); tv = mul_rn(v, sf); }
                     }
-                    const int slot = acc_slot(T, act, key, lane);
+                    const int slot = dense ? 0 : acc_slot(T, act, key, lane);
                     if (T.overflow) break;
                     if (act) {
-                        const double ga = acc_fold(T, slot, tv);
+                        const double ga = dense ? dacc_fold(DA, dacc_rank(DA, key), key, tv) : acc_fold(T, slot, tv);
                         G[w] = gap_code(gs, &badgap) | (gap_code(ga, &badgap) << 16);
                     }
                 }
@@ -607,7 +612,7 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
         }
     wsync();
     res.off = m0;
-    res.n = acc_emit(c, T, tm.as, deg, m0);           // the buckets are no longer needed: the result lands at m0
+    res.n = dense ? dacc_emit(c, DA, m0) : acc_emit(c, T, tm.as, deg, m0);      // the buckets are no longer needed: the result lands at m0
     res.e = e;
     c.A.top = m0 + res.n * AB_TW;
     arena_mark_peak(c);

@@ -130,6 +130,7 @@ struct CellState {
 AB_HDN void cell_begin(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellState& st) {
     Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
     const int n0 = S.loc[loc0].n;
+    ctx_stage_tables(c);
     st.qcap = (P.max_working_sets > 0 && P.max_working_sets < AB_MAXQ) ? P.max_working_sets : AB_MAXQ;
     st.qbase = c.A.top;
     if ((long long)st.qbase + (long long)(st.qcap + AB_MAXEV + 1) * AB_QW + 64 > (long long)c.A.limit) { fail(c, ST_ARENA); st.nq = 0; return; }

@@ -321,17 +321,24 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
     c.rnd = RN;
 }
 
-// ---- the sparse accumulator ----------------------------------------------------------------------------------------
+// ---- the accumulators ---------------------------------------------------------------------------------------------
 // Shared-memory staging area of one warp, in 64-bit words:
-//   [ hash index: AB_SM_NIDX uint32 | keys: AB_KW x AB_SM_CAP | coefficients: AB_SM_CAP | gap codes: AB_SM_G16 uint16 |
-//     staged factor: keys AB_KW x AB_SM_YCAP, coefficients AB_SM_YCAP ]
-// When an accumulator outgrows the shared area it is rebuilt in the free part of the arena (same code, generic pointers).
+//   [ accumulator: AB_SM_ACCW | rank table: AB_SM_BTABW | gap codes: AB_SM_G16 uint16 | staged factor: keys AB_KW x AB_SM_YCAP,
+//     coefficients AB_SM_YCAP ]
+// The accumulator area holds either the DENSE accumulator (structure-of-arrays keys | coefficients indexed by the monomial's
+// rank in the graded order: no search, no insertion, emission is a scan) when the monomial space of the result fits, or the
+// hash accumulator (index | keys | coefficients) otherwise. When even that is outgrown the hash accumulator is rebuilt in the
+// free part of the arena (same code, generic pointers).
+#ifndef AB_SM_ACCW
+#define AB_SM_ACCW 2048
+#endif
+#define AB_SM_BTABW 128
+#define AB_SM_DENSE (AB_SM_ACCW / (AB_KW + 1))          // ranks the dense accumulator can hold
+#define AB_BTAB_STRIDE 36                               // rank-table row: sums of exponents 0..35
 #ifndef AB_SM_NIDX
 #define AB_SM_NIDX 1024
 #endif
-#ifndef AB_SM_CAP
-#define AB_SM_CAP 448
-#endif
+#define AB_SM_CAP ((AB_SM_ACCW - AB_SM_NIDX / 2) / (AB_KW + 1))
 #ifndef AB_SM_G16
 #define AB_SM_G16 4096
 #endif
@@ -341,10 +348,33 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
 #define AB_SM_OFF_IDX 0
 #define AB_SM_OFF_KEY (AB_SM_NIDX / 2)
 #define AB_SM_OFF_VAL (AB_SM_OFF_KEY + AB_KW * AB_SM_CAP)
-#define AB_SM_OFF_G16 (AB_SM_OFF_VAL + AB_SM_CAP)
+#define AB_SM_OFF_BTAB AB_SM_ACCW
+#define AB_SM_OFF_G16 (AB_SM_ACCW + AB_SM_BTABW)
 #define AB_SM_OFF_YK (AB_SM_OFF_G16 + AB_SM_G16 / 4)
 #define AB_SM_OFF_YV (AB_SM_OFF_YK + AB_KW * AB_SM_YCAP)
 #define AB_SM_WORDS (AB_SM_OFF_YV + AB_SM_YCAP)
+
+// Shared-memory accesses by 32-bit shared address (device) so that the hot loops use LDS/STS instead of generic loads with
+// 64-bit address arithmetic; plain pointers in the host builds.
+#if defined(__CUDA_ARCH__)
+typedef uint32_t smaddr_t;
+AB_HD smaddr_t sm_addr(const void* p) { return (smaddr_t)__cvta_generic_to_shared(p); }
+AB_HD uint64_t sm_ld64(smaddr_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return (uint64_t)v; }
+AB_HD void sm_st64(smaddr_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"((unsigned long long)v) : "memory"); }
+AB_HD uint32_t sm_ld32(smaddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+AB_HD void sm_st32(smaddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+AB_HD uint32_t sm_ld16(smaddr_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return (uint32_t)v; }
+AB_HD void sm_st16(smaddr_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v) : "memory"); }
+#else
+typedef uintptr_t smaddr_t;
+inline smaddr_t sm_addr(const void* p) { return (smaddr_t)p; }
+inline uint64_t sm_ld64(smaddr_t a) { return *(const uint64_t*)a; }
+inline void sm_st64(smaddr_t a, uint64_t v) { *(uint64_t*)a = v; }
+inline uint32_t sm_ld32(smaddr_t a) { return *(const uint32_t*)a; }
+inline void sm_st32(smaddr_t a, uint32_t v) { *(uint32_t*)a = v; }
+inline uint32_t sm_ld16(smaddr_t a) { return *(const uint16_t*)a; }
+inline void sm_st16(smaddr_t a, uint32_t v) { *(uint16_t*)a = (uint16_t)v; }
+#endif
 
 #define AB_IDX_EMPTY 0xFFFFFFFFu
 #define AB_ABSENT 0x7FF8AB200AB200ABull      // coefficient slot of a key whose sum cancelled to zero (dropped, as _add2 does)
@@ -597,6 +627,103 @@ AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
     return acc_emit_sorted(c, T, dst);
 }
 
+// ---- the dense accumulator -----------------------------------------------------------------------------------------------
+// Entry r holds the monomial of rank r in the graded order (include/multi_index.h:346-358) among all monomials of degree <= D
+// in `as` variables: rank = sum_{k=1..as} C(S_k - 1 + k, k), S_k = sum of the last k exponents (S_as = degree). The sums S_k are
+// the bytes of (packed exponents) x 0x0101..01, the binomials come from a small table staged in shared memory, so a product
+// finds its entry with one multiply and `as` table reads. An entry whose coefficient is AB_ABSENT is empty.
+struct DAcc {
+    smaddr_t key, val, btab;    // shared addresses: key word w of rank r at key + 8*(w*AB_SM_DENSE + r), coefficient at val + 8*r
+    int R;                      // ranks in use
+    int as;
+};
+AB_HD bool dacc_fits(const Ctx& c, int as, int D) {
+    if (!c.sm || !c.binom || as < 1 || as > 7 || D < 0 || D >= AB_BTAB_STRIDE) return false;
+    return monomial_count(c.binom, D, as) <= (long long)AB_SM_DENSE;
+}
+// The rank table B[k][s] = C(s-1+k, k), k = 1..7, s = 0..35, staged once per cell (ctx_stage_tables).
+AB_HDN void ctx_stage_tables(Ctx& c) {
+    if (!c.sm || !c.binom) return;
+    const int W = AB_W, lane = c.lane;
+    const smaddr_t bt = sm_addr(c.sm + AB_SM_OFF_BTAB);
+    wsync();
+    #pragma unroll 1
+    for (int q = lane; q < 7 * AB_BTAB_STRIDE; q += W) {
+        const int k = q / AB_BTAB_STRIDE + 1, sk = q - (k - 1) * AB_BTAB_STRIDE;
+        sm_st32(bt + 4u * (uint32_t)q, sk >= 1 ? binom_at(c.binom, sk - 1 + k, k) : 0u);
+    }
+    wsync();
+}
+// Empty the R = C(D+as, as) entries.
+AB_HDN void dacc_open(Ctx& c, DAcc& A, int as, int D) {
+    const int W = AB_W, lane = c.lane;
+    A.key = sm_addr(c.sm); A.val = sm_addr(c.sm + AB_KW * AB_SM_DENSE); A.btab = sm_addr(c.sm + AB_SM_OFF_BTAB);
+    A.as = as; A.R = (int)monomial_count(c.binom, D, as);
+    wsync();
+    #pragma unroll 1
+    for (int r = lane; r < A.R; r += W) sm_st64(A.val + 8u * (uint32_t)r, AB_ABSENT);
+    wsync();
+}
+AB_HD int dacc_rank(const DAcc& A, const Key& k) {
+    const uint64_t S = (k.w[0] >> (8 * (7 - A.as))) * 0x0101010101010101ull;      // byte j-1 = sum of the last j exponents
+    int r = 0;
+    #pragma unroll 1
+    for (int j = 0; j < A.as; ++j) r += (int)sm_ld32(A.btab + 4u * (uint32_t)(j * AB_BTAB_STRIDE + (int)((S >> (8 * j)) & 0xFF)));
+    return r;
+}
+// one step of _add2 on entry r (src/taylor_model.cpp:505-512): see acc_fold
+AB_HD double dacc_fold(const DAcc& A, int r, const Key& k, double tv) {
+    const smaddr_t va = A.val + 8u * (uint32_t)r;
+    const uint64_t cb = sm_ld64(va);
+    if (cb == AB_ABSENT) {
+        sm_st64(va, d2u(tv));
+        for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + r), k.w[w]);
+        return 0.0;
+    }
+    const double cur = u2d(cb);
+    const double u = add_ru(cur, tv), ml = sub_ru(-cur, tv);
+    const double nv = add_rn(cur, tv);
+    sm_st64(va, (nv == 0) ? AB_ABSENT : d2u(nv));
+    return add_ru(u, ml);
+}
+// Add the terms of model t as one stream; returns te, the upward sum of the rounding gaps in key order.
+AB_HDN double dacc_add_model(Ctx& c, const DAcc& A, const TM& t, bool gaps) {
+    const int W = AB_W, lane = c.lane, n = t.n;
+    const uint64_t* const base = c.A.base;
+    double te = 0.0;
+    #pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += W) {
+        const int j = j0 + lane;
+        double g = 0.0;
+        if (j < n) { const Key k = bkey(base, t.off + j * AB_TW); g = dacc_fold(A, dacc_rank(A, k), k, bval(base, t.off + j * AB_TW)); }
+        if (gaps) { const unsigned gm = wballot(g != 0.0); if (gm) te = chain_ru_masked(te, g, gm); }
+    }
+    wsync();
+    return te;
+}
+// Write the entries in use to the arena at word `dst`, in rank (= key) order; returns the number of terms.
+AB_HDN int dacc_emit(Ctx& c, const DAcc& A, int dst) {
+    const int W = AB_W, lane = c.lane, R = A.R;
+    uint64_t* const base = c.A.base;
+    if (!arena_room(c, dst, R)) return 0;
+    wsync();
+    int total = 0;
+    #pragma unroll 1
+    for (int r0 = 0; r0 < R; r0 += W) {
+        const int r = r0 + lane;
+        const uint64_t cb = (r < R) ? sm_ld64(A.val + 8u * (uint32_t)r) : AB_ABSENT;
+        const unsigned m = wballot(cb != AB_ABSENT);
+        if (cb != AB_ABSENT) {
+            const int o = dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW;
+            for (int w = 0; w < AB_KW; ++w) base[o + w] = sm_ld64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + r));
+            base[o + AB_KW] = cb;
+        }
+        total += popc32(m);
+    }
+    wsync();
+    return total;
+}
+
 // ---- binary operations: results are begun at the arena top ------------------------------------------------------
 
 // r' = ((r + t[0]) + t[1]) + ... + t[B-1] with the exact semantics of B successive _add2 calls
@@ -607,12 +734,28 @@ AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
 #ifndef AB_MAXSTREAMS
 #define AB_MAXSTREAMS 32
 #endif
+AB_HDN TM tm_add_many_dense(Ctx& c, const TM& r, const TM* t, int B, Acc acc, int D) {
+    const int m = c.A.top;
+    TM out; out.off = m; out.n = 0; out.as = r.as; out.acc = acc; out.e = r.e;
+    DAcc A; dacc_open(c, A, r.as, D);
+    dacc_add_model(c, A, r, false);
+    double e = r.e;
+    #pragma unroll 1
+    for (int s = 0; s < B; ++s) { const double te = dacc_add_model(c, A, t[s], true); e = add_ru(add_ru(e, t[s].e), te / 2); }
+    out.n = dacc_emit(c, A, m);
+    out.e = e;
+    c.A.top = m + out.n * AB_TW;
+    arena_mark_peak(c);
+    c.rnd = RN;
+    return out;
+}
 AB_HDN TM tm_add_many(Ctx& c, const TM& r, const TM* t, int B, Acc acc) { AB_CALL(1, r.n); AB_CALL(9, B); AB_FLOPS(3 * B);
     const int m = c.A.top;
     TM out; out.off = m; out.n = 0; out.as = r.as; out.acc = acc; out.e = r.e;
     long long want = r.n; int maxdeg = tm_degree(c, r);
     #pragma unroll 1
     for (int s = 0; s < B; ++s) { want += t[s].n; const int d = tm_degree(c, t[s]); if (d > maxdeg) maxdeg = d; }
+    if (dacc_fits(c, r.as, maxdeg)) return tm_add_many_dense(c, r, t, B, acc, maxdeg);
     double te[AB_MAXSTREAMS];
     AccTab T;
     #pragma unroll 1
@@ -749,7 +892,86 @@ AB_HDN TM tm_mul_simple(Ctx& c, const TM& x, const TM& y, Acc acc) {
     #undef AB_DISCARD
     return r;
 }
+// The general product on the dense accumulator (monomial space of the result and factor y fit the shared area): stream i is
+// x[i]*y, folded by all lanes at once (the keys of one stream are distinct); gap codes per (x-term, y-term), summed afterwards
+// by one lane per x-term.
+AB_HDN TM tm_mul_general_dense(Ctx& c, const TM& x, const TM& y, Acc acc, int D) {
+    uint64_t* const base = c.A.base;
+    const int W = AB_W, lane = c.lane;
+    const int m = c.A.top;
+    const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
+    const double xe = x.e, ye = y.e;
+    const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
+    TM r; r.off = m; r.n = 0; r.as = as; r.e = 0.0; r.acc = acc;
+    DAcc A; dacc_open(c, A, as, D);
+    // factor y staged as structure-of-arrays (keys | coefficients)
+    const smaddr_t yk = sm_addr(c.sm + AB_SM_OFF_YK), yv = sm_addr(c.sm + AB_SM_OFF_YV), g16 = sm_addr(c.sm + AB_SM_OFF_G16);
+    #pragma unroll 1
+    for (int j = lane; j < yn; j += W) {
+        for (int w = 0; w < AB_KW; ++w) sm_st64(yk + 8u * (uint32_t)(w * AB_SM_YCAP + j), base[yoff + j * AB_TW + w]);
+        sm_st64(yv + 8u * (uint32_t)j, base[yoff + j * AB_TW + AB_KW]);
+    }
+    int gs = yn + ((2 - (yn & 3)) & 3); if (gs < 2) gs = 2;      // row stride = 2 mod 4: conflict-free column reads
+    int Bi = AB_SM_G16 / gs; if (Bi > W) Bi = W;
+    wsync();
+    double re = 0.0; bool badgap = false;
+    #pragma unroll 1
+    for (int i0 = 0; i0 < xn; i0 += Bi) {
+        const int nb = (xn - i0 < Bi) ? (xn - i0) : Bi;
+        Key mxa = key_zero(); double mxv = 0.0;          // lane b holds x-term i0+b
+        if (lane < nb) { mxa = bkey(base, xoff + (i0 + lane) * AB_TW); mxv = bval(base, xoff + (i0 + lane) * AB_TW); }
+        #pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            Key xa; for (int w = 0; w < AB_KW; ++w) xa.w[w] = wshfl(mxa.w[w], b);
+            const double xv = wshfl(mxv, b);
+            const smaddr_t row = g16 + 2u * (uint32_t)(b * gs);
+            #pragma unroll 1
+            for (int j = lane; j < yn; j += W) {
+                Key ta; for (int w = 0; w < AB_KW; ++w) ta.w[w] = xa.w[w] + sm_ld64(yk + 8u * (uint32_t)(w * AB_SM_YCAP + j));
+                const double tv = mul_rn(xv, u2d(sm_ld64(yv + 8u * (uint32_t)j)));
+                uint32_t code = AB_G16_DISCARD;
+                if (!(dabs(tv) < sweep || key_deg(ta) > maxdeg)) code = gap_code(dacc_fold(A, dacc_rank(A, ta), ta, tv), &badgap);
+                sm_st16(row + 2u * (uint32_t)j, code);
+            }
+            wsync();          // the next x-term may meet the entries this one wrote
+        }
+        // per x-term sums, upward and in y order: lane b sums the row of x-term i0+b
+        double tte = 0.0, te = 0.0;
+        if (lane < nb) {
+            const double axv = dabs(mxv);
+            const smaddr_t row = g16 + 2u * (uint32_t)(lane * gs);
+            #pragma unroll 1
+            for (int j = 0; j < yn; ++j) {
+                const uint32_t code = sm_ld16(row + 2u * (uint32_t)j);
+                if (code & AB_G16_DISCARD) tte = add_ru(tte, mul_ru(axv, dabs(u2d(sm_ld64(yv + 8u * (uint32_t)j)))));
+                else if (code) te = add_ru(te, gap_value(code));
+            }
+        }
+        wsync();
+        // t.error()=tte+(tte/2) (upward), then the _add2 error chain in x-term order
+        #pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            const double tt = wshfl(tte, b), ee = wshfl(te, b);
+            re = add_ru(add_ru(re, add_ru(tt, tt / 2)), ee / 2);
+        }
+    }
+    if (wany(badgap)) fail(c, ST_UNSUPPORTED);
+    r.n = dacc_emit(c, A, m);
+    double xs = 0, ys = 0;
+    #pragma unroll 1
+    for (int i0 = 0; i0 < xn; i0 += W) { const int i = i0 + lane; xs = chain_ru(xs, i < xn ? dabs(bval(base, xoff + i * AB_TW)) : 0.0, (xn - i0 < W) ? xn - i0 : W); }
+    #pragma unroll 1
+    for (int j0 = 0; j0 < yn; j0 += W) { const int j = j0 + lane; ys = chain_ru(ys, j < yn ? dabs(bval(base, yoff + j * AB_TW)) : 0.0, (yn - j0 < W) ? yn - j0 : W); }
+    r.e = add_ru(re, add_ru(add_ru(mul_ru(xs, ye), mul_ru(ys, xe)), mul_ru(xe, ye)));
+    c.rnd = RN;
+    c.A.top = m + r.n * AB_TW;
+    arena_mark_peak(c);
+    return r;
+}
 AB_HDN TM tm_mul_general(Ctx& c, const TM& x, const TM& y, Acc acc) {
+    { int Dd = tm_degree(c, x) + tm_degree(c, y); if (Dd > acc.maxdeg) Dd = acc.maxdeg;
+      if (y.n <= AB_SM_YCAP && dacc_fits(c, x.as, Dd)) return tm_mul_general_dense(c, x, y, acc, Dd); }
+
     uint64_t* const base = c.A.base;
     const int W = AB_W, lane = c.lane;
     const int m = c.A.top;
@@ -762,6 +984,9 @@ AB_HDN TM tm_mul_general(Ctx& c, const TM& x, const TM& y, Acc acc) {
     // An upper bound of the number of result terms: distinct monomials of degree <= min(maxdeg, deg x + deg y).
     int D = tm_degree(c, x) + tm_degree(c, y); if (D > maxdeg) D = maxdeg;
     long long bound = monomial_count(c.binom, D, as);
+#ifdef AB_MULG_STATS
+    if (c.lane == 0) { extern long long g_mg[64][4]; int b = 0; while ((1LL << b) < bound && b < 20) ++b; g_mg[b][0]++; g_mg[b][1] += (long long)xn * yn; g_mg[40 + (as < 20 ? as : 19)][0]++; g_mg[40 + (as < 20 ? as : 19)][1] += (long long)xn * yn; if (D > g_mg[63][0]) g_mg[63][0] = D; }
+#endif
     { const long long prod = (long long)xn * (long long)yn; if (prod < bound) bound = prod; }
     double re = 0.0;
     AccTab T;
@@ -1039,7 +1264,69 @@ AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) { AB_FLOPS(4 * x.n + 2);
 // reference's throw does) when the models are disjoint; the caller then keeps y, as unchecked_flow does.
 // The union of the two key sets is built in the accumulator (x's coefficient in the entry, y's beside it); every key is
 // then treated independently, and the result error is a maximum, which does not depend on the order.
+// intersection on the dense accumulator: x's coefficient in the entry, y's beside it (gap-code area)
+AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int D) {
+    const int W = AB_W, lane = c.lane;
+    const uint64_t* const base = c.A.base;
+    const int m = c.A.top;
+    TM r = tm_begin(c, x.as, x.acc);
+    const double xe = x.e, ye = y.e;
+    DAcc A; dacc_open(c, A, x.as, D);
+    const smaddr_t yval = sm_addr(c.sm + AB_SM_OFF_G16);
+    #pragma unroll 1
+    for (int rr = lane; rr < A.R; rr += W) sm_st64(yval + 8u * (uint32_t)rr, d2u(0.0));
+    wsync();
+    #pragma unroll 1
+    for (int j = lane; j < x.n; j += W) {
+        const Key k = bkey(base, x.off + j * AB_TW); const int rr = dacc_rank(A, k);
+        sm_st64(A.val + 8u * (uint32_t)rr, base[x.off + j * AB_TW + AB_KW]);
+        for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + rr), k.w[w]);
+    }
+    wsync();
+    #pragma unroll 1
+    for (int j = lane; j < y.n; j += W) {
+        const Key k = bkey(base, y.off + j * AB_TW); const int rr = dacc_rank(A, k);
+        if (sm_ld64(A.val + 8u * (uint32_t)rr) == AB_ABSENT) {
+            sm_st64(A.val + 8u * (uint32_t)rr, d2u(0.0));
+            for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + rr), k.w[w]);
+        }
+        sm_st64(yval + 8u * (uint32_t)rr, base[y.off + j * AB_TW + AB_KW]);
+    }
+    wsync();
+    // per key: src/taylor_model.cpp:2905-2945
+    double lmax = 0.0; bool bad = false;
+    #pragma unroll 1
+    for (int rr = lane; rr < A.R; rr += W) {
+        const uint64_t xb = sm_ld64(A.val + 8u * (uint32_t)rr);
+        if (xb == AB_ABSENT) continue;
+        const double xv = u2d(xb), yv = u2d(sm_ld64(yval + 8u * (uint32_t)rr));
+        double xu = add_ru(xv, xe), yu = add_ru(yv, ye), mxl = sub_ru(xe, xv), myl = sub_ru(ye, yv);
+        double u = dmin(xu, yu), ml = dmin(mxl, myl);
+        const double sg = add_ru(u, ml);
+        if (sg < 0) bad = true;
+        lmax = dmax(lmax, sg);
+        xu = add_rn(xv, xe); yu = add_rn(yv, ye); mxl = sub_rn(xe, xv); myl = sub_rn(ye, yv);
+        u = dmin(xu, yu); ml = dmin(mxl, myl);
+        const double rv = sub_rn(u, ml) / 2;
+        sm_st64(A.val + 8u * (uint32_t)rr, (rv != 0.0) ? d2u(rv) : AB_ABSENT);
+    }
+    wsync();
+    if (wany(bad)) { c.rnd = RU; c.A.top = r.off; return false; }
+    double tme = 0.0;
+    #pragma unroll 1
+    for (int l = 0; l < W; ++l) tme = dmax(tme, wshfl(lmax, l));
+    r.n = dacc_emit(c, A, m);
+    c.A.top = m + r.n * AB_TW;
+    arena_mark_peak(c);
+    r.e = tme / 2;
+    c.rnd = RN;
+    out = r;
+    return true;
+}
 AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
+    { int Dd = tm_degree(c, x); const int d2 = tm_degree(c, y); if (d2 > Dd) Dd = d2;
+      if (AB_SM_DENSE <= AB_SM_G16 / 4 && dacc_fits(c, x.as, Dd)) { AB_FLOPS(1 + 12 * (x.n + y.n)); return tm_intersection_dense(c, x, y, out, Dd); } }
+
     const int W = AB_W, lane = c.lane;
     uint64_t* const base = c.A.base;
     const int m = c.A.top;

@@ -22,6 +22,9 @@
 #include <algorithm>
 
 using namespace ab200;
+#ifdef AB_MULG_STATS
+namespace ab200 { inline namespace AB_VARIANT { long long g_mg[64][4] = {{0}}; } }
+#endif
 #ifdef AB_COMPOSE_STATS
 namespace ab200 { inline namespace AB_VARIANT { long long g_cs[8] = {0}; } }
 #endif
@@ -189,6 +192,11 @@ int main(int argc, char** argv) {
     printf("arena word accesses: %lld (%.0f per step)\n", g_aw_count, (double)g_aw_count / total_steps);
     const char* names[] = {"tm_mul(incl)", "tm_compose(incl)", "tm_split", "flow_model(incl)", "flow_apply(incl)", "integration_step", "reachability_step"};
     for (int i = 0; i < 7; ++i) printf("  %-22s %.0f per step\n", names[i], (double)g_sec[i] / total_steps);
+#endif
+#ifdef AB_MULG_STATS
+    for (int b = 0; b < 21; ++b) if (g_mg[b][0]) printf("general muls with monomial bound <= 2^%d: %.1f per step, %.0f products per step\n", b, (double)g_mg[b][0] / total_steps, (double)g_mg[b][1] / total_steps);
+    for (int a = 0; a < 20; ++a) if (g_mg[40 + a][0]) printf("general muls with %d variables: %.1f per step, %.0f products per step\n", a, (double)g_mg[40 + a][0] / total_steps, (double)g_mg[40 + a][1] / total_steps);
+    printf("largest degree bound %lld\n", g_mg[63][0]);
 #endif
     return bad ? 1 : 0;
 }

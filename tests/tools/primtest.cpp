@@ -52,7 +52,7 @@ static Result run_with(int W, bool use_sm, const Body& body) {
     Result out;
     std::fill(g_arena.begin(), g_arena.begin() + 200000, 0xDEADBEEFDEADBEEFull);
     wemu::run(W, [&](int lane) {
-        Ctx c; ctx_init(c, g_arena.data(), g_arena_limit, use_sm ? g_sm.data() : 0, binom_host());
+        Ctx c; ctx_init(c, g_arena.data(), g_arena_limit, use_sm ? g_sm.data() : 0, binom_host()); ctx_stage_tables(c);
         Result r; body(c, r);
         if (lane == 0) out = r;
     });
