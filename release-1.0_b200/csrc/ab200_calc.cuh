@@ -333,6 +333,140 @@ AB_HDN void term_times_monomial(Ctx& c, TM& t, const TM& q, Acc acc) {
     c.A.top = off + rn * AB_TW;
 }
 
+// ---- composition on the dense accumulator -------------------------------------------------------------------------------
+// State of one product chain t = c * prod_j powers[j][e_j]. While the running product has at most one term it lives in
+// registers (the coefficient of a high-order term times a power usually falls below the sweep threshold entirely, or leaves
+// one term); it becomes a model in the arena only when two or more terms survive.
+struct ChainState {
+    int kind;          // 0 = empty (every product discarded), 1 = one term in registers, 2 = model `tt` in the arena
+    Key ka; double va; // the one term
+    double e;          // error of the running product (kinds 0 and 1)
+    TM tt;
+};
+// {ka: va, error xe} * p with accuracy acc (_mul4 with a one-term left factor, src/taylor_model.cpp:763-824): the products are
+// folded straight into the accumulator as one stream when `fold` is set (last factor of the chain), else the survivors become
+// the new state. Returns te, the gap sum of the stream (fold only); *te_out error of the product.
+AB_HDN double chain_times_power(Ctx& c, DAcc& DA, ChainState& st, const TM& p, int pslot, Acc acc, bool fold, double* e_out) {
+    const int W = AB_W, lane = c.lane, n = p.n, soff = p.off;
+    uint64_t* const base = c.A.base;
+    const Key fa = st.ka; const double fv = st.va, afv = dabs(fv), xe = st.e;
+    const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
+    const int m = c.A.top;
+    double tte = 0.0, te = 0.0; int rn = 0;
+    Key k1 = key_zero(); double v1 = 0.0;      // a lone survivor
+    const bool to_arena = !fold && n > W;      // survivors of a long power go to the arena as they come
+    if (to_arena && !arena_room(c, m, n)) { *e_out = 0.0; return 0.0; }
+    if (to_arena) wsync();
+    #pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += W) {
+        const int j = j0 + lane; const bool act = j < n;
+        Key ta = key_zero(); double sv = 0.0, tv = 0.0; bool disc = false;
+        if (act) { const int w = soff + j * AB_TW; sv = bval(base, w); ta = key_add(fa, bkey(base, w)); tv = mul_rn(fv, sv); disc = dabs(tv) < sweep || key_deg(ta) > maxdeg; }
+        const unsigned dm = wballot(disc);
+        if (fold) {
+            double g = 0.0;
+            if (act && !disc) g = dacc_fold(DA, dacc_rank(DA, ta), ta, tv);
+            const unsigned gm = wballot(g != 0.0);
+            if (gm) te = chain_ru_masked(te, g, gm);
+        } else {
+            const unsigned km = wballot(act && !disc);
+            if (to_arena) { if (act && !disc) bput(base, m + (rn + popc32(km & lanemask_lt(lane))) * AB_TW, ta, tv); }
+            else if (km) {
+                const int cnt = popc32(km);
+                if (cnt == 1) { const int src = ffs32(km) - 1; for (int w = 0; w < AB_KW; ++w) k1.w[w] = wshfl(ta.w[w], src); v1 = wshfl(tv, src); }
+                else {      // two or more survivors of a short power: they become a model
+                    if (!arena_room(c, m, cnt)) { *e_out = 0.0; return 0.0; }
+                    wsync();
+                    if (act && !disc) bput(base, m + popc32(km & lanemask_lt(lane)) * AB_TW, ta, tv);
+                }
+            }
+            rn += popc32(km);
+        }
+        if (dm) tte = chain_ru_masked(tte, mul_ru(afv, dabs(sv)), dm);
+    }
+    const double nm = (xe != 0.0) ? ph_norm(c, pslot, p) : 0.0;
+    const double e = add_ru(add_ru(tte, tte / 2), add_ru(add_ru(mul_ru(afv, p.e), mul_ru(nm, xe)), mul_ru(xe, p.e)));
+    c.rnd = RN;
+    *e_out = e;
+    AB_FLOPS(5.0 * n + 3.0 + 2.0 * (1 + n) + 6.0);
+    if (fold) { wsync(); return te; }
+    if (to_arena || rn >= 2) {
+        wsync();
+        st.kind = 2; st.tt.off = m; st.tt.n = rn; st.tt.as = p.as; st.tt.e = e; st.tt.acc = acc;
+        c.A.top = m + rn * AB_TW; arena_mark_peak(c);
+    } else if (rn == 1) { st.kind = 1; st.ka = k1; st.va = v1; st.e = e; }
+    else { st.kind = 0; st.e = e; }
+    return 0.0;
+}
+// r = x o ys for one model x on the dense accumulator; the sum stays in shared memory while the terms stream through it.
+// A chain that needs a general product (both factors with two or more terms) parks the sum in the arena at ri first, since
+// the product uses the accumulator itself. Result written at ri.
+AB_HDN TM compose_stream_dense(Ctx& c, const TM& xi, const TM* ys, int nys, const int* tab, int as, Acc acc0, int Dc, int ri) {
+    const int W = AB_W, lane = c.lane;
+    TM ra; ra.off = ri; ra.n = 0; ra.as = as; ra.e = xi.e; ra.acc = acc0;
+    const int sbase = ri + AB_SM_DENSE * AB_TW;            // product chains are built above the room kept for the parked sum
+    if (!arena_room(c, sbase, 8)) return ra;
+    DAcc DA; dacc_open(c, DA, as, Dc);
+    bool open = true; double e_run = xi.e;
+    Key pk = key_zero(); double pv = 0.0;                  // this lane's term of the current chunk of x
+    #pragma unroll 1
+    for (int t = 0; t < xi.n; ++t) {
+        if (t % W == 0) { const int q = t + lane; if (q < xi.n) { pk = tm_key(c, xi, q); pv = tm_val(c, xi, q); } }
+        Key a; for (int w = 0; w < AB_KW; ++w) a.w[w] = wshfl(pk.w[w], t % W);
+        const double cv = wshfl(pv, t % W);
+        c.A.top = sbase;
+        int lastj = -1;
+        #pragma unroll 1
+        for (int j = 0; j < nys; ++j) if (key_get(a, j) != 0) lastj = j;
+        ChainState st; st.kind = (cv == 0.0) ? 0 : 1; st.ka = key_zero(); st.va = cv; st.e = 0.0;
+        double te = 0.0, t_e = 0.0; bool folded = false;
+        #pragma unroll 1
+        for (int j = 0; j <= lastj; ++j) {
+            const int e = key_get(a, j);
+            if (e == 0) continue;
+            const int pslot = tab[j] + AB_PHW * e;
+            const TM pw = ph_load(c, pslot, as, ys[j].acc);
+            const Acc accj = ys[j].acc;
+            if (st.kind == 0) {
+                // every product so far was discarded: _mul4 with an empty left factor leaves only the error cross terms
+                const double nm = (st.e != 0.0) ? ph_norm(c, pslot, pw) : 0.0;
+                st.e = add_ru(0.0, add_ru(add_ru(mul_ru(0.0, pw.e), mul_ru(nm, st.e)), mul_ru(st.e, pw.e)));
+                c.rnd = RN;
+            } else if (st.kind == 1) {
+                if (pw.n == 0) {      // one term times an empty power: only the cross term |x| * error(power) remains
+                    st.e = add_ru(0.0, add_ru(add_ru(mul_ru(dabs(st.va), pw.e), mul_ru(0.0, st.e)), mul_ru(st.e, pw.e)));
+                    st.kind = 0; c.rnd = RN;
+                } else if (j == lastj && open) { te = chain_times_power(c, DA, st, pw, pslot, accj, true, &t_e); folded = true; }
+                else { double eo; chain_times_power(c, DA, st, pw, pslot, accj, false, &eo); }
+            } else {
+                if (pw.n == 1 && st.tt.n >= 1 && tm_end(st.tt) == c.A.top) term_times_monomial(c, st.tt, pw, accj);
+                else {
+                    if (st.tt.n > 1 && pw.n > 1 && open) { ra.n = dacc_emit(c, DA, ri); ra.e = e_run; open = false; }
+                    st.tt = tm_mul(c, st.tt, pw, accj);
+                }
+            }
+            if (c.status != ST_OK) { if (open) dacc_emit(c, DA, -1); return ra; }
+        }
+        if (!open) { dacc_open(c, DA, as, Dc); dacc_add_model(c, DA, ra, false); open = true; }
+        if (!folded) {
+            if (st.kind == 1) {
+                double g = 0.0;
+                if (lane == 0) g = dacc_fold(DA, dacc_rank(DA, st.ka), st.ka, st.va);
+                te = add_ru(0.0, wshfl(g, 0)); t_e = st.e;
+                wsync();
+            } else if (st.kind == 0) { te = 0.0; t_e = st.e; }
+            else { te = dacc_add_model(c, DA, st.tt, true); t_e = st.tt.e; }
+        }
+        e_run = add_ru(add_ru(e_run, t_e), te / 2);
+    }
+    ra.n = dacc_emit(c, DA, ri);
+    ra.e = e_run;
+    c.rnd = RN;
+    c.A.top = ri + ra.n * AB_TW;
+    arena_mark_peak(c);
+    return ra;
+}
+
 // _compose2 (src/taylor_model.cpp:3187-3240): r[i] = x[i] o ys, nx models in xas=nys variables.
 // Results are written to r[0..nx) packed from the arena top recorded on entry.
 AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r) {
@@ -388,11 +522,15 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
         // shared-memory accumulator while the terms stream through it (no intermediate merges); a term whose product chain
         // needs a general product -- which uses the accumulator itself -- first parks the sum in the arena at ri.
         bool streamed = false;
+        int Dc0 = 0; for (int j = 0; j < nys; ++j) if (ys[j].acc.maxdeg > Dc0) Dc0 = ys[j].acc.maxdeg;
+        if (dacc_fits(c, as, Dc0) && (long long)ri + (long long)(AB_SM_DENSE + 8) * AB_TW < (long long)c.A.limit) {
+            ra = compose_stream_dense(c, x[i], ys, nys, tab, as, acc0, Dc0, ri);
+            if (c.status != ST_OK) { for (int q = i; q < nx; ++q) r[q] = tm_begin(c, as, acc0); return; }
+            streamed = true;
+        } else
         if (c.sm && (long long)ri + (long long)(AB_SM_CAP + 8) * AB_TW < (long long)c.A.limit) {
             const int sbase = ri + AB_SM_CAP * AB_TW;           // product chains are built above the room kept for the parked sum
-            AccTab T; DAcc DA; bool open = false, failed = false; int dmax = 0; double e_run = x[i].e;
-            int Dc = 0; for (int j = 0; j < nys; ++j) if (ys[j].acc.maxdeg > Dc) Dc = ys[j].acc.maxdeg;
-            const bool dense = dacc_fits(c, as, Dc);             // every product is cut at its factor's degree limit
+            AccTab T; bool open = false, failed = false; int dmax = 0; double e_run = x[i].e;
             T.overflow = false;
             Key pk = key_zero(); double pv = 0.0;               // this lane's term of the current chunk of x[i]
             const int W = AB_W, lane = c.lane;
@@ -421,7 +559,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                         tt.acc = ys[j].acc; c.rnd = RN;
                     } else {
                         if (tt.n > 1 && pw.n > 1 && open) {      // general product ahead: it needs the accumulator
-                            ra.n = dense ? dacc_emit(c, DA, ri) : acc_emit(c, T, as, dmax, ri); ra.e = e_run; open = false;
+                            ra.n = acc_emit(c, T, as, dmax, ri); ra.e = e_run; open = false;
                         }
                         tt = tm_mul(c, tt, pw, ys[j].acc);
                     }
@@ -430,17 +568,17 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                 if (c.status != ST_OK) { failed = true; break; }
                 if (!open) {
                     const int keep = c.A.top;
-                    if (dense) { dacc_open(c, DA, as, Dc); dacc_add_model(c, DA, ra, false); }
-                    else { if (!acc_open(c, T, 0, keep, AB_SM_CAP)) { failed = true; break; } acc_add_model(c, T, ra); }
+                    if (!acc_open(c, T, 0, keep, AB_SM_CAP)) { failed = true; break; }
+                    acc_add_model(c, T, ra);
                     open = true;
                 }
-                const double te = dense ? dacc_add_model(c, DA, tt, true) : (T.overflow ? 0.0 : acc_add_model(c, T, tt));
+                const double te = T.overflow ? 0.0 : acc_add_model(c, T, tt);
                 if (T.overflow) { failed = true; break; }
                 { const int d = tm_degree(c, tt); if (d > dmax) dmax = d; }
                 e_run = add_ru(add_ru(e_run, tt.e), te / 2);
             }
             if (!failed) {
-                if (open) { ra.n = dense ? dacc_emit(c, DA, ri) : acc_emit(c, T, as, dmax, ri); }
+                if (open) { ra.n = acc_emit(c, T, as, dmax, ri); }
                 ra.e = e_run; ra.off = ri;
                 c.rnd = RN;
                 streamed = true;

@@ -116,6 +116,7 @@ struct Ctx {
     int lane;      // this thread's lane in the warp
     uint64_t* sm;  // the warp's shared-memory staging area (AB_SM_WORDS words); null in host-side callers
     const uint32_t* binom;   // binomial table for monomial ranks (binom_fill)
+    int sm_dirty;            // the hash accumulator has written over the dense accumulator's area since it was last emptied
 };
 #define AB_BINOM_N 64
 #define AB_BINOM_K 24
@@ -129,11 +130,11 @@ inline void binom_fill(uint32_t* t) {
 struct BinomTab { uint32_t t[AB_BINOM_N * AB_BINOM_K]; BinomTab() { binom_fill(t); } };
 inline const uint32_t* binom_host() { static BinomTab b; return b.t; }
 AB_HD void ctx_init(Ctx& c, uint64_t* arena, int limit, uint64_t* sm, const uint32_t* binom) {
-    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom;
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom; c.sm_dirty = 1;
 }
 // host-side callers (no warp, no shared area)
 inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
-    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host();
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1;
 }
 
 AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[i]; }
@@ -401,6 +402,7 @@ AB_HD bool acc_open(Ctx& c, AccTab& T, int attempt, int above, long long want) {
     const int W = AB_W, lane = c.lane;
     wsync();
     if (attempt == 0 && c.sm) {
+        c.sm_dirty = 1;
         uint32_t nidx = 64; while (nidx < AB_SM_NIDX && (long long)nidx < 2 * want) nidx <<= 1;      // small sums clear a small index
         T.idx = (uint32_t*)(c.sm + AB_SM_OFF_IDX); T.mask = nidx - 1; T.key = c.sm + AB_SM_OFF_KEY; T.val = c.sm + AB_SM_OFF_VAL;
         T.cap = (int)(nidx / 2) < AB_SM_CAP ? (int)(nidx / 2) : AB_SM_CAP;
@@ -636,6 +638,7 @@ struct DAcc {
     smaddr_t key, val, btab;    // shared addresses: key word w of rank r at key + 8*(w*AB_SM_DENSE + r), coefficient at val + 8*r
     int R;                      // ranks in use
     int as;
+    uint32_t touched;           // per lane: blocks of 32 ranks this lane has written to (emission visits only those)
 };
 AB_HD bool dacc_fits(const Ctx& c, int as, int D) {
     if (!c.sm || !c.binom || as < 1 || as > 7 || D < 0 || D >= AB_BTAB_STRIDE) return false;
@@ -654,26 +657,35 @@ AB_HDN void ctx_stage_tables(Ctx& c) {
     }
     wsync();
 }
-// Empty the R = C(D+as, as) entries.
-AB_HDN void dacc_open(Ctx& c, DAcc& A, int as, int D) {
+// Empty every entry of the dense accumulator (at the start of a cell and after the hash accumulator has used the area).
+AB_HDN void dacc_clear_all(Ctx& c) {
     const int W = AB_W, lane = c.lane;
-    A.key = sm_addr(c.sm); A.val = sm_addr(c.sm + AB_KW * AB_SM_DENSE); A.btab = sm_addr(c.sm + AB_SM_OFF_BTAB);
-    A.as = as; A.R = (int)monomial_count(c.binom, D, as);
+    const smaddr_t val = sm_addr(c.sm + AB_KW * AB_SM_DENSE);
     wsync();
     #pragma unroll 1
-    for (int r = lane; r < A.R; r += W) sm_st64(A.val + 8u * (uint32_t)r, AB_ABSENT);
+    for (int r = lane; r < AB_SM_DENSE; r += W) sm_st64(val + 8u * (uint32_t)r, AB_ABSENT);
     wsync();
+    c.sm_dirty = 0;
+}
+// All entries are empty between two uses (emission puts back what it takes), so opening costs nothing.
+AB_HD void dacc_open(Ctx& c, DAcc& A, int as, int D) {
+    if (c.sm_dirty) dacc_clear_all(c);
+    A.key = sm_addr(c.sm); A.val = sm_addr(c.sm + AB_KW * AB_SM_DENSE); A.btab = sm_addr(c.sm + AB_SM_OFF_BTAB);
+    A.as = as; A.R = (int)monomial_count(c.binom, D, as); A.touched = 0u;
 }
 AB_HD int dacc_rank(const DAcc& A, const Key& k) {
     const uint64_t S = (k.w[0] >> (8 * (7 - A.as))) * 0x0101010101010101ull;      // byte j-1 = sum of the last j exponents
-    int r = 0;
+    const int s1 = (int)(S & 0xFF), s2 = (int)((S >> 8) & 0xFF);
+    int r = s1;                                               // C(s1, 1)
+    if (A.as >= 2) r += (s2 * (s2 + 1)) >> 1;                 // C(s2 + 1, 2)
     #pragma unroll 1
-    for (int j = 0; j < A.as; ++j) r += (int)sm_ld32(A.btab + 4u * (uint32_t)(j * AB_BTAB_STRIDE + (int)((S >> (8 * j)) & 0xFF)));
+    for (int j = 2; j < A.as; ++j) r += (int)sm_ld32(A.btab + 4u * (uint32_t)(j * AB_BTAB_STRIDE + (int)((S >> (8 * j)) & 0xFF)));
     return r;
 }
 // one step of _add2 on entry r (src/taylor_model.cpp:505-512): see acc_fold
-AB_HD double dacc_fold(const DAcc& A, int r, const Key& k, double tv) {
+AB_HD double dacc_fold(DAcc& A, int r, const Key& k, double tv) {
     const smaddr_t va = A.val + 8u * (uint32_t)r;
+    A.touched |= 1u << (r >> 5);
     const uint64_t cb = sm_ld64(va);
     if (cb == AB_ABSENT) {
         sm_st64(va, d2u(tv));
@@ -687,7 +699,7 @@ AB_HD double dacc_fold(const DAcc& A, int r, const Key& k, double tv) {
     return add_ru(u, ml);
 }
 // Add the terms of model t as one stream; returns te, the upward sum of the rounding gaps in key order.
-AB_HDN double dacc_add_model(Ctx& c, const DAcc& A, const TM& t, bool gaps) {
+AB_HDN double dacc_add_model(Ctx& c, DAcc& A, const TM& t, bool gaps) {
     const int W = AB_W, lane = c.lane, n = t.n;
     const uint64_t* const base = c.A.base;
     double te = 0.0;
@@ -701,24 +713,43 @@ AB_HDN double dacc_add_model(Ctx& c, const DAcc& A, const TM& t, bool gaps) {
     wsync();
     return te;
 }
-// Write the entries in use to the arena at word `dst`, in rank (= key) order; returns the number of terms.
-AB_HDN int dacc_emit(Ctx& c, const DAcc& A, int dst) {
-    const int W = AB_W, lane = c.lane, R = A.R;
+// blocks touched by any lane
+AB_HD uint32_t dacc_touched(const DAcc& A, int lane) {
+    uint32_t m = A.touched;
+    const int W = AB_W;
+    #pragma unroll 1
+    for (int d = 1; d < W; d <<= 1) m |= (uint32_t)wshfl((int)m, lane ^ d);
+    return m;
+}
+// Write the entries in use to the arena at word `dst`, in rank (= key) order, and leave the accumulator empty; returns the
+// number of terms. (dst < 0: only empty it.)
+AB_HDN int dacc_emit(Ctx& c, DAcc& A, int dst) {
+    const int lane = c.lane, R = A.R;
     uint64_t* const base = c.A.base;
-    if (!arena_room(c, dst, R)) return 0;
     wsync();
+    uint32_t blocks = dacc_touched(A, lane);
+    A.touched = 0u;
+    if (dst >= 0 && !arena_room(c, dst, popc32(blocks) * 32)) dst = -1;
     int total = 0;
     #pragma unroll 1
-    for (int r0 = 0; r0 < R; r0 += W) {
-        const int r = r0 + lane;
-        const uint64_t cb = (r < R) ? sm_ld64(A.val + 8u * (uint32_t)r) : AB_ABSENT;
-        const unsigned m = wballot(cb != AB_ABSENT);
-        if (cb != AB_ABSENT) {
-            const int o = dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW;
-            for (int w = 0; w < AB_KW; ++w) base[o + w] = sm_ld64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + r));
-            base[o + AB_KW] = cb;
+    while (blocks) {
+        const int blk = ffs32(blocks) - 1; blocks &= blocks - 1;
+        #pragma unroll 1
+        for (int sub = 0; sub < 32; sub += AB_W) {              // one pass on the device (32 lanes)
+            const int r = blk * 32 + sub + lane;
+            const smaddr_t va = A.val + 8u * (uint32_t)r;
+            const uint64_t cb = (r < R) ? sm_ld64(va) : AB_ABSENT;
+            const unsigned m = wballot(cb != AB_ABSENT);
+            if (cb != AB_ABSENT) {
+                if (dst >= 0) {
+                    const int o = dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW;
+                    for (int w = 0; w < AB_KW; ++w) base[o + w] = sm_ld64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + r));
+                    base[o + AB_KW] = cb;
+                }
+                sm_st64(va, AB_ABSENT);
+            }
+            total += popc32(m);
         }
-        total += popc32(m);
     }
     wsync();
     return total;
@@ -1273,12 +1304,12 @@ AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int
     const double xe = x.e, ye = y.e;
     DAcc A; dacc_open(c, A, x.as, D);
     const smaddr_t yval = sm_addr(c.sm + AB_SM_OFF_G16);
-    #pragma unroll 1
-    for (int rr = lane; rr < A.R; rr += W) sm_st64(yval + 8u * (uint32_t)rr, d2u(0.0));
     wsync();
     #pragma unroll 1
     for (int j = lane; j < x.n; j += W) {
         const Key k = bkey(base, x.off + j * AB_TW); const int rr = dacc_rank(A, k);
+        A.touched |= 1u << (rr >> 5);
+        sm_st64(yval + 8u * (uint32_t)rr, d2u(0.0));
         sm_st64(A.val + 8u * (uint32_t)rr, base[x.off + j * AB_TW + AB_KW]);
         for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + rr), k.w[w]);
     }
@@ -1286,6 +1317,7 @@ AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int
     #pragma unroll 1
     for (int j = lane; j < y.n; j += W) {
         const Key k = bkey(base, y.off + j * AB_TW); const int rr = dacc_rank(A, k);
+        A.touched |= 1u << (rr >> 5);
         if (sm_ld64(A.val + 8u * (uint32_t)rr) == AB_ABSENT) {
             sm_st64(A.val + 8u * (uint32_t)rr, d2u(0.0));
             for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + rr), k.w[w]);
@@ -1296,7 +1328,10 @@ AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int
     // per key: src/taylor_model.cpp:2905-2945
     double lmax = 0.0; bool bad = false;
     #pragma unroll 1
-    for (int rr = lane; rr < A.R; rr += W) {
+    for (uint32_t blocks = dacc_touched(A, lane); blocks; blocks &= blocks - 1)
+      for (int sub = 0; sub < 32; sub += W) {
+        const int rr = (ffs32(blocks) - 1) * 32 + sub + lane;
+        if (rr >= A.R) continue;
         const uint64_t xb = sm_ld64(A.val + 8u * (uint32_t)rr);
         if (xb == AB_ABSENT) continue;
         const double xv = u2d(xb), yv = u2d(sm_ld64(yval + 8u * (uint32_t)rr));
@@ -1311,7 +1346,7 @@ AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int
         sm_st64(A.val + 8u * (uint32_t)rr, (rv != 0.0) ? d2u(rv) : AB_ABSENT);
     }
     wsync();
-    if (wany(bad)) { c.rnd = RU; c.A.top = r.off; return false; }
+    if (wany(bad)) { dacc_emit(c, A, -1); c.rnd = RU; c.A.top = r.off; return false; }
     double tme = 0.0;
     #pragma unroll 1
     for (int l = 0; l < W; ++l) tme = dmax(tme, wshfl(lmax, l));
