@@ -72,6 +72,9 @@ typedef struct ab200_status {
     double  evolve_ms;        /* device time of the evolution kernel(s) */
     double  raster_ms;        /* device time of rasterise + compact + sort */
     int64_t launches;         /* kernels launched by this call */
+    int32_t build;            /* evolution build used by the last batch: 0 = one warp per cell (one-word MultiIndex keys),
+                                 1 = one warp per cell (two-word keys), 2 = one lane per cell (very large frontiers) */
+    int32_t reserved;
 } ab200_status;
 
 void ab200_default_settings(ab200_settings* s);

@@ -47,7 +47,8 @@ class Settings(C.Structure):
 
 class Status(C.Structure):
     _fields_ = [("code", C.c_int32), ("cell", C.c_int64), ("steps", C.c_int64), ("keys_emitted", C.c_int64),
-                ("arena_peak", C.c_int32), ("evolve_ms", C.c_double), ("raster_ms", C.c_double), ("launches", C.c_int64)]
+                ("arena_peak", C.c_int32), ("evolve_ms", C.c_double), ("raster_ms", C.c_double), ("launches", C.c_int64),
+                ("build", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Ab200Error(RuntimeError):

@@ -26,6 +26,21 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* 
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
+// The one-cell-per-lane build (ab200_kernels_lane.cu): its own launcher signature (no work counter: one lane per cell,
+// arenas interleaved per warp of 32 cells).
+namespace ab200 { namespace lane {
+int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen);
+int dev_evolve_capacity_v(char* errbuf, int errlen);
+int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
+                        uint64_t* arena, int arena_words, double* reach, int32_t* reach_loc, int32_t* n_reach,
+                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
+                        char* errbuf, int errlen); } }
+// A batch this large goes to the lane build (one-word keys only). Below it the warp build is faster: a lap of the lane build
+// costs the latency of its slowest cell (seconds), whatever the frontier.
+#ifndef AB_LANE_THRESHOLD
+#define AB_LANE_THRESHOLD 24576
+#endif
+#define AB_LANE_ARENA_WORDS 12288
 struct EvolveBuild {
     const char* name;
     int (*upload)(const void*, char*, int);
@@ -137,6 +152,7 @@ static int upload_system(ab200_ctx* ctx, bool changed) {
     if (!changed && ctx->device < 64 && g_sys_owner[ctx->device] == ctx) return AB200_OK;
     CTX_CK(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < kNumBuilds; ++b) DEV_CK(kBuilds[b].upload(&ctx->sys.desc, eb_, sizeof(eb_)));
+    DEV_CK(ab200::lane::dev_upload_system_v(&ctx->sys.desc, eb_, sizeof(eb_)));
     if (ctx->device < 64) g_sys_owner[ctx->device] = ctx;
     return AB200_OK;
 }
@@ -265,35 +281,63 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         // AB200_TUNE=kw2 forces the two-word build for a system that would fit one word (test hook).
         const bool wide = ctx->sys.desc.loc[0].n > 2;
         const EvolveBuild* build = find_build(wide ? "kw2" : "kw1");
+        // AB200_TUNE=lane / warp overrides the size rule for one-word systems (test hook).
+        bool use_lane = !wide && nb >= AB_LANE_THRESHOLD && P.max_events < 64;
         if (const char* tune = getenv("AB200_TUNE")) {
-            if (!find_build(tune) || (wide && strcmp(tune, "kw2"))) { ctx->err = std::string("AB200_TUNE: no such build for this system: ") + tune; return AB200_E_ARGUMENT; }
-            build = find_build(tune);
+            if (!strcmp(tune, "lane") && !wide) use_lane = true;
+            else if (!strcmp(tune, "warp")) use_lane = false;
+            else {
+                if (!find_build(tune) || (wide && strcmp(tune, "kw2"))) { ctx->err = std::string("AB200_TUNE: no such build for this system: ") + tune; return AB200_E_ARGUMENT; }
+                build = find_build(tune); use_lane = false;
+            }
         }
-        int slots; DEV_CK((slots = build->capacity(eb_, sizeof(eb_))) < 0);
-        if (const char* e = getenv("AB200_SLOTS_PER_SM")) {     // development hook: fewer resident cells per SM than the occupancy allows
-            int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-            if (atoi(e) > 0 && sms * atoi(e) < slots) slots = sms * atoi(e);
-        }
-        if (slots > nb) slots = nb;
-        CTX_CK(ctx->d_arena.ensure((size_t)slots * S.arena_words));
-        CTX_CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_loc.p, loc + b0, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_box.p, boxes + b0 * stride, (size_t)nb * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, ctx->d_binom.p, ctx->d_next.p,
-                             ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                             ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
-        stl.launches += 1;
-        CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         std::vector<int32_t> h_status(nb), h_steps(nb), h_peak(nb), h_nreach(nb), h_nfin(nb);
-        CTX_CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        float ms = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            if (use_lane) {
+                const int lane_words = S.arena_words < AB_LANE_ARENA_WORDS ? S.arena_words : AB_LANE_ARENA_WORDS;
+                const int nwarps = (nb + 31) / 32;
+                CTX_CK(ctx->d_arena.ensure((size_t)nwarps * 32 * lane_words));
+                EvolveParams PL = P; if (PL.max_working_sets > 12) PL.max_working_sets = 12;
+                DEV_CK(ab200::lane::dev_launch_evolve_v(ctx->stream, nb, ctx->d_loc.p, ctx->d_box.p, &PL, ctx->d_arena.p, lane_words,
+                                                       ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                                       ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+            } else {
+                int slots; DEV_CK((slots = build->capacity(eb_, sizeof(eb_))) < 0);
+                if (const char* e = getenv("AB200_SLOTS_PER_SM")) {     // development hook: fewer resident cells per SM than the occupancy allows
+                    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+                    if (atoi(e) > 0 && sms * atoi(e) < slots) slots = sms * atoi(e);
+                }
+                if (slots > nb + 3) slots = nb + 3;                     // (a CTA may hold up to four cell slots)
+                CTX_CK(ctx->d_arena.ensure((size_t)(slots + 4) * S.arena_words));
+                CTX_CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream));
+                DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, ctx->d_binom.p, ctx->d_next.p,
+                                     ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
+                                     ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+            }
+            stl.launches += 1;
+            CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CTX_CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CTX_CK(cudaStreamSynchronize(ctx->stream));
+            float ms1 = 0; cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1); ms += ms1;
+            // the lane build has fixed device limits (scratch words and pending working sets per cell): a batch that hits one
+            // is run again by the warp build, which has neither
+            bool retry = false;
+            if (use_lane) for (int i = 0; i < nb; ++i) if (h_status[i] == ST_ARENA || h_status[i] == ST_WORKING_SETS) { retry = true; break; }
+            stl.build = use_lane ? 2 : (wide ? 1 : 0);
+            if (!retry) break;
+            use_lane = false;
+        }
         const char* dump_steps = getenv("AB200_DUMP_STEPS");      // profiling aid: per-cell _evolution_step counts of the last lap
         CTX_CK(cudaMemcpyAsync(h_steps.data(), ctx->d_steps.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_peak.data(), ctx->d_peak.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_nreach.data(), ctx->d_nreach.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_nfin.data(), ctx->d_nfin.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaStreamSynchronize(ctx->stream));
-        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); evolve_ms += ms;
+        evolve_ms += ms;
         if (dump_steps) { if (FILE* f = fopen(dump_steps, b0 == 0 ? "wb" : "ab")) { fwrite(h_steps.data(), sizeof(int32_t), (size_t)nb, f); fclose(f); } }
         for (int i = 0; i < nb; ++i) {
             stl.steps += h_steps[i];

@@ -331,10 +331,13 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
 // hash accumulator (index | keys | coefficients) otherwise. When even that is outgrown the hash accumulator is rebuilt in the
 // free part of the arena (same code, generic pointers).
 #ifndef AB_SM_ACCW
-#define AB_SM_ACCW 2048
+#define AB_SM_ACCW 1536
 #endif
 #define AB_SM_BTABW 128
-#define AB_SM_DENSE (AB_SM_ACCW / (AB_KW + 1))          // ranks the dense accumulator can hold
+// Dense accumulator: coefficients of AB_SM_DENSE ranks, then their keys. With at most 3 variables a key is the upper half
+// of the packed MultiIndex word (degree and three exponent bytes), so AB_SM_DENSE keys take half a word each; with 4..7
+// variables the full word is kept and only AB_SM_DENSE/2 ranks are available.
+#define AB_SM_DENSE (2 * AB_SM_ACCW / 3)
 #define AB_BTAB_STRIDE 36                               // rank-table row: sums of exponents 0..35
 #ifndef AB_SM_NIDX
 #define AB_SM_NIDX 1024
@@ -635,14 +638,14 @@ AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
 // the bytes of (packed exponents) x 0x0101..01, the binomials come from a small table staged in shared memory, so a product
 // finds its entry with one multiply and `as` table reads. An entry whose coefficient is AB_ABSENT is empty.
 struct DAcc {
-    smaddr_t key, val, btab;    // shared addresses: key word w of rank r at key + 8*(w*AB_SM_DENSE + r), coefficient at val + 8*r
+    smaddr_t key, val, btab;    // shared addresses: coefficient of rank r at val + 8*r, its key at key + 4*r (as <= 3) or key + 8*r
     int R;                      // ranks in use
     int as;
     uint32_t touched;           // per lane: blocks of 32 ranks this lane has written to (emission visits only those)
 };
 AB_HD bool dacc_fits(const Ctx& c, int as, int D) {
     if (!c.sm || !c.binom || as < 1 || as > 7 || D < 0 || D >= AB_BTAB_STRIDE) return false;
-    return monomial_count(c.binom, D, as) <= (long long)AB_SM_DENSE;
+    return monomial_count(c.binom, D, as) <= (long long)(as <= 3 ? AB_SM_DENSE : AB_SM_DENSE / 2);
 }
 // The rank table B[k][s] = C(s-1+k, k), k = 1..7, s = 0..35, staged once per cell (ctx_stage_tables).
 AB_HDN void ctx_stage_tables(Ctx& c) {
@@ -660,7 +663,7 @@ AB_HDN void ctx_stage_tables(Ctx& c) {
 // Empty every entry of the dense accumulator (at the start of a cell and after the hash accumulator has used the area).
 AB_HDN void dacc_clear_all(Ctx& c) {
     const int W = AB_W, lane = c.lane;
-    const smaddr_t val = sm_addr(c.sm + AB_KW * AB_SM_DENSE);
+    const smaddr_t val = sm_addr(c.sm);
     wsync();
     #pragma unroll 1
     for (int r = lane; r < AB_SM_DENSE; r += W) sm_st64(val + 8u * (uint32_t)r, AB_ABSENT);
@@ -670,8 +673,16 @@ AB_HDN void dacc_clear_all(Ctx& c) {
 // All entries are empty between two uses (emission puts back what it takes), so opening costs nothing.
 AB_HD void dacc_open(Ctx& c, DAcc& A, int as, int D) {
     if (c.sm_dirty) dacc_clear_all(c);
-    A.key = sm_addr(c.sm); A.val = sm_addr(c.sm + AB_KW * AB_SM_DENSE); A.btab = sm_addr(c.sm + AB_SM_OFF_BTAB);
+    A.val = sm_addr(c.sm); A.key = sm_addr(c.sm + AB_SM_DENSE); A.btab = sm_addr(c.sm + AB_SM_OFF_BTAB);
     A.as = as; A.R = (int)monomial_count(c.binom, D, as); A.touched = 0u;
+}
+AB_HD void dacc_put_key(const DAcc& A, int r, const Key& k) {
+    if (A.as <= 3) sm_st32(A.key + 4u * (uint32_t)r, (uint32_t)(k.w[0] >> 32)); else sm_st64(A.key + 8u * (uint32_t)r, k.w[0]);
+}
+AB_HD Key dacc_get_key(const DAcc& A, int r) {
+    Key k = key_zero();
+    k.w[0] = (A.as <= 3) ? ((uint64_t)sm_ld32(A.key + 4u * (uint32_t)r) << 32) : sm_ld64(A.key + 8u * (uint32_t)r);
+    return k;
 }
 AB_HD int dacc_rank(const DAcc& A, const Key& k) {
     const uint64_t S = (k.w[0] >> (8 * (7 - A.as))) * 0x0101010101010101ull;      // byte j-1 = sum of the last j exponents
@@ -689,7 +700,7 @@ AB_HD double dacc_fold(DAcc& A, int r, const Key& k, double tv) {
     const uint64_t cb = sm_ld64(va);
     if (cb == AB_ABSENT) {
         sm_st64(va, d2u(tv));
-        for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + r), k.w[w]);
+        dacc_put_key(A, r, k);
         return 0.0;
     }
     const double cur = u2d(cb);
@@ -743,8 +754,7 @@ AB_HDN int dacc_emit(Ctx& c, DAcc& A, int dst) {
             if (cb != AB_ABSENT) {
                 if (dst >= 0) {
                     const int o = dst + (total + popc32(m & lanemask_lt(lane))) * AB_TW;
-                    for (int w = 0; w < AB_KW; ++w) base[o + w] = sm_ld64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + r));
-                    base[o + AB_KW] = cb;
+                    bput(base, o, dacc_get_key(A, r), u2d(cb));
                 }
                 sm_st64(va, AB_ABSENT);
             }
@@ -1311,7 +1321,7 @@ AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int
         A.touched |= 1u << (rr >> 5);
         sm_st64(yval + 8u * (uint32_t)rr, d2u(0.0));
         sm_st64(A.val + 8u * (uint32_t)rr, base[x.off + j * AB_TW + AB_KW]);
-        for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + rr), k.w[w]);
+        dacc_put_key(A, rr, k);
     }
     wsync();
     #pragma unroll 1
@@ -1320,7 +1330,7 @@ AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int
         A.touched |= 1u << (rr >> 5);
         if (sm_ld64(A.val + 8u * (uint32_t)rr) == AB_ABSENT) {
             sm_st64(A.val + 8u * (uint32_t)rr, d2u(0.0));
-            for (int w = 0; w < AB_KW; ++w) sm_st64(A.key + 8u * (uint32_t)(w * AB_SM_DENSE + rr), k.w[w]);
+            dacc_put_key(A, rr, k);
         }
         sm_st64(yval + 8u * (uint32_t)rr, base[y.off + j * AB_TW + AB_KW]);
     }

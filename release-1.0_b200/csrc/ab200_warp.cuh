@@ -27,14 +27,27 @@ void sync();
 
 inline namespace AB_VARIANT {
 
+// AB_GROUP lanes work on one cell: 32 = one warp per cell; 16 or 8 = two or four cells side by side in one warp, each on its
+// own lane group (own shuffle segment, own ballot bits, own barrier mask). Groups that follow the same control flow share
+// the instruction stream; groups that diverge are serialised by the hardware and meet again at the reconvergence point.
+#ifndef AB_GROUP
+#define AB_GROUP 32
+#endif
 #if defined(__CUDA_ARCH__)
-#define AB_W 32
-AB_HD int wlane() { return (int)(threadIdx.x & 31u); }
-AB_HD void wsync() { __syncwarp(); }
+#define AB_W AB_GROUP
+AB_HD int wlane() { return (int)(threadIdx.x & (AB_GROUP - 1)); }
+#if AB_GROUP == 32
+AB_HD unsigned wgmask() { return 0xFFFFFFFFu; }
 AB_HD unsigned wballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
-AB_HD uint64_t wshfl(uint64_t v, int src) { return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, src); }
-AB_HD double wshfl(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-AB_HD int wshfl(int v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+#else
+AB_HD unsigned wgshift() { return threadIdx.x & 31u & ~(unsigned)(AB_GROUP - 1); }
+AB_HD unsigned wgmask() { return ((1u << AB_GROUP) - 1u) << wgshift(); }
+AB_HD unsigned wballot(bool p) { return (__ballot_sync(wgmask(), p) >> wgshift()) & ((1u << AB_GROUP) - 1u); }
+#endif
+AB_HD void wsync() { __syncwarp(wgmask()); }
+AB_HD uint64_t wshfl(uint64_t v, int src) { return (uint64_t)__shfl_sync(wgmask(), (unsigned long long)v, src, AB_GROUP); }
+AB_HD double wshfl(double v, int src) { return __shfl_sync(wgmask(), v, src, AB_GROUP); }
+AB_HD int wshfl(int v, int src) { return __shfl_sync(wgmask(), v, src, AB_GROUP); }
 AB_HD int popc32(unsigned m) { return __popc(m); }
 AB_HD int ffs32(unsigned m) { return __ffs((int)m); }
 AB_HD uint32_t cas32(uint32_t* p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }

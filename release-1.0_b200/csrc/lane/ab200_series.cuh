@@ -1,0 +1,132 @@
+// [lane build] One frontier cell per LANE: the throughput build of the evolution kernel, used only for frontiers far larger
+// than the device can hold one-warp-per-cell (ab200_capi.cu picks it above AB_LANE_THRESHOLD cells). Same algorithm and
+// arithmetic as the warp build one directory up, written as sequential per-lane code over lane-interleaved scratch arenas.
+// ab200_series.cuh -- series-based TaylorModel functions.
+//   rec(x)   src/taylor_model.cpp:1882-1920 (geometric series about the range centre)
+//   sqrt(x)  src/taylor_model.cpp:1840-1880 (binomial series about the range centre, include/series.h:115-125)
+//   abs/max  src/taylor_model.cpp:1486-1527 (range tests, else the reference's fixed degree-12 even polynomial +-0.035)
+#pragma once
+#include "ab200_calc.cuh"
+
+namespace ab200 { inline namespace AB_VARIANT {
+
+// rec(x). For a constant model (every "/ constant" of the configs) eps is exactly 0 and the series has one term, so
+// no libm value enters the result. For eps>0 the series degree and the truncation bound use log()/pow(), which the
+// reference takes from glibc; the device values can differ in the last bit, so that branch is flagged unpinned.
+AB_HDN TM tm_rec(Ctx& c, const TM& x) {
+    const int m0 = c.A.top;
+    Ivl r = tm_range(c, x);
+    if (r.u >= 0 && r.l <= 0) { fail(c, ST_DIVZERO); return tm_copy(c, x); }
+    double a = div_m(c.rnd, add_m(c.rnd, r.l, r.u), 2.0);
+    double eps = dabs(div_ru(sub_ru(r.u, r.l), add_ru(r.u, r.l)));
+    c.rnd = RN;
+    unsigned d;
+    if (eps == 0.0) d = 1;
+    else d = (unsigned)(log(mul_rn(sub_rn(1.0, eps), x.acc.sweep)) / log(eps)) + 1;
+    // y=1-(x/a)
+    TM xa = tm_copy(c, x);
+    tm_scal(c, xa, ivl_div(ivl(1.0), a));
+    TM y = tm_neg(c, xa);
+    tm_acc(c, y, 1.0);
+    // z=(-1)^d; z=1+z*y, d times
+    TM z = tm_begin(c, x.as, x.acc);
+    tm_acc(c, z, (d % 2) ? -1.0 : 1.0);
+    for (unsigned i = 0; i < d; ++i) {
+        TM p = tm_mul(c, z, y, y.acc);
+        tm_acc(c, p, 1.0);
+        tm_slide(c, p, z.off);
+        z = p;
+    }
+    double te = (eps == 0.0) ? 0.0 : div_rn(pow(eps, (double)d), sub_rn(1.0, eps));
+    z.e = add_ru(te, z.e);
+    c.rnd = RN;
+    if (a == 0) { fail(c, ST_DIVZERO); }
+    tm_scal(c, z, ivl_div(ivl(1.0), a));
+    tm_slide(c, z, m0);
+    return z;
+}
+
+// sqrt(x). The series degree d and the truncation bound use log()/pow() (glibc in the reference); on the device these
+// may differ in the last bit. d only changes if the quotient of logs sits within an ulp of an integer, and the
+// truncation bound (~sweep threshold) is added to an error many orders larger, so results coincide in practice; the
+// parity tests for sqrt systems therefore compare cell sets exactly and boxes to 1e-12 relative width.
+#define AB_MAXSER 48
+AB_HDN TM tm_sqrt(Ctx& c, const TM& x) {
+    const int m0 = c.A.top;
+    Ivl r = tm_range(c, x);
+    if (r.l <= 0) { fail(c, ST_DOMAIN); return tm_copy(c, x); }
+    double a = div_m(c.rnd, add_m(c.rnd, r.l, r.u), 2.0);
+    double eps = div_ru(sub_ru(r.u, r.l), add_ru(r.u, r.l));
+    c.rnd = RN;
+    unsigned d;
+    if (eps == 0.0) d = 1;
+    else d = (unsigned)(log(mul_rn(sub_rn(1.0, eps), x.acc.sweep)) / log(eps) + 1);
+    if (d + 1 > AB_MAXSER) { fail(c, ST_UNSUPPORTED); return tm_copy(c, x); }
+    // y=(x/a)-1
+    TM y = tm_copy(c, x);
+    tm_scal(c, y, ivl_div(ivl(1.0), a));
+    tm_acc(c, y, -1.0);
+    // Series<Interval>::sqrt(d,Interval(1))
+    Ivl ser[AB_MAXSER];
+    int st = ST_OK;
+    ser[0] = ivl_sqrt(ivl(1.0), &st);
+    Ivl mhr = ivl_div(-0.5, ivl(1.0), &st);
+    for (unsigned i = 1; i <= d; ++i) ser[i] = ivl_mul(ivl_div(ivl_mul(mhr, (double)(2 * (int)i - 3)), (double)i), ser[i - 1]);
+    TM z = tm_begin(c, x.as, x.acc);
+    tm_acc(c, z, ser[d - 1]);
+    for (unsigned i = 0; i < d; ++i) {
+        TM p = tm_mul(c, z, y, y.acc);
+        tm_acc(c, p, ser[d - i - 1]);
+        tm_clean(c, p, p.acc);
+        tm_slide(c, p, z.off);
+        z = p;
+    }
+    double te = (eps == 0.0) ? 0.0 : mul_m(c.rnd, div_m(c.rnd, pow(eps, (double)d), sub_m(c.rnd, 1.0, eps)), ivl_mag(ser[d]));
+    z.e = add_m(c.rnd, z.e, te);
+    tm_scal(c, z, ivl_sqrt(ivl(a), &st));
+    if (st != ST_OK) fail(c, st);
+    tm_slide(c, z, m0);
+    return z;
+}
+// abs(x) src/taylor_model.cpp:1503-1527. Result at the arena top recorded on entry.
+AB_HDN TM tm_abs(Ctx& c, const TM& x) {
+    const int m0 = c.A.top;
+    Ivl xr = tm_range(c, x);
+    if (xr.l >= 0.0) return tm_copy(c, x);
+    if (xr.u <= 0.0) return tm_neg(c, x);
+    const double p[7] = {0.0112167620474, 5.6963263292747541, -31.744583789655049, 100.43002481377681, -162.01366698662306, 127.45243493284417, -38.829743345344667};
+    const double err = 0.035;
+    double xmag = ivl_mag(xr);
+    TM s0 = tm_copy(c, x);
+    tm_scal(c, s0, ivl_div(ivl(1.0), xmag));                    // x/xmag
+    TM s = tm_mul(c, s0, s0, s0.acc);                           // sqr(s)
+    TM r = tm_begin(c, x.as, acc_default());
+    tm_append(c, r, key_zero(), p[6]);
+    for (int i = 0; i < 6; ++i) {
+        int j = 5 - i;
+        TM t = tm_mul(c, s, r, r.acc);
+        tm_acc(c, t, p[j]);
+        tm_slide(c, t, r.off);
+        r = t;
+    }
+    tm_acc(c, r, ivl(-err, err));
+    tm_scal(c, r, xmag);
+    tm_slide(c, r, m0);
+    return r;
+}
+// max(x,y) src/taylor_model.cpp:1486-1496. Result at the arena top recorded on entry.
+AB_HDN TM tm_max(Ctx& c, const TM& x, const TM& y) {
+    const int m0 = c.A.top;
+    Ivl xr = tm_range(c, x), yr = tm_range(c, y);
+    if (xr.l >= yr.u) return tm_copy(c, x);
+    if (yr.l >= xr.u) return tm_copy(c, y);
+    TM sum = tm_add(c, x, y);
+    TM dif = tm_sub(c, x, y);
+    TM ad = tm_abs(c, dif);
+    TM r = tm_add(c, sum, ad);
+    tm_scal(c, r, ivl_div(ivl(1.0), 2.0));                      // .../2
+    tm_slide(c, r, m0);
+    return r;
+}
+
+} } // namespace ab200

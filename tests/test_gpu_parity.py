@@ -287,3 +287,32 @@ def test_round_trip_properties_at_scale(pkg):
         assert np.isin(own.keys, r_all.keys).all()
     finally:
         an.close()
+
+
+def test_lane_build_matches_warp_build(pkg, monkeypatch):
+    """The one-lane-per-cell build (used above AB_LANE_THRESHOLD cells) and the one-warp-per-cell build are two schedules of
+    the same arithmetic: identical boxes and identical cell keys on the same frontier. Also checks the golden boxes through
+    the lane build, and that an unknown AB200_TUNE value is refused."""
+    d = golden_io.load_dump("vanderpol_cells_acc7.txt.gz")
+    ev = _evolver(pkg, d, arena_words=32768, max_boxes=320)
+    try:
+        locs = [ev.location(c["loc"]) for c in d["cells"]]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], 2)
+        T, events = d["config"]["T"], d["config"]["events"]
+        out = {}
+        for build in ("warp", "lane"):
+            monkeypatch.setenv("AB200_TUNE", build)
+            (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, T, events, d["config"]["ignore_activations"])
+            assert ev.last_status.build == (2 if build == "lane" else 0)
+            r, e = ev.upper_reach_evolve(np.array(locs, dtype=np.int32), boxes, T, events)
+            out[build] = (roff.copy(), rbox.copy(), foff.copy(), fbox.copy(), r.keys.copy(), e.keys.copy())
+            for i, c in enumerate(d["cells"]):
+                assert golden_io.boxes_equal_bits(rbox[roff[i]:roff[i + 1], :4], c["reach"]), "%s build, reach boxes of cell %d" % (build, c["id"])
+                assert golden_io.boxes_equal_bits(fbox[foff[i]:foff[i + 1], :4], c["final"]), "%s build, final boxes of cell %d" % (build, c["id"])
+        for a, b in zip(out["warp"], out["lane"]):
+            assert a.shape == b.shape and a.tobytes() == b.tobytes()
+        monkeypatch.setenv("AB200_TUNE", "no-such-build")
+        with pytest.raises(pkg.Ab200Error):
+            ev.upper_reach_evolve(np.array(locs, dtype=np.int32), boxes, T, events)
+    finally:
+        ev.close()
