@@ -4,7 +4,7 @@
 A "step" is one lock-to-grid lap of HybridReachabilityAnalyser::upper_reach over one frontier: every frontier cell is
 evolved for lock_to_grid_time by the evolution kernel, its reach/final boxes are rasterised, de-duplicated and
 sorted on the device. Workload = BASELINE.json configs[2]: van der Pol (mu=1), Taylor orders 6/6, >= 10^5 initial grid
-cells (initial box [-2.2,2.2]x[-2.8,2.8] minced at accuracy 7 -> 101,400 cells), domain [-3,3]^2.
+cells (initial box [-2.2,2.2]x[-2.8,2.8] minced at accuracy 7 -> 101,520 cells), domain [-3,3]^2.
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA)
   python bench.py --impl reference ...                     the reference's own CPU analyser (oracle/_ref), host cores
@@ -29,6 +29,7 @@ DOMAIN = [-3.0, 3.0, -3.0, 3.0]
 INIT = [-2.2, 2.2, -2.8, 2.8]
 ACC = 7
 EVENTS = 5
+FRONTIER = 101520     # cells of the minced initial set at accuracy 7
 
 
 def read_peaks():
@@ -82,6 +83,30 @@ def frontier_cells(pkg, an, n_cells):
     return np.ascontiguousarray(cells)
 
 
+def fp64_sample(pkg, an, cells, locs_dtype):
+    """Algorithmic FP64 operations per evolution step of THIS workload, measured in this run: a strided sample of the
+    frontier goes through the warp build, whose kernels count the operations of the reference algorithm per primitive on
+    the actual term counts (SURVEY.md 8d formulas; ab200_status.alg_flops). The lane build runs the same arithmetic and
+    has no counters, so its FP64 rate is quoted with this per-step figure."""
+    import numpy as np
+    n = cells.shape[0]
+    take = min(n, 2048)
+    sel = np.linspace(0, n - 1, take).astype(np.int64)
+    boxes = pkg.pack_boxes(np.ascontiguousarray(cells[sel]), 2)
+    locs = np.zeros((take,), dtype=locs_dtype)
+    old = os.environ.get("AB200_TUNE")
+    os.environ["AB200_TUNE"] = "warp"
+    try:
+        an.evolver.upper_reach_evolve(locs, boxes, an.lock_to_grid_time, EVENTS)
+        st = an.evolver.last_status
+        return (st.alg_flops / st.steps) if st.steps else None, int(take)
+    finally:
+        if old is None:
+            os.environ.pop("AB200_TUNE", None)
+        else:
+            os.environ["AB200_TUNE"] = old
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -98,23 +123,25 @@ def run_ours(args):
     an = pkg.HybridReachabilityAnalyser(system, DOMAIN, ACC, device=local, settings={"arena_words": args.arena_words, "max_boxes": args.max_boxes, "hash_log2": 25})
     ev = an.evolver
     all_cells = frontier_cells(pkg, an, args.cells)
-    # Frontier cells are independent units (no data-path collective until the key exchange), so the path scales by
-    # giving every GPU its own frontier: WEAK scaling, 101,520 cells per rank. The global frontier of an N-GPU run is
-    # N translates of the configs[2] frontier (shard r is shifted by r/N of a cell width along x, so the shards are
-    # distinct enclosures with the same distribution of work); rank r owns shard r.
     import importlib.util
     spec = importlib.util.spec_from_file_location("ab200_parallel", os.path.join(ROOT, "release-1.0_b200", "parallel.py"))
     par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
-    mine = all_cells.copy()
-    mine[:, 0:2] += (float(rank) / world) * (all_cells[0, 1] - all_cells[0, 0])
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        # STRONG scaling: ONE frontier, dealt round-robin in blocks of 64 cells to the ranks.
+        mine = np.ascontiguousarray(all_cells[par.deal_blocks(all_cells.shape[0], rank, world, 64)])
+    else:
+        # WEAK scaling (the default; frontier cells are independent units): one configs[2] frontier per GPU. The global
+        # frontier of an N-GPU run is N translates of it (shard r shifted by r/N of a cell width along x, so the shards are
+        # distinct enclosures with the same distribution of work); rank r owns shard r.
+        mine = all_cells.copy()
+        mine[:, 0:2] += (float(rank) / world) * (all_cells[0, 1] - all_cells[0, 0])
     n_mine = mine.shape[0]
     boxes = pkg.pack_boxes(mine, 2)
     locs = np.zeros((n_mine,), dtype=np.int32)
     T = an.lock_to_grid_time * args.lap_scale
-    # tune exactly as the analyser's lap does (restriction bounding box)
     an.lib.ab200_analyser_set_lock_time(an.handle, T)
-    import ctypes as C
-    # one throw-away analyser call on a tiny set performs the tuning upload (tune_evolver)
+    # one throw-away analyser call on a tiny set performs the tuning upload of a lap (tune_evolver)
     an.upper_reach_evolve({0: [1.0, 1.0 + 1e-3, 1.0, 1.0 + 1e-3]}, 1e-3, EVENTS)
 
     def lap():
@@ -131,13 +158,16 @@ def run_ours(args):
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t0 = time.perf_counter()
-    ev_ms = 0.0; ra_ms = 0.0; steps = 0; keys = 0; reach_n = 0; launches = 0
+    ev_ms = 0.0; ra_ms = 0.0; steps = 0; keys = 0; reach_n = 0; launches = 0; flops = 0.0; build = 0
+    reach_sha = None
     for _ in range(args.steps):
         r, e, st = lap()
         ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r); launches += st.launches
+        flops += st.alg_flops; build = st.build
         if world > 1:
             # newly reached cell ids are exchanged so that every rank holds the lap's reach set (NCCL all-gather)
             reach_n = int(par.exchange_keys(r.keys, dist, torch.device("cuda", local)).shape[0])
+        last_r, last_e = r, e
     barrier()
     t1 = time.perf_counter()
     sampler.stop_flag = True; sampler.join()
@@ -150,52 +180,61 @@ def run_ours(args):
     n_total, steps_total, keys_total = [float(x) for x in tot.tolist()]
     e2e_value = n_total * args.steps / wall
     dev_value = n_total * args.steps / ((ev_ms + ra_ms) * 1e-3)
-    # roofline of the dominant kernel (K_evolve). The per-cell loop is latency/FP64 work on per-cell scratch in HBM;
-    # the contract's "bound" keys are hbm|tensor, so the HBM view is reported: algorithmic bytes = the words each
-    # _evolution_step must move through its scratch (2 x arena peak words x 8 B per step).
+    # ---- parity of the benchmark's own output: fingerprint of the reach / evolve cell sets of the full configs[2] lap,
+    # against the fingerprint of the reference's UpperReachEvolveWorker::get_result() on the same frontier
+    # (tests/golden/vanderpol_bench_fingerprint.json, made by tests/golden/make_bench_fingerprint.sh)
+    parity = None
+    if world == 1 and args.lap_scale == 1.0 and not args.cells:
+        parity = check_fingerprint(pkg, an, last_r, last_e)
+    # ---- roofline of the dominant kernel (K_evolve): FP64 CUDA-core work. achieved = algorithmic FP64
+    # operations of the reference algorithm / event time of the kernel; peak = separately rounded DMUL+DADD rate measured in
+    # this run (interval arithmetic cannot fuse: every product and every sum carries its own rounding direction); the
+    # DFMA rate is reported beside it.
     peaks = read_peaks()
+    fp64 = fp64_fma = None
+    try:
+        fp64 = ev.probe_fp64(); fp64_fma = ev.probe_fp64(fma=True)
+    except Exception:
+        pass
+    flops_per_step = None; flops_sample = None
+    if flops > 0 and steps > 0:
+        flops_per_step = flops / steps; flops_sample = "every cell of the timed laps (device counters)"
+    else:
+        fps, take = fp64_sample(pkg, an, all_cells, np.int32)
+        flops_per_step = fps; flops_sample = "%d-cell strided sample of the same frontier through the warp build (device counters)" % take
+    alg_gflops = (steps / args.steps) * (flops_per_step or 0.0) / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # 2,314 words = largest live scratch of one cell during a step of this workload (arena high-water mark of the
-    # compact slide-every-batch layout, round 1); every live word is produced once and consumed once.
-    alg_bytes_per_step = 2.0 * 2314 * 8.0
-    # per launch on ONE GPU (this rank's steps; ev_ms is the max over ranks), so that frac is against one GPU's peak
-    achieved = (steps / args.steps) * alg_bytes_per_step / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
-    # DRAM bytes of one K_evolve launch from the committed single-pass ncu capture of this very command (profiles/);
-    # only quoted when the run matches the captured configuration
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "K_evolve_traffic.json")))
-        if tj.get("frontier_cells_per_gpu") == int(n_mine) and not os.environ.get("AB200_TUNE") and args.lap_scale == 1.0:
+        if tj.get("frontier_cells_per_gpu") == int(n_mine) and tj.get("build") == int(build) and args.lap_scale == 1.0:
             traffic = tj.get("dram_bytes_per_launch")
     except Exception:
         pass
-    fp64 = None
-    try:
-        fp64 = ev.probe_fp64()
-    except Exception:
-        pass
-    # Algorithmic FP64 work: operations of the REFERENCE algorithm by its per-primitive formulas, counted on
-    # 64 cells of this frontier (tests/golden/vanderpol_cells_acc7.txt.gz, 8,842 steps) with the instrumented host build
-    # of the kernel headers: 299,860 operations per evolution step.
-    FLOPS_PER_STEP = 299860.0
-    alg_gflops = (steps / args.steps) * FLOPS_PER_STEP / ((ev_ms / args.steps) * 1e-3) / 1e9 if ev_ms > 0 else 0.0
+    build_name = {0: "warp (one warp per cell)", 1: "warp, two-word keys", 2: "lane (one lane per cell)"}.get(int(build), str(build))
     line = {
         "metric": METRIC, "value": dev_value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %d frontier cells per GPU (configs[2])" % (ACC, int(n_mine)),
-                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "frontier_cells_per_gpu": int(n_mine), "lap_time": T, "tune": os.environ.get("AB200_TUNE", "default"),
-                   "l2_policy": "per-cell scratch arenas (%.1f GB) exceed L2; no flush needed" % (n_total / world * args.arena_words * 8 / 1e9)},
+                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "frontier_cells_per_gpu": int(n_mine), "lap_time": T,
+                   "evolution_build": build_name,
+                   "l2_policy": "every lap rewrites its scratch arenas and box lists (GBs, far beyond L2); no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_mine * (80 + 4)), "d2h_bytes_per_step": int(8 * (reach_n + 0) + 24 * n_mine)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
-                     "traffic": traffic, "kernel": "K_evolve", "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
+        "roofline": {"bound": "fp64", "achieved": alg_gflops, "peak": fp64, "unit": "GFLOP/s", "frac": (alg_gflops / fp64) if fp64 else None,
+                     "traffic": traffic, "kernel": "K_evolve",
+                     "peak_source": "measured in this run: DMUL.RD+DADD.RU chains (directed rounding cannot use FMA); DFMA chains give fp64_fma_gflops",
+                     "fp64_fma_gflops": fp64_fma, "frac_of_fma_peak": (alg_gflops / fp64_fma) if fp64_fma else None,
+                     "flops_per_step": flops_per_step, "flops_counted_on": flops_sample,
+                     "evolve_ms_per_step": ev_ms / args.steps, "raster_sort_ms_per_step": ra_ms / args.steps,
                      "evolution_steps_per_s": steps_total / (ev_ms * 1e-3) if ev_ms > 0 else None,
-                     "fp64_directed_gflops_peak_measured": fp64, "peak_source": "measured" if peaks else "fallback",
-                     "fp64_algorithmic": {"achieved_gflops": alg_gflops, "peak_gflops": fp64, "frac": (alg_gflops / fp64) if fp64 else None,
-                                          "flops_per_step": FLOPS_PER_STEP}},
+                     "hbm": {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                             "raster_sort_keys_per_step": keys_total / args.steps if args.steps else None,
+                             "raster_sort_gbs": (keys_total / args.steps) * 8.0 * (1 + 2 * 3 + 2) / ((ra_ms / args.steps) * 1e-3) / 1e9 if ra_ms > 0 else None}},
         "reach_cells": reach_n,
+        "parity": parity,
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
@@ -204,6 +243,26 @@ def run_ours(args):
     an.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def check_fingerprint(pkg, an, reach, evolve):
+    """sha256 of the reach / evolve cell sets of the lap, enumerated as the reference enumerates a HybridDenotableSet (maximal
+    dyadic cells, boxes printed as C hex floats), against the committed fingerprint of the reference's own result."""
+    import hashlib
+    path = os.path.join(ROOT, "tests", "golden", "vanderpol_bench_fingerprint.json")
+    try:
+        want = json.load(open(path))
+    except Exception:
+        return {"verdict": "unchecked", "why": "no committed fingerprint"}
+    out = {}
+    for name, cs in (("reach", reach), ("evolve", evolve)):
+        _, boxes = an.enumerate(cs, mince=False)
+        h = hashlib.sha256()
+        for b in boxes:
+            h.update((" ".join(float(x).hex() for x in b[:4]) + "\n").encode())
+        out[name] = {"cells": int(boxes.shape[0]), "sha256": h.hexdigest()}
+    ok = all(out[k]["sha256"] == want[k]["sha256"] and out[k]["cells"] == want[k]["cells"] for k in ("reach", "evolve"))
+    return {"verdict": "identical to the reference" if ok else "MISMATCH", "reach": out["reach"], "evolve": out["evolve"], "reference": want}
 
 
 def cpu_baseline(n_cells, threads=None):
@@ -215,7 +274,7 @@ def cpu_baseline(n_cells, threads=None):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_harness missing"}
     cores = threads or os.cpu_count() or 1
     env = dict(os.environ); env["ORACLE_THREADS"] = str(cores)
-    total_frontier = 101400
+    total_frontier = FRONTIER
     stride = max(1, total_frontier // n_cells)
     cmd = [harness, SYSTEM, "worker", "acc=%d" % ACC, "ncells=%d" % n_cells, "stride=%d" % stride, "init=%s" % ",".join(str(x) for x in INIT)]
     o = subprocess.check_output(cmd, env=env).decode()
@@ -229,10 +288,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # Sample size: as many cells as keep the whole --steps/--warmup run within about five minutes, at most 8,192 per step
+    # (the rate is probed on 8 cells per host thread first).
+    cores = os.cpu_count() or 1
+    probe = cpu_baseline(8 * cores)
+    rate = probe["value"] or 50.0
+    runs = args.steps + min(args.warmup, 1)
+    n = args.cpu_cells or int(max(16 * cores, min(8192, 280.0 * rate / max(runs, 1))))
     vals = []
-    n = args.cpu_cells or 32 * (os.cpu_count() or 1)
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(max(os.cpu_count() or 1, n // 3))
+        cpu_baseline(n)
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
@@ -242,7 +307,7 @@ def run_reference(args):
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, bounded sample of the 101400-cell frontier" % ACC,
+            "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, bounded sample (%d cells per step) of the %d-cell frontier (configs[2])" % (ACC, n, FRONTIER),
                        "system": SYSTEM, "accuracy": ACC},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -255,11 +320,12 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cells", type=int, default=0, help="subsample the frontier (0 = the full 101,400 cells)")
+    ap.add_argument("--cells", type=int, default=0, help="subsample the frontier (0 = the full 101,520 cells)")
     ap.add_argument("--cpu-cells", type=int, default=0, help="CPU sample size (0 = 3 cells per host thread)")
     ap.add_argument("--arena-words", type=int, default=32768)
     ap.add_argument("--max-boxes", type=int, default=320)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: one frontier per GPU (weak, default) or one frontier dealt to all GPUs (strong)")
     ap.add_argument("--lap-scale", type=float, default=1.0, help="PROFILING ONLY: shorten the lap so that ncu can replay the kernel; not a bench value")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -75,6 +75,8 @@ typedef struct ab200_status {
     int32_t build;            /* evolution build used by the last batch: 0 = one warp per cell (one-word MultiIndex keys),
                                  1 = one warp per cell (two-word keys), 2 = one lane per cell (very large frontiers) */
     int32_t reserved;
+    double  alg_flops;        /* FP64 operations of the REFERENCE algorithm executed by this call, counted per primitive on the
+                                 actual term counts with the formulas of SURVEY.md 8(d) (0 when the lane build ran) */
 } ab200_status;
 
 void ab200_default_settings(ab200_settings* s);
@@ -167,7 +169,8 @@ int  ab200_analyser_enumerate(const ab200_analyser* an, const ab200_cellset* cs,
                               int32_t* locs, double* boxes);
 
 /* Device probes used by bench.py for the roofline denominators. */
-int  ab200_probe_fp64(ab200_ctx* ctx, double* gflops_rounded_ops);
+int  ab200_probe_fp64(ab200_ctx* ctx, double* gflops_rounded_ops);      /* DMUL.RD + DADD.RU chains: what this library can issue */
+int  ab200_probe_fp64_fma(ab200_ctx* ctx, double* gflops_fma);          /* DFMA chains, 2 operations each: the nominal peak */
 
 #ifdef __cplusplus
 }

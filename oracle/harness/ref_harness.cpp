@@ -351,6 +351,7 @@ int main(int argc, char** argv) {
         double ws=std::chrono::duration<double>(std::chrono::steady_clock::now()-w0).count();
         fprintf(out,"worker seconds %.6f cells %lu frontier %lu reach_cells %lu evolve_cells %lu threads %u\n",ws,n,(unsigned long)all.size(),
                 (unsigned long)res.first.size(),(unsigned long)res.second.size(),boost::thread::hardware_concurrency());
+        if(geti(kv,"dump",0)) { dump_set(out,"reach",res.first); dump_set(out,"evolve",res.second); }   // full result, for fingerprints
         return 0;
     }
 

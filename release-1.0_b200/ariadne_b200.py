@@ -34,7 +34,7 @@ EXPORTS = [
     "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
-    "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64",
+    "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma",
 ]
 
 
@@ -48,7 +48,7 @@ class Settings(C.Structure):
 class Status(C.Structure):
     _fields_ = [("code", C.c_int32), ("cell", C.c_int64), ("steps", C.c_int64), ("keys_emitted", C.c_int64),
                 ("arena_peak", C.c_int32), ("evolve_ms", C.c_double), ("raster_ms", C.c_double), ("launches", C.c_int64),
-                ("build", C.c_int32), ("reserved", C.c_int32)]
+                ("build", C.c_int32), ("reserved", C.c_int32), ("alg_flops", C.c_double)]
 
 
 class Ab200Error(RuntimeError):
@@ -112,6 +112,7 @@ def load_library():
     lib.ab200_analyser_cells_evolved.argtypes = [vp]; lib.ab200_analyser_cells_evolved.restype = i64
     lib.ab200_analyser_enumerate.argtypes = [vp, vp, C.c_int, P(u64), P(i32), P(dbl)]; lib.ab200_analyser_enumerate.restype = C.c_int
     lib.ab200_probe_fp64.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64.restype = C.c_int
+    lib.ab200_probe_fp64_fma.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64_fma.restype = C.c_int
     lib.ab200_system_check.argtypes = [C.c_char_p, P(i32), P(i32), P(i32), C.c_char_p, i32]; lib.ab200_system_check.restype = C.c_int
     _lib = lib
     return lib
@@ -266,9 +267,11 @@ class Evolver(object):
                 out[k, 1 + i] = idx[i]
         return out
 
-    def probe_fp64(self):
+    def probe_fp64(self, fma=False):
+        """Measured FP64 rate in GFLOP/s: separately rounded multiply + add chains (what interval arithmetic can issue), or
+        fused multiply-adds counted as two operations (the nominal peak)."""
         g = C.c_double(0)
-        self._check(self.lib.ab200_probe_fp64(self.handle, C.byref(g)))
+        self._check((self.lib.ab200_probe_fp64_fma if fma else self.lib.ab200_probe_fp64)(self.handle, C.byref(g)))
         return g.value
 
 

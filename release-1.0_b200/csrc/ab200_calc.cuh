@@ -280,6 +280,7 @@ AB_HD TM ph_load(Ctx& c, int slot, int as, Acc acc) {
 // Result at the arena top.
 AB_HDN TM term_times_power(Ctx& c, double cv, const TM& p, Acc acc) {
     const int W = AB_W, lane = c.lane, n = p.n, m = c.A.top, soff = p.off;
+    AB_FLOPS(5.0 * n + 3.0 + 2.0 * (1 + n) + 6.0);
     uint64_t* const base = c.A.base;
     TM r; r.off = m; r.n = 0; r.as = p.as; r.e = 0.0; r.acc = acc;
     if (!arena_room(c, m, n)) return r;
@@ -309,6 +310,7 @@ AB_HDN TM term_times_power(Ctx& c, double cv, const TM& p, Acc acc) {
 // chain in x order, and the cross terms use the norm of t (needed only when q carries an error).
 AB_HDN void term_times_monomial(Ctx& c, TM& t, const TM& q, Acc acc) {
     const int W = AB_W, lane = c.lane, n = t.n, off = t.off;
+    AB_FLOPS(10.0 * n + 8.0);
     uint64_t* const base = c.A.base;
     const Key qa = bkey(base, q.off); const double qv = bval(base, q.off), aqv = dabs(qv), qe = q.e, te0 = t.e;
     const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
@@ -364,10 +366,13 @@ AB_HDN double chain_times_power(Ctx& c, DAcc& DA, ChainState& st, const TM& p, i
         if (act) { const int w = soff + j * AB_TW; sv = bval(base, w); ta = key_add(fa, bkey(base, w)); tv = mul_rn(fv, sv); disc = dabs(tv) < sweep || key_deg(ta) > maxdeg; }
         const unsigned dm = wballot(disc);
         if (fold) {
-            double g = 0.0;
-            if (act && !disc) g = dacc_fold(DA, dacc_rank(DA, ta), ta, tv);
+            double g = 0.0; bool co = false;
+            if (act && !disc) g = dacc_fold(DA, dacc_rank(DA, ta), ta, tv, &co);
             const unsigned gm = wballot(g != 0.0);
             if (gm) te = chain_ru_masked(te, g, gm);
+#if defined(AB_COUNT_FLOPS) || defined(AB_MUL_HIST)
+            { const int cc_ = popc32(wballot(co)); AB_FLOPS(5 * cc_); }
+#endif
         } else {
             const unsigned km = wballot(act && !disc);
             if (to_arena) { if (act && !disc) bput(base, m + (rn + popc32(km & lanemask_lt(lane))) * AB_TW, ta, tv); }
@@ -431,7 +436,7 @@ AB_HDN TM compose_stream_dense(Ctx& c, const TM& xi, const TM* ys, int nys, cons
                 // every product so far was discarded: _mul4 with an empty left factor leaves only the error cross terms
                 const double nm = (st.e != 0.0) ? ph_norm(c, pslot, pw) : 0.0;
                 st.e = add_ru(0.0, add_ru(add_ru(mul_ru(0.0, pw.e), mul_ru(nm, st.e)), mul_ru(st.e, pw.e)));
-                c.rnd = RN;
+                c.rnd = RN; AB_FLOPS(2.0 * pw.n + 6.0);
             } else if (st.kind == 1) {
                 if (pw.n == 0) {      // one term times an empty power: only the cross term |x| * error(power) remains
                     st.e = add_ru(0.0, add_ru(add_ru(mul_ru(dabs(st.va), pw.e), mul_ru(0.0, st.e)), mul_ru(st.e, pw.e)));
@@ -452,12 +457,12 @@ AB_HDN TM compose_stream_dense(Ctx& c, const TM& xi, const TM* ys, int nys, cons
             if (st.kind == 1) {
                 double g = 0.0;
                 if (lane == 0) g = dacc_fold(DA, dacc_rank(DA, st.ka), st.ka, st.va);
-                te = add_ru(0.0, wshfl(g, 0)); t_e = st.e;
+                te = add_ru(0.0, wshfl(g, 0)); t_e = st.e; AB_FLOPS(5);
                 wsync();
             } else if (st.kind == 0) { te = 0.0; t_e = st.e; }
             else { te = dacc_add_model(c, DA, st.tt, true); t_e = st.tt.e; }
         }
-        e_run = add_ru(add_ru(e_run, t_e), te / 2);
+        e_run = add_ru(add_ru(e_run, t_e), te / 2); AB_FLOPS(3);
     }
     ra.n = dacc_emit(c, DA, ri);
     ra.e = e_run;
@@ -738,6 +743,9 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
         if (!T.overflow) break;
         if (attempt == 1) { fail(c, ST_ARENA); return res; }
     }
+#if defined(AB_COUNT_FLOPS) || defined(AB_MUL_HIST)
+    for (int j = 0; j <= deg; ++j) if (bn[j]) AB_FLOPS((double)(j + 1) * (4.0 * bn[j] + 3.0 + 3.0 + 5.0 * bn[j] * 0.5));   // _scal + _add2 per stream (about half the terms coincide)
+#endif
     // error chain in the reference's stream order; an empty bucket contributes nothing
     double e = tm.e;
     #pragma unroll 1

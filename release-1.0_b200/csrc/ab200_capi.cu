@@ -23,7 +23,7 @@ int dev_upload_system_v(const void* system_desc, char* errbuf, int errlen); \
 int dev_evolve_capacity_v(char* errbuf, int errlen); \
 int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
                         uint64_t* arena, int arena_words, const uint32_t* binom, int* next_cell, double* reach, int32_t* reach_loc, int32_t* n_reach, \
-                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, \
+                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, double* flops, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
 // The one-cell-per-lane build (ab200_kernels_lane.cu): its own launcher signature (no work counter: one lane per cell,
@@ -46,7 +46,7 @@ struct EvolveBuild {
     int (*upload)(const void*, char*, int);
     int (*capacity)(char*, int);
     int (*launch)(cudaStream_t, int, int, const int32_t*, const double*, const void*, uint64_t*, int, const uint32_t*, int*, double*, int32_t*, int32_t*,
-                  double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, char*, int);
+                  double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, double*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
 static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2) };
@@ -89,7 +89,7 @@ struct ab200_ctx {
     std::string err;
     // device buffers
     DevBuf<int32_t> d_loc, d_nreach, d_nfin, d_status, d_steps, d_peak, d_rloc, d_floc;
-    DevBuf<double> d_box, d_reach, d_fin;
+    DevBuf<double> d_box, d_reach, d_fin, d_flops;
     DevBuf<uint64_t> d_arena, d_table, d_keys, d_tmp;
     DevBuf<unsigned> d_hist;
     DevBuf<unsigned long long> d_counters;
@@ -137,7 +137,7 @@ extern "C" void ab200_ctx_destroy(ab200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_loc.release(); ctx->d_nreach.release(); ctx->d_nfin.release(); ctx->d_status.release(); ctx->d_steps.release(); ctx->d_peak.release();
     ctx->d_rloc.release(); ctx->d_floc.release(); ctx->d_box.release(); ctx->d_reach.release(); ctx->d_fin.release();
-    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release();
+    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release(); ctx->d_flops.release();
     if (ctx->device >= 0 && ctx->device < 64 && g_sys_owner[ctx->device] == ctx) g_sys_owner[ctx->device] = 0;
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -274,7 +274,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             ctx->err = "time to live exceeded"; if (status) *status = stl; return AB200_E_TIMEOUT; }
         const int nb = (int)std::min<uint64_t>(S.batch_cells, n_cells - b0);
         CTX_CK(ctx->d_loc.ensure(nb)); CTX_CK(ctx->d_box.ensure((size_t)nb * stride));
-        CTX_CK(ctx->d_nreach.ensure(nb)); CTX_CK(ctx->d_nfin.ensure(nb)); CTX_CK(ctx->d_status.ensure(nb)); CTX_CK(ctx->d_steps.ensure(nb)); CTX_CK(ctx->d_peak.ensure(nb));
+        CTX_CK(ctx->d_flops.ensure(nb)); CTX_CK(ctx->d_nreach.ensure(nb)); CTX_CK(ctx->d_nfin.ensure(nb)); CTX_CK(ctx->d_status.ensure(nb)); CTX_CK(ctx->d_steps.ensure(nb)); CTX_CK(ctx->d_peak.ensure(nb));
         CTX_CK(ctx->d_reach.ensure((size_t)nb * S.max_boxes * stride)); CTX_CK(ctx->d_fin.ensure((size_t)nb * S.max_boxes * stride));
         CTX_CK(ctx->d_rloc.ensure((size_t)nb * S.max_boxes)); CTX_CK(ctx->d_floc.ensure((size_t)nb * S.max_boxes));
         // Build selection: set models have up to max(2n+1,3n) parameters -- one-word keys hold 7, two-word keys 15.
@@ -316,7 +316,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
                 CTX_CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream));
                 DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, ctx->d_binom.p, ctx->d_next.p,
                                      ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                     ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, eb_, sizeof(eb_)));
+                                     ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, ctx->d_flops.p, eb_, sizeof(eb_)));
             }
             stl.launches += 1;
             CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -336,7 +336,10 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(cudaMemcpyAsync(h_peak.data(), ctx->d_peak.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_nreach.data(), ctx->d_nreach.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaMemcpyAsync(h_nfin.data(), ctx->d_nfin.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<double> h_flops(stl.build == 2 ? 0 : nb);
+        if (!h_flops.empty()) CTX_CK(cudaMemcpyAsync(h_flops.data(), ctx->d_flops.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < h_flops.size(); ++i) stl.alg_flops += h_flops[i];
         evolve_ms += ms;
         if (dump_steps) { if (FILE* f = fopen(dump_steps, b0 == 0 ? "wb" : "ab")) { fwrite(h_steps.data(), sizeof(int32_t), (size_t)nb, f); fclose(f); } }
         for (int i = 0; i < nb; ++i) {
@@ -482,26 +485,28 @@ extern "C" int ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc,
     return AB200_OK;
 }
 
-extern "C" int ab200_probe_fp64(ab200_ctx* ctx, double* gflops) {
+static int probe_fp64(ab200_ctx* ctx, int fma, double* gflops) {
     if (!ctx || !gflops) return AB200_E_ARGUMENT;
     CTX_CK(cudaSetDevice(ctx->device));
     const int blocks = 148 * 8, threads = 256, iters = 20000;
     DevBuf<double> scratch;
     if (scratch.ensure((size_t)blocks * threads) != cudaSuccess) { ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
     char eb[256];
-    dev_fp64_peak(ctx->stream, scratch.p, blocks, threads, 100, eb, sizeof(eb));   // warm-up
+    dev_fp64_peak(ctx->stream, scratch.p, blocks, threads, 100, fma, eb, sizeof(eb));   // warm-up
     cudaStreamSynchronize(ctx->stream);
     cudaEventRecord(ctx->ev0, ctx->stream);
-    dev_fp64_peak(ctx->stream, scratch.p, blocks, threads, iters, eb, sizeof(eb));
+    dev_fp64_peak(ctx->stream, scratch.p, blocks, threads, iters, fma, eb, sizeof(eb));
     cudaEventRecord(ctx->ev1, ctx->stream);
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     scratch.release();
     if (es != cudaSuccess) { ctx->err = cudaGetErrorString(es); return AB200_E_CUDA; }
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    double ops = (double)blocks * threads * (double)iters * 16.0;   // 8 accumulators x (1 mul + 1 add), directed rounding
+    double ops = (double)blocks * threads * (double)iters * 16.0;   // 8 accumulators x (1 mul + 1 add), or 8 FMAs = 16 operations
     *gflops = ops / (ms * 1e-3) / 1e9;
     return AB200_OK;
 }
+extern "C" int ab200_probe_fp64(ab200_ctx* ctx, double* gflops) { return probe_fp64(ctx, 0, gflops); }
+extern "C" int ab200_probe_fp64_fma(ab200_ctx* ctx, double* gflops) { return probe_fp64(ctx, 1, gflops); }
 
 // the analyser entry points live in ab200_analyser.cu and use these two accessors
 const ab200::HostSystem* ab200_ctx_system(const ab200_ctx* ctx) { return ctx && ctx->have_system ? &ctx->sys : 0; }

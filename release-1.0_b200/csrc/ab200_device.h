@@ -14,7 +14,7 @@ int dev_evolve_capacity_v(char* errbuf, int errlen);
 int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params,
                         uint64_t* arena, int arena_words, const uint32_t* binom, int* next_cell,
                         double* reach, int32_t* reach_loc, int32_t* n_reach,
-                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak,
+                        double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, double* flops,
                         char* errbuf, int errlen);
 int dev_set_stack(size_t bytes, char* errbuf, int errlen);
 int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
@@ -26,5 +26,5 @@ int dev_launch_compact(cudaStream_t st, const uint64_t* table, size_t n, uint64_
 int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned* hist, int* result_in_tmp,
                    char* errbuf, int errlen);
 int dev_sort_tile();
-int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, char* errbuf, int errlen);
+int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, int fma, char* errbuf, int errlen);
 } }

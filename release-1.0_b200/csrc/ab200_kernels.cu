@@ -8,6 +8,7 @@
 //   K_compact / radix sort: unique keys -> sorted array, the form the host cell sets merge.
 // The op tapes of the system sit in __constant__ memory (SystemDesc), as every lane reads the same op at the same
 // time.
+#define AB_COUNT_FLOPS 1
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include "ab200_evolve.cuh"
@@ -23,7 +24,7 @@ __global__ void K_flow_bounds(int n_cells, const int32_t* cell_loc, const double
                               double* h_out, double* b_out, int32_t* status) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cells) return;
-    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = 0;
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = 0; c.sm_dirty = 0; c.flops = 0.0;
     const LocDesc& L = c_sys.loc[cell_loc[cell]];
     Ivl r[AB_MAXN], b[AB_MAXN];
     for (int i = 0; i < L.n; ++i) r[i] = ivl(cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i], cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i + 1]);
@@ -182,6 +183,18 @@ __global__ void K_fp64_peak(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// The same probe with fused multiply-adds (the nominal FP64 peak counts an FMA as two operations; the directed-rounding
+// arithmetic of this library cannot use FMAs -- every product and every sum is rounded separately).
+__global__ void K_fp64_peak_fma(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+    const double m = 1.0000001, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
+        a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 // ---- host-callable launchers ------------------------------------------------------------------------------------------
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(errbuf, errlen, "%s: %s", #x, cudaGetErrorString(e_)); return (int)e_; } } while (0)
 
@@ -233,8 +246,9 @@ int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int
     return 0;
 }
 int dev_sort_tile() { return AB_SORT_TILE; }
-int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, char* errbuf, int errlen) {
-    K_fp64_peak<<<blocks, threads, 0, st>>>(scratch, iters);
+int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, int fma, char* errbuf, int errlen) {
+    if (fma) K_fp64_peak_fma<<<blocks, threads, 0, st>>>(scratch, iters);
+    else K_fp64_peak<<<blocks, threads, 0, st>>>(scratch, iters);
     CK(cudaGetLastError());
     return 0;
 }

@@ -117,6 +117,7 @@ struct Ctx {
     uint64_t* sm;  // the warp's shared-memory staging area (AB_SM_WORDS words); null in host-side callers
     const uint32_t* binom;   // binomial table for monomial ranks (binom_fill)
     int sm_dirty;            // the hash accumulator has written over the dense accumulator's area since it was last emptied
+    double flops;            // algorithmic FP64 operations of the reference algorithm so far (AB_FLOPS)
 };
 #define AB_BINOM_N 64
 #define AB_BINOM_K 24
@@ -130,11 +131,11 @@ inline void binom_fill(uint32_t* t) {
 struct BinomTab { uint32_t t[AB_BINOM_N * AB_BINOM_K]; BinomTab() { binom_fill(t); } };
 inline const uint32_t* binom_host() { static BinomTab b; return b.t; }
 AB_HD void ctx_init(Ctx& c, uint64_t* arena, int limit, uint64_t* sm, const uint32_t* binom) {
-    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom; c.sm_dirty = 1;
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom; c.sm_dirty = 1; c.flops = 0.0;
 }
 // host-side callers (no warp, no shared area)
 inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
-    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1;
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1; c.flops = 0.0;
 }
 
 AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[i]; }
@@ -146,6 +147,11 @@ extern long long g_calls[16], g_words[16];   // development counters (tests/tool
 // the actual term counts (host development builds only; the figure bench.py quotes comes from these counters).
 extern double g_flops;
 #define AB_FLOPS(n) do { if (c.lane == 0) g_flops += (double)(n); } while (0)
+#elif defined(AB_COUNT_FLOPS)
+// Device builds: the same count kept per cell (warp-uniform, one FP64 add per primitive call) and returned with the lap's
+// status, so that the FP64 roofline of bench.py is measured on the run itself.
+#define AB_CALL(id, w)
+#define AB_FLOPS(n) do { c.flops += (double)(n); } while (0)
 #else
 #define AB_CALL(id, w)
 #define AB_FLOPS(n)
@@ -694,10 +700,11 @@ AB_HD int dacc_rank(const DAcc& A, const Key& k) {
     return r;
 }
 // one step of _add2 on entry r (src/taylor_model.cpp:505-512): see acc_fold
-AB_HD double dacc_fold(DAcc& A, int r, const Key& k, double tv) {
+AB_HD double dacc_fold(DAcc& A, int r, const Key& k, double tv, bool* coincident = 0) {
     const smaddr_t va = A.val + 8u * (uint32_t)r;
     A.touched |= 1u << (r >> 5);
     const uint64_t cb = sm_ld64(va);
+    if (coincident) *coincident = (cb != AB_ABSENT);
     if (cb == AB_ABSENT) {
         sm_st64(va, d2u(tv));
         dacc_put_key(A, r, k);
@@ -717,9 +724,12 @@ AB_HDN double dacc_add_model(Ctx& c, DAcc& A, const TM& t, bool gaps) {
     #pragma unroll 1
     for (int j0 = 0; j0 < n; j0 += W) {
         const int j = j0 + lane;
-        double g = 0.0;
-        if (j < n) { const Key k = bkey(base, t.off + j * AB_TW); g = dacc_fold(A, dacc_rank(A, k), k, bval(base, t.off + j * AB_TW)); }
+        double g = 0.0; bool co = false;
+        if (j < n) { const Key k = bkey(base, t.off + j * AB_TW); g = dacc_fold(A, dacc_rank(A, k), k, bval(base, t.off + j * AB_TW), &co); }
         if (gaps) { const unsigned gm = wballot(g != 0.0); if (gm) te = chain_ru_masked(te, g, gm); }
+#if defined(AB_COUNT_FLOPS) || defined(AB_MUL_HIST)
+        if (gaps) { const int cc_ = popc32(wballot(co)); AB_FLOPS(5 * cc_); }
+#endif
     }
     wsync();
     return te;
@@ -955,7 +965,7 @@ AB_HDN TM tm_mul_general_dense(Ctx& c, const TM& x, const TM& y, Acc acc, int D)
     int gs = yn + ((2 - (yn & 3)) & 3); if (gs < 2) gs = 2;      // row stride = 2 mod 4: conflict-free column reads
     int Bi = AB_SM_G16 / gs; if (Bi > W) Bi = W;
     wsync();
-    double re = 0.0; bool badgap = false;
+    double re = 0.0; bool badgap = false; int kept = 0;
     #pragma unroll 1
     for (int i0 = 0; i0 < xn; i0 += Bi) {
         const int nb = (xn - i0 < Bi) ? (xn - i0) : Bi;
@@ -985,7 +995,7 @@ AB_HDN TM tm_mul_general_dense(Ctx& c, const TM& x, const TM& y, Acc acc, int D)
             for (int j = 0; j < yn; ++j) {
                 const uint32_t code = sm_ld16(row + 2u * (uint32_t)j);
                 if (code & AB_G16_DISCARD) tte = add_ru(tte, mul_ru(axv, dabs(u2d(sm_ld64(yv + 8u * (uint32_t)j)))));
-                else if (code) te = add_ru(te, gap_value(code));
+                else { if (code) te = add_ru(te, gap_value(code)); ++kept; }
             }
         }
         wsync();
@@ -998,6 +1008,13 @@ AB_HDN TM tm_mul_general_dense(Ctx& c, const TM& x, const TM& y, Acc acc, int D)
     }
     if (wany(badgap)) fail(c, ST_UNSUPPORTED);
     r.n = dacc_emit(c, A, m);
+#if defined(AB_COUNT_FLOPS) || defined(AB_MUL_HIST)
+    {   // coincident products (5 operations each in _add2) = surviving products that did not open a new entry
+        #pragma unroll 1
+        for (int d = 1; d < W; d <<= 1) kept += wshfl(kept, lane ^ d);
+        if (kept > r.n) AB_FLOPS(5 * (kept - r.n));
+    }
+#endif
     double xs = 0, ys = 0;
     #pragma unroll 1
     for (int i0 = 0; i0 < xn; i0 += W) { const int i = i0 + lane; xs = chain_ru(xs, i < xn ? dabs(bval(base, xoff + i * AB_TW)) : 0.0, (xn - i0 < W) ? xn - i0 : W); }
