@@ -128,8 +128,10 @@ def run_ours(args):
     par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
     strong = args.scaling == "strong" and world > 1
     if strong:
-        # STRONG scaling: ONE frontier, dealt round-robin in blocks of 64 cells to the ranks.
-        mine = np.ascontiguousarray(all_cells[par.deal_blocks(all_cells.shape[0], rank, world, 64)])
+        # STRONG scaling: ONE frontier. Every rank passes all of it to the library, which deals blocks of 64 cells round-robin
+        # to the ranks, evolves its share and exchanges the sorted cell keys with ncclAllGather on the device.
+        ev.init_comm(dist)
+        mine = all_cells
     else:
         # WEAK scaling (the default; frontier cells are independent units): one configs[2] frontier per GPU. The global
         # frontier of an N-GPU run is N translates of it (shard r shifted by r/N of a cell width along x, so the shards are
@@ -164,7 +166,7 @@ def run_ours(args):
         r, e, st = lap()
         ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r); launches += st.launches
         flops += st.alg_flops; build = st.build
-        if world > 1:
+        if world > 1 and not strong:
             # newly reached cell ids are exchanged so that every rank holds the lap's reach set (NCCL all-gather)
             reach_n = int(par.exchange_keys(r.keys, dist, torch.device("cuda", local)).shape[0])
         last_r, last_e = r, e
@@ -173,7 +175,7 @@ def run_ours(args):
     sampler.stop_flag = True; sampler.join()
     wall = t1 - t0
     times = torch.tensor([wall, ev_ms, ra_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(n_mine), float(steps), float(keys)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_mine) / (world if strong else 1), float(steps), float(keys)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     wall, ev_ms, ra_ms = [float(x) for x in times.tolist()]

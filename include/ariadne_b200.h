@@ -168,6 +168,19 @@ int64_t ab200_analyser_cells_evolved(const ab200_analyser* an);
 int  ab200_analyser_enumerate(const ab200_analyser* an, const ab200_cellset* cs, int mince, uint64_t* count,
                               int32_t* locs, double* boxes);
 
+/* Multi-GPU laps (replaces the thread farm of UpperReachEvolveWorker, include/workers.h:102-153, across GPUs).
+ * One process per GPU, one context per process. Rank 0 obtains an id with ab200_comm_unique_id and hands the 128 bytes to
+ * the other ranks by whatever the host program uses (MPI, torch.distributed, a file); every rank then calls
+ * ab200_comm_init. From then on every lap of the context (ab200_upper_reach_evolve and the analyser calls built on it) is
+ * sharded: all ranks pass the same frontier, blocks of 64 cells are dealt round-robin, each rank evolves and rasterises its
+ * share, and the sorted cell keys are all-gathered with NCCL and merged on the device, so every rank receives the reach /
+ * evolve sets of the whole lap. A failing cell on any rank fails the lap on every rank. ab200_status counts this rank's
+ * share. NCCL (libnccl.so.2) is loaded on first use. */
+int  ab200_comm_unique_id(uint8_t* id128);
+int  ab200_comm_init(ab200_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id128);
+void ab200_comm_destroy(ab200_ctx* ctx);
+int  ab200_comm_info(const ab200_ctx* ctx, int32_t* n_ranks, int32_t* rank);
+
 /* Device probes used by bench.py for the roofline denominators. */
 int  ab200_probe_fp64(ab200_ctx* ctx, double* gflops_rounded_ops);      /* DMUL.RD + DADD.RU chains: what this library can issue */
 int  ab200_probe_fp64_fma(ab200_ctx* ctx, double* gflops_fma);          /* DFMA chains, 2 operations each: the nominal peak */

@@ -34,7 +34,7 @@ EXPORTS = [
     "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
-    "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma",
+    "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
 ]
 
 
@@ -113,6 +113,10 @@ def load_library():
     lib.ab200_analyser_enumerate.argtypes = [vp, vp, C.c_int, P(u64), P(i32), P(dbl)]; lib.ab200_analyser_enumerate.restype = C.c_int
     lib.ab200_probe_fp64.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64.restype = C.c_int
     lib.ab200_probe_fp64_fma.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64_fma.restype = C.c_int
+    lib.ab200_comm_unique_id.argtypes = [C.c_char_p]; lib.ab200_comm_unique_id.restype = C.c_int
+    lib.ab200_comm_init.argtypes = [vp, i32, i32, C.c_char_p]; lib.ab200_comm_init.restype = C.c_int
+    lib.ab200_comm_destroy.argtypes = [vp]; lib.ab200_comm_destroy.restype = None
+    lib.ab200_comm_info.argtypes = [vp, P(i32), P(i32)]; lib.ab200_comm_info.restype = C.c_int
     lib.ab200_system_check.argtypes = [C.c_char_p, P(i32), P(i32), P(i32), C.c_char_p, i32]; lib.ab200_system_check.restype = C.c_int
     _lib = lib
     return lib
@@ -180,6 +184,7 @@ class Evolver(object):
     def __init__(self, system_text, device=0, settings=None):
         self.lib = load_library()
         self.handle = C.c_void_p()
+        self.device = device
         rc = self.lib.ab200_ctx_create(C.byref(self.handle), device)
         if rc != 0:
             self.handle = None
@@ -266,6 +271,20 @@ class Evolver(object):
             for i in range(self.dims[0]):
                 out[k, 1 + i] = idx[i]
         return out
+
+    def init_comm(self, dist):
+        """Join the ranks of an initialised torch.distributed process group into the library's NCCL communicator: rank 0's
+        ncclUniqueId is broadcast as bytes; afterwards every lap of this evolver is sharded over the ranks."""
+        import torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            self._check(self.lib.ab200_comm_unique_id(buf))
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        self._check(self.lib.ab200_comm_init(self.handle, world, rank, raw))
 
     def probe_fp64(self, fma=False):
         """Measured FP64 rate in GFLOP/s: separately rounded multiply + add chains (what interval arithmetic can issue), or

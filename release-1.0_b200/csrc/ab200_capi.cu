@@ -7,6 +7,8 @@
 #include <chrono>
 #include <cstring>
 #include <cstdio>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "../../include/ariadne_b200.h"
 #include "ab200_device.h"
 #include "ab200_system.h"
@@ -96,10 +98,14 @@ struct ab200_ctx {
     DevBuf<uint32_t> d_binom;
     DevBuf<int> d_next;
     unsigned long long sys_generation;     // bumped by every change of the system description or tuning
+    // multi-GPU exchange (ab200_comm_init): one process per GPU, NCCL communicator over NVLink
+    ncclComm_t comm; int n_ranks, rank;
+    DevBuf<uint64_t> d_gather; DevBuf<unsigned long long> d_counts; DevBuf<unsigned> d_pos;
     cudaEvent_t ev0, ev1;
 };
 
 #define CTX_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return AB200_E_CUDA; } } while (0)
+extern "C" void ab200_comm_destroy(ab200_ctx* ctx);
 #define DEV_CK(x) do { char eb_[256]; eb_[0] = 0; int r_ = (x); if (r_ != 0) { ctx->err = eb_; return AB200_E_CUDA; } } while (0)
 
 extern "C" void ab200_default_settings(ab200_settings* s) {
@@ -118,7 +124,7 @@ extern "C" int ab200_ctx_create(ab200_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AB200_E_CUDA;
     if (prop.major != 10) return AB200_E_CUDA;    // kernels are built for sm_100a only
     ab200_ctx* ctx = new ab200_ctx();
-    ctx->device = device; ctx->have_system = false; ctx->have_layout = false; ctx->accuracy = 0; ctx->sys_generation = 0;
+    ctx->device = device; ctx->have_system = false; ctx->have_layout = false; ctx->accuracy = 0; ctx->sys_generation = 0; ctx->comm = 0; ctx->n_ranks = 1; ctx->rank = 0;
     ab200_default_settings(&ctx->settings);
     if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return AB200_E_CUDA; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
@@ -137,7 +143,8 @@ extern "C" void ab200_ctx_destroy(ab200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_loc.release(); ctx->d_nreach.release(); ctx->d_nfin.release(); ctx->d_status.release(); ctx->d_steps.release(); ctx->d_peak.release();
     ctx->d_rloc.release(); ctx->d_floc.release(); ctx->d_box.release(); ctx->d_reach.release(); ctx->d_fin.release();
-    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release(); ctx->d_flops.release();
+    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release(); ctx->d_flops.release(); ctx->d_gather.release(); ctx->d_counts.release(); ctx->d_pos.release();
+    ab200_comm_destroy(ctx);
     if (ctx->device >= 0 && ctx->device < 64 && g_sys_owner[ctx->device] == ctx) g_sys_owner[ctx->device] = 0;
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -232,6 +239,133 @@ extern "C" int ab200_key_decode(const ab200_ctx* ctx, uint64_t key, int32_t* loc
     key_unpack(ctx->K, key, &l, v);
     if (loc) *loc = l;
     if (idx) for (int i = 0; i < ctx->K.dim; ++i) idx[i] = v[i];
+    return AB200_OK;
+}
+
+// ---- NCCL, loaded on demand (a single-GPU user never needs it) ----------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* h;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+};
+NcclApi* nccl_api(std::string* err) {
+    static NcclApi api; static bool tried = false, ok = false;
+    if (!tried) {
+        tried = true;
+        api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) {
+            api.GetUniqueId = (ncclResult_t (*)(ncclUniqueId*))dlsym(api.h, "ncclGetUniqueId");
+            api.CommInitRank = (ncclResult_t (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(api.h, "ncclCommInitRank");
+            api.CommDestroy = (ncclResult_t (*)(ncclComm_t))dlsym(api.h, "ncclCommDestroy");
+            api.AllGather = (ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t))dlsym(api.h, "ncclAllGather");
+            api.GetErrorString = (const char* (*)(ncclResult_t))dlsym(api.h, "ncclGetErrorString");
+            ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+        }
+    }
+    if (!ok) { if (err) *err = "libnccl.so.2 could not be loaded"; return 0; }
+    return &api;
+}
+}
+#define NCCL_CK(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { ctx->err = std::string(#x) + ": " + nc->GetErrorString(r_); return AB200_E_CUDA; } } while (0)
+
+extern "C" int ab200_comm_unique_id(uint8_t* id128) {
+    if (!id128) return AB200_E_ARGUMENT;
+    NcclApi* nc = nccl_api(0);
+    if (!nc) return AB200_E_CUDA;
+    ncclUniqueId id;
+    if (nc->GetUniqueId(&id) != ncclSuccess) return AB200_E_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return AB200_OK;
+}
+extern "C" int ab200_comm_init(ab200_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id128) {
+    if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return AB200_E_ARGUMENT;
+    if (ctx->comm) return AB200_E_ARGUMENT;
+    NcclApi* nc = nccl_api(&ctx->err);
+    if (!nc) return AB200_E_CUDA;
+    CTX_CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    NCCL_CK(nc->CommInitRank(&ctx->comm, n_ranks, id, rank));
+    ctx->n_ranks = n_ranks; ctx->rank = rank;
+    return AB200_OK;
+}
+extern "C" void ab200_comm_destroy(ab200_ctx* ctx) {
+    if (!ctx || !ctx->comm) return;
+    if (NcclApi* nc = nccl_api(0)) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); nc->CommDestroy(ctx->comm); }
+    ctx->comm = 0; ctx->n_ranks = 1; ctx->rank = 0;
+}
+extern "C" int ab200_comm_info(const ab200_ctx* ctx, int32_t* n_ranks, int32_t* rank) {
+    if (!ctx) return AB200_E_ARGUMENT;
+    if (n_ranks) *n_ranks = ctx->n_ranks;
+    if (rank) *rank = ctx->rank;
+    return AB200_OK;
+}
+// Union over the ranks of this rank's sorted duplicate-free keys (device array `mine`, `cnt` keys): all-gather of the counts,
+// all-gather of the payloads padded to the largest count, radix sort of the concatenation and removal of duplicates, all on
+// the device; the union is copied to `dst`. Every rank must call it (it is a collective).
+static int exchange_keys(ab200_ctx* ctx, const uint64_t* mine, unsigned long long cnt, int total_bits, std::vector<uint64_t>* dst, ab200_status& stl) {
+    NcclApi* nc = nccl_api(&ctx->err);
+    if (!nc) return AB200_E_CUDA;
+    const int n = ctx->n_ranks;
+    CTX_CK(ctx->d_counts.ensure(2 * (size_t)n + 2));
+    CTX_CK(cudaMemcpyAsync(ctx->d_counts.p + n, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CK(nc->AllGather(ctx->d_counts.p + n, ctx->d_counts.p, 1, ncclUint64, ctx->comm, ctx->stream));
+    std::vector<unsigned long long> counts(n);
+    CTX_CK(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CTX_CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long mx = 0; for (int i = 0; i < n; ++i) if (counts[i] > mx) mx = counts[i];
+    if (mx == 0) { if (dst) dst->clear(); return AB200_OK; }
+    const size_t total = (size_t)mx * n;
+    CTX_CK(ctx->d_gather.ensure(2 * total + mx));            // [send | gathered | sort scratch shares d_tmp]
+    uint64_t* send = ctx->d_gather.p; uint64_t* all = ctx->d_gather.p + mx; uint64_t* out = all + total;
+    char eb[256]; eb[0] = 0;
+    if (dev_launch_fill(ctx->stream, send, mx, ~0ull, eb, sizeof(eb)) != 0) { ctx->err = eb; return AB200_E_CUDA; }
+    if (cnt) CTX_CK(cudaMemcpyAsync(send, mine, cnt * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    NCCL_CK(nc->AllGather(send, all, mx, ncclUint64, ctx->comm, ctx->stream));
+    // sort the concatenation (padding = all ones sorts last) and drop duplicates
+    CTX_CK(ctx->d_tmp.ensure(total));
+    size_t nblocks = (total + dev_sort_tile() - 1) / dev_sort_tile();
+    CTX_CK(ctx->d_hist.ensure(256 * nblocks));
+    int in_tmp = 0;
+    if (dev_radix_sort(ctx->stream, all, ctx->d_tmp.p, total, 64, ctx->d_hist.p, &in_tmp, eb, sizeof(eb)) != 0) { ctx->err = eb; return AB200_E_CUDA; }
+    (void)total_bits;
+    const uint64_t* sorted = in_tmp ? ctx->d_tmp.p : all;
+    CTX_CK(ctx->d_pos.ensure(total + 1));
+    if (dev_unique_sorted(ctx->stream, sorted, total, ctx->d_pos.p, out, eb, sizeof(eb)) != 0) { ctx->err = eb; return AB200_E_CUDA; }
+    stl.launches += 3 * 8 + 4;
+    unsigned last_pos = 0; uint64_t last_key = 0, prev_key = 0;
+    CTX_CK(cudaMemcpyAsync(&last_pos, ctx->d_pos.p + (total - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CTX_CK(cudaMemcpyAsync(&last_key, sorted + (total - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (total > 1) CTX_CK(cudaMemcpyAsync(&prev_key, sorted + (total - 2), sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CTX_CK(cudaStreamSynchronize(ctx->stream));
+    const bool last_kept = last_key != ~0ull && (total == 1 || last_key != prev_key);
+    const size_t uniq = (size_t)last_pos + (last_kept ? 1 : 0);
+    if (dst) {
+        dst->resize(uniq);
+        if (uniq) CTX_CK(cudaMemcpy(dst->data(), out, uniq * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    return AB200_OK;
+}
+// All ranks agree on the outcome of a sharded lap: the smallest non-zero code wins on every rank (first error wins, as in
+// include/workers.h:129-139, and no rank is left waiting in a collective).
+static int agree_on_status(ab200_ctx* ctx, int code, int* agreed) {
+    NcclApi* nc = nccl_api(&ctx->err);
+    if (!nc) return AB200_E_CUDA;
+    const int n = ctx->n_ranks;
+    CTX_CK(ctx->d_counts.ensure(2 * (size_t)n + 2));
+    unsigned long long c = (unsigned long long)code;
+    CTX_CK(cudaMemcpyAsync(ctx->d_counts.p + n, &c, sizeof(c), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CK(nc->AllGather(ctx->d_counts.p + n, ctx->d_counts.p, 1, ncclUint64, ctx->comm, ctx->stream));
+    std::vector<unsigned long long> codes(n);
+    CTX_CK(cudaMemcpyAsync(codes.data(), ctx->d_counts.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CTX_CK(cudaStreamSynchronize(ctx->stream));
+    *agreed = 0;
+    for (int i = 0; i < n; ++i) if (codes[i] != 0) { *agreed = (int)codes[i]; break; }
     return AB200_OK;
 }
 
@@ -386,8 +520,22 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         unsigned long long hc[8];
         CTX_CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
         stl.keys_emitted = (int64_t)(hc[2] + hc[5]);
-        if (hc[0] || hc[3]) { ctx->err = "cell de-duplication table full: raise ab200_settings.hash_log2"; if (status) *status = stl; return AB200_E_KEYSPACE; }
-        if (hc[1] || hc[4]) { ctx->err = "a reached cell lies outside the packed-key window"; if (status) *status = stl; return AB200_E_KEYSPACE; }
+        if (hc[0] || hc[3]) { ctx->err = "cell de-duplication table full: raise ab200_settings.hash_log2"; stl.evolve_ms = evolve_ms; stl.raster_ms = raster_ms; if (status) *status = stl; return AB200_E_KEYSPACE; }
+        if (hc[1] || hc[4]) { ctx->err = "a reached cell lies outside the packed-key window"; stl.evolve_ms = evolve_ms; stl.raster_ms = raster_ms; if (status) *status = stl; return AB200_E_KEYSPACE; }
+    }
+    stl.evolve_ms = evolve_ms; stl.raster_ms = raster_ms;
+    if (status) *status = stl;
+    return AB200_OK;
+}
+
+// Second half of a lap: the de-duplication tables of the two sets -> sorted key arrays (on the host; through the NCCL exchange
+// when the lap was sharded over ranks, so that every rank gets the union).
+static int lap_keys(ab200_ctx* ctx, LapOut& out, bool sharded, ab200_status* status) {
+    const ab200_settings& S = ctx->settings;
+    const size_t table_n = (size_t)1 << S.hash_log2;
+    ab200_status stl; if (status) stl = *status; else memset(&stl, 0, sizeof(stl));
+    float raster_ms = (float)stl.raster_ms;
+    {
         CTX_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         int total_bits = ctx->K.loc_bits; for (int i = 0; i < ctx->K.dim; ++i) total_bits += ctx->K.bits[i];
         for (int which = 0; which < 2; ++which) {
@@ -404,7 +552,10 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
                 CTX_CK(ctx->d_hist.ensure(256 * nblocks));
                 DEV_CK(dev_radix_sort(ctx->stream, ctx->d_keys.p, ctx->d_tmp.p, cnt, total_bits, ctx->d_hist.p, &in_tmp, eb_, sizeof(eb_))); stl.launches += 3 * ((total_bits + 7) / 8);
             }
-            if (dst) {
+            if (sharded) {
+                int rc_ = exchange_keys(ctx, in_tmp ? ctx->d_tmp.p : ctx->d_keys.p, cnt, total_bits, dst, stl);
+                if (rc_ != AB200_OK) return rc_;
+            } else if (dst) {
                 dst->resize(cnt);
                 if (cnt) CTX_CK(cudaMemcpyAsync(dst->data(), in_tmp ? ctx->d_tmp.p : ctx->d_keys.p, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
             }
@@ -414,9 +565,38 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         CTX_CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); raster_ms += ms;
     }
-    stl.evolve_ms = evolve_ms; stl.raster_ms = raster_ms;
+    stl.raster_ms = raster_ms;
     if (status) *status = stl;
     return AB200_OK;
+}
+
+// One lap. With a communicator (ab200_comm_init) every rank passes the SAME frontier; blocks of 64 cells are dealt round-robin
+// to the ranks, each rank evolves and rasterises its share, the ranks agree on the outcome, and the sorted keys
+// are exchanged on the device, so every rank returns the sets of the whole lap.
+static int run_lap(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T, int32_t max_events,
+                   int ignore_activations, int direction, LapOut& out, ab200_status* status) {
+    ab200_status stl; memset(&stl, 0, sizeof(stl)); stl.cell = -1;
+    const bool want_keys = out.reach_keys || out.fin_keys;
+    const bool sharded = ctx && ctx->comm && ctx->n_ranks > 1 && want_keys;
+    int rc;
+    if (!sharded) rc = run_batches(ctx, n_cells, loc, boxes, T, max_events, ignore_activations, direction, out, &stl);
+    else {
+        const int stride = AB200_BOX_STRIDE;
+        std::vector<int32_t> ml; std::vector<double> mb; std::vector<uint64_t> index;
+        for (uint64_t i = 0; i < n_cells; ++i) if ((int)((i / 64) % (uint64_t)ctx->n_ranks) == ctx->rank) {
+            ml.push_back(loc[i]); mb.insert(mb.end(), boxes + i * stride, boxes + (i + 1) * stride); index.push_back(i);
+        }
+        rc = run_batches(ctx, ml.size(), ml.data(), mb.data(), T, max_events, ignore_activations, direction, out, &stl);
+        if (stl.cell >= 0 && (size_t)stl.cell < index.size()) stl.cell = (int64_t)index[(size_t)stl.cell];
+        int agreed = 0;
+        int rc2 = agree_on_status(ctx, rc, &agreed);
+        if (rc2 != AB200_OK) { if (status) *status = stl; return rc2; }
+        if (agreed != 0 && rc == AB200_OK) ctx->err = "another rank failed its share of the lap";
+        rc = agreed;
+    }
+    if (rc == AB200_OK && want_keys) rc = lap_keys(ctx, out, sharded, &stl);
+    if (status) *status = stl;
+    return rc;
 }
 
 extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes,
@@ -426,7 +606,7 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
     *reach_out = 0; *evolve_out = 0;
     ab200_cellset* r = new ab200_cellset(); ab200_cellset* e = new ab200_cellset();
     LapOut out; out.reach_keys = &r->keys; out.fin_keys = &e->keys; out.reach_boxes = 0; out.fin_boxes = 0;
-    int rc = run_batches(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
+    int rc = run_lap(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
     if (rc != AB200_OK) { delete r; delete e; return rc; }
     *reach_out = r; *evolve_out = e;
     return AB200_OK;
@@ -446,7 +626,7 @@ extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const 
     *reach_out = 0; *final_out = 0;
     ab200_boxlist* r = new ab200_boxlist(); ab200_boxlist* f = new ab200_boxlist();
     LapOut out; out.reach_keys = 0; out.fin_keys = 0; out.reach_boxes = r; out.fin_boxes = f;
-    int rc = run_batches(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
+    int rc = run_lap(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
     if (rc != AB200_OK) { delete r; delete f; return rc; }
     *reach_out = r; *final_out = f;
     return AB200_OK;

@@ -26,5 +26,6 @@ int dev_launch_compact(cudaStream_t st, const uint64_t* table, size_t n, uint64_
 int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned* hist, int* result_in_tmp,
                    char* errbuf, int errlen);
 int dev_sort_tile();
+int dev_unique_sorted(cudaStream_t st, const uint64_t* in, size_t n, unsigned* pos, uint64_t* out, char* errbuf, int errlen);
 int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, int fma, char* errbuf, int errlen);
 } }

@@ -172,6 +172,18 @@ __global__ void K_sort_scatter(const uint64_t* __restrict__ in, uint64_t* __rest
     }
 }
 
+// ---- merge of gathered key arrays (multi-GPU exchange): flag the first occurrence of every key of a sorted array, scan, scatter
+__global__ void K_unique_flag(const uint64_t* __restrict__ in, size_t n, unsigned* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stridex = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stridex) flag[i] = (in[i] != AB_EMPTY_KEY && (i == 0 || in[i] != in[i - 1])) ? 1u : 0u;
+}
+__global__ void K_unique_scatter(const uint64_t* __restrict__ in, size_t n, const unsigned* __restrict__ pos, uint64_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stridex = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stridex) if (in[i] != AB_EMPTY_KEY && (i == 0 || in[i] != in[i - 1])) out[pos[i]] = in[i];
+}
+
 // ---- FP64 pipe peak probe (reported beside the roofline) -------------------------------------------------
 __global__ void K_fp64_peak(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
@@ -246,6 +258,16 @@ int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int
     return 0;
 }
 int dev_sort_tile() { return AB_SORT_TILE; }
+// Sorted `in` (n keys, AB_EMPTY_KEY padding allowed) -> duplicate-free `out`; pos: n+1 unsigned of scratch. The number of keys
+// kept is pos[n-1] + (flag of the last key), read back by the caller from pos_last / flag_last.
+int dev_unique_sorted(cudaStream_t st, const uint64_t* in, size_t n, unsigned* pos, uint64_t* out, char* errbuf, int errlen) {
+    if (n == 0) return 0;
+    K_unique_flag<<<148 * 4, 256, 0, st>>>(in, n, pos);
+    K_sort_scan<<<1, 1024, 0, st>>>(pos, n);
+    K_unique_scatter<<<148 * 4, 256, 0, st>>>(in, n, pos, out);
+    CK(cudaGetLastError());
+    return 0;
+}
 int dev_fp64_peak(cudaStream_t st, double* scratch, int blocks, int threads, int iters, int fma, char* errbuf, int errlen) {
     if (fma) K_fp64_peak_fma<<<blocks, threads, 0, st>>>(scratch, iters);
     else K_fp64_peak<<<blocks, threads, 0, st>>>(scratch, iters);
