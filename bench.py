@@ -139,6 +139,7 @@ def run_ours(args):
         mine = all_cells.copy()
         mine[:, 0:2] += (float(rank) / world) * (all_cells[0, 1] - all_cells[0, 0])
     n_mine = mine.shape[0]
+    n_share = (n_mine + world - 1) // world if strong else n_mine          # cells this GPU evolves per lap
     boxes = pkg.pack_boxes(mine, 2)
     locs = np.zeros((n_mine,), dtype=np.int32)
     T = an.lock_to_grid_time * args.lap_scale
@@ -209,7 +210,7 @@ def run_ours(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "K_evolve_traffic.json")))
-        if tj.get("frontier_cells_per_gpu") == int(n_mine) and tj.get("build") == int(build) and args.lap_scale == 1.0:
+        if tj.get("frontier_cells_per_gpu") == int(n_share) and tj.get("build") == int(build) and args.lap_scale == 1.0:
             traffic = tj.get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -218,11 +219,11 @@ def run_ours(args):
         "metric": METRIC, "value": dev_value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %d frontier cells per GPU (configs[2])" % (ACC, int(n_mine)),
-                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "frontier_cells_per_gpu": int(n_mine), "lap_time": T,
+        "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %s (configs[2])" % (ACC, ("ONE frontier of %d cells dealt to %d GPUs" % (int(n_mine), world)) if strong else ("%d frontier cells per GPU" % int(n_mine))),
+                   "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "frontier_cells_per_gpu": int(n_share), "lap_time": T,
                    "evolution_build": build_name,
                    "l2_policy": "every lap rewrites its scratch arenas and box lists (GBs, far beyond L2); no flush needed"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_mine * (80 + 4)), "d2h_bytes_per_step": int(8 * (reach_n + 0) + 24 * n_mine)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_share * (80 + 4)), "d2h_bytes_per_step": int(8 * (reach_n + 0) + 24 * n_share)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "fp64", "achieved": alg_gflops, "peak": fp64, "unit": "GFLOP/s", "frac": (alg_gflops / fp64) if fp64 else None,

@@ -30,6 +30,7 @@
 #include "watertank-hysteresis.h"
 #include "springs.h"
 #include "boost-converter.h"
+#include "workers_b200.h"
 
 using namespace Ariadne;
 
@@ -139,102 +140,8 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
     return c;
 }
 
-// ---- system -> op-tape text (release-1.0_b200/csrc/ab200_system.h) through the public expression API ----
-static void emit_tape(FILE* f, const RealExpression& e, const std::map<std::string,int>& var_index) {
-    Operator op=e.op();
-    if(op==VAR) {
-        std::stringstream ss; ss<<e; std::string name=ss.str();
-        std::map<std::string,int>::const_iterator it=var_index.find(name);
-        if(it==var_index.end()) { fprintf(stderr,"unknown variable '%s'\n",name.c_str()); exit(3); }
-        fprintf(f," V%d",it->second); return;
-    }
-    if(op==CNST || op==PAR) {
-        Interval v=evaluate(e,Vector<Interval>(1));
-        fprintf(f," C%a,%a",v.lower(),v.upper()); return;
-    }
-    List<RealExpression> sub=e.subexpressions();
-    for(uint i=0;i<sub.size();++i) emit_tape(f,sub[i],var_index);
-    const char* name=0;
-    switch(op) {
-        case ADD: name="ADD"; break; case SUB: name="SUB"; break; case MUL: name="MUL"; break; case DIV: name="DIV"; break;
-        case NEG: name="NEG"; break; case POS: name="POS"; break; case REC: name="REC"; break; case SQR: name="SQR"; break;
-        case SQRT: name="SQRT"; break; case EXP: name="EXP"; break; case LOG: name="LOG"; break; case SIN: name="SIN"; break;
-        case COS: name="COS"; break; case TAN: name="TAN"; break; case ABS: name="ABS"; break; case MAX: name="MAX"; break; case MIN: name="MIN"; break;
-        default: fprintf(stderr,"unsupported operator %d\n",int(op)); exit(3);
-    }
-    fprintf(f," %s",name);
-}
-
-static void dump_system(FILE* f, const HybridIOAutomaton& sys) {
-    HybridSpace space=sys.state_space();
-    std::map<std::string,int> loc_index; int L=0;
-    for(HybridSpace::const_iterator it=space.begin(); it!=space.end(); ++it) loc_index[it->first.name()]=L++;
-    fprintf(f,"system %s\nlocations %d\n",sys.name().c_str(),L);
-    for(HybridSpace::const_iterator it=space.begin(); it!=space.end(); ++it) {
-        DiscreteLocation loc=it->first;
-        RealSpace cs=sys.continuous_state_space(loc);
-        std::map<std::string,int> var_index;
-        for(uint i=0;i<cs.size();++i) var_index[cs.variable(i).name()]=i;
-        Set<DiscreteEvent> events=sys.events(loc);
-        fprintf(f,"location %d %s n %u events %lu\n",loc_index[loc.name()],loc.name().c_str(),(unsigned)cs.size(),(unsigned long)events.size());
-        for(std::list<DiscreteIOMode>::const_iterator m=sys.modes().begin(); m!=sys.modes().end(); ++m) {
-            if(!(m->location()==loc)) continue;
-            uint i=0;
-            for(std::map<RealVariable,RealExpression>::const_iterator d=m->dynamics().begin(); d!=m->dynamics().end(); ++d,++i) {
-                fprintf(f,"  dyn %u",i); emit_tape(f,d->second,var_index); fprintf(f," ;\n"); }
-        }
-        int k=0;
-        for(Set<DiscreteEvent>::const_iterator e=events.begin(); e!=events.end(); ++e,++k) {
-            EventKind kind=sys.event_kind(loc,*e);
-            const char* kn = kind==INVARIANT?"invariant":kind==URGENT?"urgent":"permissive";
-            int target = kind==INVARIANT ? loc_index[loc.name()] : loc_index[sys.target(loc,*e).name()];
-            fprintf(f,"  event %d %s kind %s target %d id %d\n",k,e->name().c_str(),kn,target,k);
-            if(kind==INVARIANT) {
-                for(std::list<DiscreteIOMode>::const_iterator m=sys.modes().begin(); m!=sys.modes().end(); ++m) {
-                    if(!(m->location()==loc)) continue;
-                    std::map<DiscreteEvent,RealExpression>::const_iterator inv=m->invariants().find(*e);
-                    fprintf(f,"    guard"); emit_tape(f,inv->second,var_index); fprintf(f," ;\n");
-                    // lie derivative of the invariant function: used by the lower-semantics discard test
-                    // (has_nonnegative_crossing, src/hybrid_evolver-image.cpp:612-632)
-                    std::map<RealVariable,RealExpression>::const_iterator d=m->dynamics().begin();
-                    try {
-                        RealExpression lie=derivative(inv->second,cs.variable(0))*d->second; ++d;
-                        for(uint i=1;i<cs.size();++i,++d) lie=lie+derivative(inv->second,cs.variable(i))*d->second;
-                        fprintf(f,"    lie"); emit_tape(f,lie,var_index); fprintf(f," ;\n");
-                    } catch(std::exception& ex) {
-                        fprintf(f,"    # lie derivative not computable in the reference: %s\n","derivative() throws");
-                    }
-                }
-            } else {
-                for(std::list<DiscreteIOTransition>::const_iterator t=sys.transitions().begin(); t!=sys.transitions().end(); ++t) {
-                    if(!(t->source()==loc && t->event()==*e)) continue;
-                    fprintf(f,"    guard"); emit_tape(f,t->activation(),var_index); fprintf(f," ;\n");
-                    {
-                        // lie_derivative(activation,dynamic) as ScalarFunction arithmetic builds it (src/function.cpp:1308-1331,
-                        // :863-909): r=dg/dx0*f0; r=r+dg/dxi*fi, with Ariadne::derivative on the expressions
-                        // (src/function.cpp:118). Used by the grid-side jump test (src/set_checker.cpp:148-161).
-                        const std::map<RealVariable,RealExpression>* dyn=0;
-                        for(std::list<DiscreteIOMode>::const_iterator m=sys.modes().begin(); m!=sys.modes().end(); ++m) if(m->location()==loc) dyn=&m->dynamics();
-                        std::map<RealVariable,RealExpression>::const_iterator d=dyn->begin();
-                        try {
-                            RealExpression lie=derivative(t->activation(),cs.variable(0))*d->second; ++d;
-                            for(uint i=1;i<cs.size();++i,++d) lie=lie+derivative(t->activation(),cs.variable(i))*d->second;
-                            fprintf(f,"    lie"); emit_tape(f,lie,var_index); fprintf(f," ;\n");
-                        } catch(std::exception& ex) {
-                            // the reference itself cannot differentiate this guard (e.g. min(-iL,iL)): its grid-side jump
-                            // test would fail with "Failed to compute Lie derivative" (src/function.cpp:1329)
-                            fprintf(f,"    # lie derivative not computable in the reference: %s\n","derivative() throws");
-                        }
-                    }
-                    uint i=0;
-                    for(std::map<RealVariable,RealExpression>::const_iterator r=t->reset().begin(); r!=t->reset().end(); ++r,++i) {
-                        fprintf(f,"    reset %u",i); emit_tape(f,r->second,var_index); fprintf(f," ;\n"); }
-                    break;
-                }
-            }
-        }
-    }
-}
+// ---- system -> op-tape text: adapter/workers_b200.cpp (b200_system_text), the same walker the adapter ships ----
+static void dump_system(FILE* f, const HybridIOAutomaton& sys) { std::string t=b200_system_text(sys); fputs(t.c_str(),f); }
 
 static void dump_box(FILE* f, const Box& b) { for(uint i=0;i<b.size();++i) fprintf(f," %a %a",b[i].lower(),b[i].upper()); }
 

@@ -316,3 +316,33 @@ def test_lane_build_matches_warp_build(pkg, monkeypatch):
             ev.upper_reach_evolve(np.array(locs, dtype=np.int32), boxes, T, events)
     finally:
         ev.close()
+
+
+ADAPTER_CASES = [
+    ("vanderpol", "vanderpol_reach_acc4.txt", ["acc=4", "init=-1.6,-1.3,0.3,0.8", "laps=1"]),
+    ("vanderpol", "vanderpol_reach_acc3.txt", ["acc=3", "init=1.0,1.3,1.0,1.6", "laps=2"]),
+    ("bouncingball", "bouncingball_chain_acc5.txt", ["acc=5"]),
+    ("watertank", "watertank_reach_acc3.txt", ["acc=3", "T=0.5", "initr=1.0,1.0,7.6,7.7", "initf=0.0,0.0,5.7,5.8"]),
+    ("boost", "boost_reach_acc4.txt", ["acc=4", "chain=0", "T=0.011"]),
+]
+
+
+@pytest.mark.parametrize("config,golden,args", ADAPTER_CASES)
+def test_reference_analyser_with_b200_worker(tmp_path, config, golden, args):
+    """The drop-in boundary, compiled: the REFERENCE's own HybridReachabilityAnalyser (unmodified sources, oracle/_ref) with
+    adapter/workers_b200 swapped in where src/reachability_analyser.cpp:192-198 builds its UpperReachEvolveWorker. Every lap
+    goes through ab200_upper_reach_evolve; everything else (grid, lock time, restriction, jump sets, BDD set algebra) is the
+    reference's. Its result must be the stock run's (the committed golden) cell for cell."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(golden_io.GOLDEN), "..", "oracle", "_ref", "ref_harness_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_harness_b200 has not been built (make -C oracle adapter)")
+    out = str(tmp_path / "b200.txt")
+    subprocess.check_call([exe, config, "reach", "out=" + out] + args, timeout=600)
+    mine = golden_io.load_dump(out)
+    ref = golden_io.load_dump(golden)
+    assert mine["config"]["lock"] == ref["config"]["lock"]
+    for which in ("reach", "evolve"):
+        assert set(mine["sets"][which].keys()) == set(ref["sets"][which].keys())
+        for lname, cells in ref["sets"][which].items():
+            assert golden_io.boxes_equal_bits(np.array(mine["sets"][which][lname]), cells), "%s cells of %s in %s" % (which, config, lname)
