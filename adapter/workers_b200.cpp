@@ -123,6 +123,12 @@ B200Context& b200_context(const HybridIOAutomaton& sys) {
     if(!c.ctx) {
         int device=0; if(const char* d=getenv("AB200_DEVICE")) device=atoi(d);
         if(ab200_ctx_create(&c.ctx,device)!=AB200_OK) throw std::runtime_error("ab200_ctx_create: no usable sm_100 GPU");
+        // device sizing: generous per-cell scratch and box lists (overridable: AB200_ARENA_WORDS, AB200_MAX_BOXES)
+        ab200_settings st; ab200_default_settings(&st);
+        st.arena_words=262144; st.max_boxes=512;
+        if(const char* e=getenv("AB200_ARENA_WORDS")) st.arena_words=atoi(e);
+        if(const char* e=getenv("AB200_MAX_BOXES")) st.max_boxes=atoi(e);
+        if(ab200_set_settings(c.ctx,&st)!=AB200_OK) throw std::runtime_error(std::string("ab200_set_settings: ")+ab200_last_error(c.ctx));
         std::string text=b200_system_text(sys);
         if(ab200_set_system_text(c.ctx,text.c_str())!=AB200_OK) throw std::runtime_error(std::string("ab200_set_system_text: ")+ab200_last_error(c.ctx));
         c.system_name=sys.name();
