@@ -132,6 +132,21 @@ void ab200_boxlist_free(ab200_boxlist* bl);
 int  ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
                        double* h_out, double* bounds_out, int32_t* status_out);
 
+/* == IntegratorBase::flow_bounds (src/integrator.cpp:44-113): the integrator's own constants (8 step halvings, 4 refinements,
+ * no widening of singleton coordinates); this is what IntegratorInterface::flow_bounds of a TaylorIntegrator computes. */
+int  ab200_integrator_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
+                                  double* h_out, double* bounds_out, int32_t* status_out);
+/* == TaylorIntegrator(temporal_order)::flow(vector_field, state_domain, suggested_time_step)
+ * (include/integrator.h:56-68, src/integrator.cpp:116-152) for the dynamics of location `loc`: the VectorTaylorFunction of
+ * the flow over domain = box x [-h,h] (written to domain_out, 2*(n+1) doubles), returned as one polynomial model per state
+ * variable in n+1 scaled arguments (exponent bytes per term, coefficient, uniform error). */
+typedef struct ab200_taylor_models ab200_taylor_models;
+int  ab200_integrator_flow(ab200_ctx* ctx, int32_t loc, const double* box, double hmax, int32_t temporal_order,
+                           double* h_out, double* domain_out, ab200_taylor_models** out);
+int  ab200_taylor_models_view(const ab200_taylor_models* m, int32_t i, int32_t* nargs, int32_t* n_terms, double* error,
+                              const uint8_t** exponents /* [n_terms][nargs] */, const double** coefficients);
+void ab200_taylor_models_free(ab200_taylor_models* m);
+
 /* Host mirror of HybridReachabilityAnalyser (include/reachability_analyser.h:122-172): grid, lock-to-grid time and
  * evolver tuning derived from the domain exactly as HybridReachabilityAnalyser(system,domain,accuracy) does
  * (src/reachability_analyser.cpp:83-100,1028-1170; src/hybrid_set.cpp:485-515), laps driven through

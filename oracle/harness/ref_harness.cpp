@@ -25,6 +25,8 @@
 #include "taylor_calculus.h"
 #include "hybrid_evolver-image.h"
 #include "logging.h"
+#include "integrator.h"
+#include "taylor_function.h"
 #include <boost/thread.hpp>
 #include "workers.h"
 #include "watertank-hysteresis.h"
@@ -84,6 +86,20 @@ static HybridIOAutomaton make_bouncingball() {
     return ball;
 }
 
+// the vector field of test/test_integrator.cpp:73-157: x'=2, y'=3
+static HybridIOAutomaton make_constder() {
+    HybridIOAutomaton a("constder");
+    DiscreteLocation loc("loc");
+    RealVariable x("x"), y("y");
+    a.add_internal_var(x); a.add_internal_var(y);
+    a.new_mode(loc);
+    RealExpression dx = 2.0;
+    RealExpression dy = 3.0;
+    a.set_dynamics(loc,x,dx);
+    a.set_dynamics(loc,y,dy);
+    return a;
+}
+
 static std::map<std::string,std::string> parse_kv(int argc, char** argv, int first) {
     std::map<std::string,std::string> kv;
     for(int i=first;i<argc;++i) { std::string s(argv[i]); size_t p=s.find('='); if(p!=std::string::npos) kv[s.substr(0,p)]=s.substr(p+1); }
@@ -107,6 +123,12 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
         c.initial=HybridBoundedConstraintSet(c.sys.state_space());
         c.initial[DiscreteLocation("loc")]=box_from(kv,"init",Box(2,-2.2,2.2,-2.8,2.8));
         c.acc=geti(kv,"acc",6); c.T=getd(kv,"T",0.0);
+    } else if(name=="constder") {
+        c.sys=make_constder();
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,-1.0,5.0,-1.0,6.0)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("loc")]=box_from(kv,"init",Box(2,0.0,1.0,-0.5,1.5));
+        c.acc=geti(kv,"acc",3); c.T=getd(kv,"T",0.0);
     } else if(name=="bouncingball") {
         c.sys=make_bouncingball();
         // state order is alphabetical: (vx,x)
@@ -164,6 +186,28 @@ int main(int argc, char** argv) {
     int verb=geti(kv,"verb",0);
 
     if(mode=="system") { dump_system(out,c.sys); return 0; }
+    if(mode=="integrator") {
+        // IntegratorInterface::flow_bounds / flow of the reference's TaylorIntegrator (src/integrator.cpp:44-152) on the dynamics
+        // of one location: the golden vectors of the B4 facade (ab200_integrator_flow_bounds, ab200_integrator_flow)
+        DiscreteLocation loc(kv.count("loc")?kv["loc"]:c.sys.modes().front().location().name());
+        VectorFunction vf=c.sys.dynamic_function(loc);
+        Box bx=box_from(kv,"box",Box(2,0.0,1.0,-0.5,1.5));
+        double hmax=getd(kv,"h",1.0); int order=geti(kv,"order",4);
+        TaylorIntegrator integrator(order);
+        Pair<Float,Vector<Interval> > fb=integrator.flow_bounds(vf,bx,hmax);
+        fprintf(out,"integrator loc %s order %d hmax %a box",loc.name().c_str(),order,hmax); dump_box(out,bx); fprintf(out,"\n");
+        fprintf(out,"bounds h %a b",fb.first); dump_box(out,Box(fb.second)); fprintf(out,"\n");
+        VectorTaylorFunction phi=integrator.flow(vf,bx,hmax);
+        fprintf(out,"domain"); dump_box(out,Box(phi.domain())); fprintf(out,"\n");
+        for(uint i=0;i<phi.result_size();++i) {
+            const TaylorModel& m=phi.models()[i];
+            fprintf(out,"model %u terms %u error %a\n",i,(unsigned)m.number_of_nonzeros(),m.error());
+            for(TaylorModel::const_iterator it=m.begin(); it!=m.end(); ++it) {
+                fprintf(out,"t"); for(uint j=0;j<m.argument_size();++j) fprintf(out," %u",(unsigned)it->key()[j]); fprintf(out," %a\n",it->data());
+            }
+        }
+        return 0;
+    }
 
     HybridReachabilityAnalyser analyser(c.sys,c.domain,c.acc);
     analyser.verbosity=verb;

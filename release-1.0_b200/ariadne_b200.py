@@ -35,6 +35,7 @@ EXPORTS = [
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
     "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
+    "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free",
 ]
 
 
@@ -113,6 +114,10 @@ def load_library():
     lib.ab200_analyser_enumerate.argtypes = [vp, vp, C.c_int, P(u64), P(i32), P(dbl)]; lib.ab200_analyser_enumerate.restype = C.c_int
     lib.ab200_probe_fp64.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64.restype = C.c_int
     lib.ab200_probe_fp64_fma.argtypes = [vp, P(dbl)]; lib.ab200_probe_fp64_fma.restype = C.c_int
+    lib.ab200_integrator_flow_bounds.argtypes = [vp, u64, P(i32), P(dbl), dbl, P(dbl), P(dbl), P(i32)]; lib.ab200_integrator_flow_bounds.restype = C.c_int
+    lib.ab200_integrator_flow.argtypes = [vp, i32, P(dbl), dbl, i32, P(dbl), P(dbl), P(vp)]; lib.ab200_integrator_flow.restype = C.c_int
+    lib.ab200_taylor_models_view.argtypes = [vp, i32, P(i32), P(i32), P(dbl), P(P(C.c_uint8)), P(P(dbl))]; lib.ab200_taylor_models_view.restype = C.c_int
+    lib.ab200_taylor_models_free.argtypes = [vp]; lib.ab200_taylor_models_free.restype = None
     lib.ab200_comm_unique_id.argtypes = [C.c_char_p]; lib.ab200_comm_unique_id.restype = C.c_int
     lib.ab200_comm_init.argtypes = [vp, i32, i32, C.c_char_p]; lib.ab200_comm_init.restype = C.c_int
     lib.ab200_comm_destroy.argtypes = [vp]; lib.ab200_comm_destroy.restype = None
@@ -271,6 +276,38 @@ class Evolver(object):
             for i in range(self.dims[0]):
                 out[k, 1 + i] = idx[i]
         return out
+
+    def integrator_flow_bounds(self, loc, box, hmax):
+        """IntegratorBase::flow_bounds(vf, box, hmax) -> (h, bounding box) for the dynamics of a location."""
+        n = self.dims[loc]
+        b = pack_boxes([box], n)
+        h = np.zeros((1,), dtype=np.float64); out = np.zeros((1, 2 * MAX_DIM), dtype=np.float64); st = np.zeros((1,), dtype=np.int32)
+        locs = np.array([loc], dtype=np.int32)
+        self._check(self.lib.ab200_integrator_flow_bounds(self.handle, 1, locs.ctypes.data_as(C.POINTER(C.c_int32)), b.ctypes.data_as(C.POINTER(C.c_double)), hmax,
+                                                          h.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_int32))))
+        if st[0] != 0:
+            raise Ab200Error(int(st[0]), "flow_bounds")
+        return float(h[0]), out[0, :2 * n].copy()
+
+    def integrator_flow(self, loc, box, hmax, temporal_order):
+        """TaylorIntegrator(temporal_order).flow(vf, box, hmax) -> (h, domain, [(exponents[n_terms][n+1], coefficients, error)] per
+        state variable)."""
+        n = self.dims[loc]
+        b = np.ascontiguousarray(np.asarray(box, dtype=np.float64))
+        h = C.c_double(0); dom = np.zeros((2 * (n + 1),), dtype=np.float64); m = C.c_void_p()
+        self._check(self.lib.ab200_integrator_flow(self.handle, loc, b.ctypes.data_as(C.POINTER(C.c_double)), hmax, temporal_order, C.byref(h),
+                                                   dom.ctypes.data_as(C.POINTER(C.c_double)), C.byref(m)))
+        models = []
+        try:
+            for i in range(n):
+                na = C.c_int32(0); nt = C.c_int32(0); err = C.c_double(0); ex = C.POINTER(C.c_uint8)(); cf = C.POINTER(C.c_double)()
+                self.lib.ab200_taylor_models_view(m, i, C.byref(na), C.byref(nt), C.byref(err), C.byref(ex), C.byref(cf))
+                e = np.ctypeslib.as_array(ex, shape=(nt.value, na.value)).copy() if nt.value else np.zeros((0, na.value), dtype=np.uint8)
+                v = np.ctypeslib.as_array(cf, shape=(nt.value,)).copy() if nt.value else np.zeros((0,), dtype=np.float64)
+                models.append((e, v, err.value))
+        finally:
+            self.lib.ab200_taylor_models_free(m)
+        return h.value, dom, models
 
     def init_comm(self, dist):
         """Join the ranks of an initialised torch.distributed process group into the library's NCCL communicator: rank 0's

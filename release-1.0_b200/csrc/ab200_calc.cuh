@@ -188,13 +188,15 @@ AB_HDN TM eval_tm(Ctx& c, const TapeOp* ops, Func f, const TM* x) {
 // ---- flow bounder -------------------------------------------------------------------------------------------------
 // Ariadne::flow_bounds (src/taylor_calculus.cpp:55-133) preceded by the singleton widening of
 // TaylorCalculus::flow_bounds (:584-600). Returns h; writes the bounding box to b[].
-AB_HDN double flow_bounds(Ctx& c, const TapeOp* ops, const Func* vf, int n, const Ivl* r, double hmax, Ivl* bout) {
+// `integrator` selects IntegratorBase::flow_bounds (src/integrator.cpp:44-113): the same search with REDUCTION_STEPS 8,
+// REFINEMENT_STEPS 4 and no widening of singleton coordinates.
+AB_HDN double flow_bounds(Ctx& c, const TapeOp* ops, const Func* vf, int n, const Ivl* r, double hmax, Ivl* bout, bool integrator = false) {
     const double INITIAL_MULTIPLIER = 2, MULTIPLIER = 1.125, BOX_RADIUS_MULTIPLIER = 1.03125;
-    const int EXPANSION_STEPS = 8, REDUCTION_STEPS = 16, REFINEMENT_STEPS = 8;
+    const int EXPANSION_STEPS = 8, REDUCTION_STEPS = integrator ? 8 : 16, REFINEMENT_STEPS = integrator ? 4 : 8;
     const double EPS = 1e-16;
     Ivl d[AB_MAXN], delta[AB_MAXN], b[AB_MAXN], nb[AB_MAXN], df[AB_MAXN], dd[AB_MAXN];
     #pragma unroll 1
-    for (int i = 0; i < n; ++i) { d[i] = r[i]; if (d[i].l == d[i].u) d[i] = ivl_add(d[i], ivl(-EPS, EPS)); }
+    for (int i = 0; i < n; ++i) { d[i] = r[i]; if (!integrator && d[i].l == d[i].u) d[i] = ivl_add(d[i], ivl(-EPS, EPS)); }
     #pragma unroll 1
     for (int i = 0; i < n; ++i) delta[i] = ivl_mul(ivl_sub(d[i], ivl_mid(d[i])), BOX_RADIUS_MULTIPLIER - 1);
     #pragma unroll 1
@@ -1076,6 +1078,39 @@ AB_HDN int kuhn_recondition(Ctx& c, TM* set, int n, int p, int* discarded) {
     #pragma unroll 1
     for (int i = 0; i < n; ++i) set[i] = out[i];
     return nd;
+}
+
+// TaylorIntegrator::flow (src/integrator.cpp:116-152): flow_bounds, then `order` Picard iterations on function level over the
+// domain dx x [-h,h]: phi <- antiderivative(compose(f,phi), time) + phi0 with phi0 = the coordinate functions and phi
+// starting from the constant bounding box. No intersection with the previous iterate, no sweep beyond the models' own
+// (default) accuracy. Writes the n models (n+1 variables) packed at the arena top recorded on entry; returns h.
+AB_HDN double integrator_flow(Ctx& c, const TapeOp* ops, const Func* vf, int n, const Ivl* dx, double hmax, int order, TM* phi, Ivl* dom) {
+    const int m0 = c.A.top;
+    Ivl bx[AB_MAXN];
+    const double h = flow_bounds(c, ops, vf, n, dx, hmax, bx, true);
+    for (int i = 0; i < n; ++i) dom[i] = dx[i];
+    dom[n] = ivl(-h, h);
+    if (c.status != ST_OK) { for (int i = 0; i < n; ++i) phi[i] = tm_begin(c, n + 1, acc_default()); return h; }
+    TM phi0[AB_MAXN], fphi[AB_MAXN], nphi[AB_MAXN];
+    for (int i = 0; i < n; ++i) phi0[i] = tm_scaling(c, n + 1, i, dom[i]);                     // ScalarTaylorFunction::variable(dom,i)
+    const int pbase = c.A.top;
+    for (int i = 0; i < n; ++i) { phi[i] = tm_const(c, n + 1, 1.0, acc_default()); tm_scal(c, phi[i], bx[i]); }   // constant(dom,bx[i])
+    const Ivl sf = rad_ivl(dom[n]);
+    #pragma unroll 1
+    for (int k = 0; k < order; ++k) {
+        for (int i = 0; i < n; ++i) fphi[i] = eval_tm(c, ops, vf[i], phi);                   // compose(f,phi) = f.evaluate(phi.models())
+        for (int i = 0; i < n; ++i) {
+            TM w = tm_copy(c, fphi[i]);
+            tm_antidiff(c, w, n);                                                             // antiderivative(model,n) ...
+            tm_scal(c, w, sf);                                                                // ... * rad_ivl(dom[n])
+            nphi[i] = tm_add(c, w, phi0[i]);                                                  // + phi0[i]
+        }
+        for (int i = 0; i < n; ++i) phi[i] = nphi[i];
+        vec_slide(c, phi, n, pbase);
+        if (c.status != ST_OK) break;
+    }
+    vec_slide(c, phi, n, m0);
+    return h;
 }
 
 } } // namespace ab200

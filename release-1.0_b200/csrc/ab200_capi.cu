@@ -665,6 +665,86 @@ extern "C" int ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc,
     return AB200_OK;
 }
 
+// == IntegratorBase::flow_bounds (src/integrator.cpp:44-113)
+extern "C" int ab200_integrator_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
+                                            double* h_out, double* bounds_out, int32_t* status_out) {
+    if (!ctx || !ctx->have_system || !loc || !boxes || !h_out || !bounds_out) return AB200_E_ARGUMENT;
+    { int rc_ = upload_system(ctx, false); if (rc_ != AB200_OK) return rc_; }
+    const int stride = AB200_BOX_STRIDE;
+    DevBuf<double> d_h, d_b;
+    CTX_CK(ctx->d_loc.ensure(n)); CTX_CK(ctx->d_box.ensure(n * stride)); CTX_CK(ctx->d_status.ensure(n));
+    cudaError_t e1 = d_h.ensure(n), e2 = d_b.ensure(n * stride);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { d_h.release(); d_b.release(); ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
+    cudaMemcpyAsync(ctx->d_loc.p, loc, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_box.p, boxes, n * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    char eb[256]; eb[0] = 0;
+    int rc = dev_launch_integrator_flow_bounds(ctx->stream, (int)n, ctx->d_loc.p, ctx->d_box.p, hmax, d_h.p, d_b.p, ctx->d_status.p, eb, sizeof(eb));
+    if (rc == 0) {
+        cudaMemcpyAsync(h_out, d_h.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(bounds_out, d_b.p, n * stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (status_out) cudaMemcpyAsync(status_out, ctx->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    d_h.release(); d_b.release();
+    if (rc != 0) { ctx->err = eb; return AB200_E_CUDA; }
+    if (es != cudaSuccess) { ctx->err = cudaGetErrorString(es); return AB200_E_CUDA; }
+    return AB200_OK;
+}
+
+struct ab200_taylor_models { int nargs; std::vector<int32_t> n_terms; std::vector<double> error; std::vector<std::vector<uint8_t> > exps; std::vector<std::vector<double> > coefs; };
+// == TaylorIntegrator::flow (src/integrator.cpp:116-152)
+extern "C" int ab200_integrator_flow(ab200_ctx* ctx, int32_t loc, const double* box, double hmax, int32_t temporal_order,
+                                     double* h_out, double* domain_out, ab200_taylor_models** out) {
+    if (!ctx || !ctx->have_system || !box || !out || loc < 0 || loc >= ctx->sys.desc.n_locs || temporal_order < 0) return AB200_E_ARGUMENT;
+    *out = 0;
+    { int rc_ = upload_system(ctx, false); if (rc_ != AB200_OK) return rc_; }
+    const int n = ctx->sys.desc.loc[loc].n;
+    if (n + 1 > 7) { ctx->err = "integrator flow supports up to 6 state variables"; return AB200_E_UNSUPPORTED; }
+    const int out_words = 1 << 20;
+    DevBuf<uint64_t> d_out; DevBuf<double> d_bx;
+    CTX_CK(ctx->d_arena.ensure((size_t)ctx->settings.arena_words));
+    if (d_out.ensure(out_words) != cudaSuccess || d_bx.ensure(AB200_BOX_STRIDE) != cudaSuccess) { d_out.release(); d_bx.release(); ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
+    cudaMemcpyAsync(d_bx.p, box, 2 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    char eb[256]; eb[0] = 0;
+    int rc = dev_launch_integrator_flow(ctx->stream, loc, d_bx.p, hmax, temporal_order, ctx->d_arena.p, ctx->settings.arena_words, ctx->d_binom.p, d_out.p, out_words, eb, sizeof(eb));
+    std::vector<uint64_t> h(3);
+    if (rc == 0) cudaMemcpyAsync(h.data(), d_out.p, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (rc != 0 || es != cudaSuccess) { d_out.release(); d_bx.release(); ctx->err = rc ? eb : cudaGetErrorString(es); return AB200_E_CUDA; }
+    double hh; memcpy(&hh, &h[0], 8);
+    if (h_out) *h_out = hh;
+    if (domain_out) { for (int i = 0; i < n; ++i) { domain_out[2 * i] = box[2 * i]; domain_out[2 * i + 1] = box[2 * i + 1]; } domain_out[2 * n] = -hh; domain_out[2 * n + 1] = hh; }
+    if ((int)h[1] != ST_OK) { d_out.release(); d_bx.release(); ctx->err = "integrator flow failed on the device"; return map_status((int)h[1]); }
+    std::vector<uint64_t> w(h[2]);
+    cudaMemcpy(w.data(), d_out.p, h[2] * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    d_out.release(); d_bx.release();
+    ab200_taylor_models* m = new ab200_taylor_models(); m->nargs = n + 1;
+    size_t p = 3;
+    for (int i = 0; i < n; ++i) {
+        const int nt = (int)w[p++]; double e; memcpy(&e, &w[p++], 8);
+        m->n_terms.push_back(nt); m->error.push_back(e);
+        std::vector<uint8_t> ex((size_t)nt * (n + 1)); std::vector<double> cf(nt);
+        for (int t = 0; t < nt; ++t) {
+            const uint64_t key = w[p++]; memcpy(&cf[t], &w[p++], 8);
+            for (int j = 0; j <= n; ++j) ex[(size_t)t * (n + 1) + j] = (uint8_t)((key >> (8 * (6 - j))) & 0xFF);
+        }
+        m->exps.push_back(ex); m->coefs.push_back(cf);
+    }
+    *out = m;
+    return AB200_OK;
+}
+extern "C" int ab200_taylor_models_view(const ab200_taylor_models* m, int32_t i, int32_t* nargs, int32_t* n_terms, double* error,
+                                        const uint8_t** exponents, const double** coefficients) {
+    if (!m || i < 0 || i >= (int)m->n_terms.size()) return AB200_E_ARGUMENT;
+    if (nargs) *nargs = m->nargs;
+    if (n_terms) *n_terms = m->n_terms[i];
+    if (error) *error = m->error[i];
+    if (exponents) *exponents = m->exps[i].empty() ? 0 : m->exps[i].data();
+    if (coefficients) *coefficients = m->coefs[i].empty() ? 0 : m->coefs[i].data();
+    return AB200_OK;
+}
+extern "C" void ab200_taylor_models_free(ab200_taylor_models* m) { delete m; }
+
 static int probe_fp64(ab200_ctx* ctx, int fma, double* gflops) {
     if (!ctx || !gflops) return AB200_E_ARGUMENT;
     CTX_CK(cudaSetDevice(ctx->device));

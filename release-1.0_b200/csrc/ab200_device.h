@@ -19,6 +19,10 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* 
 int dev_set_stack(size_t bytes, char* errbuf, int errlen);
 int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
                            double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen);
+int dev_launch_integrator_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
+                                      double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen);
+int dev_launch_integrator_flow(cudaStream_t st, int loc, const double* box, double hmax, int order, uint64_t* arena, int arena_words,
+                               const uint32_t* binom, uint64_t* out, int out_words, char* errbuf, int errlen);
 int dev_launch_fill(cudaStream_t st, uint64_t* p, size_t n, uint64_t v, char* errbuf, int errlen);
 int dev_launch_raster(cudaStream_t st, int n_cells, int max_boxes, const double* boxes, const int32_t* box_loc, const int32_t* n_boxes,
                       const KeyLayout& K, int n_locs, uint64_t* table, uint64_t mask, unsigned long long* counters, char* errbuf, int errlen);

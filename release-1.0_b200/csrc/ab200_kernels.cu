@@ -34,6 +34,45 @@ __global__ void K_flow_bounds(int n_cells, const int32_t* cell_loc, const double
     status[cell] = c.status;
 }
 
+// IntegratorBase::flow_bounds with its own constants, one thread per box (include/integrator_interface.h:45-50)
+__global__ void K_integrator_flow_bounds(int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
+                                         double* h_out, double* b_out, int32_t* status) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = 0; c.sm_dirty = 0; c.flops = 0.0;
+    const LocDesc& L = c_sys.loc[cell_loc[cell]];
+    Ivl r[AB_MAXN], b[AB_MAXN];
+    for (int i = 0; i < L.n; ++i) r[i] = ivl(cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i], cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i + 1]);
+    double h = flow_bounds(c, c_sys.ops, L.dyn, L.n, r, hmax, b, true);
+    h_out[cell] = h;
+    for (int i = 0; i < L.n; ++i) { b_out[(size_t)cell * 2 * AB_MAXN + 2 * i] = b[i].l; b_out[(size_t)cell * 2 * AB_MAXN + 2 * i + 1] = b[i].u; }
+    status[cell] = c.status;
+}
+// TaylorIntegrator::flow for one box, one warp: the n flow models are written to `out` as
+// [n_terms, error bits, then n_terms x (key word, coefficient bits)] per model; out[0] = h, out[1] = status, out[2] = words used.
+__global__ void __launch_bounds__(32, 1)
+K_integrator_flow(int loc, const double* __restrict__ box, double hmax, int order, uint64_t* __restrict__ arena, int arena_words,
+                  const uint32_t* __restrict__ binom, uint64_t* __restrict__ out, int out_words) {
+    extern __shared__ uint64_t ab_smem[];
+    Ctx c; ctx_init(c, arena, arena_words, ab_smem, binom);
+    ctx_stage_tables(c);
+    const LocDesc& L = c_sys.loc[loc];
+    const int n = L.n;
+    Ivl dx[AB_MAXN], dom[AB_MAXN + 1]; TM phi[AB_MAXN];
+    for (int i = 0; i < n; ++i) dx[i] = ivl(box[2 * i], box[2 * i + 1]);
+    const double h = integrator_flow(c, c_sys.ops, L.dyn, n, dx, hmax, order, phi, dom);
+    wsync();
+    if (wlane() == 0) {
+        int w = 3;
+        for (int i = 0; i < n && c.status == ST_OK; ++i) {
+            if (w + 2 + phi[i].n * AB_TW > out_words) { c.status = ST_OUTPUT; break; }
+            out[w++] = (uint64_t)phi[i].n; out[w++] = d2u(phi[i].e);
+            for (int t = 0; t < phi[i].n * AB_TW; ++t) out[w++] = c.A.base[phi[i].off + t];
+        }
+        out[0] = d2u(h); out[1] = (uint64_t)c.status; out[2] = (uint64_t)w;
+    }
+}
+
 // ---- rasterise + hash-set insert ------------------------------------------------------------------------------------
 #define AB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
@@ -219,6 +258,19 @@ int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc
                            double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen) {
     if (n_cells == 0) return 0;
     K_flow_bounds<<<(n_cells + 127) / 128, 128, 0, st>>>(n_cells, cell_loc, cell_box, hmax, h_out, b_out, status);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_integrator_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,
+                                      double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen) {
+    if (n_cells == 0) return 0;
+    K_integrator_flow_bounds<<<(n_cells + 127) / 128, 128, 0, st>>>(n_cells, cell_loc, cell_box, hmax, h_out, b_out, status);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_integrator_flow(cudaStream_t st, int loc, const double* box, double hmax, int order, uint64_t* arena, int arena_words,
+                               const uint32_t* binom, uint64_t* out, int out_words, char* errbuf, int errlen) {
+    K_integrator_flow<<<1, 32, AB_SM_WORDS * sizeof(uint64_t), st>>>(loc, box, hmax, order, arena, arena_words, binom, out, out_words);
     CK(cudaGetLastError());
     return 0;
 }

@@ -49,3 +49,11 @@ $H watertank reach acc=3 T=2 out=$G/watertank_reach_acc3_T2.txt
 $H springs reach acc=3 out=$G/springs_reach_acc3.txt && gzip -9 -f -n $G/springs_reach_acc3.txt
 # outer_chain_reach(initial, DIRECTION_BACKWARD): backward laps plus backward_jump_set between them
 $H bouncingball reach acc=5 backward=1 init=2.0,4.0,0.0,0.3 out=$G/bouncingball_backward_chain_acc5.txt
+# IntegratorInterface::flow_bounds / TaylorIntegrator::flow (src/integrator.cpp:44-152): the vector field of
+# test/test_integrator.cpp (x'=2, y'=3) with its box and step, and the van der Pol / bouncing-ball dynamics
+$H constder system out=$G/constder.sys
+$H constder integrator box=0.0,1.0,-0.5,1.5 h=1.0 order=4 out=$G/integrator_constder.txt
+$H constder integrator box=0.0,1.0,-0.5,1.5 h=1.0 order=1 out=$G/integrator_constder_o1.txt
+$H vanderpol integrator box=1.0,1.25,0.5,0.75 h=0.25 order=4 out=$G/integrator_vanderpol_o4.txt
+$H vanderpol integrator box=-2.0,-1.9375,0.0,0.0625 h=0.125 order=6 out=$G/integrator_vanderpol_o6.txt
+$H bouncingball integrator box=0.0,0.5,1.0,2.0 h=0.5 order=3 out=$G/integrator_bouncingball.txt

@@ -347,3 +347,54 @@ def test_reference_analyser_with_b200_worker(tmp_path, config, golden, args):
         assert set(mine["sets"][which].keys()) == set(ref["sets"][which].keys())
         for lname, cells in ref["sets"][which].items():
             assert golden_io.boxes_equal_bits(np.array(mine["sets"][which][lname]), cells), "%s cells of %s in %s" % (which, config, lname)
+
+
+def _load_integrator_golden(name):
+    out = {"models": []}
+    with open(os.path.join(golden_io.GOLDEN, name)) as f:
+        for line in f:
+            t = line.split()
+            if t[0] == "integrator":
+                out["loc"] = t[2]; out["order"] = int(t[4]); out["hmax"] = float.fromhex(t[6]); out["box"] = [float.fromhex(x) for x in t[8:]]
+            elif t[0] == "bounds":
+                out["h"] = float.fromhex(t[2]); out["bounds"] = [float.fromhex(x) for x in t[4:]]
+            elif t[0] == "domain":
+                out["domain"] = [float.fromhex(x) for x in t[1:]]
+            elif t[0] == "model":
+                out["models"].append({"error": float.fromhex(t[5]), "exps": [], "coefs": []})
+            elif t[0] == "t":
+                out["models"][-1]["exps"].append([int(x) for x in t[1:-1]]); out["models"][-1]["coefs"].append(float.fromhex(t[-1]))
+    return out
+
+
+@pytest.mark.parametrize("system,name", [("constder", "integrator_constder_o1.txt"), ("constder", "integrator_constder.txt"),
+                                         ("vanderpol", "integrator_vanderpol_o4.txt"), ("vanderpol", "integrator_vanderpol_o6.txt"),
+                                         ("bouncingball", "integrator_bouncingball.txt")])
+def test_integrator_flow_bounds_and_flow_bit_exact(pkg, system, name):
+    """IntegratorInterface (SURVEY 8a row a17): IntegratorBase::flow_bounds with the integrator's own constants and
+    TaylorIntegrator::flow (src/integrator.cpp:44-152), against the reference's results on the vector field, box and step of
+    test/test_integrator.cpp:73-157 (x'=2, y'=3, box [0,1]x[-0.5,1.5], h=1, order 1) and on the van der Pol / bouncing-ball
+    dynamics: step, bounding box, and every term, coefficient and error of the flow's Taylor models, bit for bit."""
+    g = _load_integrator_golden(name)
+    ev = pkg.Evolver(_system(system), settings={"arena_words": 262144})
+    try:
+        loc = ev.location(g["loc"])
+        h, b = ev.integrator_flow_bounds(loc, g["box"], g["hmax"])
+        assert h == g["h"] and golden_io.boxes_equal_bits(b, g["bounds"])
+        h2, dom, models = ev.integrator_flow(loc, g["box"], g["hmax"], g["order"])
+        assert h2 == g["h"] and golden_io.boxes_equal_bits(dom, g["domain"])
+        assert len(models) == len(g["models"])
+        for (ex, cf, err), ref in zip(models, g["models"]):
+            assert ex.tolist() == ref["exps"]
+            assert golden_io.boxes_equal_bits(cf, ref["coefs"]) and golden_io.boxes_equal_bits([err], [ref["error"]])
+        if system == "constder":
+            # the reference test's own checks (test/test_integrator.cpp:73-107): step kept, bounds cover [0,3]x[-0.5,4.5], and the
+            # flow is (x0+2t, y0+3t) to 1e-10 in the supremum norm of the scaled polynomial
+            assert h == 1.0 and b[0] <= 0.0 and b[1] >= 3.0 and b[2] <= -0.5 and b[3] >= 4.5
+            expect = [{(0, 0, 0): 0.5, (1, 0, 0): 0.5, (0, 0, 1): 2.0}, {(0, 0, 0): 0.5, (0, 1, 0): 1.0, (0, 0, 1): 3.0}]
+            for (ex, cf, err), want in zip(models, expect):
+                got = {tuple(e): c for e, c in zip(ex.tolist(), cf.tolist())}
+                norm = err + sum(abs(got.get(k, 0.0) - want.get(k, 0.0)) for k in set(got) | set(want))
+                assert norm < 1e-10
+    finally:
+        ev.close()
