@@ -249,9 +249,12 @@ def run_ours(args):
 
 
 def check_fingerprint(pkg, an, reach, evolve):
-    """sha256 of the reach / evolve cell sets of the lap, enumerated as the reference enumerates a HybridDenotableSet (maximal
-    dyadic cells, boxes printed as C hex floats), against the committed fingerprint of the reference's own result."""
-    import hashlib
+    """Fingerprint (cell count + sha256 over the sorted boxes of the maximal dyadic cells, raw bits) of the reach / evolve
+    cell sets of the lap, against the committed fingerprint of the reference's own UpperReachEvolveWorker::get_result() on
+    the same 101,520-cell frontier (tests/golden/vanderpol_bench_fingerprint.json, made by
+    tests/golden/make_bench_fingerprint.sh from the compiled reference)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from bench_fingerprint import fingerprint
     path = os.path.join(ROOT, "tests", "golden", "vanderpol_bench_fingerprint.json")
     try:
         want = json.load(open(path))
@@ -260,12 +263,10 @@ def check_fingerprint(pkg, an, reach, evolve):
     out = {}
     for name, cs in (("reach", reach), ("evolve", evolve)):
         _, boxes = an.enumerate(cs, mince=False)
-        h = hashlib.sha256()
-        for b in boxes:
-            h.update((" ".join(float(x).hex() for x in b[:4]) + "\n").encode())
-        out[name] = {"cells": int(boxes.shape[0]), "sha256": h.hexdigest()}
+        out[name] = fingerprint(boxes[:, :4])
     ok = all(out[k]["sha256"] == want[k]["sha256"] and out[k]["cells"] == want[k]["cells"] for k in ("reach", "evolve"))
-    return {"verdict": "identical to the reference" if ok else "MISMATCH", "reach": out["reach"], "evolve": out["evolve"], "reference": want}
+    return {"verdict": "identical to the reference" if ok else "MISMATCH", "reach": out["reach"], "evolve": out["evolve"],
+            "reference": {k: want[k] for k in ("reach", "evolve")}}
 
 
 def cpu_baseline(n_cells, threads=None):

@@ -107,6 +107,11 @@ int  ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s);
 int  ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max_step, const double* ref_widths,
                                const double* grid_origin, const double* grid_lengths);
 int  ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy);
+/* The same with the packed cell keys sized to the analysed domain (n_locations boxes of AB200_BOX_STRIDE doubles, lo/hi per
+ * coordinate; what HybridReachabilityAnalyser is constructed with, src/reachability_analyser.cpp:83-100). A BDDTreeSet has
+ * no index range; a 64-bit key has, and the uniform split of ab200_set_accuracy does not hold a 5-variable system at
+ * accuracy 10 (BASELINE configs[3]). The uniform layout is kept whenever it fits, so keys do not change for smaller systems. */
+int  ab200_set_accuracy_for_domain(ab200_ctx* ctx, int32_t accuracy, const double* domain_boxes);
 
 /* The hot call == UpperReachEvolveWorker::get_result() (include/workers.h:51-81,102-153): evolve every enclosure for
  * (t_continuous, max_events), discretise reach and final sets at the context's accuracy. */

@@ -267,9 +267,10 @@ int main(int argc, char** argv) {
                 for(HEnclList::const_iterator r=re.second.begin(); r!=re.second.end(); ++r) {
                     fprintf(out,"f %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
                 if(geti(kv,"disc",0)) {
-                    // what UpperReachEvolveWorker adjoins for this enclosure (include/workers.h:144-148)
+                    // what UpperReachEvolveWorker adjoins for this enclosure (include/workers.h:144-148); disc=2: only the union
+                    if(geti(kv,"disc",0)==1) {
                     dump_set(out,"dreach",outer_approximation(re.first,grid,c.acc));
-                    dump_set(out,"dfinal",outer_approximation(re.second,grid,c.acc));
+                    dump_set(out,"dfinal",outer_approximation(re.second,grid,c.acc)); }
                     ureach.adjoin(outer_approximation(re.first,grid,c.acc)); ufinal.adjoin(outer_approximation(re.second,grid,c.acc));
                 }
             } catch(std::exception& e) {

@@ -30,7 +30,7 @@ AB200_E_CUDA, AB200_E_ARGUMENT, AB200_E_KEYSPACE, AB200_E_TIMEOUT = 100, 101, 10
 
 EXPORTS = [
     "ab200_default_settings", "ab200_ctx_create", "ab200_ctx_destroy", "ab200_last_error", "ab200_set_system_text",
-    "ab200_system_info", "ab200_system_check", "ab200_location_index", "ab200_set_settings", "ab200_set_location_tuning", "ab200_set_accuracy",
+    "ab200_system_info", "ab200_system_check", "ab200_location_index", "ab200_set_settings", "ab200_set_location_tuning", "ab200_set_accuracy", "ab200_set_accuracy_for_domain",
     "ab200_upper_reach_evolve", "ab200_cellset_view", "ab200_cellset_free", "ab200_key_decode", "ab200_reach_evolve_boxes",
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
@@ -88,6 +88,7 @@ def load_library():
     lib.ab200_set_settings.argtypes = [vp, P(Settings)]; lib.ab200_set_settings.restype = C.c_int
     lib.ab200_set_location_tuning.argtypes = [vp, i32, dbl, P(dbl), P(dbl), P(dbl)]; lib.ab200_set_location_tuning.restype = C.c_int
     lib.ab200_set_accuracy.argtypes = [vp, i32]; lib.ab200_set_accuracy.restype = C.c_int
+    lib.ab200_set_accuracy_for_domain.argtypes = [vp, i32, P(dbl)]; lib.ab200_set_accuracy_for_domain.restype = C.c_int
     lib.ab200_upper_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, C.c_int, C.c_int, P(vp), P(vp), P(Status)]
     lib.ab200_upper_reach_evolve.restype = C.c_int
     lib.ab200_cellset_view.argtypes = [vp, P(P(u64)), P(u64)]; lib.ab200_cellset_view.restype = C.c_int
@@ -146,19 +147,31 @@ def pack_boxes(boxes, dim):
 class CellSet(object):
     """Sorted, duplicate-free packed cell keys of a HybridDenotableSet (host copy)."""
 
-    def __init__(self, keys):
+    def __init__(self, keys, lib=None, handle=None):
         self.keys = keys
+        self._lib = lib
+        self._handle = handle        # the library object (kept for HybridReachabilityAnalyser.enumerate), freed with this one
 
     def __len__(self):
         return int(self.keys.shape[0])
+
+    def release(self):
+        if self._handle is not None and self._lib is not None:
+            self._lib.ab200_cellset_free(self._handle)
+        self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def _take_cellset(lib, handle):
     keys = C.POINTER(C.c_uint64)(); n = C.c_uint64(0)
     lib.ab200_cellset_view(handle, C.byref(keys), C.byref(n))
     arr = np.ctypeslib.as_array(keys, shape=(n.value,)).copy() if n.value else np.zeros((0,), dtype=np.uint64)
-    lib.ab200_cellset_free(handle)
-    return CellSet(arr)
+    return CellSet(arr, lib, handle)
 
 
 def _take_boxlist(lib, handle, n_cells):
@@ -423,14 +436,7 @@ class HybridReachabilityAnalyser(object):
         return int(self.lib.ab200_analyser_cells_evolved(self.handle))
 
     def _wrap(self, handle):
-        # keep the library object alive for enumerate(); copy the keys for numpy users
-        keys = C.POINTER(C.c_uint64)(); n = C.c_uint64(0)
-        self.lib.ab200_cellset_view(handle, C.byref(keys), C.byref(n))
-        arr = np.ctypeslib.as_array(keys, shape=(n.value,)).copy() if n.value else np.zeros((0,), dtype=np.uint64)
-        cs = CellSet(arr)
-        cs._handle = handle
-        cs._owner = self
-        return cs
+        return _take_cellset(self.lib, handle)
 
     def enumerate(self, cellset, mince=False):
         """Cells of a set as the reference iterates them: (locs, boxes[count, 2*dim])."""
@@ -442,6 +448,4 @@ class HybridReachabilityAnalyser(object):
         return locs, boxes[:, :2 * self.dim]
 
     def free(self, cellset):
-        if getattr(cellset, "_handle", None):
-            self.lib.ab200_cellset_free(cellset._handle)
-            cellset._handle = None
+        cellset.release()

@@ -149,7 +149,7 @@ extern "C" int ab200_analyser_create(ab200_analyser** out, ab200_ctx* ctx, const
         int rc = ab200_set_location_tuning(ctx, l, an->max_step[l], refw, g.origin, g.lengths);
         if (rc != AB200_OK) { delete an; return rc; }
     }
-    int rc = ab200_set_accuracy(ctx, accuracy);
+    int rc = ab200_set_accuracy_for_domain(ctx, accuracy, domain_boxes);
     if (rc != AB200_OK) { delete an; return rc; }
     an->K = *ab200_ctx_layout(ctx);
     an->restriction.resize(L); an->discretised.assign(L, 0);

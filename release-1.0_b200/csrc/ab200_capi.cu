@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
+#include <cmath>
 #include <map>
 #include <algorithm>
 #include <chrono>
@@ -231,6 +232,48 @@ extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
     for (int i = 0; i < dim; ++i) { K.bits[i] = per; K.bias[i] = 1LL << (per - 1); }
     for (int i = dim; i < AB_GRID_MAXN; ++i) { K.bits[i] = 0; K.bias[i] = 0; }
     ctx->K = K; ctx->accuracy = accuracy; ctx->have_layout = true;
+    return AB200_OK;
+}
+// Cell keys sized to a domain (a 5-variable system at accuracy 10 does not fit the uniform split of 63 bits).
+// Per coordinate the key field covers the lattice indices of the domain boxes of all locations at this accuracy plus a
+// margin of a quarter base cell (at least 16 cells) per side; spare bits widen the margins evenly. Cells that fall outside
+// the key space are reported (AB200_E_KEYSPACE), never dropped.
+extern "C" int ab200_set_accuracy_for_domain(ab200_ctx* ctx, int32_t accuracy, const double* domain_boxes) {
+    if (!ctx || !ctx->have_system || !domain_boxes || accuracy < 0 || accuracy > 24) return AB200_E_ARGUMENT;
+    if (ab200_set_accuracy(ctx, accuracy) == AB200_OK) return AB200_OK;          // the uniform layout is kept whenever it fits
+    const SystemDesc& S = ctx->sys.desc;
+    const int dim = S.loc[0].n;
+    for (int l = 1; l < S.n_locs; ++l) if (S.loc[l].n != dim) return AB200_E_UNSUPPORTED;
+    KeyLayout K; K.dim = dim; K.acc = accuracy;
+    int lb = 0; while ((1 << lb) < S.n_locs) ++lb;
+    K.loc_bits = lb;
+    const double fine = (double)(1LL << accuracy);
+    long long margin = (1LL << accuracy) / 4; if (margin < 16) margin = 16;
+    int total = lb;
+    long long lo[AB_GRID_MAXN], hi[AB_GRID_MAXN];
+    for (int i = 0; i < dim; ++i) {
+        bool any = false;
+        for (int l = 0; l < S.n_locs; ++l) {
+            const double a = domain_boxes[(size_t)l * AB200_BOX_STRIDE + 2 * i], b = domain_boxes[(size_t)l * AB200_BOX_STRIDE + 2 * i + 1];
+            if (!(a <= b)) continue;                                                // empty domain in this location
+            const double o = S.loc[l].grid_origin[i], len = S.loc[l].grid_length[i];
+            if (!(len > 0)) { ctx->err = "ab200_set_location_tuning must be called for every location first"; return AB200_E_ARGUMENT; }
+            const double fa = std::floor((a - o) / len * fine), fb = std::ceil((b - o) / len * fine);
+            if (!(std::fabs(fa) < 4.0e18) || !(std::fabs(fb) < 4.0e18)) { ctx->err = "domain too large for 64-bit cell keys"; return AB200_E_KEYSPACE; }
+            const long long ia = (long long)fa - margin, ib = (long long)fb + margin;
+            if (!any || ia < lo[i]) lo[i] = ia;
+            if (!any || ib > hi[i]) hi[i] = ib;
+            any = true;
+        }
+        if (!any) { lo[i] = -margin; hi[i] = margin; }
+        int b = 1; while (b < 62 && (1LL << b) < hi[i] - lo[i] + 1) ++b;
+        K.bits[i] = b; total += b;
+    }
+    if (total > 63) { ctx->err = "accuracy too fine for 64-bit cell keys on this domain"; return AB200_E_KEYSPACE; }
+    for (int i = 0; total < 63 && K.bits[i % dim] < 40; ++i) { if (i >= 64 * dim) break; K.bits[i % dim]++; total++; }      // spare bits: wider margins
+    for (int i = 0; i < dim; ++i) { const long long span = 1LL << K.bits[i], used = hi[i] - lo[i] + 1; K.bias[i] = -lo[i] + (span - used) / 2; }
+    for (int i = dim; i < AB_GRID_MAXN; ++i) { K.bits[i] = 0; K.bias[i] = 0; }
+    ctx->K = K; ctx->accuracy = accuracy; ctx->have_layout = true; ctx->err.clear();
     return AB200_OK;
 }
 extern "C" int ab200_key_decode(const ab200_ctx* ctx, uint64_t key, int32_t* loc, int64_t* idx) {

@@ -57,3 +57,10 @@ $H constder integrator box=0.0,1.0,-0.5,1.5 h=1.0 order=1 out=$G/integrator_cons
 $H vanderpol integrator box=1.0,1.25,0.5,0.75 h=0.25 order=4 out=$G/integrator_vanderpol_o4.txt
 $H vanderpol integrator box=-2.0,-1.9375,0.0,0.0625 h=0.125 order=6 out=$G/integrator_vanderpol_o6.txt
 $H bouncingball integrator box=0.0,0.5,1.0,2.0 h=0.5 order=3 out=$G/integrator_bouncingball.txt
+# ---- BASELINE depth (configs[0] grid depth 6, configs[3] grid depth 10, configs[4] at accuracy 6): per-enclosure boxes of
+# sampled frontier cells over a horizon the compiled reference finishes in seconds, plus the fingerprint of the union of
+# their discretisations (what UpperReachEvolveWorker adjoins). A full lock-to-grid lap at these depths costs the reference hours.
+D=${TMPDIR:-/tmp}
+$H watertank cells acc=6 T=3.0 ncells=24 stride=14 disc=2 out=$D/wt6.txt && python $G/fingerprint_unions.py $D/wt6.txt $G/watertank_cells_acc6.txt && gzip -9 -f -n $G/watertank_cells_acc6.txt
+$H springs cells acc=10 T=6.0 ncells=2 disc=2 out=$D/sp10.txt && python $G/fingerprint_unions.py $D/sp10.txt $G/springs_cells_acc10.txt && gzip -9 -f -n $G/springs_cells_acc10.txt
+$H boost cells acc=6 chain=0 T=0.011 disc=2 out=$D/bo6.txt && python $G/fingerprint_unions.py $D/bo6.txt $G/boost_cells_acc6.txt && gzip -9 -f -n $G/boost_cells_acc6.txt

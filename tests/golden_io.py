@@ -59,6 +59,10 @@ def load_dump(name):
                 cur_set = cur_cell[k]
             elif k == "union":
                 cur_cell = None
+            elif k in ("ureach_fp", "ufinal_fp"):
+                # fingerprint of a large union set (tests/golden/fingerprint_unions.py): count + sha256 of the sorted boxes
+                out.setdefault("fp", {}).setdefault(k[:-3], {})[t[2]] = {"cells": int(t[4]), "sha256": t[6]}
+                cur_set = None
             elif k in ("reach", "evolve", "ureach", "ufinal"):
                 cur_set = out["sets"].setdefault(k, {}).setdefault(t[2], [])
             elif k == "c" and cur_set is not None:

@@ -207,6 +207,57 @@ def test_lap_cell_sets_match_union_of_reference_discretisations(pkg):
         ev.close()
 
 
+DEPTH_CASES = [
+    # BASELINE.json grid depths: configs[0] watertank depth 6, configs[3] springs depth 10, configs[4] boost at accuracy 6
+    ("watertank", "watertank_cells_acc6.txt.gz", [0.0, 1.0, 4.5, 9.0], 131072),
+    ("springs", "springs_cells_acc10.txt.gz", [0.0, 40.0, -2.0, 2.0, -3.0, 3.0, -1.0, 3.0, 0.0, 4.0], 262144),
+    ("boost", "boost_cells_acc6.txt.gz", [0.0, 0.001, 0.0, 3.0, 0.0, 6.0], 32768),
+]
+
+
+@pytest.mark.parametrize("system,name,domain,arena", DEPTH_CASES)
+def test_baseline_depth_sampled_cells_bit_exact(pkg, system, name, domain, arena):
+    """The three hybrid configs at the grid depth BASELINE.json quotes: sampled frontier cells over a horizon the compiled
+    reference finishes in seconds. Per-enclosure reach / final boxes bit-exact, and the discretised union (what
+    UpperReachEvolveWorker adjoins) identical cell for cell (count + sha256 of the sorted cell boxes per location).
+    springs at accuracy 10 needs the domain-sized key layout (ab200_set_accuracy_for_domain)."""
+    import sys as _sys
+    _sys.path.insert(0, golden_io.GOLDEN)
+    from bench_fingerprint import fingerprint
+    d = golden_io.load_dump(name)
+    an = pkg.HybridReachabilityAnalyser(_system(system), domain, d["config"]["acc"], settings={"arena_words": arena, "max_boxes": 2048, "hash_log2": 22})
+    ev = an.evolver
+    try:
+        assert an.lock_to_grid_time == d["config"]["lock"]
+        for lname, g in d["grid"].items():
+            l = ev.location(lname)
+            assert list(an.grid_lengths[l][:g["n"]]) == g["lengths"] and list(an.grid_origin[l][:g["n"]]) == g["origin"]
+            ev.tune_settings(l, g["maxstep"], g["refw"], g["origin"], g["lengths"])
+        dim = ev.dims[0]
+        locs = [ev.location(c["loc"]) for c in d["cells"]]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
+        T, events = d["config"]["T"], d["config"]["events"]
+        (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, T, events, d["config"]["ignore_activations"])
+        for i, c in enumerate(d["cells"]):
+            assert c["error"] is None
+            # the reference's list sets are grouped by location (HybridListSet is a map over locations, iterated in name
+            # order); within a location the insertion order is kept. Compare location by location.
+            for mine_b, mine_l, ref_b, ref_l, what in ((rbox[roff[i]:roff[i + 1]], rloc[roff[i]:roff[i + 1]], c["reach"], c["reach_loc"], "reach"),
+                                                       (fbox[foff[i]:foff[i + 1]], floc[foff[i]:foff[i + 1]], c["final"], c["final_loc"], "final")):
+                assert len(ref_b) == mine_b.shape[0], "%s box count of cell %d" % (what, c["id"])
+                for lname in set(ref_l) | set(d["grid"].keys()):
+                    ref_rows = [b for b, n in zip(ref_b, ref_l) if n == lname]
+                    assert golden_io.boxes_equal_bits(mine_b[mine_l == ev.location(lname), :2 * dim], ref_rows), "%s boxes of cell %d in %s" % (what, c["id"], lname)
+        reach, evolve = ev.upper_reach_evolve(locs, boxes, T, events, d["config"]["ignore_activations"])
+        for which, cs in (("ureach", reach), ("ufinal", evolve)):
+            cl, cb = an.enumerate(cs)
+            for lname, want in d["fp"][which].items():
+                mine = fingerprint(cb[cl == ev.location(lname)])
+                assert mine["cells"] == want["cells"] and (want["cells"] == 0 or mine["sha256"] == want["sha256"]), "%s cells of %s in %s" % (which, system, lname)
+    finally:
+        an.close()
+
+
 def test_flow_bounds_facade(pkg):
     d = golden_io.load_dump("vanderpol_cells_acc6.txt.gz")
     ev = _evolver(pkg, d)

@@ -40,6 +40,8 @@ extern "C" int ab200_set_location_tuning(ab200_ctx* ctx, int32_t loc, double max
     for (int i = 0; i < L.n; ++i) { L.ref_width[i] = ref_widths[i]; L.grid_origin[i] = grid_origin[i]; L.grid_length[i] = grid_lengths[i]; }
     return AB200_OK;
 }
+extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy);
+extern "C" int ab200_set_accuracy_for_domain(ab200_ctx* ctx, int32_t accuracy, const double*) { return ab200_set_accuracy(ctx, accuracy); }
 extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
     const SystemDesc& S = ctx->sys.desc;
     int dim = S.loc[0].n;
