@@ -152,6 +152,23 @@ int  ab200_taylor_models_view(const ab200_taylor_models* m, int32_t i, int32_t* 
                               const uint8_t** exponents /* [n_terms][nargs] */, const double** coefficients);
 void ab200_taylor_models_free(ab200_taylor_models* m);
 
+/* Primitive-level entry points (rows a8 / a15 of the scope table): ONE TaylorModel operator or function of
+ * include/taylor_model.h / src/taylor_model.cpp, run by one warp with the kernels' own primitives, and a batch of Interval
+ * operations of include/numeric.h. They exist so that the reference's unit-test vectors (test/test_taylor_model.cpp:164-270,
+ * test/test_interval.cpp:152-254) can be replayed on the device bit for bit; models are given and returned as
+ * (exponent bytes [n_terms][nargs] in the reference's graded order, coefficients, uniform error), default Accuracy.
+ * op: 0 x+y, 1 x-y, 2 x*y, 3 x+s, 4 x-s, 5 x*s, 6 x/s, 7 x+I, 8 x-I, 9 x*I, 10 x/I, 11 -x, 12 intersection(x,y),
+ *     13 split(x,k,flag), 14 antiderivative(x,k), 15 rec(x), 16 sqrt(x), 17 abs(x), 18 max(x,y), 19 x.range() -> range_out. */
+int  ab200_taylor_model_op(ab200_ctx* ctx, int32_t op, int32_t nargs,
+                           int32_t x_terms, const uint8_t* x_exps, const double* x_coefs, double x_error,
+                           int32_t y_terms, const uint8_t* y_exps, const double* y_coefs, double y_error,
+                           int32_t k, int32_t flag, double s, const double* interval /* [2] */, double* range_out /* [2] */,
+                           ab200_taylor_models** out);
+/* ops[i] = {op, m, a.lower, a.upper, b.lower, b.upper}, results[i] = {lower, upper, status}.
+ * op: 0 a+b, 1 a-b, 2 a*b, 3 a/b, 4 a+Float(b.lower), 5 a-Float, 6 a*Float, 7 a/Float, 8 Float(a.lower)-b, 9 Float/b,
+ *     10 sqr(a), 11 sqrt(a), 12 pow(a,m), 13 rec(a), 14 abs(a), 15 -a, 16 max(a,b), 17 min(a,b). */
+int  ab200_interval_op(ab200_ctx* ctx, int32_t n, const double* ops, double* results);
+
 /* Host mirror of HybridReachabilityAnalyser (include/reachability_analyser.h:122-172): grid, lock-to-grid time and
  * evolver tuning derived from the domain exactly as HybridReachabilityAnalyser(system,domain,accuracy) does
  * (src/reachability_analyser.cpp:83-100,1028-1170; src/hybrid_set.cpp:485-515), laps driven through

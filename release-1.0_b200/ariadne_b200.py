@@ -35,7 +35,7 @@ EXPORTS = [
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
     "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
-    "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free",
+    "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free", "ab200_taylor_model_op", "ab200_interval_op",
 ]
 
 
@@ -88,6 +88,9 @@ def load_library():
     lib.ab200_set_settings.argtypes = [vp, P(Settings)]; lib.ab200_set_settings.restype = C.c_int
     lib.ab200_set_location_tuning.argtypes = [vp, i32, dbl, P(dbl), P(dbl), P(dbl)]; lib.ab200_set_location_tuning.restype = C.c_int
     lib.ab200_set_accuracy.argtypes = [vp, i32]; lib.ab200_set_accuracy.restype = C.c_int
+    lib.ab200_taylor_model_op.argtypes = [vp, i32, i32, i32, P(C.c_uint8), P(dbl), dbl, i32, P(C.c_uint8), P(dbl), dbl, i32, i32, dbl, P(dbl), P(dbl), P(vp)]
+    lib.ab200_taylor_model_op.restype = C.c_int
+    lib.ab200_interval_op.argtypes = [vp, i32, P(dbl), P(dbl)]; lib.ab200_interval_op.restype = C.c_int
     lib.ab200_set_accuracy_for_domain.argtypes = [vp, i32, P(dbl)]; lib.ab200_set_accuracy_for_domain.restype = C.c_int
     lib.ab200_upper_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, C.c_int, C.c_int, P(vp), P(vp), P(Status)]
     lib.ab200_upper_reach_evolve.restype = C.c_int
@@ -321,6 +324,41 @@ class Evolver(object):
         finally:
             self.lib.ab200_taylor_models_free(m)
         return h.value, dom, models
+
+    TM_OPS = {"add": 0, "sub": 1, "mul": 2, "addf": 3, "subf": 4, "mulf": 5, "divf": 6, "addi": 7, "subi": 8, "muli": 9, "divi": 10, "neg": 11,
+              "intersection": 12, "split": 13, "antiderivative": 14, "rec": 15, "sqrt": 16, "abs": 17, "max": 18, "range": 19}
+    IV_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "addf": 4, "subf": 5, "mulf": 6, "divf": 7, "fsub": 8, "fdiv": 9, "sqr": 10, "sqrt": 11,
+              "pow": 12, "rec": 13, "abs": 14, "neg": 15, "max": 16, "min": 17}
+
+    def taylor_model_op(self, op, nargs, x, y=None, k=0, flag=0, s=0.0, interval=(0.0, 0.0)):
+        """One TaylorModel operator / function on the device. x, y: (exponents[n][nargs] uint8, coefficients[n], error).
+        Returns (exponents, coefficients, error) -- or the range interval for op "range"."""
+        def unpack(m):
+            if m is None:
+                return 0, None, None, 0.0, None
+            e = np.ascontiguousarray(np.asarray(m[0], dtype=np.uint8).reshape(-1, nargs)); v = np.ascontiguousarray(np.asarray(m[1], dtype=np.float64))
+            n = int(v.shape[0])
+            return n, (e.ctypes.data_as(C.POINTER(C.c_uint8)) if n else None), (v.ctypes.data_as(C.POINTER(C.c_double)) if n else None), float(m[2]), (e, v)
+        nx, xe, xv, xerr, keepx = unpack(x); ny, ye, yv, yerr, keepy = unpack(y)
+        iv = (C.c_double * 2)(float(interval[0]), float(interval[1])); rng = (C.c_double * 2)(0.0, 0.0); m = C.c_void_p()
+        self._check(self.lib.ab200_taylor_model_op(self.handle, self.TM_OPS[op], nargs, nx, xe, xv, xerr, ny, ye, yv, yerr, int(k), int(flag), float(s), iv, rng, C.byref(m)))
+        try:
+            na = C.c_int32(0); nt = C.c_int32(0); err = C.c_double(0); ex = C.POINTER(C.c_uint8)(); cf = C.POINTER(C.c_double)()
+            self.lib.ab200_taylor_models_view(m, 0, C.byref(na), C.byref(nt), C.byref(err), C.byref(ex), C.byref(cf))
+            e = np.ctypeslib.as_array(ex, shape=(nt.value, na.value)).copy() if nt.value else np.zeros((0, nargs), dtype=np.uint8)
+            v = np.ctypeslib.as_array(cf, shape=(nt.value,)).copy() if nt.value else np.zeros((0,), dtype=np.float64)
+        finally:
+            self.lib.ab200_taylor_models_free(m)
+        if op == "range":
+            return (rng[0], rng[1])
+        return e, v, err.value
+
+    def interval_ops(self, ops):
+        """Batch of Interval operations: ops = [(name, m, (al, au), (bl, bu))] -> array [n][3] = lower, upper, status."""
+        a = np.ascontiguousarray(np.asarray([[self.IV_OPS[o], m, x[0], x[1], y[0], y[1]] for o, m, x, y in ops], dtype=np.float64).reshape(-1, 6))
+        out = np.zeros((a.shape[0], 3), dtype=np.float64)
+        self._check(self.lib.ab200_interval_op(self.handle, a.shape[0], _dptr(a), _dptr(out)))
+        return out
 
     def init_comm(self, dist):
         """Join the ranks of an initialised torch.distributed process group into the library's NCCL communicator: rank 0's

@@ -776,6 +776,75 @@ extern "C" int ab200_integrator_flow(ab200_ctx* ctx, int32_t loc, const double* 
     *out = m;
     return AB200_OK;
 }
+// ---- primitive-level entry points: one TaylorModel operator / function, a batch of Interval operations ---------------
+// (include/taylor_model.h operators and functions, include/numeric.h Interval arithmetic; used by the known-answer tests,
+// which replay the vectors of the reference's test/test_taylor_model.cpp and test/test_interval.cpp on the device)
+extern "C" int ab200_taylor_model_op(ab200_ctx* ctx, int32_t op, int32_t nargs,
+                                     int32_t x_terms, const uint8_t* x_exps, const double* x_coefs, double x_error,
+                                     int32_t y_terms, const uint8_t* y_exps, const double* y_coefs, double y_error,
+                                     int32_t k, int32_t flag, double s, const double* interval, double* range_out, ab200_taylor_models** out) {
+    if (!ctx || !out || nargs < 1 || nargs > 7 || x_terms < 0 || y_terms < 0 || (x_terms && (!x_exps || !x_coefs)) || (y_terms && (!y_exps || !y_coefs))) return AB200_E_ARGUMENT;
+    *out = 0;
+    std::vector<uint64_t> in;
+    double iv[2] = { interval ? interval[0] : 0.0, interval ? interval[1] : 0.0 };
+    uint64_t u; 
+    in.push_back((uint64_t)op); in.push_back((uint64_t)nargs); in.push_back((uint64_t)(int64_t)k); in.push_back((uint64_t)(int64_t)flag);
+    memcpy(&u, &s, 8); in.push_back(u); memcpy(&u, &iv[0], 8); in.push_back(u); memcpy(&u, &iv[1], 8); in.push_back(u);
+    const int32_t nt[2] = { x_terms, y_terms }; const uint8_t* ex[2] = { x_exps, y_exps }; const double* cf[2] = { x_coefs, y_coefs }; const double er[2] = { x_error, y_error };
+    for (int q = 0; q < 2; ++q) {
+        in.push_back((uint64_t)nt[q]); memcpy(&u, &er[q], 8); in.push_back(u);
+        for (int t = 0; t < nt[q]; ++t) {
+            uint64_t key = 0; unsigned deg = 0;
+            for (int j = 0; j < nargs; ++j) { const unsigned e = ex[q][(size_t)t * nargs + j]; if (e > 127) return AB200_E_ARGUMENT; deg += e; key |= (uint64_t)e << (8 * (6 - j)); }
+            if (deg > 255) return AB200_E_ARGUMENT;
+            key |= (uint64_t)deg << 56;
+            in.push_back(key); memcpy(&u, &cf[q][t], 8); in.push_back(u);
+        }
+    }
+    const int out_words = 1 << 18;
+    DevBuf<uint64_t> d_in, d_out;
+    CTX_CK(ctx->d_arena.ensure((size_t)ctx->settings.arena_words));
+    if (d_in.ensure(in.size()) != cudaSuccess || d_out.ensure(out_words) != cudaSuccess) { d_in.release(); d_out.release(); ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
+    cudaMemcpyAsync(d_in.p, in.data(), in.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    char eb[256]; eb[0] = 0;
+    int rc = dev_launch_tm_op(ctx->stream, d_in.p, ctx->d_arena.p, ctx->settings.arena_words, ctx->d_binom.p, d_out.p, out_words, eb, sizeof(eb));
+    std::vector<uint64_t> h(4);
+    if (rc == 0) cudaMemcpyAsync(h.data(), d_out.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (rc != 0 || es != cudaSuccess) { d_in.release(); d_out.release(); ctx->err = rc ? eb : cudaGetErrorString(es); return AB200_E_CUDA; }
+    if ((int)h[0] != ST_OK) { d_in.release(); d_out.release(); ctx->err = "TaylorModel operation failed on the device"; return map_status((int)h[0]); }
+    if (range_out) { memcpy(&range_out[0], &h[2], 8); memcpy(&range_out[1], &h[3], 8); }
+    std::vector<uint64_t> w(h[1]);
+    cudaMemcpy(w.data(), d_out.p, h[1] * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    d_in.release(); d_out.release();
+    ab200_taylor_models* m = new ab200_taylor_models(); m->nargs = nargs;
+    size_t p = 4;
+    const int n = (int)w[p++]; double e; memcpy(&e, &w[p++], 8);
+    m->n_terms.push_back(n); m->error.push_back(e);
+    std::vector<uint8_t> exo((size_t)n * nargs); std::vector<double> cfo(n);
+    for (int t = 0; t < n; ++t) {
+        const uint64_t key = w[p++]; memcpy(&cfo[t], &w[p++], 8);
+        for (int j = 0; j < nargs; ++j) exo[(size_t)t * nargs + j] = (uint8_t)((key >> (8 * (6 - j))) & 0xFF);
+    }
+    m->exps.push_back(exo); m->coefs.push_back(cfo);
+    *out = m;
+    return AB200_OK;
+}
+// ops[i] = {op, m, a.lower, a.upper, b.lower, b.upper}; results[i] = {lower, upper, status}
+extern "C" int ab200_interval_op(ab200_ctx* ctx, int32_t n, const double* ops, double* results) {
+    if (!ctx || n < 0 || (n && (!ops || !results))) return AB200_E_ARGUMENT;
+    if (n == 0) return AB200_OK;
+    DevBuf<double> d_in, d_out;
+    if (d_in.ensure((size_t)n * 6) != cudaSuccess || d_out.ensure((size_t)n * 3) != cudaSuccess) { d_in.release(); d_out.release(); ctx->err = "cudaMalloc failed"; return AB200_E_CUDA; }
+    cudaMemcpyAsync(d_in.p, ops, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    char eb[256]; eb[0] = 0;
+    int rc = dev_launch_interval_op(ctx->stream, n, d_in.p, d_out.p, eb, sizeof(eb));
+    if (rc == 0) cudaMemcpyAsync(results, d_out.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    d_in.release(); d_out.release();
+    if (rc != 0 || es != cudaSuccess) { ctx->err = rc ? eb : cudaGetErrorString(es); return AB200_E_CUDA; }
+    return AB200_OK;
+}
 extern "C" int ab200_taylor_models_view(const ab200_taylor_models* m, int32_t i, int32_t* nargs, int32_t* n_terms, double* error,
                                         const uint8_t** exponents, const double** coefficients) {
     if (!m || i < 0 || i >= (int)m->n_terms.size()) return AB200_E_ARGUMENT;

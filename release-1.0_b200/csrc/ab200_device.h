@@ -23,6 +23,9 @@ int dev_launch_integrator_flow_bounds(cudaStream_t st, int n_cells, const int32_
                                       double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen);
 int dev_launch_integrator_flow(cudaStream_t st, int loc, const double* box, double hmax, int order, uint64_t* arena, int arena_words,
                                const uint32_t* binom, uint64_t* out, int out_words, char* errbuf, int errlen);
+int dev_launch_tm_op(cudaStream_t st, const uint64_t* in, uint64_t* arena, int arena_words, const uint32_t* binom, uint64_t* out, int out_words,
+                     char* errbuf, int errlen);
+int dev_launch_interval_op(cudaStream_t st, int n, const double* in, double* out, char* errbuf, int errlen);
 int dev_launch_fill(cudaStream_t st, uint64_t* p, size_t n, uint64_t v, char* errbuf, int errlen);
 int dev_launch_raster(cudaStream_t st, int n_cells, int max_boxes, const double* boxes, const int32_t* box_loc, const int32_t* n_boxes,
                       const KeyLayout& K, int n_locs, uint64_t* table, uint64_t mask, unsigned long long* counters, char* errbuf, int errlen);

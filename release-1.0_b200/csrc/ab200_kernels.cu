@@ -73,6 +73,94 @@ K_integrator_flow(int loc, const double* __restrict__ box, double hmax, int orde
     }
 }
 
+// ---- primitive level entry points (known-answer tests against the reference's own unit-test vectors) -----------------
+// One TaylorModel operation, one warp. in: [op, as, k, flag, s, il, iu, nx, xe, (key, coef) x nx, ny, ye, (key, coef) x ny];
+// out: [status, words used, range.l, range.u, n_terms, error bits, (key, coef) x n_terms].
+__global__ void __launch_bounds__(32, 1)
+K_tm_op(const uint64_t* __restrict__ in, uint64_t* __restrict__ arena, int arena_words, const uint32_t* __restrict__ binom,
+        uint64_t* __restrict__ out, int out_words) {
+    extern __shared__ uint64_t ab_smem[];
+    Ctx c; ctx_init(c, arena, arena_words, ab_smem, binom);
+    ctx_stage_tables(c);
+    const int op = (int)in[0], as = (int)in[1], k = (int)in[2], flag = (int)in[3];
+    const double s = u2d(in[4]); const Ivl iv = ivl(u2d(in[5]), u2d(in[6]));
+    int p = 7;
+    TM m[2];
+    for (int q = 0; q < 2; ++q) {
+        const int n = (int)in[p++]; const double e = u2d(in[p++]);
+        m[q] = tm_begin(c, as, acc_default());
+        for (int t = 0; t < n; ++t) { Key key = key_zero(); key.w[0] = in[p]; tm_append(c, m[q], key, u2d(in[p + 1])); p += 2; }
+        m[q].e = e;
+        wsync();
+    }
+    const TM& x = m[0]; const TM& y = m[1];
+    TM r = tm_begin(c, as, acc_default());
+    Ivl rng = ivl(0.0, 0.0); int st = ST_OK;
+    switch (op) {
+    case 0: r = tm_add(c, x, y); break;                                            // operator+(TaylorModel,TaylorModel)
+    case 1: r = tm_sub(c, x, y); break;
+    case 2: r = tm_mul(c, x, y); break;
+    case 3: r = tm_copy(c, x); tm_acc(c, r, s); break;                              // x+Float: _acc
+    case 4: r = tm_copy(c, x); tm_acc(c, r, -s); break;                             // x-Float
+    case 5: r = tm_copy(c, x); tm_scal(c, r, s); break;                             // x*Float: _scal
+    case 6: r = tm_copy(c, x); tm_scal(c, r, ivl_div(ivl(1.0), s)); break;          // x/Float: _scal(Interval(1)/c)
+    case 7: r = tm_copy(c, x); tm_acc(c, r, iv); break;
+    case 8: r = tm_copy(c, x); tm_acc(c, r, ivl_neg(iv)); break;
+    case 9: r = tm_copy(c, x); tm_scal(c, r, iv); break;
+    case 10: r = tm_copy(c, x); tm_scal(c, r, ivl_div(1.0, iv, &st)); break;        // x/Interval: _scal(1/c)
+    case 11: r = tm_neg(c, x); break;
+    case 12: if (!tm_intersection(c, x, y, r)) fail(c, ST_DOMAIN); break;
+    case 13: r = tm_split(c, x, k, flag != 0); break;
+    case 14: r = tm_copy(c, x); tm_antidiff(c, r, k); break;
+    case 15: r = tm_rec(c, x); break;
+    case 16: r = tm_sqrt(c, x); break;
+    case 17: r = tm_abs(c, x); break;
+    case 18: r = tm_max(c, x, y); break;
+    case 19: rng = tm_range(c, x); r = tm_copy(c, x); break;
+    default: fail(c, ST_UNSUPPORTED);
+    }
+    if (st != ST_OK) fail(c, st);
+    wsync();
+    if (wlane() == 0) {
+        int w = 4;
+        if (c.status == ST_OK) {
+            if (w + 2 + r.n * AB_TW > out_words) c.status = ST_OUTPUT;
+            else { out[w++] = (uint64_t)r.n; out[w++] = d2u(r.e); for (int t = 0; t < r.n * AB_TW; ++t) out[w++] = c.A.base[r.off + t]; }
+        }
+        out[0] = (uint64_t)c.status; out[1] = (uint64_t)w; out[2] = d2u(rng.l); out[3] = d2u(rng.u);
+    }
+}
+// Interval arithmetic, one thread per operation: in[i] = {op, m, a.l, a.u, b.l, b.u}, out[i] = {r.l, r.u, status}.
+__global__ void K_interval_op(int n, const double* __restrict__ in, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int op = (int)in[6 * i], m = (int)in[6 * i + 1];
+    const Ivl a = ivl(in[6 * i + 2], in[6 * i + 3]), b = ivl(in[6 * i + 4], in[6 * i + 5]);
+    Ivl r = ivl(0.0, 0.0); int st = ST_OK;
+    switch (op) {
+    case 0: r = ivl_add(a, b); break;
+    case 1: r = ivl_sub(a, b); break;
+    case 2: r = ivl_mul(a, b); break;
+    case 3: r = ivl_div(a, b, &st); break;
+    case 4: r = ivl_add(a, b.l); break;
+    case 5: r = ivl_sub(a, b.l); break;
+    case 6: r = ivl_mul(a, b.l); break;
+    case 7: r = ivl_div(a, b.l); break;
+    case 8: r = ivl_sub(a.l, b); break;
+    case 9: r = ivl_div(a.l, b, &st); break;
+    case 10: r = ivl_sqr(a); break;
+    case 11: r = ivl_sqrt(a, &st); break;
+    case 12: r = ivl_pow(a, (unsigned)m); break;
+    case 13: r = ivl_rec(a, &st); break;
+    case 14: r = ivl_abs(a); break;
+    case 15: r = ivl_neg(a); break;
+    case 16: r = ivl_max(a, b); break;
+    case 17: r = ivl_min(a, b); break;
+    default: st = ST_UNSUPPORTED;
+    }
+    out[3 * i] = r.l; out[3 * i + 1] = r.u; out[3 * i + 2] = (double)st;
+}
+
 // ---- rasterise + hash-set insert ------------------------------------------------------------------------------------
 #define AB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
@@ -271,6 +359,18 @@ int dev_launch_integrator_flow_bounds(cudaStream_t st, int n_cells, const int32_
 int dev_launch_integrator_flow(cudaStream_t st, int loc, const double* box, double hmax, int order, uint64_t* arena, int arena_words,
                                const uint32_t* binom, uint64_t* out, int out_words, char* errbuf, int errlen) {
     K_integrator_flow<<<1, 32, AB_SM_WORDS * sizeof(uint64_t), st>>>(loc, box, hmax, order, arena, arena_words, binom, out, out_words);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_tm_op(cudaStream_t st, const uint64_t* in, uint64_t* arena, int arena_words, const uint32_t* binom, uint64_t* out, int out_words,
+                     char* errbuf, int errlen) {
+    K_tm_op<<<1, 32, AB_SM_WORDS * sizeof(uint64_t), st>>>(in, arena, arena_words, binom, out, out_words);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_interval_op(cudaStream_t st, int n, const double* in, double* out, char* errbuf, int errlen) {
+    if (n == 0) return 0;
+    K_interval_op<<<(n + 127) / 128, 128, 0, st>>>(n, in, out);
     CK(cudaGetLastError());
     return 0;
 }

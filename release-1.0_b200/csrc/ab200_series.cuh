@@ -48,7 +48,7 @@ AB_HDN TM tm_rec(Ctx& c, const TM& x) {
 // may differ in the last bit. d only changes if the quotient of logs sits within an ulp of an integer, and the
 // truncation bound (~sweep threshold) is added to an error many orders larger, so results coincide in practice; the
 // parity tests for sqrt systems therefore compare cell sets exactly and boxes to 1e-12 relative width.
-#define AB_MAXSER 48
+#define AB_MAXSER 96
 AB_HDN TM tm_sqrt(Ctx& c, const TM& x) {
     const int m0 = c.A.top;
     Ivl r = tm_range(c, x);

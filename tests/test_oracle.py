@@ -36,3 +36,25 @@ def test_system_tapes_are_what_the_reference_automata_hold(name):
 ])
 def test_oracle_reproduces_committed_goldens(golden, args):
     assert _lines(_run(*args)) == _lines(golden_io._open(golden).read())
+
+
+def test_primitive_kat_vectors_come_from_the_reference_and_hold_its_unit_test_answers():
+    """tests/golden/kat_primitives.txt.gz is the output of oracle/_ref/ref_kat (the reference library itself); it must
+    regenerate byte for byte, and it must contain the literal answers the reference's own unit tests assert
+    (test/test_taylor_model.cpp:176,231-234; test/test_interval.cpp:155,169)."""
+    import gzip
+    text = gzip.open(os.path.join(golden_io.GOLDEN, "kat_primitives.txt.gz"), "rt").read()
+    kat = os.path.join(ROOT, "oracle", "_ref", "ref_kat")
+    if os.path.exists(kat):
+        assert subprocess.run([kat], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=600, check=True).stdout.decode() == text
+    L = text.splitlines()
+    # (1-2x+3x^2 +/-0.75)*(3+2x-4x^2 +/-0.5) = 3-4x+x^2+14x^3-12x^4 +/-10.125
+    i = [k for k, l in enumerate(L) if l.startswith("tm mul as 1")][1]
+    r = L.index("r 5 %s" % float(10.125).hex().replace("0x1.4400000000000p+3", "0x1.44p+3"), i)
+    assert [float.fromhex(l.split()[-1]) for l in L[r + 1:r + 6]] == [3.0, -4.0, 1.0, 14.0, -12.0]
+    # intersection with roundoff: 1.0583333333333331 +/- 0.10833333333333339
+    assert any(l.startswith("r 1 ") and float.fromhex(l.split()[2]) == 0.10833333333333339 for l in L)
+    assert any(l.startswith("t 0 ") and float.fromhex(l.split()[-1]) == 1.0583333333333331 for l in L)
+    # Interval(1)/Interval(3), pow(Interval(3,5),-1) is rec: [0.33333333333333331,0.33333333333333337]
+    iv = [l.split() for l in L if l.startswith("iv div a 0x1p+0 0x1p+0 b 0x1.8p+1 0x1.8p+1")][0]
+    assert (float.fromhex(iv[-2]), float.fromhex(iv[-1])) == (0.33333333333333331, 0.33333333333333337)
