@@ -2,6 +2,7 @@
 #include "ariadne.h"
 #include "workers.h"
 #include "workers_b200.h"
+#include "evolver_b200.h"
 
 #include <cmath>
 #include <cstdio>
@@ -210,6 +211,72 @@ std::pair<HybridDenotableSet,HybridDenotableSet> B200UpperReachEvolveWorker::get
     std::pair<HDS,HDS> result(_to_denotable(reach),_to_denotable(evolve));
     ab200_cellset_free(reach); ab200_cellset_free(evolve);
     return result;
+}
+
+// ---- B2: EvolverInterface seam ------------------------------------------------------------------------------------------
+void B200ImageSetHybridEvolver::_evolution(EnclosureListType& final, EnclosureListType& reachable, EnclosureListType& intermediate,
+        const EnclosureType& initial, const TimeType& time, bool ignore_activations, ContinuousEvolutionDirection direction,
+        Semantics semantics) const {
+    const HybridIOAutomaton* sys=dynamic_cast<const HybridIOAutomaton*>(&this->system());
+    if(!sys) throw std::runtime_error("B200ImageSetHybridEvolver: needs a HybridIOAutomaton");
+    ab200_ctx* ctx=b200_context(*sys).ctx;
+    // the settings of this object (tune_settings or the defaults) become the device tuning; boxes need no grid
+    const std::map<DiscreteLocation,Float>& hmax=this->settings().maximum_step_size();
+    const HybridFloatVector& refw=this->settings().reference_enclosure_widths();
+    HybridSpace space=sys->state_space();
+    for(HybridSpace::const_iterator it=space.begin(); it!=space.end(); ++it) {
+        int li=ab200_location_index(ctx,it->first.name().c_str());
+        double rw[AB200_MAX_DIM]={0}, org[AB200_MAX_DIM]={0}, len[AB200_MAX_DIM];
+        for(int i=0;i<AB200_MAX_DIM;++i) len[i]=1.0;
+        std::map<DiscreteLocation,Float>::const_iterator h=hmax.find(it->first);
+        HybridFloatVector::const_iterator w=refw.find(it->first);
+        if(h==hmax.end() || w==refw.end()) throw std::runtime_error("B200ImageSetHybridEvolver: no settings for location "+it->first.name());
+        for(uint i=0;i<it->second;++i) rw[i]=w->second[i];
+        if(ab200_set_location_tuning(ctx,li,h->second,rw,org,len)!=AB200_OK) throw std::runtime_error(ab200_last_error(ctx));
+    }
+    ab200_settings st; ab200_ctx_get_settings(ctx,&st);
+    st.semantics = (semantics==LOWER_SEMANTICS) ? 1 : 0;
+    st.maximum_enclosure_widths_ratio=this->settings().maximum_enclosure_widths_ratio();
+    if(ab200_set_settings(ctx,&st)!=AB200_OK) throw std::runtime_error(ab200_last_error(ctx));
+
+    const TaylorSet& ts=initial.second;
+    int32_t loc=ab200_location_index(ctx,initial.first.name().c_str());
+    double box[AB200_BOX_STRIDE]={0};
+    for(uint i=0;i<ts.dimension();++i) {
+        Interval c;
+        try { c=recover_cell_interval(ts,i); }
+        catch(std::runtime_error&) {
+            if(semantics==LOWER_SEMANTICS) throw std::runtime_error("B200ImageSetHybridEvolver: LOWER_SEMANTICS needs a box enclosure");
+            c=ts.models()[i].range();                                  // over-approximation: sound for UPPER_SEMANTICS
+        }
+        box[2*i]=c.lower(); box[2*i+1]=c.upper();
+    }
+    ab200_boxlist *rb=0,*fb=0; ab200_status status;
+    int rc=ab200_reach_evolve_boxes(ctx,1,&loc,box,time.continuous_time(),time.discrete_time(),ignore_activations?1:0,
+                                    direction==DIRECTION_FORWARD?0:1,&rb,&fb,&status);
+    switch(rc) {
+        case AB200_OK: break;
+        case AB200_E_SQRT: throw SqrtNumericException(ab200_last_error(ctx));
+        case AB200_E_TIMEOUT: throw TimeoutException();
+        case AB200_E_WORKING_SETS: throw WorkingSetTooLargeException(ab200_last_error(ctx));
+        default: throw std::runtime_error(std::string("libariadne_b200: ")+ab200_last_error(ctx));
+    }
+    std::vector<DiscreteLocation> locs;
+    for(HybridSpace::const_iterator it=space.begin(); it!=space.end(); ++it) locs.push_back(it->first);   // library order
+    ab200_boxlist* lists[2]={rb,fb}; EnclosureListType* outs[2]={&reachable,&final};
+    for(int w=0;w<2;++w) {
+        const uint64_t* off=0; const double* bx=0; const int32_t* bl=0;
+        ab200_boxlist_view(lists[w],&off,&bx,&bl);
+        for(uint64_t k=off[0];k<off[1];++k) {
+            const DiscreteLocation& q=locs[bl[k]];
+            const uint n=space[q];
+            Box b(n);
+            for(uint i=0;i<n;++i) b[i]=Interval(bx[k*AB200_BOX_STRIDE+2*i],bx[k*AB200_BOX_STRIDE+2*i+1]);
+            outs[w]->adjoin(EnclosureType(q,TaylorSet(b)));
+        }
+        ab200_boxlist_free(lists[w]);
+    }
+    (void)intermediate;
 }
 
 // keys -> HybridDenotableSet. A key is (location, lattice index per coordinate at resolution 2^-accuracy of the base grid);

@@ -33,6 +33,7 @@
 #include "springs.h"
 #include "boost-converter.h"
 #include "workers_b200.h"
+#include "evolver_b200.h"
 
 using namespace Ariadne;
 
@@ -217,7 +218,11 @@ int main(int argc, char** argv) {
 
     HybridFloatVector hmad=getHybridMidpointAbsoluteDerivatives(c.sys,c.domain);
     HybridGrid grid=getHybridGrid(hmad,c.domain,false);
-    ImageSetHybridEvolver evolver(c.sys);
+    // b200=1: the same calls through the EvolverInterface seam of the adapter (adapter/evolver_b200.h), i.e. an
+    // ImageSetHybridEvolver whose _evolution runs on libariadne_b200.so
+    B200ImageSetHybridEvolver evolver_b200(c.sys);
+    ImageSetHybridEvolver evolver_stock(c.sys);
+    ImageSetHybridEvolver& evolver = geti(kv,"b200",0) ? static_cast<ImageSetHybridEvolver&>(evolver_b200) : evolver_stock;
     // The analyser tunes its evolver on ReachabilityRestriction::bounding_box(), i.e. the domain widened by one cell
     // while the domain has not been discretised (src/reachability_analyser.cpp:125-142,
     // src/reachability_restriction.cpp:597-621); outer=0 tunes on the plain domain instead.

@@ -400,6 +400,44 @@ def test_reference_analyser_with_b200_worker(tmp_path, config, golden, args):
             assert golden_io.boxes_equal_bits(np.array(mine["sets"][which][lname]), cells), "%s cells of %s in %s" % (which, config, lname)
 
 
+EVOLVER_CASES = [
+    ("vanderpol", "vanderpol_cells_acc6.txt.gz", ["acc=6", "mince=1", "ncells=24", "stride=1050"]),
+    ("bouncingball", "bouncingball_cells_acc5.txt", ["acc=5", "init=-3.0,3.0,0.0,2.0", "ncells=60", "stride=37"]),
+    ("watertank", "watertank_cells_acc6.txt.gz", ["acc=6", "T=3.0", "ncells=24", "stride=14"]),
+]
+
+
+@pytest.mark.parametrize("config,golden,args", EVOLVER_CASES)
+def test_reference_evolver_interface_with_b200_evolution(tmp_path, config, golden, args):
+    """The EvolverInterface seam, compiled (adapter/evolver_b200.h): an ImageSetHybridEvolver whose _evolution runs on the
+    device, driven by the reference's own reach_evolve(enclosure, time, ignore_activations, direction, semantics). Every
+    enclosure it returns must contain the stock evolver's (north_star: "every per-cell final enclosure must contain the
+    reference enclosure"), with the same number of enclosures per location, and be no wider than a few ulps more."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(golden_io.GOLDEN), "..", "oracle", "_ref", "ref_harness")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_harness has not been built (make -C oracle harness)")
+    out = str(tmp_path / "b200_evolver.txt")
+    subprocess.check_call([exe, config, "cells", "b200=1", "out=" + out] + args, timeout=600)
+    mine = golden_io.load_dump(out); ref = golden_io.load_dump(golden)
+    assert len(mine["cells"]) == len(ref["cells"]) > 0
+    n_boxes = 0
+    for cm, cr in zip(mine["cells"], ref["cells"]):
+        assert cm["error"] is None and cm["id"] == cr["id"]
+        for which in ("reach", "final"):
+            assert len(cm[which]) == len(cr[which]), "%s enclosures of cell %d" % (which, cr["id"])
+            for lname in set(cr[which + "_loc"]):
+                a = np.array([b for b, n in zip(cm[which], cm[which + "_loc"]) if n == lname])
+                b = np.array([b for b, n in zip(cr[which], cr[which + "_loc"]) if n == lname])
+                assert a.shape == b.shape, "%s enclosures of cell %d in %s" % (which, cr["id"], lname)
+                lo_m, hi_m, lo_r, hi_r = a[:, 0::2], a[:, 1::2], b[:, 0::2], b[:, 1::2]
+                assert np.all(lo_m <= lo_r) and np.all(hi_m >= hi_r), "containment, cell %d" % cr["id"]
+                tol = 1e-12 * np.maximum(hi_r - lo_r, 0.0) + 64 * np.spacing(np.maximum(np.abs(lo_r), np.abs(hi_r)))
+                assert np.all(lo_r - lo_m <= tol) and np.all(hi_m - hi_r <= tol), "excess width, cell %d" % cr["id"]
+                n_boxes += a.shape[0]
+    assert n_boxes > 0
+
+
 def _load_integrator_golden(name):
     out = {"models": []}
     with open(os.path.join(golden_io.GOLDEN, name)) as f:
