@@ -813,6 +813,7 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
     dom[n] = ivl(0.0, h);
     TM xs[AB_MAXN], usvf[AB_MAXN], yz[AB_MAXN], y[AB_MAXN], ny[AB_MAXN], outs[AB_MAXN];
     // vector-field model on bb: tape over scalings(bb), effectively at the default accuracy
+    cta_align(c, 3);
     #pragma unroll 1
     for (int j = 0; j < n; ++j) xs[j] = tm_scaling(c, n, j, bb[j]);
     #pragma unroll 1
@@ -849,7 +850,9 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
     for (int i = 0; i < n; ++i) AB_DUMP(c, "y0", i, y[i]);
     #pragma unroll 1
     for (int it = 0; it < order; ++it) {
+        cta_align(c, it < 8 ? 4 + 3 * it : 28);
         tm_compose(c, usvf, n, y, n, ny);                 // new_y=compose(vf,y)
+        cta_align(c, it < 8 ? 5 + 3 * it : 28);
         int pout = c.A.top;
         #pragma unroll 1
         for (int i = 0; i < n; ++i) {
@@ -871,6 +874,7 @@ AB_HDN void flow_model(Ctx& c, const TapeOp* ops, const Func* vf, int n, const I
         for (int i = 0; i < n; ++i) AB_DUMP(c, "y", (it + 1) * 10 + i, y[i]);
         if (c.status != ST_OK) break;
     }
+    cta_align(c, 29);
     #pragma unroll 1
     for (int i = 0; i < n; ++i) tm_sweep(c, y[i], 0.0);   // leaves the ambient mode upward
     // model_flow=scale(unit_scaled_flow,b); then split(model_flow,n,true) because the time interval is [0,h]

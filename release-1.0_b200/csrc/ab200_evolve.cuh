@@ -192,10 +192,12 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             double hprop = dmin(remaining, L.max_step);
             Ivl bb[AB_MAXN], dom[AB_MAXN + 1];
             const Func* vf = P.backward ? L.dyn_back : L.dyn;      // get_directed_dynamic (:470)
+            cta_align(c, 1);
             double h = flow_bounds(c, S.ops, vf, n, range, hprop, bb);
             if (c.status != ST_OK) break;
             TM flow[AB_MAXN], fset[AB_MAXN];
             flow_model(c, S.ops, vf, n, range, h, bb, P.temporal_order, flow, dom);
+            cta_align(c, 32);
             flow_apply(c, flow, n, dom, ws.set, p, h, fset);
 #ifdef AB_DEBUG_DUMP
             printf("h %a bb", h); for (int i = 0; i < n; ++i) printf(" %a %a", bb[i].l, bb[i].u); printf("\n");
@@ -211,6 +213,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
             TM tstep = tm_begin(c, p, spacial); tm_append(c, tstep, key_zero(), 1.0);     // time_model(1.0,Box(p))
             TM zero_t = tm_begin(c, p, spacial); tm_append(c, zero_t, key_zero(), 0.0);   // time_model(0.0,Box(p))
             BlockingInfo B;
+            cta_align(c, 34);
             compute_blocking_info(c, S, L, fset, n, p, tstep, spacial, B);
             if (c.status != ST_OK) break;
             if (!enclosure_to_be_discarded(c, S, L, ws.set, n, p, P.lower, P.backward)) {
@@ -225,6 +228,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                 {
                     const int m = c.A.top;
                     TM reach[AB_MAXN];
+                    cta_align(c, 36);
                     reachability_step(c, fset, n, p, zero_t, B.time, spacial, reach);
                     Ivl rb[AB_MAXN];
                     #pragma unroll 1
@@ -237,6 +241,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                 // _computeEvolutionForEvents (:1000-1082); with LOWER semantics only when the blocking event is unique (:544)
                 if (!P.lower || ((B.finishing ? 1 : 0) + B.n_blocking) == 1) {
                 TM ev[AB_MAXN];
+                cta_align(c, 38);
                 integration_step(c, fset, n, p, B.time, spacial, ev);
                 #pragma unroll 1
                 for (int i = 0; i < n; ++i) AB_DUMP(c, "evolved", i, ev[i]);
@@ -249,6 +254,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
                     tm_slide(c, ft, m);
                 }
                 int np = p;
+                cta_align(c, 40);
                 {   // reconditioning (enable_reconditioning)
                     double thr[AB_MAXN];
                     #pragma unroll 1
@@ -313,6 +319,7 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
         if (c.status != ST_OK) break;
         // ---- pop the front, push the successors at the back, re-pack the queue at the bottom of the arena
         if (nq - 1 + ns > st.qcap) { fail(c, ST_WORKING_SETS); break; }
+        cta_align(c, 44);
         wsync();
         // 1. copy the successors to the top in canonical order (their models may be anywhere above qend)
         #pragma unroll 1

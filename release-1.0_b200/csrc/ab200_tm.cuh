@@ -118,6 +118,8 @@ struct Ctx {
     const uint32_t* binom;   // binomial table for monomial ranks (binom_fill)
     int sm_dirty;            // the hash accumulator has written over the dense accumulator's area since it was last emptied
     double flops;            // algorithmic FP64 operations of the reference algorithm so far (AB_FLOPS)
+    // phase alignment of the warps of a CTA (K_evolve): shared progress words, warps in the CTA, this warp, loop iteration
+    int* al_phase; int al_n; int al_warp; int al_iter;
 };
 #define AB_BINOM_N 64
 #define AB_BINOM_K 24
@@ -132,12 +134,46 @@ struct BinomTab { uint32_t t[AB_BINOM_N * AB_BINOM_K]; BinomTab() { binom_fill(t
 inline const uint32_t* binom_host() { static BinomTab b; return b.t; }
 AB_HD void ctx_init(Ctx& c, uint64_t* arena, int limit, uint64_t* sm, const uint32_t* binom) {
     c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom; c.sm_dirty = 1; c.flops = 0.0;
+    c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0;
 }
 // host-side callers (no warp, no shared area)
 inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
     c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1; c.flops = 0.0;
+    c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0;
 }
 
+// Phase alignment (device, CTAs of several warps): the warps of a CTA evolve different cells through the same sequence of
+// primitives; meeting at the main stages of a step keeps them in the same few kilobytes of code, which is what the SM's
+// instruction cache can hold. A warp publishes (loop iteration, stage) and waits until no warp of its CTA is behind that
+// stage. A warp that skips a stage publishes a later one, and the end of the loop iteration is stage 63, so the warp
+// that is furthest behind never waits and nobody waits for ever. Pure scheduling: no arithmetic depends on it.
+#ifndef AB_ALIGN_SPINS
+#define AB_ALIGN_SPINS (1 << 18)
+#endif
+AB_HD void cta_publish(Ctx& c, int stage) {
+#if defined(__CUDA_ARCH__)
+    if (c.al_n > 1 && c.lane == 0) ((volatile int*)c.al_phase)[c.al_warp] = (c.al_iter << 6) | stage;
+#endif
+}
+AB_HDN void cta_align(Ctx& c, int stage) {
+#if defined(__CUDA_ARCH__)
+    if (c.al_n <= 1) return;
+    if (stage > 62) stage = 62;
+    const int my = (c.al_iter << 6) | stage;
+    volatile int* ph = (volatile int*)c.al_phase;
+    __syncwarp();
+    if (c.lane == 0) ph[c.al_warp] = my;
+    int spins = 0;
+    for (;;) {
+        int lo = my;
+        #pragma unroll 1
+        for (int w = 0; w < c.al_n; ++w) { const int v = ph[w]; if (v < lo) lo = v; }
+        if (lo >= my || ++spins > AB_ALIGN_SPINS) break;
+        __nanosleep(40);
+    }
+    __syncwarp();
+#endif
+}
 AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[i]; }
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 #ifdef AB_MUL_HIST
@@ -337,7 +373,7 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
 // hash accumulator (index | keys | coefficients) otherwise. When even that is outgrown the hash accumulator is rebuilt in the
 // free part of the arena (same code, generic pointers).
 #ifndef AB_SM_ACCW
-#define AB_SM_ACCW 1536
+#define AB_SM_ACCW 1024
 #endif
 #define AB_SM_BTABW 128
 // Dense accumulator: coefficients of AB_SM_DENSE ranks, then their keys. With at most 3 variables a key is the upper half
@@ -346,11 +382,11 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
 #define AB_SM_DENSE (2 * AB_SM_ACCW / 3)
 #define AB_BTAB_STRIDE 36                               // rank-table row: sums of exponents 0..35
 #ifndef AB_SM_NIDX
-#define AB_SM_NIDX 1024
+#define AB_SM_NIDX 512
 #endif
 #define AB_SM_CAP ((AB_SM_ACCW - AB_SM_NIDX / 2) / (AB_KW + 1))
 #ifndef AB_SM_G16
-#define AB_SM_G16 4096
+#define AB_SM_G16 2048
 #endif
 #ifndef AB_SM_YCAP
 #define AB_SM_YCAP 128
