@@ -110,6 +110,21 @@ std::string b200_system_text(const HybridIOAutomaton& sys) {
     return f.str();
 }
 
+std::string b200_constraint_text(const HybridIOAutomaton& sys, const DiscreteLocation& loc, const Box& domain,
+                                 const List<RealExpression>& functions, const Box& codomain) {
+    std::ostringstream f; char buf[64];
+    RealSpace cs=sys.continuous_state_space(loc);
+    std::map<std::string,int> var_index;
+    for(uint i=0;i<cs.size();++i) var_index[cs.variable(i).name()]=i;
+    f<<"set "<<loc.name()<<" m "<<functions.size()<<"\n  domain";
+    for(uint i=0;i<domain.size();++i) { snprintf(buf,sizeof(buf)," %a %a",domain[i].lower(),domain[i].upper()); f<<buf; }
+    f<<"\n  codomain";
+    for(uint i=0;i<codomain.size();++i) { snprintf(buf,sizeof(buf)," %a %a",codomain[i].lower(),codomain[i].upper()); f<<buf; }
+    f<<"\n";
+    for(uint i=0;i<functions.size();++i) { f<<"  f "<<i; emit_tape(f,functions[i],var_index); f<<" ;\n"; }
+    return f.str();
+}
+
 namespace {
 
 // One device context per automaton (by name), created on first use; lives for the process.

@@ -23,6 +23,12 @@ namespace Ariadne {
 // std::set<DiscreteEvent> order, which is the order ab200_set_system_text requires.
 std::string b200_system_text(const HybridIOAutomaton& sys);
 
+// A constraint-set initial set in one location, { x in domain : functions(x) in codomain } (BoundedConstraintSet,
+// include/function_set.h:143-200), as the `set` block ab200_analyser_discretise_constraint reads. The functions are given
+// as the expressions the set was built from (a VectorFunction cannot be walked through the public API).
+std::string b200_constraint_text(const HybridIOAutomaton& sys, const DiscreteLocation& loc, const Box& domain,
+                                 const List<RealExpression>& functions, const Box& codomain);
+
 class B200UpperReachEvolveWorker
 {
   public:

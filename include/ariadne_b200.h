@@ -202,6 +202,16 @@ int  ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const
 int64_t ab200_analyser_cells_evolved(const ab200_analyser* an);
 /* Enumerate a cell set as the reference does (maximal dyadic cells, boxes by bisection, src/bdd_set.cpp:800-891).
  * Pass boxes==NULL to query the count. */
+/* Constraint-set initial sets: ReachabilityRestriction::outer_intersection_with(HybridBoundedConstraintSet)
+ * (src/reachability_restriction.cpp:413-434,522-533) with ConstraintSet::overlaps / covers (src/function_set.cpp:218-235,
+ * include/geometry.h:93-109) deciding every cell, i.e. what upper_reach / outer_chain_reach do with their initial_set
+ * argument before the first lap. `text` holds one `set` per location (domain box, m constraint functions as op tapes over the
+ * location's variables, codomain box; release-1.0_b200/csrc/ab200_system.h). The *_from calls run the analyses from such a set. */
+int  ab200_analyser_discretise_constraint(ab200_analyser* an, const char* text, ab200_cellset** out);
+int  ab200_analyser_upper_reach_evolve_from(ab200_analyser* an, const ab200_cellset* initial, double t_continuous, int32_t max_events, int mince,
+                                            ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status);
+int  ab200_analyser_outer_chain_reach_from(ab200_analyser* an, const ab200_cellset* initial, int32_t direction,
+                                           ab200_cellset** reach_out, ab200_status* status);
 int  ab200_analyser_enumerate(const ab200_analyser* an, const ab200_cellset* cs, int mince, uint64_t* count,
                               int32_t* locs, double* boxes);
 

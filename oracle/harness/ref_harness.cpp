@@ -49,6 +49,7 @@ struct Config {
     double T;
     int events;
     bool chain;
+    std::string cons_text;      // the constraint-set initial set as text for ab200_analyser_discretise_constraint (cons=...)
 };
 
 // van der Pol oscillator, mu=1: x'=y, y'=mu(1-x^2)y-x  (system of examples/vanderpol.cc:36-54)
@@ -160,6 +161,27 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
         fprintf(stderr,"unknown config %s\n",name.c_str()); exit(2);
     }
     if(kv.count("chain")) c.chain=geti(kv,"chain",0)!=0;
+    if(kv.count("cons")) {
+        // Constraint-set initial set in the first location: { x in init box : f(x) in codomain } with
+        //   cons=disc   f = (x0-cx)^2 + (x1-cy)^2, codomain [-1, r^2]       (centre = cc=cx,cy; r = cr)
+        //   cons=band   f = (x0 + x1, x0*x1),     codomain [slo,shi] x [plo,phi]  (cb=slo,shi,plo,phi)
+        DiscreteLocation loc=c.sys.modes().front().location();
+        RealSpace sp=c.sys.continuous_state_space(loc);
+        Box dom=c.initial[loc].domain();
+        List<RealExpression> fs; Box cod;
+        RealExpression x0(sp.variable(0)), x1(sp.variable(1));
+        if(kv["cons"]=="disc") {
+            Box cc=box_from(kv,"cc",Box(1,1.2,1.3)); double r=getd(kv,"cr",0.25);
+            fs.append(Ariadne::sqr(x0-cc[0].lower())+Ariadne::sqr(x1-cc[0].upper()));
+            cod=Box(1,-1.0,r*r);
+        } else {
+            Box cb=box_from(kv,"cb",Box(2,2.2,2.6,1.3,1.7));
+            fs.append(x0+x1); fs.append(x0*x1);
+            cod=cb;
+        }
+        c.initial[loc]=BoundedConstraintSet(dom,VectorFunction(fs,sp),cod);
+        c.cons_text="constraints\n"+b200_constraint_text(c.sys,loc,dom,fs,cod);
+    }
     return c;
 }
 
@@ -337,6 +359,13 @@ int main(int argc, char** argv) {
         return 0;
     }
     fprintf(out,"seconds %.3f err '%s'\n",secs,err.c_str());
+    if(!c.cons_text.empty()) {
+        // the initial cells of the constraint set (ReachabilityRestriction::outer_intersection_with) and its text form
+        std::stringstream ss(c.cons_text); std::string line;
+        while(std::getline(ss,line)) fprintf(out,"cons| %s\n",line.c_str());
+        ReachabilityRestriction rr(c.domain,grid,c.acc);
+        dump_set(out,"initial",rr.outer_intersection_with(c.initial));
+    }
     dump_set(out,"reach",reach);
     dump_set(out,"evolve",evolve);
     return 0;

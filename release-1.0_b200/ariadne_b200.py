@@ -35,7 +35,7 @@ EXPORTS = [
     "ab200_boxlist_view", "ab200_boxlist_free", "ab200_flow_bounds", "ab200_analyser_create", "ab200_analyser_destroy",
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
     "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
-    "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free", "ab200_taylor_model_op", "ab200_interval_op",
+    "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free", "ab200_taylor_model_op", "ab200_interval_op", "ab200_analyser_discretise_constraint", "ab200_analyser_upper_reach_evolve_from", "ab200_analyser_outer_chain_reach_from",
 ]
 
 
@@ -88,6 +88,9 @@ def load_library():
     lib.ab200_set_settings.argtypes = [vp, P(Settings)]; lib.ab200_set_settings.restype = C.c_int
     lib.ab200_set_location_tuning.argtypes = [vp, i32, dbl, P(dbl), P(dbl), P(dbl)]; lib.ab200_set_location_tuning.restype = C.c_int
     lib.ab200_set_accuracy.argtypes = [vp, i32]; lib.ab200_set_accuracy.restype = C.c_int
+    lib.ab200_analyser_discretise_constraint.argtypes = [vp, C.c_char_p, P(vp)]; lib.ab200_analyser_discretise_constraint.restype = C.c_int
+    lib.ab200_analyser_upper_reach_evolve_from.argtypes = [vp, vp, dbl, i32, C.c_int, P(vp), P(vp), P(Status)]; lib.ab200_analyser_upper_reach_evolve_from.restype = C.c_int
+    lib.ab200_analyser_outer_chain_reach_from.argtypes = [vp, vp, i32, P(vp), P(Status)]; lib.ab200_analyser_outer_chain_reach_from.restype = C.c_int
     lib.ab200_taylor_model_op.argtypes = [vp, i32, i32, i32, P(C.c_uint8), P(dbl), dbl, i32, P(C.c_uint8), P(dbl), dbl, i32, i32, dbl, P(dbl), P(dbl), P(vp)]
     lib.ab200_taylor_model_op.restype = C.c_int
     lib.ab200_interval_op.argtypes = [vp, i32, P(dbl), P(dbl)]; lib.ab200_interval_op.restype = C.c_int
@@ -468,6 +471,27 @@ class HybridReachabilityAnalyser(object):
         locs, boxes = self._initial(initial_set)
         r = C.c_void_p()
         self.evolver._check(self.lib.ab200_analyser_discretise(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), C.byref(r)))
+        return self._wrap(r)
+
+    def discretise_constraint(self, text):
+        """outer_intersection_with(HybridBoundedConstraintSet): the initial cells of a constraint-set initial set."""
+        r = C.c_void_p()
+        self.evolver._check(self.lib.ab200_analyser_discretise_constraint(self.handle, text.encode(), C.byref(r)))
+        return self._wrap(r)
+
+    def upper_reach_evolve_from(self, initial_cells, time, max_events=5, mince=False):
+        r = C.c_void_p(); e = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_analyser_upper_reach_evolve_from(self.handle, initial_cells._handle, float(time), int(max_events), int(bool(mince)),
+                                                             C.byref(r), C.byref(e), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
+        return self._wrap(r), self._wrap(e)
+
+    def outer_chain_reach_from(self, initial_cells, backward=False):
+        r = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_analyser_outer_chain_reach_from(self.handle, initial_cells._handle, int(bool(backward)), C.byref(r), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
         return self._wrap(r)
 
     def cells_evolved(self):

@@ -513,10 +513,94 @@ extern "C" int ab200_analyser_discretise(ab200_analyser* an, uint64_t n_init, co
 }
 static ab200_cellset* to_cellset(const HybridCells& h) { ab200_cellset* cs = ab200_cellset_new(); join_keys(h, ab200_cellset_keys(cs)); return cs; }
 
-extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
-                                                 double T, int32_t max_events, int mince,
-                                                 ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
-    if (!an || !reach_out || !evolve_out) return AB200_E_ARGUMENT;
+// ---- constraint-set initial sets ---------------------------------------------------------------------------------------
+// ReachabilityRestriction::outer_intersection_with(HybridBoundedConstraintSet) (src/reachability_restriction.cpp:522-533):
+// per location the cells of the set's domain box, outer-restricted to the constraint
+// (BDDTreeSet::outer_restrict(OpenSetInterface), src/bdd_set.cpp:589-637,1670-1686: a cell is dropped when the set
+// definitely does not overlap it, kept whole when the set definitely covers it, kept at the leaves otherwise), then the
+// analyser's own restriction. ConstraintSet::overlaps / covers are src/function_set.cpp:218-235: overlaps through the
+// subdividing test of include/geometry.h:93-109 to a tolerance of radius(codomain)/8, covers by one interval evaluation.
+namespace {
+enum { T_FALSE = 0, T_TRUE = 1, T_INDET = 2 };
+struct ConstraintEval {
+    const HostConstraints* H; const ConstraintSetDesc* S; int n;
+    void image(const Ivl* d, Ivl* out, int* st) const {
+        Ctx c; ctx_init_host(c, 0, 0);
+        for (int i = 0; i < S->m; ++i) out[i] = eval_ivl(c, H->ops.data(), S->f[i], d);
+        if (c.status != ST_OK) *st = c.status;
+    }
+    // disjoint(d, f, b, eps) of include/geometry.h:93-109
+    int disjoint(const Ivl* d, double eps, int* st, int depth) const {
+        Ivl fd[AB_MAXN], fc[AB_MAXN], mid[AB_MAXN];
+        image(d, fd, st);
+        for (int i = 0; i < n; ++i) mid[i] = ivl(ivl_mid(d[i]));
+        image(mid, fc, st);
+        for (int i = 0; i < S->m; ++i) { const Ivl b = ivl(S->codomain[2 * i], S->codomain[2 * i + 1]); if (fd[i].l > b.u || fd[i].u < b.l) return T_TRUE; }
+        bool in = true;
+        for (int i = 0; i < S->m; ++i) { const Ivl b = ivl(S->codomain[2 * i], S->codomain[2 * i + 1]); if (!(fc[i].l > b.l && fc[i].u < b.u)) in = false; }
+        if (in) return T_FALSE;
+        double dmax = 0.0; int imax = 0;                                   // Box::radius (include/box.h:93-99), irmax (geometry.h:39-50)
+        for (int i = 0; i < n; ++i) { const double w = ivl_width(d[i]); if (w > dmax) { dmax = w; imax = i; } }
+        const double half = dmax / 2, rad = half > 0 ? half * (1 + 2e-16) : half * (1 - 2e-16);   // up(dmax/2), include/numeric.h:111
+        if (eps == 0 || rad < eps || depth > 60) return T_INDET;
+        Ivl l[AB_MAXN], r[AB_MAXN];
+        for (int i = 0; i < n; ++i) { l[i] = d[i]; r[i] = d[i]; }
+        const double cm = ivl_mid(d[imax]);                                 // med_approx
+        l[imax].u = cm; r[imax].l = cm;
+        const int a = disjoint(l, eps, st, depth + 1), b = disjoint(r, eps, st, depth + 1);
+        if (a == T_FALSE || b == T_FALSE) return T_FALSE;                  // tribool &&
+        if (a == T_TRUE && b == T_TRUE) return T_TRUE;
+        return T_INDET;
+    }
+    int check(const double* box, int* st) const {
+        Ivl d[AB_MAXN];
+        for (int i = 0; i < n; ++i) d[i] = ivl(box[2 * i], box[2 * i + 1]);
+        double rc = 0.0;                                                    // radius(codomain): max of the interval radii (src/vector.cpp:312-319)
+        for (int i = 0; i < S->m; ++i) rc = std::max(rc, ivl_rad(ivl(S->codomain[2 * i], S->codomain[2 * i + 1])));
+        if (disjoint(d, rc / 8, st, 0) == T_TRUE) return 0;                // !possibly(overlaps)
+        Ivl fd[AB_MAXN];
+        image(d, fd, st);
+        bool covers = true;                                                 // definitely(approximate_inside(f(bx),codomain))
+        for (int i = 0; i < S->m; ++i) if (!(fd[i].l > S->codomain[2 * i] && fd[i].u < S->codomain[2 * i + 1])) covers = false;
+        return covers ? 1 : 2;
+    }
+};
+}
+extern "C" int ab200_analyser_discretise_constraint(ab200_analyser* an, const char* text, ab200_cellset** out) {
+    if (!an || !text || !out) return AB200_E_ARGUMENT;
+    *out = 0;
+    const HostSystem* hs = ab200_ctx_system(an->ctx);
+    HostConstraints H;
+    std::string err = parse_constraints(text, *hs, H);
+    if (!err.empty()) { ab200_ctx_set_error(an->ctx, ("constraint set: " + err).c_str()); return AB200_E_ARGUMENT; }
+    HybridCells initial = empty_cells(an);
+    bool ok = true; int st = ST_OK;
+    for (size_t k = 0; k < H.sets.size(); ++k) {
+        const ConstraintSetDesc& S = H.sets[k];
+        const int l = S.loc, n = hs->desc.loc[l].n;
+        bool empty = false;
+        for (int i = 0; i < n; ++i) if (S.domain[2 * i] > S.domain[2 * i + 1]) empty = true;
+        if (empty) continue;                                                // has_empty(loc): an empty set in this location
+        double dom[AB200_BOX_STRIDE] = {0};
+        for (int i = 0; i < 2 * n; ++i) dom[i] = S.domain[i];
+        CellSet s(an->grid[l], an->K, l);
+        ok = s.adjoin_outer_approximation(dom) && ok;                       // _insert_domain_discretisation
+        if (S.m > 0) {                                                      // !unconstrained()
+            ConstraintEval E; E.H = &H; E.S = &S; E.n = n;
+            s.outer_restrict([&](const double* box) { return E.check(box, &st); });
+        }
+        initial[l].adjoin(s);
+    }
+    if (st != ST_OK) { ab200_ctx_set_error(an->ctx, "constraint function cannot be evaluated on a cell"); return st; }
+    ok = apply_restriction(an, initial) && ok;
+    if (!ok) { ab200_ctx_set_error(an->ctx, "initial set or domain lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    *out = to_cellset(initial);
+    return AB200_OK;
+}
+
+// upper_reach_evolve (src/reachability_analyser.cpp:309-377) from an already discretised initial set
+static int upper_reach_evolve_cells(ab200_analyser* an, const HybridCells& initial, double T, int32_t max_events, int mince,
+                                    ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
     *reach_out = 0; *evolve_out = 0;
     an->cells_evolved = 0;
     ab200_status st; memset(&st, 0, sizeof(st)); st.cell = -1;
@@ -524,9 +608,7 @@ extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_
     unsigned time_steps = (unsigned)(T / lock);
     double remaining = T - time_steps * lock;
     if (time_steps == 0) { time_steps = 1; remaining = 0.0; lock = T; }
-    HybridCells initial;
-    int rc = discretise_initial(an, n_init, loc, boxes, initial);
-    if (rc != AB200_OK) return rc;
+    int rc;
     HybridCells reach = empty_cells(an), evolve = empty_cells(an), found, next;
     // first lap: evolver->orbit per initial enclosure (:348-353)
     rc = lap(an, initial, mince, lock, max_events, 0, 0, found, next, &st);
@@ -549,6 +631,23 @@ extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_
     *reach_out = to_cellset(reach); *evolve_out = to_cellset(evolve);
     if (status) *status = st;
     return AB200_OK;
+}
+extern "C" int ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
+                                                 double T, int32_t max_events, int mince,
+                                                 ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    if (!an || !reach_out || !evolve_out) return AB200_E_ARGUMENT;
+    *reach_out = 0; *evolve_out = 0;
+    HybridCells initial;
+    int rc = discretise_initial(an, n_init, loc, boxes, initial);
+    if (rc != AB200_OK) return rc;
+    return upper_reach_evolve_cells(an, initial, T, max_events, mince, reach_out, evolve_out, status);
+}
+extern "C" int ab200_analyser_upper_reach_evolve_from(ab200_analyser* an, const ab200_cellset* initial_cells, double T, int32_t max_events, int mince,
+                                                      ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    if (!an || !initial_cells || !reach_out || !evolve_out) return AB200_E_ARGUMENT;
+    HybridCells initial = empty_cells(an);
+    split_keys(an, ab200_cellset_keys(const_cast<ab200_cellset*>(initial_cells)), initial);
+    return upper_reach_evolve_cells(an, initial, T, max_events, mince, reach_out, evolve_out, status);
 }
 
 // lower_reach_evolve (src/reachability_analyser.cpp:230-275): the midpoints of the discretised initial cells
@@ -632,15 +731,29 @@ extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_
     return AB200_OK;
 }
 
+static int outer_chain_reach_cells(ab200_analyser* an, HybridCells current, int32_t direction, ab200_cellset** reach_out, ab200_status* status);
 extern "C" int ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
                                                 int32_t direction, ab200_cellset** reach_out, ab200_status* status) {
     if (!an || !reach_out) return AB200_E_ARGUMENT;
     *reach_out = 0;
-    an->cells_evolved = 0;
-    ab200_status st; memset(&st, 0, sizeof(st)); st.cell = -1;
     HybridCells current;
     int rc = discretise_initial(an, n_init, loc, boxes, current);
     if (rc != AB200_OK) return rc;
+    return outer_chain_reach_cells(an, current, direction, reach_out, status);
+}
+extern "C" int ab200_analyser_outer_chain_reach_from(ab200_analyser* an, const ab200_cellset* initial_cells, int32_t direction,
+                                                     ab200_cellset** reach_out, ab200_status* status) {
+    if (!an || !initial_cells || !reach_out) return AB200_E_ARGUMENT;
+    HybridCells current = empty_cells(an);
+    split_keys(an, ab200_cellset_keys(const_cast<ab200_cellset*>(initial_cells)), current);
+    return outer_chain_reach_cells(an, current, direction, reach_out, status);
+}
+// outer_chain_reach (src/reachability_analyser.cpp:380-493) from an already discretised initial set
+static int outer_chain_reach_cells(ab200_analyser* an, HybridCells current, int32_t direction, ab200_cellset** reach_out, ab200_status* status) {
+    *reach_out = 0;
+    an->cells_evolved = 0;
+    ab200_status st; memset(&st, 0, sizeof(st)); st.cell = -1;
+    int rc;
     HybridCells reach = empty_cells(an), fin = empty_cells(an), new_reach, new_final;
     int guard = 0;
     while (!all_empty(current) && guard++ < 100000) {

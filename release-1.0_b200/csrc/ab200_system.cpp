@@ -145,4 +145,57 @@ std::string parse_system(const std::string& text, HostSystem& out) {
     return "";
 }
 
+
+static double parse_bound(const std::string& t) {
+    if (t == "inf" || t == "+inf") return 1.0 / 0.0;
+    if (t == "-inf") return -1.0 / 0.0;
+    return strtod(t.c_str(), 0);
+}
+
+std::string parse_constraints(const std::string& text, const HostSystem& sys, HostConstraints& out) {
+    std::string clean; clean.reserve(text.size());
+    bool incomment = false;
+    for (size_t i = 0; i < text.size(); ++i) {
+        char ch = text[i];
+        if (ch == '#') incomment = true;
+        if (ch == '\n') incomment = false;
+        if (!incomment) clean.push_back(ch);
+    }
+    std::istringstream in(clean);
+    out.sets.clear(); out.ops.clear();
+    // the tapes are parsed into a scratch SystemDesc (parse_tape appends to its op array) and copied out
+    SystemDesc* scratch = new SystemDesc();
+    memset(scratch, 0, sizeof(SystemDesc));
+    std::string tok, err;
+    int cur = -1;
+    while (in >> tok) {
+        if (tok == "constraints") continue;
+        if (tok == "set") {
+            std::string name, k; int m;
+            in >> name >> k >> m;
+            if (k != "m" || m < 0 || m > AB_MAXN) { delete scratch; return "bad set header"; }
+            int li = -1;
+            for (size_t l = 0; l < sys.loc_names.size(); ++l) if (sys.loc_names[l] == name) li = (int)l;
+            if (li < 0) { delete scratch; return "unknown location " + name; }
+            ConstraintSetDesc d; memset(&d, 0, sizeof(d)); d.loc = li; d.m = m;
+            out.sets.push_back(d); cur = (int)out.sets.size() - 1;
+        } else if (cur < 0) { delete scratch; return "expected 'set' before " + tok; }
+        else if (tok == "domain") {
+            const int n = sys.desc.loc[out.sets[cur].loc].n;
+            for (int i = 0; i < 2 * n; ++i) { std::string t; if (!(in >> t)) { delete scratch; return "short domain"; } out.sets[cur].domain[i] = parse_bound(t); }
+        } else if (tok == "codomain") {
+            for (int i = 0; i < 2 * out.sets[cur].m; ++i) { std::string t; if (!(in >> t)) { delete scratch; return "short codomain"; } out.sets[cur].codomain[i] = parse_bound(t); }
+        } else if (tok == "f") {
+            int i; in >> i;
+            if (i < 0 || i >= out.sets[cur].m) { delete scratch; return "bad function index"; }
+            if (!parse_tape(in, *scratch, out.sets[cur].f[i], sys.desc.loc[out.sets[cur].loc].n, err)) { delete scratch; return err; }
+        } else { delete scratch; return "unknown token " + tok; }
+    }
+    for (size_t k = 0; k < out.sets.size(); ++k) for (int i = 0; i < out.sets[k].m; ++i)
+        if (out.sets[k].f[i].end <= out.sets[k].f[i].begin) { delete scratch; return "missing constraint function"; }
+    out.ops.assign(scratch->ops, scratch->ops + scratch->n_ops);
+    delete scratch;
+    return "";
+}
+
 } // namespace ab200

@@ -32,4 +32,24 @@ struct HostSystem {
 // Returns an empty string on success, else an error message.
 std::string parse_system(const std::string& text, HostSystem& out);
 
+// A HybridBoundedConstraintSet (include/hybrid_set.h:367-410): per location a domain box, a function (m tapes over the
+// location's n variables) and a codomain box; m = 0 is the plain box set. Text form:
+//   constraints
+//   set <location name> m <m>
+//     domain <lo> <hi> ... (n pairs)
+//     codomain <lo> <hi> ... (m pairs; inf / -inf allowed)
+//     f <i> <tape...> ;
+struct ConstraintSetDesc {
+    int loc;
+    int m;
+    double domain[2 * AB_MAXN];
+    double codomain[2 * AB_MAXN];
+    Func f[AB_MAXN];
+};
+struct HostConstraints {
+    std::vector<ConstraintSetDesc> sets;
+    std::vector<TapeOp> ops;
+};
+std::string parse_constraints(const std::string& text, const HostSystem& sys, HostConstraints& out);
+
 } // namespace ab200

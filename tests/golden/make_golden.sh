@@ -64,3 +64,9 @@ D=${TMPDIR:-/tmp}
 $H watertank cells acc=6 T=3.0 ncells=24 stride=14 disc=2 out=$D/wt6.txt && python $G/fingerprint_unions.py $D/wt6.txt $G/watertank_cells_acc6.txt && gzip -9 -f -n $G/watertank_cells_acc6.txt
 $H springs cells acc=10 T=6.0 ncells=2 disc=2 out=$D/sp10.txt && python $G/fingerprint_unions.py $D/sp10.txt $G/springs_cells_acc10.txt && gzip -9 -f -n $G/springs_cells_acc10.txt
 $H boost cells acc=6 chain=0 T=0.011 disc=2 out=$D/bo6.txt && python $G/fingerprint_unions.py $D/bo6.txt $G/boost_cells_acc6.txt && gzip -9 -f -n $G/boost_cells_acc6.txt
+# ---- constraint-set initial sets (ReachabilityRestriction::outer_intersection_with(HybridBoundedConstraintSet),
+# src/reachability_restriction.cpp:413-434,522-533): a disc and a two-function band as initial sets of upper_reach_evolve and
+# outer_chain_reach; the dumps hold the constraint as text (cons| lines), the initial cells and the analysis result
+$H vanderpol reach acc=4 cons=disc init=0.9,1.5,1.0,1.6 laps=1 out=$G/vanderpol_cons_disc_acc4.txt
+$H vanderpol reach acc=6 cons=band init=0.5,2.0,0.5,2.0 T=0.02 out=$G/vanderpol_cons_band_acc6.txt
+$H bouncingball reach acc=5 cons=disc init=-0.5,0.5,1.5,2.0 cc=0.0,1.8 cr=0.2 out=$G/bouncingball_cons_disc_chain_acc5.txt

@@ -63,7 +63,9 @@ def load_dump(name):
                 # fingerprint of a large union set (tests/golden/fingerprint_unions.py): count + sha256 of the sorted boxes
                 out.setdefault("fp", {}).setdefault(k[:-3], {})[t[2]] = {"cells": int(t[4]), "sha256": t[6]}
                 cur_set = None
-            elif k in ("reach", "evolve", "ureach", "ufinal"):
+            elif k == "cons|":
+                out.setdefault("cons_text", []).append(line[len("cons| "):])
+            elif k in ("reach", "evolve", "ureach", "ufinal", "initial"):
                 cur_set = out["sets"].setdefault(k, {}).setdefault(t[2], [])
             elif k == "c" and cur_set is not None:
                 cur_set.append([_f(x) for x in t[1:]])

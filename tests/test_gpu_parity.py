@@ -258,6 +258,40 @@ def test_baseline_depth_sampled_cells_bit_exact(pkg, system, name, domain, arena
         an.close()
 
 
+CONSTRAINT_CASES = [
+    ("vanderpol", "vanderpol_cons_disc_acc4.txt", [-3.0, 3.0, -3.0, 3.0], 131072),
+    ("vanderpol", "vanderpol_cons_band_acc6.txt", [-3.0, 3.0, -3.0, 3.0], 32768),
+    ("bouncingball", "bouncingball_cons_disc_chain_acc5.txt", [-10.1, 10.1, -0.1, 2.1], 65536),
+]
+
+
+@pytest.mark.parametrize("system,name,domain,arena", CONSTRAINT_CASES)
+def test_constraint_set_initial_sets_identical_cells(pkg, system, name, domain, arena):
+    """Initial sets given as constraint sets { x in box : f(x) in codomain } (HybridBoundedConstraintSet): the initial cells
+    (outer_intersection_with: ConstraintSet::overlaps by subdivision, covers by one evaluation, decided cell by cell down the
+    paving) and the upper_reach_evolve / outer_chain_reach run from them, against the compiled reference."""
+    d = golden_io.load_dump(name)
+    an = pkg.HybridReachabilityAnalyser(_system(system), domain, d["config"]["acc"], settings={"arena_words": arena})
+    try:
+        initial = an.discretise_constraint("".join(d["cons_text"]))
+        il, ib = an.enumerate(initial)
+        for lname, ref in d["sets"]["initial"].items():
+            assert golden_io.boxes_equal_bits(ib[il == an.evolver.location(lname)], ref), "initial cells in %s" % lname
+        assert len(ib) == sum(len(v) for v in d["sets"]["initial"].values()) > 0
+        if d["config"]["chain"]:
+            reach = an.outer_chain_reach_from(initial)
+            sets = {"reach": reach}
+        else:
+            reach, evolve = an.upper_reach_evolve_from(initial, d["config"]["T"], d["config"]["events"])
+            sets = {"reach": reach, "evolve": evolve}
+        for which, cs in sets.items():
+            cl, cb = an.enumerate(cs)
+            for lname, ref in d["sets"][which].items():
+                assert golden_io.boxes_equal_bits(cb[cl == an.evolver.location(lname)], ref), "%s cells in %s" % (which, lname)
+    finally:
+        an.close()
+
+
 def test_flow_bounds_facade(pkg):
     d = golden_io.load_dump("vanderpol_cells_acc6.txt.gz")
     ev = _evolver(pkg, d)
