@@ -137,6 +137,12 @@ std::string parse_system(const std::string& text, HostSystem& out) {
     }
     // DiscreteEvent orders by its string id and the evolver's finishing event is DiscreteEvent(-2) == "e-2"
     // (include/discrete_event.h:39-48, src/hybrid_evolver-image.cpp:86-88)
+    // The evolver resolves ties between blocking events and orders the successors of a step by event INDEX, where the
+    // reference iterates std::map / std::set<DiscreteEvent>, i.e. by name: the events of a location must come sorted by name.
+    for (int l = 0; l < out.desc.n_locs; ++l)
+        for (int e = 1; e < out.desc.loc[l].n_events; ++e)
+            if (!(out.event_names[l][e - 1] < out.event_names[l][e]))
+                return "events of location " + out.loc_names[l] + " are not in ascending name order (" + out.event_names[l][e - 1] + ", " + out.event_names[l][e] + ")";
     for (int l = 0; l < out.desc.n_locs; ++l) {
         int r = 0;
         for (int e = 0; e < out.desc.loc[l].n_events; ++e) if (out.event_names[l][e] < std::string("e-2")) ++r;

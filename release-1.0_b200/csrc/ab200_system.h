@@ -14,6 +14,8 @@
 //       guard <tape...> ;
 //       lie <tape...> ;                  (transitions only: Lie derivative of the guard along the dynamics)
 //       reset <i> <tape...> ;            (transitions only)
+//   The events of a location must be listed in ascending order of their names (the order of std::set<DiscreteEvent>, which the
+//   reference's evolver iterates; adapter/workers_b200.cpp emits them that way); parse_system rejects any other order.
 //   tape tokens: V<j> | C<lo>,<hi> (hex or decimal doubles) | ADD SUB MUL DIV NEG POS REC SQR SQRT EXP LOG SIN COS TAN ABS MAX MIN
 #pragma once
 #include <string>

@@ -60,3 +60,14 @@ def test_system_texts_parse_on_the_host(pkg):
         pkg.system_check("system broken\nlocations 1\nlocation 0 a n 2 events 0\n  dyn 0 V7 ;\n")
     with pytest.raises(pkg.Ab200Error):
         pkg.system_check("system broken\nlocations 1\nlocation 0 a n 1 events 0\n  dyn 0 V0 FROB ;\n")
+    # events out of name order: index order would no longer be the reference's std::set<DiscreteEvent> order
+    wt = open(os.path.join(golden_io.GOLDEN, "watertank.sys")).read()
+    lines = wt.split("\n")
+    ev = [i for i, l in enumerate(lines) if l.strip().startswith("event ")]
+    names = [lines[i].split()[2] for i in ev[:2]]
+    swapped = list(lines)
+    swapped[ev[0]] = lines[ev[0]].replace(" " + names[0] + " ", " " + names[1] + " ", 1)
+    swapped[ev[1]] = lines[ev[1]].replace(" " + names[1] + " ", " " + names[0] + " ", 1)
+    with pytest.raises(pkg.Ab200Error) as e:
+        pkg.system_check("\n".join(swapped))
+    assert "ascending name order" in str(e.value)
