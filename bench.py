@@ -253,21 +253,22 @@ def run_ours(args):
 
 
 def check_fingerprint(pkg, an, reach, evolve):
-    """Fingerprint (cell count + sha256 over the sorted boxes of the maximal dyadic cells, raw bits) of the reach / evolve
-    cell sets of the lap, against the committed fingerprint of the reference's own UpperReachEvolveWorker::get_result() on
-    the same 101,520-cell frontier (tests/golden/vanderpol_bench_fingerprint.json, made by
-    tests/golden/make_bench_fingerprint.sh from the compiled reference)."""
+    """Fingerprint (leaf-cell count + sha256 over the sorted lattice indices) of the reach / evolve cell sets of the lap,
+    against the committed fingerprint of the reference's own UpperReachEvolveWorker::get_result() on the same 101,520-cell
+    frontier (tests/golden/vanderpol_bench_fingerprint.json, made by tests/golden/make_bench_fingerprint.sh from the
+    compiled reference)."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    from bench_fingerprint import fingerprint
+    from bench_fingerprint import leaf_fingerprint
     path = os.path.join(ROOT, "tests", "golden", "vanderpol_bench_fingerprint.json")
     try:
         want = json.load(open(path))
     except Exception:
         return {"verdict": "unchecked", "why": "no committed fingerprint"}
+    if want.get("frontier_cells") != FRONTIER:
+        return {"verdict": "unchecked", "why": "the committed fingerprint covers %s of the %d frontier cells" % (want.get("frontier_cells"), FRONTIER)}
     out = {}
     for name, cs in (("reach", reach), ("evolve", evolve)):
-        _, boxes = an.enumerate(cs, mince=False)
-        out[name] = fingerprint(boxes[:, :4])
+        out[name] = leaf_fingerprint(an.evolver.decode(cs.keys)[:, 1:3])
     ok = all(out[k]["sha256"] == want[k]["sha256"] and out[k]["cells"] == want[k]["cells"] for k in ("reach", "evolve"))
     return {"verdict": "identical to the reference" if ok else "MISMATCH", "reach": out["reach"], "evolve": out["evolve"],
             "reference": {k: want[k] for k in ("reach", "evolve")}}

@@ -14,6 +14,7 @@
 #include "../../include/ariadne_b200.h"
 #include "ab200_events.cuh"
 #include "ab200_series.cuh"
+#include "ab200_jump.cuh"
 #include "ab200_system.h"
 #include "ab200_paving.h"
 
@@ -22,6 +23,10 @@ using namespace ab200;
 const HostSystem* ab200_ctx_system(const ab200_ctx* ctx);
 const KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx);
 void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg);
+// ForwardDiscreteJumpSetChecker::check for a batch of cell boxes (stride AB200_BOX_STRIDE) of transition `event` out of
+// location `loc`, on the device (K_jump_check, one warp per box): tri[i] = 0 false / 1 true / 2 indeterminate. Returns an
+// AB200 code; *lie_missing is set if the guard has no Lie derivative.
+int ab200_ctx_jump_check(ab200_ctx* ctx, int loc, int event, size_t n, const double* boxes, int* tri, int* lie_missing);
 std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs);
 ab200_cellset* ab200_cellset_new();
 
@@ -255,60 +260,13 @@ struct JumpCalc {
     static int tri_not(int t) { return t == TRI_INDET ? TRI_INDET : (t == TRI_TRUE ? TRI_FALSE : TRI_TRUE); }
     static int tri_and(int a, int b) { if (a == TRI_FALSE || b == TRI_FALSE) return TRI_FALSE; if (a == TRI_TRUE && b == TRI_TRUE) return TRI_TRUE; return TRI_INDET; }
 
-    // _is_outside_any_invariant (src/set_checker.cpp:111-135)
-    int outside_any_invariant(int l, const Ivl* bx) {
-        const LocDesc& L = S.loc[l];
-        int result = TRI_FALSE;
-        for (int e = 0; e < L.n_events; ++e) {
-            if (L.ev[e].kind != EV_INVARIANT && L.ev[e].kind != EV_URGENT) continue;
-            int act = tribool_of(eval_ivl(c, S.ops, L.ev[e].guard, bx));
-            if (act == TRI_TRUE) return TRI_TRUE;
-            if (act == TRI_INDET) result = TRI_INDET;
-        }
-        return result;
-    }
+    // the checks themselves live in ab200_jump.cuh (shared with K_jump_check)
+    int outside_any_invariant(int l, const Ivl* bx) { return jump_outside_any_invariant(c, S, l, bx); }
     // TaylorSet(Box) (src/taylor_set.cpp:69-72)
     void box_set(const Ivl* bx, int n, TM* set) { for (int i = 0; i < n; ++i) set[i] = tm_scaling(c, n, i, bx[i]); }
-    // _is_transition_taken (src/set_checker.cpp:66-108)
-    int transition_taken(int l, int e, const TM* src, int n) {
-        const EventDesc& E = S.loc[l].ev[e];
-        const bool urgent = (E.kind == EV_URGENT);
-        int act = guard_active(c, S, E.guard, src);
-        if (act == TRI_TRUE && urgent) return TRI_FALSE;
-        if (act != TRI_FALSE && !urgent) return act;
-        if (act != TRI_FALSE && urgent) {
-            // _is_positively_crossing: Lie derivative of the guard over the enclosure's bounding box
-            if (E.lie.end <= E.lie.begin) { lie_missing = true; fail(c, ST_UNSUPPORTED); return TRI_INDET; }
-            Ivl bb[AB_MAXN];
-            for (int i = 0; i < n; ++i) bb[i] = tm_range(c, src[i]);
-            Ivl d = eval_ivl(c, S.ops, E.lie, bb);
-            if (d.u < 0) return TRI_FALSE;
-            return TRI_INDET;
-        }
-        return TRI_FALSE;
-    }
+    int transition_taken(int l, int e, const TM* src, int n) { int lm = 0; int r = jump_transition_taken(c, S, l, e, src, n, &lm); if (lm) lie_missing = true; return r; }
     // ForwardDiscreteJumpSetChecker::check (src/set_checker.cpp:171-203)
-    int check(int l, int e, const double* box) {
-        const int n = S.loc[l].n;
-        const int m = c.A.top;
-        Ivl bx[AB_MAXN];
-        for (int i = 0; i < n; ++i) bx[i] = ivl(box[2 * i], box[2 * i + 1]);
-        int out_src = outside_any_invariant(l, bx);
-        if (out_src == TRI_TRUE) return TRI_FALSE;
-        int result = TRI_FALSE;
-        TM src[AB_MAXN]; box_set(bx, n, src);
-        int taken = transition_taken(l, e, src, n);
-        if (taken != TRI_FALSE) {
-            const EventDesc& E = S.loc[l].ev[e];
-            const int nt = S.loc[E.target].n;
-            Ivl tb[AB_MAXN];
-            for (int i = 0; i < nt; ++i) { TM t = eval_tm(c, S.ops, E.reset[i], src); tb[i] = tm_range(c, t); }
-            int out_trg = outside_any_invariant(E.target, tb);
-            result = tri_and(tri_and(tri_not(out_src), taken), tri_not(out_trg));
-        }
-        c.A.top = m;
-        return result;
-    }
+    int check(int l, int e, const double* box) { int lm = 0; int r = jump_check(c, S, l, e, box, &lm); if (lm) lie_missing = true; return r; }
 
     // BackwardDiscreteJumpSetChecker (src/set_checker.cpp:229-352): a source cell is kept if some transition may be taken
     // from it into the set reached so far (`start`, one tree per location, with the bounding boxes of its cells).
@@ -429,7 +387,21 @@ static int forward_jump_set(ab200_analyser* an, const HybridCells& reach, Hybrid
             const int trg = L.ev[e].target;
             const int n = L.n, nt = S.loc[trg].n;
             CellSet feasible = reach[l];
-            feasible.outer_restrict([&](const double* box) { return J.check(l, e, box); });
+            // the activation test of every cell box of a level of the paving goes to the device in one batch; AB200_JUMP_HOST=1
+            // runs the same descent with the host build of the same check (the checker the tests compare against)
+            const bool on_host = getenv("AB200_JUMP_HOST") != 0;
+            if (on_host) feasible.outer_restrict([&](const double* box) { return J.check(l, e, box); });
+            else {
+                int brc = AB200_OK; int lm = 0;
+                feasible.outer_restrict_batched([&](const std::vector<CellBox>& boxes, std::vector<int>& tri) {
+                    std::vector<double> flat(boxes.size() * AB200_BOX_STRIDE, 0.0);
+                    for (size_t k = 0; k < boxes.size(); ++k) for (int i = 0; i < 2 * n; ++i) flat[k * AB200_BOX_STRIDE + i] = boxes[k].b[i];
+                    tri.assign(boxes.size(), TRI_INDET);
+                    if (brc == AB200_OK) brc = ab200_ctx_jump_check(an->ctx, l, e, boxes.size(), flat.data(), tri.data(), &lm);
+                });
+                if (lm) { J.lie_missing = true; fail(J.c, ST_UNSUPPORTED); }
+                else if (brc != AB200_OK) return brc;
+            }
             // get_reset (src/set_checker.cpp:206-226)
             CellSet image(an->grid[trg], an->K, trg);
             std::vector<CellBox> cells; feasible.enumerate(cells);

@@ -98,6 +98,7 @@ struct ab200_ctx {
     DevBuf<unsigned long long> d_counters;
     DevBuf<uint32_t> d_binom;
     DevBuf<int> d_next;
+    DevBuf<double> d_jbox; DevBuf<int32_t> d_jout;      // jump-set check batches (ab200_ctx_jump_check)
     unsigned long long sys_generation;     // bumped by every change of the system description or tuning
     // multi-GPU exchange (ab200_comm_init): one process per GPU, NCCL communicator over NVLink
     ncclComm_t comm; int n_ranks, rank;
@@ -144,7 +145,7 @@ extern "C" void ab200_ctx_destroy(ab200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_loc.release(); ctx->d_nreach.release(); ctx->d_nfin.release(); ctx->d_status.release(); ctx->d_steps.release(); ctx->d_peak.release();
     ctx->d_rloc.release(); ctx->d_floc.release(); ctx->d_box.release(); ctx->d_reach.release(); ctx->d_fin.release();
-    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release(); ctx->d_flops.release(); ctx->d_gather.release(); ctx->d_counts.release(); ctx->d_pos.release();
+    ctx->d_arena.release(); ctx->d_table.release(); ctx->d_keys.release(); ctx->d_tmp.release(); ctx->d_hist.release(); ctx->d_counters.release(); ctx->d_binom.release(); ctx->d_next.release(); ctx->d_jbox.release(); ctx->d_jout.release(); ctx->d_flops.release(); ctx->d_gather.release(); ctx->d_counts.release(); ctx->d_pos.release();
     ab200_comm_destroy(ctx);
     if (ctx->device >= 0 && ctx->device < 64 && g_sys_owner[ctx->device] == ctx) g_sys_owner[ctx->device] = 0;
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -882,6 +883,34 @@ extern "C" int ab200_probe_fp64_fma(ab200_ctx* ctx, double* gflops) { return pro
 
 // the analyser entry points live in ab200_analyser.cu and use these two accessors
 const ab200::HostSystem* ab200_ctx_system(const ab200_ctx* ctx) { return ctx && ctx->have_system ? &ctx->sys : 0; }
+// ForwardDiscreteJumpSetChecker::check for a batch of cell boxes on the device (ab200_analyser.cu: forward_jump_set)
+int ab200_ctx_jump_check(ab200_ctx* ctx, int loc, int event, size_t n, const double* boxes, int* tri, int* lie_missing) {
+    if (!ctx || !ctx->have_system || loc < 0 || loc >= ctx->sys.desc.n_locs || event < 0 || event >= ctx->sys.desc.loc[loc].n_events) return AB200_E_ARGUMENT;
+    if (n == 0) return AB200_OK;
+    { int rc_ = upload_system(ctx, false); if (rc_ != AB200_OK) return rc_; }
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int blocks = sms * 8; if ((size_t)blocks > n) blocks = (int)n;
+    const int aw = ctx->settings.arena_words;
+    CTX_CK(ctx->d_arena.ensure((size_t)blocks * aw));
+    CTX_CK(ctx->d_jbox.ensure(n * AB200_BOX_STRIDE)); CTX_CK(ctx->d_jout.ensure(2 * n + 1));
+    int32_t* const d_out = ctx->d_jout.p;
+    cudaMemcpyAsync(ctx->d_jbox.p, boxes, n * AB200_BOX_STRIDE * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream);
+    cudaMemsetAsync(d_out + 2 * n, 0, sizeof(int32_t), ctx->stream);
+    char eb[256]; eb[0] = 0;
+    int rc = dev_launch_jump_check(ctx->stream, (int)n, blocks, loc, event, ctx->d_jbox.p, ctx->d_arena.p, aw, ctx->d_binom.p, ctx->d_next.p,
+                                   d_out, d_out + n, d_out + 2 * n, eb, sizeof(eb));
+    std::vector<int32_t> h(2 * n + 1);
+    if (rc == 0) cudaMemcpyAsync(h.data(), d_out, (2 * n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (rc != 0 || es != cudaSuccess) { ctx->err = rc ? eb : cudaGetErrorString(es); return AB200_E_CUDA; }
+    if (lie_missing && h[2 * n]) *lie_missing = 1;
+    for (size_t i = 0; i < n; ++i) {
+        tri[i] = h[i];
+        if (h[n + i] != ST_OK && !(h[2 * n] && h[n + i] == ST_UNSUPPORTED)) { ctx->err = "jump set check failed on the device"; return map_status(h[n + i]); }
+    }
+    return AB200_OK;
+}
 const ab200::KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return ctx && ctx->have_layout ? &ctx->K : 0; }
 void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg) { if (ctx) ctx->err = msg; }
 std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs) { return cs->keys; }

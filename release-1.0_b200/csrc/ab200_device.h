@@ -23,6 +23,8 @@ int dev_launch_integrator_flow_bounds(cudaStream_t st, int n_cells, const int32_
                                       double* h_out, double* b_out, int32_t* status, char* errbuf, int errlen);
 int dev_launch_integrator_flow(cudaStream_t st, int loc, const double* box, double hmax, int order, uint64_t* arena, int arena_words,
                                const uint32_t* binom, uint64_t* out, int out_words, char* errbuf, int errlen);
+int dev_launch_jump_check(cudaStream_t st, int n, int blocks, int loc, int ev, const double* boxes, uint64_t* arena, int arena_words,
+                          const uint32_t* binom, int* next, int32_t* tri, int32_t* status, int32_t* lie_missing, char* errbuf, int errlen);
 int dev_launch_tm_op(cudaStream_t st, const uint64_t* in, uint64_t* arena, int arena_words, const uint32_t* binom, uint64_t* out, int out_words,
                      char* errbuf, int errlen);
 int dev_launch_interval_op(cudaStream_t st, int n, const double* in, double* out, char* errbuf, int errlen);

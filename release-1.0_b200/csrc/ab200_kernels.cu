@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include "ab200_evolve.cuh"
+#include "ab200_jump.cuh"
 #include "ab200_grid.cuh"
 #include "ab200_device.h"
 
@@ -159,6 +160,31 @@ __global__ void K_interval_op(int n, const double* __restrict__ in, double* __re
     default: st = ST_UNSUPPORTED;
     }
     out[3 * i] = r.l; out[3 * i + 1] = r.u; out[3 * i + 2] = (double)st;
+}
+
+// ---- grid-side jump sets: the activation test of a batch of cell boxes ----------------------------------------------------
+// ForwardDiscreteJumpSetChecker::check (src/set_checker.cpp:171-203) for transition `ev` out of location `loc`: one warp per
+// box, persistent one-warp CTAs pulling boxes from a counter. tri[b] = 0 false / 1 true / 2 indeterminate.
+__global__ void __launch_bounds__(32, 8)
+K_jump_check(int n, int loc, int ev, const double* __restrict__ boxes, uint64_t* __restrict__ arena, int arena_words,
+             const uint32_t* __restrict__ binom, int* __restrict__ next, int32_t* __restrict__ tri, int32_t* __restrict__ status,
+             int32_t* __restrict__ lie_missing) {
+    extern __shared__ uint64_t ab_smem[];
+    const int lane = wlane();
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(next, 1);
+        b = wshfl(b, 0);
+        if (b >= n) break;
+        Ctx c; ctx_init(c, arena + (size_t)blockIdx.x * (size_t)arena_words, arena_words, ab_smem, binom);
+        ctx_stage_tables(c);
+        double box[2 * AB_MAXN];
+        for (int i = 0; i < 2 * AB_MAXN; ++i) box[i] = boxes[(size_t)b * 2 * AB_MAXN + i];
+        int lm = 0;
+        const int r = jump_check(c, c_sys, loc, ev, box, &lm);
+        wsync();
+        if (lane == 0) { tri[b] = r; status[b] = c.status; if (lm) atomicOr(lie_missing, 1); }
+    }
 }
 
 // ---- rasterise + hash-set insert ------------------------------------------------------------------------------------
@@ -359,6 +385,13 @@ int dev_launch_integrator_flow_bounds(cudaStream_t st, int n_cells, const int32_
 int dev_launch_integrator_flow(cudaStream_t st, int loc, const double* box, double hmax, int order, uint64_t* arena, int arena_words,
                                const uint32_t* binom, uint64_t* out, int out_words, char* errbuf, int errlen) {
     K_integrator_flow<<<1, 32, AB_SM_WORDS * sizeof(uint64_t), st>>>(loc, box, hmax, order, arena, arena_words, binom, out, out_words);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dev_launch_jump_check(cudaStream_t st, int n, int blocks, int loc, int ev, const double* boxes, uint64_t* arena, int arena_words,
+                          const uint32_t* binom, int* next, int32_t* tri, int32_t* status, int32_t* lie_missing, char* errbuf, int errlen) {
+    if (n == 0) return 0;
+    K_jump_check<<<blocks, 32, AB_SM_WORDS * sizeof(uint64_t), st>>>(n, loc, ev, boxes, arena, arena_words, binom, next, tri, status, lie_missing);
     CK(cudaGetLastError());
     return 0;
 }

@@ -187,6 +187,57 @@ void CellSet::outer_restrict(const BoxTest& check) {
     keys.swap(out);
 }
 
+void CellSet::outer_restrict_batched(const BatchTest& check) {
+    if (keys.empty()) return;
+    const int dim = grid.dim;
+    Root root = minimal_root();
+    int l2[AB_GRID_MAXN], ns[AB_GRID_MAXN]; long long lower[AB_GRID_MAXN];
+    root_extent(root, dim, l2, lower);
+    for (int i = 0; i < dim; ++i) ns[i] = l2[i] + K.acc;
+    std::vector<PathKey> P(keys.size());
+    long long idx[AB_GRID_MAXN], rel[AB_GRID_MAXN];
+    for (size_t k = 0; k < keys.size(); ++k) {
+        int l; key_unpack(K, keys[k], &l, idx);
+        for (int i = 0; i < dim; ++i) rel[i] = idx[i] - lower[i] * (1LL << K.acc);
+        P[k].p = make_path(root, dim, K.acc, rel, ns); P[k].key = keys[k];
+    }
+    std::sort(P.begin(), P.end());
+    Ivl rc[AB_GRID_MAXN];
+    root_box(grid.origin, grid.lengths, dim, root, rc);
+    struct Node { size_t lo, hi; int split; CellBox box; };
+    std::vector<Node> level(1), next;
+    level[0].lo = 0; level[0].hi = P.size(); level[0].split = splitting_coordinate(root.height, dim);
+    for (int i = 0; i < dim; ++i) { level[0].box.b[2 * i] = rc[i].l; level[0].box.b[2 * i + 1] = rc[i].u; }
+    const int depth = root.height + dim * K.acc;
+    std::vector<uint64_t> out;
+    std::vector<CellBox> boxes; std::vector<int> tri;
+    for (int lv = 0; lv <= depth && !level.empty(); ++lv) {
+        boxes.resize(level.size());
+        for (size_t q = 0; q < level.size(); ++q) boxes[q] = level[q].box;
+        check(boxes, tri);
+        next.clear();
+        for (size_t q = 0; q < level.size(); ++q) {
+            const Node& nd = level[q];
+            const int prop = tri[q];
+            if (prop == 0) continue;
+            if (prop == 1 || lv == depth) { for (size_t k = nd.lo; k < nd.hi; ++k) out.push_back(P[k].key); continue; }
+            const int shift = depth - 1 - lv;
+            size_t a = nd.lo, b = nd.hi;
+            while (a < b) { size_t m = (a + b) / 2; if ((P[m].p >> shift) & 1) b = m; else a = m + 1; }
+            const double c = (nd.box.b[2 * nd.split] + nd.box.b[2 * nd.split + 1]) / 2.0;
+            Node L = nd, R = nd;
+            L.hi = a; R.lo = a;
+            L.box.b[2 * nd.split + 1] = c; R.box.b[2 * nd.split] = c;
+            L.split = R.split = (nd.split + 1) % dim;
+            if (L.hi > L.lo) next.push_back(L);                     // enabled_cells == bddfalse: nothing below
+            if (R.hi > R.lo) next.push_back(R);
+        }
+        level.swap(next);
+    }
+    std::sort(out.begin(), out.end());
+    keys.swap(out);
+}
+
 namespace {
 struct AdjoinCtx {
     const CellSet* cs; const CellSet::BoxTest* disjoint; int dim, depth; long long base[AB_GRID_MAXN];

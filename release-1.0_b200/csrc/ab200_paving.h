@@ -53,6 +53,10 @@ class CellSet {
     // descend from the minimal root; a subtree is dropped where the check is false, kept whole where it is true,
     // and kept at the leaves where it stays indeterminate.
     void outer_restrict(const BoxTest& check);
+    // The same descent level by level: all boxes of one level are tested in one call (a device batch), then the undecided
+    // ones are split. The test is pure, so the result is the depth-first one.
+    typedef std::function<void(const std::vector<CellBox>&, std::vector<int>&)> BatchTest;
+    void outer_restrict_batched(const BatchTest& check);
     // adjoin_outer_approximation(CompactSetInterface,accuracy) (src/bdd_set.cpp:1548-1574,455-493): grow the root over
     // `bbox`, then mark every leaf reached without meeting a cell the set is definitely disjoint from
     // (`disjoint` returns 1 only for "definitely disjoint"). Returns false if a cell fell outside the key window.

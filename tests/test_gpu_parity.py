@@ -171,6 +171,31 @@ def test_lower_reach_evolve_identical_cells(pkg, system, name, domain, init):
         an.close()
 
 
+@pytest.mark.parametrize("name,init", [("bouncingball_chain_acc5.txt", [0.0, 0.001, 1.999, 2.0]),
+                                       ("bouncingball_chain_acc6.txt", [-2.0, 0.5, 0.5, 1.5])])
+def test_jump_set_checks_on_the_device_match_the_host_checker(pkg, name, init, monkeypatch):
+    """forward_jump_set: the activation test of every cell box of the paving descent
+    (ForwardDiscreteJumpSetChecker::check, src/set_checker.cpp:171-203) runs on the device, one warp per box per level
+    (K_jump_check). AB200_JUMP_HOST=1 runs the same descent with the host build of the same check: both must give the
+    golden's cells, and the device path must have launched its kernel."""
+    d = golden_io.load_dump(name)
+    results = []
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("AB200_JUMP_HOST", "1")
+        else:
+            monkeypatch.delenv("AB200_JUMP_HOST", raising=False)
+        an = pkg.HybridReachabilityAnalyser(_system("bouncingball"), [-10.1, 10.1, -0.1, 2.1], d["config"]["acc"], settings={"arena_words": 65536})
+        try:
+            reach = an.outer_chain_reach({"freefall": init})
+            _, rb = an.enumerate(reach)
+            assert golden_io.boxes_equal_bits(rb, d["sets"]["reach"]["freefall"])
+            results.append(reach.keys.copy())
+        finally:
+            an.close()
+    assert np.array_equal(results[0], results[1])
+
+
 def test_boost_outer_chain_reach_fails_like_the_reference(pkg):
     """configs[4]: the reference's own outer_chain_reach on the boost converter throws in forward_jump_set because
     lie_derivative cannot differentiate the min() guard (src/function.cpp:1329). Same laps, same failure here."""

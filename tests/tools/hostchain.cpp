@@ -28,6 +28,19 @@ extern "C" int ab200_boxlist_view(const ab200_boxlist* bl, const uint64_t** offs
 extern "C" void ab200_boxlist_free(ab200_boxlist* bl) { delete bl; }
 
 const HostSystem* ab200_ctx_system(const ab200_ctx* ctx) { return &ctx->sys; }
+// stand-in for the device batch of ab200_capi.cu: the same check, serially on the host
+#include "../../release-1.0_b200/csrc/ab200_jump.cuh"
+int ab200_ctx_jump_check(ab200_ctx* ctx, int loc, int event, size_t n, const double* boxes, int* tri, int* lie_missing) {
+    static std::vector<uint64_t> arena(1u << 22);
+    for (size_t i = 0; i < n; ++i) {
+        Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
+        int lm = 0;
+        tri[i] = jump_check(c, ctx->sys.desc, loc, event, boxes + i * AB200_BOX_STRIDE, &lm);
+        if (lm && lie_missing) *lie_missing = 1;
+        if (c.status != ST_OK && !lm) return c.status;
+    }
+    return AB200_OK;
+}
 const KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return &ctx->K; }
 void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg) { ctx->err = msg; }
 std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs) { return cs->keys; }
