@@ -297,13 +297,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # Sample size: as many cells as keep the whole --steps/--warmup run within about five minutes, at most 8,192 per step
-    # (the rate is probed on 8 cells per host thread first).
+    # Sample size: as many cells as keep the whole --steps/--warmup run within about three minutes, at most 2,048 per step.
+    # The rate is probed on 8 cells per host thread first; it FALLS with the sample size, because the worker discretises and
+    # adjoins every cell's result under one mutex (include/workers.h:141-150) into a set that keeps growing: 60 cells/s on 512
+    # cells, 26 cells/s on 7,399 cells with 16 threads (gpurun_out/r2_bench_reference.json), so small samples flatter the
+    # reference.
     cores = os.cpu_count() or 1
     probe = cpu_baseline(8 * cores)
     rate = probe["value"] or 50.0
     runs = args.steps + min(args.warmup, 1)
-    n = args.cpu_cells or int(max(16 * cores, min(8192, 280.0 * rate / max(runs, 1))))
+    n = args.cpu_cells or int(max(16 * cores, min(2048, 120.0 * rate / max(runs, 1))))
     vals = []
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(n)
