@@ -74,7 +74,10 @@ typedef struct ab200_status {
     int64_t launches;         /* kernels launched by this call */
     int32_t build;            /* evolution build used by the last batch: 0 = one warp per cell (one-word MultiIndex keys),
                                  1 = one warp per cell (two-word keys), 2 = one lane per cell (very large frontiers) */
-    int32_t reserved;
+    int32_t libm_sensitive;   /* rec / sqrt model calls of this call whose series degree or truncation bound could change with
+                                 the last bits of log() / pow() (glibc in the reference, CUDA on the device). 0 certifies that no
+                                 result of the call depends on them. Counted by the warp builds (build 0 / 1); the lane build
+                                 (build 2) does not count and always reports 0 */
     double  alg_flops;        /* FP64 operations of the REFERENCE algorithm executed by this call, counted per primitive on the
                                  actual term counts with the formulas of SURVEY.md 8(d) (0 when the lane build ran) */
 } ab200_status;

@@ -49,7 +49,7 @@ class Settings(C.Structure):
 class Status(C.Structure):
     _fields_ = [("code", C.c_int32), ("cell", C.c_int64), ("steps", C.c_int64), ("keys_emitted", C.c_int64),
                 ("arena_peak", C.c_int32), ("evolve_ms", C.c_double), ("raster_ms", C.c_double), ("launches", C.c_int64),
-                ("build", C.c_int32), ("reserved", C.c_int32), ("alg_flops", C.c_double)]
+                ("build", C.c_int32), ("libm_sensitive", C.c_int32), ("alg_flops", C.c_double)]
 
 
 class Ab200Error(RuntimeError):

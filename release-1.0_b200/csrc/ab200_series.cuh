@@ -7,6 +7,25 @@
 
 namespace ab200 { inline namespace AB_VARIANT {
 
+// log() and pow() are glibc's in the reference and CUDA's here; both are accurate to a few ulps but not bit-identical. What
+// enters the result is (1) the series degree d = unsigned(log(a)/log(eps) [+1]) and (2) the truncation bound pow(eps,d)/..., which
+// is added to an error term many orders larger. Each call CERTIFIES that neither can change with the last bits: the degree is
+// recomputed with the quotient moved by 16 ulps either way, the error sum with the bound moved by 8 ulps either way (CUDA pow
+// <= 2 ulp, glibc < 1 ulp in any rounding mode, plus the division and product after it). If either differs the call is counted
+// in Ctx::libm_sensitive and reported in ab200_status.libm_sensitive: a lap that reports 0 is bit-exact by construction, not
+// by luck.
+AB_HD unsigned series_degree(Ctx& c, double num_log_arg, double eps, double plus_inside, unsigned plus_outside) {
+    const double q = log(num_log_arg) / log(eps);
+    const unsigned d = (unsigned)(q + plus_inside) + plus_outside;
+    const double w = dabs(q) * 3.6e-15;                                  // 16 ulps of the quotient
+    if ((unsigned)(q - w + plus_inside) + plus_outside != d || (unsigned)(q + w + plus_inside) + plus_outside != d) c.libm_sensitive++;
+    return d;
+}
+AB_HD void series_certify_sum(Ctx& c, int mode, double err, double te, double sum) {
+    const double lo = te * (1.0 - 1.8e-15), hi = te * (1.0 + 1.8e-15);    // 8 ulps of the bound
+    if (add_m(mode, err, lo) != sum || add_m(mode, err, hi) != sum) c.libm_sensitive++;
+}
+
 // rec(x). For a constant model (every "/ constant" of the configs) eps is exactly 0 and the series has one term, so
 // no libm value enters the result. For eps>0 the series degree and the truncation bound use log()/pow(), which the
 // reference takes from glibc; the device values can differ in the last bit, so that branch is flagged unpinned.
@@ -19,7 +38,7 @@ AB_HDN TM tm_rec(Ctx& c, const TM& x) {
     c.rnd = RN;
     unsigned d;
     if (eps == 0.0) d = 1;
-    else d = (unsigned)(log(mul_rn(sub_rn(1.0, eps), x.acc.sweep)) / log(eps)) + 1;
+    else d = series_degree(c, mul_rn(sub_rn(1.0, eps), x.acc.sweep), eps, 0.0, 1u);
     // y=1-(x/a)
     TM xa = tm_copy(c, x);
     tm_scal(c, xa, ivl_div(ivl(1.0), a));
@@ -36,7 +55,7 @@ AB_HDN TM tm_rec(Ctx& c, const TM& x) {
         z = p;
     }
     double te = (eps == 0.0) ? 0.0 : div_rn(pow(eps, (double)d), sub_rn(1.0, eps));
-    z.e = add_ru(te, z.e);
+    { const double ze = z.e; z.e = add_ru(te, ze); if (eps != 0.0) series_certify_sum(c, RU, ze, te, z.e); }
     c.rnd = RN;
     if (a == 0) { fail(c, ST_DIVZERO); }
     tm_scal(c, z, ivl_div(ivl(1.0), a));
@@ -58,7 +77,7 @@ AB_HDN TM tm_sqrt(Ctx& c, const TM& x) {
     c.rnd = RN;
     unsigned d;
     if (eps == 0.0) d = 1;
-    else d = (unsigned)(log(mul_rn(sub_rn(1.0, eps), x.acc.sweep)) / log(eps) + 1);
+    else d = series_degree(c, mul_rn(sub_rn(1.0, eps), x.acc.sweep), eps, 1.0, 0u);
     if (d + 1 > AB_MAXSER) { fail(c, ST_UNSUPPORTED); return tm_copy(c, x); }
     // y=(x/a)-1
     TM y = tm_copy(c, x);
@@ -82,7 +101,7 @@ AB_HDN TM tm_sqrt(Ctx& c, const TM& x) {
         z = p;
     }
     double te = (eps == 0.0) ? 0.0 : mul_m(c.rnd, div_m(c.rnd, pow(eps, (double)d), sub_m(c.rnd, 1.0, eps)), ivl_mag(ser[d]));
-    z.e = add_m(c.rnd, z.e, te);
+    { const double ze = z.e; z.e = add_m(c.rnd, ze, te); if (eps != 0.0) series_certify_sum(c, c.rnd, ze, te, z.e); }
     tm_scal(c, z, ivl_sqrt(ivl(a), &st));
     if (st != ST_OK) fail(c, st);
     tm_slide(c, z, m0);

@@ -120,6 +120,7 @@ struct Ctx {
     double flops;            // algorithmic FP64 operations of the reference algorithm so far (AB_FLOPS)
     // phase alignment of the warps of a CTA (K_evolve): shared progress words, warps in the CTA, this warp, loop iteration
     int* al_phase; int al_n; int al_warp; int al_iter;
+    int libm_sensitive;      // rec / sqrt calls whose result could change with the last bits of log / pow (ab200_series.cuh)
 };
 #define AB_BINOM_N 64
 #define AB_BINOM_K 24
@@ -134,12 +135,12 @@ struct BinomTab { uint32_t t[AB_BINOM_N * AB_BINOM_K]; BinomTab() { binom_fill(t
 inline const uint32_t* binom_host() { static BinomTab b; return b.t; }
 AB_HD void ctx_init(Ctx& c, uint64_t* arena, int limit, uint64_t* sm, const uint32_t* binom) {
     c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom; c.sm_dirty = 1; c.flops = 0.0;
-    c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0;
+    c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0; c.libm_sensitive = 0;
 }
 // host-side callers (no warp, no shared area)
 inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
     c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1; c.flops = 0.0;
-    c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0;
+    c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0; c.libm_sensitive = 0;
 }
 
 // Phase alignment (device, CTAs of several warps): the warps of a CTA evolve different cells through the same sequence of

@@ -273,6 +273,11 @@ def test_baseline_depth_sampled_cells_bit_exact(pkg, system, name, domain, arena
                 for lname in set(ref_l) | set(d["grid"].keys()):
                     ref_rows = [b for b, n in zip(ref_b, ref_l) if n == lname]
                     assert golden_io.boxes_equal_bits(mine_b[mine_l == ev.location(lname), :2 * dim], ref_rows), "%s boxes of cell %d in %s" % (what, c["id"], lname)
+        # sqrt / rec series: how many calls could have changed with the last bits of libm's log / pow (0 = certified exact)
+        print("%s: %d steps, %d libm-sensitive series calls" % (system, ev.last_status.steps, ev.last_status.libm_sensitive))
+        assert ev.last_status.libm_sensitive <= ev.last_status.steps // 100
+        if system != "watertank":
+            assert ev.last_status.libm_sensitive == 0          # no sqrt / rec of a non-constant model in these systems
         reach, evolve = ev.upper_reach_evolve(locs, boxes, T, events, d["config"]["ignore_activations"])
         for which, cs in (("ureach", reach), ("ufinal", evolve)):
             cl, cb = an.enumerate(cs)
