@@ -21,6 +21,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+_OUT = sys.stdout
 
 METRIC = "grid cells evolved/sec (upper_reach)"
 UNIT = "cells/s"
@@ -124,23 +125,29 @@ def run_ours(args):
     an = pkg.HybridReachabilityAnalyser(system, DOMAIN, ACC, device=local, settings={"arena_words": args.arena_words, "max_boxes": args.max_boxes, "hash_log2": 25})
     ev = an.evolver
     all_cells = frontier_cells(pkg, an, args.cells)
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("ab200_parallel", os.path.join(ROOT, "release-1.0_b200", "parallel.py"))
-    par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
     strong = args.scaling == "strong" and world > 1
-    if strong:
-        # STRONG scaling: ONE frontier. Every rank passes all of it to the library, which deals blocks of 64 cells round-robin
-        # to the ranks, evolves its share and exchanges the sorted cell keys with ncclAllGather on the device.
+    if world > 1:
+        # One process per GPU; the library shards every lap: all ranks pass the SAME global frontier, the library deals blocks
+        # of 64 cells round-robin to the ranks, each rank evolves and rasterises its share, and the sorted cell keys
+        # are exchanged with ncclAllGather and de-duplicated on the device, so every rank returns the lap's full sets.
         ev.init_comm(dist)
+    if strong:
+        # STRONG scaling: ONE configs[2] frontier dealt to all GPUs.
         mine = all_cells
+    elif world > 1:
+        # WEAK scaling (the default; frontier cells are independent units): one configs[2] frontier PER GPU. The global
+        # frontier of an N-GPU run is N translates of it (copy r shifted by r/N of a cell width along x, so the copies are
+        # distinct enclosures with the same distribution of work); the library deals it, every GPU evolves 101,520 cells.
+        w = all_cells[0, 1] - all_cells[0, 0]
+        copies = []
+        for r in range(world):
+            c = all_cells.copy(); c[:, 0:2] += (float(r) / world) * w
+            copies.append(c)
+        mine = np.ascontiguousarray(np.concatenate(copies, axis=0))
     else:
-        # WEAK scaling (the default; frontier cells are independent units): one configs[2] frontier per GPU. The global
-        # frontier of an N-GPU run is N translates of it (shard r shifted by r/N of a cell width along x, so the shards are
-        # distinct enclosures with the same distribution of work); rank r owns shard r.
-        mine = all_cells.copy()
-        mine[:, 0:2] += (float(rank) / world) * (all_cells[0, 1] - all_cells[0, 0])
+        mine = all_cells
     n_mine = mine.shape[0]
-    n_share = (n_mine + world - 1) // world if strong else n_mine          # cells this GPU evolves per lap
+    n_share = (n_mine + world - 1) // world                                 # cells this GPU evolves per lap
     boxes = pkg.pack_boxes(mine, 2)
     locs = np.zeros((n_mine,), dtype=np.int32)
     T = an.lock_to_grid_time * args.lap_scale
@@ -168,16 +175,13 @@ def run_ours(args):
         r, e, st = lap()
         ev_ms += st.evolve_ms; ra_ms += st.raster_ms; steps += st.steps; keys += st.keys_emitted; reach_n = len(r); launches += st.launches
         flops += st.alg_flops; build = st.build
-        if world > 1 and not strong:
-            # newly reached cell ids are exchanged so that every rank holds the lap's reach set (NCCL all-gather)
-            reach_n = int(par.exchange_keys(r.keys, dist, torch.device("cuda", local)).shape[0])
         last_r, last_e = r, e
     barrier()
     t1 = time.perf_counter()
     sampler.stop_flag = True; sampler.join()
     wall = t1 - t0
     times = torch.tensor([wall, ev_ms, ra_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(n_mine) / (world if strong else 1), float(steps), float(keys)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_mine) / world, float(steps), float(keys)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     wall, ev_ms, ra_ms = [float(x) for x in times.tolist()]
@@ -221,7 +225,7 @@ def run_ours(args):
         "metric": METRIC, "value": dev_value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %s (configs[2])" % (ACC, ("ONE frontier of %d cells dealt to %d GPUs" % (int(n_mine), world)) if strong else ("%d frontier cells per GPU" % int(n_mine))),
+        "config": {"workload": "vanderpol upper_reach lap, Taylor order 6/6, accuracy %d, %s (configs[2])" % (ACC, ("ONE frontier of %d cells dealt to %d GPUs" % (int(n_mine), world)) if strong else (("%d frontier cells per GPU" % int(n_share)) + ((", %d in all, dealt by the library" % int(n_mine)) if world > 1 else ""))),
                    "system": SYSTEM, "accuracy": ACC, "frontier_cells": int(n_total), "frontier_cells_per_gpu": int(n_share), "lap_time": T,
                    "evolution_build": build_name,
                    "l2_policy": "every lap rewrites its scratch arenas and box lists (GBs, far beyond L2); no flush needed"},
@@ -246,7 +250,7 @@ def run_ours(args):
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_cells or 32 * (os.cpu_count() or 1))
-        print(json.dumps(line))
+        _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     an.close()
     if world > 1:
         dist.destroy_process_group()
@@ -323,7 +327,7 @@ def run_reference(args):
                        "system": SYSTEM, "accuracy": ACC},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
 
 
 def main():
@@ -340,10 +344,18 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: one frontier per GPU (weak, default) or one frontier dealt to all GPUs (strong)")
     ap.add_argument("--lap-scale", type=float, default=1.0, help="PROFILING ONLY: shorten the lap so that ncu can replay the kernel; not a bench value")
     args = ap.parse_args()
+    # Rank 0 prints ONE JSON line on stdout and nothing else: whatever libraries write to file descriptor 1 while the run lasts
+    # (NCCL prints its version there when NCCL_DEBUG is set) is sent to stderr; the line goes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _OUT
+    _OUT = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
