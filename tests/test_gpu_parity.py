@@ -196,6 +196,33 @@ def test_jump_set_checks_on_the_device_match_the_host_checker(pkg, name, init, m
     assert np.array_equal(results[0], results[1])
 
 
+@pytest.mark.parametrize("system,name,wpc", [("bouncingball", "bouncingball_cells_acc5.txt", 8), ("bouncingball", "bouncingball_cells_acc5.txt", 3),
+                                              ("watertank", "watertank_cells_acc6.txt.gz", 6), ("vanderpol", "vanderpol_cells_acc7.txt.gz", 12)])
+def test_phase_aligned_ctas_with_events_bit_exact(pkg, system, name, wpc, monkeypatch):
+    """CTAs of several warps that meet at the stages of a step (the launch shape of large frontiers), forced onto small hybrid
+    batches: warps of one CTA then take different paths (urgent bounces, permissive jumps with activation windows, early
+    termination, cells of different length, warps running out of cells), which is exactly what the alignment protocol must
+    survive without waiting for ever. Results are the goldens, bit for bit."""
+    monkeypatch.setenv("AB200_WPC", str(wpc))
+    d = golden_io.load_dump(name)
+    ev = _evolver(pkg, d, system=system, arena_words=131072, max_boxes=2048)
+    try:
+        dim = ev.dims[0]
+        locs = [ev.location(c["loc"]) for c in d["cells"]]
+        boxes = pkg.pack_boxes([c["box"] for c in d["cells"]], dim)
+        events = 1 if d["config"]["chain"] else d["config"]["events"]
+        (roff, rbox, rloc), (foff, fbox, floc) = ev.reach_evolve(locs, boxes, d["config"]["T"], events, d["config"]["ignore_activations"])
+        for i, c in enumerate(d["cells"]):
+            for mine_b, mine_l, ref_b, ref_l in ((rbox[roff[i]:roff[i + 1]], rloc[roff[i]:roff[i + 1]], c["reach"], c["reach_loc"]),
+                                                 (fbox[foff[i]:foff[i + 1]], floc[foff[i]:foff[i + 1]], c["final"], c["final_loc"])):
+                assert len(ref_b) == mine_b.shape[0]
+                for lname in set(ref_l):
+                    ref_rows = [b for b, n in zip(ref_b, ref_l) if n == lname]
+                    assert golden_io.boxes_equal_bits(mine_b[mine_l == ev.location(lname), :2 * dim], ref_rows), "cell %d in %s" % (c["id"], lname)
+    finally:
+        ev.close()
+
+
 def test_boost_outer_chain_reach_fails_like_the_reference(pkg):
     """configs[4]: the reference's own outer_chain_reach on the boost converter throws in forward_jump_set because
     lie_derivative cannot differentiate the min() guard (src/function.cpp:1329). Same laps, same failure here."""
