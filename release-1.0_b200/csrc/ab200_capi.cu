@@ -376,7 +376,7 @@ static int exchange_keys(ab200_ctx* ctx, const uint64_t* mine, unsigned long lon
     size_t nblocks = (total + dev_sort_tile() - 1) / dev_sort_tile();
     CTX_CK(ctx->d_hist.ensure(256 * nblocks));
     int in_tmp = 0;
-    if (dev_radix_sort(ctx->stream, all, ctx->d_tmp.p, total, 64, ctx->d_hist.p, &in_tmp, eb, sizeof(eb)) != 0) { ctx->err = eb; return AB200_E_CUDA; }
+    if (dev_radix_sort(ctx->stream, all, ctx->d_tmp.p, total, 64, ~0ull, ctx->d_hist.p, &in_tmp, eb, sizeof(eb)) != 0) { ctx->err = eb; return AB200_E_CUDA; }
     (void)total_bits;
     const uint64_t* sorted = in_tmp ? ctx->d_tmp.p : all;
     CTX_CK(ctx->d_pos.ensure(total + 1));
@@ -441,7 +441,7 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
     if (out.fin_boxes) { out.fin_boxes->offsets.assign(1, 0); }
     if (want_keys) {
         CTX_CK(ctx->d_table.ensure(table_n * 2));
-        CTX_CK(ctx->d_counters.ensure(8));
+        CTX_CK(ctx->d_counters.ensure(12));
         DEV_CK(dev_launch_fill(ctx->stream, ctx->d_table.p, table_n * 2, ~0ull, eb_, sizeof(eb_))); stl.launches += 1;
         CTX_CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     }
@@ -586,17 +586,21 @@ static int lap_keys(ab200_ctx* ctx, LapOut& out, bool sharded, ab200_status* sta
         int total_bits = ctx->K.loc_bits; for (int i = 0; i < ctx->K.dim; ++i) total_bits += ctx->K.bits[i];
         for (int which = 0; which < 2; ++which) {
             std::vector<uint64_t>* dst = which ? out.fin_keys : out.reach_keys;
-            CTX_CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, sizeof(unsigned long long), ctx->stream));
+            { const unsigned long long init3[3] = { 0ull, 0ull, ~0ull };        // count, OR of the keys, AND of the keys
+              CTX_CK(cudaMemcpyAsync(ctx->d_counters.p + 8, init3, sizeof(init3), cudaMemcpyHostToDevice, ctx->stream)); }
             CTX_CK(ctx->d_keys.ensure(table_n)); CTX_CK(ctx->d_tmp.ensure(table_n));
-            DEV_CK(dev_launch_compact(ctx->stream, ctx->d_table.p + (size_t)which * table_n, table_n, ctx->d_keys.p, ctx->d_counters.p + 6, eb_, sizeof(eb_))); stl.launches += 1;
-            unsigned long long cnt = 0;
-            CTX_CK(cudaMemcpyAsync(&cnt, ctx->d_counters.p + 6, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+            DEV_CK(dev_launch_compact(ctx->stream, ctx->d_table.p + (size_t)which * table_n, table_n, ctx->d_keys.p, ctx->d_counters.p + 8, eb_, sizeof(eb_))); stl.launches += 1;
+            unsigned long long cnt3[3] = { 0ull, 0ull, 0ull };
+            CTX_CK(cudaMemcpyAsync(cnt3, ctx->d_counters.p + 8, sizeof(cnt3), cudaMemcpyDeviceToHost, ctx->stream));
             CTX_CK(cudaStreamSynchronize(ctx->stream));
+            const unsigned long long cnt = cnt3[0];
+            const unsigned long long varying = cnt ? (cnt3[1] ^ cnt3[2]) : 0ull;       // bits in which the keys of this set differ
             int in_tmp = 0;
             if (cnt > 1) {
                 size_t nblocks = (cnt + dev_sort_tile() - 1) / dev_sort_tile();
                 CTX_CK(ctx->d_hist.ensure(256 * nblocks));
-                DEV_CK(dev_radix_sort(ctx->stream, ctx->d_keys.p, ctx->d_tmp.p, cnt, total_bits, ctx->d_hist.p, &in_tmp, eb_, sizeof(eb_))); stl.launches += 3 * ((total_bits + 7) / 8);
+                DEV_CK(dev_radix_sort(ctx->stream, ctx->d_keys.p, ctx->d_tmp.p, cnt, total_bits, varying, ctx->d_hist.p, &in_tmp, eb_, sizeof(eb_)));
+                for (int shift = 0; shift < total_bits; shift += 8) if ((varying >> shift) & 0xFFull) stl.launches += 3;
             }
             if (sharded) {
                 int rc_ = exchange_keys(ctx, in_tmp ? ctx->d_tmp.p : ctx->d_keys.p, cnt, total_bits, dst, stl);

@@ -32,7 +32,7 @@ int dev_launch_fill(cudaStream_t st, uint64_t* p, size_t n, uint64_t v, char* er
 int dev_launch_raster(cudaStream_t st, int n_cells, int max_boxes, const double* boxes, const int32_t* box_loc, const int32_t* n_boxes,
                       const KeyLayout& K, int n_locs, uint64_t* table, uint64_t mask, unsigned long long* counters, char* errbuf, int errlen);
 int dev_launch_compact(cudaStream_t st, const uint64_t* table, size_t n, uint64_t* out, unsigned long long* count, char* errbuf, int errlen);
-int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned* hist, int* result_in_tmp,
+int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned long long varying, unsigned* hist, int* result_in_tmp,
                    char* errbuf, int errlen);
 int dev_sort_tile();
 int dev_unique_sorted(cudaStream_t st, const uint64_t* in, size_t n, unsigned* pos, uint64_t* out, char* errbuf, int errlen);

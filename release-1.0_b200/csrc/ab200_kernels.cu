@@ -248,23 +248,29 @@ __global__ void K_raster(int n_cells, int max_boxes, const double* __restrict__ 
     atomicAdd(&counters[2], emitted);
 }
 
+// count[0] = number of keys; count[1] / count[2] = OR / AND of all keys (preset to 0 / ~0): the bits in which the keys differ are
+// OR ^ AND, and the radix sort only has to visit the digits that hold one of them.
 __global__ void K_compact(const uint64_t* __restrict__ table, size_t n, uint64_t* __restrict__ out, unsigned long long* count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stridex = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stridex) {
-        uint64_t k = table[i];
+    const int lane = threadIdx.x & 31;
+    unsigned long long orb = 0ull, andb = ~0ull;
+    const size_t rounds = (n + stridex - 1) / stridex;          // every lane of a warp takes part in every ballot
+    for (size_t r = 0; r < rounds; ++r, i += stridex) {
+        uint64_t k = (i < n) ? table[i] : AB_EMPTY_KEY;
         bool live = (k != AB_EMPTY_KEY);
         unsigned m = __ballot_sync(0xFFFFFFFFu, live);
         // warp-aggregated append
-        int lane = threadIdx.x & 31;
         unsigned long long base = 0;
         if (m) {
             int leader = __ffs(m) - 1;
             if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (live) out[base + __popc(m & ((1u << lane) - 1))] = k;
+            if (live) { out[base + __popc(m & ((1u << lane) - 1))] = k; orb |= k; andb &= k; }
         }
     }
+    for (int d = 16; d > 0; d >>= 1) { orb |= __shfl_xor_sync(0xFFFFFFFFu, orb, d); andb &= __shfl_xor_sync(0xFFFFFFFFu, andb, d); }
+    if (lane == 0 && orb != 0ull) { atomicOr(count + 1, orb); atomicAnd(count + 2, andb); }
 }
 
 // ---- LSD radix sort (8-bit digits), stable, one warp per tile -------------------------------------------------------
@@ -426,13 +432,15 @@ int dev_launch_compact(cudaStream_t st, const uint64_t* table, size_t n, uint64_
     return 0;
 }
 // Sorts keys[0..n) ascending on the low `bits` bits; tmp and hist are scratch (hist: 256*ceil(n/TILE) unsigned).
-int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned* hist, int* result_in_tmp,
+// `varying`: the bits in which the keys differ (all ones if unknown); digits without such a bit are skipped.
+int dev_radix_sort(cudaStream_t st, uint64_t* keys, uint64_t* tmp, size_t n, int bits, unsigned long long varying, unsigned* hist, int* result_in_tmp,
                    char* errbuf, int errlen) {
     *result_in_tmp = 0;
     if (n <= 1) return 0;
     int nblocks = (int)((n + AB_SORT_TILE - 1) / AB_SORT_TILE);
     uint64_t* src = keys; uint64_t* dst = tmp;
     for (int shift = 0; shift < bits; shift += 8) {
+        if (((varying >> shift) & 0xFFull) == 0ull) continue;
         K_sort_hist<<<nblocks, 256, 0, st>>>(src, n, shift, hist, nblocks);
         K_sort_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblocks);
         K_sort_scatter<<<nblocks, 32, 0, st>>>(src, dst, n, shift, hist, nblocks);
