@@ -169,7 +169,8 @@ int  ab200_taylor_model_op(ab200_ctx* ctx, int32_t op, int32_t nargs,
                            ab200_taylor_models** out);
 /* ops[i] = {op, m, a.lower, a.upper, b.lower, b.upper}, results[i] = {lower, upper, status}.
  * op: 0 a+b, 1 a-b, 2 a*b, 3 a/b, 4 a+Float(b.lower), 5 a-Float, 6 a*Float, 7 a/Float, 8 Float(a.lower)-b, 9 Float/b,
- *     10 sqr(a), 11 sqrt(a), 12 pow(a,m), 13 rec(a), 14 abs(a), 15 -a, 16 max(a,b), 17 min(a,b). */
+ *     10 sqr(a), 11 sqrt(a), 12 pow(a,m), 13 rec(a), 14 abs(a), 15 -a, 16 max(a,b), 17 min(a,b), 18 exp(a), 19 log(a),
+ *     20 sin(a), 21 cos(a). */
 int  ab200_interval_op(ab200_ctx* ctx, int32_t n, const double* ops, double* results);
 
 /* Host mirror of HybridReachabilityAnalyser (include/reachability_analyser.h:122-172): grid, lock-to-grid time and

@@ -66,12 +66,15 @@ static T random_model(uint as, uint deg, double fill, double scale, double err) 
 static void iv(const char* op, Interval a, Interval b, int m) {
     set_rounding_to_nearest();
     std::string o(op); Interval r(0,0);
+    try {
     if(o=="add") r=a+b; else if(o=="sub") r=a-b; else if(o=="mul") r=a*b; else if(o=="div") r=a/b;
     else if(o=="addf") r=a+Float(b.lower()); else if(o=="subf") r=a-Float(b.lower()); else if(o=="mulf") r=a*Float(b.lower()); else if(o=="divf") r=a/Float(b.lower());
     else if(o=="fsub") r=Float(a.lower())-b; else if(o=="fdiv") r=Float(a.lower())/b;
     else if(o=="sqr") r=sqr(a); else if(o=="sqrt") r=sqrt(a); else if(o=="pow") r=pow(a,(uint)m); else if(o=="rec") r=rec(a);
     else if(o=="abs") r=abs(a); else if(o=="neg") r=-a; else if(o=="max") r=max(a,b); else if(o=="min") r=min(a,b);
+    else if(o=="exp") r=exp(a); else if(o=="log") r=log(a); else if(o=="sin") r=sin(a); else if(o=="cos") r=cos(a);
     else { fprintf(stderr,"unknown interval op %s\n",op); exit(2); }
+    } catch(std::exception& e) { set_rounding_to_nearest(); fprintf(stderr,"skipping interval %s: %s\n",op,e.what()); return; }   // e.g. the reference's log of a point below 1 gives lower>upper
     set_rounding_to_nearest();
     printf("iv %s a %a %a b %a %a m %d r %a %a\n",op,a.lower(),a.upper(),b.lower(),b.upper(),m,r.lower(),r.upper());
 }
@@ -130,5 +133,14 @@ int main() {
     for(int i=1;i<=6;++i) { Interval x(1.0/(2*i+1),2.0/(2*i+1)), y(-3.0/7*i,5.0/(3*i));
         iv("add",x,y,0); iv("sub",x,y,0); iv("mul",x,y,0); iv("mul",y,y,0); iv("div",y,x,0); iv("sqr",y,I0,0); iv("sqr",x,I0,0); iv("sqrt",x,I0,0); iv("rec",x,I0,0);
         iv("pow",y,I0,3); iv("pow",y,I0,4); iv("abs",y,I0,0); iv("neg",y,I0,0); iv("max",x,y,0); iv("min",x,y,0); iv("mulf",y,Interval(1.0/3),0); iv("divf",y,Interval(7.0/3),0); }
+    // ---- exp / log / sin / cos of intervals (src/numeric.cpp:912-966; the reference's own rounded series, no libm) ----
+    { const double xs[]={ -20.5, -3.25, -1.0, -0.4, -0.1, -1e-3, 0.0, 1e-9, 0.05, 0.3, 0.5, 0.7, 1.0, 1.5, 2.0, 2.5, 3.0, 3.14, 3.2, 4.0, 4.7, 5.5, 6.2, 6.3, 7.0, 9.5, 12.0, 25.0, 100.25, 710.0 };
+      const int nx=sizeof(xs)/sizeof(xs[0]);
+      for(int i=0;i<nx;++i) { double x=xs[i]; double w=(i%3==0)?0.0:((i%3==1)?1e-3:0.37);
+          iv("exp",Interval(x<700?x:700.0,(x<700?x:700.0)+w),I0,0);
+          iv("sin",Interval(x,x+w),I0,0); iv("cos",Interval(x,x+w),I0,0); iv("sin",Interval(-x-w,-x),I0,0); iv("cos",Interval(-x-w,-x),I0,0);
+          if(x>0) { iv("log",Interval(x,x+w),I0,0); iv("log",Interval(x/1024,x/1024+w/7),I0,0); } }
+      iv("cos",Interval(-1.0,2.0),I0,0); iv("cos",Interval(1.0,4.0),I0,0); iv("cos",Interval(3.0,7.0),I0,0); iv("cos",Interval(-0.5,13.0),I0,0);
+      iv("sin",Interval(-1.0,2.0),I0,0); iv("sin",Interval(1.0,4.0),I0,0); iv("exp",Interval(-1.0/3,1.0/3),I0,0); iv("log",Interval(1.0/3,3.0),I0,0); }
     return 0;
 }

@@ -331,7 +331,7 @@ class Evolver(object):
     TM_OPS = {"add": 0, "sub": 1, "mul": 2, "addf": 3, "subf": 4, "mulf": 5, "divf": 6, "addi": 7, "subi": 8, "muli": 9, "divi": 10, "neg": 11,
               "intersection": 12, "split": 13, "antiderivative": 14, "rec": 15, "sqrt": 16, "abs": 17, "max": 18, "range": 19}
     IV_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "addf": 4, "subf": 5, "mulf": 6, "divf": 7, "fsub": 8, "fdiv": 9, "sqr": 10, "sqrt": 11,
-              "pow": 12, "rec": 13, "abs": 14, "neg": 15, "max": 16, "min": 17}
+              "pow": 12, "rec": 13, "abs": 14, "neg": 15, "max": 16, "min": 17, "exp": 18, "log": 19, "sin": 20, "cos": 21}
 
     def taylor_model_op(self, op, nargs, x, y=None, k=0, flag=0, s=0.0, interval=(0.0, 0.0)):
         """One TaylorModel operator / function on the device. x, y: (exponents[n][nargs] uint8, coefficients[n], error).

@@ -12,6 +12,7 @@
 //                                    src/taylor_set.cpp:499-577; src/taylor_model.cpp:3882-3956
 #pragma once
 #include "ab200_tm.cuh"
+#include "ab200_elem.cuh"
 
 namespace ab200 { inline namespace AB_VARIANT {
 
@@ -97,7 +98,11 @@ AB_HDN Ivl eval_ivl(Ctx& c, const TapeOp* ops, Func f, const Ivl* x) {
             case OP_SQR: st[sp - 1] = ivl_sqr(st[sp - 1]); break;
             case OP_SQRT: st[sp - 1] = ivl_sqrt(st[sp - 1], &c.status); break;
             case OP_ABS: st[sp - 1] = ivl_abs(st[sp - 1]); break;
-            default: fail(c, ST_UNSUPPORTED); break;
+            case OP_EXP: st[sp - 1] = ivl_exp(st[sp - 1]); break;
+            case OP_LOG: st[sp - 1] = ivl_log(st[sp - 1], &c.status); break;
+            case OP_SIN: st[sp - 1] = ivl_sin(st[sp - 1], c.rnd); break;
+            case OP_COS: st[sp - 1] = ivl_cos(st[sp - 1], c.rnd); break;
+            default: fail(c, ST_UNSUPPORTED); break;          // tan: not implemented for intervals in the reference either
         }
     }
     return st[0];

@@ -157,6 +157,10 @@ __global__ void K_interval_op(int n, const double* __restrict__ in, double* __re
     case 15: r = ivl_neg(a); break;
     case 16: r = ivl_max(a, b); break;
     case 17: r = ivl_min(a, b); break;
+    case 18: r = ivl_exp(a); break;
+    case 19: r = ivl_log(a, &st); break;
+    case 20: r = ivl_sin(a, RN); break;
+    case 21: r = ivl_cos(a, RN); break;
     default: st = ST_UNSUPPORTED;
     }
     out[3 * i] = r.l; out[3 * i + 1] = r.u; out[3 * i + 2] = (double)st;

@@ -92,7 +92,7 @@ def test_literal_vectors_of_the_reference_unit_tests(ev):
 
 def test_interval_primitives_bit_exact(ev):
     _, ivs = load_kat()
-    assert len(ivs) >= 150
+    assert len(ivs) >= 350 and {c["op"] for c in ivs} >= {"exp", "log", "sin", "cos"}
     out = ev.interval_ops([(c["op"], c["m"], c["a"], c["b"]) for c in ivs])
     for c, r in zip(ivs, out):
         assert r[2] == 0, c
