@@ -161,7 +161,8 @@ void ab200_taylor_models_free(ab200_taylor_models* m);
  * test/test_interval.cpp:152-254) can be replayed on the device bit for bit; models are given and returned as
  * (exponent bytes [n_terms][nargs] in the reference's graded order, coefficients, uniform error), default Accuracy.
  * op: 0 x+y, 1 x-y, 2 x*y, 3 x+s, 4 x-s, 5 x*s, 6 x/s, 7 x+I, 8 x-I, 9 x*I, 10 x/I, 11 -x, 12 intersection(x,y),
- *     13 split(x,k,flag), 14 antiderivative(x,k), 15 rec(x), 16 sqrt(x), 17 abs(x), 18 max(x,y), 19 x.range() -> range_out. */
+ *     13 split(x,k,flag), 14 antiderivative(x,k), 15 rec(x), 16 sqrt(x), 17 abs(x), 18 max(x,y), 19 x.range() -> range_out,
+ *     20 exp(x), 21 log(x), 22 sin(x), 23 cos(x). */
 int  ab200_taylor_model_op(ab200_ctx* ctx, int32_t op, int32_t nargs,
                            int32_t x_terms, const uint8_t* x_exps, const double* x_coefs, double x_error,
                            int32_t y_terms, const uint8_t* y_exps, const double* y_coefs, double y_error,

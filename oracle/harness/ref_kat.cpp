@@ -42,6 +42,7 @@ static void emit(const char* op, const T& x, const T& y, int k, int flag, double
         else if(o=="split") r=split(x,(uint)k,tribool(flag!=0));
         else if(o=="antiderivative") r=antiderivative(x,(uint)k);
         else if(o=="rec") r=rec(x); else if(o=="sqrt") r=sqrt(x); else if(o=="abs") r=abs(x); else if(o=="max") r=max(x,y);
+        else if(o=="exp") r=exp(x); else if(o=="log") r=log(x); else if(o=="sin") r=sin(x); else if(o=="cos") r=cos(x);
         else if(o=="range") { rng=x.range(); is_range=true; }
         else { fprintf(stderr,"unknown op %s\n",op); exit(2); }
     } catch(std::exception& e) { set_rounding_to_nearest(); fprintf(stderr,"skipping %s: %s\n",op,e.what()); return; }
@@ -115,6 +116,17 @@ int main() {
         emit("rec",p,none(as),0,0,0.0,I0); emit("sqrt",p,none(as),0,0,0.0,I0);
         T q=random_model(as,2,0.9,0.5,1e-8);
         emit("abs",q,none(as),0,0,0.0,I0); emit("max",x,y,0,0,0.0,I0); emit("abs",p,none(as),0,0,0.0,I0);
+    }
+    // ---- exp / log / sin / cos of models: the vectors of test/test_taylor_model.cpp:183-205 and rounding pseudo-random models ----
+    { T x(E(1,1, 0.0,1.0),0.0), xz(E(1,1, 0.0,0.5),0.0), xo(E(1,1, 1.0,0.5),0.0), xl(E(1,1, 0.693147,0.5),0.0);
+      emit("exp",x,none(1),0,0,0.0,I0); emit("sin",x,none(1),0,0,0.0,I0); emit("cos",x,none(1),0,0,0.0,I0);
+      emit("exp",xz,none(1),0,0,0.0,I0); emit("sin",xz,none(1),0,0,0.0,I0); emit("cos",xz,none(1),0,0,0.0,I0);
+      emit("log",xo,none(1),0,0,0.0,I0); emit("exp",xl,none(1),0,0,0.0,I0); }
+    for(uint as=2; as<=3; ++as) for(int rep=0; rep<2; ++rep) {
+        T q=random_model(as,3,0.9,0.4,1e-8), p=random_model(as,3,0.9,0.2,1e-8)+Float(2.0), w=random_model(as,2,0.9,1.5,1e-6)+Float(7.0+3*rep);
+        emit("exp",q,none(as),0,0,0.0,I0); emit("sin",q,none(as),0,0,0.0,I0); emit("cos",q,none(as),0,0,0.0,I0);
+        emit("exp",w,none(as),0,0,0.0,I0); emit("sin",w,none(as),0,0,0.0,I0); emit("cos",w,none(as),0,0,0.0,I0);
+        emit("log",p,none(as),0,0,0.0,I0); emit("log",w,none(as),0,0,0.0,I0);
     }
     // ---- Interval arithmetic: test/test_interval.cpp:152-254 ----
     const double eps=2.2204460492503131e-16, mn=4.9406564584124654e-324;

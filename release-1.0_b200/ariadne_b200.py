@@ -329,7 +329,7 @@ class Evolver(object):
         return h.value, dom, models
 
     TM_OPS = {"add": 0, "sub": 1, "mul": 2, "addf": 3, "subf": 4, "mulf": 5, "divf": 6, "addi": 7, "subi": 8, "muli": 9, "divi": 10, "neg": 11,
-              "intersection": 12, "split": 13, "antiderivative": 14, "rec": 15, "sqrt": 16, "abs": 17, "max": 18, "range": 19}
+              "intersection": 12, "split": 13, "antiderivative": 14, "rec": 15, "sqrt": 16, "abs": 17, "max": 18, "range": 19, "exp": 20, "log": 21, "sin": 22, "cos": 23}
     IV_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "addf": 4, "subf": 5, "mulf": 6, "divf": 7, "fsub": 8, "fdiv": 9, "sqr": 10, "sqrt": 11,
               "pow": 12, "rec": 13, "abs": 14, "neg": 15, "max": 16, "min": 17, "exp": 18, "log": 19, "sin": 20, "cos": 21}
 

@@ -121,6 +121,9 @@ struct TmSlot { TM v; int mark; };
 
 AB_HDN TM tm_rec(Ctx& c, const TM& x);
 AB_HDN TM tm_sqrt(Ctx& c, const TM& x);
+AB_HDN TM tm_exp(Ctx& c, const TM& x);
+AB_HDN TM tm_log(Ctx& c, const TM& x);
+AB_HDN TM tm_sincos(Ctx& c, const TM& x, bool want_sin);
 AB_HDN TM tm_max(Ctx& c, const TM& x, const TM& y);
 AB_HDN TM tm_abs(Ctx& c, const TM& x);
 
@@ -174,7 +177,11 @@ AB_HDN TM eval_tm(Ctx& c, const TapeOp* ops, Func f, const TM* x) {
                 } break;
                 case OP_SQRT: r = tm_sqrt(c, a); break;
                 case OP_ABS: r = tm_abs(c, a); break;
-                default: fail(c, ST_UNSUPPORTED); r = a; break;
+                case OP_EXP: r = tm_exp(c, a); break;
+                case OP_LOG: r = tm_log(c, a); break;
+                case OP_SIN: r = tm_sincos(c, a, true); break;
+                case OP_COS: r = tm_sincos(c, a, false); break;
+                default: fail(c, ST_UNSUPPORTED); r = a; break;          // tan
             }
             if (o.op != OP_POS) tm_slide(c, r, st[sp - 1].mark);
             st[sp - 1].v = r;

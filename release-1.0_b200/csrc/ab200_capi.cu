@@ -501,12 +501,12 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             CTX_CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             CTX_CK(cudaStreamSynchronize(ctx->stream));
             float ms1 = 0; cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1); ms += ms1;
-            // the lane build has fixed device limits (scratch words and pending working sets per cell): a batch that hits one
-            // is run again by the warp build, which has neither
+            // the lane build has fixed device limits (scratch words and pending working sets per cell) and no exp / log / sin / cos:
+            // a batch that hits one is run again by the warp build
             // warp builds: bits 8.. of the status word carry the cell's count of libm-sensitive series calls (ab200_series.cuh)
             if (!use_lane) for (int i = 0; i < nb; ++i) { stl.libm_sensitive += (h_status[i] >> 8) & 0xFFFFF; h_status[i] &= 0xFF; }
             bool retry = false;
-            if (use_lane) for (int i = 0; i < nb; ++i) if (h_status[i] == ST_ARENA || h_status[i] == ST_WORKING_SETS) { retry = true; break; }
+            if (use_lane) for (int i = 0; i < nb; ++i) if (h_status[i] == ST_ARENA || h_status[i] == ST_WORKING_SETS || h_status[i] == ST_UNSUPPORTED) { retry = true; break; }
             stl.build = use_lane ? 2 : (wide ? 1 : 0);
             if (!retry) break;
             use_lane = false;

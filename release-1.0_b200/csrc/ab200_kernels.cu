@@ -118,6 +118,10 @@ K_tm_op(const uint64_t* __restrict__ in, uint64_t* __restrict__ arena, int arena
     case 17: r = tm_abs(c, x); break;
     case 18: r = tm_max(c, x, y); break;
     case 19: rng = tm_range(c, x); r = tm_copy(c, x); break;
+    case 20: r = tm_exp(c, x); break;
+    case 21: r = tm_log(c, x); break;
+    case 22: r = tm_sincos(c, x, true); break;
+    case 23: r = tm_sincos(c, x, false); break;
     default: fail(c, ST_UNSUPPORTED);
     }
     if (st != ST_OK) fail(c, st);

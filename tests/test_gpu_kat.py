@@ -51,7 +51,7 @@ def ev(pkg):
 
 def test_taylor_model_primitives_bit_exact(ev):
     tms, _ = load_kat()
-    assert len(tms) >= 180
+    assert len(tms) >= 225
     seen = set(); bad = []
     for i, c in enumerate(tms):
         x = (c["x"]["exps"], c["x"]["coefs"], c["x"]["error"]); y = (c["y"]["exps"], c["y"]["coefs"], c["y"]["error"])
@@ -74,7 +74,7 @@ def test_taylor_model_primitives_bit_exact(ev):
         seen.add(c["op"])
     assert not bad, "\n".join(bad)
     assert seen >= {"add", "sub", "mul", "addf", "mulf", "divf", "addi", "muli", "divi", "neg", "intersection", "split",
-                    "antiderivative", "rec", "sqrt", "abs", "max", "range"}
+                    "antiderivative", "rec", "sqrt", "abs", "max", "range", "exp", "log", "sin", "cos"}
 
 
 def test_literal_vectors_of_the_reference_unit_tests(ev):
