@@ -67,6 +67,21 @@ static HybridIOAutomaton make_vanderpol() {
     return a;
 }
 
+// damped pendulum with transcendental terms (not a BASELINE config: it exists to pin exp / log / sin / cos on the tapes):
+// x'=y, y'=-sin(x)+0.1 cos(y)-0.05 exp(0.3 x)+0.01 log(12+x^2)
+static HybridIOAutomaton make_pendulum() {
+    HybridIOAutomaton a("pendulum");
+    DiscreteLocation loc("loc");
+    RealVariable x("x"), y("y");
+    a.add_internal_var(x); a.add_internal_var(y);
+    a.new_mode(loc);
+    RealExpression dx = y;
+    RealExpression dy = -Ariadne::sin(x) + 0.1*Ariadne::cos(y) - 0.05*Ariadne::exp(0.3*x) + 0.01*Ariadne::log(12.0+Ariadne::sqr(x));
+    a.set_dynamics(loc,x,dx);
+    a.set_dynamics(loc,y,dy);
+    return a;
+}
+
 // bouncing ball: x'=vx, vx'=-g; forced x<=0 -> vx:=-a vx  (system of examples/bouncingball.cc:33-64)
 static HybridIOAutomaton make_bouncingball() {
     RealParameter a("a",0.5), g("g",9.81);
@@ -125,6 +140,12 @@ static Config make_config(const std::string& name, std::map<std::string,std::str
         c.initial=HybridBoundedConstraintSet(c.sys.state_space());
         c.initial[DiscreteLocation("loc")]=box_from(kv,"init",Box(2,-2.2,2.2,-2.8,2.8));
         c.acc=geti(kv,"acc",6); c.T=getd(kv,"T",0.0);
+    } else if(name=="pendulum") {
+        c.sys=make_pendulum();
+        c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,-3.0,3.0,-3.0,3.0)));
+        c.initial=HybridBoundedConstraintSet(c.sys.state_space());
+        c.initial[DiscreteLocation("loc")]=box_from(kv,"init",Box(2,0.9,1.2,-0.2,0.1));
+        c.acc=geti(kv,"acc",4); c.T=getd(kv,"T",0.0);
     } else if(name=="constder") {
         c.sys=make_constder();
         c.domain=HybridBoxes(c.sys.state_space(),box_from(kv,"domain",Box(2,-1.0,5.0,-1.0,6.0)));

@@ -70,3 +70,6 @@ $H boost cells acc=6 chain=0 T=0.011 disc=2 out=$D/bo6.txt && python $G/fingerpr
 $H vanderpol reach acc=4 cons=disc init=0.9,1.5,1.0,1.6 laps=1 out=$G/vanderpol_cons_disc_acc4.txt
 $H vanderpol reach acc=6 cons=band init=0.5,2.0,0.5,2.0 T=0.02 out=$G/vanderpol_cons_band_acc6.txt
 $H bouncingball reach acc=5 cons=disc init=-0.5,0.5,1.5,2.0 cc=0.0,1.8 cr=0.2 out=$G/bouncingball_cons_disc_chain_acc5.txt
+# exp / log / sin / cos on the tapes: a pendulum with transcendental terms (not a BASELINE config), three cells, T=1
+$H pendulum system out=$G/pendulum.sys
+$H pendulum cells acc=4 T=1.0 ncells=12 stride=1 out=$G/pendulum_cells_acc4.txt

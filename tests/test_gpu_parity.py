@@ -24,7 +24,8 @@ def _evolver(pkg, dump, system="vanderpol", **settings):
 
 @pytest.mark.parametrize("system,name,arena", [("vanderpol", "vanderpol_cells_acc6.txt.gz", 16384), ("vanderpol", "vanderpol_cells_acc3.txt", 131072),
                                                ("vanderpol", "vanderpol_cells_acc7.txt.gz", 12288),
-                                               ("bouncingball", "bouncingball_cells_acc4.txt", 16384), ("bouncingball", "bouncingball_cells_acc5.txt", 16384)])
+                                               ("bouncingball", "bouncingball_cells_acc4.txt", 16384), ("bouncingball", "bouncingball_cells_acc5.txt", 16384),
+                                               ("pendulum", "pendulum_cells_acc4.txt", 1048576)])
 def test_reach_evolve_boxes_bit_exact(pkg, system, name, arena):
     """Per-enclosure reach / final boxes. The bouncing-ball vectors run in chain-reach mode (ignore_activations) and
     exercise the urgent-guard path: activity tests, touching-time bisection and implicit crossing-time models."""

@@ -23,7 +23,7 @@ def _run(*args):
     return subprocess.run([HARNESS] + list(args), stdout=subprocess.PIPE, timeout=600, check=True).stdout.decode()
 
 
-@pytest.mark.parametrize("name", ["vanderpol", "bouncingball", "watertank", "springs", "boost"])
+@pytest.mark.parametrize("name", ["vanderpol", "bouncingball", "watertank", "springs", "boost", "pendulum"])
 def test_system_tapes_are_what_the_reference_automata_hold(name):
     assert _run(name, "system") == open(os.path.join(golden_io.GOLDEN, name + ".sys")).read()
 
