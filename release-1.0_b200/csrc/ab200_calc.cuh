@@ -293,7 +293,7 @@ AB_HD TM ph_load(Ctx& c, int slot, int as, Acc acc) {
 // tte (upward, in term order), error = up(tte+tte/2) + |cv|*p.e (the other cross terms vanish with the factor's error).
 // Result at the arena top.
 AB_HDN TM term_times_power(Ctx& c, double cv, const TM& p, Acc acc) {
-    const int W = AB_W, lane = c.lane, n = p.n, m = c.A.top, soff = p.off;
+    const int W = AB_W, lane = wlane(), n = p.n, m = c.A.top, soff = p.off;
     AB_FLOPS(5.0 * n + 3.0 + 2.0 * (1 + n) + 6.0);
     uint64_t* const base = c.A.base;
     TM r; r.off = m; r.n = 0; r.as = p.as; r.e = 0.0; r.acc = acc;
@@ -323,7 +323,7 @@ AB_HDN TM term_times_power(Ctx& c, double cv, const TM& p, Acc acc) {
 // a one-term right factor -- every x-term is its own stream {x_i*q}, a dropped product adds up(tte_i+tte_i/2) to the error
 // chain in x order, and the cross terms use the norm of t (needed only when q carries an error).
 AB_HDN void term_times_monomial(Ctx& c, TM& t, const TM& q, Acc acc) {
-    const int W = AB_W, lane = c.lane, n = t.n, off = t.off;
+    const int W = AB_W, lane = wlane(), n = t.n, off = t.off;
     AB_FLOPS(10.0 * n + 8.0);
     uint64_t* const base = c.A.base;
     const Key qa = bkey(base, q.off); const double qv = bval(base, q.off), aqv = dabs(qv), qe = q.e, te0 = t.e;
@@ -363,7 +363,7 @@ struct ChainState {
 // folded straight into the accumulator as one stream when `fold` is set (last factor of the chain), else the survivors become
 // the new state. Returns te, the gap sum of the stream (fold only); *te_out error of the product.
 AB_HDN double chain_times_power(Ctx& c, DAcc& DA, ChainState& st, const TM& p, int pslot, Acc acc, bool fold, double* e_out) {
-    const int W = AB_W, lane = c.lane, n = p.n, soff = p.off;
+    const int W = AB_W, lane = wlane(), n = p.n, soff = p.off;
     uint64_t* const base = c.A.base;
     const Key fa = st.ka; const double fv = st.va, afv = dabs(fv), xe = st.e;
     const double sweep = acc.sweep; const int maxdeg = acc.maxdeg;
@@ -421,7 +421,7 @@ AB_HDN double chain_times_power(Ctx& c, DAcc& DA, ChainState& st, const TM& p, i
 // A chain that needs a general product (both factors with two or more terms) parks the sum in the arena at ri first, since
 // the product uses the accumulator itself. Result written at ri.
 AB_HDN TM compose_stream_dense(Ctx& c, const TM& xi, const TM* ys, int nys, const int* tab, int as, Acc acc0, int Dc, int ri) {
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     TM ra; ra.off = ri; ra.n = 0; ra.as = as; ra.e = xi.e; ra.acc = acc0;
     const int sbase = ri + AB_SM_DENSE * AB_TW;            // product chains are built above the room kept for the parked sum
     if (!arena_room(c, sbase, 8)) return ra;
@@ -444,8 +444,8 @@ AB_HDN TM compose_stream_dense(Ctx& c, const TM& xi, const TM* ys, int nys, cons
             const int e = key_get(a, j);
             if (e == 0) continue;
             const int pslot = tab[j] + AB_PHW * e;
-            const TM pw = ph_load(c, pslot, as, ys[j].acc);
-            const Acc accj = ys[j].acc;
+            const TM pw = ph_load(c, pslot, as, c.cmp_acc[j]);
+            const Acc accj = c.cmp_acc[j];
             if (st.kind == 0) {
                 // every product so far was discarded: _mul4 with an empty left factor leaves only the error cross terms
                 const double nm = (st.e != 0.0) ? ph_norm(c, pslot, pw) : 0.0;
@@ -495,7 +495,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     const Acc acc0 = ys[0].acc;
     int maxp[AB_MAXARGS + 1];
     {   // largest exponent of every variable: per-byte maximum of the key words, lanes over terms, then across the lanes
-        const int W = AB_W, lane = c.lane;
+        const int W = AB_W, lane = wlane();
         uint64_t mx[AB_KW]; for (int w = 0; w < AB_KW; ++w) mx[w] = 0;
         #pragma unroll 1
         for (int i = 0; i < nx; ++i)
@@ -508,13 +508,15 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
         for (int j = 0; j < nys; ++j) { const int e = key_get(km, j); maxp[j] = e > 1 ? e : 1; }
     }
     // handle table
-    int tab[AB_MAXARGS + 1];
+    int* const tab = c.cmp_tab;
     int slot = m0;
     #pragma unroll 1
     for (int j = 0; j < nys; ++j) { tab[j] = slot; slot += AB_PHW * (maxp[j] + 1); if (maxp[j] >= AB_MAXPOW) fail(c, ST_ARENA); }
     if (slot > c.A.limit) { fail(c, ST_ARENA); for (int i = 0; i < nx; ++i) r[i] = tm_begin(c, as, acc0); return; }
     c.A.top = slot;
     if (c.A.top > c.A.peak) c.A.peak = c.A.top;
+    #pragma unroll 1
+    for (int j = 0; j < nys; ++j) c.cmp_acc[j] = ys[j].acc;
     #pragma unroll 1
     for (int j = 0; j < nys; ++j) {
         TM p0 = tm_copy(c, ys[j]); tm_scal(c, p0, 0.0); c.A.top = p0.off;       // powers[j][0]=ys[j]*0
@@ -530,7 +532,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
     }
     const int mr = c.A.top;     // results start here; slid down to m0 at the end
 #ifdef AB_COMPOSE_STATS
-    if (c.lane == 0) { extern long long g_cs[8]; g_cs[0]++; for (int i = 0; i < nx; ++i) g_cs[1] += x[i].n; }
+    if (wlane() == 0) { extern long long g_cs[8]; g_cs[0]++; for (int i = 0; i < nx; ++i) g_cs[1] += x[i].n; }
 #endif
     #pragma unroll 1
     for (int i = 0; i < nx; ++i) {
@@ -552,7 +554,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
             AccTab T; bool open = false, failed = false; int dmax = 0; double e_run = x[i].e;
             T.overflow = false;
             Key pk = key_zero(); double pv = 0.0;               // this lane's term of the current chunk of x[i]
-            const int W = AB_W, lane = c.lane;
+            const int W = AB_W, lane = wlane();
             #pragma unroll 1
             for (int t = 0; t < x[i].n && !failed; ++t) {
                 if (t % W == 0) { const int q = t + lane; if (q < x[i].n) { pk = tm_key(c, x[i], q); pv = tm_val(c, x[i], q); } }
@@ -565,22 +567,22 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                 for (int j = 0; j < nys; ++j) {
                     const int e = key_get(a, j);
                     if (e == 0) continue;
-                    const TM pw = ph_load(c, tab[j] + AB_PHW * e, as, ys[j].acc);
+                    const TM pw = ph_load(c, tab[j] + AB_PHW * e, as, c.cmp_acc[j]);
                     if (!started) {
-                        if (pw.n == 0) { tt = tm_const(c, as, cv, acc0); tt = tm_mul(c, tt, pw, ys[j].acc); }
-                        else tt = term_times_power(c, cv, pw, ys[j].acc);
+                        if (pw.n == 0) { tt = tm_const(c, as, cv, acc0); tt = tm_mul(c, tt, pw, c.cmp_acc[j]); }
+                        else tt = term_times_power(c, cv, pw, c.cmp_acc[j]);
                         started = true;
-                    } else if (pw.n == 1 && tt.n >= 1 && tm_end(tt) == c.A.top) term_times_monomial(c, tt, pw, ys[j].acc);
+                    } else if (pw.n == 1 && tt.n >= 1 && tm_end(tt) == c.A.top) term_times_monomial(c, tt, pw, c.cmp_acc[j]);
                     else if (tt.n == 0) {
                         // every product so far was discarded: _mul4 with an empty left factor leaves only the error cross terms
                         const double nm = (tt.e != 0.0) ? ph_norm(c, tab[j] + AB_PHW * e, pw) : 0.0;
                         tt.e = add_ru(0.0, add_ru(add_ru(mul_ru(0.0, pw.e), mul_ru(nm, tt.e)), mul_ru(tt.e, pw.e)));
-                        tt.acc = ys[j].acc; c.rnd = RN;
+                        tt.acc = c.cmp_acc[j]; c.rnd = RN;
                     } else {
                         if (tt.n > 1 && pw.n > 1 && open) {      // general product ahead: it needs the accumulator
                             ra.n = acc_emit(c, T, as, dmax, ri); ra.e = e_run; open = false;
                         }
-                        tt = tm_mul(c, tt, pw, ys[j].acc);
+                        tt = tm_mul(c, tt, pw, c.cmp_acc[j]);
                     }
                 }
                 if (!started) tt = tm_const(c, as, cv, acc0);
@@ -630,7 +632,7 @@ AB_HDN void tm_compose(Ctx& c, const TM* x, int nx, const TM* ys, int nys, TM* r
                     if (e == 0) continue;
                     const TM pw = ph_load(c, tab[j] + AB_PHW * e, as, ys[j].acc);
 #ifdef AB_COMPOSE_STATS
-                    if (c.lane == 0) { extern long long g_cs[8]; g_cs[2]++; g_cs[3] += (long long)(started ? tt.n : 1) * pw.n; if (!started || tt.n <= 1 || pw.n <= 1) g_cs[4]++; }
+                    if (wlane() == 0) { extern long long g_cs[8]; g_cs[2]++; g_cs[3] += (long long)(started ? tt.n : 1) * pw.n; if (!started || tt.n <= 1 || pw.n <= 1) g_cs[4]++; }
 #endif
                     if (!started) {
                         if (pw.n == 0) { tt = tm_const(c, as, cv, acc0); tt = tm_mul(c, tt, pw, ys[j].acc); }
@@ -666,7 +668,7 @@ AB_HDN TM tm_split(Ctx& c, const TM& tm, int k, bool upper) {
     AB_SECTION(2);
     const int m0 = c.A.top;
     const int deg = tm_degree(c, tm);
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     uint64_t* const base = c.A.base;
     TM res = tm_begin(c, tm.as, tm.acc);
     res.e = tm.e;

@@ -25,7 +25,7 @@ __global__ void K_flow_bounds(int n_cells, const int32_t* cell_loc, const double
                               double* h_out, double* b_out, int32_t* status) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cells) return;
-    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = 0; c.sm_dirty = 0; c.flops = 0.0;
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.sm = 0; c.binom = 0; c.sm_dirty = 0; c.flops = 0.0;
     const LocDesc& L = c_sys.loc[cell_loc[cell]];
     Ivl r[AB_MAXN], b[AB_MAXN];
     for (int i = 0; i < L.n; ++i) r[i] = ivl(cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i], cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i + 1]);
@@ -40,7 +40,7 @@ __global__ void K_integrator_flow_bounds(int n_cells, const int32_t* cell_loc, c
                                          double* h_out, double* b_out, int32_t* status) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cells) return;
-    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = 0; c.sm_dirty = 0; c.flops = 0.0;
+    Ctx c; c.A.base = 0; c.A.top = 0; c.A.limit = 0; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.sm = 0; c.binom = 0; c.sm_dirty = 0; c.flops = 0.0;
     const LocDesc& L = c_sys.loc[cell_loc[cell]];
     Ivl r[AB_MAXN], b[AB_MAXN];
     for (int i = 0; i < L.n; ++i) r[i] = ivl(cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i], cell_box[(size_t)cell * 2 * AB_MAXN + 2 * i + 1]);

@@ -114,7 +114,7 @@ AB_HD double tm_value(Ctx& c, const TM& x) { return (x.n > 0 && key_deg(tm_key(c
 AB_HD double rec_fac_up(Ctx& c, unsigned n) { double r = 1.0; for (unsigned i = 1; i <= n; ++i) r = div_ru(r, (double)i); c.rnd = RU; return r; }
 // _scal_exact (src/taylor_model.cpp:229-238): coefficients and error times a power of two, in the ambient mode
 AB_HDN void tm_scal_exact(Ctx& c, TM& r, double s) {
-    const int W = AB_W, lane = c.lane, n = r.n, m = c.rnd;
+    const int W = AB_W, lane = wlane(), n = r.n, m = c.rnd;
     wsync();
     #pragma unroll 1
     for (int i = lane; i < n; i += W) tm_set_val(c, r, i, mul_m(m, tm_val(c, r, i), s));

@@ -109,11 +109,14 @@ struct Arena {
     int peak;
 };
 
+// Every field of Ctx is warp-uniform (all lanes of the cell's warp hold the same value at the same point of the program), so
+// the kernels keep ONE copy per warp in shared memory instead of 32 thread-local copies on the stack: the noinline primitives
+// take it by reference, and a stack copy costs a 256-byte local-memory transaction per field access. The lane index is
+// therefore not a field: use wlane().
 struct Ctx {
     Arena A;
     int rnd;       // ambient rounding mode left behind by the last routine (mirrors MXCSR in the reference)
     int status;    // sticky first error
-    int lane;      // this thread's lane in the warp
     uint64_t* sm;  // the warp's shared-memory staging area (AB_SM_WORDS words); null in host-side callers
     const uint32_t* binom;   // binomial table for monomial ranks (binom_fill)
     int sm_dirty;            // the hash accumulator has written over the dense accumulator's area since it was last emptied
@@ -121,6 +124,10 @@ struct Ctx {
     // phase alignment of the warps of a CTA (K_evolve): shared progress words, warps in the CTA, this warp, loop iteration
     int* al_phase; int al_n; int al_warp; int al_iter;
     int libm_sensitive;      // rec / sqrt calls whose result could change with the last bits of log / pow (ab200_series.cuh)
+    // tm_compose: power-table base and accuracy per inner model; arrays indexed at run time, kept here (shared memory in the
+    // kernels) rather than on the stack, where every lookup in the term x factor loop would be a local-memory transaction
+    int cmp_tab[AB_MAXARGS + 1];
+    Acc cmp_acc[AB_MAXARGS + 1];
 };
 #define AB_BINOM_N 64
 #define AB_BINOM_K 24
@@ -134,12 +141,12 @@ inline void binom_fill(uint32_t* t) {
 struct BinomTab { uint32_t t[AB_BINOM_N * AB_BINOM_K]; BinomTab() { binom_fill(t); } };
 inline const uint32_t* binom_host() { static BinomTab b; return b.t; }
 AB_HD void ctx_init(Ctx& c, uint64_t* arena, int limit, uint64_t* sm, const uint32_t* binom) {
-    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = wlane(); c.sm = sm; c.binom = binom; c.sm_dirty = 1; c.flops = 0.0;
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.sm = sm; c.binom = binom; c.sm_dirty = 1; c.flops = 0.0;
     c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0; c.libm_sensitive = 0;
 }
 // host-side callers (no warp, no shared area)
 inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
-    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.lane = 0; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1; c.flops = 0.0;
+    c.A.base = arena; c.A.top = 0; c.A.limit = limit; c.A.peak = 0; c.rnd = RN; c.status = ST_OK; c.sm = 0; c.binom = binom_host(); c.sm_dirty = 1; c.flops = 0.0;
     c.al_phase = 0; c.al_n = 1; c.al_warp = 0; c.al_iter = 0; c.libm_sensitive = 0;
 }
 
@@ -153,7 +160,7 @@ inline void ctx_init_host(Ctx& c, uint64_t* arena, int limit) {
 #endif
 AB_HD void cta_publish(Ctx& c, int stage) {
 #if defined(__CUDA_ARCH__)
-    if (c.al_n > 1 && c.lane == 0) ((volatile int*)c.al_phase)[c.al_warp] = (c.al_iter << 6) | stage;
+    if (c.al_n > 1 && wlane() == 0) ((volatile int*)c.al_phase)[c.al_warp] = (c.al_iter << 6) | stage;
 #endif
 }
 AB_HDN void cta_align(Ctx& c, int stage) {
@@ -163,7 +170,7 @@ AB_HDN void cta_align(Ctx& c, int stage) {
     const int my = (c.al_iter << 6) | stage;
     volatile int* ph = (volatile int*)c.al_phase;
     __syncwarp();
-    if (c.lane == 0) ph[c.al_warp] = my;
+    if (wlane() == 0) ph[c.al_warp] = my;
     int spins = 0;
     for (;;) {
         int lo = my;
@@ -179,11 +186,11 @@ AB_HD uint64_t& aw(Ctx& c, int i) { return c.A.base[i]; }
 AB_HD void fail(Ctx& c, int st) { if (c.status == ST_OK) c.status = st; }
 #ifdef AB_MUL_HIST
 extern long long g_calls[16], g_words[16];   // development counters (tests/tools/hostdbg.cpp)
-#define AB_CALL(id, w) do { if (c.lane == 0) { g_calls[id]++; g_words[id] += (w); } } while (0)
+#define AB_CALL(id, w) do { if (wlane() == 0) { g_calls[id]++; g_words[id] += (w); } } while (0)
 // Algorithmic FP64 operations of the REFERENCE algorithm by the per-primitive formulas of SURVEY.md 8(d), evaluated on
 // the actual term counts (host development builds only; the figure bench.py quotes comes from these counters).
 extern double g_flops;
-#define AB_FLOPS(n) do { if (c.lane == 0) g_flops += (double)(n); } while (0)
+#define AB_FLOPS(n) do { if (wlane() == 0) g_flops += (double)(n); } while (0)
 #elif defined(AB_COUNT_FLOPS)
 // Device builds: the same count kept per cell (warp-uniform, one FP64 add per primitive call) and returned with the lap's
 // status, so that the FP64 roofline of bench.py is measured on the run itself.
@@ -236,7 +243,7 @@ AB_HD void tm_append(Ctx& c, TM& r, const Key& k, double v) {
 AB_HDN void tm_slide(Ctx& c, TM& x, int dst) { AB_CALL(2, x.off == dst ? 0 : x.n);
     if (x.off != dst) {
         wsync();
-        const int nw = x.n * AB_TW, src = x.off, W = AB_W, lane = c.lane;
+        const int nw = x.n * AB_TW, src = x.off, W = AB_W, lane = wlane();
         uint64_t* const base = c.A.base;
         if (src - dst >= nw) { for (int i = lane; i < nw; i += W) base[dst + i] = base[src + i]; }
         else for (int i0 = 0; i0 < nw; i0 += W) {      // overlapping: a chunk is read by all lanes before it is written
@@ -257,7 +264,7 @@ AB_HDN TM tm_copy(Ctx& c, const TM& x) { AB_CALL(3, x.n);
     if (!arena_room(c, r.off, x.n)) return r;
     { uint64_t* const base = c.A.base; const int dst = r.off, src = x.off, W = AB_W;
       #pragma unroll 1
-      for (int i = c.lane; i < nw; i += W) base[dst + i] = base[src + i]; }
+      for (int i = wlane(); i < nw; i += W) base[dst + i] = base[src + i]; }
     wsync();
     r.n = x.n; r.e = x.e;
     c.A.top = r.off + nw;
@@ -273,7 +280,7 @@ AB_HD int tm_degree(Ctx& c, const TM& x) { return x.n == 0 ? 0 : key_deg(tm_key(
 AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_FLOPS(4 * r.n + 3); AB_CALL(4, r.n);
     if (s == 0) { r.n = 0; r.e = 0; return; }     // (arena words stay allocated; harmless)
     if (s == 1) return;
-    const int W = AB_W, lane = c.lane, n = r.n;
+    const int W = AB_W, lane = wlane(), n = r.n;
     wsync();
     if (s == 2 || s == 0.5) {
         const int m = c.rnd;
@@ -301,7 +308,7 @@ AB_HDN void tm_scal(Ctx& c, TM& r, double s) { AB_FLOPS(4 * r.n + 3); AB_CALL(4,
 }
 // _scal(TaylorModel&, Interval) src/taylor_model.cpp:276-314
 AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_FLOPS(5 * r.n + 4); AB_CALL(5, r.n);
-    const int W = AB_W, lane = c.lane, n = r.n;
+    const int W = AB_W, lane = wlane(), n = r.n;
     wsync();
     double te = 0; const double cu = s.u, mcl = -s.l;
     const double m = add_rn(s.u, s.l) / 2;
@@ -324,7 +331,7 @@ AB_HDN void tm_scal(Ctx& c, TM& r, Ivl s) { AB_FLOPS(5 * r.n + 4); AB_CALL(5, r.
 }
 // Insert a constant term in front of a model that is the LAST thing on the arena.
 AB_HDN void tm_prepend_top(Ctx& c, TM& r, double v) {
-    const int nw = r.n * AB_TW, W = AB_W, lane = c.lane;
+    const int nw = r.n * AB_TW, W = AB_W, lane = wlane();
     if (!arena_room(c, r.off, r.n + 1)) return;
     uint64_t* const base = c.A.base;
     wsync();
@@ -445,7 +452,7 @@ AB_HD uint32_t acc_hash(const AccTab& T, const Key& k) {
 }
 // Place the accumulator in the warp's shared area (attempt 0) or above `above` in the arena with room for `want` entries.
 AB_HD bool acc_open(Ctx& c, AccTab& T, int attempt, int above, long long want) {
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     wsync();
     if (attempt == 0 && c.sm) {
         c.sm_dirty = 1;
@@ -524,7 +531,7 @@ AB_HD double acc_fold(AccTab& T, int slot, double tv) {
 }
 // Add the terms of model t as one stream; returns te, the upward sum of the rounding gaps in key order.
 AB_HD double acc_add_model(Ctx& c, AccTab& T, const TM& t) {
-    const int W = AB_W, lane = c.lane, n = t.n;
+    const int W = AB_W, lane = wlane(), n = t.n;
     const uint64_t* const base = c.A.base;
     double te = 0.0;
     #pragma unroll 1
@@ -567,7 +574,7 @@ AB_HD uint32_t key_rank(const uint32_t* tab, const Key& k, int as) {
 // Ordering of the accumulator for monomial spaces too large for the rank bitmap: bitonic sort of the entry numbers by key
 // (in the hash index area, which is no longer needed). Kept out of acc_emit so that the common path stays small.
 AB_HDN int acc_emit_sorted(Ctx& c, const AccTab T, int dst) {
-    const int W = AB_W, lane = c.lane, nd = T.nd;
+    const int W = AB_W, lane = wlane(), nd = T.nd;
     uint64_t* const base = c.A.base;
     int P = 1; while (P < nd) P <<= 1;
     uint32_t* perm = T.idx;                       // index area holds >= 2*cap cells
@@ -616,7 +623,7 @@ AB_HDN int acc_emit_sorted(Ctx& c, const AccTab T, int dst) {
 // Write the accumulator to the arena at word `dst` in key order, skipping dropped entries; returns the number of terms.
 // `scratch` is shared (or arena) memory free for the ordering: gap-code and staging areas when the table is in shared memory.
 AB_HDN int acc_emit(Ctx& c, const AccTab T, int as, int maxdeg, int dst) {
-    const int W = AB_W, lane = c.lane, nd = T.nd;
+    const int W = AB_W, lane = wlane(), nd = T.nd;
     uint64_t* const base = c.A.base;
     if (nd == 0) return 0;
     if (!arena_room(c, dst, nd)) return 0;
@@ -693,7 +700,7 @@ AB_HD bool dacc_fits(const Ctx& c, int as, int D) {
 // The rank table B[k][s] = C(s-1+k, k), k = 1..7, s = 0..35, staged once per cell (ctx_stage_tables).
 AB_HDN void ctx_stage_tables(Ctx& c) {
     if (!c.sm || !c.binom) return;
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     const smaddr_t bt = sm_addr(c.sm + AB_SM_OFF_BTAB);
     wsync();
     #pragma unroll 1
@@ -705,7 +712,7 @@ AB_HDN void ctx_stage_tables(Ctx& c) {
 }
 // Empty every entry of the dense accumulator (at the start of a cell and after the hash accumulator has used the area).
 AB_HDN void dacc_clear_all(Ctx& c) {
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     const smaddr_t val = sm_addr(c.sm);
     wsync();
     #pragma unroll 1
@@ -755,7 +762,7 @@ AB_HD double dacc_fold(DAcc& A, int r, const Key& k, double tv, bool* coincident
 }
 // Add the terms of model t as one stream; returns te, the upward sum of the rounding gaps in key order.
 AB_HDN double dacc_add_model(Ctx& c, DAcc& A, const TM& t, bool gaps) {
-    const int W = AB_W, lane = c.lane, n = t.n;
+    const int W = AB_W, lane = wlane(), n = t.n;
     const uint64_t* const base = c.A.base;
     double te = 0.0;
     #pragma unroll 1
@@ -782,7 +789,7 @@ AB_HD uint32_t dacc_touched(const DAcc& A, int lane) {
 // Write the entries in use to the arena at word `dst`, in rank (= key) order, and leave the accumulator empty; returns the
 // number of terms. (dst < 0: only empty it.)
 AB_HDN int dacc_emit(Ctx& c, DAcc& A, int dst) {
-    const int lane = c.lane, R = A.R;
+    const int lane = wlane(), R = A.R;
     uint64_t* const base = c.A.base;
     wsync();
     uint32_t blocks = dacc_touched(A, lane);
@@ -878,7 +885,7 @@ AB_HDN TM tm_neg(Ctx& c, const TM& x) { AB_CALL(6, x.n);
     if (!arena_room(c, r.off, x.n)) return r;
     uint64_t* const base = c.A.base; const int W = AB_W;
     #pragma unroll 1
-    for (int i = c.lane; i < x.n; i += W) bput(base, r.off + i * AB_TW, bkey(base, x.off + i * AB_TW), -bval(base, x.off + i * AB_TW));
+    for (int i = wlane(); i < x.n; i += W) bput(base, r.off + i * AB_TW, bkey(base, x.off + i * AB_TW), -bval(base, x.off + i * AB_TW));
     wsync();
     r.n = x.n; r.e = x.e;
     c.A.top = r.off + r.n * AB_TW;
@@ -921,7 +928,7 @@ extern long long g_mul_prod[8][8];
 // compacted over the discarded products, and the error chain of the general path reduces to the truncation terms.
 AB_HDN TM tm_mul_simple(Ctx& c, const TM& x, const TM& y, Acc acc) {
     uint64_t* const base = c.A.base;
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     const int m = c.A.top;
     const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
     const double xe = x.e, ye = y.e;
@@ -985,7 +992,7 @@ AB_HDN TM tm_mul_simple(Ctx& c, const TM& x, const TM& y, Acc acc) {
 // by one lane per x-term.
 AB_HDN TM tm_mul_general_dense(Ctx& c, const TM& x, const TM& y, Acc acc, int D) {
     uint64_t* const base = c.A.base;
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     const int m = c.A.top;
     const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
     const double xe = x.e, ye = y.e;
@@ -1068,7 +1075,7 @@ AB_HDN TM tm_mul_general(Ctx& c, const TM& x, const TM& y, Acc acc) {
       if (y.n <= AB_SM_YCAP && dacc_fits(c, x.as, Dd)) return tm_mul_general_dense(c, x, y, acc, Dd); }
 
     uint64_t* const base = c.A.base;
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     const int m = c.A.top;
     const int xoff = x.off, xn = x.n, yoff = y.off, yn = y.n, as = x.as;
     const double xe = x.e, ye = y.e;
@@ -1080,7 +1087,7 @@ AB_HDN TM tm_mul_general(Ctx& c, const TM& x, const TM& y, Acc acc) {
     int D = tm_degree(c, x) + tm_degree(c, y); if (D > maxdeg) D = maxdeg;
     long long bound = monomial_count(c.binom, D, as);
 #ifdef AB_MULG_STATS
-    if (c.lane == 0) { extern long long g_mg[64][4]; int b = 0; while ((1LL << b) < bound && b < 20) ++b; g_mg[b][0]++; g_mg[b][1] += (long long)xn * yn; g_mg[40 + (as < 20 ? as : 19)][0]++; g_mg[40 + (as < 20 ? as : 19)][1] += (long long)xn * yn; if (D > g_mg[63][0]) g_mg[63][0] = D; }
+    if (wlane() == 0) { extern long long g_mg[64][4]; int b = 0; while ((1LL << b) < bound && b < 20) ++b; g_mg[b][0]++; g_mg[b][1] += (long long)xn * yn; g_mg[40 + (as < 20 ? as : 19)][0]++; g_mg[40 + (as < 20 ? as : 19)][1] += (long long)xn * yn; if (D > g_mg[63][0]) g_mg[63][0] = D; }
 #endif
     { const long long prod = (long long)xn * (long long)yn; if (prod < bound) bound = prod; }
     double re = 0.0;
@@ -1193,7 +1200,7 @@ AB_HDN TM tm_mul_general(Ctx& c, const TM& x, const TM& y, Acc acc) {
 }
 AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y, Acc acc) {
 #ifdef AB_MUL_HIST
-    if (c.lane == 0) { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
+    if (wlane() == 0) { int bx = 0, by = 0; while ((1 << bx) < x.n && bx < 7) ++bx; while ((1 << by) < y.n && by < 7) ++by; g_mul_hist[bx][by]++; g_mul_prod[bx][by] += (long long)x.n * y.n; }
 #endif
     AB_FLOPS((double)x.n * (5.0 * y.n + 3.0) + 2.0 * (x.n + y.n) + 6.0);
     return (x.n <= 1 || y.n <= 1) ? tm_mul_simple(c, x, y, acc) : tm_mul_general(c, x, y, acc);
@@ -1204,7 +1211,7 @@ AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc
 // are added to the error upward, in term order. Returns through x.
 #define AB_FILTER_IN_PLACE(c, x, DROP_EXPR)                                                                        \
     do {                                                                                                           \
-        const int W_ = AB_W, lane_ = (c).lane, n_ = (x).n; int k_ = 0; double e_ = (x).e;                         \
+        const int W_ = AB_W, lane_ = wlane(), n_ = (x).n; int k_ = 0; double e_ = (x).e;                         \
         wsync();                                                                                                   \
         for (int i0_ = 0; i0_ < n_; i0_ += W_) {                                                                   \
             const int i_ = i0_ + lane_; const bool act_ = i_ < n_;                                                 \
@@ -1224,7 +1231,7 @@ AB_HD TM tm_mul(Ctx& c, const TM& x, const TM& y) { return tm_mul(c, x, y, y.acc
 // key KEY_EXPR and coefficient VAL_EXPR; the expressions see the source term as `a` (Key) and `v` (double).
 #define AB_FILTER_COPY(c, r, x, KEEP_EXPR, KEY_EXPR, VAL_EXPR)                                                     \
     do {                                                                                                           \
-        const int W_ = AB_W, lane_ = (c).lane, n_ = (x).n; int k_ = (r).n;                                        \
+        const int W_ = AB_W, lane_ = wlane(), n_ = (x).n; int k_ = (r).n;                                        \
         wsync();                                                                                                   \
         if (arena_room(c, (r).off, k_ + n_)) {                                                                     \
             for (int i0_ = 0; i0_ < n_; i0_ += W_) {                                                               \
@@ -1252,7 +1259,7 @@ AB_HDN void tm_clean(Ctx& c, TM& x, Acc acc) { AB_FLOPS(x.n + 2);
 }
 // upward sum of the coefficient magnitudes of the terms of positive degree (all terms if with_constant), starting from s
 AB_HD double tm_abs_sum(Ctx& c, const TM& x, double s, bool with_constant, double* constant) {
-    const int W = AB_W, lane = c.lane, n = x.n;
+    const int W = AB_W, lane = wlane(), n = x.n;
     double cv = 0.0;
     #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += W) {
@@ -1332,7 +1339,7 @@ AB_HD TM tm_embed(Ctx& c, const TM& x, int extra) { TM r = tm_copy(c, x); r.as =
 
 // antidifferentiate(k) src/taylor_model.cpp:2251-2284 -- in place
 AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) { AB_FLOPS(4 * x.n + 2);
-    const int W = AB_W, lane = c.lane, n = x.n;
+    const int W = AB_W, lane = wlane(), n = x.n;
     wsync();
     double tre = 0;
     #pragma unroll 1
@@ -1361,7 +1368,7 @@ AB_HDN void tm_antidiff(Ctx& c, TM& x, int k) { AB_FLOPS(4 * x.n + 2);
 // then treated independently, and the result error is a maximum, which does not depend on the order.
 // intersection on the dense accumulator: x's coefficient in the entry, y's beside it (gap-code area)
 AB_HDN bool tm_intersection_dense(Ctx& c, const TM& x, const TM& y, TM& out, int D) {
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     const uint64_t* const base = c.A.base;
     const int m = c.A.top;
     TM r = tm_begin(c, x.as, x.acc);
@@ -1426,7 +1433,7 @@ AB_HDN bool tm_intersection(Ctx& c, const TM& x, const TM& y, TM& out) {
     { int Dd = tm_degree(c, x); const int d2 = tm_degree(c, y); if (d2 > Dd) Dd = d2;
       if (AB_SM_DENSE <= AB_SM_G16 / 4 && dacc_fits(c, x.as, Dd)) { AB_FLOPS(1 + 12 * (x.n + y.n)); return tm_intersection_dense(c, x, y, out, Dd); } }
 
-    const int W = AB_W, lane = c.lane;
+    const int W = AB_W, lane = wlane();
     uint64_t* const base = c.A.base;
     const int m = c.A.top;
     TM r = tm_begin(c, x.as, x.acc);
