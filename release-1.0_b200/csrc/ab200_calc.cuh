@@ -362,7 +362,7 @@ struct ChainState {
 // {ka: va, error xe} * p with accuracy acc (_mul4 with a one-term left factor, src/taylor_model.cpp:763-824): the products are
 // folded straight into the accumulator as one stream when `fold` is set (last factor of the chain), else the survivors become
 // the new state. Returns te, the gap sum of the stream (fold only); *te_out error of the product.
-AB_HDN double chain_times_power(Ctx& c, DAcc& DA, ChainState& st, const TM& p, int pslot, Acc acc, bool fold, double* e_out) {
+AB_HD double chain_times_power(Ctx& c, DAcc& DA, ChainState& st, const TM& p, int pslot, Acc acc, bool fold, double* e_out) {
     const int W = AB_W, lane = wlane(), n = p.n, soff = p.off;
     uint64_t* const base = c.A.base;
     const Key fa = st.ka; const double fv = st.va, afv = dabs(fv), xe = st.e;

@@ -381,7 +381,7 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
 // hash accumulator (index | keys | coefficients) otherwise. When even that is outgrown the hash accumulator is rebuilt in the
 // free part of the arena (same code, generic pointers).
 #ifndef AB_SM_ACCW
-#define AB_SM_ACCW 1024
+#define AB_SM_ACCW 1536
 #endif
 #define AB_SM_BTABW 128
 // Dense accumulator: coefficients of AB_SM_DENSE ranks, then their keys. With at most 3 variables a key is the upper half
@@ -390,7 +390,7 @@ AB_HDN void tm_acc(Ctx& c, TM& r, Ivl s) { AB_FLOPS(6);
 #define AB_SM_DENSE (2 * AB_SM_ACCW / 3)
 #define AB_BTAB_STRIDE 36                               // rank-table row: sums of exponents 0..35
 #ifndef AB_SM_NIDX
-#define AB_SM_NIDX 512
+#define AB_SM_NIDX 1024
 #endif
 #define AB_SM_CAP ((AB_SM_ACCW - AB_SM_NIDX / 2) / (AB_KW + 1))
 #ifndef AB_SM_G16
