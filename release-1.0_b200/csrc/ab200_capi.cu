@@ -41,7 +41,7 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, const int32_t* cell_loc, c
 // A batch this large goes to the lane build (one-word keys only). Below it the warp build is faster: a lap of the lane build
 // costs the latency of its slowest cell (seconds), whatever the frontier.
 #ifndef AB_LANE_THRESHOLD
-#define AB_LANE_THRESHOLD 24576
+#define AB_LANE_THRESHOLD 36864
 #endif
 #define AB_LANE_ARENA_WORDS 12288
 struct EvolveBuild {
