@@ -91,7 +91,7 @@ extern long long g_cs[8];
 #else
 #define AB_CHAIN_STAT(i, n)
 #endif
-AB_HDN double chain_ru(double s, double v, int cnt) {
+AB_HD double chain_ru(double s, double v, int cnt) {
     AB_CHAIN_STAT(5, cnt);
     int k = 0;
     #pragma unroll 1
@@ -110,7 +110,7 @@ AB_HDN double chain_m(int m, double s, double v, int cnt) {
     return s;
 }
 // Chain over the lanes flagged in `mask` only, in lane order.
-AB_HDN double chain_ru_masked(double s, double v, unsigned mask) {
+AB_HD double chain_ru_masked(double s, double v, unsigned mask) {
     AB_CHAIN_STAT(6, popc32(mask)); AB_CHAIN_STAT(7, 1);
     #pragma unroll 1
     while (mask) { const int k = ffs32(mask) - 1; mask &= mask - 1; s = add_ru(s, wshfl(v, k)); }
