@@ -252,6 +252,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args.cpu_cells or 32 * (os.cpu_count() or 1))
         _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     an.close()
+    if parity and parity.get("verdict") == "MISMATCH":
+        raise SystemExit("bench.py: the lap's cell sets differ from the reference's fingerprint (see the parity field of the line)")
     if world > 1:
         dist.destroy_process_group()
 

@@ -350,6 +350,32 @@ def test_constraint_set_initial_sets_identical_cells(pkg, system, name, domain, 
         an.close()
 
 
+def test_bench_lap_matches_the_reference_fingerprint(pkg):
+    """The benchmark's own workload at full size: van der Pol, accuracy 7, all 101,520 frontier cells, one lock-to-grid lap
+    (the lane build). Its reach / evolve sets must be, leaf cell for leaf cell, what the compiled reference's
+    UpperReachEvolveWorker::get_result() returns on the same frontier (tests/golden/vanderpol_bench_fingerprint.json, 13.5
+    CPU-hours of the reference in six chunks, tests/golden/make_bench_fingerprint.sh)."""
+    import json
+    import sys as _sys
+    _sys.path.insert(0, golden_io.GOLDEN)
+    from bench_fingerprint import leaf_fingerprint
+    want = json.load(open(os.path.join(golden_io.GOLDEN, "vanderpol_bench_fingerprint.json")))
+    an = pkg.HybridReachabilityAnalyser(_system(), [-3.0, 3.0, -3.0, 3.0], 7, settings={"arena_words": 32768, "max_boxes": 320, "hash_log2": 25})
+    try:
+        initial = an.discretise({0: [-2.2, 2.2, -2.8, 2.8]})
+        _, cells = an.enumerate(initial, mince=True)
+        assert cells.shape[0] == want["frontier_cells"] == 101520
+        an.upper_reach_evolve({0: [1.0, 1.0 + 1e-3, 1.0, 1.0 + 1e-3]}, 1e-3, 5)            # the tuning upload of a lap
+        ev = an.evolver
+        reach, evolve = ev.upper_reach_evolve(np.zeros((cells.shape[0],), dtype=np.int32), pkg.pack_boxes(cells, 2), an.lock_to_grid_time, 5)
+        assert ev.last_status.build == 2
+        for name, cs in (("reach", reach), ("evolve", evolve)):
+            got = leaf_fingerprint(ev.decode(cs.keys)[:, 1:3])
+            assert got["cells"] == want[name]["cells"] and got["sha256"] == want[name]["sha256"], name
+    finally:
+        an.close()
+
+
 def test_flow_bounds_facade(pkg):
     d = golden_io.load_dump("vanderpol_cells_acc6.txt.gz")
     ev = _evolver(pkg, d)
