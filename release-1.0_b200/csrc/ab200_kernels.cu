@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include "ab200_evolve.cuh"
 #include "ab200_jump.cuh"
+#include "ab200_kat.cuh"
 #include "ab200_grid.cuh"
 #include "ab200_device.h"
 
@@ -94,37 +95,8 @@ K_tm_op(const uint64_t* __restrict__ in, uint64_t* __restrict__ arena, int arena
         m[q].e = e;
         wsync();
     }
-    const TM& x = m[0]; const TM& y = m[1];
-    TM r = tm_begin(c, as, acc_default());
-    Ivl rng = ivl(0.0, 0.0); int st = ST_OK;
-    switch (op) {
-    case 0: r = tm_add(c, x, y); break;                                            // operator+(TaylorModel,TaylorModel)
-    case 1: r = tm_sub(c, x, y); break;
-    case 2: r = tm_mul(c, x, y); break;
-    case 3: r = tm_copy(c, x); tm_acc(c, r, s); break;                              // x+Float: _acc
-    case 4: r = tm_copy(c, x); tm_acc(c, r, -s); break;                             // x-Float
-    case 5: r = tm_copy(c, x); tm_scal(c, r, s); break;                             // x*Float: _scal
-    case 6: r = tm_copy(c, x); tm_scal(c, r, ivl_div(ivl(1.0), s)); break;          // x/Float: _scal(Interval(1)/c)
-    case 7: r = tm_copy(c, x); tm_acc(c, r, iv); break;
-    case 8: r = tm_copy(c, x); tm_acc(c, r, ivl_neg(iv)); break;
-    case 9: r = tm_copy(c, x); tm_scal(c, r, iv); break;
-    case 10: r = tm_copy(c, x); tm_scal(c, r, ivl_div(1.0, iv, &st)); break;        // x/Interval: _scal(1/c)
-    case 11: r = tm_neg(c, x); break;
-    case 12: if (!tm_intersection(c, x, y, r)) fail(c, ST_DOMAIN); break;
-    case 13: r = tm_split(c, x, k, flag != 0); break;
-    case 14: r = tm_copy(c, x); tm_antidiff(c, r, k); break;
-    case 15: r = tm_rec(c, x); break;
-    case 16: r = tm_sqrt(c, x); break;
-    case 17: r = tm_abs(c, x); break;
-    case 18: r = tm_max(c, x, y); break;
-    case 19: rng = tm_range(c, x); r = tm_copy(c, x); break;
-    case 20: r = tm_exp(c, x); break;
-    case 21: r = tm_log(c, x); break;
-    case 22: r = tm_sincos(c, x, true); break;
-    case 23: r = tm_sincos(c, x, false); break;
-    default: fail(c, ST_UNSUPPORTED);
-    }
-    if (st != ST_OK) fail(c, st);
+    Ivl rng = ivl(0.0, 0.0);
+    TM r = kat_tm_op(c, op, m[0], m[1], k, flag, s, iv, &rng);
     wsync();
     if (wlane() == 0) {
         int w = 4;
@@ -141,32 +113,8 @@ __global__ void K_interval_op(int n, const double* __restrict__ in, double* __re
     if (i >= n) return;
     const int op = (int)in[6 * i], m = (int)in[6 * i + 1];
     const Ivl a = ivl(in[6 * i + 2], in[6 * i + 3]), b = ivl(in[6 * i + 4], in[6 * i + 5]);
-    Ivl r = ivl(0.0, 0.0); int st = ST_OK;
-    switch (op) {
-    case 0: r = ivl_add(a, b); break;
-    case 1: r = ivl_sub(a, b); break;
-    case 2: r = ivl_mul(a, b); break;
-    case 3: r = ivl_div(a, b, &st); break;
-    case 4: r = ivl_add(a, b.l); break;
-    case 5: r = ivl_sub(a, b.l); break;
-    case 6: r = ivl_mul(a, b.l); break;
-    case 7: r = ivl_div(a, b.l); break;
-    case 8: r = ivl_sub(a.l, b); break;
-    case 9: r = ivl_div(a.l, b, &st); break;
-    case 10: r = ivl_sqr(a); break;
-    case 11: r = ivl_sqrt(a, &st); break;
-    case 12: r = ivl_pow(a, (unsigned)m); break;
-    case 13: r = ivl_rec(a, &st); break;
-    case 14: r = ivl_abs(a); break;
-    case 15: r = ivl_neg(a); break;
-    case 16: r = ivl_max(a, b); break;
-    case 17: r = ivl_min(a, b); break;
-    case 18: r = ivl_exp(a); break;
-    case 19: r = ivl_log(a, &st); break;
-    case 20: r = ivl_sin(a, RN); break;
-    case 21: r = ivl_cos(a, RN); break;
-    default: st = ST_UNSUPPORTED;
-    }
+    int st = ST_OK;
+    const Ivl r = kat_interval_op(op, m, a, b, &st);
     out[3 * i] = r.l; out[3 * i + 1] = r.u; out[3 * i + 2] = (double)st;
 }
 

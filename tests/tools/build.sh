@@ -10,3 +10,4 @@ g++ $F -DAB_KW=2 -o build/hostdbg2 tests/tools/hostdbg.cpp $S
 g++ $F -o build/hoststep tests/tools/hoststep.cpp release-1.0_b200/csrc/ab200_system.cpp
 g++ $F -o build/hostlap tests/tools/hostlap.cpp $S
 g++ $F -x c++ -o build/hostchain tests/tools/hostchain.cpp $S
+g++ $F -o build/hostkat tests/tools/hostkat.cpp
