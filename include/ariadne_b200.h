@@ -42,6 +42,7 @@ typedef struct ab200_ctx ab200_ctx;
 typedef struct ab200_cellset ab200_cellset;   /* sorted, duplicate-free packed cell keys */
 typedef struct ab200_boxlist ab200_boxlist;   /* per-enclosure bounding boxes (parity / debugging) */
 typedef struct ab200_analyser ab200_analyser;
+typedef struct ab200_enclosures ab200_enclosures;   /* TaylorSet enclosures (set models) in the device's record format */
 
 /* ImageSetHybridEvolverSettings + TaylorCalculus orders (src/hybrid_evolver-image.cpp:1347-1359,
  * src/taylor_calculus.cpp:136-146) plus device sizing. ab200_default_settings fills the reference defaults. */
@@ -135,6 +136,25 @@ int  ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const int32_t* l
 int  ab200_boxlist_view(const ab200_boxlist* bl, const uint64_t** offsets, const double** boxes, const int32_t** locs);
 void ab200_boxlist_free(ab200_boxlist* bl);
 
+/* == EvolverInterface::reach_evolve(initial_enclosure, time, semantics) (include/evolver_interface.h:95-124) with the
+ * enclosures themselves handed over, as LowerReachEpsilonWorker::_compute needs (include/workers.h:264-303: the final
+ * TaylorSets of one lap are the initial sets of the next). Unit i starts from initial enclosure i when `initial` is given
+ * (n_units, loc and boxes are then ignored) and from box i otherwise. final_enclosures receives every final set as a
+ * TaylorSet -- the set models as the reference keeps them in Orbit::final(), src/hybrid_evolver-image.cpp:304 -- in unit
+ * order; the box lists are those of ab200_reach_evolve_boxes. max_enclosure_words bounds the records of one unit
+ * (0 = 16384 words; AB200_E_OUTPUT beyond it). The semantics is ab200_settings.semantics. Warp builds only. */
+int  ab200_reach_evolve_enclosures(ab200_ctx* ctx, uint64_t n_units, const int32_t* loc, const double* boxes, const ab200_enclosures* initial,
+                                   double t_continuous, int32_t max_events, int ignore_activations, int direction, int32_t max_enclosure_words,
+                                   ab200_boxlist** reach_out, ab200_boxlist** final_out, ab200_enclosures** final_enclosures, ab200_status* status);
+/* count enclosures with their locations; unit_offsets has n_units+1 entries (enclosures of unit u: [unit_offsets[u], unit_offsets[u+1])). */
+int  ab200_enclosures_view(const ab200_enclosures* e, uint64_t* count, const int32_t** locs, const uint64_t** unit_offsets, uint64_t* n_units);
+/* Coordinate model k of enclosure i as a TaylorModel: exps is [n_terms][nargs] (MultiIndex), coefs [n_terms]; pass NULL for
+ * exps / coefs to query nargs, n_terms and the uniform error only. */
+int  ab200_enclosures_model(const ab200_enclosures* e, uint64_t i, int32_t k, int32_t* nargs, int32_t* n_terms, double* error, uint8_t* exps, double* coefs);
+/* The enclosures idx[0..n) of src as a new list (ReachabilityRestriction::filter, _filter_enclosures keep a subset). */
+int  ab200_enclosures_select(const ab200_enclosures* src, uint64_t n, const uint64_t* idx, ab200_enclosures** out);
+void ab200_enclosures_free(ab200_enclosures* e);
+
 /* == IntegratorInterface::flow_bounds (include/integrator_interface.h:45-50) with the TaylorCalculus constants
  * (src/taylor_calculus.cpp:55-133,584-600). */
 int  ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
@@ -199,6 +219,21 @@ int  ab200_analyser_upper_reach_evolve(ab200_analyser* an, uint64_t n_init, cons
 int  ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
                                        double T, int32_t max_events,
                                        ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status);
+/* HybridReachabilityAnalyser::epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627) with
+ * LowerReachEpsilonWorker (include/workers.h:171-329) on the device, for an empty constraint set and singleton parameters
+ * (the verifier's parameter splitting and constraint checking are out of scope): the midpoints of the discretised initial
+ * cells are evolved with LOWER_SEMANTICS one lock-to-grid lap at a time, the final TaylorSets of a lap being the initial
+ * sets of the next, until a lap reaches no new cell. epsilon_out is [n_locations][AB200_MAX_DIM]: per location the largest
+ * reach-enclosure widths plus one cell (HybridFloatVector). prune = Settings::enable_lower_pruning (the reference default is
+ * 1): a final enclosure is kept with probability 2 * adjoined / superposed evolve cells of its location, drawn from glibc's
+ * rand() sequence for seed 1 in unit order -- what the reference draws in a fresh process whose worker runs one thread;
+ * with more threads the reference's own result depends on their completion order. AB200_E_DOMAIN as in lower_reach_evolve.
+ * substituted_system_text (or NULL): the system with its nonsingleton parameters at their midpoints, in the format of
+ * ab200_set_system_text. The reference evolves that system (_system->substitute_all(midpoints), :517-527) while the grid and
+ * the lock time stay those of the analyser's own system; the context's system is put back before the call returns. */
+int  ab200_analyser_epsilon_lower_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, int32_t prune,
+                                              const char* substituted_system_text,
+                                              ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status);
 /* direction: 0 = DIRECTION_FORWARD (forward_jump_set between laps), 1 = DIRECTION_BACKWARD (backward_jump_set,
  * src/reachability_restriction.cpp:381-408, src/set_checker.cpp:229-352). */
 int  ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,

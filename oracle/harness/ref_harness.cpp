@@ -226,6 +226,9 @@ int main(int argc, char** argv) {
     Config c=make_config(argv[1],kv);
     if(kv.count("chain")) c.chain=geti(kv,"chain",0)!=0;
     std::string mode(argv[2]);
+    // midparams=1: every nonsingleton parameter replaced by its midpoint, as epsilon_lower_chain_reach substitutes them
+    // (getMidpointsSet, src/reachability_analyser.cpp:1000-1014) -- used with mode "system" for the substituted system's text
+    if(geti(kv,"midparams",0)) { std::list<RealParameterSet> l; l.push_back(c.sys.nonsingleton_parameters()); c.sys.substitute_all(getMidpointsSet(l).front()); }
     FILE* out=stdout; if(kv.count("out")) out=fopen(kv["out"].c_str(),"w");
     int verb=geti(kv,"verb",0);
 
@@ -307,9 +310,13 @@ int main(int argc, char** argv) {
         for(std::list<HEncl>::const_iterator it=encl.begin(); it!=encl.end() && done<ncells; ++it,++k,++cell_it) {
             if(k<offset || (k-offset)%stride) continue;
             ++done;
-            fprintf(out,"cell %d loc %s box",k,it->first.name().c_str()); dump_box(out,cell_it->second); fprintf(out,"\n");
+            // midpoints=1: the enclosure is the centre of (cell box ^ initial box), as lower_reach_evolve and
+            // epsilon_lower_chain_reach start (_enclosures_from_discretised_initial_set_midpoints, src/reachability_analyser.cpp:1220-1241)
+            HEncl start=*it; Box start_box=cell_it->second;
+            if(geti(kv,"midpoints",0)) { Box isect=intersection(Box(cell_it->second),c.initial.find(it->first)->second.domain()); start_box=Box(isect.centre()); start=HEncl(it->first,HEncl::second_type(start_box)); }
+            fprintf(out,"cell %d loc %s box",k,it->first.name().c_str()); dump_box(out,start_box); fprintf(out,"\n");
             try {
-                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(*it,ht,ignore_act,geti(kv,"backward",0)?DIRECTION_BACKWARD:DIRECTION_FORWARD,geti(kv,"lower",0)?LOWER_SEMANTICS:UPPER_SEMANTICS);
+                std::pair<HEnclList,HEnclList> re=evolver.reach_evolve(start,ht,ignore_act,geti(kv,"backward",0)?DIRECTION_BACKWARD:DIRECTION_FORWARD,geti(kv,"lower",0)?LOWER_SEMANTICS:UPPER_SEMANTICS);
                 for(HEnclList::const_iterator r=re.first.begin(); r!=re.first.end(); ++r) {
                     fprintf(out,"r %s",r->first.name().c_str()); dump_box(out,r->second.bounding_box()); fprintf(out,"\n"); }
                 for(HEnclList::const_iterator r=re.second.begin(); r!=re.second.end(); ++r) {
@@ -352,6 +359,25 @@ int main(int argc, char** argv) {
         fprintf(out,"worker seconds %.6f cells %lu frontier %lu reach_cells %lu evolve_cells %lu threads %u\n",ws,n,(unsigned long)all.size(),
                 (unsigned long)res.first.size(),(unsigned long)res.second.size(),boost::thread::hardware_concurrency());
         if(geti(kv,"dump",0)) { dump_set(out,"reach",res.first); dump_set(out,"evolve",res.second); }   // full result, for fingerprints
+        return 0;
+    }
+
+    if(mode=="epslower") {
+        // epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627) with no constraint set. prune=0 switches
+        // enable_lower_pruning off (order-independent result); prune=1 keeps the default, whose rand() draws follow the
+        // order in which LowerReachEpsilonWorker's threads finish -- run it with ORACLE_THREADS=1 for a reproducible golden.
+        analyser.settings().enable_lower_pruning=geti(kv,"prune",1)!=0;
+        std::pair<HybridDenotableSet,HybridFloatVector> r; std::string err;
+        std::chrono::steady_clock::time_point t0=std::chrono::steady_clock::now();
+        try { r=analyser.epsilon_lower_chain_reach(c.initial); } catch(std::exception& e) { err=e.what(); }
+        double secs=std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
+        fprintf(out,"seconds %.3f err '%s' prune %d threads %u\n",secs,err.c_str(),geti(kv,"prune",1),boost::thread::hardware_concurrency());
+        for(HybridFloatVector::const_iterator ei=r.second.begin(); ei!=r.second.end(); ++ei) {
+            fprintf(out,"epsilon loc %s",ei->first.name().c_str());
+            for(uint i=0;i<ei->second.size();++i) fprintf(out," %a",ei->second[i]);
+            fprintf(out,"\n");
+        }
+        dump_set(out,"reach",r.first);
         return 0;
     }
 

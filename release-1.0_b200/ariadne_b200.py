@@ -36,6 +36,8 @@ EXPORTS = [
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
     "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
     "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free", "ab200_taylor_model_op", "ab200_interval_op", "ab200_analyser_discretise_constraint", "ab200_analyser_upper_reach_evolve_from", "ab200_analyser_outer_chain_reach_from",
+    "ab200_reach_evolve_enclosures", "ab200_enclosures_view", "ab200_enclosures_model", "ab200_enclosures_select", "ab200_enclosures_free",
+    "ab200_analyser_epsilon_lower_chain_reach",
 ]
 
 
@@ -113,6 +115,14 @@ def load_library():
     lib.ab200_analyser_upper_reach_evolve.restype = C.c_int
     lib.ab200_analyser_lower_reach_evolve.argtypes = [vp, u64, P(i32), P(dbl), dbl, i32, P(vp), P(vp), P(Status)]
     lib.ab200_analyser_lower_reach_evolve.restype = C.c_int
+    lib.ab200_analyser_epsilon_lower_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), i32, C.c_char_p, P(vp), P(dbl), P(i32), P(Status)]
+    lib.ab200_analyser_epsilon_lower_chain_reach.restype = C.c_int
+    lib.ab200_reach_evolve_enclosures.argtypes = [vp, u64, P(i32), P(dbl), vp, dbl, i32, C.c_int, C.c_int, i32, P(vp), P(vp), P(vp), P(Status)]
+    lib.ab200_reach_evolve_enclosures.restype = C.c_int
+    lib.ab200_enclosures_view.argtypes = [vp, P(u64), P(P(i32)), P(P(u64)), P(u64)]; lib.ab200_enclosures_view.restype = C.c_int
+    lib.ab200_enclosures_model.argtypes = [vp, u64, i32, P(i32), P(i32), P(dbl), P(C.c_uint8), P(dbl)]; lib.ab200_enclosures_model.restype = C.c_int
+    lib.ab200_enclosures_select.argtypes = [vp, u64, P(u64), P(vp)]; lib.ab200_enclosures_select.restype = C.c_int
+    lib.ab200_enclosures_free.argtypes = [vp]; lib.ab200_enclosures_free.restype = None
     lib.ab200_ctx_get_settings.argtypes = [vp, P(Settings)]; lib.ab200_ctx_get_settings.restype = C.c_int
     lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), i32, P(vp), P(Status)]
     lib.ab200_analyser_outer_chain_reach.restype = C.c_int
@@ -191,6 +201,50 @@ def _take_boxlist(lib, handle, n_cells):
     return offsets, boxes, locs
 
 
+class Enclosures(object):
+    """A list of TaylorSet enclosures (ab200_enclosures) as the evolution returns its final sets: the hand-over between
+    the laps of LowerReachEpsilonWorker (include/workers.h:299-302)."""
+
+    def __init__(self, lib, handle):
+        self.lib = lib; self._handle = handle
+        n = C.c_uint64(0); lc = C.POINTER(C.c_int32)(); uo = C.POINTER(C.c_uint64)(); nu = C.c_uint64(0)
+        lib.ab200_enclosures_view(handle, C.byref(n), C.byref(lc), C.byref(uo), C.byref(nu))
+        self.locs = np.ctypeslib.as_array(lc, shape=(n.value,)).copy() if n.value else np.zeros((0,), dtype=np.int32)
+        self.unit_offsets = np.ctypeslib.as_array(uo, shape=(nu.value + 1,)).copy() if uo else np.zeros((1,), dtype=np.uint64)
+
+    def __len__(self):
+        return int(self.locs.shape[0])
+
+    def model(self, i, k):
+        """Coordinate model k of enclosure i: (exponents [terms, nargs] uint8, coefficients [terms], error)."""
+        na = C.c_int32(0); nt = C.c_int32(0); err = C.c_double(0.0)
+        rc = self.lib.ab200_enclosures_model(self._handle, i, k, C.byref(na), C.byref(nt), C.byref(err), None, None)
+        if rc:
+            raise Ab200Error(rc, "no such enclosure model")
+        ex = np.zeros((nt.value, na.value), dtype=np.uint8); co = np.zeros((nt.value,), dtype=np.float64)
+        self.lib.ab200_enclosures_model(self._handle, i, k, C.byref(na), C.byref(nt), C.byref(err),
+                                        ex.ctypes.data_as(C.POINTER(C.c_uint8)), _dptr(co))
+        return ex, co, err.value
+
+    def select(self, idx):
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.uint64))
+        out = C.c_void_p()
+        rc = self.lib.ab200_enclosures_select(self._handle, idx.shape[0], idx.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(out))
+        if rc:
+            raise Ab200Error(rc, "enclosure index out of range")
+        return Enclosures(self.lib, out)
+
+    def release(self):
+        if self._handle is not None:
+            self.lib.ab200_enclosures_free(self._handle); self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 def system_check(system_text):
     """Parse a system text on the host (no GPU): returns (n_locations, n_events, n_ops) or raises Ab200Error."""
     lib = load_library()
@@ -266,6 +320,22 @@ class Evolver(object):
         self.last_status = st
         self._check(rc)
         return _take_boxlist(self.lib, r, n), _take_boxlist(self.lib, f, n)
+
+    def reach_evolve_enclosures(self, locs, boxes, time, max_events, initial=None, ignore_activations=False, backward=False, max_enclosure_words=0):
+        """EvolverInterface::reach_evolve with the final sets handed back as TaylorSets (and, with `initial`, started from
+        TaylorSets): returns (reach boxlist, final boxlist, Enclosures)."""
+        if initial is None:
+            locs = np.ascontiguousarray(np.asarray(locs, dtype=np.int32))
+            boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64))
+            n = locs.shape[0]; lp = _iptr(locs); bp = _dptr(boxes); ih = None
+        else:
+            n = len(initial); lp = None; bp = None; ih = initial._handle
+        r = C.c_void_p(); f = C.c_void_p(); e = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_reach_evolve_enclosures(self.handle, n, lp, bp, ih, float(time), int(max_events), int(bool(ignore_activations)),
+                                                    int(bool(backward)), int(max_enclosure_words), C.byref(r), C.byref(f), C.byref(e), C.byref(st))
+        self.last_status = st
+        self._check(rc)
+        return _take_boxlist(self.lib, r, n), _take_boxlist(self.lib, f, n), Enclosures(self.lib, e)
 
     def upper_reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False, backward=False):
         """UpperReachEvolveWorker::get_result(): (reach CellSet, evolve CellSet)."""
@@ -457,6 +527,19 @@ class HybridReachabilityAnalyser(object):
 
     def lower_evolve(self, initial_set, time, max_events=5):
         return self.lower_reach_evolve(initial_set, time, max_events)[1]
+
+    def epsilon_lower_chain_reach(self, initial_set, prune=True, substituted_system_text=None):
+        """HybridReachabilityAnalyser::epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627) without a constraint
+        set: returns (reach CellSet, epsilon [n_locations, dim], laps)."""
+        locs, boxes = self._initial(initial_set)
+        r = C.c_void_p(); st = Status(); laps = C.c_int32(0)
+        eps = np.zeros((self.evolver.n_locations, MAX_DIM), dtype=np.float64)
+        sub = substituted_system_text.encode() if substituted_system_text is not None else None
+        rc = self.lib.ab200_analyser_epsilon_lower_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), int(bool(prune)), sub,
+                                                               C.byref(r), _dptr(eps), C.byref(laps), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
+        return self._wrap(r), eps, laps.value
 
     def outer_chain_reach(self, initial_set, backward=False):
         locs, boxes = self._initial(initial_set)

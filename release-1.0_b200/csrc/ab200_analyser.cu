@@ -622,6 +622,28 @@ extern "C" int ab200_analyser_upper_reach_evolve_from(ab200_analyser* an, const 
     return upper_reach_evolve_cells(an, initial, T, max_events, mince, reach_out, evolve_out, status);
 }
 
+// _enclosures_from_discretised_initial_set_midpoints (src/reachability_analyser.cpp:1218-1243), box-only initial sets: the
+// centre of every discretised initial cell intersected with the initial box of its location, as a degenerate box
+static void midpoint_enclosures(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, const HybridCells& initial,
+                                std::vector<int32_t>& elocs, std::vector<double>& eboxes) {
+    const int dim = an->dim;
+    for (int l = 0; l < an->n_locs; ++l) {
+        const double* ib = 0;
+        for (uint64_t k = 0; k < n_init; ++k) if (loc[k] == l) { ib = boxes + k * AB200_BOX_STRIDE; break; }
+        if (!ib) continue;
+        std::vector<CellBox> cells; initial[l].enumerate(cells);
+        for (size_t k = 0; k < cells.size(); ++k) {
+            elocs.push_back(l);
+            size_t o = eboxes.size(); eboxes.resize(o + AB200_BOX_STRIDE, 0.0);
+            for (int i = 0; i < dim; ++i) {
+                double lo = std::max(cells[k].b[2 * i], ib[2 * i]), hi = std::min(cells[k].b[2 * i + 1], ib[2 * i + 1]);   // intersection(cell,domain)
+                double mid = (lo + hi) / 2;                                                                          // Box::centre
+                eboxes[o + 2 * i] = mid; eboxes[o + 2 * i + 1] = mid;
+            }
+        }
+    }
+}
+
 // lower_reach_evolve (src/reachability_analyser.cpp:230-275): the midpoints of the discretised initial cells
 // (_enclosures_from_discretised_initial_set_midpoints :1218-1243, box-only initial sets) are evolved for the whole time
 // with LOWER_SEMANTICS; every orbit is discretised on its own, checked against the outer domain widened by
@@ -639,21 +661,7 @@ extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_
     if (rc != AB200_OK) return rc;
     const int dim = an->dim;
     std::vector<int32_t> elocs; std::vector<double> eboxes;
-    for (int l = 0; l < an->n_locs; ++l) {
-        const double* ib = 0;
-        for (uint64_t k = 0; k < n_init; ++k) if (loc[k] == l) { ib = boxes + k * AB200_BOX_STRIDE; break; }
-        if (!ib) continue;
-        std::vector<CellBox> cells; initial[l].enumerate(cells);
-        for (size_t k = 0; k < cells.size(); ++k) {
-            elocs.push_back(l);
-            size_t o = eboxes.size(); eboxes.resize(o + AB200_BOX_STRIDE, 0.0);
-            for (int i = 0; i < dim; ++i) {
-                double lo = std::max(cells[k].b[2 * i], ib[2 * i]), hi = std::min(cells[k].b[2 * i + 1], ib[2 * i + 1]);   // intersection(cell,domain)
-                double mid = (lo + hi) / 2;                                                                          // Box::centre
-                eboxes[o + 2 * i] = mid; eboxes[o + 2 * i + 1] = mid;
-            }
-        }
-    }
+    midpoint_enclosures(an, n_init, loc, boxes, initial, elocs, eboxes);
     an->cells_evolved = (int64_t)elocs.size();
     { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
     ab200_settings saved, low;
@@ -700,6 +708,189 @@ extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_
     if (result != AB200_OK) return result;
     if (!ok) { ab200_ctx_set_error(an->ctx, "a reached cell lies outside the packed-key window"); return AB200_E_KEYSPACE; }
     *reach_out = to_cellset(reach); *evolve_out = to_cellset(evolve);
+    return AB200_OK;
+}
+
+// glibc's rand() for a process that never called srand(): the TYPE_3 additive feedback generator of random_r.c seeded with 1
+// (r[i] = r[i-31] + r[i-3] after a Lehmer-seeded table and 310 discarded draws; the result is the sum shifted right by one).
+// _filter_enclosures (src/reachability_analyser.cpp:704-727) draws from it.
+struct GlibcRand {
+    std::vector<uint32_t> r;
+    GlibcRand() {
+        r.resize(34);
+        r[0] = 1;
+        for (int i = 1; i < 31; ++i) { long long v = (16807LL * (long long)(int32_t)r[i - 1]) % 2147483647LL; if (v < 0) v += 2147483647LL; r[i] = (uint32_t)v; }
+        for (int i = 31; i < 34; ++i) r[i] = r[i - 31];
+        for (int i = 34; i < 344; ++i) r.push_back(r[i - 31] + r[i - 3]);
+    }
+    int next() { const size_t k = r.size(); r.push_back(r[k - 31] + r[k - 3]); return (int)(r.back() >> 1); }
+};
+
+// epsilon_lower_chain_reach / _epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627) with LowerReachEpsilonWorker
+// (include/workers.h:171-329): see include/ariadne_b200.h. The evolution of a lap's enclosures runs on the device
+// (ab200_reach_evolve_enclosures: one warp per enclosure, final set models handed to the next lap); discretising the returned
+// boxes, the widened-domain check, the set algebra and the pruning draw are host work on a few hundred enclosures per lap.
+int ab200_ctx_swap_system(ab200_ctx* ctx, HostSystem* other);     // ab200_capi.cu: exchange the context's system with *other and upload it
+struct SubstitutedSystem {      // _system->substitute_all(midpoints) ... substitute_all(original_parameters)
+    ab200_ctx* ctx; HostSystem other; bool active;
+    SubstitutedSystem() : ctx(0), active(false) { }
+    ~SubstitutedSystem() { if (active) ab200_ctx_swap_system(ctx, &other); }
+};
+extern "C" int ab200_analyser_epsilon_lower_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, int32_t prune,
+                                                        const char* substituted_system_text,
+                                                        ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status) {
+    if (!an || !reach_out || (n_init && (!loc || !boxes))) return AB200_E_ARGUMENT;
+    *reach_out = 0;
+    an->cells_evolved = 0;
+    SubstitutedSystem sub;
+    if (substituted_system_text) {
+        const HostSystem* hs = ab200_ctx_system(an->ctx);
+        std::string e = parse_system(substituted_system_text, sub.other);
+        if (!e.empty()) { ab200_ctx_set_error(an->ctx, ("substituted system: " + e).c_str()); return AB200_E_ARGUMENT; }
+        if (sub.other.loc_names != hs->loc_names || sub.other.desc.loc[0].n != hs->desc.loc[0].n) { ab200_ctx_set_error(an->ctx, "the substituted system has other locations or variables"); return AB200_E_ARGUMENT; }
+        sub.ctx = an->ctx;
+        int src = ab200_ctx_swap_system(an->ctx, &sub.other);
+        if (src != AB200_OK) return src;
+        sub.active = true;
+    }
+    HybridCells initial;
+    int rc = discretise_initial(an, n_init, loc, boxes, initial);
+    if (rc != AB200_OK) return rc;
+    const int dim = an->dim, L = an->n_locs;
+    const double divider = (double)(1 << an->accuracy);
+    std::vector<int32_t> elocs; std::vector<double> eboxes;
+    midpoint_enclosures(an, n_init, loc, boxes, initial, elocs, eboxes);
+    // _restriction->filter(initial_enclosures) (src/reachability_restriction.cpp:186-228): an enclosure whose box the
+    // (undiscretised) outer domain covers is kept; otherwise it is kept if its outer approximation meets the domain cells
+    {
+        std::vector<int32_t> kl; std::vector<double> kb;
+        for (size_t k = 0; k < elocs.size(); ++k) {
+            const int l = elocs[k]; const double* b = &eboxes[k * AB200_BOX_STRIDE];
+            bool keep = false;
+            if (!an->discretised[l]) {
+                keep = true;
+                for (int i = 0; keep && i < dim; ++i) {
+                    const double cell = an->grid[l].lengths[i] / divider;
+                    if (!(b[2 * i] > an->domain[l][2 * i] - cell && b[2 * i + 1] < an->domain[l][2 * i + 1] + cell)) keep = false;    // Box::covers is strict
+                }
+            }
+            if (!keep) {
+                ensure_restriction(an, l);
+                CellSet t(an->grid[l], an->K, l);
+                t.adjoin_outer_approximation(b); t.restrict(an->restriction[l]);
+                keep = !t.empty();
+            }
+            if (keep) { kl.push_back(l); kb.insert(kb.end(), b, b + AB200_BOX_STRIDE); }
+        }
+        elocs.swap(kl); eboxes.swap(kb);
+    }
+    { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
+    ab200_settings saved, low;
+    ab200_ctx_get_settings(an->ctx, &saved);
+    low = saved; low.semantics = 1;
+    HybridCells reach = empty_cells(an);
+    std::vector<std::vector<double> > epsilon(L, std::vector<double>(dim, 0.0));
+    ab200_enclosures* current = 0;            // null: the first lap starts from the midpoint boxes
+    size_t n_current = elocs.size();
+    ab200_status total; memset(&total, 0, sizeof(total)); total.cell = -1;
+    GlibcRand rnd;
+    int laps = 0, result = AB200_OK; bool ok = true;
+    while (n_current > 0 && result == AB200_OK) {
+        ++laps;
+        if (getenv("AB200_EPS_DEBUG")) fprintf(stderr, "lap %d initial enclosures %zu\n", laps, n_current);
+        an->cells_evolved += (int64_t)n_current;
+        ab200_boxlist *rb = 0, *fb = 0; ab200_enclosures* fe = 0; ab200_status st; memset(&st, 0, sizeof(st));
+        rc = ab200_set_settings(an->ctx, &low);
+        if (rc == AB200_OK) rc = ab200_reach_evolve_enclosures(an->ctx, elocs.size(), elocs.data(), eboxes.data(), current, an->lock_time, 1 /* lock_to_grid_steps */, 0, 0, 0, &rb, &fb, &fe, &st);
+        ab200_set_settings(an->ctx, &saved);
+        total.steps += st.steps; total.launches += st.launches; total.evolve_ms += st.evolve_ms; total.libm_sensitive += st.libm_sensitive; total.alg_flops += st.alg_flops;
+        if (st.arena_peak > total.arena_peak) total.arena_peak = st.arena_peak;
+        total.build = st.build;
+        if (rc != AB200_OK) { total.code = st.code; total.cell = st.cell; result = rc; break; }
+        // LowerReachEpsilonWorker::_compute, in unit order: discretise every orbit, collect widths, cell counts and final sets
+        HybridCells local_reach = empty_cells(an), evolve_global = empty_cells(an);
+        std::vector<std::vector<double> > local_eps(L, std::vector<double>(dim, 0.0));
+        std::vector<uint64_t> superposed(L, 0);
+        const uint64_t *roff, *foff; const double *rbx, *fbx; const int32_t *rl, *fl;
+        ab200_boxlist_view(rb, &roff, &rbx, &rl); ab200_boxlist_view(fb, &foff, &fbx, &fl);
+        for (size_t e = 0; e < n_current; ++e) {
+            HybridCells cur_reach = empty_cells(an), cur_evolve = empty_cells(an);
+            for (uint64_t k = roff[e]; k < roff[e + 1]; ++k) {
+                const double* b = rbx + k * AB200_BOX_STRIDE;
+                ok = cur_reach[rl[k]].adjoin_outer_approximation(b) && ok;
+                for (int i = 0; i < dim; ++i) local_eps[rl[k]][i] = std::max(local_eps[rl[k]][i], ivl_width(ivl(b[2 * i], b[2 * i + 1])));
+            }
+            for (uint64_t k = foff[e]; k < foff[e + 1]; ++k) ok = cur_evolve[fl[k]].adjoin_outer_approximation(fbx + k * AB200_BOX_STRIDE) && ok;
+            for (int l = 0; l < L; ++l) {
+                local_reach[l].adjoin(cur_reach[l]); evolve_global[l].adjoin(cur_evolve[l]);
+                if (!cur_evolve[l].empty()) { std::vector<CellBox> cells; cur_evolve[l].enumerate(cells); superposed[l] += cells.size(); }
+            }
+        }
+        const uint64_t n_rb = roff[n_current], n_fb = foff[n_current];
+        ab200_boxlist_free(rb); ab200_boxlist_free(fb);
+        for (int l = 0; l < L; ++l) for (int i = 0; i < dim; ++i) {
+            local_eps[l][i] += an->grid[l].lengths[i] / divider;                           // get_result: plus the minimum cell lengths
+            epsilon[l][i] = std::max(epsilon[l][i], local_eps[l][i]);
+        }
+        // widen(outer_domain_box, local_epsilon).superset(local_reach.bounding_box())
+        for (int l = 0; l < L && result == AB200_OK; ++l) {
+            double bb[2 * AB_GRID_MAXN];
+            if (!local_reach[l].bounding_box(bb)) continue;
+            for (int i = 0; i < dim; ++i) {
+                const double cell = an->grid[l].lengths[i] / divider;
+                const double lo = (an->domain[l][2 * i] - cell) - local_eps[l][i], hi = (an->domain[l][2 * i + 1] + cell) + local_eps[l][i];
+                if (!(bb[2 * i] >= lo && bb[2 * i + 1] <= hi)) {
+                    ab200_ctx_set_error(an->ctx, "The lower reach is not inside the over-approximated domain. Check the domain used for variables.");
+                    result = AB200_E_DOMAIN;
+                }
+            }
+        }
+        if (result != AB200_OK) { ab200_enclosures_free(fe); break; }
+        apply_restriction(an, local_reach);
+        if (getenv("AB200_EPS_DEBUG")) { size_t c = 0; for (int l = 0; l < L; ++l) { std::vector<CellBox> cells; local_reach[l].enumerate(cells); c += cells.size(); } fprintf(stderr, "  reach boxes %llu final boxes %llu reach size before removal %zu\n", (unsigned long long)n_rb, (unsigned long long)n_fb, c); }
+        // (no constraint set: _epsilon_lower_chain_reach_constraint_check finds no infeasible cell)
+        bool any_new = false;
+        for (int l = 0; l < L; ++l) { local_reach[l].remove(reach[l]); if (!local_reach[l].empty()) any_new = true; }
+        if (!any_new) { ab200_enclosures_free(fe); break; }
+        for (int l = 0; l < L; ++l) reach[l].adjoin(local_reach[l]);
+        // _filter_enclosures: the final enclosures become the next initial ones, all of them or a random share
+        uint64_t n_final = 0, n_units = 0; const int32_t* flocs = 0; const uint64_t* uoff = 0;
+        ab200_enclosures_view(fe, &n_final, &flocs, &uoff, &n_units);
+        // the worker appends a unit's final sets location by location (ListSet's std::map, ordered by location name)
+        std::vector<uint64_t> order;
+        {
+            const HostSystem* hs = ab200_ctx_system(an->ctx);
+            for (uint64_t u = 0; u < n_units; ++u) {
+                const size_t o = order.size();
+                for (uint64_t k = uoff[u]; k < uoff[u + 1]; ++k) order.push_back(k);
+                std::stable_sort(order.begin() + o, order.end(), [&](uint64_t a, uint64_t b) { return hs->loc_names[flocs[a]] < hs->loc_names[flocs[b]]; });
+            }
+        }
+        std::vector<uint64_t> adjoined(L, 0);
+        for (int l = 0; l < L; ++l) if (!evolve_global[l].empty()) { std::vector<CellBox> cells; evolve_global[l].enumerate(cells); adjoined[l] = cells.size(); }
+        std::vector<uint64_t> keep;
+        for (size_t kk = 0; kk < order.size(); ++kk) {
+            const uint64_t k = order[kk];
+            if (prune) {
+                const int l = flocs[k];
+                const double coverage_ratio = (double)adjoined[l] / (double)superposed[l];
+                if (keep.size() <= 2 || (double)rnd.next() < 2 * coverage_ratio * 2147483647.0) keep.push_back(k);
+            } else keep.push_back(k);
+        }
+        ab200_enclosures* next = 0;
+        rc = ab200_enclosures_select(fe, keep.size(), keep.data(), &next);
+        ab200_enclosures_free(fe);
+        if (current) ab200_enclosures_free(current);
+        current = next; n_current = keep.size();
+        if (rc != AB200_OK) { result = rc; break; }
+    }
+    if (current) ab200_enclosures_free(current);
+    if (status) *status = total;
+    if (laps_out) *laps_out = laps;
+    if (result != AB200_OK) return result;
+    if (!ok) { ab200_ctx_set_error(an->ctx, "a reached cell lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    if (epsilon_out) for (int l = 0; l < L; ++l) for (int i = 0; i < AB200_MAX_DIM; ++i) epsilon_out[(size_t)l * AB200_MAX_DIM + i] = i < dim ? epsilon[l][i] : 0.0;
+    *reach_out = to_cellset(reach);
     return AB200_OK;
 }
 

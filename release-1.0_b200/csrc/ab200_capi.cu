@@ -27,6 +27,7 @@ int dev_evolve_capacity_v(char* errbuf, int errlen); \
 int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* cell_loc, const double* cell_box, const void* evolve_params, \
                         uint64_t* arena, int arena_words, const uint32_t* binom, int* next_cell, double* reach, int32_t* reach_loc, int32_t* n_reach, \
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, double* flops, \
+                        const uint64_t* enc_in, const uint64_t* enc_in_off, uint64_t* enc_out, int enc_cap, int32_t* enc_used, \
                         char* errbuf, int errlen); } }
 AB_DECL_VARIANT(kw2)
 // The one-cell-per-lane build (ab200_kernels_lane.cu): its own launcher signature (no work counter: one lane per cell,
@@ -49,7 +50,7 @@ struct EvolveBuild {
     int (*upload)(const void*, char*, int);
     int (*capacity)(char*, int);
     int (*launch)(cudaStream_t, int, int, const int32_t*, const double*, const void*, uint64_t*, int, const uint32_t*, int*, double*, int32_t*, int32_t*,
-                  double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, double*, char*, int);
+                  double*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, double*, const uint64_t*, const uint64_t*, uint64_t*, int, int32_t*, char*, int);
 };
 #define AB_BUILD(ns) { #ns, ab200::ns::dev_upload_system_v, ab200::ns::dev_evolve_capacity_v, ab200::ns::dev_launch_evolve_v }
 static const EvolveBuild kBuilds[] = { AB_BUILD(kw1), AB_BUILD(kw2) };
@@ -79,6 +80,8 @@ template<class T> struct DevBuf {
 
 struct ab200_cellset { std::vector<uint64_t> keys; };
 struct ab200_boxlist { std::vector<uint64_t> offsets; std::vector<double> boxes; std::vector<int32_t> locs; };
+// Enclosures (set models) in the device's own record format (ab200_evolve.cuh: out_enclosure); record i starts at word offsets[i].
+struct ab200_enclosures { std::vector<uint64_t> offsets; std::vector<uint64_t> words; std::vector<int32_t> locs; std::vector<uint64_t> unit_offsets; int key_words; };
 
 struct ab200_ctx {
     int device;
@@ -99,6 +102,7 @@ struct ab200_ctx {
     DevBuf<uint32_t> d_binom;
     DevBuf<int> d_next;
     DevBuf<double> d_jbox; DevBuf<int32_t> d_jout;      // jump-set check batches (ab200_ctx_jump_check)
+    DevBuf<uint64_t> d_enc_in, d_enc_off, d_enc_out; DevBuf<int32_t> d_enc_used;   // enclosure hand-over (ab200_reach_evolve_enclosures)
     unsigned long long sys_generation;     // bumped by every change of the system description or tuning
     // multi-GPU exchange (ab200_comm_init): one process per GPU, NCCL communicator over NVLink
     ncclComm_t comm; int n_ranks, rank;
@@ -419,6 +423,9 @@ static int map_status(int st) { return st; }   // device ST_* codes coincide wit
 struct LapOut {
     std::vector<uint64_t>* reach_keys; std::vector<uint64_t>* fin_keys;   // sorted unique (may be null)
     ab200_boxlist* reach_boxes; ab200_boxlist* fin_boxes;                 // (may be null)
+    const ab200_enclosures* enc_in;      // (may be null) the evolution of unit i starts from enclosure i instead of box i
+    ab200_enclosures* enc_out;           // (may be null) receives the final sets as enclosures, in unit order
+    int enc_cap;                         // words of enclosure output per unit
 };
 
 static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T, int32_t max_events,
@@ -445,6 +452,17 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         DEV_CK(dev_launch_fill(ctx->stream, ctx->d_table.p, table_n * 2, ~0ull, eb_, sizeof(eb_))); stl.launches += 1;
         CTX_CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     }
+    const bool wide_sys = ctx->sys.desc.loc[0].n > 2;
+    if (out.enc_in) {
+        // enclosure hand-over: all records once, the per-unit word offsets beside them
+        if (out.enc_in->locs.size() != n_cells) { ctx->err = "one enclosure per unit expected"; return AB200_E_ARGUMENT; }
+        CTX_CK(ctx->d_enc_in.ensure(out.enc_in->words.size() + 1)); CTX_CK(ctx->d_enc_off.ensure(n_cells + 1));
+        CTX_CK(cudaMemcpyAsync(ctx->d_enc_in.p, out.enc_in->words.data(), out.enc_in->words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CTX_CK(cudaMemcpyAsync(ctx->d_enc_off.p, out.enc_in->offsets.data(), n_cells * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (out.enc_out) { out.enc_out->offsets.clear(); out.enc_out->words.clear(); out.enc_out->locs.clear(); out.enc_out->unit_offsets.assign(1, 0); out.enc_out->key_words = wide_sys ? 2 : 1; }
+    (void)wide_sys;
+    const bool hand_over = out.enc_in || out.enc_out;
     float evolve_ms = 0, raster_ms = 0;
     std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
     for (uint64_t b0 = 0; b0 < n_cells; b0 += (uint64_t)S.batch_cells) {
@@ -460,14 +478,19 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
         const bool wide = ctx->sys.desc.loc[0].n > 2;
         const EvolveBuild* build = find_build(wide ? "kw2" : "kw1");
         // AB200_TUNE=lane / warp overrides the size rule for one-word systems (test hook).
-        bool use_lane = !wide && nb >= AB_LANE_THRESHOLD && P.max_events < 64;
+        bool use_lane = !wide && nb >= AB_LANE_THRESHOLD && P.max_events < 64 && !hand_over;      // (enclosure records are a warp-build feature)
         if (const char* tune = getenv("AB200_TUNE")) {
-            if (!strcmp(tune, "lane") && !wide) use_lane = true;
+            if (!strcmp(tune, "lane") && !wide) use_lane = !hand_over;
             else if (!strcmp(tune, "warp")) use_lane = false;
             else {
                 if (!find_build(tune) || (wide && strcmp(tune, "kw2"))) { ctx->err = std::string("AB200_TUNE: no such build for this system: ") + tune; return AB200_E_ARGUMENT; }
                 build = find_build(tune); use_lane = false;
             }
+        }
+        {   // enclosure records carry the MultiIndex keys of the build that wrote them
+            const int kw = strcmp(build->name, "kw2") ? 1 : 2;
+            if (out.enc_in && out.enc_in->key_words != kw) { ctx->err = "enclosures were written by a build with another key width"; return AB200_E_ARGUMENT; }
+            if (out.enc_out) out.enc_out->key_words = kw;
         }
         CTX_CK(cudaMemcpyAsync(ctx->d_loc.p, loc + b0, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CTX_CK(cudaMemcpyAsync(ctx->d_box.p, boxes + b0 * stride, (size_t)nb * stride * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -492,9 +515,12 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
                 if (slots > nb + 3) slots = nb + 3;                     // (a CTA may hold up to four cell slots)
                 CTX_CK(ctx->d_arena.ensure((size_t)(slots + 4) * S.arena_words));
                 CTX_CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(int), ctx->stream));
+                if (out.enc_out) { CTX_CK(ctx->d_enc_out.ensure((size_t)nb * (size_t)out.enc_cap)); CTX_CK(ctx->d_enc_used.ensure(nb)); }
                 DEV_CK(build->launch(ctx->stream, nb, slots, ctx->d_loc.p, ctx->d_box.p, &P, ctx->d_arena.p, S.arena_words, ctx->d_binom.p, ctx->d_next.p,
                                      ctx->d_reach.p, ctx->d_rloc.p, ctx->d_nreach.p, ctx->d_fin.p, ctx->d_floc.p, ctx->d_nfin.p,
-                                     ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, ctx->d_flops.p, eb_, sizeof(eb_)));
+                                     ctx->d_status.p, ctx->d_steps.p, ctx->d_peak.p, ctx->d_flops.p,
+                                     out.enc_in ? ctx->d_enc_in.p : 0, out.enc_in ? ctx->d_enc_off.p + b0 : 0,
+                                     out.enc_out ? ctx->d_enc_out.p : 0, out.enc_cap, out.enc_out ? ctx->d_enc_used.p : 0, eb_, sizeof(eb_)));
             }
             stl.launches += 1;
             CTX_CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -531,6 +557,25 @@ static int run_batches(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, con
             // first failure aborts the lap and discards its results (include/workers.h:129-139,159-166)
             char msg[160]; snprintf(msg, sizeof(msg), "cell %lld failed with code %d", (long long)stl.cell, stl.code);
             ctx->err = msg; stl.evolve_ms = evolve_ms; if (status) *status = stl; return stl.code;
+        }
+        if (out.enc_out) {
+            // the final sets of every unit as enclosure records, in unit order and, within a unit, in the order they were emitted
+            std::vector<int32_t> used(nb);
+            CTX_CK(cudaMemcpy(used.data(), ctx->d_enc_used.p, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            std::vector<uint64_t> rec;
+            for (int i = 0; i < nb; ++i) {
+                rec.resize((size_t)used[i]);
+                if (used[i] > 0) CTX_CK(cudaMemcpy(rec.data(), ctx->d_enc_out.p + (size_t)i * (size_t)out.enc_cap, (size_t)used[i] * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+                for (size_t o = 0; o < rec.size(); ) {
+                    const size_t len = (size_t)(rec[o + 1] & 0xFFFFFFFFu);
+                    if (len < 2 || o + len > rec.size()) { ctx->err = "malformed enclosure record"; return AB200_E_CUDA; }
+                    out.enc_out->offsets.push_back(out.enc_out->words.size());
+                    out.enc_out->locs.push_back((int32_t)(rec[o] >> 32));
+                    out.enc_out->words.insert(out.enc_out->words.end(), rec.begin() + o, rec.begin() + o + len);
+                    o += len;
+                }
+                out.enc_out->unit_offsets.push_back(out.enc_out->locs.size());
+            }
         }
         if (out.reach_boxes || out.fin_boxes) {
             for (int which = 0; which < 2; ++which) {
@@ -655,7 +700,7 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
     if (!ctx || !reach_out || !evolve_out || (n_cells && (!loc || !boxes))) return AB200_E_ARGUMENT;
     *reach_out = 0; *evolve_out = 0;
     ab200_cellset* r = new ab200_cellset(); ab200_cellset* e = new ab200_cellset();
-    LapOut out; out.reach_keys = &r->keys; out.fin_keys = &e->keys; out.reach_boxes = 0; out.fin_boxes = 0;
+    LapOut out; out.reach_keys = &r->keys; out.fin_keys = &e->keys; out.reach_boxes = 0; out.fin_boxes = 0; out.enc_in = 0; out.enc_out = 0; out.enc_cap = 0;
     int rc = run_lap(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
     if (rc != AB200_OK) { delete r; delete e; return rc; }
     *reach_out = r; *evolve_out = e;
@@ -675,7 +720,7 @@ extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const 
     if (!ctx || !reach_out || !final_out || (n_cells && (!loc || !boxes))) return AB200_E_ARGUMENT;
     *reach_out = 0; *final_out = 0;
     ab200_boxlist* r = new ab200_boxlist(); ab200_boxlist* f = new ab200_boxlist();
-    LapOut out; out.reach_keys = 0; out.fin_keys = 0; out.reach_boxes = r; out.fin_boxes = f;
+    LapOut out; out.reach_keys = 0; out.fin_keys = 0; out.reach_boxes = r; out.fin_boxes = f; out.enc_in = 0; out.enc_out = 0; out.enc_cap = 0;
     int rc = run_lap(ctx, n_cells, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
     if (rc != AB200_OK) { delete r; delete f; return rc; }
     *reach_out = r; *final_out = f;
@@ -689,6 +734,73 @@ extern "C" int ab200_boxlist_view(const ab200_boxlist* bl, const uint64_t** offs
     return AB200_OK;
 }
 extern "C" void ab200_boxlist_free(ab200_boxlist* bl) { delete bl; }
+
+// reach_evolve with enclosure hand-over: EvolverInterface::reach_evolve(enclosure,time,semantics) (include/evolver_interface.h:95-124)
+// as LowerReachEpsilonWorker::_compute calls it (include/workers.h:264-303) -- every unit starts from a TaylorSet (a final set of
+// an earlier call) or from a box, and its final sets come back as TaylorSets as well as boxes.
+extern "C" int ab200_reach_evolve_enclosures(ab200_ctx* ctx, uint64_t n_units, const int32_t* loc, const double* boxes, const ab200_enclosures* initial,
+                                             double t_continuous, int32_t max_events, int ignore_activations, int direction, int32_t max_enclosure_words,
+                                             ab200_boxlist** reach_out, ab200_boxlist** final_out, ab200_enclosures** final_enclosures, ab200_status* status) {
+    if (!ctx || !reach_out || !final_out || !final_enclosures) return AB200_E_ARGUMENT;
+    if (!initial && n_units && (!loc || !boxes)) return AB200_E_ARGUMENT;
+    *reach_out = 0; *final_out = 0; *final_enclosures = 0;
+    std::vector<int32_t> locs; std::vector<double> zero;
+    if (initial) {
+        // the units are the enclosures; their locations come from the records and the boxes are not read
+        n_units = initial->locs.size(); locs = initial->locs; zero.assign((size_t)n_units * AB200_BOX_STRIDE, 0.0);
+        loc = locs.data(); boxes = zero.data();
+    }
+    ab200_boxlist* r = new ab200_boxlist(); ab200_boxlist* f = new ab200_boxlist(); ab200_enclosures* e = new ab200_enclosures();
+    LapOut out; out.reach_keys = 0; out.fin_keys = 0; out.reach_boxes = r; out.fin_boxes = f;
+    out.enc_in = initial; out.enc_out = e; out.enc_cap = max_enclosure_words > 0 ? max_enclosure_words : 16384;
+    int rc = run_lap(ctx, n_units, loc, boxes, t_continuous, max_events, ignore_activations, direction, out, status);
+    if (rc != AB200_OK) { delete r; delete f; delete e; return rc; }
+    *reach_out = r; *final_out = f; *final_enclosures = e;
+    return AB200_OK;
+}
+extern "C" int ab200_enclosures_view(const ab200_enclosures* e, uint64_t* count, const int32_t** locs, const uint64_t** unit_offsets, uint64_t* n_units) {
+    if (!e) return AB200_E_ARGUMENT;
+    if (count) *count = e->locs.size();
+    if (locs) *locs = e->locs.empty() ? 0 : e->locs.data();
+    if (unit_offsets) *unit_offsets = e->unit_offsets.empty() ? 0 : e->unit_offsets.data();
+    if (n_units) *n_units = e->unit_offsets.empty() ? 0 : e->unit_offsets.size() - 1;
+    return AB200_OK;
+}
+// Model k (a coordinate of the set) of enclosure i, decoded: exps is [n_terms][nargs] (MultiIndex exponents), coefs [n_terms].
+// With null exps / coefs only the sizes and the error are returned.
+extern "C" int ab200_enclosures_model(const ab200_enclosures* e, uint64_t i, int32_t k, int32_t* nargs, int32_t* n_terms, double* error, uint8_t* exps, double* coefs) {
+    if (!e || i >= e->locs.size() || k < 0) return AB200_E_ARGUMENT;
+    const uint64_t* q = e->words.data() + e->offsets[i];
+    const int n = (int)(q[1] >> 32), tw = e->key_words + 1;
+    if (k >= n) return AB200_E_ARGUMENT;
+    size_t o = 2;
+    for (int m = 0; m < k; ++m) o += 2 + (size_t)(q[o] >> 32) * tw;
+    const int nt = (int)(q[o] >> 32), as = (int)(q[o] & 0xFFFFFFFFu);
+    if (nargs) *nargs = as;
+    if (n_terms) *n_terms = nt;
+    if (error) memcpy(error, &q[o + 1], sizeof(double));
+    for (int t = 0; t < nt; ++t) {
+        const uint64_t* w = q + o + 2 + (size_t)t * tw;
+        if (exps) for (int j = 0; j < as; ++j) exps[(size_t)t * as + j] = (uint8_t)(j < 7 ? (w[0] >> (8 * (6 - j))) & 0xFF : (e->key_words > 1 ? (w[1] >> (8 * (14 - j))) & 0xFF : 0));
+        if (coefs) memcpy(&coefs[t], &w[e->key_words], sizeof(double));
+    }
+    return AB200_OK;
+}
+// The enclosures idx[0..n) of src as a new list (the hand-over keeps a subset: ReachabilityRestriction::filter, _filter_enclosures).
+extern "C" int ab200_enclosures_select(const ab200_enclosures* src, uint64_t n, const uint64_t* idx, ab200_enclosures** out) {
+    if (!src || !out || (n && !idx)) return AB200_E_ARGUMENT;
+    ab200_enclosures* e = new ab200_enclosures(); e->key_words = src->key_words; e->unit_offsets.assign(1, 0);
+    for (uint64_t k = 0; k < n; ++k) {
+        if (idx[k] >= src->locs.size()) { delete e; return AB200_E_ARGUMENT; }
+        const uint64_t* q = src->words.data() + src->offsets[idx[k]];
+        e->offsets.push_back(e->words.size()); e->locs.push_back(src->locs[idx[k]]);
+        e->words.insert(e->words.end(), q, q + (size_t)(q[1] & 0xFFFFFFFFu));
+        e->unit_offsets.push_back(e->locs.size());
+    }
+    *out = e;
+    return AB200_OK;
+}
+extern "C" void ab200_enclosures_free(ab200_enclosures* e) { delete e; }
 
 extern "C" int ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,
                                  double* h_out, double* bounds_out, int32_t* status_out) {
@@ -918,6 +1030,7 @@ int ab200_ctx_jump_check(ab200_ctx* ctx, int loc, int event, size_t n, const dou
     return AB200_OK;
 }
 const ab200::KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return ctx && ctx->have_layout ? &ctx->K : 0; }
+int ab200_ctx_swap_system(ab200_ctx* ctx, HostSystem* other) { std::swap(ctx->sys, *other); return upload_system(ctx, true); }
 void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg) { if (ctx) ctx->err = msg; }
 std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs) { return cs->keys; }
 ab200_cellset* ab200_cellset_new() { return new ab200_cellset(); }

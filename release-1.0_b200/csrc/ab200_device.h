@@ -15,6 +15,7 @@ int dev_launch_evolve_v(cudaStream_t st, int n_cells, int slots, const int32_t* 
                         uint64_t* arena, int arena_words, const uint32_t* binom, int* next_cell,
                         double* reach, int32_t* reach_loc, int32_t* n_reach,
                         double* fin, int32_t* fin_loc, int32_t* n_fin, int32_t* status, int32_t* steps, int32_t* peak, double* flops,
+                        const uint64_t* enc_in, const uint64_t* enc_in_off, uint64_t* enc_out, int enc_cap, int32_t* enc_used,
                         char* errbuf, int errlen);
 int dev_set_stack(size_t bytes, char* errbuf, int errlen);
 int dev_launch_flow_bounds(cudaStream_t st, int n_cells, const int32_t* cell_loc, const double* cell_box, double hmax,

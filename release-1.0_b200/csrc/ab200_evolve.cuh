@@ -33,6 +33,9 @@ struct CellOutput {
     double* final_; int32_t* final_loc;  int32_t n_final;
     int32_t stride;            // doubles per box record (2*AB_MAXN)
     int32_t steps;             // number of _evolution_step calls (work counter)
+    // final sets as enclosures (set models, not only their boxes) for callers that hand them to the next lap
+    // (LowerReachEpsilonWorker, include/workers.h:299-302); null = not wanted
+    uint64_t* enc; int32_t enc_cap; int32_t enc_used; int32_t n_enc;
 };
 
 // The reference hands enclosures to the discretiser through HybridSetConstIterator::dereference
@@ -54,6 +57,14 @@ AB_HD void out_box(Ctx& c, double* dst, int32_t* dloc, int32_t& count, int cap, 
     ++count;
 }
 
+// Enclosure record (ab200_reach_evolve_enclosures): the TaylorSet of a final set as the reference keeps it in
+// final_sets.adjoin(loc,_toolbox->enclosure(set_model)) (src/hybrid_evolver-image.cpp:304; enclosure() is the identity,
+// src/taylor_calculus.cpp:758-763). Words: [loc<<32 | p] [n<<32 | words of the whole record] then per model
+// [terms<<32 | argument size] [error bits] and the terms as they lie in the arena (AB_TW words each). The record is opaque
+// to the host and specific to the key width of the build that wrote it.
+struct WorkingSet;
+AB_HD int enc_words(const TM* set, int n) { int w = 2; for (int i = 0; i < n; ++i) w += 2 + set[i].n * AB_TW; return w; }
+
 // A working set (EvolutionData, include/hybrid_evolver-image.h): location, event count, set model (n models in p
 // variables) and time model, stored packed in the arena starting at `base`.
 struct WorkingSet {
@@ -63,6 +74,28 @@ struct WorkingSet {
     TM set[AB_MAXN];
     TM time;
 };
+
+AB_HD void out_enclosure(Ctx& c, CellOutput& O, const WorkingSet& ws, int n) {
+    if (!O.enc) return;
+    const int need = enc_words(ws.set, n);
+    if (O.enc_used + need > O.enc_cap) { fail(c, ST_OUTPUT); return; }
+    uint64_t* q = O.enc + O.enc_used;
+    const int W = AB_W, lane = wlane();
+    wsync();
+    if (lane == 0) { q[0] = ((uint64_t)(uint32_t)ws.loc << 32) | (uint32_t)ws.p; q[1] = ((uint64_t)(uint32_t)n << 32) | (uint32_t)need; }
+    int o = 2;
+    #pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const TM& m = ws.set[i];
+        if (lane == 0) { q[o] = ((uint64_t)(uint32_t)m.n << 32) | (uint32_t)m.as; q[o + 1] = d2u(m.e); }
+        const int nw = m.n * AB_TW;
+        const uint64_t* src = c.A.base + m.off;
+        for (int k = lane; k < nw; k += W) q[o + 2 + k] = src[k];
+        o += 2 + nw;
+    }
+    wsync();
+    O.enc_used += need; O.n_enc++;
+}
 
 // _is_enclosure_too_large  src/hybrid_evolver-image.cpp:1253-1284
 AB_HD bool enclosure_too_large(Ctx& c, const LocDesc& L, const Ivl* range, const double* init_w, double ratio) {
@@ -127,7 +160,9 @@ struct CellState {
     double init_w[AB_MAXN];
 };
 
-AB_HDN void cell_begin(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellState& st) {
+// enc: null, or the enclosure record the evolution starts from instead of the box (_evolution_add_initialSet with a TaylorSet:
+// set_model(enclosure) is a copy with the spacial accuracy, src/taylor_calculus.cpp:746-753; time_model(0.0) over its p parameters)
+AB_HDN void cell_begin(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellState& st, const uint64_t* enc = 0) {
     Acc spacial; spacial.sweep = P.spacial_sweep; spacial.maxdeg = P.spacial_order;
     const int n0 = S.loc[loc0].n;
     ctx_stage_tables(c);
@@ -142,9 +177,30 @@ AB_HDN void cell_begin(Ctx& c, const SystemDesc& S, int loc0, const double* box,
     w0.loc = loc0; w0.n_events = 0; w0.p = n0;
     #pragma unroll 1
     for (int i = 0; i < AB_MAXN; ++i) { w0.set[i].off = 0; w0.set[i].n = 0; w0.set[i].as = 0; w0.set[i].e = 0.0; w0.set[i].acc = spacial; }
+    if (enc) {
+        const int pe = (int)(enc[0] & 0xFFFFFFFFu), ne = (int)(enc[1] >> 32);
+        if ((int)(enc[0] >> 32) != loc0 || ne != n0 || pe < 0 || pe > AB_MAXARGS) { fail(c, ST_UNSUPPORTED); st.nq = 0; return; }
+        w0.p = pe;
+        const int W = AB_W, lane = wlane();
+        int o = 2;
+        #pragma unroll 1
+        for (int i = 0; i < n0; ++i) {
+            TM m = tm_begin(c, pe, spacial);
+            m.n = (int)(enc[o] >> 32); m.as = (int)(enc[o] & 0xFFFFFFFFu); m.e = u2d(enc[o + 1]);
+            const int nw = m.n * AB_TW;
+            if (m.as != pe || !arena_room(c, m.off, m.n)) { if (c.status == ST_OK) fail(c, ST_UNSUPPORTED); st.nq = 0; return; }
+            uint64_t* dst = c.A.base + m.off;
+            for (int k = lane; k < nw; k += W) dst[k] = enc[o + 2 + k];
+            c.A.top = m.off + nw; arena_mark_peak(c);
+            wsync();
+            w0.set[i] = m;
+            o += 2 + nw;
+        }
+    } else {
     #pragma unroll 1
     for (int i = 0; i < n0; ++i) { w0.set[i] = tm_scaling(c, n0, i, ivl(box[2 * i], box[2 * i + 1])); w0.set[i].acc = spacial; }
-    w0.time = tm_begin(c, n0, spacial); tm_append(c, w0.time, key_zero(), 0.0);          // constant(as,0.0): explicit zero term
+    }
+    w0.time = tm_begin(c, w0.p, spacial); tm_append(c, w0.time, key_zero(), 0.0);          // constant(as,0.0): explicit zero term
     #pragma unroll 1
     for (int i = 0; i < n0; ++i) st.init_w[i] = ivl_width(tm_range(c, w0.set[i]));   // _indexed_set_models_widths
     ws_store(c, st.qbase, 0, w0);
@@ -176,9 +232,10 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
         bool too_large = enclosure_too_large(c, L, range, init_w, P.ratio);
         if (trange.l >= P.T || ws.n_events >= P.max_events) {
             out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
+            out_enclosure(c, O, ws, n);
         } else if (too_large) {
             // premature termination on enclosure size; UPPER semantics keeps the set as final, LOWER drops it (:308-313)
-            if (!P.lower) out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n);
+            if (!P.lower) { out_box(c, O.final_, O.final_loc, O.n_final, P.max_boxes, O.stride, ws.loc, range, n); out_enclosure(c, O, ws, n); }
         } else {
             // ---- _evolution_step ------------------------------------------------------------------------------
             O.steps++;
@@ -342,9 +399,9 @@ AB_HDN bool cell_advance(Ctx& c, const SystemDesc& S, const EvolveParams& P, Cel
     return nq > 0 && c.status == ST_OK;
 }
 
-AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O) {
+AB_HDN void evolve_cell(Ctx& c, const SystemDesc& S, int loc0, const double* box, const EvolveParams& P, CellOutput& O, const uint64_t* enc = 0) {
     CellState st;
-    cell_begin(c, S, loc0, box, P, st);
+    cell_begin(c, S, loc0, box, P, st, enc);
     #pragma unroll 1
     while (cell_advance(c, S, P, st, O)) { }
 }

@@ -49,6 +49,14 @@ $H watertank reach acc=3 T=2 out=$G/watertank_reach_acc3_T2.txt
 $H springs reach acc=3 out=$G/springs_reach_acc3.txt && gzip -9 -f -n $G/springs_reach_acc3.txt
 # outer_chain_reach(initial, DIRECTION_BACKWARD): backward laps plus backward_jump_set between them
 $H bouncingball reach acc=5 backward=1 init=2.0,4.0,0.0,0.3 out=$G/bouncingball_backward_chain_acc5.txt
+# epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627): lock-to-grid laps of the midpoints with LOWER_SEMANTICS, the
+# final TaylorSets of a lap starting the next. One worker thread, so that the pruning draws (rand()) come in unit order.
+ORACLE_THREADS=1 $H vanderpol epslower acc=3 prune=0 init=1.0,1.3,1.0,1.6 out=$G/vanderpol_epslower_acc3.txt
+ORACLE_THREADS=1 $H bouncingball epslower acc=4 out=$G/bouncingball_epslower_acc4.txt
+ORACLE_THREADS=1 $H watertank epslower acc=3 prune=0 out=$G/watertank_epslower_acc3.txt
+ORACLE_THREADS=1 $H watertank epslower acc=3 prune=1 out=$G/watertank_epslower_acc3_prune.txt
+# the system the laps evolve: interval parameters at their midpoints (getMidpointsSet, :1000-1014)
+$H watertank system midparams=1 out=$G/watertank_midparams.sys
 # IntegratorInterface::flow_bounds / TaylorIntegrator::flow (src/integrator.cpp:44-152): the vector field of
 # test/test_integrator.cpp (x'=2, y'=3) with its box and step, and the van der Pol / bouncing-ball dynamics
 $H constder system out=$G/constder.sys

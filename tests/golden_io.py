@@ -69,6 +69,9 @@ def load_dump(name):
                 cur_set = out["sets"].setdefault(k, {}).setdefault(t[2], [])
             elif k == "c" and cur_set is not None:
                 cur_set.append([_f(x) for x in t[1:]])
+            elif k == "epsilon":
+                # "epsilon loc <name> v0 v1 ..": the HybridFloatVector of epsilon_lower_chain_reach
+                out.setdefault("epsilon", {})[t[2]] = [_f(x) for x in t[3:]]
             elif k == "seconds":
                 out["config"]["ref_seconds"] = float(t[1])
     return out

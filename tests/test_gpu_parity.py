@@ -98,6 +98,86 @@ def test_analyser_upper_reach_evolve_identical_cells(pkg, name, init, laps):
         an.close()
 
 
+EPS_CASES = [
+    ("bouncingball", "bouncingball_epslower_acc4.txt", [-10.1, 10.1, -0.1, 2.1], {"freefall": [0.0, 0.001, 1.999, 2.0]}, True, None),
+    ("vanderpol", "vanderpol_epslower_acc3.txt", [-3.0, 3.0, -3.0, 3.0], {"loc": [1.0, 1.3, 1.0, 1.6]}, False, None),
+    ("watertank", "watertank_epslower_acc3.txt", [0.0, 1.0, 4.5, 9.0],
+     {"flow,idle,rising": [1.0, 1.0, 6.0, 7.5], "flow,idle,falling": [0.0, 0.0, 6.0, 7.5]}, False, "watertank_midparams"),
+    ("watertank", "watertank_epslower_acc3_prune.txt", [0.0, 1.0, 4.5, 9.0],
+     {"flow,idle,rising": [1.0, 1.0, 6.0, 7.5], "flow,idle,falling": [0.0, 0.0, 6.0, 7.5]}, True, "watertank_midparams"),
+]
+
+
+@pytest.mark.parametrize("system,name,domain,init,prune,substituted", EPS_CASES)
+def test_epsilon_lower_chain_reach_identical_cells_and_epsilon(pkg, system, name, domain, init, prune, substituted):
+    """HybridReachabilityAnalyser::epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627) with
+    LowerReachEpsilonWorker (include/workers.h:171-329) on the device: the final TaylorSets of a lap are handed to the next lap
+    as enclosure records. The reached cells and the epsilon vector equal the reference's bit for bit; with pruning on, the
+    kept enclosures follow glibc's rand() sequence as in a fresh single-worker reference process."""
+    d = golden_io.load_dump(name)
+    an = pkg.HybridReachabilityAnalyser(_system(system), domain, d["config"]["acc"], settings={"arena_words": 262144, "max_boxes": 512})
+    try:
+        reach, eps, laps = an.epsilon_lower_chain_reach(init, prune=prune, substituted_system_text=_system(substituted) if substituted else None)
+        rl, rb = an.enumerate(reach)
+        assert laps >= 2 and an.last_status.launches >= laps
+        for lname, ref in d["sets"]["reach"].items():
+            mine = rb[rl == an.evolver.location(lname)]
+            assert golden_io.boxes_equal_bits(mine, ref), "reach cells of %s in %s" % (system, lname)
+        assert sum(len(v) for v in d["sets"]["reach"].values()) == rb.shape[0]
+        for lname, ref in d["epsilon"].items():
+            mine = eps[an.evolver.location(lname)][:len(ref)]
+            assert golden_io.boxes_equal_bits(mine, ref), "epsilon of %s in %s: %r vs %r" % (system, lname, mine, ref)
+        assert an.evolver.settings.semantics == 0
+    finally:
+        an.close()
+
+
+def test_final_enclosures_restart_the_evolution(pkg):
+    """ab200_reach_evolve_enclosures: evolving for T in one call and in two calls of T/2, the second started from the final
+    TaylorSets of the first, gives final boxes that contain the one-call ones up to the reconditioning differences -- and the
+    models handed over decode to polynomials whose constant terms lie inside the final boxes."""
+    d = golden_io.load_dump("vanderpol_cells_acc4_backward.txt")
+    ev = _evolver(pkg, d, arena_words=65536, max_boxes=320)
+    try:
+        dim = ev.dims[0]
+        cells = d["cells"][:8]
+        locs = [ev.location(c["loc"]) for c in cells]
+        boxes = pkg.pack_boxes([c["box"] for c in cells], dim)
+        (_, _, _), (foff, fbox, _), enc = ev.reach_evolve_enclosures(locs, boxes, 0.25, 5)
+        assert len(enc) == int(foff[-1]) >= len(cells)
+        assert np.array_equal(enc.unit_offsets, foff)
+        for i in range(len(enc)):
+            for k in range(dim):
+                ex, co, err = enc.model(i, k)
+                assert ex.shape[1] >= dim and err >= 0.0
+                const = co[(ex.sum(axis=1) == 0)]
+                c0 = const[0] if const.size else 0.0
+                assert fbox[i, 2 * k] <= c0 <= fbox[i, 2 * k + 1]
+        (_, _, _), (foff2, fbox2, _), enc2 = ev.reach_evolve_enclosures(None, None, 0.25, 5, initial=enc)
+        (_, _, _), (foff1, fbox1, _), _ = ev.reach_evolve_enclosures(locs, boxes, 0.5, 5)
+        assert len(enc2) == int(foff2[-1]) and foff2.shape[0] == len(enc) + 1
+        # the same flow either way: where a cell gave one final set in every call, the two final boxes overlap (both enclose
+        # the image of the cell under the flow for 0.5) and have comparable widths
+        compared = 0
+        for i in range(len(cells)):
+            if foff[i + 1] - foff[i] != 1 or foff1[i + 1] - foff1[i] != 1:
+                continue
+            u = int(foff[i])
+            if foff2[u + 1] - foff2[u] != 1:
+                continue
+            a = fbox1[int(foff1[i])]; b = fbox2[int(foff2[u])]
+            compared += 1
+            for k in range(dim):
+                assert max(a[2 * k], b[2 * k]) <= min(a[2 * k + 1], b[2 * k + 1])
+                w1 = a[2 * k + 1] - a[2 * k]; w2 = b[2 * k + 1] - b[2 * k]
+                assert w2 <= 16 * w1 + 1e-9 and w1 <= 16 * w2 + 1e-9
+        assert compared >= len(cells) // 2
+        sub = enc.select([3, 1])
+        assert len(sub) == 2 and np.array_equal(sub.model(0, 0)[1], enc.model(3, 0)[1])
+    finally:
+        ev.close()
+
+
 @pytest.mark.parametrize("name,init", [("bouncingball_chain_acc5.txt", [0.0, 0.001, 1.999, 2.0]),
                                          ("bouncingball_chain_acc6.txt", [-2.0, 0.5, 0.5, 1.5]),
                                          ("bouncingball_backward_chain_acc5.txt", [2.0, 4.0, 0.0, 0.3])])

@@ -66,6 +66,24 @@ def test_host_build_reproduces_reference_cell_sets(hostchain, system, golden, ar
     assert "cell sets identical (bit-exact boxes)" in out, out[-2000:]
 
 
+# epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627): laps of LOWER_SEMANTICS evolution whose final TaylorSets
+# start the next lap; the cells AND the epsilon vector must equal the reference's bit for bit. The watertank case evolves the
+# system with its interval parameter at the midpoint and draws the pruning from glibc's rand() sequence.
+EPS_CASES = [
+    ("bouncingball", "bouncingball_epslower_acc4.txt", ["epslower", "acc=4", "domain=-10.1,10.1,-0.1,2.1", "init=0.0,0.001,1.999,2.0"]),
+    ("watertank", "watertank_epslower_acc3_prune.txt", ["epslower", "acc=3", "prune=1", "subsys=" + os.path.join(ROOT, "tests", "golden", "watertank_midparams.sys"),
+                                                        "domain=0.0,1.0,4.5,9.0", "loc=2", "init=1.0,1.0,6.0,7.5", "loc=1", "init=0.0,0.0,6.0,7.5"]),
+]
+
+
+@pytest.mark.parametrize("system,golden,args", EPS_CASES)
+def test_host_build_epsilon_lower_chain_reach(hostchain, system, golden, args):
+    g = os.path.join(ROOT, "tests", "golden")
+    out = subprocess.run([hostchain, os.path.join(g, system + ".sys"), os.path.join(g, golden)] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600).stdout.decode()
+    assert "cell sets identical (bit-exact boxes)" in out and "differs" not in out, out[-2000:]
+
+
 WIDE_CASES = [
     ("springs", "springs_reach_acc3.txt.gz", ["upper", "acc=3", "T=40", "domain=0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0",
                                               "init=0,0,0,0,0,0,0,0,3,3"]),

@@ -20,6 +20,7 @@ using namespace ab200;
 
 struct ab200_cellset { std::vector<uint64_t> keys; };
 struct ab200_boxlist { std::vector<uint64_t> offsets; std::vector<double> boxes; std::vector<int32_t> locs; };
+struct ab200_enclosures { std::vector<uint64_t> offsets; std::vector<uint64_t> words; std::vector<int32_t> locs; std::vector<uint64_t> unit_offsets; int key_words; };
 struct ab200_ctx { HostSystem sys; KeyLayout K; bool have_layout; std::string err; int accuracy; ab200_settings settings; };
 extern "C" int ab200_set_settings(ab200_ctx* ctx, const ab200_settings* s) { ctx->settings = *s; return AB200_OK; }
 extern "C" int ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s) { *s = ctx->settings; return AB200_OK; }
@@ -42,6 +43,7 @@ int ab200_ctx_jump_check(ab200_ctx* ctx, int loc, int event, size_t n, const dou
     return AB200_OK;
 }
 const KeyLayout* ab200_ctx_layout(const ab200_ctx* ctx) { return &ctx->K; }
+int ab200_ctx_swap_system(ab200_ctx* ctx, HostSystem* other) { std::swap(ctx->sys, *other); return AB200_OK; }
 void ab200_ctx_set_error(ab200_ctx* ctx, const char* msg) { ctx->err = msg; }
 std::vector<uint64_t>& ab200_cellset_keys(ab200_cellset* cs) { return cs->keys; }
 ab200_cellset* ab200_cellset_new() { return new ab200_cellset(); }
@@ -69,7 +71,7 @@ extern "C" int ab200_set_accuracy(ab200_ctx* ctx, int32_t accuracy) {
 }
 
 static std::vector<uint64_t> arena(1 << 22);
-static long g_cells = 0, g_steps = 0; static int g_peak = 0, g_maxboxes = 0;
+static long g_cells = 0, g_steps = 0; static int g_peak = 0, g_maxboxes = 0, g_maxenc = 0;
 
 extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const int32_t* loc, const double* boxes, double T,
                                         int32_t max_events, int32_t ignore_activations, int32_t direction,
@@ -83,7 +85,7 @@ extern "C" int ab200_upper_reach_evolve(ab200_ctx* ctx, uint64_t n_cells, const 
     for (uint64_t ci = 0; ci < n_cells; ++ci) {
         Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
         EvolveParams P; P.lower = 0; P.backward = direction ? 1 : 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
-        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0; O.enc = 0; O.enc_cap = 0; O.enc_used = 0; O.n_enc = 0;
         evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
         g_cells++; g_steps += O.steps; if (c.A.peak > g_peak) g_peak = c.A.peak; if (O.n_reach > g_maxboxes) g_maxboxes = O.n_reach;
         if (c.status != ST_OK) { printf("cell %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
@@ -124,7 +126,7 @@ extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const 
     for (uint64_t ci = 0; ci < n_cells; ++ci) {
         Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
         EvolveParams P; P.lower = ctx->settings.semantics; P.backward = 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
-        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0; O.enc = 0; O.enc_cap = 0; O.enc_used = 0; O.n_enc = 0;
         evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
         g_cells++; g_steps += O.steps;
         if (c.status != ST_OK) { printf("cell %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
@@ -136,6 +138,61 @@ extern "C" int ab200_reach_evolve_boxes(ab200_ctx* ctx, uint64_t n_cells, const 
     if (status) memset(status, 0, sizeof(*status));
     return AB200_OK;
 }
+
+// stand-ins for the enclosure hand-over of ab200_capi.cu: the same record format, written and read by the same device code
+extern "C" int ab200_reach_evolve_enclosures(ab200_ctx* ctx, uint64_t n_units, const int32_t* loc, const double* boxes, const ab200_enclosures* initial,
+                                             double T, int32_t max_events, int ignore_activations, int direction, int32_t max_enclosure_words,
+                                             ab200_boxlist** reach, ab200_boxlist** fin, ab200_enclosures** fenc, ab200_status* status) {
+    (void)direction;
+    const SystemDesc& S = ctx->sys.desc;
+    const int MAXB = 4096, ENC = max_enclosure_words > 0 ? max_enclosure_words : 16384;
+    std::vector<double> rb(MAXB * 2 * AB_MAXN), fb(MAXB * 2 * AB_MAXN); std::vector<int32_t> rl(MAXB), fl(MAXB); std::vector<uint64_t> eb(ENC);
+    ab200_boxlist* R = new ab200_boxlist(); ab200_boxlist* F = new ab200_boxlist(); ab200_enclosures* E = new ab200_enclosures();
+    R->offsets.push_back(0); F->offsets.push_back(0); E->unit_offsets.push_back(0); E->key_words = AB_KW;
+    if (initial) n_units = initial->locs.size();
+    std::vector<double> zero(AB200_BOX_STRIDE, 0.0);
+    for (uint64_t ci = 0; ci < n_units; ++ci) {
+        Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
+        EvolveParams P; P.lower = ctx->settings.semantics; P.backward = 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
+        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        O.enc = eb.data(); O.enc_cap = ENC; O.enc_used = 0; O.n_enc = 0;
+        if (initial) evolve_cell(c, S, initial->locs[ci], zero.data(), P, O, initial->words.data() + initial->offsets[ci]);
+        else evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
+        g_cells++; g_steps += O.steps; if (c.A.peak > g_peak) g_peak = c.A.peak; if (O.enc_used > g_maxenc) g_maxenc = O.enc_used; if (O.n_reach > g_maxboxes) g_maxboxes = O.n_reach;
+        if (c.status != ST_OK) { printf("unit %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
+        for (int k = 0; k < O.n_reach; ++k) { for (int j = 0; j < AB200_BOX_STRIDE; ++j) R->boxes.push_back(rb[k * O.stride + j]); R->locs.push_back(rl[k]); }
+        for (int k = 0; k < O.n_final; ++k) { for (int j = 0; j < AB200_BOX_STRIDE; ++j) F->boxes.push_back(fb[k * O.stride + j]); F->locs.push_back(fl[k]); }
+        R->offsets.push_back(R->locs.size()); F->offsets.push_back(F->locs.size());
+        for (int o = 0; o < O.enc_used; ) {
+            const int len = (int)(eb[o + 1] & 0xFFFFFFFFu);
+            E->offsets.push_back(E->words.size()); E->locs.push_back((int32_t)(eb[o] >> 32));
+            E->words.insert(E->words.end(), eb.begin() + o, eb.begin() + o + len);
+            o += len;
+        }
+        E->unit_offsets.push_back(E->locs.size());
+    }
+    *reach = R; *fin = F; *fenc = E;
+    if (status) memset(status, 0, sizeof(*status));
+    return AB200_OK;
+}
+extern "C" int ab200_enclosures_view(const ab200_enclosures* e, uint64_t* count, const int32_t** locs, const uint64_t** unit_offsets, uint64_t* n_units) {
+    if (count) *count = e->locs.size();
+    if (locs) *locs = e->locs.data();
+    if (unit_offsets) *unit_offsets = e->unit_offsets.data();
+    if (n_units) *n_units = e->unit_offsets.size() - 1;
+    return AB200_OK;
+}
+extern "C" int ab200_enclosures_select(const ab200_enclosures* src, uint64_t n, const uint64_t* idx, ab200_enclosures** out) {
+    ab200_enclosures* e = new ab200_enclosures(); e->key_words = src->key_words; e->unit_offsets.assign(1, 0);
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint64_t* q = src->words.data() + src->offsets[idx[k]];
+        e->offsets.push_back(e->words.size()); e->locs.push_back(src->locs[idx[k]]);
+        e->words.insert(e->words.end(), q, q + (size_t)(q[1] & 0xFFFFFFFFu));
+        e->unit_offsets.push_back(e->locs.size());
+    }
+    *out = e; return AB200_OK;
+}
+extern "C" void ab200_enclosures_free(ab200_enclosures* e) { delete e; }
 
 #include "../../release-1.0_b200/csrc/ab200_analyser.cu"
 
@@ -149,12 +206,16 @@ int main(int argc, char** argv) {
     const bool chain = !strcmp(argv[3], "chain");
     const bool lower = !strcmp(argv[3], "lower");
     const bool bchain = !strcmp(argv[3], "bchain");
+    const bool epslower = !strcmp(argv[3], "epslower");
+    int prune = 1; const char* subsys = 0;     // subsys=<file>: the system with its interval parameters at their midpoints
     memset(&ctx.settings, 0, sizeof(ctx.settings));
     int acc = 4, events = 5, mince = 0; double T = 1.0, lock = 0; std::vector<double> dom; std::vector<std::vector<double> > inits; std::vector<int32_t> init_locs; int init_loc = 0;
     for (int a = 4; a < argc; ++a) {
         if (!strncmp(argv[a], "acc=", 4)) acc = atoi(argv[a] + 4);
         if (!strncmp(argv[a], "events=", 7)) events = atoi(argv[a] + 7);
         if (!strncmp(argv[a], "mince=", 6)) mince = atoi(argv[a] + 6);
+        if (!strncmp(argv[a], "prune=", 6)) prune = atoi(argv[a] + 6);
+        if (!strncmp(argv[a], "subsys=", 7)) subsys = argv[a] + 7;
         if (!strncmp(argv[a], "T=", 2)) T = atof(argv[a] + 2);
         if (!strncmp(argv[a], "lock=", 5)) lock = strtod(argv[a] + 5, 0);
         if (!strncmp(argv[a], "domain=", 7)) dom = csv(argv[a] + 7);
@@ -171,21 +232,39 @@ int main(int argc, char** argv) {
     if (lock > 0) ab200_analyser_set_lock_time(an, lock);
     printf("lock %a\n", an->lock_time);
     ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
-    if (lower) rc = ab200_analyser_lower_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, &reach, &evolve, &st);
+    std::vector<double> eps((size_t)L * AB200_MAX_DIM, 0.0); int laps = 0;
+    if (epslower) {
+        // the pruning draw restates glibc's rand(): check it against the C library of this machine first
+        { GlibcRand g; for (int i = 0; i < 100000; ++i) if (g.next() != rand()) { printf("GlibcRand differs from rand() at draw %d\n", i); return 1; } }
+        std::string subtext;
+        if (subsys) { std::ifstream f2(subsys); std::stringstream s2; s2 << f2.rdbuf(); subtext = s2.str(); }
+        rc = ab200_analyser_epsilon_lower_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), prune, subsys ? subtext.c_str() : 0, &reach, eps.data(), &laps, &st);
+    }
+    else if (lower) rc = ab200_analyser_lower_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, &reach, &evolve, &st);
     else if (chain || bchain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), bchain ? 1 : 0, &reach, &st);
     else rc = ab200_analyser_upper_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, mince, &reach, &evolve, &st);
     if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld arena peak %d\n", rc, ctx.err.c_str(), g_cells, g_steps, g_peak); return 1; }
-    printf("cells evolved %ld steps %ld arena peak %d words, max reach boxes per cell %d\n", g_cells, g_steps, g_peak, g_maxboxes);
+    printf("cells evolved %ld steps %ld arena peak %d words, max reach boxes per cell %d, max enclosure words per unit %d\n", g_cells, g_steps, g_peak, g_maxboxes, g_maxenc);
     // compare with the oracle dump: lines "reach"/"evolve" followed by "c <loc?> boxes"
     std::ifstream df(argv[2]); std::string line;
     std::vector<std::vector<double> > ref_reach, ref_evolve; std::vector<std::vector<double> >* cur = 0;
+    int bad = 0;
     while (std::getline(df, line)) {
         std::istringstream in(line); std::string t; in >> t;
+        if (t == "epsilon" && epslower) {
+            // "epsilon loc <name> v0 v1 ..": HybridFloatVector of the reference, compared bit for bit
+            std::string kw, name; in >> kw >> name; int l = -1;
+            for (size_t k = 0; k < ctx.sys.loc_names.size(); ++k) if (ctx.sys.loc_names[k] == name) l = (int)k;
+            std::string v; int i = 0;
+            while (l >= 0 && in >> v) { double r = strtod(v.c_str(), 0); if (memcmp(&r, &eps[(size_t)l * AB200_MAX_DIM + i], 8)) { printf("epsilon %s[%d] differs: %a vs %a\n", name.c_str(), i, eps[(size_t)l * AB200_MAX_DIM + i], r); bad = 1; } ++i; }
+            if (l < 0) { printf("unknown location %s\n", name.c_str()); bad = 1; }
+            continue;
+        }
         if (t == "reach") cur = &ref_reach; else if (t == "evolve") cur = &ref_evolve;
         else if (t == "c" && cur) { std::vector<double> b; std::string v; while (in >> v) b.push_back(strtod(v.c_str(), 0)); cur->push_back(b); }
     }
-    int bad = 0;
-    for (int which = 0; which < ((chain || bchain) ? 1 : 2); ++which) {
+    if (epslower) printf("laps %d\n", laps);
+    for (int which = 0; which < ((chain || bchain || epslower) ? 1 : 2); ++which) {
         uint64_t cnt = 0; ab200_analyser_enumerate(an, which ? evolve : reach, 0, &cnt, 0, 0);
         std::vector<int32_t> locs(cnt); std::vector<double> boxes(cnt * AB200_BOX_STRIDE);
         ab200_analyser_enumerate(an, which ? evolve : reach, 0, &cnt, locs.data(), boxes.data());

@@ -88,7 +88,7 @@ int main(int argc, char** argv) {
         RefCell& rc = cells[ci];
         EvolveParams P; P.lower = lower_sem; P.backward = backward_dir; P.T = T; P.max_events = chain ? 1 : events; P.ignore_activations = ignore_act; P.max_boxes = MAXB; P.temporal_order = 6;
         P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
-        CellOutput O; O.reach = reach.data(); O.reach_loc = rloc.data(); O.n_reach = 0; O.final_ = fin.data(); O.final_loc = floc.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        CellOutput O; O.reach = reach.data(); O.reach_loc = rloc.data(); O.n_reach = 0; O.final_ = fin.data(); O.final_loc = floc.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0; O.enc = 0; O.enc_cap = 0; O.enc_used = 0; O.n_enc = 0;
         Ctx c;
 #ifndef AB_NO_EMU
         {   // one fiber per lane; every lane holds the same (warp-uniform) state, lane 0's copy is reported

@@ -31,7 +31,7 @@ static void host_lap(const CellSet& frontier, int mince, double T, int events, C
     for (size_t ci = 0; ci < cells.size(); ++ci) {
         Ctx c; ctx_init_host(c, arena.data(), (int)arena.size());
         EvolveParams P; P.lower = 0; P.backward = 0; P.T = T; P.max_events = events; P.ignore_activations = 0; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
-        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
+        CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0; O.enc = 0; O.enc_cap = 0; O.enc_used = 0; O.n_enc = 0;
         evolve_cell(c, hs.desc, 0, cells[ci].b, P, O);
         if (c.status != ST_OK) { printf("cell %zu status %d\n", ci, c.status); exit(1); }
         for (int which = 0; which < 2; ++which) {

@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
         c.A.top = 0;
         EvolveParams P; P.lower = 0; P.backward = 0; P.T = T; P.max_events = getenv("AB_EVENTS") ? atoi(getenv("AB_EVENTS")) : 5; P.ignore_activations = getenv("AB_IGNORE") ? 1 : 0; P.max_boxes = 4096; P.temporal_order = 6; P.ratio = getenv("AB_RATIO") ? atof(getenv("AB_RATIO")) : 1e30; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 4;
         static double rb[4096 * 10], fb[4096 * 10]; static int32_t rl[4096], fl[4096];
-        CellOutput O; O.reach = rb; O.reach_loc = rl; O.n_reach = 0; O.final_ = fb; O.final_loc = fl; O.n_final = 0; O.stride = 10; O.steps = 0;
+        CellOutput O; O.reach = rb; O.reach_loc = rl; O.n_reach = 0; O.final_ = fb; O.final_loc = fl; O.n_final = 0; O.stride = 10; O.steps = 0; O.enc = 0; O.enc_cap = 0; O.enc_used = 0; O.n_enc = 0;
         double box[10]; for (int i = 0; i < 2 * n; ++i) box[i] = strtod(argv[2 + i], 0);
         (void)nsteps;
         evolve_cell(c, H.desc, 0, box, P, O);
