@@ -11,6 +11,10 @@
 #include <fstream>
 #include <sstream>
 #include <algorithm>
+#ifdef AB_CHAIN_EMU      // the enclosure hand-over under the 32-lane warp emulator (lane-strided record copies, wsync placement)
+#define AB_WARP_EMU 1
+#include "warp_emu.h"
+#endif
 #include "../../release-1.0_b200/csrc/ab200_evolve.cuh"
 #include "../../release-1.0_b200/csrc/ab200_system.h"
 #include "../../release-1.0_b200/csrc/ab200_paving.h"
@@ -156,8 +160,24 @@ extern "C" int ab200_reach_evolve_enclosures(ab200_ctx* ctx, uint64_t n_units, c
         EvolveParams P; P.lower = ctx->settings.semantics; P.backward = 0; P.T = T; P.max_events = max_events; P.ignore_activations = ignore_activations; P.max_boxes = MAXB; P.temporal_order = 6; P.ratio = 5.0; P.spacial_sweep = 1e-12; P.spacial_order = 6; P.max_working_sets = 16;
         CellOutput O; O.reach = rb.data(); O.reach_loc = rl.data(); O.n_reach = 0; O.final_ = fb.data(); O.final_loc = fl.data(); O.n_final = 0; O.stride = 2 * AB_MAXN; O.steps = 0;
         O.enc = eb.data(); O.enc_cap = ENC; O.enc_used = 0; O.n_enc = 0;
-        if (initial) evolve_cell(c, S, initial->locs[ci], zero.data(), P, O, initial->words.data() + initial->offsets[ci]);
-        else evolve_cell(c, S, loc[ci], boxes + ci * AB200_BOX_STRIDE, P, O);
+        const int l0 = initial ? initial->locs[ci] : loc[ci];
+        const double* b0 = initial ? zero.data() : boxes + ci * AB200_BOX_STRIDE;
+        const uint64_t* e0 = initial ? initial->words.data() + initial->offsets[ci] : 0;
+#ifdef AB_CHAIN_EMU
+        {   // one fiber per lane; every lane holds the same (warp-uniform) state, lane 0's copy is reported
+            static std::vector<uint64_t> smem(AB_SM_WORDS);
+            CellOutput O0 = O; Ctx c0;
+            wemu::run(32, [&](int lane) {
+                Ctx cl; ctx_init(cl, arena.data(), (int)arena.size(), smem.data(), binom_host());
+                CellOutput Ol = O;
+                evolve_cell(cl, S, l0, b0, P, Ol, e0);
+                if (lane == 0) { O0 = Ol; c0 = cl; }
+            });
+            O = O0; c = c0;
+        }
+#else
+        evolve_cell(c, S, l0, b0, P, O, e0);
+#endif
         g_cells++; g_steps += O.steps; if (c.A.peak > g_peak) g_peak = c.A.peak; if (O.enc_used > g_maxenc) g_maxenc = O.enc_used; if (O.n_reach > g_maxboxes) g_maxboxes = O.n_reach;
         if (c.status != ST_OK) { printf("unit %llu status %d\n", (unsigned long long)ci, c.status); if (status) { status->code = c.status; status->cell = (int64_t)ci; } return c.status; }
         for (int k = 0; k < O.n_reach; ++k) { for (int j = 0; j < AB200_BOX_STRIDE; ++j) R->boxes.push_back(rb[k * O.stride + j]); R->locs.push_back(rl[k]); }
