@@ -7,4 +7,5 @@
 #include_next "workers.h"
 #include "workers_b200.h"
 #define UpperReachEvolveWorker B200UpperReachEvolveWorker
+#define LowerReachEpsilonWorker B200LowerReachEpsilonWorker     /* src/reachability_analyser.cpp:583 */
 #endif

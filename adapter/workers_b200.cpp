@@ -130,7 +130,7 @@ namespace {
 // One device context per automaton (by name), created on first use; lives for the process.
 struct B200Context {
     ab200_ctx* ctx;
-    std::string system_name;
+    std::string system_name, system_text;
     B200Context() : ctx(0) { }
 };
 B200Context& b200_context(const HybridIOAutomaton& sys) {
@@ -145,9 +145,14 @@ B200Context& b200_context(const HybridIOAutomaton& sys) {
         if(const char* e=getenv("AB200_ARENA_WORDS")) st.arena_words=atoi(e);
         if(const char* e=getenv("AB200_MAX_BOXES")) st.max_boxes=atoi(e);
         if(ab200_set_settings(c.ctx,&st)!=AB200_OK) throw std::runtime_error(std::string("ab200_set_settings: ")+ab200_last_error(c.ctx));
-        std::string text=b200_system_text(sys);
-        if(ab200_set_system_text(c.ctx,text.c_str())!=AB200_OK) throw std::runtime_error(std::string("ab200_set_system_text: ")+ab200_last_error(c.ctx));
         c.system_name=sys.name();
+    }
+    // the automaton may have had parameters substituted since the last call (epsilon_lower_chain_reach evolves the system
+    // with its interval parameters at their midpoints, src/reachability_analyser.cpp:517-527): upload the text when it changed
+    std::string text=b200_system_text(sys);
+    if(text!=c.system_text) {
+        if(ab200_set_system_text(c.ctx,text.c_str())!=AB200_OK) throw std::runtime_error(std::string("ab200_set_system_text: ")+ab200_last_error(c.ctx));
+        c.system_text=text;
     }
     return c;
 }
@@ -226,6 +231,122 @@ std::pair<HybridDenotableSet,HybridDenotableSet> B200UpperReachEvolveWorker::get
     std::pair<HDS,HDS> result(_to_denotable(reach),_to_denotable(evolve));
     ab200_cellset_free(reach); ab200_cellset_free(evolve);
     return result;
+}
+
+// ---- LowerReachEpsilonWorker ---------------------------------------------------------------------------------------------
+B200LowerReachEpsilonWorker::B200LowerReachEpsilonWorker(const EvolverType& evolver, EL& initial_enclosures, const HybridTime& time,
+        const HybridGrid& grid, const int& accuracy)
+    : _evolver(evolver), _initial_enclosures(initial_enclosures), _time(time), _grid(grid), _accuracy(accuracy) { }
+
+tuple<std::pair<B200LowerReachEpsilonWorker::HUM,B200LowerReachEpsilonWorker::HUM>,B200LowerReachEpsilonWorker::EL,HybridDenotableSet,HybridFloatVector>
+B200LowerReachEpsilonWorker::get_result() {
+    const HybridIOAutomaton* sys=dynamic_cast<const HybridIOAutomaton*>(&_evolver->system());
+    const ImageSetHybridEvolver* ise=dynamic_cast<const ImageSetHybridEvolver*>(_evolver.get());
+    if(!sys || !ise) throw std::runtime_error("B200LowerReachEpsilonWorker: needs an ImageSetHybridEvolver over a HybridIOAutomaton");
+    ab200_ctx* ctx=b200_context(*sys).ctx;
+    const std::map<DiscreteLocation,Float>& hmax=ise->settings().maximum_step_size();
+    const HybridFloatVector& refw=ise->settings().reference_enclosure_widths();
+    std::vector<DiscreteLocation> locs;                               // library order = map order of the grid
+    for(HybridGrid::locations_const_iterator gi=_grid.locations_begin(); gi!=_grid.locations_end(); ++gi) {
+        const DiscreteLocation& q=gi->first; const Grid& g=gi->second;
+        int li=ab200_location_index(ctx,q.name().c_str());
+        if(li!=(int)locs.size()) throw std::runtime_error("B200LowerReachEpsilonWorker: location order differs for "+q.name());
+        locs.push_back(q);
+        double rw[AB200_MAX_DIM]={0}, org[AB200_MAX_DIM]={0}, len[AB200_MAX_DIM]={0};
+        const Vector<Float>& w=refw.find(q)->second;
+        for(uint i=0;i<g.dimension();++i) { rw[i]=w[i]; org[i]=g.origin()[i]; len[i]=g.lengths()[i]; }
+        if(ab200_set_location_tuning(ctx,li,hmax.find(q)->second,rw,org,len)!=AB200_OK) throw std::runtime_error(ab200_last_error(ctx));
+    }
+    if(ab200_set_accuracy(ctx,_accuracy)!=AB200_OK) throw std::runtime_error(ab200_last_error(ctx));
+
+    // the initial TaylorSets as enclosure records (consumes the list, as include/workers.h:256-257 does)
+    std::vector<int32_t> eloc, nargs, nterms; std::vector<double> errors, coefs; std::vector<uint8_t> exps;
+    while(!_initial_enclosures.empty()) {
+        const EnclosureType& e=_initial_enclosures.front();
+        const TaylorSet& ts=e.second;
+        eloc.push_back(ab200_location_index(ctx,e.first.name().c_str()));
+        nargs.push_back((int32_t)ts.argument_size());
+        for(uint i=0;i<ts.dimension();++i) {
+            const TaylorModel& m=ts.models()[i];
+            nterms.push_back((int32_t)m.number_of_nonzeros()); errors.push_back(m.error());
+            for(TaylorModel::const_iterator it=m.begin(); it!=m.end(); ++it) {
+                for(uint j=0;j<m.argument_size();++j) exps.push_back((uint8_t)it->key()[j]);
+                coefs.push_back(it->data());
+            }
+        }
+        _initial_enclosures.pop_front();
+    }
+    const size_t n_units=eloc.size();
+    ab200_enclosures* initial=0;
+    if(ab200_enclosures_create(ctx,n_units,n_units?&eloc[0]:0,n_units?&nargs[0]:0,nterms.empty()?0:&nterms[0],errors.empty()?0:&errors[0],
+                               exps.empty()?0:&exps[0],coefs.empty()?0:&coefs[0],&initial)!=AB200_OK)
+        throw std::runtime_error(std::string("ab200_enclosures_create: ")+ab200_last_error(ctx));
+
+    ab200_settings saved, low; ab200_ctx_get_settings(ctx,&saved);
+    low=saved; low.semantics=1; low.maximum_enclosure_widths_ratio=ise->settings().maximum_enclosure_widths_ratio();
+    ab200_boxlist *rb=0,*fb=0; ab200_enclosures* fe=0; ab200_status st;
+    int rc=ab200_set_settings(ctx,&low);
+    if(rc==AB200_OK) rc=ab200_reach_evolve_enclosures(ctx,n_units,0,0,initial,_time.continuous_time(),_time.discrete_time(),0,0,0,&rb,&fb,&fe,&st);
+    ab200_set_settings(ctx,&saved);
+    ab200_enclosures_free(initial);
+    switch(rc) {                                                     // same exception kinds as include/workers.h:318-326
+        case AB200_OK: break;
+        case AB200_E_SQRT: throw SqrtNumericException(ab200_last_error(ctx));
+        case AB200_E_TIMEOUT: throw TimeoutException();
+        default: throw std::runtime_error(std::string("libariadne_b200: ")+ab200_last_error(ctx));
+    }
+
+    HDS reach(_grid), evolve_global(_grid);
+    HUM adjoined, superposed; EL final_enclosures; HybridFloatVector epsilon;
+    HybridSpace state_space=_evolver->system().state_space();
+    for(HybridSpace::const_iterator hs=state_space.begin(); hs!=state_space.end(); ++hs)
+        epsilon.insert(std::pair<DiscreteLocation,Vector<Float> >(hs->first,Vector<Float>(hs->second)));
+    const uint64_t *roff=0,*foff=0,*uoff=0; const double *rbx=0,*fbx=0; const int32_t *rl=0,*fl=0,*el=0; uint64_t n_final=0,n_u=0;
+    ab200_boxlist_view(rb,&roff,&rbx,&rl); ab200_boxlist_view(fb,&foff,&fbx,&fl);
+    ab200_enclosures_view(fe,&n_final,&el,&uoff,&n_u);
+    std::vector<uint8_t> ex; std::vector<double> co;
+    for(size_t u=0;u<n_units;++u) {                                  // LowerReachEpsilonWorker::_compute, unit by unit
+        HDS current_reach(_grid), current_evolve(_grid);
+        for(uint64_t k=roff[u];k<roff[u+1];++k) {
+            const DiscreteLocation& q=locs[rl[k]]; const uint n=state_space[q];
+            Box b(n); for(uint i=0;i<n;++i) b[i]=Interval(rbx[k*AB200_BOX_STRIDE+2*i],rbx[k*AB200_BOX_STRIDE+2*i+1]);
+            current_reach[q].adjoin_outer_approximation(b,_accuracy);
+            epsilon[q]=max_elementwise(epsilon[q],b.widths());
+        }
+        for(uint64_t k=foff[u];k<foff[u+1];++k) {
+            const DiscreteLocation& q=locs[fl[k]]; const uint n=state_space[q];
+            Box b(n); for(uint i=0;i<n;++i) b[i]=Interval(fbx[k*AB200_BOX_STRIDE+2*i],fbx[k*AB200_BOX_STRIDE+2*i+1]);
+            current_evolve[q].adjoin_outer_approximation(b,_accuracy);
+        }
+        reach.adjoin(current_reach); evolve_global.adjoin(current_evolve);
+        for(HDS::locations_const_iterator it=current_evolve.locations_begin(); it!=current_evolve.locations_end(); ++it)
+            superposed[it->first]+=it->second.size();
+        // the final sets of the unit, location by location (ListSet keeps a map over locations), as TaylorSets
+        for(size_t li=0;li<locs.size();++li) for(uint64_t k=uoff[u];k<uoff[u+1];++k) {
+            if(el[k]!=(int32_t)li) continue;
+            const uint n=state_space[locs[li]];
+            Vector<TaylorModel> models(n);
+            for(uint i=0;i<n;++i) {
+                int32_t as=0,nt=0; double err=0;
+                ab200_enclosures_model(fe,k,(int32_t)i,&as,&nt,&err,0,0);
+                ex.assign((size_t)nt*as+1,0); co.assign((size_t)nt+1,0.0);
+                ab200_enclosures_model(fe,k,(int32_t)i,&as,&nt,&err,&ex[0],&co[0]);
+                Expansion<Float> f(as); f.reserve(nt);
+                MultiIndex a(as);
+                for(int32_t t=0;t<nt;++t) { for(int32_t j=0;j<as;++j) a.set(j,ex[(size_t)t*as+j]); f.append(a,co[t]); }
+                models[i]=TaylorModel(f,err);
+            }
+            final_enclosures.push_back(EnclosureType(locs[li],TaylorSet(models)));
+        }
+    }
+    ab200_boxlist_free(rb); ab200_boxlist_free(fb); ab200_enclosures_free(fe);
+    for(HDS::locations_const_iterator it=evolve_global.locations_begin(); it!=evolve_global.locations_end(); ++it)
+        adjoined[it->first]=it->second.size();
+    Float accuracy_divider=(1<<_accuracy);
+    HybridFloatVector grid_lengths=_grid.lengths();
+    for(HybridSpace::const_iterator hs=state_space.begin(); hs!=state_space.end(); ++hs)
+        epsilon[hs->first]+=grid_lengths[hs->first]/accuracy_divider;
+    return make_tuple<std::pair<HUM,HUM>,EL,HDS,HybridFloatVector>(std::make_pair(adjoined,superposed),final_enclosures,reach,epsilon);
 }
 
 // ---- B2: EvolverInterface seam ------------------------------------------------------------------------------------------

@@ -56,6 +56,33 @@ class B200UpperReachEvolveWorker
     const ContinuousEvolutionDirection& _continuous_direction;
 };
 
+// LowerReachEpsilonWorker (/root/reference/include/workers.h:171-329) on the library: same constructor and get_result().
+// One call evolves every initial TaylorSet for one lock-to-grid lap with LOWER_SEMANTICS on the device
+// (ab200_reach_evolve_enclosures: the sets go over as enclosure records, ab200_enclosures_create, and the final sets come
+// back as TaylorSets built from ab200_enclosures_model); discretisation, epsilon and the cell counts are taken in the
+// order of the input list, i.e. what the reference computes with one worker thread.
+class B200LowerReachEpsilonWorker
+{
+  public:
+    typedef HybridDenotableSet HDS;
+    typedef HybridEvolver::EnclosureType EnclosureType;
+    typedef HybridEvolver::ContinuousEnclosureType CE;
+    typedef std::list<EnclosureType> EL;
+    typedef std::map<DiscreteLocation,uint> HUM;
+    typedef boost::shared_ptr<EvolverInterface<HybridAutomatonInterface,EnclosureType> > EvolverType;
+
+    B200LowerReachEpsilonWorker(const EvolverType& evolver, EL& initial_enclosures, const HybridTime& time,
+                                const HybridGrid& grid, const int& accuracy);
+    tuple<std::pair<HUM,HUM>,EL,HDS,HybridFloatVector> get_result();
+
+  private:
+    const EvolverType& _evolver;
+    EL& _initial_enclosures;
+    const HybridTime& _time;
+    const HybridGrid& _grid;
+    const int& _accuracy;
+};
+
 } // namespace Ariadne
 
 #endif

@@ -151,6 +151,13 @@ int  ab200_enclosures_view(const ab200_enclosures* e, uint64_t* count, const int
 /* Coordinate model k of enclosure i as a TaylorModel: exps is [n_terms][nargs] (MultiIndex), coefs [n_terms]; pass NULL for
  * exps / coefs to query nargs, n_terms and the uniform error only. */
 int  ab200_enclosures_model(const ab200_enclosures* e, uint64_t i, int32_t k, int32_t* nargs, int32_t* n_terms, double* error, uint8_t* exps, double* coefs);
+/* Enclosures from the caller's TaylorModels (the reverse of ab200_enclosures_model), for an adapter that receives TaylorSets
+ * from the reference (LowerReachEpsilonWorker's initial_enclosures, include/workers.h:171-200). Enclosure i lies in location
+ * locs[i], has nargs[i] parameters and one model per state variable of that location; models are numbered across all
+ * enclosures in order (n_terms[m], errors[m]); exps ([terms][nargs of the enclosure]) and coefs run on across the models.
+ * Terms in the reference's Expansion order (graded, include/multi_index.h:346-358); AB200_E_ARGUMENT otherwise. */
+int  ab200_enclosures_create(ab200_ctx* ctx, uint64_t count, const int32_t* locs, const int32_t* nargs, const int32_t* n_terms,
+                             const double* errors, const uint8_t* exps, const double* coefs, ab200_enclosures** out);
 /* The enclosures idx[0..n) of src as a new list (ReachabilityRestriction::filter, _filter_enclosures keep a subset). */
 int  ab200_enclosures_select(const ab200_enclosures* src, uint64_t n, const uint64_t* idx, ab200_enclosures** out);
 void ab200_enclosures_free(ab200_enclosures* e);

@@ -36,7 +36,7 @@ EXPORTS = [
     "ab200_analyser_info", "ab200_analyser_set_lock_time", "ab200_analyser_upper_reach_evolve",
     "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
     "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free", "ab200_taylor_model_op", "ab200_interval_op", "ab200_analyser_discretise_constraint", "ab200_analyser_upper_reach_evolve_from", "ab200_analyser_outer_chain_reach_from",
-    "ab200_reach_evolve_enclosures", "ab200_enclosures_view", "ab200_enclosures_model", "ab200_enclosures_select", "ab200_enclosures_free",
+    "ab200_reach_evolve_enclosures", "ab200_enclosures_view", "ab200_enclosures_model", "ab200_enclosures_select", "ab200_enclosures_free", "ab200_enclosures_create",
     "ab200_analyser_epsilon_lower_chain_reach",
 ]
 
@@ -123,6 +123,7 @@ def load_library():
     lib.ab200_enclosures_model.argtypes = [vp, u64, i32, P(i32), P(i32), P(dbl), P(C.c_uint8), P(dbl)]; lib.ab200_enclosures_model.restype = C.c_int
     lib.ab200_enclosures_select.argtypes = [vp, u64, P(u64), P(vp)]; lib.ab200_enclosures_select.restype = C.c_int
     lib.ab200_enclosures_free.argtypes = [vp]; lib.ab200_enclosures_free.restype = None
+    lib.ab200_enclosures_create.argtypes = [vp, u64, P(i32), P(i32), P(i32), P(dbl), P(C.c_uint8), P(dbl), P(vp)]; lib.ab200_enclosures_create.restype = C.c_int
     lib.ab200_ctx_get_settings.argtypes = [vp, P(Settings)]; lib.ab200_ctx_get_settings.restype = C.c_int
     lib.ab200_analyser_outer_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), i32, P(vp), P(Status)]
     lib.ab200_analyser_outer_chain_reach.restype = C.c_int
@@ -336,6 +337,24 @@ class Evolver(object):
         self.last_status = st
         self._check(rc)
         return _take_boxlist(self.lib, r, n), _take_boxlist(self.lib, f, n), Enclosures(self.lib, e)
+
+    def enclosures_create(self, sets):
+        """Enclosures from TaylorSets given as [(location index, [(exponents [terms, nargs], coefficients [terms], error), ...])]."""
+        locs = []; nargs = []; nterms = []; errors = []; exps = []; coefs = []
+        for loc, models in sets:
+            locs.append(int(loc)); nargs.append(int(np.asarray(models[0][0]).reshape(len(models[0][1]), -1).shape[1]) if len(models[0][1]) else 0)
+            for ex, co, err in models:
+                co = np.asarray(co, dtype=np.float64); ex = np.asarray(ex, dtype=np.uint8).reshape(co.shape[0], -1)
+                nterms.append(co.shape[0]); errors.append(float(err)); exps.append(ex.reshape(-1)); coefs.append(co)
+        locs = np.asarray(locs, dtype=np.int32); nargs = np.asarray(nargs, dtype=np.int32); nterms = np.asarray(nterms, dtype=np.int32)
+        errors = np.asarray(errors, dtype=np.float64)
+        exps = np.ascontiguousarray(np.concatenate(exps) if exps else np.zeros((0,), dtype=np.uint8)).astype(np.uint8)
+        coefs = np.ascontiguousarray(np.concatenate(coefs) if coefs else np.zeros((0,), dtype=np.float64))
+        out = C.c_void_p()
+        rc = self.lib.ab200_enclosures_create(self.handle, locs.shape[0], _iptr(locs), _iptr(nargs), _iptr(nterms), _dptr(errors),
+                                              exps.ctypes.data_as(C.POINTER(C.c_uint8)), _dptr(coefs), C.byref(out))
+        self._check(rc)
+        return Enclosures(self.lib, out)
 
     def upper_reach_evolve(self, locs, boxes, time, max_events, ignore_activations=False, backward=False):
         """UpperReachEvolveWorker::get_result(): (reach CellSet, evolve CellSet)."""

@@ -800,6 +800,55 @@ extern "C" int ab200_enclosures_select(const ab200_enclosures* src, uint64_t n, 
     *out = e;
     return AB200_OK;
 }
+// Enclosures from the caller's own TaylorModels (the reverse of ab200_enclosures_model): what an adapter does with the
+// TaylorSets the reference hands to LowerReachEpsilonWorker (include/workers.h:171-200). Terms must come in the order the
+// reference's Expansion keeps them (graded, include/multi_index.h:346-358), which is the order the device merges rely on.
+extern "C" int ab200_enclosures_create(ab200_ctx* ctx, uint64_t count, const int32_t* locs, const int32_t* nargs, const int32_t* n_terms,
+                                       const double* errors, const uint8_t* exps, const double* coefs, ab200_enclosures** out) {
+    if (!ctx || !ctx->have_system || !out || (count && (!locs || !nargs || !n_terms || !errors))) return AB200_E_ARGUMENT;
+    *out = 0;
+    const int kw = ctx->sys.desc.loc[0].n > 2 ? 2 : 1, maxargs = kw == 1 ? 7 : 15;
+    ab200_enclosures* e = new ab200_enclosures(); e->key_words = kw; e->unit_offsets.assign(1, 0);
+    size_t m = 0, t = 0, x = 0;                  // running model, term and exponent indices
+    const uint64_t M = 0x00FFFFFFFFFFFFFFull;
+    for (uint64_t i = 0; i < count; ++i) {
+        const int l = locs[i], as = nargs[i];
+        if (l < 0 || l >= ctx->sys.desc.n_locs || as < 0 || as > maxargs) { delete e; ctx->err = "enclosure: bad location or too many parameters"; return AB200_E_ARGUMENT; }
+        const int n = ctx->sys.desc.loc[l].n;
+        const size_t start = e->words.size();
+        e->offsets.push_back(start); e->locs.push_back(l);
+        e->words.push_back(((uint64_t)(uint32_t)l << 32) | (uint32_t)as); e->words.push_back(0);
+        for (int k = 0; k < n; ++k, ++m) {
+            const int nt = n_terms[m];
+            if (nt < 0 || !(errors[m] >= 0.0) || (nt && (!exps || !coefs))) { delete e; ctx->err = "enclosure: bad model"; return AB200_E_ARGUMENT; }
+            uint64_t eb; memcpy(&eb, &errors[m], 8);
+            e->words.push_back(((uint64_t)(uint32_t)nt << 32) | (uint32_t)as); e->words.push_back(eb);
+            uint64_t p0 = 0, p1 = 0;
+            for (int q = 0; q < nt; ++q, ++t) {
+                uint64_t w0 = 0, w1 = 0; unsigned deg = 0;
+                for (int j = 0; j < as; ++j, ++x) {
+                    const unsigned ex = exps[x];
+                    if (ex > 127) { delete e; ctx->err = "enclosure: exponent above 127"; return AB200_E_ARGUMENT; }
+                    deg += ex;
+                    if (j < 7) w0 |= (uint64_t)ex << (8 * (6 - j)); else w1 |= (uint64_t)ex << (8 * (14 - j));
+                }
+                if (deg > 255) { delete e; ctx->err = "enclosure: degree above 255"; return AB200_E_ARGUMENT; }
+                w0 |= (uint64_t)deg << 56;
+                if (q > 0) {        // strictly ascending in the order of key_less (ab200_tm.cuh)
+                    const uint64_t sa = p0 ^ M, sb = w0 ^ M;
+                    if (!(sa < sb || (sa == sb && p1 > w1))) { delete e; ctx->err = "enclosure: terms out of order"; return AB200_E_ARGUMENT; }
+                }
+                p0 = w0; p1 = w1;
+                uint64_t cb; memcpy(&cb, &coefs[t], 8);
+                e->words.push_back(w0); if (kw > 1) e->words.push_back(w1); e->words.push_back(cb);
+            }
+        }
+        e->words[start + 1] = ((uint64_t)(uint32_t)n << 32) | (uint32_t)(e->words.size() - start);
+        e->unit_offsets.push_back(e->locs.size());
+    }
+    *out = e;
+    return AB200_OK;
+}
 extern "C" void ab200_enclosures_free(ab200_enclosures* e) { delete e; }
 
 extern "C" int ab200_flow_bounds(ab200_ctx* ctx, uint64_t n, const int32_t* loc, const double* boxes, double hmax,

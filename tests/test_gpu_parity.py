@@ -172,6 +172,13 @@ def test_final_enclosures_restart_the_evolution(pkg):
                 w1 = a[2 * k + 1] - a[2 * k]; w2 = b[2 * k + 1] - b[2 * k]
                 assert w2 <= 16 * w1 + 1e-9 and w1 <= 16 * w2 + 1e-9
         assert compared >= len(cells) // 2
+        # the same TaylorSets rebuilt from their decoded models (ab200_enclosures_create) evolve to the same bits
+        rebuilt = ev.enclosures_create([(int(enc.locs[i]), [enc.model(i, k) for k in range(dim)]) for i in range(len(enc))])
+        (_, _, _), (foff3, fbox3, _), _ = ev.reach_evolve_enclosures(None, None, 0.25, 5, initial=rebuilt)
+        assert np.array_equal(foff3, foff2) and golden_io.boxes_equal_bits(fbox3, fbox2)
+        with pytest.raises(pkg.Ab200Error):          # terms out of the Expansion order are refused
+            ex0, co0, err0 = enc.model(0, 0)
+            ev.enclosures_create([(int(enc.locs[0]), [(ex0[::-1], co0[::-1], err0)] * dim)])
         sub = enc.select([3, 1])
         assert len(sub) == 2 and np.array_equal(sub.model(0, 0)[1], enc.model(3, 0)[1])
     finally:
@@ -596,6 +603,35 @@ def test_reference_analyser_with_b200_worker(tmp_path, config, golden, args):
         assert set(mine["sets"][which].keys()) == set(ref["sets"][which].keys())
         for lname, cells in ref["sets"][which].items():
             assert golden_io.boxes_equal_bits(np.array(mine["sets"][which][lname]), cells), "%s cells of %s in %s" % (which, config, lname)
+
+
+ADAPTER_EPS_CASES = [
+    ("bouncingball", "bouncingball_epslower_acc4.txt", ["acc=4"]),
+    ("vanderpol", "vanderpol_epslower_acc3.txt", ["acc=3", "prune=0", "init=1.0,1.3,1.0,1.6"]),
+    ("watertank", "watertank_epslower_acc3_prune.txt", ["acc=3", "prune=1"]),
+]
+
+
+@pytest.mark.parametrize("config,golden,args", ADAPTER_EPS_CASES)
+def test_reference_analyser_with_b200_lower_worker(tmp_path, config, golden, args):
+    """The reference's own epsilon_lower_chain_reach (unmodified src/reachability_analyser.cpp:497-627: parameter midpoints,
+    restriction, pruning with its own rand(), epsilon bookkeeping) with adapter/workers_b200's B200LowerReachEpsilonWorker
+    where :583 builds its LowerReachEpsilonWorker: the TaylorSets of every lap cross the C ABI both ways
+    (ab200_enclosures_create / ab200_enclosures_model). Cells and epsilon must equal the stock run's bit for bit."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(golden_io.GOLDEN), "..", "oracle", "_ref", "ref_harness_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_harness_b200 has not been built (make -C oracle adapter)")
+    out = str(tmp_path / "b200_eps.txt")
+    subprocess.check_call([exe, config, "epslower", "out=" + out] + args, timeout=600)
+    mine = golden_io.load_dump(out); ref = golden_io.load_dump(golden)
+    assert "reach" in mine["sets"], open(out).read()[-600:]
+    assert set(mine["sets"]["reach"].keys()) == set(ref["sets"]["reach"].keys())
+    for lname, cells in ref["sets"]["reach"].items():
+        assert golden_io.boxes_equal_bits(np.array(mine["sets"]["reach"][lname]), cells), "reach cells of %s in %s" % (config, lname)
+    assert set(mine["epsilon"].keys()) == set(ref["epsilon"].keys())
+    for lname, e in ref["epsilon"].items():
+        assert golden_io.boxes_equal_bits(mine["epsilon"][lname], e), "epsilon of %s in %s" % (config, lname)
 
 
 EVOLVER_CASES = [
