@@ -55,6 +55,8 @@ ORACLE_THREADS=1 $H vanderpol epslower acc=3 prune=0 init=1.0,1.3,1.0,1.6 out=$G
 ORACLE_THREADS=1 $H bouncingball epslower acc=4 out=$G/bouncingball_epslower_acc4.txt
 ORACLE_THREADS=1 $H watertank epslower acc=3 prune=0 out=$G/watertank_epslower_acc3.txt
 ORACLE_THREADS=1 $H watertank epslower acc=3 prune=1 out=$G/watertank_epslower_acc3_prune.txt
+# five variables (two-word MultiIndex keys in the enclosure records); lock time 1 keeps the reference run short
+ORACLE_THREADS=1 $H springs epslower acc=2 prune=1 lock=1.0 out=$G/springs_epslower_acc2_lock1.txt
 # the system the laps evolve: interval parameters at their midpoints (getMidpointsSet, :1000-1014)
 $H watertank system midparams=1 out=$G/watertank_midparams.sys
 # IntegratorInterface::flow_bounds / TaylorIntegrator::flow (src/integrator.cpp:44-152): the vector field of

@@ -84,6 +84,15 @@ def test_host_build_epsilon_lower_chain_reach(hostchain, system, golden, args):
     assert "cell sets identical (bit-exact boxes)" in out and "differs" not in out, out[-2000:]
 
 
+def test_host_build_wide_keys_epsilon_lower_chain_reach(hostchain_wide):
+    """The enclosure hand-over with two-word MultiIndex keys (springs, five variables; three words per term in the records)."""
+    g = os.path.join(ROOT, "tests", "golden")
+    args = ["epslower", "acc=2", "prune=1", "lock=1.0", "domain=0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0", "init=0,0,0,0,0,0,0,0,3,3"]
+    out = subprocess.run([hostchain_wide, os.path.join(g, "springs.sys"), os.path.join(g, "springs_epslower_acc2_lock1.txt")] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600).stdout.decode()
+    assert "cell sets identical (bit-exact boxes)" in out and "differs" not in out and "laps 3" in out, out[-2000:]
+
+
 WIDE_CASES = [
     ("springs", "springs_reach_acc3.txt.gz", ["upper", "acc=3", "T=40", "domain=0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0",
                                               "init=0,0,0,0,0,0,0,0,3,3"]),
