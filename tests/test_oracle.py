@@ -38,6 +38,22 @@ def test_oracle_reproduces_committed_goldens(golden, args):
     assert _lines(_run(*args)) == _lines(golden_io._open(golden).read())
 
 
+@pytest.mark.parametrize("golden,args", [
+    ("bouncingball_epslower_acc4.txt", ["bouncingball", "epslower", "acc=4"]),
+    ("springs_epslower_acc2_lock1.txt", ["springs", "epslower", "acc=2", "prune=1", "lock=1.0"]),
+    ("watertank_epslower_acc3_prune.txt", ["watertank", "epslower", "acc=3", "prune=1"]),
+])
+def test_oracle_reproduces_epsilon_lower_chain_reach_goldens(golden, args, monkeypatch):
+    """epsilon_lower_chain_reach with pruning draws rand() in the order its worker threads finish: one thread (ORACLE_THREADS=1,
+    oracle/shim/boost/thread.hpp) gives the reproducible run the goldens were taken from."""
+    monkeypatch.setenv("ORACLE_THREADS", "1")
+    assert _lines(_run(*args)) == _lines(golden_io._open(golden).read())
+
+
+def test_midpoint_parameter_system_is_what_the_reference_substitutes():
+    assert _run("watertank", "system", "midparams=1") == open(os.path.join(golden_io.GOLDEN, "watertank_midparams.sys")).read()
+
+
 def test_primitive_kat_vectors_come_from_the_reference_and_hold_its_unit_test_answers():
     """tests/golden/kat_primitives.txt.gz is the output of oracle/_ref/ref_kat (the reference library itself); it must
     regenerate byte for byte, and it must contain the literal answers the reference's own unit tests assert
