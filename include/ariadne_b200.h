@@ -241,6 +241,15 @@ int  ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_init, cons
 int  ab200_analyser_epsilon_lower_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, int32_t prune,
                                               const char* substituted_system_text,
                                               ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status);
+/* lower_reach_evolve / epsilon_lower_chain_reach from a constraint-set initial set (HybridBoundedConstraintSet, the text of
+ * ab200_analyser_discretise_constraint): the midpoint of (initial cell ^ domain of the set) starts an evolution when the set
+ * is unconstrained or definitely covers it (_enclosures_from_discretised_initial_set_midpoints,
+ * src/reachability_analyser.cpp:1218-1243; BoundedConstraintSet::covers, src/function_set.cpp:327-333). */
+int  ab200_analyser_lower_reach_evolve_constraint(ab200_analyser* an, const char* constraint_text, double T, int32_t max_events,
+                                                  ab200_cellset** reach, ab200_cellset** evolve, ab200_status* status);
+int  ab200_analyser_epsilon_lower_chain_reach_constraint(ab200_analyser* an, const char* constraint_text, int32_t prune,
+                                                         const char* substituted_system_text,
+                                                         ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status);
 /* direction: 0 = DIRECTION_FORWARD (forward_jump_set between laps), 1 = DIRECTION_BACKWARD (backward_jump_set,
  * src/reachability_restriction.cpp:381-408, src/set_checker.cpp:229-352). */
 int  ab200_analyser_outer_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,

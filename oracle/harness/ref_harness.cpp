@@ -372,6 +372,7 @@ int main(int argc, char** argv) {
         try { r=analyser.epsilon_lower_chain_reach(c.initial); } catch(std::exception& e) { err=e.what(); }
         double secs=std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
         fprintf(out,"seconds %.3f err '%s' prune %d threads %u\n",secs,err.c_str(),geti(kv,"prune",1),boost::thread::hardware_concurrency());
+        if(!c.cons_text.empty()) { std::stringstream ss(c.cons_text); std::string line; while(std::getline(ss,line)) fprintf(out,"cons| %s\n",line.c_str()); }
         for(HybridFloatVector::const_iterator ei=r.second.begin(); ei!=r.second.end(); ++ei) {
             fprintf(out,"epsilon loc %s",ei->first.name().c_str());
             for(uint i=0;i<ei->second.size();++i) fprintf(out," %a",ei->second[i]);

@@ -37,7 +37,7 @@ EXPORTS = [
     "ab200_analyser_outer_chain_reach", "ab200_analyser_lower_reach_evolve", "ab200_ctx_get_settings", "ab200_analyser_discretise", "ab200_analyser_cells_evolved", "ab200_analyser_enumerate", "ab200_probe_fp64", "ab200_probe_fp64_fma", "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_info",
     "ab200_integrator_flow_bounds", "ab200_integrator_flow", "ab200_taylor_models_view", "ab200_taylor_models_free", "ab200_taylor_model_op", "ab200_interval_op", "ab200_analyser_discretise_constraint", "ab200_analyser_upper_reach_evolve_from", "ab200_analyser_outer_chain_reach_from",
     "ab200_reach_evolve_enclosures", "ab200_enclosures_view", "ab200_enclosures_model", "ab200_enclosures_select", "ab200_enclosures_free", "ab200_enclosures_create",
-    "ab200_analyser_epsilon_lower_chain_reach",
+    "ab200_analyser_epsilon_lower_chain_reach", "ab200_analyser_lower_reach_evolve_constraint", "ab200_analyser_epsilon_lower_chain_reach_constraint",
 ]
 
 
@@ -117,6 +117,10 @@ def load_library():
     lib.ab200_analyser_lower_reach_evolve.restype = C.c_int
     lib.ab200_analyser_epsilon_lower_chain_reach.argtypes = [vp, u64, P(i32), P(dbl), i32, C.c_char_p, P(vp), P(dbl), P(i32), P(Status)]
     lib.ab200_analyser_epsilon_lower_chain_reach.restype = C.c_int
+    lib.ab200_analyser_lower_reach_evolve_constraint.argtypes = [vp, C.c_char_p, dbl, i32, P(vp), P(vp), P(Status)]
+    lib.ab200_analyser_lower_reach_evolve_constraint.restype = C.c_int
+    lib.ab200_analyser_epsilon_lower_chain_reach_constraint.argtypes = [vp, C.c_char_p, i32, C.c_char_p, P(vp), P(dbl), P(i32), P(Status)]
+    lib.ab200_analyser_epsilon_lower_chain_reach_constraint.restype = C.c_int
     lib.ab200_reach_evolve_enclosures.argtypes = [vp, u64, P(i32), P(dbl), vp, dbl, i32, C.c_int, C.c_int, i32, P(vp), P(vp), P(vp), P(Status)]
     lib.ab200_reach_evolve_enclosures.restype = C.c_int
     lib.ab200_enclosures_view.argtypes = [vp, P(u64), P(P(i32)), P(P(u64)), P(u64)]; lib.ab200_enclosures_view.restype = C.c_int
@@ -541,6 +545,15 @@ class HybridReachabilityAnalyser(object):
         self.evolver._check(rc)
         return self._wrap(r), self._wrap(e)
 
+    def lower_reach_evolve_constraint(self, constraint_text, time, max_events=5):
+        """lower_reach_evolve from a constraint-set initial set (the text discretise_constraint takes)."""
+        r = C.c_void_p(); e = C.c_void_p(); st = Status()
+        rc = self.lib.ab200_analyser_lower_reach_evolve_constraint(self.handle, constraint_text.encode(), float(time), int(max_events),
+                                                                   C.byref(r), C.byref(e), C.byref(st))
+        self.last_status = st
+        self.evolver._check(rc)
+        return self._wrap(r), self._wrap(e)
+
     def lower_reach(self, initial_set, time, max_events=5):
         return self.lower_reach_evolve(initial_set, time, max_events)[0]
 
@@ -550,12 +563,16 @@ class HybridReachabilityAnalyser(object):
     def epsilon_lower_chain_reach(self, initial_set, prune=True, substituted_system_text=None):
         """HybridReachabilityAnalyser::epsilon_lower_chain_reach (src/reachability_analyser.cpp:497-627) without a constraint
         set: returns (reach CellSet, epsilon [n_locations, dim], laps)."""
-        locs, boxes = self._initial(initial_set)
         r = C.c_void_p(); st = Status(); laps = C.c_int32(0)
         eps = np.zeros((self.evolver.n_locations, MAX_DIM), dtype=np.float64)
         sub = substituted_system_text.encode() if substituted_system_text is not None else None
-        rc = self.lib.ab200_analyser_epsilon_lower_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), int(bool(prune)), sub,
-                                                               C.byref(r), _dptr(eps), C.byref(laps), C.byref(st))
+        if isinstance(initial_set, str):              # a constraint-set initial set (the text discretise_constraint takes)
+            rc = self.lib.ab200_analyser_epsilon_lower_chain_reach_constraint(self.handle, initial_set.encode(), int(bool(prune)), sub,
+                                                                              C.byref(r), _dptr(eps), C.byref(laps), C.byref(st))
+        else:
+            locs, boxes = self._initial(initial_set)
+            rc = self.lib.ab200_analyser_epsilon_lower_chain_reach(self.handle, locs.shape[0], _iptr(locs), _dptr(boxes), int(bool(prune)), sub,
+                                                                   C.byref(r), _dptr(eps), C.byref(laps), C.byref(st))
         self.last_status = st
         self.evolver._check(rc)
         return self._wrap(r), eps, laps.value

@@ -538,14 +538,12 @@ struct ConstraintEval {
     }
 };
 }
-extern "C" int ab200_analyser_discretise_constraint(ab200_analyser* an, const char* text, ab200_cellset** out) {
-    if (!an || !text || !out) return AB200_E_ARGUMENT;
-    *out = 0;
+// the discretised initial set of a constraint-set text (shared by ab200_analyser_discretise_constraint and the lower analyses)
+static int discretise_constraint_sets(ab200_analyser* an, const char* text, HostConstraints& H, HybridCells& initial) {
     const HostSystem* hs = ab200_ctx_system(an->ctx);
-    HostConstraints H;
     std::string err = parse_constraints(text, *hs, H);
     if (!err.empty()) { ab200_ctx_set_error(an->ctx, ("constraint set: " + err).c_str()); return AB200_E_ARGUMENT; }
-    HybridCells initial = empty_cells(an);
+    initial = empty_cells(an);
     bool ok = true; int st = ST_OK;
     for (size_t k = 0; k < H.sets.size(); ++k) {
         const ConstraintSetDesc& S = H.sets[k];
@@ -559,14 +557,59 @@ extern "C" int ab200_analyser_discretise_constraint(ab200_analyser* an, const ch
         ok = s.adjoin_outer_approximation(dom) && ok;                       // _insert_domain_discretisation
         if (S.m > 0) {                                                      // !unconstrained()
             ConstraintEval E; E.H = &H; E.S = &S; E.n = n;
-            s.outer_restrict([&](const double* box) { return E.check(box, &st); });
+            s.outer_restrict([&](const double* box) { return E.check(box, &st); }, true);     // (down to the BDD's own depth)
         }
         initial[l].adjoin(s);
     }
     if (st != ST_OK) { ab200_ctx_set_error(an->ctx, "constraint function cannot be evaluated on a cell"); return st; }
     ok = apply_restriction(an, initial) && ok;
     if (!ok) { ab200_ctx_set_error(an->ctx, "initial set or domain lies outside the packed-key window"); return AB200_E_KEYSPACE; }
+    return AB200_OK;
+}
+extern "C" int ab200_analyser_discretise_constraint(ab200_analyser* an, const char* text, ab200_cellset** out) {
+    if (!an || !text || !out) return AB200_E_ARGUMENT;
+    *out = 0;
+    HostConstraints H; HybridCells initial;
+    int rc = discretise_constraint_sets(an, text, H, initial);
+    if (rc != AB200_OK) return rc;
     *out = to_cellset(initial);
+    return AB200_OK;
+}
+// _enclosures_from_discretised_initial_set_midpoints (src/reachability_analyser.cpp:1218-1243) for constraint-set initial sets:
+// the centre of (cell ^ domain of the set) is kept when the set is unconstrained or definitely covers it
+// (BoundedConstraintSet::covers, src/function_set.cpp:327-333: the domain covers the point strictly and f(point) lies strictly
+// inside the codomain)
+static int constraint_midpoint_enclosures(ab200_analyser* an, const HostConstraints& H, const HybridCells& initial,
+                                          std::vector<int32_t>& elocs, std::vector<double>& eboxes) {
+    const HostSystem* hs = ab200_ctx_system(an->ctx);
+    int st = ST_OK;
+    for (int l = 0; l < an->n_locs; ++l) {
+        const ConstraintSetDesc* S = 0;
+        for (size_t k = 0; k < H.sets.size(); ++k) if (H.sets[k].loc == l) { S = &H.sets[k]; break; }
+        if (!S) continue;
+        const int n = hs->desc.loc[l].n;
+        std::vector<CellBox> cells; initial[l].enumerate(cells);
+        ConstraintEval E; E.H = &H; E.S = S; E.n = n;
+        for (size_t k = 0; k < cells.size(); ++k) {
+            double mb[AB200_BOX_STRIDE] = {0}; Ivl d[AB_MAXN];
+            bool inside = true;
+            for (int i = 0; i < n; ++i) {
+                const double lo = std::max(cells[k].b[2 * i], S->domain[2 * i]), hi = std::min(cells[k].b[2 * i + 1], S->domain[2 * i + 1]);
+                const double mid = (lo + hi) / 2;
+                mb[2 * i] = mid; mb[2 * i + 1] = mid; d[i] = ivl(mid);
+                if (!(S->domain[2 * i] < mid && S->domain[2 * i + 1] > mid)) inside = false;      // Ariadne::covers(domain,bx) is strict
+            }
+            if (S->m > 0) {
+                if (!inside) continue;
+                Ivl fd[AB_MAXN]; E.image(d, fd, &st);
+                bool covers = true;
+                for (int i = 0; i < S->m; ++i) if (!(fd[i].l > S->codomain[2 * i] && fd[i].u < S->codomain[2 * i + 1])) covers = false;
+                if (!covers) continue;
+            }
+            elocs.push_back(l); eboxes.insert(eboxes.end(), mb, mb + AB200_BOX_STRIDE);
+        }
+    }
+    if (st != ST_OK) { ab200_ctx_set_error(an->ctx, "constraint function cannot be evaluated on a midpoint"); return st; }
     return AB200_OK;
 }
 
@@ -650,6 +693,8 @@ static void midpoint_enclosures(ab200_analyser* an, uint64_t n_init, const int32
 // get_epsilon (:1255-1275) and restricted (the evolve set is not). The evolution runs on the device; the per-orbit
 // discretisation and the domain check are host work on the returned enclosure boxes -- this is not the hot path.
 extern "C" int ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s);
+static int lower_reach_evolve_units(ab200_analyser* an, const std::vector<int32_t>& elocs, const std::vector<double>& eboxes, double T, int32_t max_events,
+                                    ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status);
 extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes,
                                                  double T, int32_t max_events,
                                                  ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
@@ -659,9 +704,28 @@ extern "C" int ab200_analyser_lower_reach_evolve(ab200_analyser* an, uint64_t n_
     HybridCells initial;
     int rc = discretise_initial(an, n_init, loc, boxes, initial);
     if (rc != AB200_OK) return rc;
-    const int dim = an->dim;
     std::vector<int32_t> elocs; std::vector<double> eboxes;
     midpoint_enclosures(an, n_init, loc, boxes, initial, elocs, eboxes);
+    return lower_reach_evolve_units(an, elocs, eboxes, T, max_events, reach_out, evolve_out, status);
+}
+// The same from a constraint-set initial set (text of ab200_analyser_discretise_constraint).
+extern "C" int ab200_analyser_lower_reach_evolve_constraint(ab200_analyser* an, const char* constraint_text, double T, int32_t max_events,
+                                                            ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    if (!an || !constraint_text || !reach_out || !evolve_out) return AB200_E_ARGUMENT;
+    *reach_out = 0; *evolve_out = 0;
+    an->cells_evolved = 0;
+    HostConstraints H; HybridCells initial;
+    int rc = discretise_constraint_sets(an, constraint_text, H, initial);
+    if (rc != AB200_OK) return rc;
+    std::vector<int32_t> elocs; std::vector<double> eboxes;
+    rc = constraint_midpoint_enclosures(an, H, initial, elocs, eboxes);
+    if (rc != AB200_OK) return rc;
+    return lower_reach_evolve_units(an, elocs, eboxes, T, max_events, reach_out, evolve_out, status);
+}
+static int lower_reach_evolve_units(ab200_analyser* an, const std::vector<int32_t>& elocs, const std::vector<double>& eboxes, double T, int32_t max_events,
+                                    ab200_cellset** reach_out, ab200_cellset** evolve_out, ab200_status* status) {
+    const int dim = an->dim;
+    int rc;
     an->cells_evolved = (int64_t)elocs.size();
     { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
     ab200_settings saved, low;
@@ -736,10 +800,25 @@ struct SubstitutedSystem {      // _system->substitute_all(midpoints) ... substi
     SubstitutedSystem() : ctx(0), active(false) { }
     ~SubstitutedSystem() { if (active) ab200_ctx_swap_system(ctx, &other); }
 };
+static int epsilon_lower_chain_reach_impl(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, const char* constraint_text,
+                                         int32_t prune, const char* substituted_system_text,
+                                         ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status);
 extern "C" int ab200_analyser_epsilon_lower_chain_reach(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, int32_t prune,
                                                         const char* substituted_system_text,
                                                         ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status) {
     if (!an || !reach_out || (n_init && (!loc || !boxes))) return AB200_E_ARGUMENT;
+    return epsilon_lower_chain_reach_impl(an, n_init, loc, boxes, 0, prune, substituted_system_text, reach_out, epsilon_out, laps_out, status);
+}
+// The same from a constraint-set initial set (text of ab200_analyser_discretise_constraint).
+extern "C" int ab200_analyser_epsilon_lower_chain_reach_constraint(ab200_analyser* an, const char* constraint_text, int32_t prune,
+                                                                   const char* substituted_system_text,
+                                                                   ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status) {
+    if (!an || !reach_out || !constraint_text) return AB200_E_ARGUMENT;
+    return epsilon_lower_chain_reach_impl(an, 0, 0, 0, constraint_text, prune, substituted_system_text, reach_out, epsilon_out, laps_out, status);
+}
+static int epsilon_lower_chain_reach_impl(ab200_analyser* an, uint64_t n_init, const int32_t* loc, const double* boxes, const char* constraint_text,
+                                         int32_t prune, const char* substituted_system_text,
+                                         ab200_cellset** reach_out, double* epsilon_out, int32_t* laps_out, ab200_status* status) {
     *reach_out = 0;
     an->cells_evolved = 0;
     SubstitutedSystem sub;
@@ -753,13 +832,21 @@ extern "C" int ab200_analyser_epsilon_lower_chain_reach(ab200_analyser* an, uint
         if (src != AB200_OK) return src;
         sub.active = true;
     }
-    HybridCells initial;
-    int rc = discretise_initial(an, n_init, loc, boxes, initial);
-    if (rc != AB200_OK) return rc;
+    int rc;
     const int dim = an->dim, L = an->n_locs;
     const double divider = (double)(1 << an->accuracy);
     std::vector<int32_t> elocs; std::vector<double> eboxes;
-    midpoint_enclosures(an, n_init, loc, boxes, initial, elocs, eboxes);
+    if (constraint_text) {
+        HostConstraints H; HybridCells initial;
+        rc = discretise_constraint_sets(an, constraint_text, H, initial);
+        if (rc == AB200_OK) rc = constraint_midpoint_enclosures(an, H, initial, elocs, eboxes);
+        if (rc != AB200_OK) return rc;
+    } else {
+        HybridCells initial;
+        rc = discretise_initial(an, n_init, loc, boxes, initial);
+        if (rc != AB200_OK) return rc;
+        midpoint_enclosures(an, n_init, loc, boxes, initial, elocs, eboxes);
+    }
     // _restriction->filter(initial_enclosures) (src/reachability_restriction.cpp:186-228): an enclosure whose box the
     // (undiscretised) outer domain covers is kept; otherwise it is kept if its outer approximation meets the domain cells
     {

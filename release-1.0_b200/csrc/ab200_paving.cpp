@@ -147,22 +147,22 @@ namespace {
 struct PathKey { Path p; uint64_t key; bool operator<(const PathKey& o) const { return p < o.p; } };
 }
 static void restrict_rec(const std::vector<PathKey>& P, size_t lo, size_t hi, int level, int depth, int split, int dim,
-                         const CellBox& box, const CellSet::BoxTest& check, std::vector<uint64_t>& out) {
+                         const CellBox& box, const CellSet::BoxTest& check, std::vector<uint64_t>& out, int stop = -1) {
     if (hi == lo) return;                                   // enabled_cells == bddfalse
     int prop = check(box.b);
     if (prop == 0) return;
-    if (prop == 1 || level == depth) { for (size_t k = lo; k < hi; ++k) out.push_back(P[k].key); return; }
+    if (prop == 1 || level == (stop >= 0 ? stop : depth)) { for (size_t k = lo; k < hi; ++k) out.push_back(P[k].key); return; }
     int shift = depth - 1 - level;
     size_t a = lo, b = hi;
     while (a < b) { size_t m = (a + b) / 2; if ((P[m].p >> shift) & 1) b = m; else a = m + 1; }
     double c = (box.b[2 * split] + box.b[2 * split + 1]) / 2.0;          // Box::split -> midpoint (src/vector.cpp:246-253)
     CellBox left = box, right = box;
     left.b[2 * split + 1] = c; right.b[2 * split] = c;
-    restrict_rec(P, lo, a, level + 1, depth, (split + 1) % dim, dim, left, check, out);
-    restrict_rec(P, a, hi, level + 1, depth, (split + 1) % dim, dim, right, check, out);
+    restrict_rec(P, lo, a, level + 1, depth, (split + 1) % dim, dim, left, check, out, stop);
+    restrict_rec(P, a, hi, level + 1, depth, (split + 1) % dim, dim, right, check, out, stop);
 }
 
-void CellSet::outer_restrict(const BoxTest& check) {
+void CellSet::outer_restrict(const BoxTest& check, bool to_bdd_depth) {
     if (keys.empty()) return;
     const int dim = grid.dim;
     Root root = minimal_root();
@@ -182,7 +182,22 @@ void CellSet::outer_restrict(const BoxTest& check) {
     CellBox rb;
     for (int i = 0; i < dim; ++i) { rb.b[2 * i] = rc[i].l; rb.b[2 * i + 1] = rc[i].u; }
     std::vector<uint64_t> out;
-    restrict_rec(P, 0, P.size(), 0, root.height + dim * K.acc, splitting_coordinate(root.height, dim), dim, rb, check, out);
+    const int full = root.height + dim * K.acc;
+    int stop = -1;
+    if (to_bdd_depth) {
+        // the last variable in the support of the BDD: the deepest path bit the set is not invariant under
+        stop = root.height;                                   // (depth() is never negative: at least down to the unit cells)
+        for (int sh = 0; sh < full - root.height; ++sh) {
+            bool invariant = true;
+            for (size_t k = 0; k < P.size() && invariant; ++k) {
+                PathKey q; q.p = P[k].p ^ ((Path)1 << sh); q.key = 0;
+                std::vector<PathKey>::const_iterator it = std::lower_bound(P.begin(), P.end(), q);
+                if (it == P.end() || it->p != q.p) invariant = false;
+            }
+            if (!invariant) { stop = full - sh; break; }
+        }
+    }
+    restrict_rec(P, 0, P.size(), 0, full, splitting_coordinate(root.height, dim), dim, rb, check, out, stop);
     std::sort(out.begin(), out.end());
     keys.swap(out);
 }

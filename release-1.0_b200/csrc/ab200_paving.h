@@ -52,7 +52,10 @@ class CellSet {
     // outer_restrict(SetCheckerInterface,accuracy) (src/bdd_set.cpp:1706-1721 -> _approximate_restrict :640-690, AS_OUTER):
     // descend from the minimal root; a subtree is dropped where the check is false, kept whole where it is true,
     // and kept at the leaves where it stays indeterminate.
-    void outer_restrict(const BoxTest& check);
+    // to_bdd_depth: descend only as deep as the set's own BDD goes -- BDDTreeSet::outer_restrict(OpenSetInterface)
+    // (src/bdd_set.cpp:1670-1686) stops at BDDTreeSet::depth() (:1171-1190), the last variable its BDD depends on, which is
+    // above the accuracy when the finest levels of the set are merged (a box whose faces pair up sibling cells).
+    void outer_restrict(const BoxTest& check, bool to_bdd_depth = false);
     // The same descent level by level: all boxes of one level are tested in one call (a device batch), then the undecided
     // ones are split. The test is pure, so the result is the depth-first one.
     typedef std::function<void(const std::vector<CellBox>&, std::vector<int>&)> BatchTest;

@@ -80,6 +80,10 @@ $H boost cells acc=6 chain=0 T=0.011 disc=2 out=$D/bo6.txt && python $G/fingerpr
 $H vanderpol reach acc=4 cons=disc init=0.9,1.5,1.0,1.6 laps=1 out=$G/vanderpol_cons_disc_acc4.txt
 $H vanderpol reach acc=6 cons=band init=0.5,2.0,0.5,2.0 T=0.02 out=$G/vanderpol_cons_band_acc6.txt
 $H bouncingball reach acc=5 cons=disc init=-0.5,0.5,1.5,2.0 cc=0.0,1.8 cr=0.2 out=$G/bouncingball_cons_disc_chain_acc5.txt
+# a constraint set over the default (large) initial box: the finest levels of the box's paving are merged, so
+# BDDTreeSet::outer_restrict stops above the accuracy (BDDTreeSet::depth()); lower analyses start from the midpoints the set covers
+ORACLE_THREADS=1 $H vanderpol reach lower=1 cons=disc acc=4 T=1.5 out=$G/vanderpol_cons_disc_lower_reach_acc4.txt
+ORACLE_THREADS=1 $H vanderpol epslower cons=disc acc=4 prune=1 out=$G/vanderpol_cons_disc_epslower_acc4.txt
 # exp / log / sin / cos on the tapes: a pendulum with transcendental terms (not a BASELINE config), three cells, T=1
 $H pendulum system out=$G/pendulum.sys
 $H pendulum cells acc=4 T=1.0 ncells=12 stride=1 out=$G/pendulum_cells_acc4.txt

@@ -136,6 +136,30 @@ def test_epsilon_lower_chain_reach_identical_cells_and_epsilon(pkg, system, name
         an.close()
 
 
+def test_lower_analyses_from_a_constraint_set(pkg):
+    """lower_reach_evolve and epsilon_lower_chain_reach from a HybridBoundedConstraintSet: the midpoints of the initial cells
+    that the set definitely covers (src/reachability_analyser.cpp:1218-1243). The set lies in the default (large) initial box,
+    whose paving has its finest levels merged, so BDDTreeSet::outer_restrict stops above the accuracy (BDDTreeSet::depth(),
+    src/bdd_set.cpp:1171-1190): the initial cells are coarser than the grid's and only 5 of 12 midpoints are covered."""
+    d = golden_io.load_dump("vanderpol_cons_disc_lower_reach_acc4.txt")
+    an = pkg.HybridReachabilityAnalyser(_system("vanderpol"), [-3.0, 3.0, -3.0, 3.0], 4, settings={"arena_words": 262144, "max_boxes": 512})
+    try:
+        text = "".join(d["cons_text"])
+        il, ib = an.enumerate(an.discretise_constraint(text))
+        assert golden_io.boxes_equal_bits(ib, d["sets"]["initial"]["loc"])
+        reach, evolve = an.lower_reach_evolve_constraint(text, d["config"]["T"], d["config"]["events"])
+        assert an.cells_evolved() == 5
+        assert golden_io.boxes_equal_bits(an.enumerate(reach)[1], d["sets"]["reach"]["loc"])
+        assert golden_io.boxes_equal_bits(an.enumerate(evolve)[1], d["sets"]["evolve"]["loc"])
+        e = golden_io.load_dump("vanderpol_cons_disc_epslower_acc4.txt")
+        reach, eps, laps = an.epsilon_lower_chain_reach("".join(e["cons_text"]), prune=True)
+        assert laps == 3
+        assert golden_io.boxes_equal_bits(an.enumerate(reach)[1], e["sets"]["reach"]["loc"])
+        assert golden_io.boxes_equal_bits(eps[0][:2], e["epsilon"]["loc"])
+    finally:
+        an.close()
+
+
 @pytest.mark.parametrize("system,name,tuning,half", [("vanderpol", "vanderpol_cells_acc4_backward.txt", None, 0.25),
                                                      ("springs", "springs_cells_acc10.txt.gz", "springs_reach_acc2.txt.gz", 0.125)])
 def test_final_enclosures_restart_the_evolution(pkg, system, name, tuning, half):

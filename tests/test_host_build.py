@@ -93,6 +93,24 @@ def test_host_build_wide_keys_epsilon_lower_chain_reach(hostchain_wide):
     assert "cell sets identical (bit-exact boxes)" in out and "differs" not in out and "laps 3" in out, out[-2000:]
 
 
+# constraint-set initial sets: the golden carries the set's text (cons| lines); the tool discretises it
+# (ab200_analyser_discretise_constraint) and runs the analysis from the cells / from the midpoints the set covers
+CONS_CASES = [
+    ("vanderpol", "vanderpol_cons_band_acc6.txt", ["upper", "acc=6", "T=0.02", "domain=-3,3,-3,3"]),
+    ("bouncingball", "bouncingball_cons_disc_chain_acc5.txt", ["chain", "acc=5", "domain=-10.1,10.1,-0.1,2.1"]),
+    ("vanderpol", "vanderpol_cons_disc_lower_reach_acc4.txt", ["lower", "acc=4", "T=1.5", "domain=-3,3,-3,3"]),
+    ("vanderpol", "vanderpol_cons_disc_epslower_acc4.txt", ["epslower", "acc=4", "prune=1", "domain=-3,3,-3,3"]),
+]
+
+
+@pytest.mark.parametrize("system,golden,args", CONS_CASES)
+def test_host_build_constraint_set_initial_sets(hostchain, system, golden, args):
+    g = os.path.join(ROOT, "tests", "golden")
+    out = subprocess.run([hostchain, os.path.join(g, system + ".sys"), os.path.join(g, golden)] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600).stdout.decode()
+    assert "cell sets identical (bit-exact boxes)" in out and "differs" not in out, out[-2000:]
+
+
 WIDE_CASES = [
     ("springs", "springs_reach_acc3.txt.gz", ["upper", "acc=3", "T=40", "domain=0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0",
                                               "init=0,0,0,0,0,0,0,0,3,3"]),

@@ -253,14 +253,26 @@ int main(int argc, char** argv) {
     printf("lock %a\n", an->lock_time);
     ab200_cellset *reach = 0, *evolve = 0; ab200_status st; memset(&st, 0, sizeof(st));
     std::vector<double> eps((size_t)L * AB200_MAX_DIM, 0.0); int laps = 0;
+    // a golden taken with a constraint-set initial set carries the set's text in its "cons| " lines (lower / epslower use it)
+    std::string cons_text;
+    { std::ifstream cf(argv[2]); std::string cl; while (std::getline(cf, cl)) if (!cl.compare(0, 6, "cons| ")) cons_text += cl.substr(6) + "\n"; }
     if (epslower) {
         // the pruning draw restates glibc's rand(): check it against the C library of this machine first
         { GlibcRand g; for (int i = 0; i < 100000; ++i) if (g.next() != rand()) { printf("GlibcRand differs from rand() at draw %d\n", i); return 1; } }
         std::string subtext;
         if (subsys) { std::ifstream f2(subsys); std::stringstream s2; s2 << f2.rdbuf(); subtext = s2.str(); }
-        rc = ab200_analyser_epsilon_lower_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), prune, subsys ? subtext.c_str() : 0, &reach, eps.data(), &laps, &st);
+        if (!cons_text.empty()) rc = ab200_analyser_epsilon_lower_chain_reach_constraint(an, cons_text.c_str(), prune, subsys ? subtext.c_str() : 0, &reach, eps.data(), &laps, &st);
+        else rc = ab200_analyser_epsilon_lower_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), prune, subsys ? subtext.c_str() : 0, &reach, eps.data(), &laps, &st);
     }
+    else if (lower && !cons_text.empty()) rc = ab200_analyser_lower_reach_evolve_constraint(an, cons_text.c_str(), T, events, &reach, &evolve, &st);
     else if (lower) rc = ab200_analyser_lower_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, &reach, &evolve, &st);
+    else if (!cons_text.empty()) {
+        // upper_reach_evolve / outer_chain_reach from the constraint-set initial set of the golden
+        ab200_cellset* ini = 0;
+        rc = ab200_analyser_discretise_constraint(an, cons_text.c_str(), &ini);
+        if (!rc) rc = (chain || bchain) ? ab200_analyser_outer_chain_reach_from(an, ini, bchain ? 1 : 0, &reach, &st)
+                                        : ab200_analyser_upper_reach_evolve_from(an, ini, T, events, mince, &reach, &evolve, &st);
+    }
     else if (chain || bchain) rc = ab200_analyser_outer_chain_reach(an, inits.size(), init_locs.data(), init_box.data(), bchain ? 1 : 0, &reach, &st);
     else rc = ab200_analyser_upper_reach_evolve(an, inits.size(), init_locs.data(), init_box.data(), T, events, mince, &reach, &evolve, &st);
     if (rc) { printf("rc=%d %s\ncells evolved %ld steps %ld arena peak %d\n", rc, ctx.err.c_str(), g_cells, g_steps, g_peak); return 1; }
