@@ -18,6 +18,7 @@ import golden_io  # noqa: E402
 pkg = load_pkg()
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 300.0
 out_path = sys.argv[2] if len(sys.argv) > 2 else None
+only = os.environ.get("SWEEP_ONLY")          # comma-separated golden basenames: run just these
 
 
 def system(name):
@@ -47,7 +48,7 @@ def compare(an, d, got, which):
     return None
 
 
-def run(case):
+def run(case, arena_words=262144):
     k = case["kind"]; a = kv(case["args"]); acc = int(a["acc"])
     d = golden_io.load_dump(os.path.join(ROOT, case["golden"]))
     if k.startswith("vdp"):
@@ -60,7 +61,7 @@ def run(case):
         sysname, domain = "watertank", [0.0, 1.0, 4.5, 9.0]
         init = {"flow,idle,rising": boxof(a["initr"]), "flow,idle,falling": boxof(a["initf"])}
     cons = "".join(d.get("cons_text", []))
-    an = pkg.HybridReachabilityAnalyser(system(sysname), domain, acc, settings={"arena_words": 262144, "max_boxes": 1024})
+    an = pkg.HybridReachabilityAnalyser(system(sysname), domain, acc, settings={"arena_words": arena_words, "max_boxes": 1024})
     try:
         try:
             if k in ("vdp_upper", "wt_upper"):
@@ -86,16 +87,24 @@ def run(case):
             else:
                 return "unknown kind"
         except pkg.Ab200Error as ex:
+            if "ArenaExhausted" in str(ex) and arena_words < 2097152:
+                # a device limit, reported as an error (coarse grids give large sets): once more with eight times the scratch
+                an.close(); an = None
+                case["arena_retry"] = arena_words * 8
+                return run(case, arena_words * 8)
             return None if case["referr"] else "library error: %s" % ex
         if case["referr"]:
             return "the reference rejected this run, the library did not"
         return err
     finally:
-        an.close()
+        if an is not None:
+            an.close()
 
 
 cases = json.load(open(os.path.join(ROOT, "build", "sweep", "manifest.json")))
 # cheapest first within each kind, kinds interleaved, so that a short budget still covers every analysis
+if only:
+    cases = [c for c in cases if os.path.basename(c["golden"]) in only.split(",")]
 cases.sort(key=lambda c: c["ref_seconds"])
 t0 = time.time(); done = 0; bad = []; per_kind = {}
 for c in cases:
@@ -106,7 +115,7 @@ for c in cases:
     per_kind[c["kind"]] = per_kind.get(c["kind"], 0) + 1
     if e:
         bad.append({"case": c, "error": e}); print("MISMATCH", c["kind"], c["args"], e, flush=True)
-summary = {"cases_run": done, "cases_total": len(cases), "mismatches": len(bad), "per_kind": per_kind, "seconds": time.time() - t0,
+summary = {"cases_run": done, "cases_total": len(cases), "mismatches": len(bad), "per_kind": per_kind, "arena_retries": [os.path.basename(c["golden"]) for c in cases[:done] if c.get("arena_retry")], "seconds": time.time() - t0,
            "reference_seconds_of_the_cases_run": sum(c["ref_seconds"] for c in cases[:done]), "bad": bad}
 print(json.dumps(summary), flush=True)
 if out_path:
