@@ -301,6 +301,12 @@ class Evolver(object):
             raise KeyError(name)
         return i
 
+    def get_settings(self):
+        """The context's current settings (the analyser may have raised arena_words, see ab200_analyser.cu: with_arena_growth)."""
+        s = Settings()
+        self._check(self.lib.ab200_ctx_get_settings(self.handle, C.byref(s)))
+        return s
+
     def set_settings(self, **kw):
         for k, v in kw.items():
             setattr(self.settings, k, v)

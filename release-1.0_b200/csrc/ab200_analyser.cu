@@ -215,6 +215,23 @@ static int tune_evolver(ab200_analyser* an) {
 }
 
 // to_enclosures (src/reachability_analyser.cpp:1244-1253) + UpperReachEvolveWorker::get_result.
+// The reference has no scratch limit (its TaylorModels live on the heap). The analyser therefore answers AB200_E_ARENA by raising
+// the context's arena_words eightfold (up to AB_ARENA_GROW_MAX words per cell) and running the lap again; the raised value
+// stays for the laps that follow. The evolver-level entry points keep the strict error (ab200_settings.arena_words is theirs).
+#define AB_ARENA_GROW_MAX (4 * 1024 * 1024)
+extern "C" int ab200_ctx_get_settings(const ab200_ctx* ctx, ab200_settings* s);
+template<class F> static int with_arena_growth(ab200_analyser* an, F call) {
+    int rc = call();
+    while (rc == AB200_E_ARENA) {
+        ab200_settings s; ab200_ctx_get_settings(an->ctx, &s);
+        if (s.arena_words >= AB_ARENA_GROW_MAX) break;
+        s.arena_words = s.arena_words * 8 < AB_ARENA_GROW_MAX ? s.arena_words * 8 : AB_ARENA_GROW_MAX;
+        if (ab200_set_settings(an->ctx, &s) != AB200_OK) break;
+        rc = call();
+    }
+    return rc;
+}
+
 static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, double T, int events, int ignore_activations, int direction,
                HybridCells& reach, HybridCells& evolve, ab200_status* st_acc) {
     std::vector<int32_t> locs; std::vector<double> boxes;
@@ -230,7 +247,7 @@ static int lap(ab200_analyser* an, const HybridCells& frontier, int mince, doubl
     an->cells_evolved += (int64_t)locs.size();
     { int trc = tune_evolver(an); if (trc != AB200_OK) return trc; }
     ab200_cellset *r = 0, *e = 0; ab200_status st; memset(&st, 0, sizeof(st));
-    int rc = ab200_upper_reach_evolve(an->ctx, locs.size(), locs.data(), boxes.data(), T, events, ignore_activations, direction, &r, &e, &st);
+    int rc = with_arena_growth(an, [&]() { return ab200_upper_reach_evolve(an->ctx, locs.size(), locs.data(), boxes.data(), T, events, ignore_activations, direction, &r, &e, &st); });
     if (st_acc) {
         st_acc->steps += st.steps; st_acc->launches += st.launches; st_acc->keys_emitted += st.keys_emitted; st_acc->evolve_ms += st.evolve_ms; st_acc->raster_ms += st.raster_ms;
         st_acc->arena_peak = std::max(st_acc->arena_peak, st.arena_peak);
@@ -734,7 +751,8 @@ static int lower_reach_evolve_units(ab200_analyser* an, const std::vector<int32_
     rc = ab200_set_settings(an->ctx, &low);
     if (rc != AB200_OK) return rc;
     ab200_boxlist *rb = 0, *fb = 0; ab200_status st; memset(&st, 0, sizeof(st));
-    rc = ab200_reach_evolve_boxes(an->ctx, elocs.size(), elocs.data(), eboxes.data(), T, max_events, 0, 0, &rb, &fb, &st);
+    rc = with_arena_growth(an, [&]() { return ab200_reach_evolve_boxes(an->ctx, elocs.size(), elocs.data(), eboxes.data(), T, max_events, 0, 0, &rb, &fb, &st); });
+    { ab200_settings now; ab200_ctx_get_settings(an->ctx, &now); saved.arena_words = now.arena_words; }     // (keep a raised scratch limit)
     ab200_set_settings(an->ctx, &saved);
     if (status) *status = st;
     if (rc != AB200_OK) return rc;
@@ -888,7 +906,8 @@ static int epsilon_lower_chain_reach_impl(ab200_analyser* an, uint64_t n_init, c
         an->cells_evolved += (int64_t)n_current;
         ab200_boxlist *rb = 0, *fb = 0; ab200_enclosures* fe = 0; ab200_status st; memset(&st, 0, sizeof(st));
         rc = ab200_set_settings(an->ctx, &low);
-        if (rc == AB200_OK) rc = ab200_reach_evolve_enclosures(an->ctx, elocs.size(), elocs.data(), eboxes.data(), current, an->lock_time, 1 /* lock_to_grid_steps */, 0, 0, 0, &rb, &fb, &fe, &st);
+        if (rc == AB200_OK) rc = with_arena_growth(an, [&]() { return ab200_reach_evolve_enclosures(an->ctx, elocs.size(), elocs.data(), eboxes.data(), current, an->lock_time, 1 /* lock_to_grid_steps */, 0, 0, 0, &rb, &fb, &fe, &st); });
+        { ab200_settings now; ab200_ctx_get_settings(an->ctx, &now); saved.arena_words = now.arena_words; low.arena_words = now.arena_words; }   // (keep a raised scratch limit)
         ab200_set_settings(an->ctx, &saved);
         total.steps += st.steps; total.launches += st.launches; total.evolve_ms += st.evolve_ms; total.libm_sensitive += st.libm_sensitive; total.alg_flops += st.alg_flops;
         if (st.arena_peak > total.arena_peak) total.arena_peak = st.arena_peak;

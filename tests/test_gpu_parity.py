@@ -136,6 +136,21 @@ def test_epsilon_lower_chain_reach_identical_cells_and_epsilon(pkg, system, name
         an.close()
 
 
+def test_analyser_raises_the_scratch_limit_instead_of_failing(pkg):
+    """The reference has no per-cell scratch limit. An analyser lap that ends with AB200_E_ARENA is run again with eight
+    times the arena (with_arena_growth, ab200_analyser.cu) and gives the golden's cells; the evolver-level entry points keep
+    the strict error (test_error_paths)."""
+    d = golden_io.load_dump("vanderpol_reach_acc4.txt")
+    an = pkg.HybridReachabilityAnalyser(_system("vanderpol"), [-3.0, 3.0, -3.0, 3.0], 4, settings={"arena_words": 1024, "max_boxes": 512})
+    try:
+        reach, evolve = an.upper_reach_evolve({"loc": [-1.6, -1.3, 0.3, 0.8]}, d["config"]["T"], d["config"]["events"])
+        assert golden_io.boxes_equal_bits(an.enumerate(reach)[1], d["sets"]["reach"]["loc"])
+        assert golden_io.boxes_equal_bits(an.enumerate(evolve)[1], d["sets"]["evolve"]["loc"])
+        assert an.evolver.get_settings().arena_words >= 8192
+    finally:
+        an.close()
+
+
 def test_lower_analyses_from_a_constraint_set(pkg):
     """lower_reach_evolve and epsilon_lower_chain_reach from a HybridBoundedConstraintSet: the midpoints of the initial cells
     that the set definitely covers (src/reachability_analyser.cpp:1218-1243). The set lies in the default (large) initial box,
