@@ -57,6 +57,9 @@ def run(case, arena_words=262144):
     elif k.startswith("bb"):
         sysname, domain = "bouncingball", [-10.1, 10.1, -0.1, 2.1]
         init = {"freefall": boxof(a["init"])}
+    elif k.startswith("sp"):
+        sysname, domain = "springs", [0.0, 40.0, -2.0, 2.0, -3.0, 3.0, -1.0, 3.0, 0.0, 4.0]
+        init = {"free1,free2": boxof(a["init"])}
     else:
         sysname, domain = "watertank", [0.0, 1.0, 4.5, 9.0]
         init = {"flow,idle,rising": boxof(a["initr"]), "flow,idle,falling": boxof(a["initf"])}
@@ -64,13 +67,15 @@ def run(case, arena_words=262144):
     an = pkg.HybridReachabilityAnalyser(system(sysname), domain, acc, settings={"arena_words": arena_words, "max_boxes": 1024})
     try:
         try:
-            if k in ("vdp_upper", "wt_upper"):
+            if "lock" in a:
+                an.set_lock_to_grid_time(float(a["lock"]))
+            if k in ("vdp_upper", "wt_upper", "sp_upper"):
                 r, e = an.upper_reach_evolve(init, float(a["T"]), 5)
                 err = compare(an, d, r, "reach") or compare(an, d, e, "evolve")
             elif k == "vdp_cons_upper":
                 r, e = an.upper_reach_evolve_from(an.discretise_constraint(cons), float(a["T"]), 5)
                 err = compare(an, d, r, "reach") or compare(an, d, e, "evolve")
-            elif k in ("vdp_lower", "bb_lower"):
+            elif k in ("vdp_lower", "bb_lower", "wt_lower"):
                 r, e = an.lower_reach_evolve(init, float(a["T"]), 5)
                 err = compare(an, d, r, "reach") or compare(an, d, e, "evolve")
             elif k == "vdp_cons_lower":
@@ -78,8 +83,9 @@ def run(case, arena_words=262144):
                 err = compare(an, d, r, "reach") or compare(an, d, e, "evolve")
             elif k == "bb_chain":
                 err = compare(an, d, an.outer_chain_reach(init), "reach")
-            elif k in ("vdp_eps", "bb_eps", "vdp_cons_eps"):
-                r, eps, laps = an.epsilon_lower_chain_reach(cons if k == "vdp_cons_eps" else init, prune=bool(int(a.get("prune", "1"))))
+            elif k in ("vdp_eps", "bb_eps", "vdp_cons_eps", "wt_eps", "sp_eps"):
+                r, eps, laps = an.epsilon_lower_chain_reach(cons if k == "vdp_cons_eps" else init, prune=bool(int(a.get("prune", "1"))),
+                                                            substituted_system_text=system("watertank_midparams") if k == "wt_eps" else None)
                 err = compare(an, d, r, "reach")
                 for lname, ref in d.get("epsilon", {}).items():
                     if not err and not golden_io.boxes_equal_bits(eps[an.evolver.location(lname)][:len(ref)], ref):
@@ -101,7 +107,7 @@ def run(case, arena_words=262144):
             an.close()
 
 
-cases = json.load(open(os.path.join(ROOT, "build", "sweep", "manifest.json")))
+cases = json.load(open(os.path.join(ROOT, "build", "sweep", os.environ.get("SWEEP_MANIFEST", "manifest.json"))))
 # cheapest first within each kind, kinds interleaved, so that a short budget still covers every analysis
 if only:
     cases = [c for c in cases if os.path.basename(c["golden"]) in only.split(",")]

@@ -17,6 +17,8 @@ def box(lo,hi,wmax):
 while time.time()<t_end:
     kinds=['vdp_upper','vdp_lower','bb_chain','bb_lower','vdp_eps','bb_eps','wt_upper']
     if os.environ.get('SWEEP_CONS'): kinds=['vdp_cons_upper','vdp_cons_lower','vdp_cons_eps']      # constraint-set initial sets (disc)
+    if os.environ.get('SWEEP_WT'): kinds=['wt_lower','wt_eps','wt_upper']          # watertank: transitions, sqrt dynamics, interval parameter
+    if os.environ.get('SWEEP_SPRINGS'): kinds=['sp_upper','sp_eps']              # five variables: two-word keys (build/hostchain2_eps, -DAB_KW=2)
     kind=random.choice(kinds)
     out='/tmp/fz/g%s_%d.txt'%(sys.argv[1],n)
     if kind.startswith('vdp_cons'):
@@ -41,6 +43,17 @@ while time.time()<t_end:
         if kind=='bb_chain': ra=['bouncingball','reach','acc=%d'%acc,'init='+init]; ha=['chain','acc=%d'%acc]
         elif kind=='bb_lower': T=random.choice([0.5,1.5]); ra=['bouncingball','reach','chain=0','lower=1','acc=%d'%acc,'init='+init,'T=%r'%T]; ha=['lower','acc=%d'%acc,'T=%r'%T]
         else: pr=random.choice([0,1]); ra=['bouncingball','epslower','acc=%d'%acc,'init='+init,'prune=%d'%pr]; ha=['epslower','acc=%d'%acc,'prune=%d'%pr]
+    elif kind.startswith('sp_'):
+        acc=2; sysf='springs'; dom='0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0'
+        a=box(-0.3,0.3,0.1); b=box(-0.3,0.3,0.1); c=box(0.0,0.8,0.1); e=box(2.5,3.5,0.1)
+        init='0,0,%r,%r,%r,%r,%r,%r,%r,%r'%(a[0],a[1],b[0],b[1],c[0],c[1],e[0],e[1])
+        if kind=='sp_upper': T=random.choice([0.5,1.0,1.5]); ra=['springs','reach','acc=2','T=%r'%T,'init='+init]; ha=['upper','acc=2','T=%r'%T]
+        else: L=random.choice([0.5,1.0]); pr=random.choice([0,1]); ra=['springs','epslower','acc=2','prune=%d'%pr,'lock=%r'%L,'init='+init]; ha=['epslower','acc=2','prune=%d'%pr,'lock=%r'%L]
+    elif kind in ('wt_lower','wt_eps'):
+        acc=random.choice([2,3]); x=box(5.5,8.0,0.3); sysf='watertank'; dom='0.0,1.0,4.5,9.0'; init=None
+        ini=['initr=1.0,1.0,%r,%r'%x,'initf=0.0,0.0,%r,%r'%x]; hini=['loc=2','init=1.0,1.0,%r,%r'%x,'loc=1','init=0.0,0.0,%r,%r'%x]
+        if kind=='wt_lower': T=random.choice([0.5,2.0,6.0]); ra=['watertank','reach','lower=1','acc=%d'%acc,'T=%r'%T]+ini; ha=['lower','acc=%d'%acc,'T=%r'%T]+hini
+        else: pr=random.choice([0,1,1]); ra=['watertank','epslower','acc=%d'%acc,'prune=%d'%pr]+ini; ha=['epslower','acc=%d'%acc,'prune=%d'%pr,'subsys='+R+'/tests/golden/watertank_midparams.sys']+hini
     else:
         acc=random.choice([2,3]); T=random.choice([0.5,1.0]); x=box(5.5,8.0,0.3)
         ra=['watertank','reach','acc=%d'%acc,'T=%r'%T,'initr=1.0,1.0,%r,%r'%x,'initf=0.0,0.0,%r,%r'%x]; sysf='watertank'
@@ -51,7 +64,7 @@ while time.time()<t_end:
         print('ref skip',kind,ra[2:],type(e).__name__,flush=True); continue
     txt=open(out).read()
     referr = "err ''" not in txt
-    args=[HC,R+'/tests/golden/%s.sys'%sysf,out]+ha+['domain='+dom]+(['init='+init] if init else [])
+    args=[(HC.replace('hostchain_eps','hostchain2_eps') if sysf=='springs' else HC),R+'/tests/golden/%s.sys'%sysf,out]+ha+['domain='+dom]+(['init='+init] if init else [])
     try:
         o=subprocess.run(args,timeout=240,stdout=subprocess.PIPE,stderr=subprocess.STDOUT).stdout.decode()
     except subprocess.TimeoutExpired:
