@@ -57,6 +57,8 @@ ORACLE_THREADS=1 $H watertank epslower acc=3 prune=0 out=$G/watertank_epslower_a
 ORACLE_THREADS=1 $H watertank epslower acc=3 prune=1 out=$G/watertank_epslower_acc3_prune.txt
 # five variables (two-word MultiIndex keys in the enclosure records); lock time 1 keeps the reference run short
 ORACLE_THREADS=1 $H springs epslower acc=2 prune=1 lock=1.0 out=$G/springs_epslower_acc2_lock1.txt
+# the reference's own failure: the lower reach of the boost converter leaves the widened domain in the first lap
+ORACLE_THREADS=1 $H boost epslower acc=3 prune=1 out=$G/boost_epslower_acc3_domain_error.txt
 # the system the laps evolve: interval parameters at their midpoints (getMidpointsSet, :1000-1014)
 $H watertank system midparams=1 out=$G/watertank_midparams.sys
 # IntegratorInterface::flow_bounds / TaylorIntegrator::flow (src/integrator.cpp:44-152): the vector field of

@@ -136,6 +136,20 @@ def test_epsilon_lower_chain_reach_identical_cells_and_epsilon(pkg, system, name
         an.close()
 
 
+def test_epsilon_lower_chain_reach_domain_error_as_the_reference(pkg):
+    """The boost converter's lower reach leaves the widened domain in the first lap: the reference throws
+    (src/reachability_analyser.cpp:596-599, golden boost_epslower_acc3_domain_error.txt), the library returns AB200_E_DOMAIN."""
+    g = open(os.path.join(golden_io.GOLDEN, "boost_epslower_acc3_domain_error.txt")).read()
+    assert "The lower reach is not inside the over-approximated domain" in g
+    an = pkg.HybridReachabilityAnalyser(_system("boost"), [0.0, 0.001, 0.0, 3.0, 0.0, 6.0], 3, settings={"arena_words": 262144, "max_boxes": 512})
+    try:
+        with pytest.raises(pkg.Ab200Error) as ei:
+            an.epsilon_lower_chain_reach({"incr,below_duty": [0.0, 0.0, 1.0, 1.0, 1.0, 1.0]}, prune=True)
+        assert ei.value.code == pkg.AB200_E_DOMAIN and "lower reach is not inside" in str(ei.value)
+    finally:
+        an.close()
+
+
 def test_analyser_raises_the_scratch_limit_instead_of_failing(pkg):
     """The reference has no per-cell scratch limit. An analyser lap that ends with AB200_E_ARENA is run again with eight
     times the arena (with_arena_growth, ab200_analyser.cu) and gives the golden's cells; the evolver-level entry points keep

@@ -111,6 +111,17 @@ def test_host_build_constraint_set_initial_sets(hostchain, system, golden, args)
     assert "cell sets identical (bit-exact boxes)" in out and "differs" not in out, out[-2000:]
 
 
+def test_host_build_reproduces_the_reference_domain_error(hostchain_wide):
+    """epsilon_lower_chain_reach of the boost converter: the reference throws "The lower reach is not inside the over-approximated
+    domain" (src/reachability_analyser.cpp:596-599; the golden holds its message); the mirror returns AB200_E_DOMAIN with it."""
+    g = os.path.join(ROOT, "tests", "golden")
+    assert "The lower reach is not inside the over-approximated domain" in open(os.path.join(g, "boost_epslower_acc3_domain_error.txt")).read()
+    args = ["epslower", "acc=3", "prune=1", "domain=0.0,0.001,0.0,3.0,0.0,6.0", "loc=1", "init=0.0,0.0,1.0,1.0,1.0,1.0"]
+    out = subprocess.run([hostchain_wide, os.path.join(g, "boost.sys"), os.path.join(g, "boost_epslower_acc3_domain_error.txt")] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600).stdout.decode()
+    assert "rc=3 The lower reach is not inside the over-approximated domain" in out, out[-2000:]
+
+
 WIDE_CASES = [
     ("springs", "springs_reach_acc3.txt.gz", ["upper", "acc=3", "T=40", "domain=0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0",
                                               "init=0,0,0,0,0,0,0,0,3,3"]),
