@@ -51,7 +51,13 @@ def compare(an, d, got, which):
 def run(case, arena_words=262144):
     k = case["kind"]; a = kv(case["args"]); acc = int(a["acc"])
     d = golden_io.load_dump(os.path.join(ROOT, case["golden"]))
-    if k.startswith("vdp"):
+    if k == "pend_upper":
+        sysname, domain = "pendulum", [-3.0, 3.0, -3.0, 3.0]
+        init = {"loc": boxof(a["init"])}
+    elif k == "boost_upper":
+        sysname, domain = "boost", [0.0, 0.001, 0.0, 3.0, 0.0, 6.0]
+        init = {"incr,below_duty": boxof(a["init"])}
+    elif k.startswith("vdp"):
         sysname, domain = "vanderpol", [-3.0, 3.0, -3.0, 3.0]
         init = {"loc": boxof(a["init"])} if "init" in a else None
     elif k.startswith("bb"):
@@ -64,12 +70,12 @@ def run(case, arena_words=262144):
         sysname, domain = "watertank", [0.0, 1.0, 4.5, 9.0]
         init = {"flow,idle,rising": boxof(a["initr"]), "flow,idle,falling": boxof(a["initf"])}
     cons = "".join(d.get("cons_text", []))
-    an = pkg.HybridReachabilityAnalyser(system(sysname), domain, acc, settings={"arena_words": arena_words, "max_boxes": 1024})
+    an = pkg.HybridReachabilityAnalyser(system(sysname), domain, acc, settings={"arena_words": max(arena_words, 1048576) if k == "pend_upper" else arena_words, "max_boxes": 1024})
     try:
         try:
             if "lock" in a:
                 an.set_lock_to_grid_time(float(a["lock"]))
-            if k in ("vdp_upper", "wt_upper", "sp_upper"):
+            if k in ("vdp_upper", "wt_upper", "sp_upper", "pend_upper", "boost_upper"):
                 r, e = an.upper_reach_evolve(init, float(a["T"]), 5)
                 err = compare(an, d, r, "reach") or compare(an, d, e, "evolve")
             elif k == "vdp_cons_upper":
@@ -83,6 +89,8 @@ def run(case, arena_words=262144):
                 err = compare(an, d, r, "reach") or compare(an, d, e, "evolve")
             elif k == "bb_chain":
                 err = compare(an, d, an.outer_chain_reach(init), "reach")
+            elif k in ("bb_bchain", "vdp_bupper"):
+                err = compare(an, d, an.outer_chain_reach(init, backward=True), "reach")
             elif k in ("vdp_eps", "bb_eps", "vdp_cons_eps", "wt_eps", "sp_eps"):
                 r, eps, laps = an.epsilon_lower_chain_reach(cons if k == "vdp_cons_eps" else init, prune=bool(int(a.get("prune", "1"))),
                                                             substituted_system_text=system("watertank_midparams") if k == "wt_eps" else None)
