@@ -19,10 +19,26 @@ while time.time()<t_end:
     if os.environ.get('SWEEP_CONS'): kinds=['vdp_cons_upper','vdp_cons_lower','vdp_cons_eps']      # constraint-set initial sets (disc)
     if os.environ.get('SWEEP_WT'): kinds=['wt_lower','wt_eps','wt_upper']          # watertank: transitions, sqrt dynamics, interval parameter
     if os.environ.get('SWEEP_SPRINGS'): kinds=['sp_upper','sp_eps']              # five variables: two-word keys (build/hostchain2_eps, -DAB_KW=2)
-    if os.environ.get('SWEEP_MISC'): kinds=['bb_bchain','pend_upper','boost_upper','vdp_bupper']   # backward analyses, sin / cos dynamics, three variables
+    if os.environ.get('SWEEP_MISC'): kinds=['bb_bchain','pend_upper','boost_upper']   # backward chain reach, sin dynamics, three variables (van der Pol backward chains take the reference minutes)
     kind=random.choice(kinds)
     out='/tmp/fz/g%s_%d.txt'%(sys.argv[1],n)
-    if kind.startswith('vdp_cons'):
+    if kind=='bb_bchain':
+        acc=random.choice([3,4,5]); v=box(-3.0,4.0,0.5); x=box(0.0,1.5,0.3)
+        init='%r,%r,%r,%r'%(v[0],v[1],x[0],x[1]); dom='-10.1,10.1,-0.1,2.1'; sysf='bouncingball'
+        ra=['bouncingball','reach','acc=%d'%acc,'backward=1','init='+init]; ha=['bchain','acc=%d'%acc]
+    elif kind=='pend_upper':
+        acc=random.choice([3,4]); x=box(-2.0,2.0,0.3); y=box(-1.5,1.5,0.3); T=random.choice([0.5,1.0])
+        init='%r,%r,%r,%r'%(x[0],x[1],y[0],y[1]); dom='-3,3,-3,3'; sysf='pendulum'
+        ra=['pendulum','reach','acc=%d'%acc,'T=%r'%T,'init='+init]; ha=['upper','acc=%d'%acc,'T=%r'%T]
+    elif kind=='boost_upper':
+        acc=random.choice([3,4]); a=box(0.5,2.0,0.1); b=box(0.5,3.0,0.1); T=random.choice([0.003,0.011])
+        init='0.0,0.0,%r,%r,%r,%r'%(a[0],a[1],b[0],b[1]); dom='0.0,0.001,0.0,3.0,0.0,6.0'; sysf='boost'
+        ra=['boost','reach','acc=%d'%acc,'chain=0','T=%r'%T,'init='+init]; ha=['upper','acc=%d'%acc,'T=%r'%T,'loc=1']
+    elif kind=='vdp_bupper':
+        acc=random.choice([3,4]); x=box(-2.0,2.0,0.3); y=box(-2.5,2.5,0.3); dom='-3,3,-3,3'; sysf='vanderpol'
+        init='%r,%r,%r,%r'%(x[0],x[1],y[0],y[1])
+        ra=['vanderpol','reach','chain=1','backward=1','acc=%d'%acc,'init='+init]; ha=['bchain','acc=%d'%acc]
+    elif kind.startswith('vdp_cons'):
         acc=random.choice([3,4,5]); cx=random.uniform(-1.5,1.5); cy=random.uniform(cx,2.0); cr=random.uniform(0.05,0.4)
         big=random.choice([0,1]); w=cr*random.uniform(0.8,1.6)
         init=None if big else '%r,%r,%r,%r'%(cx-w,cx+w,cy-w,cy+w)
@@ -44,22 +60,6 @@ while time.time()<t_end:
         if kind=='bb_chain': ra=['bouncingball','reach','acc=%d'%acc,'init='+init]; ha=['chain','acc=%d'%acc]
         elif kind=='bb_lower': T=random.choice([0.5,1.5]); ra=['bouncingball','reach','chain=0','lower=1','acc=%d'%acc,'init='+init,'T=%r'%T]; ha=['lower','acc=%d'%acc,'T=%r'%T]
         else: pr=random.choice([0,1]); ra=['bouncingball','epslower','acc=%d'%acc,'init='+init,'prune=%d'%pr]; ha=['epslower','acc=%d'%acc,'prune=%d'%pr]
-    elif kind=='bb_bchain':
-        acc=random.choice([3,4,5]); v=box(-3.0,4.0,0.5); x=box(0.0,1.5,0.3)
-        init='%r,%r,%r,%r'%(v[0],v[1],x[0],x[1]); dom='-10.1,10.1,-0.1,2.1'; sysf='bouncingball'
-        ra=['bouncingball','reach','acc=%d'%acc,'backward=1','init='+init]; ha=['bchain','acc=%d'%acc]
-    elif kind=='pend_upper':
-        acc=random.choice([3,4]); x=box(-2.0,2.0,0.3); y=box(-1.5,1.5,0.3); T=random.choice([0.5,1.0])
-        init='%r,%r,%r,%r'%(x[0],x[1],y[0],y[1]); dom='-3,3,-3,3'; sysf='pendulum'
-        ra=['pendulum','reach','acc=%d'%acc,'T=%r'%T,'init='+init]; ha=['upper','acc=%d'%acc,'T=%r'%T]
-    elif kind=='boost_upper':
-        acc=random.choice([3,4]); a=box(0.5,2.0,0.1); b=box(0.5,3.0,0.1); T=random.choice([0.003,0.011])
-        init='0.0,0.0,%r,%r,%r,%r'%(a[0],a[1],b[0],b[1]); dom='0.0,0.001,0.0,3.0,0.0,6.0'; sysf='boost'
-        ra=['boost','reach','acc=%d'%acc,'chain=0','T=%r'%T,'init='+init]; ha=['upper','acc=%d'%acc,'T=%r'%T,'loc=1']
-    elif kind=='vdp_bupper':
-        acc=random.choice([3,4]); x=box(-2.0,2.0,0.3); y=box(-2.5,2.5,0.3); dom='-3,3,-3,3'; sysf='vanderpol'
-        init='%r,%r,%r,%r'%(x[0],x[1],y[0],y[1])
-        ra=['vanderpol','reach','chain=1','backward=1','acc=%d'%acc,'init='+init]; ha=['bchain','acc=%d'%acc]
     elif kind.startswith('sp_'):
         acc=2; sysf='springs'; dom='0.0,40.0,-2.0,2.0,-3.0,3.0,-1.0,3.0,0.0,4.0'
         a=box(-0.3,0.3,0.1); b=box(-0.3,0.3,0.1); c=box(0.0,0.8,0.1); e=box(2.5,3.5,0.1)
