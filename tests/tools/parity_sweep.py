@@ -49,13 +49,13 @@ while time.time()<t_end:
         else: pr=random.choice([0,1]); ra=['vanderpol','epslower','acc=%d'%acc,'prune=%d'%pr]+cons; ha=['epslower','acc=%d'%acc,'prune=%d'%pr]
         init=None
     elif kind.startswith('vdp'):
-        acc=random.choice([2,3,4]); x=box(-2.0,2.0,0.4); y=box(-2.5,2.5,0.4)
+        acc=random.choice([5,6] if os.environ.get('SWEEP_DEEP') else [2,3,4]); x=box(-2.0,2.0,0.05 if os.environ.get('SWEEP_DEEP') else 0.4); y=box(-2.5,2.5,0.05 if os.environ.get('SWEEP_DEEP') else 0.4)
         init='%r,%r,%r,%r'%(x[0],x[1],y[0],y[1]); dom='-3,3,-3,3'; sysf='vanderpol'
         if kind=='vdp_upper': T=random.choice([0.7,2.0,3.1]); ra=['vanderpol','reach','acc=%d'%acc,'init='+init,'T=%r'%T]; ha=['upper','acc=%d'%acc,'T=%r'%T]
         elif kind=='vdp_lower': T=random.choice([0.7,1.5]); ra=['vanderpol','reach','lower=1','acc=%d'%acc,'init='+init,'T=%r'%T]; ha=['lower','acc=%d'%acc,'T=%r'%T]
         else: pr=random.choice([0,1]); ra=['vanderpol','epslower','acc=%d'%acc,'init='+init,'prune=%d'%pr]; ha=['epslower','acc=%d'%acc,'prune=%d'%pr]
     elif kind.startswith('bb'):
-        acc=random.choice([3,4,5]); v=box(-3.0,3.0,0.5); x=box(0.0,2.0,0.5)
+        acc=random.choice([6,7] if os.environ.get('SWEEP_DEEP') else [3,4,5]); v=box(-3.0,3.0,0.1 if os.environ.get('SWEEP_DEEP') else 0.5); x=box(0.0,2.0,0.1 if os.environ.get('SWEEP_DEEP') else 0.5)
         init='%r,%r,%r,%r'%(v[0],v[1],x[0],x[1]); dom='-10.1,10.1,-0.1,2.1'; sysf='bouncingball'
         if kind=='bb_chain': ra=['bouncingball','reach','acc=%d'%acc,'init='+init]; ha=['chain','acc=%d'%acc]
         elif kind=='bb_lower': T=random.choice([0.5,1.5]); ra=['bouncingball','reach','chain=0','lower=1','acc=%d'%acc,'init='+init,'T=%r'%T]; ha=['lower','acc=%d'%acc,'T=%r'%T]
