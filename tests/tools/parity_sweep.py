@@ -44,6 +44,9 @@ while time.time()<t_end:
         init=None if big else '%r,%r,%r,%r'%(cx-w,cx+w,cy-w,cy+w)
         dom='-3,3,-3,3'; sysf='vanderpol'
         cons=['cons=disc','cc=%r,%r'%(cx,cy),'cr=%r'%cr]+([] if big else ['init='+init])
+        if os.environ.get('SWEEP_CONS')=='band':      # two functions (x0+x1, x0*x1) in a random codomain box
+            sm=cx+cy; pm=cx*cy; ws=random.uniform(0.05,0.5); wp=random.uniform(0.05,0.5)
+            cons=['cons=band','cb=%r,%r,%r,%r'%(sm-ws,sm+ws,pm-wp,pm+wp)]+([] if big else ['init='+init])
         if kind=='vdp_cons_upper': T=random.choice([0.3,0.7]); ra=['vanderpol','reach','acc=%d'%acc,'T=%r'%T]+cons; ha=['upper','acc=%d'%acc,'T=%r'%T]
         elif kind=='vdp_cons_lower': T=random.choice([0.7,1.5]); ra=['vanderpol','reach','lower=1','acc=%d'%acc,'T=%r'%T]+cons; ha=['lower','acc=%d'%acc,'T=%r'%T]
         else: pr=random.choice([0,1]); ra=['vanderpol','epslower','acc=%d'%acc,'prune=%d'%pr]+cons; ha=['epslower','acc=%d'%acc,'prune=%d'%pr]
