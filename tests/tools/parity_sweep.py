@@ -70,7 +70,7 @@ while time.time()<t_end:
         if kind=='sp_upper': T=random.choice([0.5,1.0,1.5]); ra=['springs','reach','acc=2','T=%r'%T,'init='+init]; ha=['upper','acc=2','T=%r'%T]
         else: L=random.choice([0.5,1.0]); pr=random.choice([0,1]); ra=['springs','epslower','acc=2','prune=%d'%pr,'lock=%r'%L,'init='+init]; ha=['epslower','acc=2','prune=%d'%pr,'lock=%r'%L]
     elif kind in ('wt_lower','wt_eps'):
-        acc=random.choice([2,3]); x=box(5.5,8.0,0.3); sysf='watertank'; dom='0.0,1.0,4.5,9.0'; init=None
+        acc=random.choice([4] if os.environ.get('SWEEP_DEEP') else [2,3]); x=box(5.5,8.0,0.05 if os.environ.get('SWEEP_DEEP') else 0.3); sysf='watertank'; dom='0.0,1.0,4.5,9.0'; init=None
         ini=['initr=1.0,1.0,%r,%r'%x,'initf=0.0,0.0,%r,%r'%x]; hini=['loc=2','init=1.0,1.0,%r,%r'%x,'loc=1','init=0.0,0.0,%r,%r'%x]
         if kind=='wt_lower': T=random.choice([0.5,2.0,6.0]); ra=['watertank','reach','lower=1','acc=%d'%acc,'T=%r'%T]+ini; ha=['lower','acc=%d'%acc,'T=%r'%T]+hini
         else: pr=random.choice([0,1,1]); ra=['watertank','epslower','acc=%d'%acc,'prune=%d'%pr]+ini; ha=['epslower','acc=%d'%acc,'prune=%d'%pr,'subsys='+R+'/tests/golden/watertank_midparams.sys']+hini
